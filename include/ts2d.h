@@ -1,0 +1,178 @@
+/*
+ * ts2d.h -- C ABI of the B200-native 2D triangle-splatting rasterizer (libts2d.so).
+ *
+ * This is the drop-in boundary for the hot path BASELINE.json:north_star names.  It replaces the
+ * reference's host orchestration + kernels behind its pybind module
+ *     R2D = submodules/diff-triangle-rasterization-2D
+ *     R2D/ext.cpp:4-9                        rasterize_triangles / rasterize_triangles_backward
+ *     R2D/src/extension_interface.cu:19-260  (tensor checks, output allocation)
+ *     R2D/src/rasterizer.cu:101-358          Rasterizer::forward / Rasterizer::backward
+ *     R2D/src/param_struct.h:127-194         CameraInfo / GeometryInfo / ForwardOutput / BackwardInput / LossInput / BackwardOutput
+ * with plain pointers and sizes: no torch (or any C++) types cross this boundary.  Every pointer
+ * is a DEVICE pointer unless the name ends in _host.  All arrays are fp32 / int32 / uint8, dense,
+ * in the layouts of the reference's tensors (extension_interface.cu:99-128, 229-233).
+ *
+ * Memory is caller-owned.  The three opaque "state" blobs mirror the reference's geometryBuffer /
+ * binningBuffer / imageBuffer tensors (param_struct.h:44-123): the caller asks for their sizes,
+ * allocates them (the Python host side uses torch uint8 tensors so that autograd keeps them alive
+ * exactly like the reference, __init__.py:100), and passes them to forward and again to backward.
+ * Their internal layout is private to this library (ts2d_export_* decode them for parity tests).
+ *
+ * Forward is split in two calls because the size of the binning state depends on the number of
+ * (triangle, tile) instances R (`num_rendered`), which is only known after the per-triangle
+ * preprocess -- the reference resizes its binningBuffer tensor at the same point
+ * (rasterizer.cu:189-195):
+ *     ts2d_forward_geometry()  -> K1 preprocess + SH colour, depth sort, scan; returns R on the host
+ *     ts2d_forward_render()    -> key emission, tile binning, tile ranges, front-to-back composite
+ * Backward is one call:
+ *     ts2d_backward()          -> reverse-walk composite gradients + preprocess/SH backward
+ *
+ * Error convention: every entry point returns 0 on success; a negative TS2D_E_* code for argument
+ * errors (the cases where the reference raises via AT_ERROR, extension_interface.cu:53-81); or a
+ * positive cudaError_t.  ts2d_error_string() explains either.  When `debug` is non-zero every
+ * launch is followed by a stream synchronisation + error check (reference: CHECK_CUDA,
+ * auxiliary.h:358-367).  All work is enqueued on `stream` (a cudaStream_t passed as void*); the
+ * only host synchronisation is the one inside ts2d_forward_geometry() that returns R.
+ *
+ * Multi-GPU (image-space tile sharding, no counterpart in the reference): `shard_rank`/`shard_world`
+ * restrict key emission and compositing to the tiles with tile_id % shard_world == shard_rank.
+ * shard_world == 1 is the single-GPU path.  Collectives live above this ABI (torch.distributed/NCCL).
+ */
+#ifndef TS2D_H_
+#define TS2D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TS2D_ABI_VERSION 1
+#define TS2D_TILE 16          /* R2D/src/config.h:4-5  BLOCK_X = BLOCK_Y = 16 */
+#define TS2D_MAX_CHANNELS 3   /* R2D/src/config.h:3 */
+
+enum {
+    TS2D_OK = 0,
+    TS2D_E_BAD_VERTEX = -1,    /* extension_interface.cu:53-56 */
+    TS2D_E_BAD_FEATURE = -2,   /* :57-60 */
+    TS2D_E_BAD_SHS = -3,       /* :61-64 */
+    TS2D_E_CHANNELS = -4,      /* :65-68  C > MAX_CHANNELS */
+    TS2D_E_BACKGROUND = -5,    /* :69-72 */
+    TS2D_E_GAMMA = -6,         /* :73-76 */
+    TS2D_E_NULL = -7,          /* required pointer missing */
+    TS2D_E_STATE_SIZE = -8,    /* state blob smaller than ts2d_*_state_bytes() */
+    TS2D_E_SH_DEGREE = -9,     /* (sh_degree+1)^2 > M or sh_degree > 3 */
+    TS2D_E_SHARD = -10,        /* shard_rank/shard_world invalid */
+    TS2D_E_SIZE = -11          /* image or primitive count out of range */
+};
+
+/* R2D/src/param_struct.h:127-137 (CameraInfo).  Matrices are the 16 floats of the (contiguous)
+ * torch tensors the reference receives: element [i] = row i/4, col i%4 of world_view_transform /
+ * full_proj_transform, i.e. column-major w.r.t. the mathematical W2C matrix (auxiliary.h:40-58). */
+typedef struct ts2d_camera {
+    int32_t width, height;
+    float tan_fovx, tan_fovy;
+    const float *viewmatrix;   /* [16] */
+    const float *projmatrix;   /* [16] */
+    const float *campos;       /* [3]  */
+} ts2d_camera;
+
+/* R2D/src/param_struct.h:139-155 (GeometryInfo) + the three flags of Rasterizer::forward. */
+typedef struct ts2d_geometry {
+    int32_t P;                 /* triangles */
+    int32_t sh_degree;         /* D: active SH degree 0..3 */
+    int32_t M;                 /* stored SH coefficients per triangle (shs is [P][M][3]) */
+    int32_t C;                 /* channels: 3 in SH mode, feature.size(1) otherwise (<= 3) */
+    int32_t use_shs;           /* 1: colour from SH (shs), 0: `feature` [P][C] given */
+    float gamma;               /* compactness exponent: power = -0.5 * ecc^(2*gamma) */
+    float scale_modifier;      /* carried for API parity; unused by the reference kernels too */
+    float background_depth;
+    const float *background;   /* [C] */
+    const float *vertex;       /* [P][3][3] */
+    const float *shs;          /* [P][M][3] or NULL */
+    const float *feature;      /* [P][C]   or NULL */
+    const float *opacity;      /* [P] (post-activation) */
+} ts2d_geometry;
+
+typedef struct ts2d_flags {
+    int32_t back_culling;
+    int32_t rich_info;
+    int32_t debug;
+    int32_t shard_rank;        /* tile ownership for multi-GPU; 0 */
+    int32_t shard_world;       /* 1 = all tiles */
+    int32_t exact;             /* 1: per-pair arithmetic mirrors the reference op-for-op (IEEE div, powf,
+                                  expf); 0: fast path with exact re-evaluation inside the decision bands */
+} ts2d_flags;
+
+/* R2D/src/param_struct.h:157-169 (ForwardOutput), minus the three state tensors. */
+typedef struct ts2d_forward_out {
+    float *out_feature;        /* [C][H][W] planar */
+    int32_t *radii;            /* [P] */
+    float *depth;              /* [H][W]      (rich_info) */
+    float *normal;             /* [3][H][W]   (rich_info) */
+    float *contrib_sum;        /* [P]         (rich_info) */
+    float *contrib_max;        /* [P]         (rich_info) */
+} ts2d_forward_out;
+
+/* R2D/src/param_struct.h:180-185 (LossInput). dL_dout_depth / dL_dout_normal may be NULL when
+ * rich_info == 0 (the reference's Python backward would raise there, __init__.py:114-117,141-142). */
+typedef struct ts2d_loss_in {
+    const float *dL_dout_feature;  /* [C][H][W] */
+    const float *dL_dout_depth;    /* [H][W] */
+    const float *dL_dout_normal;   /* [3][H][W] */
+} ts2d_loss_in;
+
+/* R2D/src/param_struct.h:187-194 (BackwardOutput).  Every element is written (no pre-zeroing
+ * needed; the reference relies on torch::zeros, extension_interface.cu:229-233). */
+typedef struct ts2d_backward_out {
+    float *dL_dvertex;     /* [P][3][3] */
+    float *dL_dcenter2D;   /* [P][2] */
+    float *dL_dshs;        /* [P][M][3] (M may be 0) */
+    float *dL_dfeature;    /* [P][C]   (SH mode: dL/d rgb, like the reference's scratch use) */
+    float *dL_dopacity;    /* [P] */
+} ts2d_backward_out;
+
+int ts2d_abi_version(void);
+const char *ts2d_error_string(int code);
+
+/* Sizes of the opaque state blobs (bytes).  cf. BaseDataBuffer::requiredSize, param_struct.h:36-40. */
+size_t ts2d_geometry_state_bytes(int32_t P);
+size_t ts2d_binning_state_bytes(int64_t num_rendered, int32_t width, int32_t height);
+size_t ts2d_image_state_bytes(int32_t width, int32_t height);
+/* Scratch for backward: per-triangle screen-space gradient accumulators (the reference's dL_dv*_2D,
+ * dL_dnormal_view, dL_dv_depth temporaries, rasterizer.cu:289-300). */
+size_t ts2d_backward_scratch_bytes(int32_t P);
+
+/* Replaces rasterizer.cu:116-193: preprocess (forward.cu:61-193), then ordering + scan.
+ * Writes radii[P]; returns num_rendered through *num_rendered_host (one stream synchronisation). */
+int ts2d_forward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags,
+                          int32_t *radii, void *geometry_state, size_t geometry_state_bytes,
+                          int64_t *num_rendered_host, void *stream);
+
+/* Replaces rasterizer.cu:195-266: duplicateWithKeys, SortPairs, identifyTileRanges, FORWARD::renderCUDA. */
+int ts2d_forward_render(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags,
+                        int64_t num_rendered, const void *geometry_state, void *binning_state, size_t binning_state_bytes,
+                        void *image_state, size_t image_state_bytes, const ts2d_forward_out *out, void *stream);
+
+/* Replaces rasterizer.cu:269-358: BACKWARD::renderCUDA + BACKWARD::preprocessCUDA. */
+int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int64_t num_rendered,
+                  const int32_t *radii, const void *geometry_state, const void *binning_state, const void *image_state,
+                  const ts2d_loss_in *loss, const ts2d_backward_out *out, void *scratch, size_t scratch_bytes, void *stream);
+
+/* ---- state decoding, for parity tests against the reference's buffers ----
+ * Each writes arrays in the reference's own element types/order.  Any output pointer may be NULL. */
+int ts2d_export_geometry(const void *geometry_state, int32_t P,
+                         float *v2d /*[P][3][2]*/, float *area2 /*[P]*/, float *normal_view /*[P][3]*/, float *v_depth /*[P][3]*/,
+                         float *depth /*[P]*/, float *rgb /*[P][3]*/, uint8_t *clamped /*[P][3]*/, uint32_t *tiles_touched /*[P]*/,
+                         uint32_t *rect_min /*[P][2]*/, uint32_t *rect_max /*[P][2]*/, void *stream);
+int ts2d_export_binning(const void *geometry_state, const void *binning_state, const void *image_state, int32_t P, int64_t num_rendered,
+                        int32_t width, int32_t height, uint64_t *keys_sorted /*[R]*/, uint32_t *point_list /*[R]*/,
+                        uint32_t *ranges /*[tiles][2]*/, void *stream);
+int ts2d_export_image(const void *image_state, int32_t width, int32_t height, uint32_t *n_contrib /*[H][W]*/, float *final_T /*[H][W]*/,
+                      void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TS2D_H_ */

@@ -1,0 +1,103 @@
+"""ctypes binding of libts2d.so -- the C ABI declared in include/ts2d.h.
+
+This is the only place the Python host side touches native code.  There is NO fallback: if the
+shared library is missing and cannot be built, importing the rasterizer raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+from . import build as _build
+
+_LIB = None
+
+
+class Camera(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
+                ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p)]
+
+
+class Geometry(C.Structure):
+    _fields_ = [("P", C.c_int32), ("sh_degree", C.c_int32), ("M", C.c_int32), ("C", C.c_int32), ("use_shs", C.c_int32),
+                ("gamma", C.c_float), ("scale_modifier", C.c_float), ("background_depth", C.c_float),
+                ("background", C.c_void_p), ("vertex", C.c_void_p), ("shs", C.c_void_p), ("feature", C.c_void_p),
+                ("opacity", C.c_void_p)]
+
+
+class Flags(C.Structure):
+    _fields_ = [("back_culling", C.c_int32), ("rich_info", C.c_int32), ("debug", C.c_int32), ("shard_rank", C.c_int32),
+                ("shard_world", C.c_int32), ("exact", C.c_int32)]
+
+
+class ForwardOut(C.Structure):
+    _fields_ = [("out_feature", C.c_void_p), ("radii", C.c_void_p), ("depth", C.c_void_p), ("normal", C.c_void_p),
+                ("contrib_sum", C.c_void_p), ("contrib_max", C.c_void_p)]
+
+
+class LossIn(C.Structure):
+    _fields_ = [("dL_dout_feature", C.c_void_p), ("dL_dout_depth", C.c_void_p), ("dL_dout_normal", C.c_void_p)]
+
+
+class BackwardOut(C.Structure):
+    _fields_ = [("dL_dvertex", C.c_void_p), ("dL_dcenter2D", C.c_void_p), ("dL_dshs", C.c_void_p), ("dL_dfeature", C.c_void_p),
+                ("dL_dopacity", C.c_void_p)]
+
+
+# every symbol include/ts2d.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = {
+    "ts2d_abi_version": (C.c_int, []),
+    "ts2d_error_string": (C.c_char_p, [C.c_int]),
+    "ts2d_geometry_state_bytes": (C.c_size_t, [C.c_int32]),
+    "ts2d_binning_state_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
+    "ts2d_image_state_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "ts2d_backward_scratch_bytes": (C.c_size_t, [C.c_int32]),
+    "ts2d_forward_geometry": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.POINTER(C.c_int64), C.c_void_p]),
+    "ts2d_forward_render": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_int64, C.c_void_p, C.c_void_p,
+                                      C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(ForwardOut), C.c_void_p]),
+    "ts2d_backward": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.POINTER(LossIn), C.POINTER(BackwardOut), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ts2d_export_geometry": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 10 + [C.c_void_p]),
+    "ts2d_export_binning": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ts2d_export_image": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+
+def lib_path() -> Path:
+    return _build.LIB
+
+
+def load() -> C.CDLL:
+    """Load (building first if the sources are newer / the .so is absent and nvcc is available)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if os.environ.get("TS2D_NO_AUTOBUILD", "0") != "1":
+        try:
+            if _build.needs_build():
+                _build.build()
+        except Exception as ex:  # nvcc missing etc.: fall through to the explicit error below if no .so
+            if not path.exists():
+                raise RuntimeError(f"libts2d.so is missing and could not be built: {ex}") from ex
+    if not path.exists():
+        raise RuntimeError(f"{path} not found: run `python -m triangle_splatting_b200.build` (needs nvcc); there is no CPU fallback")
+    lib = C.CDLL(str(path))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # raises AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def error_string(code: int) -> str:
+    return load().ts2d_error_string(int(code)).decode()
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise RuntimeError(f"{what}: {error_string(code)} (ts2d code {code})")

@@ -1,0 +1,66 @@
+"""Build libts2d.so (hand-written sm_100a CUDA + C ABI) in-tree with nvcc.
+
+    python -m triangle_splatting_b200.build [--force]
+
+Output: triangle_splatting_b200/lib/libts2d.so (git-ignored; travels to the GPU box with gpurun).
+No torch / pybind dependency: the library is plain CUDA runtime + CUB headers from the toolkit.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIBDIR = PKG / "lib"
+LIB = LIBDIR / "libts2d.so"
+SOURCES = ["ts2d_api.cu", "ts2d_preprocess.cu", "ts2d_binning.cu", "ts2d_render_fwd.cu", "ts2d_render_bwd.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+# NOTE: no --use_fast_math: bit-exact tile binning needs IEEE div/sqrt and the default FMA contraction.
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + ARCH
+
+
+def nvcc() -> str:
+    return os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "ts2d.h", Path(__file__)]
+    return LIB.stat().st_mtime < max(p.stat().st_mtime for p in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    LIBDIR.mkdir(exist_ok=True)
+    objdir = LIBDIR / "obj"
+    objdir.mkdir(exist_ok=True)
+
+    def one(src: str) -> Path:
+        obj = objdir / (src + ".o")
+        cmd = [nvcc(), "-c", str(CSRC / src), "-o", str(obj)] + NVCC_FLAGS
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        (objdir / (src + ".log")).write_text(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(one, SOURCES))
+    cmd = [nvcc(), "-shared", "-o", str(LIB)] + [str(o) for o in objs] + ARCH + ["-cudart", "shared"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(p)

@@ -1,0 +1,294 @@
+// ts2d_api.cu -- extern "C" entry points of libts2d.so (declared in include/ts2d.h), argument
+// validation (R2D/src/extension_interface.cu:53-81) and carving of the opaque state blobs
+// (replaces Params::*State::fromChunk, R2D/src/param_struct.h:11-125).
+#include <stdio.h>
+
+#include "ts2d_common.cuh"
+
+namespace {
+
+struct Carver {
+    char *p;
+    size_t used;
+    explicit Carver(void *base) : p((char *)base), used(0) {}
+    template <typename T>
+    T *take(size_t count)
+    {
+        used = ts2d_align_up(used, 256);
+        T *r = p ? (T *)(p + used) : (T *)nullptr;
+        used += sizeof(T) * count;
+        return r;
+    }
+};
+
+size_t carve_geometry(void *blob, int32_t P, GeomState *gs)
+{
+    const size_t n = P > 0 ? (size_t)P : 1;
+    Carver c(blob);
+    GeomState g;
+    g.hdr = c.take<GeomHeader>(1);
+    g.rec0 = c.take<float4>(3 * n);
+    g.rec1 = c.take<float4>(2 * n);
+    g.dkey = c.take<uint32_t>(n);
+    g.dkey2 = c.take<uint32_t>(n);
+    g.ids = c.take<uint32_t>(n);
+    g.ids2 = c.take<uint32_t>(n);
+    g.tiles = c.take<uint32_t>(n);
+    g.rect = c.take<ushort4>(n);
+    g.offs = c.take<uint32_t>(n);
+    g.clamp = c.take<uint8_t>(n);
+    g.cub_temp_bytes = ts2d_depth_sort_temp_bytes(P);
+    g.cub_temp = c.take<char>(g.cub_temp_bytes);
+    if (gs) *gs = g;
+    return ts2d_align_up(c.used, 256);
+}
+
+size_t carve_binning(void *blob, int64_t R, BinState *bs)
+{
+    const size_t n = R > 0 ? (size_t)R : 1;
+    Carver c(blob);
+    BinState b;
+    b.tkey[0] = c.take<uint32_t>(n);
+    b.tkey[1] = c.take<uint32_t>(n);
+    b.tval[0] = c.take<uint32_t>(n);
+    b.tval[1] = c.take<uint32_t>(n);
+    b.cub_temp_bytes = ts2d_tile_sort_temp_bytes(R);
+    b.cub_temp = c.take<char>(b.cub_temp_bytes);
+    if (bs) *bs = b;
+    return ts2d_align_up(c.used, 256);
+}
+
+size_t carve_image(void *blob, int32_t W, int32_t H, ImageState *is)
+{
+    const size_t gx = (W + TS2D_TILE - 1) / TS2D_TILE, gy = (H + TS2D_TILE - 1) / TS2D_TILE;
+    const size_t N = (size_t)W * H;
+    Carver c(blob);
+    ImageState i;
+    i.ranges = c.take<uint2>(gx * gy);
+    i.n_contrib = c.take<uint32_t>(N);
+    i.final_T = c.take<float>(N);
+    if (is) *is = i;
+    return ts2d_align_up(c.used, 256);
+}
+
+int validate(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f)
+{
+    if (!cam || !g || !f) return TS2D_E_NULL;
+    if (cam->width <= 0 || cam->height <= 0 || g->P < 0) return TS2D_E_SIZE;
+    if ((int64_t)cam->width * cam->height > (int64_t)1 << 30) return TS2D_E_SIZE;
+    if ((cam->width + TS2D_TILE - 1) / TS2D_TILE > 65535 || (cam->height + TS2D_TILE - 1) / TS2D_TILE > 65535) return TS2D_E_SIZE;
+    if (g->C < 1 || g->C > TS2D_MAX_CHANNELS) return TS2D_E_CHANNELS;
+    if (g->gamma < 0.0f) return TS2D_E_GAMMA;
+    if (f->shard_world < 1 || f->shard_rank < 0 || f->shard_rank >= f->shard_world) return TS2D_E_SHARD;
+    if (g->P == 0) return 0;
+    if (!cam->viewmatrix || !cam->projmatrix || !cam->campos || !g->background || !g->vertex || !g->opacity) return TS2D_E_NULL;
+    if (g->use_shs) {
+        if (!g->shs) return TS2D_E_BAD_SHS;
+        if (g->C != 3) return TS2D_E_BACKGROUND;
+        if (g->sh_degree < 0 || g->sh_degree > 3 || (g->sh_degree + 1) * (g->sh_degree + 1) > g->M) return TS2D_E_SH_DEGREE;
+    } else {
+        if (!g->feature) return TS2D_E_BAD_FEATURE;
+    }
+    return 0;
+}
+
+inline int dbg_sync(const ts2d_flags *f, cudaStream_t s)
+{
+    if (!f->debug) return 0;
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaGetLastError();
+}
+
+#define TS2D_STAGE(call)                 \
+    do {                                 \
+        int _r = (call);                 \
+        if (_r) return _r;               \
+        _r = dbg_sync(flags, s);         \
+        if (_r) return _r;               \
+    } while (0)
+
+// ---- export kernels ----
+__global__ void k_export_geometry(int P, const float4 *rec0, const float4 *rec1, const uint32_t *dkey, const uint32_t *tiles,
+                                  const ushort4 *rect, const uint8_t *clamp, float *v2d, float *area2, float *normal_view, float *v_depth,
+                                  float *depth, float *rgb, uint8_t *clamped, uint32_t *tiles_touched, uint32_t *rect_min, uint32_t *rect_max)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const bool vis = dkey[i] != 0xFFFFFFFFu;
+    float4 a = make_float4(0, 0, 0, 0), b = a, c = a, q0 = a, q1 = a;
+    if (vis) {
+        a = rec0[3 * (size_t)i];
+        b = rec0[3 * (size_t)i + 1];
+        c = rec0[3 * (size_t)i + 2];
+        if (rec1) {
+            q0 = rec1[2 * (size_t)i];
+            q1 = rec1[2 * (size_t)i + 1];
+        }
+    }
+    if (v2d) { float *o = v2d + 6 * (size_t)i; o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; }
+    if (area2) area2[i] = b.z;
+    if (normal_view) { normal_view[3 * i] = q0.x; normal_view[3 * i + 1] = q0.y; normal_view[3 * i + 2] = q0.z; }
+    if (v_depth) { v_depth[3 * i] = q0.w; v_depth[3 * i + 1] = q1.x; v_depth[3 * i + 2] = q1.y; }
+    if (depth) depth[i] = c.w;
+    if (rgb) { rgb[3 * i] = c.x; rgb[3 * i + 1] = c.y; rgb[3 * i + 2] = c.z; }
+    const uint8_t m = vis ? clamp[i] : 0;
+    if (clamped) { clamped[3 * i] = m & 1; clamped[3 * i + 1] = (m >> 1) & 1; clamped[3 * i + 2] = (m >> 2) & 1; }
+    if (tiles_touched) tiles_touched[i] = tiles[i];
+    const ushort4 r = rect[i];
+    if (rect_min) { rect_min[2 * i] = r.x; rect_min[2 * i + 1] = r.y; }
+    if (rect_max) { rect_max[2 * i] = r.z; rect_max[2 * i + 1] = r.w; }
+}
+
+__global__ void k_export_keys(int64_t R, const uint32_t *tkey, const uint32_t *tval, const uint32_t *dkey, uint64_t *keys, uint32_t *list)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const uint32_t id = tval[i];
+    if (keys) keys[i] = ((uint64_t)tkey[i] << 32) | dkey[id];  // rasterizer.cu:67-69
+    if (list) list[i] = id;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ts2d_abi_version(void) { return TS2D_ABI_VERSION; }
+
+const char *ts2d_error_string(int code)
+{
+    switch (code) {
+    case TS2D_OK: return "ok";
+    case TS2D_E_BAD_VERTEX: return "vertex must have dimensions (num_points, 3, 3)";
+    case TS2D_E_BAD_FEATURE: return "feature must have dimensions (num_points, num_channels)";
+    case TS2D_E_BAD_SHS: return "shs must have dimensions (num_points, (1 + sh_degree) ** 2, 3)";
+    case TS2D_E_CHANNELS: return "feature's num_channels can't be larger than MAX_CHANNELS";
+    case TS2D_E_BACKGROUND: return "background must have the same number of channels as feature";
+    case TS2D_E_GAMMA: return "gamma must be larger than 0";
+    case TS2D_E_NULL: return "required pointer is NULL";
+    case TS2D_E_STATE_SIZE: return "state buffer smaller than ts2d_*_state_bytes()";
+    case TS2D_E_SH_DEGREE: return "sh_degree must be in 0..3 and (sh_degree + 1) ** 2 <= shs.size(1)";
+    case TS2D_E_SHARD: return "invalid shard_rank / shard_world";
+    case TS2D_E_SIZE: return "image size or primitive count out of range";
+    default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown ts2d error";
+}
+
+size_t ts2d_geometry_state_bytes(int32_t P) { return carve_geometry(nullptr, P, nullptr); }
+size_t ts2d_binning_state_bytes(int64_t R, int32_t, int32_t) { return carve_binning(nullptr, R, nullptr); }
+size_t ts2d_image_state_bytes(int32_t W, int32_t H) { return carve_image(nullptr, W, H, nullptr); }
+size_t ts2d_backward_scratch_bytes(int32_t P) { return ts2d_align_up(sizeof(float) * GACC_STRIDE * (size_t)(P > 0 ? P : 1), 256); }
+
+int ts2d_forward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int32_t *radii, void *geometry_state,
+                          size_t geometry_state_bytes, int64_t *num_rendered_host, void *stream)
+{
+    int rc = validate(cam, geom, flags);
+    if (rc) return rc;
+    if (!num_rendered_host) return TS2D_E_NULL;
+    *num_rendered_host = 0;
+    if (geom->P == 0) return 0;
+    if (!radii || !geometry_state) return TS2D_E_NULL;
+    GeomState gs;
+    if (carve_geometry(geometry_state, geom->P, &gs) > geometry_state_bytes) return TS2D_E_STATE_SIZE;
+    cudaStream_t s = (cudaStream_t)stream;
+    TS2D_STAGE(ts2d_launch_preprocess(cam, geom, flags, radii, gs, s));
+    TS2D_STAGE(ts2d_launch_order_and_scan(geom->P, gs, num_rendered_host, s));
+    return 0;
+}
+
+int ts2d_forward_render(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int64_t num_rendered,
+                        const void *geometry_state, void *binning_state, size_t binning_state_bytes, void *image_state,
+                        size_t image_state_bytes, const ts2d_forward_out *out, void *stream)
+{
+    int rc = validate(cam, geom, flags);
+    if (rc) return rc;
+    if (geom->P == 0) return 0;
+    if (!geometry_state || !binning_state || !image_state || !out || !out->out_feature) return TS2D_E_NULL;
+    if (flags->rich_info && (!out->depth || !out->normal || !out->contrib_sum || !out->contrib_max)) return TS2D_E_NULL;
+    if (num_rendered < 0 || num_rendered >= ((int64_t)1 << 31)) return TS2D_E_SIZE;
+    GeomState gs;
+    BinState bs;
+    ImageState is;
+    carve_geometry(const_cast<void *>(geometry_state), geom->P, &gs);
+    if (carve_binning(binning_state, num_rendered, &bs) > binning_state_bytes) return TS2D_E_STATE_SIZE;
+    if (carve_image(image_state, cam->width, cam->height, &is) > image_state_bytes) return TS2D_E_STATE_SIZE;
+    cudaStream_t s = (cudaStream_t)stream;
+    TS2D_STAGE(ts2d_launch_binning(cam, flags, geom->P, num_rendered, gs, bs, is, s));
+    TS2D_STAGE(ts2d_launch_render_fwd(cam, geom, flags, gs, bs.tval[1], is, out, s));
+    return 0;
+}
+
+int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int64_t num_rendered, const int32_t *radii,
+                  const void *geometry_state, const void *binning_state, const void *image_state, const ts2d_loss_in *loss,
+                  const ts2d_backward_out *out, void *scratch, size_t scratch_bytes, void *stream)
+{
+    int rc = validate(cam, geom, flags);
+    if (rc) return rc;
+    if (geom->P == 0) return 0;
+    if (!radii || !geometry_state || !binning_state || !image_state || !loss || !out || !scratch) return TS2D_E_NULL;
+    if (!loss->dL_dout_feature || !out->dL_dvertex || !out->dL_dcenter2D || !out->dL_dfeature || !out->dL_dopacity) return TS2D_E_NULL;
+    if (geom->M > 0 && !out->dL_dshs) return TS2D_E_NULL;
+    if (flags->rich_info && (!loss->dL_dout_depth || !loss->dL_dout_normal)) return TS2D_E_NULL;
+    if (scratch_bytes < ts2d_backward_scratch_bytes(geom->P)) return TS2D_E_STATE_SIZE;
+    GeomState gs;
+    BinState bs;
+    ImageState is;
+    carve_geometry(const_cast<void *>(geometry_state), geom->P, &gs);
+    carve_binning(const_cast<void *>(binning_state), num_rendered, &bs);
+    carve_image(const_cast<void *>(image_state), cam->width, cam->height, &is);
+    cudaStream_t s = (cudaStream_t)stream;
+    TS2D_STAGE(ts2d_launch_render_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
+    TS2D_STAGE(ts2d_launch_preprocess_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
+    return 0;
+}
+
+int ts2d_export_geometry(const void *geometry_state, int32_t P, float *v2d, float *area2, float *normal_view, float *v_depth, float *depth,
+                         float *rgb, uint8_t *clamped, uint32_t *tiles_touched, uint32_t *rect_min, uint32_t *rect_max, void *stream)
+{
+    if (P <= 0) return 0;
+    if (!geometry_state) return TS2D_E_NULL;
+    GeomState gs;
+    carve_geometry(const_cast<void *>(geometry_state), P, &gs);
+    k_export_geometry<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, gs.rec0, (normal_view || v_depth) ? gs.rec1 : nullptr, gs.dkey,
+                                                                        gs.tiles, gs.rect, gs.clamp, v2d, area2, normal_view, v_depth, depth,
+                                                                        rgb, clamped, tiles_touched, rect_min, rect_max);
+    return (int)cudaGetLastError();
+}
+
+int ts2d_export_binning(const void *geometry_state, const void *binning_state, const void *image_state, int32_t P, int64_t R, int32_t W,
+                        int32_t H, uint64_t *keys_sorted, uint32_t *point_list, uint32_t *ranges, void *stream)
+{
+    if (!geometry_state || !binning_state || !image_state) return TS2D_E_NULL;
+    GeomState gs;
+    BinState bs;
+    ImageState is;
+    carve_geometry(const_cast<void *>(geometry_state), P, &gs);
+    carve_binning(const_cast<void *>(binning_state), R, &bs);
+    carve_image(const_cast<void *>(image_state), W, H, &is);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (R > 0 && (keys_sorted || point_list)) {
+        k_export_keys<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, bs.tkey[1], bs.tval[1], gs.dkey, keys_sorted, point_list);
+        TS2D_CUDA_TRY(cudaGetLastError());
+    }
+    if (ranges) {
+        const size_t gx = (W + TS2D_TILE - 1) / TS2D_TILE, gy = (H + TS2D_TILE - 1) / TS2D_TILE;
+        TS2D_CUDA_TRY(cudaMemcpyAsync(ranges, is.ranges, sizeof(uint2) * gx * gy, cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+int ts2d_export_image(const void *image_state, int32_t W, int32_t H, uint32_t *n_contrib, float *final_T, void *stream)
+{
+    if (!image_state) return TS2D_E_NULL;
+    ImageState is;
+    carve_image(const_cast<void *>(image_state), W, H, &is);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)W * H;
+    if (n_contrib) TS2D_CUDA_TRY(cudaMemcpyAsync(n_contrib, is.n_contrib, sizeof(uint32_t) * N, cudaMemcpyDeviceToDevice, s));
+    if (final_T) TS2D_CUDA_TRY(cudaMemcpyAsync(final_T, is.final_T, sizeof(float) * N, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+// ts2d_common.cuh -- shared device-side definitions for libts2d (sm_100a only).
+//
+// State layout in HBM (all private to this library, decoded only by ts2d_export_*):
+//
+//   geometry state (per triangle, P entries; written by k_preprocess)
+//     rec0   float4[3P]   48 B "raster record": {v1.x v1.y v2.x v2.y} {v3.x v3.y area2 opacity} {r g b depth}
+//     rec1   float4[2P]   32 B rich record    : {n.x n.y n.z vd1} {vd2 vd3 0 0}        (rich_info only)
+//     dkey   u32[P]       fp32 bit pattern of view depth, 0xFFFFFFFF for culled triangles
+//     ids    u32[P]       iota (value input of the depth sort)
+//     dkey2  u32[P]       sorted depth keys;  ids2 u32[P]  triangle ids in depth-rank order
+//     tiles  u32[P]       number of (owned) tiles in the triangle's rect
+//     rect   ushort4[P]   {min.x, min.y, max.x, max.y} in tiles
+//     offs   u32[P]       inclusive scan of tiles[] in depth-rank order
+//     clamp  u8[P]        SH clamp mask (bit c set <=> channel c clamped at 0)
+//     hdr    GeomHeader   R (num_rendered)
+//   binning state (per instance, R entries)
+//     tkey[0]/tval[0] u32[R]  tile id / triangle id of each instance in emission (depth-rank) order
+//     tkey[1]/tval[1] u32[R]  the same after the stable tile sort; tval[1] is the per-tile list
+//   image state
+//     ranges  uint2[tiles]  [start,end) of each tile in the sorted list
+//     n_contrib u32[H*W], final_T f32[H*W]
+//
+// The raster record replaces the reference's nine SoA arrays (R2D/src/param_struct.h:44-57) so the
+// composite kernels stage one contiguous 48 B (+32 B) record per list entry instead of 9 indirect loads.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ts2d.h"
+
+#define TS2D_BLOCK 256
+#define TS2D_EPS 1e-8f  // R2D/src/auxiliary.h:8
+
+struct GeomHeader {
+    int64_t num_rendered;
+    int64_t pad;
+};
+
+struct GeomState {
+    float4 *rec0;
+    float4 *rec1;
+    uint32_t *dkey, *dkey2, *ids, *ids2;
+    uint32_t *tiles;
+    ushort4 *rect;
+    uint32_t *offs;
+    uint8_t *clamp;
+    GeomHeader *hdr;
+    char *cub_temp;
+    size_t cub_temp_bytes;
+};
+
+struct BinState {
+    uint32_t *tkey[2];
+    uint32_t *tval[2];
+    char *cub_temp;
+    size_t cub_temp_bytes;
+};
+
+struct ImageState {
+    uint2 *ranges;
+    uint32_t *n_contrib;
+    float *final_T;
+};
+
+// ---- small vector helpers (own naming; semantics are plain component-wise fp32) ----
+struct f2 { float x, y; };
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f2 mk2(float x, float y) { f2 r; r.x = x; r.y = y; return r; }
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ f2 operator+(f2 a, f2 b) { return mk2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ f2 operator-(f2 a, f2 b) { return mk2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ f2 operator*(f2 a, f2 b) { return mk2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ f2 operator*(f2 a, float s) { return mk2(a.x * s, a.y * s); }
+__device__ __forceinline__ f2 operator*(float s, f2 a) { return mk2(s * a.x, s * a.y); }
+__device__ __forceinline__ f2 operator+(f2 a, float s) { return mk2(a.x + s, a.y + s); }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ f3 operator*(float s, f3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ f3 operator/(f3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ f3 operator+(f3 a, float s) { return mk3(a.x + s, a.y + s, a.z + s); }
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float len3(f3 a) { return sqrtf(dot3(a, a)); }
+__device__ __forceinline__ float len2(f2 a) { return sqrtf(a.x * a.x + a.y * a.y); }
+__device__ __forceinline__ float cross2(f2 a, f2 b) { return a.x * b.y - a.y * b.x; }
+__device__ __forceinline__ f3 cross3(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ f2 perp2(f2 a) { return mk2(a.y, -a.x); }
+
+// Affine maps with the 16-float matrices of ts2d_camera (element [4*c + r]); the summation order
+// (x-term + y-term + z-term + translation) is the one the reference's parity depends on
+// (R2D/src/auxiliary.h:40-95).
+__device__ __forceinline__ f3 xf_point(const float *m, f3 p)
+{
+    return mk3(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+               m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]);
+}
+__device__ __forceinline__ f3 xf_vec(const float *m, f3 p)
+{
+    return mk3(m[0] * p.x + m[4] * p.y + m[8] * p.z, m[1] * p.x + m[5] * p.y + m[9] * p.z, m[2] * p.x + m[6] * p.y + m[10] * p.z);
+}
+__device__ __forceinline__ f3 xf_vec_T(const float *m, f3 p)
+{
+    return mk3(m[0] * p.x + m[1] * p.y + m[2] * p.z, m[4] * p.x + m[5] * p.y + m[6] * p.z, m[8] * p.x + m[9] * p.y + m[10] * p.z);
+}
+__device__ __forceinline__ float4 xf_hom(const float *m, f3 p)
+{
+    return make_float4(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                       m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14], m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15]);
+}
+__device__ __forceinline__ f3 project_center(const float *m, f3 p)
+{
+    float4 h = xf_hom(m, p);
+    float winv = 1.0f / (fabsf(h.w) + TS2D_EPS);
+    return mk3(h.x * winv, h.y * winv, h.z * winv);
+}
+// First-order projection of a view-space offset d at view-space point p (R2D/src/auxiliary.h:97-118).
+__device__ __forceinline__ f2 project_offset(f3 p, f3 d, float tfx, float tfy)
+{
+    return mk2((d.x - d.z * p.x / p.z) / (p.z * tfx), (d.y - d.z * p.y / p.z) / (p.z * tfy));
+}
+// The reference's one fp64 hop (R2D/src/auxiliary.h:35-38); kept so centre pixels round identically.
+__device__ __forceinline__ float ndc_to_pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
+
+// ------------------------------------------------------------------------------------------------
+// Per-(pixel, triangle) evaluation.
+//
+// eval_exact() is the op-for-op mirror of the reference's per-pair arithmetic
+// (R2D/src/forward.cu:299-314 == backward.cu:382-401) with the FMA contraction the reference's
+// sm_100 build has (checked against its SASS: t = pv2.y*pv3.x; fma(pv2.x, pv3.y, -t); IEEE divide;
+// ecc = fma(-3, min3, 1); libdevice powf / expf).  Written with explicit round-to-nearest
+// intrinsics so that no surrounding code can change the contraction.  All skip decisions
+// (ecc range, alpha < 1/255) and the value of alpha are therefore bit-identical to the reference.
+// ------------------------------------------------------------------------------------------------
+struct PairEval {
+    float a1, a2, a3, ecc, power, G, alpha;
+    float pv1x, pv1y, pv2x, pv2y, pv3x, pv3y;
+};
+
+__device__ __forceinline__ bool eval_exact(float v1x, float v1y, float v2x, float v2y, float v3x, float v3y, float area2, float op,
+                                           float two_gamma, float px, float py, PairEval &e)
+{
+    e.pv1x = __fsub_rn(v1x, px); e.pv1y = __fsub_rn(v1y, py);
+    e.pv2x = __fsub_rn(v2x, px); e.pv2y = __fsub_rn(v2y, py);
+    e.pv3x = __fsub_rn(v3x, px); e.pv3y = __fsub_rn(v3y, py);
+    const float c1 = __fmaf_rn(e.pv2x, e.pv3y, -__fmul_rn(e.pv2y, e.pv3x));
+    const float c2 = __fmaf_rn(e.pv3x, e.pv1y, -__fmul_rn(e.pv3y, e.pv1x));
+    e.a1 = __fdiv_rn(c1, area2);
+    e.a2 = __fdiv_rn(c2, area2);
+    e.a3 = __fsub_rn(__fsub_rn(1.0f, e.a1), e.a2);
+    e.ecc = __fmaf_rn(fminf(fminf(e.a1, e.a2), e.a3), -3.0f, 1.0f);
+    if (e.ecc < 0.0f || e.ecc > 10.0f) return false;
+    e.power = __fmul_rn(-0.5f, powf(e.ecc, two_gamma));
+    e.G = expf(e.power);
+    e.alpha = fminf(0.99f, __fmul_rn(op, e.G));
+    return !(e.alpha < 1.0f / 255.0f);
+}
+
+// Per-triangle gradient accumulator written by the composite backward and consumed by K9:
+// 16 floats = one 64 B line per triangle.
+//   [0..5] dL/d(v1.xy, v2.xy, v3.xy)   [6] dL/d opacity   [7] dL/d n.x
+//   [8..10] dL/d rgb                   [11] dL/d n.y      [12] dL/d n.z   [13..15] dL/d v_depth
+#define GACC_STRIDE 16
+
+// Warp helpers
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+#define TS2D_CUDA_TRY(expr)                    \
+    do {                                       \
+        cudaError_t _e = (expr);               \
+        if (_e != cudaSuccess) return (int)_e; \
+    } while (0)
+
+// Host-side helpers shared by the .cu translation units
+static inline size_t ts2d_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t ts2d_depth_sort_temp_bytes(int32_t P);
+size_t ts2d_tile_sort_temp_bytes(int64_t R);
+
+// stage launchers (each returns 0 / cudaError_t)
+int ts2d_launch_preprocess(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, int32_t *radii, GeomState gs, cudaStream_t s);
+int ts2d_launch_order_and_scan(int32_t P, GeomState gs, int64_t *R_host, cudaStream_t s);
+int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_flags *f, int32_t P, int64_t R, GeomState gs, BinState bs, ImageState is, cudaStream_t s);
+int ts2d_launch_render_fwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
+                           ImageState is, const ts2d_forward_out *out, cudaStream_t s);
+int ts2d_launch_render_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
+                           ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s);
+int ts2d_launch_preprocess_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, const int32_t *radii, GeomState gs,
+                               const float *gacc, const ts2d_backward_out *out, cudaStream_t s);

@@ -1,0 +1,372 @@
+// ts2d_preprocess.cu -- per-triangle stages: forward preprocess + SH colour (K1) and their backward (K9).
+//
+// Replaces R2D/src/forward.cu:9-193 (computeRGBFromSH, FORWARD::preprocessCUDA) and
+// R2D/src/backward.cu:9-263 (computeRGBFromSHBackward, projectPointBackward,
+// projectVecApproxBackward, BACKWARD::preprocessCUDA).
+//
+// Parity rule: every quantity that feeds a comparison or a float->int cast (cull tests, tile rect,
+// radii, depth bits) keeps the reference's expression tree, is compiled WITHOUT --use_fast_math and
+// with the default FMA contraction, so the integer outputs are bit-identical.
+// Layout is new: one 48 B (+32 B rich) record per triangle instead of 13 SoA arrays, SH
+// clamp mask packed to one byte, tile rect packed to 4 x u16.
+#include "ts2d_common.cuh"
+
+__constant__ float kC0 = 0.28209479177387814f;
+__constant__ float kC1 = 0.4886025119029199f;
+__constant__ float kC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                             -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+__device__ __forceinline__ f3 ld3(const float *p) { return mk3(p[0], p[1], p[2]); }
+
+// Real SH basis (degree <= 3) times per-triangle coefficients, +0.5, clamp at 0 with mask.
+__device__ __forceinline__ f3 sh_colour(int deg, const float *sh, f3 pos, f3 cam, uint8_t &mask)
+{
+    f3 dir = pos - cam;
+    dir = dir / len3(dir);
+    f3 rgb = kC0 * ld3(sh);
+    if (deg > 0) {
+        const float x = dir.x, y = dir.y, z = dir.z;
+        rgb = rgb - kC1 * y * ld3(sh + 3) + kC1 * z * ld3(sh + 6) - kC1 * x * ld3(sh + 9);
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            rgb = rgb + kC2[0] * xy * ld3(sh + 12) + kC2[1] * yz * ld3(sh + 15) + kC2[2] * (2.0f * zz - xx - yy) * ld3(sh + 18) +
+                  kC2[3] * xz * ld3(sh + 21) + kC2[4] * (xx - yy) * ld3(sh + 24);
+            if (deg > 2) {
+                rgb = rgb + kC3[0] * y * (3.0f * xx - yy) * ld3(sh + 27) + kC3[1] * xy * z * ld3(sh + 30) +
+                      kC3[2] * y * (4.0f * zz - xx - yy) * ld3(sh + 33) + kC3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * ld3(sh + 36) +
+                      kC3[4] * x * (4.0f * zz - xx - yy) * ld3(sh + 39) + kC3[5] * z * (xx - yy) * ld3(sh + 42) +
+                      kC3[6] * x * (xx - 3.0f * yy) * ld3(sh + 45);
+            }
+        }
+    }
+    rgb = rgb + 0.5f;
+    mask = (uint8_t)((rgb.x < 0 ? 1 : 0) | (rgb.y < 0 ? 2 : 0) | (rgb.z < 0 ? 4 : 0));
+    return mk3(fmaxf(rgb.x, 0.0f), fmaxf(rgb.y, 0.0f), fmaxf(rgb.z, 0.0f));
+}
+
+// Shared geometric prefix of K1 and K9: centre, view-space offsets, projected offsets.
+struct TriGeom {
+    f3 center, center_view, center_clip, r1v, r2v, r3v;
+    f2 r1p, r2p, r3p;
+    float limx, limy;
+};
+
+__device__ __forceinline__ void tri_geom_view(const float *vp, const float *view, float tfx, float tfy, TriGeom &t, f3 &r1, f3 &r2, f3 &r3)
+{
+    const f3 a = ld3(vp), b = ld3(vp + 3), c = ld3(vp + 6);
+    t.center = (a + b + c) / 3.0f;
+    t.center_view = xf_point(view, t.center);
+    t.limx = 1.3f * tfx * t.center_view.z;
+    t.limy = 1.3f * tfy * t.center_view.z;
+    t.center_clip = mk3(fminf(fmaxf(-t.limx, t.center_view.x), t.limx), fminf(fmaxf(-t.limy, t.center_view.y), t.limy), t.center_view.z);
+    r1 = a - t.center;
+    r2 = b - t.center;
+    r3 = c - t.center;
+}
+
+__global__ void __launch_bounds__(TS2D_BLOCK)
+k_preprocess(int W, int H, int P, int D, int M, int C, bool rich, bool use_shs, int gx, int gy, bool back_culling, float tfx, float tfy,
+             int shard_rank, int shard_world, const float *__restrict__ view, const float *__restrict__ proj, const float *__restrict__ campos,
+             const float *__restrict__ vertex, const float *__restrict__ shs, const float *__restrict__ feature,
+             const float *__restrict__ opacity, int32_t *__restrict__ radii, float4 *__restrict__ rec0, float4 *__restrict__ rec1,
+             uint32_t *__restrict__ dkey, uint32_t *__restrict__ ids, uint32_t *__restrict__ tiles, ushort4 *__restrict__ rect,
+             uint8_t *__restrict__ clamp)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+
+    int out_radius = 0;
+    uint32_t out_tiles = 0, out_key = 0xFFFFFFFFu;
+    ushort4 out_rect = make_ushort4(0, 0, 0, 0);
+
+    do {
+        TriGeom t;
+        f3 r1, r2, r3;
+        const float *vp = vertex + 9 * (size_t)idx;
+        {
+            // near culling on the projected centre happens before the view transform in the reference;
+            // order of evaluation does not change values.
+            const f3 a = ld3(vp), b = ld3(vp + 3), c = ld3(vp + 6);
+            const f3 center = (a + b + c) / 3.0f;
+            const f3 cproj = project_center(proj, center);
+            if (cproj.z <= 0) break;
+            tri_geom_view(vp, view, tfx, tfy, t, r1, r2, r3);
+            t.r1v = xf_vec(view, r1);
+            t.r2v = xf_vec(view, r2);
+            if (len3(cross3(t.r1v, t.r2v)) < TS2D_EPS) break;
+            t.r3v = xf_vec(view, r3);
+            t.r1p = project_offset(t.center_clip, t.r1v, tfx, tfy);
+            t.r2p = project_offset(t.center_clip, t.r2v, tfx, tfy);
+            t.r3p = project_offset(t.center_clip, t.r3v, tfx, tfy);
+            const float n1 = len2(t.r1p), n2 = len2(t.r2p), n3 = len2(t.r3p);
+            if (n1 < TS2D_EPS || n2 < TS2D_EPS || n3 < TS2D_EPS) break;
+
+            const f2 scaling = mk2(0.5f * W, 0.5f * H);
+            const float kernel_size = 0.5f;
+            const f2 q1 = t.r1p * (scaling + kernel_size / n1);
+            const f2 q2 = t.r2p * (scaling + kernel_size / n2);
+            const f2 q3 = t.r3p * (scaling + kernel_size / n3);
+            const f2 c2d = mk2(ndc_to_pix(cproj.x, W), ndc_to_pix(cproj.y, H));
+            const f2 s1 = c2d + q1, s2 = c2d + q2, s3 = c2d + q3;
+            const float area2 = cross2(s2 - s1, s3 - s1);
+            if (back_culling) {
+                if (area2 >= -TS2D_EPS) break;
+            } else {
+                if (fabsf(area2) < TS2D_EPS) break;
+            }
+            const float dilation = 3.0f;
+            const f2 d1 = c2d + dilation * q1, d2 = c2d + dilation * q2, d3 = c2d + dilation * q3;
+            const f2 vmin = mk2(fminf(fminf(d1.x, d2.x), d3.x), fminf(fminf(d1.y, d2.y), d3.y));
+            const f2 vmax = mk2(fmaxf(fmaxf(d1.x, d2.x), d3.x), fmaxf(fmaxf(d1.y, d2.y), d3.y));
+            const uint32_t rx0 = min((uint32_t)gx, (uint32_t)max(0, (int)(vmin.x / TS2D_TILE)));
+            const uint32_t ry0 = min((uint32_t)gy, (uint32_t)max(0, (int)(vmin.y / TS2D_TILE)));
+            const uint32_t rx1 = min((uint32_t)gx, (uint32_t)max(0, (int)((vmax.x + TS2D_TILE - 1) / TS2D_TILE)));
+            const uint32_t ry1 = min((uint32_t)gy, (uint32_t)max(0, (int)((vmax.y + TS2D_TILE - 1) / TS2D_TILE)));
+            if (rx1 <= rx0 || ry1 <= ry0) break;
+
+            f3 rgb;
+            uint8_t mask = 0;
+            if (use_shs) {
+                rgb = sh_colour(D, shs + (size_t)idx * M * 3, center, ld3(campos), mask);
+            } else {
+                const float *fp = feature + (size_t)idx * C;
+                rgb = mk3(fp[0], C > 1 ? fp[1] : 0.0f, C > 2 ? fp[2] : 0.0f);
+            }
+            clamp[idx] = mask;
+            const float depth = t.center_view.z;
+            rec0[3 * (size_t)idx + 0] = make_float4(s1.x, s1.y, s2.x, s2.y);
+            rec0[3 * (size_t)idx + 1] = make_float4(s3.x, s3.y, area2, opacity[idx]);
+            rec0[3 * (size_t)idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, depth);
+            if (rich) {
+                f3 n = cross3(t.r1v, t.r2v);
+                n = n / len3(n);
+                const f3 vd = mk3(t.r1v.z, t.r2v.z, t.r3v.z) + t.center_view.z;
+                rec1[2 * (size_t)idx + 0] = make_float4(n.x, n.y, n.z, vd.x);
+                rec1[2 * (size_t)idx + 1] = make_float4(vd.y, vd.z, 0.0f, 0.0f);
+            }
+            out_key = __float_as_uint(depth);
+            out_rect = make_ushort4((unsigned short)rx0, (unsigned short)ry0, (unsigned short)rx1, (unsigned short)ry1);
+            if (shard_world == 1) {
+                out_tiles = (rx1 - rx0) * (ry1 - ry0);
+            } else {
+                uint32_t n = 0;  // tiles of the rect this rank owns (tile_id % world == rank)
+                for (uint32_t y = ry0; y < ry1; y++)
+                    for (uint32_t x = rx0; x < rx1; x++) n += ((y * (uint32_t)gx + x) % (uint32_t)shard_world == (uint32_t)shard_rank);
+                out_tiles = n;
+            }
+            out_radius = max(ceilf((vmax.x - vmin.x) * 0.5f), ceilf((vmax.y - vmin.y) * 0.5f));
+        }
+    } while (0);
+
+    radii[idx] = out_radius;
+    tiles[idx] = out_tiles;
+    rect[idx] = out_rect;
+    dkey[idx] = out_key;
+    ids[idx] = (uint32_t)idx;
+}
+
+int ts2d_launch_preprocess(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, int32_t *radii, GeomState gs, cudaStream_t s)
+{
+    const int P = g->P;
+    const int gx = (cam->width + TS2D_TILE - 1) / TS2D_TILE, gy = (cam->height + TS2D_TILE - 1) / TS2D_TILE;
+    k_preprocess<<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(
+        cam->width, cam->height, P, g->sh_degree, g->M, g->C, f->rich_info != 0, g->use_shs != 0, gx, gy, f->back_culling != 0, cam->tan_fovx,
+        cam->tan_fovy, f->shard_rank, f->shard_world, cam->viewmatrix, cam->projmatrix, cam->campos, g->vertex, g->shs, g->feature, g->opacity,
+        radii, gs.rec0, gs.rec1, gs.dkey, gs.ids, gs.tiles, gs.rect, gs.clamp);
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9: per-triangle backward.  gacc holds, per triangle, the 16 screen-space sums produced by the
+// composite backward: [0..5] dL/d(v1,v2,v3)_2D, [6] dL/d opacity, [7] pad, [8..10] dL/d rgb, [11] pad... see GACC_* below.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ f2 grad_norm2(f2 v, f2 dv)
+{
+    const float sum2 = v.x * v.x + v.y * v.y;
+    const float n = sqrtf(sum2);
+    const float inv = 1.0f / (n * n * n);
+    return mk2(((sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y) * inv, (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y) * inv);
+}
+__device__ __forceinline__ f3 grad_norm3(f3 v, f3 dv)
+{
+    const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
+    const float n = sqrtf(sum2);
+    const float inv = 1.0f / (n * n * n);
+    return mk3(((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * inv,
+               (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * inv,
+               (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * inv);
+}
+__device__ __forceinline__ void project_offset_bwd(f3 p, f3 d, float tfx, float tfy, f2 g, f3 &gp, f3 &gd)
+{
+    const float px_pz = p.x / p.z, py_pz = p.y / p.z;
+    const float vx_pz = d.x / p.z, vy_pz = d.y / p.z, vz_pz = d.z / p.z;
+    const f2 gv = mk2(g.x / (p.z * tfx), g.y / (p.z * tfy));
+    gd = mk3(gv.x, gv.y, -gv.x * px_pz - gv.y * py_pz);
+    gp = mk3(-gv.x * vz_pz, -gv.y * vz_pz, gv.x * (2.0f * vz_pz * px_pz - vx_pz) + gv.y * (2.0f * vz_pz * py_pz - vy_pz));
+}
+
+__device__ __forceinline__ void st3(float *p, f3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+
+// SH backward: writes dL/dsh for the active coefficients, zero for the inactive ones, returns dL/dcentre.
+__device__ __forceinline__ f3 sh_colour_bwd(int deg, int M, const float *sh, f3 pos, f3 cam, uint8_t mask, f3 g, float *out)
+{
+    const f3 dir_orig = pos - cam;
+    const f3 dir = dir_orig / len3(dir_orig);
+    g.x *= (mask & 1) ? 0.0f : 1.0f;
+    g.y *= (mask & 2) ? 0.0f : 1.0f;
+    g.z *= (mask & 4) ? 0.0f : 1.0f;
+    f3 dx = mk3(0, 0, 0), dy = mk3(0, 0, 0), dz = mk3(0, 0, 0);
+    const float x = dir.x, y = dir.y, z = dir.z;
+    st3(out, kC0 * g);
+    int written = 1;
+    if (deg > 0) {
+        st3(out + 3, (-kC1 * y) * g);
+        st3(out + 6, (kC1 * z) * g);
+        st3(out + 9, (-kC1 * x) * g);
+        dx = -kC1 * ld3(sh + 9);
+        dy = -kC1 * ld3(sh + 3);
+        dz = kC1 * ld3(sh + 6);
+        written = 4;
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            st3(out + 12, (kC2[0] * xy) * g);
+            st3(out + 15, (kC2[1] * yz) * g);
+            st3(out + 18, (kC2[2] * (2.f * zz - xx - yy)) * g);
+            st3(out + 21, (kC2[3] * xz) * g);
+            st3(out + 24, (kC2[4] * (xx - yy)) * g);
+            const f3 s4 = ld3(sh + 12), s5 = ld3(sh + 15), s6 = ld3(sh + 18), s7 = ld3(sh + 21), s8 = ld3(sh + 24);
+            dx = dx + (kC2[0] * y * s4 + kC2[2] * 2.f * -x * s6 + kC2[3] * z * s7 + kC2[4] * 2.f * x * s8);
+            dy = dy + (kC2[0] * x * s4 + kC2[1] * z * s5 + kC2[2] * 2.f * -y * s6 + kC2[4] * 2.f * -y * s8);
+            dz = dz + (kC2[1] * y * s5 + kC2[2] * 2.f * 2.f * z * s6 + kC2[3] * x * s7);
+            written = 9;
+            if (deg > 2) {
+                st3(out + 27, (kC3[0] * y * (3.f * xx - yy)) * g);
+                st3(out + 30, (kC3[1] * xy * z) * g);
+                st3(out + 33, (kC3[2] * y * (4.f * zz - xx - yy)) * g);
+                st3(out + 36, (kC3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * g);
+                st3(out + 39, (kC3[4] * x * (4.f * zz - xx - yy)) * g);
+                st3(out + 42, (kC3[5] * z * (xx - yy)) * g);
+                st3(out + 45, (kC3[6] * x * (xx - 3.f * yy)) * g);
+                const f3 s9 = ld3(sh + 27), s10 = ld3(sh + 30), s11 = ld3(sh + 33), s12 = ld3(sh + 36), s13 = ld3(sh + 39), s14 = ld3(sh + 42),
+                         s15 = ld3(sh + 45);
+                dx = dx + (kC3[0] * s9 * 3.f * 2.f * xy + kC3[1] * s10 * yz + kC3[2] * s11 * -2.f * xy + kC3[3] * s12 * -3.f * 2.f * xz +
+                           kC3[4] * s13 * (-3.f * xx + 4.f * zz - yy) + kC3[5] * s14 * 2.f * xz + kC3[6] * s15 * 3.f * (xx - yy));
+                dy = dy + (kC3[0] * s9 * 3.f * (xx - yy) + kC3[1] * s10 * xz + kC3[2] * s11 * (-3.f * yy + 4.f * zz - xx) +
+                           kC3[3] * s12 * -3.f * 2.f * yz + kC3[4] * s13 * -2.f * xy + kC3[5] * s14 * -2.f * yz + kC3[6] * s15 * -3.f * 2.f * xy);
+                dz = dz + (kC3[1] * s10 * xy + kC3[2] * s11 * 4.f * 2.f * yz + kC3[3] * s12 * 3.f * (2.f * zz - xx - yy) +
+                           kC3[4] * s13 * 4.f * 2.f * xz + kC3[5] * s14 * (xx - yy));
+                written = 16;
+            }
+        }
+    }
+    for (int k = 3 * written; k < 3 * M; k++) out[k] = 0.0f;
+    const f3 gdir = mk3(dot3(g, dx), dot3(g, dy), dot3(g, dz));
+    return grad_norm3(dir_orig, gdir);
+}
+
+__global__ void __launch_bounds__(TS2D_BLOCK)
+k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool rich, float tfx, float tfy, const float *__restrict__ view,
+                 const float *__restrict__ proj, const float *__restrict__ campos, const float *__restrict__ vertex,
+                 const float *__restrict__ shs, const int32_t *__restrict__ radii, const uint8_t *__restrict__ clamp,
+                 const float4 *__restrict__ gacc, float *__restrict__ dL_dvertex, float *__restrict__ dL_dcenter2D, float *__restrict__ dL_dshs,
+                 float *__restrict__ dL_dfeature, float *__restrict__ dL_dopacity)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    float *ov = dL_dvertex + 9 * (size_t)idx;
+    if (radii[idx] <= 0) {  // reference leaves its zero-initialised outputs untouched here (backward.cu:165)
+        for (int k = 0; k < 9; k++) ov[k] = 0.0f;
+        dL_dcenter2D[2 * idx] = 0.0f;
+        dL_dcenter2D[2 * idx + 1] = 0.0f;
+        for (int k = 0; k < 3 * M; k++) dL_dshs[(size_t)idx * M * 3 + k] = 0.0f;
+        for (int k = 0; k < C; k++) dL_dfeature[(size_t)idx * C + k] = 0.0f;
+        dL_dopacity[idx] = 0.0f;
+        return;
+    }
+    const float4 A0 = gacc[4 * (size_t)idx + 0], A1 = gacc[4 * (size_t)idx + 1], A2 = gacc[4 * (size_t)idx + 2], A3 = gacc[4 * (size_t)idx + 3];
+    const f2 g1 = mk2(A0.x, A0.y), g2 = mk2(A0.z, A0.w), g3 = mk2(A1.x, A1.y);
+    const float g_op = A1.z;
+    const f3 g_rgb = mk3(A2.x, A2.y, A2.z);
+    const f3 g_n = mk3(A1.w, A2.w, A3.x);
+    const f3 g_vd = mk3(A3.y, A3.z, A3.w);
+
+    TriGeom t;
+    f3 r1, r2, r3;
+    const float *vp = vertex + 9 * (size_t)idx;
+    tri_geom_view(vp, view, tfx, tfy, t, r1, r2, r3);
+    t.r1v = xf_vec(view, r1);
+    t.r2v = xf_vec(view, r2);
+    t.r3v = xf_vec(view, r3);
+    t.r1p = project_offset(t.center_clip, t.r1v, tfx, tfy);
+    t.r2p = project_offset(t.center_clip, t.r2v, tfx, tfy);
+    t.r3p = project_offset(t.center_clip, t.r3v, tfx, tfy);
+
+    const f2 gc2d = g1 + g2 + g3;
+    const f2 scaling = mk2(0.5f * W, 0.5f * H);
+    const float kernel_size = 0.5f;
+    const f2 gp1 = scaling * g1 + kernel_size * grad_norm2(t.r1p, g1);
+    const f2 gp2 = scaling * g2 + kernel_size * grad_norm2(t.r2p, g2);
+    const f2 gp3 = scaling * g3 + kernel_size * grad_norm2(t.r3p, g3);
+    const f2 gcproj = scaling * gc2d;
+
+    f3 gr1v, gr2v, gr3v, gcc, gcv = mk3(0, 0, 0);
+    project_offset_bwd(t.center_clip, t.r1v, tfx, tfy, gp1, gcc, gr1v);
+    gcv = gcv + gcc;
+    project_offset_bwd(t.center_clip, t.r2v, tfx, tfy, gp2, gcc, gr2v);
+    gcv = gcv + gcc;
+    project_offset_bwd(t.center_clip, t.r3v, tfx, tfy, gp3, gcc, gr3v);
+    gcv = gcv + gcc;
+    if (t.center_view.x < -t.limx || t.center_view.x > t.limx) gcv.x = 0;
+    if (t.center_view.y < -t.limy || t.center_view.y > t.limy) gcv.y = 0;
+
+    if (rich) {
+        const f3 cr = cross3(t.r1v, t.r2v);
+        const f3 gcr = grad_norm3(cr, g_n);
+        gr1v = gr1v + (cross3(t.r2v, gcr) + mk3(0, 0, g_vd.x));
+        gr2v = gr2v + (cross3(gcr, t.r1v) + mk3(0, 0, g_vd.y));
+        gr3v = gr3v + mk3(0, 0, g_vd.z);
+        gcv = gcv + mk3(0, 0, g_vd.x + g_vd.y + g_vd.z);
+    }
+
+    f3 gcenter;
+    {
+        const float4 h = xf_hom(proj, t.center);
+        const float winv = 1.0f / (fabsf(h.w) + TS2D_EPS);
+        const f3 pp = mk3(h.x * winv, h.y * winv, h.z * winv);
+        const f3 gpp = mk3(gcproj.x, gcproj.y, 0);
+        const float s = fabsf(winv);
+        const float hx = s * gpp.x, hy = s * gpp.y, hz = s * gpp.z, hw = s * (-dot3(gpp, pp));
+        gcenter = mk3(proj[0] * hx + proj[1] * hy + proj[2] * hz + proj[3] * hw, proj[4] * hx + proj[5] * hy + proj[6] * hz + proj[7] * hw,
+                      proj[8] * hx + proj[9] * hy + proj[10] * hz + proj[11] * hw);
+    }
+    gcenter = gcenter + xf_vec_T(view, gcv);
+    const f3 gr1 = xf_vec_T(view, gr1v), gr2 = xf_vec_T(view, gr2v), gr3 = xf_vec_T(view, gr3v);
+
+    if (use_shs) {
+        const f3 gsh = sh_colour_bwd(D, M, shs + (size_t)idx * M * 3, t.center, ld3(campos), clamp[idx], g_rgb, dL_dshs + (size_t)idx * M * 3);
+        gcenter = gcenter + gsh;
+    } else {
+        for (int k = 0; k < 3 * M; k++) dL_dshs[(size_t)idx * M * 3 + k] = 0.0f;
+    }
+    st3(ov, (2 * gr1 - gr2 - gr3 + gcenter) / 3.0f);
+    st3(ov + 3, (2 * gr2 - gr1 - gr3 + gcenter) / 3.0f);
+    st3(ov + 6, (2 * gr3 - gr1 - gr2 + gcenter) / 3.0f);
+    dL_dcenter2D[2 * idx] = gc2d.x;
+    dL_dcenter2D[2 * idx + 1] = gc2d.y;
+    dL_dfeature[(size_t)idx * C + 0] = g_rgb.x;
+    if (C > 1) dL_dfeature[(size_t)idx * C + 1] = g_rgb.y;
+    if (C > 2) dL_dfeature[(size_t)idx * C + 2] = g_rgb.z;
+    dL_dopacity[idx] = g_op;
+}
+
+int ts2d_launch_preprocess_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, const int32_t *radii, GeomState gs,
+                               const float *gacc, const ts2d_backward_out *out, cudaStream_t s)
+{
+    const int P = g->P;
+    k_preprocess_bwd<<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(
+        cam->width, cam->height, P, g->sh_degree, g->M, g->C, g->use_shs != 0, f->rich_info != 0, cam->tan_fovx, cam->tan_fovy, cam->viewmatrix,
+        cam->projmatrix, cam->campos, g->vertex, g->shs, radii, gs.clamp, (const float4 *)gacc, out->dL_dvertex, out->dL_dcenter2D, out->dL_dshs,
+        out->dL_dfeature, out->dL_dopacity);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,76 @@
+"""Image-space tile sharding of ONE render across the GPUs of a node (no counterpart in the reference,
+which has no distributed code at all -- SURVEY.md section 2a / 8e).
+
+One process per GPU (torchrun), parameters replicated.  Tile ``t`` is owned by rank ``t % world``
+(interleaved for load balance against non-uniform triangle density).  Per frame:
+
+  forward   every rank runs the per-triangle preprocess (cheap, keeps ``radii`` identical everywhere),
+            emits/sorts/composites only its own tiles into a zero-filled full-size image;
+            one all-reduce(sum) of the packed image planes rebuilds the frame; contrib_sum is
+            all-reduced with sum, contrib_max with max.
+  backward  every rank walks its own tiles, producing partial per-triangle gradients; the five
+            gradient tensors are packed into one bucket and all-reduced(sum) over NCCL/NVLink.
+
+All collectives are issued on the current CUDA stream through torch.distributed (backend "nccl" on
+GPUs, "gloo" in the CPU tests of the host logic).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+_STATE = {"enabled": False, "group": None, "rank": 0, "world": 1}
+
+
+def enable_tile_sharding(group: Optional["dist.ProcessGroup"] = None) -> Tuple[int, int]:
+    """Turn on tile sharding over ``group`` (default: the WORLD group). Returns (rank, world)."""
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    _STATE.update(enabled=True, group=group, rank=dist.get_rank(group), world=dist.get_world_size(group))
+    return _STATE["rank"], _STATE["world"]
+
+
+def disable_tile_sharding() -> None:
+    _STATE.update(enabled=False, group=None, rank=0, world=1)
+
+
+def current_shard() -> Tuple[int, int]:
+    if not _STATE["enabled"] or _STATE["world"] == 1:
+        return (0, 1)
+    return (_STATE["rank"], _STATE["world"])
+
+
+def owned_tiles(n_tiles: int, rank: int, world: int) -> range:
+    """Tile ids owned by ``rank`` (the rule the CUDA kernels use: tile % world == rank)."""
+    return range(rank, n_tiles, world)
+
+
+def _bucket_all_reduce(tensors, op) -> None:
+    """One collective for several tensors: pack -> all_reduce -> unpack (launch-latency bound otherwise)."""
+    tensors = [t for t in tensors if t is not None and t.numel() > 0]
+    if not tensors:
+        return
+    if len(tensors) == 1:
+        dist.all_reduce(tensors[0], op=op, group=_STATE["group"])
+        return
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, op=op, group=_STATE["group"])
+    off = 0
+    for t in tensors:
+        n = t.numel()
+        t.copy_(flat[off:off + n].view_as(t))
+        off += n
+
+
+def assemble_forward(out_feature, depth=None, normal=None, contrib_sum=None, contrib_max=None) -> None:
+    """Each rank holds its tiles in zero-filled full-size planes: sum them; contrib_max by max."""
+    _bucket_all_reduce([out_feature, depth, normal, contrib_sum], dist.ReduceOp.SUM)
+    if contrib_max is not None and contrib_max.numel() > 0:
+        dist.all_reduce(contrib_max, op=dist.ReduceOp.MAX, group=_STATE["group"])
+
+
+def reduce_gradients(*grads) -> None:
+    """NCCL all-reduce(sum) of the per-triangle gradient tensors (partial sums over each rank's tiles)."""
+    _bucket_all_reduce(list(grads), dist.ReduceOp.SUM)
