@@ -1,0 +1,495 @@
+#!/usr/bin/env python3
+"""bench.py -- rasterizer fwd+bwd frames/s on the BASELINE.json workload (default C3: 1.5 M triangles, 1920x1080,
+SH degree 3, rich_info=True -- what training runs), synthetic seeded data (triangle_splatting_b200/scenes.py).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one forward + backward of the rasterizer through the reference-shaped public API
+(TriangleRasterizer / _RasterizeTriangles autograd.Function -> C ABI of libts2d.so).
+  value    whole-job frames/s, parameters and upstream gradients resident in HBM, CUDA events, max over ranks.
+  e2e      the same metric for a training-style step driven from HOST buffers: per step the camera tensors and a
+           ground-truth image are copied from pinned host memory, an L1 loss against it drives backward, and the
+           scalar loss is read back (bytes counted from the tensors copied).  `e2e_all_host` additionally moves
+           every parameter tensor H2D and every gradient tensor D2H inside the timed region.
+  roofline dominant kernel (largest per-stage device time, CUDA events recorded inside libts2d around each stage).
+  cpu_baseline  the CPU oracle port (oracle/, OpenMP) timed on a bounded sample of the same workload.
+--impl reference times the UNMODIFIED reference CUDA extension (oracle/_ref, built from /root/reference by
+oracle/build_ref.py) on the same scene through its own pybind entry points; if that module cannot be loaded
+it falls back to the CPU oracle port on a bounded sample and says so.
+N > 1: image-space tile sharding of ONE render (tile % N == rank) + NCCL all-reduce; strong scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+# ----------------------------------------------------------------------------------------------- utilities
+class ClockSampler:
+    """nvidia-smi clocks/throttle sampling DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                                          str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(P, V, R, N, T, K, M, rich):
+    """bytes each stage must touch once (no temp / zero-fill / sort-pass amplification)."""
+    rho = 1 if rich else 0
+    rec = 44 + 24 * rho
+    return {
+        "preprocess": 36 * P + 12 * K * V + (rec + 28) * V + 8 * P,
+        "order_scan": 8 * P + 8 * P,
+        "binning": 28 * V + 12 * R + 24 * R + 8 * R + 8 * T,
+        "render_fwd": (4 + rec) * R + (20 + 16 * rho) * N + 8 * rho * V,
+        "render_bwd": (4 + rec) * R + (20 + 16 * rho) * N + (40 + 24 * rho) * V,
+        "preprocess_bwd": (40 + 24 * rho) * V + (36 + 12 * K + 3) * V + 4 * P + (36 + 8 + 4 + 12 + 12 * M) * P,
+    }
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def scene_for(config: str):
+    from triangle_splatting_b200.scenes import make_config
+
+    return make_config(config)
+
+
+# --------------------------------------------------------------------------------------------- step builders
+class OursStep:
+    """fwd+bwd through TriangleRasterizer (autograd) exactly as diff_recon's TriangleRenderer calls it."""
+
+    def __init__(self, sc, dev):
+        from triangle_splatting_b200 import TriangleRasterizationSettings, TriangleRasterizer
+
+        self.sc = sc.to(dev)
+        self.dev = dev
+        self.vertex = self.sc.vertex.clone().requires_grad_(True)
+        self.shs = self.sc.shs.clone().requires_grad_(True)
+        self.opacity = self.sc.opacity.clone().requires_grad_(True)
+        self.settings_cls, self.rast_cls = TriangleRasterizationSettings, TriangleRasterizer
+        self.rast = TriangleRasterizer(raster_settings=TriangleRasterizationSettings(**self.sc.settings_kwargs()))
+        self.g = [self.sc.grads["dL_dout_feature"], self.sc.grads["dL_dout_depth"], self.sc.grads["dL_dout_normal"]]
+
+    def forward(self, rast=None):
+        center2D = torch.zeros((self.sc.P, 2), device=self.dev, requires_grad=True)
+        return (rast or self.rast).forward(vertex=self.vertex, center2D=center2D, opacity=self.opacity, shs=self.shs, feature=None)
+
+    def __call__(self):
+        self.vertex.grad = self.shs.grad = self.opacity.grad = None
+        out = self.forward()
+        torch.autograd.backward([out[0], out[2], out[3]], self.g)
+        return out
+
+    def e2e_step(self, host):
+        """camera + GT image from pinned host memory -> forward -> L1 loss -> backward -> loss to host."""
+        self.vertex.grad = self.shs.grad = self.opacity.grad = None
+        cam = {k: host[k].to(self.dev, non_blocking=True) for k in ("viewmatrix", "projmatrix", "campos", "background")}
+        gt = host["gt"].to(self.dev, non_blocking=True)
+        kw = self.sc.settings_kwargs()
+        kw.update(cam)
+        out = self.forward(self.rast_cls(raster_settings=self.settings_cls(**kw)))
+        loss = (out[0] - gt).abs().mean()
+        loss.backward()
+        return float(loss.item())
+
+    def e2e_all_host_step(self, host):
+        cam = {k: host[k].to(self.dev, non_blocking=True) for k in ("viewmatrix", "projmatrix", "campos", "background")}
+        v = host["vertex"].to(self.dev, non_blocking=True).requires_grad_(True)
+        s = host["shs"].to(self.dev, non_blocking=True).requires_grad_(True)
+        o = host["opacity"].to(self.dev, non_blocking=True).requires_grad_(True)
+        g = [host[k].to(self.dev, non_blocking=True) for k in ("g_feature", "g_depth", "g_normal")]
+        kw = self.sc.settings_kwargs()
+        kw.update(cam)
+        c2d = torch.zeros((self.sc.P, 2), device=self.dev, requires_grad=True)
+        out = self.rast_cls(raster_settings=self.settings_cls(**kw)).forward(vertex=v, center2D=c2d, opacity=o, shs=s, feature=None)
+        torch.autograd.backward([out[0], out[2], out[3]], g)
+        host["o_image"].copy_(out[0], non_blocking=True)
+        host["o_gv"].copy_(v.grad, non_blocking=True)
+        host["o_gs"].copy_(s.grad, non_blocking=True)
+        host["o_go"].copy_(o.grad, non_blocking=True)
+        host["o_gc"].copy_(c2d.grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+
+class ReferenceStep:
+    """The unmodified reference extension (oracle/_ref) driven through its own pybind entry points, wrapped in the
+    same autograd.Function shape as the reference's Python package (R2D/diff_triangle_rasterization_2D/__init__.py)."""
+
+    def __init__(self, sc, dev, ref):
+        self.sc = sc.to(dev)
+        self.dev, self.ref = dev, ref
+        self.vertex = self.sc.vertex.clone().requires_grad_(True)
+        self.shs = self.sc.shs.clone().requires_grad_(True)
+        self.opacity = self.sc.opacity.clone().requires_grad_(True)
+        self.g = [self.sc.grads["dL_dout_feature"], self.sc.grads["dL_dout_depth"], self.sc.grads["dL_dout_normal"]]
+        refmod = ref
+
+        class _Fn(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, vertex, center2D, shs, feature, opacity, s):
+                args = (s["image_width"], s["image_height"], s["tanfovx"], s["tanfovy"], s["viewmatrix"].contiguous(),
+                        s["projmatrix"].contiguous(), s["campos"].contiguous(), s["sh_degree"], s["gamma"], s["scale_modifier"],
+                        float(s["background_depth"]), s["background"].contiguous(), vertex, shs, feature, opacity, s["back_culling"],
+                        s["rich_info"], s["debug"])
+                (R, out_feature, radii, depth, normal, csum, cmax, gb, bb, ib) = refmod.rasterize_triangles(*args)
+                ctx.s, ctx.R = s, R
+                ctx.save_for_backward(vertex, shs, feature, opacity, radii, gb, bb, ib)
+                return out_feature, radii, depth, normal, csum, cmax
+
+            @staticmethod
+            def backward(ctx, g_feat, _r, g_depth, g_normal, _a, _b):
+                s = ctx.s
+                vertex, shs, feature, opacity, radii, gb, bb, ib = ctx.saved_tensors
+                args = (s["tanfovx"], s["tanfovy"], s["viewmatrix"].contiguous(), s["projmatrix"].contiguous(), s["campos"].contiguous(),
+                        s["sh_degree"], s["gamma"], s["scale_modifier"], float(s["background_depth"]), s["background"].contiguous(), vertex,
+                        shs, feature, opacity, ctx.R, radii, gb, bb, ib, g_feat.contiguous(), g_depth.contiguous(), g_normal.contiguous(),
+                        s["rich_info"], s["debug"])
+                gv, gc, gs, gf, go = refmod.rasterize_triangles_backward(*args)
+                return gv, gc, gs, None, go, None
+
+        self.fn = _Fn
+        self.empty = torch.empty(0, device=dev)
+
+    def forward(self, kw=None):
+        center2D = torch.zeros((self.sc.P, 2), device=self.dev, requires_grad=True)
+        return self.fn.apply(self.vertex, center2D, self.shs, self.empty, self.opacity, kw or self.sc.settings_kwargs())
+
+    def __call__(self):
+        self.vertex.grad = self.shs.grad = self.opacity.grad = None
+        out = self.forward()
+        torch.autograd.backward([out[0], out[2], out[3]], self.g)
+        return out
+
+    def e2e_step(self, host):
+        self.vertex.grad = self.shs.grad = self.opacity.grad = None
+        cam = {k: host[k].to(self.dev, non_blocking=True) for k in ("viewmatrix", "projmatrix", "campos", "background")}
+        gt = host["gt"].to(self.dev, non_blocking=True)
+        kw = self.sc.settings_kwargs()
+        kw.update(cam)
+        out = self.forward(kw)
+        loss = (out[0] - gt).abs().mean()
+        loss.backward()
+        return float(loss.item())
+
+
+def pinned_host_buffers(sc, all_host: bool):
+    pin = lambda t: t.detach().cpu().contiguous().pin_memory()
+    h = {k: pin(sc.cam[k]) for k in ("viewmatrix", "projmatrix", "campos")}
+    h["background"] = pin(sc.background)
+    g = torch.Generator().manual_seed(1234)
+    h["gt"] = torch.rand(sc.background.numel(), sc.cam["image_height"], sc.cam["image_width"], generator=g).pin_memory()
+    if all_host:
+        h.update(vertex=pin(sc.vertex), shs=pin(sc.shs), opacity=pin(sc.opacity), g_feature=pin(sc.grads["dL_dout_feature"]),
+                 g_depth=pin(sc.grads["dL_dout_depth"]), g_normal=pin(sc.grads["dL_dout_normal"]))
+        P = sc.P
+        h.update(o_image=torch.empty_like(h["gt"]).pin_memory(), o_gv=torch.empty(P, 3, 3).pin_memory(),
+                 o_gs=torch.empty_like(h["shs"]).pin_memory(), o_go=torch.empty(P, 1).pin_memory(), o_gc=torch.empty(P, 2).pin_memory())
+    return h
+
+
+# --------------------------------------------------------------------------------------------- CPU baseline
+def cpu_oracle_baseline(sc, tile_step=None, budget_s=20.0):
+    """Oracle port (oracle/ts2d_oracle.c, OpenMP over tiles) on a bounded sample: full per-triangle stages + binning,
+    composite fwd+bwd on every `tile_step`-th tile, extrapolated to the whole frame."""
+    import numpy as np
+
+    from oracle.oracle import Oracle
+
+    o = Oracle("f32")
+    kw = sc.settings_kwargs()
+    kw.pop("debug")
+    kw = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in kw.items()}
+    arrs = dict(vertex=sc.vertex.cpu().numpy(), shs=sc.shs.cpu().numpy(), feature=None, opacity=sc.opacity.cpu().numpy())
+    t0 = time.perf_counter()
+    st = o.forward(**kw, **arrs, stages="bin")
+    t_geom = time.perf_counter() - t0
+    R = st["num_rendered"]
+    if tile_step is None:  # ~60 ns per pair evaluated (fwd+bwd) per core as a planning figure
+        est_full = 256.0 * R * 60e-9 / max(1, os.cpu_count() or 1)
+        tile_step = max(1, int(round(est_full / max(1.0, budget_s - t_geom))))
+    t0 = time.perf_counter()
+    st = o.forward(**kw, **arrs, tile_step=tile_step, tile_offset=0)
+    t_fwd_all = time.perf_counter() - t0  # includes the geometry stages again
+    t0 = time.perf_counter()
+    o.backward(st, sc.grads["dL_dout_feature"].cpu().numpy(), sc.grads["dL_dout_depth"].cpu().numpy() if sc.rich_info else None,
+               sc.grads["dL_dout_normal"].cpu().numpy() if sc.rich_info else None)
+    t_bwd = time.perf_counter() - t0
+    t_comp_f = max(0.0, t_fwd_all - t_geom)
+    frame_s = t_geom + tile_step * t_comp_f + tile_step * t_bwd
+    return {"value": 1.0 / frame_s, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"CPU oracle port (C, OpenMP): per-triangle stages + binning of the full scene ({t_geom:.1f}s) + composite fwd+bwd on "
+                      f"every {tile_step}-th tile ({t_comp_f:.1f}s + {t_bwd:.1f}s), extrapolated x{tile_step}",
+            "seconds_measured": t_geom + t_fwd_all + t_bwd}
+
+
+# ----------------------------------------------------------------------------------------------------- main
+def timed_region(step, steps, warmup, dev, world):
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    return ms
+
+
+def wall_region(fn, steps, warmup, dev):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize(dev)
+    return (time.perf_counter() - t0) * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "rasterizer fwd+bwd frames/sec @1080p, 1.5M tris; HBM GB/s vs roofline"
+    base = {"metric": metric, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+
+    sc = scene_for(a.config)
+    cfg = {"workload": f"{a.config}: P={sc.P} triangles, {sc.cam['image_width']}x{sc.cam['image_height']}, SH degree {sc.sh_degree} "
+                       f"(M={sc.shs.shape[1]}), rich_info={sc.rich_info}, gamma={sc.gamma}, fwd+bwd",
+           "P": sc.P, "width": sc.cam["image_width"], "height": sc.cam["image_height"], "sh_degree": sc.sh_degree,
+           "l2_policy": "inputs larger than L2 (SH 288 MB + 120 MB raster records + instance lists >> 126 MB L2); no explicit flush",
+           "parallelism": "single GPU" if a.gpus == 1 else f"image-space tile sharding x{a.gpus} (tile % N == rank) + NCCL all-reduce"}
+
+    if not torch.cuda.is_available():
+        if a.impl == "reference" and rank == 0:
+            cb = cpu_oracle_baseline(sc)
+            line = dict(base, impl="reference", value=cb["value"], ms_per_step=1e3 / cb["value"], config=cfg, cpu_baseline=cb,
+                        e2e={"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0,
+                        note="no CUDA device and no loadable reference extension: CPU oracle port on a bounded sample")
+            print(json.dumps(line))
+            return
+        raise SystemExit("bench.py needs a CUDA device: the rasterizer has no CPU path")
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    # ------------------------------------------------------------------------------ reference arm
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import build_ref
+
+        ref = None
+        try:
+            ref = build_ref.load()
+        except Exception as ex:  # noqa: BLE001
+            print(f"[bench] reference extension failed to load: {ex}", file=sys.stderr)
+        if ref is None:
+            cb = cpu_oracle_baseline(sc)
+            line = dict(base, impl="reference", value=cb["value"], ms_per_step=1e3 / cb["value"], config=cfg, cpu_baseline=cb, n_gpus=1,
+                        e2e={"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0,
+                        note="oracle/_ref not loadable: CPU oracle port on a bounded sample")
+            print(json.dumps(line))
+            return
+        step = ReferenceStep(sc, dev, ref)
+        smp = ClockSampler(local_rank)
+        smp.start()
+        ms = timed_region(step, a.steps, a.warmup, dev, 1)
+        clocks = smp.stop()
+        fps = a.steps / (ms / 1e3)
+        host = pinned_host_buffers(sc, all_host=False)
+        ms_e = wall_region(lambda: step.e2e_step(host), max(3, a.steps // 2), 2, dev)
+        e2e_fps = max(3, a.steps // 2) / (ms_e / 1e3)
+        h2d = sum(host[k].numel() * 4 for k in ("viewmatrix", "projmatrix", "campos", "background", "gt"))
+        line = dict(base, impl="reference", n_gpus=1, value=fps, ms_per_step=ms / a.steps, config=cfg, clocks=clocks,
+                    e2e={"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                    cpu_baseline={"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference",
+                                  "sample": "full workload on the reference's own CUDA build (oracle/_ref, sm_100): the reference has no CPU "
+                                            "implementation of this path; 1 host thread drives the GPU"},
+                    gpu_launches=0, note="unmodified reference extension through its pybind entry points; none of our kernels on this path")
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------------------------ our arm
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from triangle_splatting_b200 import distributed as tsd
+
+        tsd.enable_tile_sharding()
+    from triangle_splatting_b200 import _lib
+
+    lib = _lib.load()
+    step = OursStep(sc, dev)
+    out = step()  # first call: also gives V, R for the byte model
+    torch.cuda.synchronize(dev)
+    radii = out[1]
+    V = int((radii > 0).sum().item())
+    N = sc.cam["image_width"] * sc.cam["image_height"]
+    T = ((sc.cam["image_width"] + 15) // 16) * ((sc.cam["image_height"] + 15) // 16)
+
+    # R of the whole frame (each rank only knows its shard's R)
+    from triangle_splatting_b200 import _C as tsC  # noqa: N811
+    R_local = None
+    lib.ts2d_profile_enable(1)
+    smp = ClockSampler(local_rank)
+    smp.start()
+    ms = timed_region(step, a.steps, a.warmup, dev, world)
+    clocks = smp.stop()
+    st_ms = (ctypes.c_float * 6)()
+    st_n = (ctypes.c_int32 * 6)()
+    lib.ts2d_profile_read(st_ms, st_n)
+    lib.ts2d_profile_enable(0)
+    n_calls = a.steps + a.warmup
+    stage_ms = {s: st_ms[i] / max(1, st_n[i]) for i, s in enumerate(_lib.STAGES)}
+    fps = a.steps / (ms / 1e3)
+
+    if rank == 0:
+        # R (num_rendered) of this rank's shard: one forward through the raw _C API
+        s, c = step.sc, step.sc.cam
+        fa = (c["image_width"], c["image_height"], c["tanfovx"], c["tanfovy"], c["viewmatrix"], c["projmatrix"], c["campos"], s.sh_degree,
+              s.gamma, 1.0, s.background_depth, s.background, s.vertex, s.shs, torch.Tensor([]), s.opacity, s.back_culling, s.rich_info, False)
+        R_local = int(tsC.rasterize_triangles(*fa, shard=(rank, world) if world > 1 else (0, 1))[0])
+    R_total = R_local * world if R_local is not None else None  # interleaved tiles: shards are balanced to <1%
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        K = (sc.sh_degree + 1) ** 2
+        ab = algorithmic_bytes(sc.P, V, R_local, N // world, T // world, K, sc.shs.shape[1], sc.rich_info)
+        dom = max(stage_ms, key=lambda k: stage_ms[k])
+        stages = {k: {"ms": round(stage_ms[k], 4), "alg_bytes": ab[k], "gbs": round(ab[k] / (stage_ms[k] * 1e-3) / 1e9, 1) if stage_ms[k] > 0 else None,
+                      "share": round(stage_ms[k] / max(1e-9, sum(stage_ms.values())), 3)} for k in stage_ms}
+        ach = ab[dom] / (stage_ms[dom] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": {"render_fwd": "k_render_fwd", "render_bwd": "k_render_bwd", "preprocess": "k_preprocess",
+                                            "preprocess_bwd": "k_preprocess_bwd", "binning": "k_emit + cub radix + k_ranges",
+                                            "order_scan": "cub radix + scan"}[dom],
+                "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5), "traffic": None, "peak_source": peak_src,
+                "note": "per-pixel composite is FP32/MUFU-issue bound, not HBM bound (SURVEY.md section 8d); per-stage figures in `stages`",
+                "whole_frame_gbs": round(sum(ab.values()) / (ms / a.steps * 1e-3) / 1e9, 1)}
+        own_per_step = 7  # k_preprocess, k_set_header, k_emit, k_ranges, k_render_fwd, k_render_bwd, k_preprocess_bwd
+        line = dict(base, impl="ours", value=fps, ms_per_step=ms / a.steps, config=cfg, clocks=clocks, roofline=roof, stages=stages,
+                    gpu_launches=own_per_step * a.steps,
+                    library_launches_note="plus ~14 CUB radix-sort/scan kernels and 4 memsets per step (toolkit library, not counted)",
+                    scene={"P": sc.P, "visible": V, "num_rendered_rank0": R_local, "num_rendered_est": R_total, "tiles": T, "pixels": N})
+
+    # e2e (all ranks participate: the step contains collectives when sharded)
+    if not a.no_e2e:
+        host = pinned_host_buffers(sc, all_host=(world == 1))
+        k_e = max(3, a.steps // 2)
+        if world > 1:
+            dist.barrier()
+        ms_e = wall_region(lambda: step.e2e_step(host), k_e, 2, dev)
+        if world > 1:
+            t = torch.tensor([ms_e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        if rank == 0:
+            h2d = sum(host[k].numel() * 4 for k in ("viewmatrix", "projmatrix", "campos", "background", "gt"))
+            line["e2e"] = {"value": k_e / (ms_e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                           "what": "camera + GT image H2D (pinned) -> TriangleRasterizer fwd -> L1 loss -> backward -> loss.item()"}
+        if world == 1:
+            ms_a = wall_region(lambda: step.e2e_all_host_step(host), 3, 1, dev)
+            h2d_all = sum(host[k].numel() * 4 for k in ("viewmatrix", "projmatrix", "campos", "background", "vertex", "shs", "opacity",
+                                                         "g_feature", "g_depth", "g_normal"))
+            d2h_all = sum(host[k].numel() * 4 for k in ("o_image", "o_gv", "o_gs", "o_go", "o_gc"))
+            line["e2e_all_host"] = {"value": 3 / (ms_a / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
+                                    "what": "every parameter + upstream gradient H2D, image + all gradients D2H, per step (PCIe bound)"}
+
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_oracle_baseline(sc)
+        except Exception as ex:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -172,6 +172,22 @@ int ts2d_export_binning(const void *geometry_state, const void *binning_state, c
 int ts2d_export_image(const void *image_state, int32_t width, int32_t height, uint32_t *n_contrib /*[H][W]*/, float *final_T /*[H][W]*/,
                       void *stream);
 
+/* ---- per-stage device timing (measurement only; used by bench.py for the roofline object) ----
+ * When enabled, every stage launched by the three entry points above is bracketed by CUDA events on
+ * the caller's stream.  ts2d_profile_read() synchronises, adds up the elapsed time per stage over
+ * all calls since the last read (ms) and the number of launches, then resets. */
+enum {
+    TS2D_STAGE_PREPROCESS = 0,     /* K1  preprocess + SH colour */
+    TS2D_STAGE_ORDER_SCAN = 1,     /* K2/K3 depth sort of P keys + scan */
+    TS2D_STAGE_BINNING = 2,        /* K4-K6 emit, tile radix sort, ranges */
+    TS2D_STAGE_RENDER_FWD = 3,     /* K7 */
+    TS2D_STAGE_RENDER_BWD = 4,     /* K8 */
+    TS2D_STAGE_PREPROCESS_BWD = 5, /* K9 */
+    TS2D_NUM_STAGES = 6
+};
+int ts2d_profile_enable(int enable);
+int ts2d_profile_read(float *ms_out /*[TS2D_NUM_STAGES]*/, int32_t *launches_out /*[TS2D_NUM_STAGES]*/);
+
 #ifdef __cplusplus
 }
 #endif

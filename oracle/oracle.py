@@ -34,7 +34,7 @@ def build(force: bool = False) -> None:
         out = lib_path(kind)
         if out.exists() and not force and out.stat().st_mtime >= SRC.stat().st_mtime:
             continue
-        cmd = ["gcc", "-O2", "-fPIC", "-shared", "-std=c11", "-ffp-contract=off", "-fno-fast-math", f"-DREAL={real}",
+        cmd = ["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-std=c11", "-ffp-contract=off", "-fno-fast-math", f"-DREAL={real}",
                str(SRC), "-o", str(out), "-lm"]
         subprocess.run(cmd, check=True)
 
@@ -63,7 +63,7 @@ class Oracle:
     # ------------------------------------------------------------------ forward
     def forward(self, *, image_width, image_height, tanfovx, tanfovy, viewmatrix, projmatrix, campos, sh_degree, gamma,
                 background_depth, background, vertex, shs, feature, opacity, back_culling=False, rich_info=False,
-                scale_modifier=1.0, debug=False, stages="all") -> dict:
+                scale_modifier=1.0, debug=False, stages="all", tile_step=1, tile_offset=0) -> dict:
         W, H = int(image_width), int(image_height)
         vertex = self._r(vertex)
         P = vertex.shape[0]
@@ -129,7 +129,8 @@ class Oracle:
             W, H, C, cr(gamma), int(bool(rich_info)), _p(st["ranges"]), _p(st["point_list"]), _p(st["v2d"]), _p(st["area2"]),
             _p(st["normal_view"]), _p(st["v_depth"]), _p(np.ascontiguousarray(st["feature"])), _p(opacity), cr(background_depth), _p(bg),
             _p(st["final_T"]), _p(st["n_contrib"]), _p(st["out_feature"]), _p(st["out_depth"]), _p(st["out_normal"]), _p(st["contrib_sum"]),
-            _p(st["contrib_max"]), P)
+            _p(st["contrib_max"]), P, int(tile_step), int(tile_offset))
+        st["tile_step"], st["tile_offset"] = int(tile_step), int(tile_offset)
         return st
 
     # ------------------------------------------------------------------ backward
@@ -154,7 +155,7 @@ class Oracle:
             W, H, C, cr(st["gamma"]), int(rich), _p(st["ranges"]), _p(st["point_list"]), _p(st["v2d"]), _p(st["area2"]), _p(st["normal_view"]),
             _p(st["v_depth"]), _p(feat), _p(st["opacity"]), cr(st["background_depth"]), _p(st["background"]), _p(st["final_T"]),
             _p(st["n_contrib"]), _p(g_img), _p(g_dep), _p(g_nrm), P, _p(out["g_v2d"]), _p(out["g_normal"]), _p(out["g_vdepth"]),
-            _p(out["g_feature"]), _p(out["g_opacity"]))
+            _p(out["g_feature"]), _p(out["g_opacity"]), int(st.get("tile_step", 1)), int(st.get("tile_offset", 0)))
         g_rgb = out["g_feature"] if st["use_shs"] else np.zeros((P, 3))
         self.lib.ts2d_oracle_preprocess_bwd(
             W, H, P, st["D"], M, int(st["use_shs"]), int(rich), cr(st["tanfovx"]), cr(st["tanfovy"]), _p(st["viewmatrix"]),

@@ -342,16 +342,22 @@ static inline int eval_pair(const real *v, real area2, real op, real gamma, real
 int ts2d_oracle_render(int W, int H, int C, real gamma, int rich_info, const uint32_t *ranges, const uint32_t *list, const real *v2d,
                        const real *area2, const real *normal_view, const real *v_depth, const real *feature, const real *opacity,
                        real background_depth, const real *background, real *final_T, uint32_t *n_contrib, real *out_feature,
-                       real *out_depth, real *out_normal, real *contrib_sum, real *contrib_max, int P)
+                       real *out_depth, real *out_normal, real *contrib_sum, real *contrib_max, int P, int tile_step, int tile_offset)
 {
+    /* tile_step/tile_offset: composite only tiles with tile_id % tile_step == tile_offset (1/0 = all).  Used for the
+     * bounded cpu_baseline sample and to emulate image-space tile sharding in the CPU (gloo) tests. */
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     double *csum = NULL;
     if (rich_info) {
         csum = (double *)calloc((size_t)(P ? P : 1), sizeof(double));
         for (int i = 0; i < P; i++) contrib_max[i] = 0;
     }
-    for (int ty = 0; ty < gy; ty++)
-        for (int tx = 0; tx < gx; tx++) {
+    if (tile_step < 1) tile_step = 1;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int tile = 0; tile < gx * gy; tile++) {
+        const int ty = tile / gx, tx = tile % gx;
+        if (tile % tile_step != tile_offset) continue;
+        {
             const uint32_t beg = ranges[2 * (ty * gx + tx)], end = ranges[2 * (ty * gx + tx) + 1];
             for (int ly = 0; ly < TILE; ly++)
                 for (int lx = 0; lx < TILE; lx++) {
@@ -371,7 +377,9 @@ int ts2d_oracle_render(int W, int H, int C, real gamma, int rich_info, const uin
                         const real contrib = pr.alpha * T;
                         for (int ch = 0; ch < C; ch++) acc[ch] += feature[(size_t)id * C + ch] * contrib;
                         if (rich_info) {
+#pragma omp atomic
                             csum[id] += (double)contrib;
+#pragma omp critical(ts2d_cmax)
                             if (contrib > contrib_max[id]) contrib_max[id] = contrib;
                             accn.x += normal_view[3 * id] * contrib; accn.y += normal_view[3 * id + 1] * contrib; accn.z += normal_view[3 * id + 2] * contrib;
                             const real d = v_depth[3 * id] * pr.a1 + v_depth[3 * id + 1] * pr.a2 + v_depth[3 * id + 2] * pr.a3;
@@ -389,6 +397,7 @@ int ts2d_oracle_render(int W, int H, int C, real gamma, int rich_info, const uin
                     }
                 }
         }
+    }
     if (rich_info) {
         for (int i = 0; i < P; i++) contrib_sum[i] = (real)csum[i];
         free(csum);
@@ -403,16 +412,20 @@ int ts2d_oracle_render_bwd(int W, int H, int C, real gamma, int rich_info, const
                            real background_depth, const real *background, const real *final_T, const uint32_t *n_contrib,
                            const real *dL_dout_feature, const real *dL_dout_depth, const real *dL_dout_normal, int P,
                            double *g_v2d /*[P][3][2]*/, double *g_normal /*[P][3]*/, double *g_vdepth /*[P][3]*/, double *g_feature /*[P][C]*/,
-                           double *g_opacity /*[P]*/)
+                           double *g_opacity /*[P]*/, int tile_step, int tile_offset)
 {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    if (tile_step < 1) tile_step = 1;
     memset(g_v2d, 0, sizeof(double) * 6 * P);
     memset(g_normal, 0, sizeof(double) * 3 * P);
     memset(g_vdepth, 0, sizeof(double) * 3 * P);
     memset(g_feature, 0, sizeof(double) * (size_t)C * P);
     memset(g_opacity, 0, sizeof(double) * P);
-    for (int ty = 0; ty < gy; ty++)
-        for (int tx = 0; tx < gx; tx++) {
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int tile = 0; tile < gx * gy; tile++) {
+        const int ty = tile / gx, tx = tile % gx;
+        if (tile % tile_step != tile_offset) continue;
+        {
             const uint32_t beg = ranges[2 * (ty * gx + tx)], end = ranges[2 * (ty * gx + tx) + 1];
             for (int ly = 0; ly < TILE; ly++)
                 for (int lx = 0; lx < TILE; lx++) {
@@ -443,18 +456,29 @@ int ts2d_oracle_render_bwd(int W, int H, int C, real gamma, int rich_info, const
                         real dL_dcontrib = 0;
                         v3 dL_da = v3_make(0, 0, 0);
                         for (int ch = 0; ch < C; ch++) {
+#pragma omp atomic
                             g_feature[(size_t)id * C + ch] += (double)(gpix[ch] * contrib);
                             const real feat = feature[(size_t)id * C + ch];
                             dL_dcontrib += gpix[ch] * (feat - acc[ch]);
                             acc[ch] = pr.alpha * feat + ((real)1.0f - pr.alpha) * acc[ch];
                         }
                         if (rich_info) {
-                            g_normal[3 * id] += (double)(gn.x * contrib); g_normal[3 * id + 1] += (double)(gn.y * contrib); g_normal[3 * id + 2] += (double)(gn.z * contrib);
+#pragma omp atomic
+                            g_normal[3 * id] += (double)(gn.x * contrib);
+#pragma omp atomic
+                            g_normal[3 * id + 1] += (double)(gn.y * contrib);
+#pragma omp atomic
+                            g_normal[3 * id + 2] += (double)(gn.z * contrib);
                             const v3 nrm = v3_make(normal_view[3 * id], normal_view[3 * id + 1], normal_view[3 * id + 2]);
                             dL_dcontrib += v3_dot(gn, v3_sub(nrm, accn));
                             accn = v3_add(v3_scale(nrm, pr.alpha), v3_scale(accn, (real)1.0f - pr.alpha));
                             const real dL_ddepth = gd * contrib;
-                            g_vdepth[3 * id] += (double)(dL_ddepth * pr.a1); g_vdepth[3 * id + 1] += (double)(dL_ddepth * pr.a2); g_vdepth[3 * id + 2] += (double)(dL_ddepth * pr.a3);
+#pragma omp atomic
+                            g_vdepth[3 * id] += (double)(dL_ddepth * pr.a1);
+#pragma omp atomic
+                            g_vdepth[3 * id + 1] += (double)(dL_ddepth * pr.a2);
+#pragma omp atomic
+                            g_vdepth[3 * id + 2] += (double)(dL_ddepth * pr.a3);
                             const v3 vd = v3_make(v_depth[3 * id], v_depth[3 * id + 1], v_depth[3 * id + 2]);
                             dL_da = v3_add(dL_da, v3_scale(vd, dL_ddepth));
                             const real dep = vd.x * pr.a1 + vd.y * pr.a2 + vd.z * pr.a3;
@@ -486,11 +510,24 @@ int ts2d_oracle_render_bwd(int W, int H, int C, real gamma, int rich_info, const
                         const v2 g2 = v2_add(v2_add(v2_scale(da1_d2, dL_da.x), v2_scale(da2_d2, dL_da.y)), v2_scale(da3_d2, dL_da.z));
                         const v2 g3 = v2_add(v2_add(v2_scale(da1_d3, dL_da.x), v2_scale(da2_d3, dL_da.y)), v2_scale(da3_d3, dL_da.z));
                         double *gv = g_v2d + 6 * (size_t)id;
-                        gv[0] += (double)g1.x; gv[1] += (double)g1.y; gv[2] += (double)g2.x; gv[3] += (double)g2.y; gv[4] += (double)g3.x; gv[5] += (double)g3.y;
+#pragma omp atomic
+                        gv[0] += (double)g1.x;
+#pragma omp atomic
+                        gv[1] += (double)g1.y;
+#pragma omp atomic
+                        gv[2] += (double)g2.x;
+#pragma omp atomic
+                        gv[3] += (double)g2.y;
+#pragma omp atomic
+                        gv[4] += (double)g3.x;
+#pragma omp atomic
+                        gv[5] += (double)g3.y;
+#pragma omp atomic
                         g_opacity[id] += (double)(dL_dalpha * pr.G); /* unconditional, :490 */
                     }
                 }
         }
+    }
     return 0;
 }
 

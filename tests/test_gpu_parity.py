@@ -1,0 +1,204 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every call goes through the
+reference-shaped host API (triangle_splatting_b200._C) and therefore the C ABI of libts2d.so.
+
+Bars (BASELINE.json north_star / SURVEY.md section 8d):
+  integers (radii, tiles_touched, rects, sorted (key,value) list, ranges, num_rendered, n_contrib) : bit-exact
+  rendered pixels / rich outputs / all five gradients                                        : <= 1e-5 relative
+against (1) the committed golden vectors produced by the reference's own CUDA build,
+(2) the live reference extension when oracle/_ref is loadable, (3) the CPU oracle.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import harness
+from harness import GRAD_KEYS, IMAGE_KEYS, INT_KEYS, STATE_FLOAT_KEYS, assert_close_modulo_flips, mismatch_count, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # relative, north_star
+
+
+def _golden(name):
+    p = os.path.join(harness.GOLDEN_DIR, name + ".npz")
+    if not os.path.exists(p):
+        pytest.skip(f"golden fixture {p} missing")
+    return dict(np.load(p))
+
+
+def _check_against(ours, ref, rich, what, float_state_exact=True):
+    for k in INT_KEYS:
+        if k in ref and k in ours:
+            assert mismatch_count(ours[k], ref[k]) == 0, f"{what}: integer field {k} differs"
+    for k in STATE_FLOAT_KEYS:
+        if k in ref and k in ours and (rich or k not in ("normal_view", "v_depth")):
+            if float_state_exact:
+                assert mismatch_count(np.asarray(ours[k]).view(np.uint32), np.asarray(ref[k]).view(np.uint32)) == 0, f"{what}: state {k} not bit-equal"
+            else:
+                assert rel_err(ours[k], ref[k]) <= TOL, f"{what}: state {k}"
+    for k in IMAGE_KEYS + GRAD_KEYS:
+        if k in ref and k in ours:
+            e = rel_err(ours[k], ref[k])
+            assert e <= TOL, f"{what}: {k} rel err {e:.3e} > {TOL}"
+
+
+@pytest.mark.parametrize("name", list(harness.GOLDEN_SCENES))
+def test_vs_golden(name, cuda_device):
+    sc = harness.golden_scene(name)
+    gold = _golden(name)
+    chk = sc.vertex.double().sum().item() + sc.opacity.double().sum().item()
+    assert abs(chk - float(gold["input_checksum"])) < 1e-9 * max(1.0, abs(chk)), "scene regeneration differs from the golden run"
+    ours = harness.run_ours(sc, cuda_device)
+    _check_against(ours, gold, sc.rich_info, f"golden[{name}]")
+
+
+@pytest.mark.parametrize("name", list(harness.GOLDEN_SCENES))
+def test_vs_live_reference(name, cuda_device):
+    ref = harness.load_reference()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    sc = harness.golden_scene(name)
+    theirs = harness.run_reference(sc, cuda_device, ref=ref)
+    ours = harness.run_ours(sc, cuda_device)
+    _check_against(ours, theirs, sc.rich_info, f"live[{name}]")
+
+
+@pytest.mark.parametrize("name", list(harness.GOLDEN_SCENES))
+def test_vs_oracle(name, cuda_device):
+    """CUDA path vs the CPU restatement (fp32 mirror): integers may differ only where a float sits within
+    rounding of a decision boundary (the oracle has no FMA contraction), so a tiny mismatch budget is allowed there."""
+    sc = harness.golden_scene(name)
+    ours = harness.run_ours(sc, cuda_device)
+    orc = harness.run_oracle(sc, "f32")
+    P = sc.P
+    assert mismatch_count(ours["radii"], orc["radii"]) <= max(1, P // 1000)
+    if mismatch_count(ours["point_list"], orc["point_list"]) == 0:
+        for k in IMAGE_KEYS + GRAD_KEYS:
+            if k in orc and k in ours:
+                assert_close_modulo_flips(ours[k], orc[k], f"oracle[{name}].{k}")
+
+
+def test_config_c1_forward_matches_reference_or_oracle(cuda_device):
+    """BASELINE configs[0]: 10k triangles, 256x256, SH deg 0, forward-only pixel match."""
+    from triangle_splatting_b200.scenes import make_config
+
+    sc = make_config("C1")
+    ours = harness.run_ours(sc, cuda_device, backward=False)
+    ref = harness.load_reference()
+    if ref is not None:
+        theirs = harness.run_reference(sc, cuda_device, backward=False, ref=ref)
+        _check_against(ours, theirs, sc.rich_info, "C1 live")
+    orc = harness.run_oracle(sc, "f32", backward=False)
+    assert mismatch_count(ours["point_list"], orc["point_list"]) <= 8
+    assert_close_modulo_flips(ours["out_feature"], orc["out_feature"], "C1 oracle out_feature")
+
+
+def test_empty_and_degenerate_inputs(cuda_device):
+    from triangle_splatting_b200 import _C
+    from triangle_splatting_b200.scenes import make_scene
+
+    dev = cuda_device
+    # P == 0: zero outputs, empty state (extension_interface.cu:130)
+    sc = make_scene("e", 0, 64, 48, sh_degree=0).to(dev)
+    fwd = _C.rasterize_triangles(*harness._fwd_args(sc))
+    assert fwd[0] == 0 and fwd[1].shape == (3, 48, 64) and float(fwd[1].abs().sum()) == 0.0
+    # everything culled (behind the camera): image == background, R == 0, grads zero
+    sc = make_scene("b", 500, 64, 48, sh_degree=0, seed=2)
+    sc.vertex[..., 2] -= 100.0
+    ours = harness.run_ours(sc, dev)
+    assert int(ours["num_rendered"]) == 0 and int((ours["radii"] > 0).sum()) == 0
+    bg = sc.background.numpy()[:, None, None]
+    assert np.array_equal(ours["out_feature"], np.broadcast_to(bg, ours["out_feature"].shape))
+    assert float(np.abs(ours["dL_dvertex"]).sum()) == 0.0
+    # ragged image (not a multiple of the tile size) and one huge triangle covering every tile
+    sc = make_scene("r", 50, 75, 37, sh_degree=0, seed=3, rho_px=400.0)
+    ours = harness.run_ours(sc, dev)
+    orc = harness.run_oracle(sc, "f32")
+    assert mismatch_count(ours["radii"], orc["radii"]) == 0
+    assert_close_modulo_flips(ours["out_feature"], orc["out_feature"], "ragged oracle out_feature")
+
+
+def test_error_behaviour(cuda_device):
+    """Argument errors raise RuntimeError like the reference's AT_ERROR paths (extension_interface.cu:53-81)."""
+    from triangle_splatting_b200 import TriangleRasterizationSettings, TriangleRasterizer, _C
+    from triangle_splatting_b200.scenes import make_scene
+
+    sc = make_scene("x", 10, 32, 32, sh_degree=0).to(cuda_device)
+    args = list(harness._fwd_args(sc))
+    bad = list(args)
+    bad[12] = sc.vertex.reshape(-1, 9)
+    with pytest.raises(RuntimeError, match="vertex must have dimensions"):
+        _C.rasterize_triangles(*bad)
+    bad = list(args)
+    bad[8] = -1.0
+    with pytest.raises(RuntimeError, match="gamma"):
+        _C.rasterize_triangles(*bad)
+    bad = list(args)
+    bad[11] = torch.zeros(2, device=cuda_device)
+    with pytest.raises(RuntimeError, match="background"):
+        _C.rasterize_triangles(*bad)
+    bad = list(args)
+    bad[12] = sc.vertex.transpose(1, 2)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        _C.rasterize_triangles(*bad)
+    r = TriangleRasterizer(TriangleRasterizationSettings(**sc.settings_kwargs()))
+    with pytest.raises(Exception, match="excatly one"):
+        r(vertex=sc.vertex, center2D=None, opacity=sc.opacity)
+
+
+def test_autograd_function_end_to_end(cuda_device):
+    """TriangleRasterizer.forward(...).backward() through torch.autograd, as diff_recon's TriangleRenderer calls it
+    (triangle_renderer.py:59-75), both rich_info settings (the reference crashes on rich_info=False backward)."""
+    from diff_triangle_rasterization_2D import TriangleRasterizationSettings, TriangleRasterizer
+
+    for name in ("sh0_plain", "sh3_rich"):
+        sc = harness.golden_scene(name).to(cuda_device)
+        vertex = sc.vertex.clone().requires_grad_(True)
+        shs = sc.shs.clone().requires_grad_(True)
+        opacity = sc.opacity.clone().requires_grad_(True)
+        center2D = torch.zeros((sc.P, 2), device=cuda_device, requires_grad=True)
+        rast = TriangleRasterizer(raster_settings=TriangleRasterizationSettings(**sc.settings_kwargs()))
+        out = rast.forward(vertex=vertex, center2D=center2D, opacity=opacity, shs=shs, feature=None)
+        assert len(out) == (6 if sc.rich_info else 2)
+        loss = (out[0] * sc.grads["dL_dout_feature"]).sum()
+        if sc.rich_info:
+            loss = loss + (out[2] * sc.grads["dL_dout_depth"]).sum() + (out[3] * sc.grads["dL_dout_normal"]).sum()
+        loss.backward()
+        direct = harness.run_ours(harness.golden_scene(name), cuda_device)
+        assert np.array_equal(out[0].detach().cpu().numpy(), direct["out_feature"])
+        for t, k in ((vertex, "dL_dvertex"), (shs, "dL_dshs"), (opacity, "dL_dopacity"), (center2D, "dL_dcenter2D")):
+            assert rel_err(t.grad.cpu().numpy(), direct[k]) <= TOL, k
+
+
+def test_properties_full_size(cuda_device):
+    """Size-independent properties at BASELINE's headline size (C3: 1.5M triangles, 1080p)."""
+    from triangle_splatting_b200.scenes import make_config
+
+    sc = make_config("C3")
+    ours = harness.run_ours(sc, cuda_device)
+    keys = ours["keys"]
+    assert np.all(keys[1:] >= keys[:-1]), "sorted keys must be non-decreasing"
+    same = keys[1:] == keys[:-1]
+    pl = ours["point_list"].astype(np.int64)
+    assert np.all(pl[1:][same] > pl[:-1][same]), "ties must stay in triangle-id order (stable sort)"
+    assert int(ours["num_rendered"]) == int(ours["tiles_touched"].sum(dtype=np.int64))
+    rng = ours["ranges"].astype(np.int64)
+    assert int((rng[:, 1] - rng[:, 0]).sum()) == int(ours["num_rendered"])
+    gx = (sc.cam["image_width"] + 15) // 16
+    tile_of_pix = (np.arange(sc.cam["image_height"])[:, None] // 16) * gx + (np.arange(sc.cam["image_width"])[None, :] // 16)
+    lens = (rng[:, 1] - rng[:, 0])[tile_of_pix]
+    assert np.all(ours["n_contrib"] <= lens)
+    fT = ours["final_T"]
+    assert np.all((fT >= 0) & (fT <= 1))
+    sat = ours["n_contrib"] < lens  # pixels that stopped early must be saturated
+    assert np.all(fT[sat] <= 1e-4)
+    assert np.all(ours["contrib_sum"] >= 0) and np.all(ours["contrib_max"] <= ours["contrib_sum"] * (1 + 1e-5) + 1e-12)
+    vis = ours["radii"] > 0
+    for k in GRAD_KEYS:
+        assert np.all(np.isfinite(ours[k])), k
+    assert float(np.abs(ours["dL_dvertex"][~vis]).sum()) == 0.0
+    # weights: sum_k contrib = 1 - T, so sum over triangles of contrib_sum == sum over pixels of (1 - final_T)
+    lhs, rhs = float(ours["contrib_sum"].astype(np.float64).sum()), float((1.0 - fT.astype(np.float64)).sum())
+    assert abs(lhs - rhs) <= 1e-4 * rhs

@@ -1,0 +1,115 @@
+"""CPU tests of the oracle itself: golden vectors from the reference's CUDA build, finite-difference
+gradient check (fp64), fp32-vs-fp64 agreement, structural properties, edge cases."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import harness
+from harness import GRAD_KEYS, IMAGE_KEYS, assert_close_modulo_flips, mismatch_count, rel_err
+from oracle.oracle import Oracle
+from triangle_splatting_b200.scenes import make_scene
+
+
+def _golden(name):
+    p = os.path.join(harness.GOLDEN_DIR, name + ".npz")
+    if not os.path.exists(p):
+        pytest.skip(f"golden fixture {p} missing")
+    return dict(np.load(p))
+
+
+@pytest.mark.parametrize("name", list(harness.GOLDEN_SCENES))
+def test_oracle_vs_reference_golden(name):
+    """Pins the oracle against the reference's own outputs (B200, oracle/_ref).  The fp32 mirror has no FMA
+    contraction and uses glibc powf/expf, so integer fields get a tiny mismatch budget (decision boundaries)
+    and floats a looser tolerance than the GPU-vs-GPU bar."""
+    sc = harness.golden_scene(name)
+    gold = _golden(name)
+    orc = harness.run_oracle(sc, "f32")
+    P = sc.P
+    budget = max(1, P // 1000)
+    assert mismatch_count(orc["radii"], gold["radii"]) <= budget
+    assert mismatch_count(orc["tiles_touched"], gold["tiles_touched"]) <= budget
+    assert abs(int(orc["num_rendered"]) - int(gold["num_rendered"])) <= 4 * budget
+    if int(orc["num_rendered"]) == int(gold["num_rendered"]):
+        assert mismatch_count(orc["point_list"], gold["point_list"]) <= 8 * budget
+        assert mismatch_count(orc["ranges"], gold["ranges"]) <= 8 * budget
+    if mismatch_count(orc["point_list"], gold["point_list"]) == 0:
+        bad = mismatch_count(orc["n_contrib"], gold["n_contrib"])
+        assert bad <= max(2, orc["n_contrib"].size // 2000), f"n_contrib differs on {bad} pixels"
+        for k in IMAGE_KEYS + GRAD_KEYS:
+            if k in gold and k in orc:
+                assert_close_modulo_flips(orc[k], gold[k], f"golden[{name}].{k}")
+    o64 = harness.run_oracle(sc, "f64")
+    for k in ("out_feature",) + GRAD_KEYS:
+        if k in gold:
+            assert_close_modulo_flips(gold[k], o64[k], f"golden-vs-f64[{name}].{k}")
+
+
+def test_fd_gradients_fp64():
+    sc = make_scene("t", 200, 48, 40, sh_degree=2, rich_info=True, geometry_grads=True, seed=5, rho_px=4.0)
+    o = Oracle("f64")
+    kw = sc.settings_kwargs()
+    kw.pop("debug")
+    kw = {k: (v.numpy().astype(np.float64) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()}
+    V, S, O = (t.numpy().astype(np.float64) for t in (sc.vertex, sc.shs, sc.opacity))
+    gf, gd, gn = (sc.grads[k].numpy().astype(np.float64) for k in ("dL_dout_feature", "dL_dout_depth", "dL_dout_normal"))
+
+    def loss(V, S, O):
+        st = o.forward(**kw, vertex=V, shs=S, feature=None, opacity=O)
+        return (st["out_feature"] * gf).sum() + (st["out_depth"] * gd).sum() + (st["out_normal"] * gn).sum(), st
+
+    _, st = loss(V, S, O)
+    g = o.backward(st, gf, gd, gn)
+    rng = np.random.default_rng(0)
+    vis = np.nonzero(st["radii"] > 0)[0]
+    for key, arr, grad in (("V", V, g["dL_dvertex"]), ("S", S, g["dL_dshs"]), ("O", O, g["dL_dopacity"])):
+        for _ in range(6):
+            i = rng.choice(vis)
+            idx = (i,) + tuple(rng.integers(0, s) for s in arr.shape[1:])
+            h = 1e-6 * max(1.0, abs(arr[idx]))
+            args = dict(V=V, S=S, O=O)
+            a, b = arr.copy(), arr.copy()
+            a[idx] += h
+            b[idx] -= h
+            args[key] = a
+            lp, _ = loss(**args)
+            args[key] = b
+            lm, _ = loss(**args)
+            fd = (lp - lm) / (2 * h)
+            assert fd == pytest.approx(grad[idx], rel=2e-4, abs=1e-9)
+
+
+def test_fp32_mirror_agrees_with_fp64_truth():
+    sc = make_scene("t", 1500, 96, 80, sh_degree=3, rich_info=True, geometry_grads=True, seed=7)
+    a, b = harness.run_oracle(sc, "f32"), harness.run_oracle(sc, "f64")
+    assert mismatch_count(a["radii"], b["radii"]) <= 2
+    if mismatch_count(a["point_list"], b["point_list"]) == 0:
+        for k in ("out_feature", "depth", "normal") + GRAD_KEYS:
+            assert_close_modulo_flips(a[k], b[k], k)
+
+
+def test_structure_and_edge_cases():
+    o = Oracle("f32")
+    sc = make_scene("t", 800, 75, 37, sh_degree=0, seed=3, rho_px=6.0)  # ragged image
+    r = harness.run_oracle(sc, "f32")
+    keys = r["keys"]
+    assert np.all(keys[1:] >= keys[:-1])
+    same = keys[1:] == keys[:-1]
+    pl = r["point_list"].astype(np.int64)
+    assert np.all(pl[1:][same] > pl[:-1][same])
+    assert int(r["num_rendered"]) == int(r["tiles_touched"].sum())
+    rng = r["ranges"].astype(np.int64)
+    assert int((rng[:, 1] - rng[:, 0]).sum()) == int(r["num_rendered"])
+    assert np.all(r["final_T"] <= 1.0) and np.all(r["final_T"] >= 0.0)
+    # empty input
+    sc0 = make_scene("e", 0, 32, 32)
+    r0 = harness.run_oracle(sc0, "f32")
+    assert int(r0["num_rendered"]) == 0 and r0["out_feature"].shape == (3, 32, 32)
+    # all culled: image == background
+    sc1 = make_scene("b", 100, 32, 32, seed=2)
+    sc1.vertex[..., 2] -= 100.0
+    r1 = harness.run_oracle(sc1, "f32")
+    assert int(r1["num_rendered"]) == 0
+    assert np.array_equal(r1["out_feature"], np.broadcast_to(sc1.background.numpy()[:, None, None], (3, 32, 32)))

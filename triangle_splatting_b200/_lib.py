@@ -63,7 +63,11 @@ SYMBOLS = {
     "ts2d_export_binning": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "ts2d_export_image": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ts2d_profile_enable": (C.c_int, [C.c_int]),
+    "ts2d_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
+
+STAGES = ("preprocess", "order_scan", "binning", "render_fwd", "render_bwd", "preprocess_bwd")
 
 
 def lib_path() -> Path:

@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(one, SOURCES))
-    cmd = [nvcc(), "-shared", "-o", str(LIB)] + [str(o) for o in objs] + ARCH + ["-cudart", "shared"]
+    cmd = [nvcc(), "-shared", "-o", str(LIB)] + [str(o) for o in objs] + ARCH + ["-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -3,9 +3,41 @@
 // (replaces Params::*State::fromChunk, R2D/src/param_struct.h:11-125).
 #include <stdio.h>
 
+#include <mutex>
+#include <vector>
+
 #include "ts2d_common.cuh"
 
 namespace {
+
+// ---- optional per-stage timing (ts2d_profile_*) ----
+struct StageEvent {
+    int stage;
+    cudaEvent_t a, b;
+};
+bool g_profile = false;
+std::vector<StageEvent> g_events;
+std::mutex g_profile_mu;
+
+struct StageTimer {
+    int stage;
+    cudaStream_t s;
+    cudaEvent_t a = nullptr, b = nullptr;
+    StageTimer(int stage_, cudaStream_t s_) : stage(stage_), s(s_)
+    {
+        if (!g_profile) return;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, s);
+    }
+    ~StageTimer()
+    {
+        if (!a) return;
+        cudaEventRecord(b, s);
+        std::lock_guard<std::mutex> lk(g_profile_mu);
+        g_events.push_back({stage, a, b});
+    }
+};
 
 struct Carver {
     char *p;
@@ -100,9 +132,13 @@ inline int dbg_sync(const ts2d_flags *f, cudaStream_t s)
     return (int)cudaGetLastError();
 }
 
-#define TS2D_STAGE(call)                 \
+#define TS2D_STAGE(stage_id, call)        \
     do {                                 \
-        int _r = (call);                 \
+        int _r;                          \
+        {                                \
+            StageTimer _t(stage_id, s);  \
+            _r = (call);                 \
+        }                                \
         if (_r) return _r;               \
         _r = dbg_sync(flags, s);         \
         if (_r) return _r;               \
@@ -193,8 +229,8 @@ int ts2d_forward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, con
     GeomState gs;
     if (carve_geometry(geometry_state, geom->P, &gs) > geometry_state_bytes) return TS2D_E_STATE_SIZE;
     cudaStream_t s = (cudaStream_t)stream;
-    TS2D_STAGE(ts2d_launch_preprocess(cam, geom, flags, radii, gs, s));
-    TS2D_STAGE(ts2d_launch_order_and_scan(geom->P, gs, num_rendered_host, s));
+    TS2D_STAGE(TS2D_STAGE_PREPROCESS, ts2d_launch_preprocess(cam, geom, flags, radii, gs, s));
+    TS2D_STAGE(TS2D_STAGE_ORDER_SCAN, ts2d_launch_order_and_scan(geom->P, gs, num_rendered_host, s));
     return 0;
 }
 
@@ -215,8 +251,8 @@ int ts2d_forward_render(const ts2d_camera *cam, const ts2d_geometry *geom, const
     if (carve_binning(binning_state, num_rendered, &bs) > binning_state_bytes) return TS2D_E_STATE_SIZE;
     if (carve_image(image_state, cam->width, cam->height, &is) > image_state_bytes) return TS2D_E_STATE_SIZE;
     cudaStream_t s = (cudaStream_t)stream;
-    TS2D_STAGE(ts2d_launch_binning(cam, flags, geom->P, num_rendered, gs, bs, is, s));
-    TS2D_STAGE(ts2d_launch_render_fwd(cam, geom, flags, gs, bs.tval[1], is, out, s));
+    TS2D_STAGE(TS2D_STAGE_BINNING, ts2d_launch_binning(cam, flags, geom->P, num_rendered, gs, bs, is, s));
+    TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd(cam, geom, flags, gs, bs.tval[1], is, out, s));
     return 0;
 }
 
@@ -239,8 +275,8 @@ int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_
     carve_binning(const_cast<void *>(binning_state), num_rendered, &bs);
     carve_image(const_cast<void *>(image_state), cam->width, cam->height, &is);
     cudaStream_t s = (cudaStream_t)stream;
-    TS2D_STAGE(ts2d_launch_render_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
-    TS2D_STAGE(ts2d_launch_preprocess_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
+    TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
+    TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
     return 0;
 }
 
@@ -289,6 +325,35 @@ int ts2d_export_image(const void *image_state, int32_t W, int32_t H, uint32_t *n
     if (n_contrib) TS2D_CUDA_TRY(cudaMemcpyAsync(n_contrib, is.n_contrib, sizeof(uint32_t) * N, cudaMemcpyDeviceToDevice, s));
     if (final_T) TS2D_CUDA_TRY(cudaMemcpyAsync(final_T, is.final_T, sizeof(float) * N, cudaMemcpyDeviceToDevice, s));
     return 0;
+}
+
+int ts2d_profile_enable(int enable)
+{
+    std::lock_guard<std::mutex> lk(g_profile_mu);
+    g_profile = enable != 0;
+    return 0;
+}
+
+int ts2d_profile_read(float *ms_out, int32_t *launches_out)
+{
+    std::lock_guard<std::mutex> lk(g_profile_mu);
+    for (int i = 0; i < TS2D_NUM_STAGES; i++) {
+        if (ms_out) ms_out[i] = 0.0f;
+        if (launches_out) launches_out[i] = 0;
+    }
+    int rc = 0;
+    for (auto &e : g_events) {
+        float ms = 0.0f;
+        cudaError_t err = cudaEventSynchronize(e.b);
+        if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e.a, e.b);
+        if (err != cudaSuccess) rc = (int)err;
+        if (ms_out) ms_out[e.stage] += ms;
+        if (launches_out) launches_out[e.stage] += 1;
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    g_events.clear();
+    return rc;
 }
 
 }  // extern "C"
