@@ -265,9 +265,13 @@ def cpu_oracle_baseline(sc, tile_step=None, budget_s=20.0):
     st = o.forward(**kw, **arrs, stages="bin")
     t_geom = time.perf_counter() - t0
     R = st["num_rendered"]
-    if tile_step is None:  # ~60 ns per pair evaluated (fwd+bwd) per core as a planning figure
-        est_full = 256.0 * R * 60e-9 / max(1, os.cpu_count() or 1)
-        tile_step = max(1, int(round(est_full / max(1.0, budget_s - t_geom))))
+    if tile_step is None:  # pilot on every 256th tile, then size the sample for ~budget_s of composite work
+        t0 = time.perf_counter()
+        stp = o.forward(**kw, **arrs, tile_step=256, tile_offset=0)
+        o.backward(stp, sc.grads["dL_dout_feature"].cpu().numpy(), sc.grads["dL_dout_depth"].cpu().numpy() if sc.rich_info else None,
+                   sc.grads["dL_dout_normal"].cpu().numpy() if sc.rich_info else None)
+        t_pilot = max(1e-3, time.perf_counter() - t0 - t_geom)
+        tile_step = int(min(256, max(1, round(256.0 * t_pilot / max(1.0, budget_s - 2 * t_geom)))))
     t0 = time.perf_counter()
     st = o.forward(**kw, **arrs, tile_step=tile_step, tile_offset=0)
     t_fwd_all = time.perf_counter() - t0  # includes the geometry stages again

@@ -348,8 +348,10 @@ int ts2d_oracle_render(int W, int H, int C, real gamma, int rich_info, const uin
      * bounded cpu_baseline sample and to emulate image-space tile sharding in the CPU (gloo) tests. */
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     double *csum = NULL;
+    uint32_t *cmax_bits = NULL;
     if (rich_info) {
         csum = (double *)calloc((size_t)(P ? P : 1), sizeof(double));
+        cmax_bits = (uint32_t *)calloc((size_t)(P ? P : 1), sizeof(uint32_t));
         for (int i = 0; i < P; i++) contrib_max[i] = 0;
     }
     if (tile_step < 1) tile_step = 1;
@@ -379,8 +381,14 @@ int ts2d_oracle_render(int W, int H, int C, real gamma, int rich_info, const uin
                         if (rich_info) {
 #pragma omp atomic
                             csum[id] += (double)contrib;
-#pragma omp critical(ts2d_cmax)
-                            if (contrib > contrib_max[id]) contrib_max[id] = contrib;
+                            { /* lock-free max: contrib > 0, so the bit patterns of fp32 values order like the values */
+                                float cf = (float)contrib;
+                                uint32_t nb, ob;
+                                memcpy(&nb, &cf, 4);
+                                uint32_t *slot = cmax_bits + id;
+                                ob = __atomic_load_n(slot, __ATOMIC_RELAXED);
+                                while (nb > ob && !__atomic_compare_exchange_n(slot, &ob, nb, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+                            }
                             accn.x += normal_view[3 * id] * contrib; accn.y += normal_view[3 * id + 1] * contrib; accn.z += normal_view[3 * id + 2] * contrib;
                             const real d = v_depth[3 * id] * pr.a1 + v_depth[3 * id + 1] * pr.a2 + v_depth[3 * id + 2] * pr.a3;
                             accd += d * contrib;
@@ -399,7 +407,8 @@ int ts2d_oracle_render(int W, int H, int C, real gamma, int rich_info, const uin
         }
     }
     if (rich_info) {
-        for (int i = 0; i < P; i++) contrib_sum[i] = (real)csum[i];
+        for (int i = 0; i < P; i++) { contrib_sum[i] = (real)csum[i]; float mf; memcpy(&mf, cmax_bits + i, 4); contrib_max[i] = (real)mf; }
+        free(cmax_bits);
         free(csum);
     }
     return 0;

@@ -11,6 +11,7 @@ Extra keyword-only arguments (no counterpart in the reference):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Tuple
 
 import torch
@@ -18,6 +19,17 @@ import torch
 from . import _lib
 
 MAX_CHANNELS = 3  # R2D/src/config.h:3
+
+# Arithmetic mode of the composite kernels (ts2d_flags.exact): False = fast path with exact re-evaluation inside the
+# decision bands (default), True = op-for-op mirror of the reference's per-pair arithmetic.  TS2D_EXACT=1 forces the mirror.
+EXACT = os.environ.get("TS2D_EXACT", "0") == "1"
+
+
+def set_exact(flag: bool) -> bool:
+    """Select the arithmetic mode for subsequent calls; returns the previous setting."""
+    global EXACT
+    old, EXACT = EXACT, bool(flag)
+    return old
 
 
 def _ptr(t: torch.Tensor | None):
@@ -67,7 +79,7 @@ def _structs(image_width, image_height, tan_fovx, tan_fovy, viewmatrix, projmatr
     cam = _lib.Camera(int(image_width), int(image_height), float(tan_fovx), float(tan_fovy), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos))
     geom = _lib.Geometry(int(P), int(sh_degree), int(M), int(Cn), int(use_shs), float(gamma), float(scale_modifier), float(background_depth),
                          _ptr(background), _ptr(vertex), _ptr(shs) if use_shs else None, None if use_shs else _ptr(feature), _ptr(opacity))
-    flags = _lib.Flags(int(bool(back_culling)), int(bool(rich_info)), int(bool(debug)), int(shard[0]), int(shard[1]), 1)
+    flags = _lib.Flags(int(bool(back_culling)), int(bool(rich_info)), int(bool(debug)), int(shard[0]), int(shard[1]), int(EXACT))
     return cam, geom, flags
 
 

@@ -252,7 +252,10 @@ int ts2d_forward_render(const ts2d_camera *cam, const ts2d_geometry *geom, const
     if (carve_image(image_state, cam->width, cam->height, &is) > image_state_bytes) return TS2D_E_STATE_SIZE;
     cudaStream_t s = (cudaStream_t)stream;
     TS2D_STAGE(TS2D_STAGE_BINNING, ts2d_launch_binning(cam, flags, geom->P, num_rendered, gs, bs, is, s));
-    TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd(cam, geom, flags, gs, bs.tval[1], is, out, s));
+    if (ts2d_use_fast(geom, flags))
+        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd_fast(cam, geom, flags, gs, bs.tval[1], is, out, s));
+    else
+        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd(cam, geom, flags, gs, bs.tval[1], is, out, s));
     return 0;
 }
 
@@ -275,7 +278,10 @@ int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_
     carve_binning(const_cast<void *>(binning_state), num_rendered, &bs);
     carve_image(const_cast<void *>(image_state), cam->width, cam->height, &is);
     cudaStream_t s = (cudaStream_t)stream;
-    TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
+    if (ts2d_use_fast(geom, flags))
+        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd_fast(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
+    else
+        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
     TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
     return 0;
 }

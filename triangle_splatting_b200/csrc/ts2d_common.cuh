@@ -187,6 +187,13 @@ int ts2d_launch_order_and_scan(int32_t P, GeomState gs, int64_t *R_host, cudaStr
 int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_flags *f, int32_t P, int64_t R, GeomState gs, BinState bs, ImageState is, cudaStream_t s);
 int ts2d_launch_render_fwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
                            ImageState is, const ts2d_forward_out *out, cudaStream_t s);
+int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
+                                ImageState is, const ts2d_forward_out *out, cudaStream_t s);
+int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
+                                ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s);
+// The fast kernels cover the gamma range the trainer schedules (1..50, VanillaTS_model.py:549-554) with margin;
+// outside it (gamma -> 0 makes ecc^(2 gamma) degenerate) the exact mirror kernels are used.
+static inline bool ts2d_use_fast(const ts2d_geometry *g, const ts2d_flags *f) { return !f->exact && g->gamma >= 0.05f && g->gamma <= 64.0f; }
 int ts2d_launch_render_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
                            ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s);
 int ts2d_launch_preprocess_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, const int32_t *radii, GeomState gs,

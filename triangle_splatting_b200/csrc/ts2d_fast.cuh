@@ -1,0 +1,157 @@
+// ts2d_fast.cuh -- shared pieces of the fast composite kernels (forward and backward).
+//
+// Fast path.  Per pixel the barycentrics are formed exactly like the reference (pixel-relative
+// cross products, R2D/src/forward.cu:299-305) but with one multiply by a per-triangle reciprocal
+// instead of two IEEE divides, ecc^(2 gamma) by ecc*ecc (gamma == 1) or MUFU lg2/ex2, and exp by
+// MUFU ex2.  That keeps alpha within a few 1e-6 (relative) of the reference's value; every
+// comparison the reference makes (ecc range, alpha < 1/255, op*G < 0.99, T <= 1e-4) is taken from the
+// fast value only when it is further from the threshold than a rigorous rounding bound ("decision
+// band"); inside the band the pair -- or the pixel's transmittance -- is re-evaluated with the
+// op-for-op mirror of the reference arithmetic (eval_exact, ts2d_common.cuh).  So the set of
+// contributing (pixel, triangle) pairs, n_contrib and the early-termination point are the
+// reference's, while values differ by fp32 rounding only.
+//
+// Sub-tile culling.  Each warp owns an 8x4-pixel sub-tile.  The staging thread tests its triangle's
+// alpha >= 1/255 footprint (the triangle scaled about its centroid by E = (2 ln(255 op))^(1/(2 gamma)),
+// clipped to ecc <= 10) against the 8 sub-tile rectangles with a conservative 3-edge test on affine
+// edge functions and stores an 8-bit mask; a warp only evaluates list entries whose bit is set
+// (ballot + ffs walk).  Margins cover the rounding of both the affine form and the reference's
+// form, so culled pairs are exactly pairs the reference would have skipped.
+#pragma once
+#include "ts2d_common.cuh"
+
+#define TS2D_LOG2E 1.4426950408889634f
+
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// gamma-dependent constants (kernel-uniform)
+struct GammaK {
+    float gamma, two_gamma, inv_two_gamma;
+    float band;      // relative half-width of the alpha decision band
+    float terr_c0;   // rel. error bound of a fast alpha = terr_c0 + terr_c1 * |power|
+    float terr_c1;
+    bool is_one;     // gamma == 1: ecc^(2 gamma) = ecc*ecc
+    bool ecc10;      // gamma < 0.6: a pair at ecc ~ 10 can still reach alpha >= 1/255, so the ecc <= 10 cut matters
+};
+
+// Error model (eps = 2^-24 = 6e-8).  The fast a_i differ from the reference's by <= 1.5 ulp (reciprocal-multiply
+// vs IEEE divide) => |d ecc| <= 3 * 1.5 eps * (1 + |a1| + |a2|) <= 1.2e-6 wherever a pair can contribute
+// (all a_i in [-0.8, 2.6]).  d ln(alpha) = gamma * ecc^(2 gamma - 1) * d ecc <= gamma * (1 + 2|power|) * d ecc
+// (gamma >= 0.5).  powf is within 4 ulp of ecc^(2 gamma), ecc*ecc within 0.5 ulp => d power <= 2.4e-7 |power|;
+// the lg2/ex2 route adds 2 gamma * 2^-22 * ln 2 relative on the power; expf vs ex2.approx (+ argument rounding)
+// adds <= 4e-7.  band is the bound evaluated at the alpha = 1/255 threshold with op = 1 (|power| = 5.54).
+__device__ __forceinline__ GammaK make_gamma(float gamma)
+{
+    GammaK g;
+    g.gamma = gamma;
+    g.two_gamma = 2.0f * gamma;
+    g.inv_two_gamma = gamma > 0.0f ? 1.0f / (2.0f * gamma) : 0.0f;
+    g.is_one = (gamma == 1.0f);
+    g.ecc10 = gamma < 0.6f;  // for gamma >= 0.6: ecc >= 9.9 => alpha <= exp(-0.5 * 9.9^1.2) < 1/255 even at op = 1
+    const float lg = g.is_one ? 0.0f : 3.3e-7f * gamma;
+    g.terr_c0 = 1.8e-6f * gamma + 4.0e-7f;
+    g.terr_c1 = 3.6e-6f * gamma + 2.4e-7f + lg;
+    g.band = 1.5f * (g.terr_c0 + g.terr_c1 * 5.6f) + 2.0e-6f;
+    return g;
+}
+
+// Sub-tile coverage mask of one triangle in the tile with origin (ox, oy).  r0 = {v1, v2}, r1 = {v3, area2, op}.
+// warp w <-> sub-tile (sx = w & 1, sy = w >> 1), pixels dx in [8sx, 8sx+7], dy in [4sy, 4sy+3].
+__device__ __forceinline__ uint32_t subtile_mask(const float4 r0, const float4 r1, float inv, float ox, float oy, const GammaK gk)
+{
+    const float op = r1.w;
+    const float p1x = r0.x - ox, p1y = r0.y - oy, p2x = r0.z - ox, p2y = r0.w - oy, p3x = r1.x - ox, p3y = r1.y - oy;
+    const float a10 = (p2x * p3y - p2y * p3x) * inv;
+    const float a20 = (p3x * p1y - p3y * p1x) * inv;
+    const float A1 = (r0.w - r1.y) * inv, B1 = (r1.x - r0.z) * inv;  // d a1 / d(px, py)
+    const float A2 = (r1.y - r0.y) * inv, B2 = (r0.x - r1.x) * inv;  // d a2 / d(px, py)
+    // rounding bound on any barycentric inside this tile, for the affine form and for the reference's form
+    const float ext = fmaxf(fmaxf(fmaxf(fabsf(p1x), fabsf(p1y)), fmaxf(fabsf(p2x), fabsf(p2y))), fmaxf(fabsf(p3x), fabsf(p3y))) + 16.0f;
+    const float err_a = 1.0e-6f * (ext * ext * fabsf(inv)) + 1.0e-6f;  // ~8 ulp of 2 ext^2 / |area2|
+    // alpha >= 1/255  <=>  ecc^(2 gamma) <= L = 2 ln(255 op)
+    const float L = 2.0f * __logf(255.0f * op);
+    if (!(L > -1.0e-3f) || !(fabsf(inv) < 3.0e37f)) return 0u;  // opacity below 1/255 (with margin): contributes nowhere
+    const float Lp = fmaxf(L, 1.0e-6f);
+    float E = gk.is_one ? sqrtf(Lp) : exp2f(__log2f(Lp) * gk.inv_two_gamma);
+    E = fminf(E, 10.0f);
+    const float Ec = E * 1.002f + 2.0e-3f + 12.0f * err_a;  // conservative footprint radius in ecc units
+    const float thr = (1.0f - Ec) * (1.0f / 3.0f);           // need min(a1,a2,a3) >= thr somewhere in the rect
+    const float A3 = -A1 - A2, B3 = -B1 - B2, a30 = 1.0f - a10 - a20;
+    float mx1[2], mx2[2], mx3[2], my1[4], my2[4], my3[4];
+#pragma unroll
+    for (int sx = 0; sx < 2; sx++) {
+        const float lo = 8.0f * sx, hi = lo + 7.0f;
+        mx1[sx] = fmaxf(A1 * lo, A1 * hi);
+        mx2[sx] = fmaxf(A2 * lo, A2 * hi);
+        mx3[sx] = fmaxf(A3 * lo, A3 * hi);
+    }
+#pragma unroll
+    for (int sy = 0; sy < 4; sy++) {
+        const float lo = 4.0f * sy, hi = lo + 3.0f;
+        my1[sy] = fmaxf(B1 * lo, B1 * hi);
+        my2[sy] = fmaxf(B2 * lo, B2 * hi);
+        my3[sy] = fmaxf(B3 * lo, B3 * hi);
+    }
+    uint32_t m = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const int sx = w & 1, sy = w >> 1;
+        const bool ok = (a10 + mx1[sx] + my1[sy] >= thr) && (a20 + mx2[sx] + my2[sy] >= thr) && (a30 + mx3[sx] + my3[sy] >= thr);
+        m |= ok ? (1u << w) : 0u;
+    }
+    return m;
+}
+
+// Fast per-pair evaluation with absolute pixel coordinates.  e1 = {v1.x, v1.y, v2.x, v2.y}, e2 = {v3.x, v3.y, 1/area2, op}.
+// Returns whether the pair contributes according to the fast value; `uncertain` says the reference's decision
+// cannot be inferred from it (then the caller uses eval_exact).
+struct FastPair {
+    float a1, a2, a3, ecc, power, G, og, alpha;
+    float pv1x, pv1y, pv2x, pv2y, pv3x, pv3y;
+};
+
+__device__ __forceinline__ bool eval_fast(const float4 e1, const float4 e2, float px, float py, const GammaK gk, FastPair &f, bool &uncertain)
+{
+    f.pv1x = e1.x - px; f.pv1y = e1.y - py;
+    f.pv2x = e1.z - px; f.pv2y = e1.w - py;
+    f.pv3x = e2.x - px; f.pv3y = e2.y - py;
+    f.a1 = fmaf(f.pv2x, f.pv3y, -(f.pv2y * f.pv3x)) * e2.z;
+    f.a2 = fmaf(f.pv3x, f.pv1y, -(f.pv3y * f.pv1x)) * e2.z;
+    f.a3 = 1.0f - f.a1 - f.a2;
+    f.ecc = fmaf(fminf(fminf(f.a1, f.a2), f.a3), -3.0f, 1.0f);
+    float pw;
+    if (gk.is_one)
+        pw = f.ecc * f.ecc;
+    else
+        pw = ex2_approx(gk.two_gamma * lg2_approx(fmaxf(f.ecc, 1.0e-30f)));
+    f.power = -0.5f * pw;
+    f.G = ex2_approx(f.power * TS2D_LOG2E);
+    f.og = e2.w * f.G;
+    f.alpha = fminf(0.99f, f.og);
+    const float d = fmaf(f.alpha, 255.0f, -1.0f);  // alpha * 255 - 1
+    uncertain = (fabsf(d) <= gk.band) || (f.ecc < 1.0e-4f);
+    bool ok = d >= 0.0f;
+    if (gk.ecc10) {
+        uncertain = uncertain || (f.ecc > 9.9f && f.ecc < 10.1f);
+        ok = ok && (f.ecc <= 10.0f);
+    }
+    return ok;
+}

@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(TS2D_BLOCK)
 k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool rich, float tfx, float tfy, const float *__restrict__ view,
                  const float *__restrict__ proj, const float *__restrict__ campos, const float *__restrict__ vertex,
                  const float *__restrict__ shs, const int32_t *__restrict__ radii, const uint8_t *__restrict__ clamp,
-                 const float4 *__restrict__ gacc, float *__restrict__ dL_dvertex, float *__restrict__ dL_dcenter2D, float *__restrict__ dL_dshs,
+                 const float4 *__restrict__ gacc, bool moments, const float4 *__restrict__ rec0, float *__restrict__ dL_dvertex, float *__restrict__ dL_dcenter2D, float *__restrict__ dL_dshs,
                  float *__restrict__ dL_dfeature, float *__restrict__ dL_dopacity)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -285,7 +285,22 @@ k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool ri
         return;
     }
     const float4 A0 = gacc[4 * (size_t)idx + 0], A1 = gacc[4 * (size_t)idx + 1], A2 = gacc[4 * (size_t)idx + 2], A3 = gacc[4 * (size_t)idx + 3];
-    const f2 g1 = mk2(A0.x, A0.y), g2 = mk2(A0.z, A0.w), g3 = mk2(A1.x, A1.y);
+    f2 g1 = mk2(A0.x, A0.y), g2 = mk2(A0.z, A0.w), g3 = mk2(A1.x, A1.y);
+    if (moments) {
+        // The fast composite backward accumulates S_k = sum ga_k, Q_k = sum ga_k (p - v1) (k = 1, 2; ga_k = dL/da_k - dL/da_3)
+        // instead of the vertex gradients; with a1 = 1 + cross(e23, q)/A, a2 = cross(e31, q)/A (q = p - v1) the reference's
+        // Jacobians (backward.cu:464-479) summed over pixels collapse to the fixed 6 -> 6 map below.
+        const float4 r0 = rec0[3 * (size_t)idx], r1 = rec0[3 * (size_t)idx + 1];
+        const f2 s1 = mk2(r0.x, r0.y), s2 = mk2(r0.z, r0.w), s3 = mk2(r1.x, r1.y);
+        const float inv = 1.0f / r1.z;
+        const f2 e12 = s2 - s1, e23 = s3 - s2, e31 = s1 - s3, w = s3 - s1;
+        const float S1 = A0.x, S2 = A0.w;
+        const f2 Q1 = mk2(A0.y, A0.z), Q2 = mk2(A1.x, A1.y);
+        const float Tt = (S1 + cross2(e23, Q1) * inv) + cross2(e31, Q2) * inv;  // sum ga1 a1 + sum ga2 a2
+        g1 = perp2(e23 * Tt - w * S2 + Q2) * inv;
+        g2 = perp2(e31 * Tt + w * S1 - Q1) * inv;
+        g3 = perp2((e12 * Tt - e12 * S1) + (Q1 - Q2)) * inv;
+    }
     const float g_op = A1.z;
     const f3 g_rgb = mk3(A2.x, A2.y, A2.z);
     const f3 g_n = mk3(A1.w, A2.w, A3.x);
@@ -366,7 +381,7 @@ int ts2d_launch_preprocess_bwd(const ts2d_camera *cam, const ts2d_geometry *g, c
     const int P = g->P;
     k_preprocess_bwd<<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(
         cam->width, cam->height, P, g->sh_degree, g->M, g->C, g->use_shs != 0, f->rich_info != 0, cam->tan_fovx, cam->tan_fovy, cam->viewmatrix,
-        cam->projmatrix, cam->campos, g->vertex, g->shs, radii, gs.clamp, (const float4 *)gacc, out->dL_dvertex, out->dL_dcenter2D, out->dL_dshs,
+        cam->projmatrix, cam->campos, g->vertex, g->shs, radii, gs.clamp, (const float4 *)gacc, ts2d_use_fast(g, f), gs.rec0, out->dL_dvertex, out->dL_dcenter2D, out->dL_dshs,
         out->dL_dfeature, out->dL_dopacity);
     return (int)cudaGetLastError();
 }
