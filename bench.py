@@ -364,8 +364,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import build_ref
+        from oracle import build_ref
 
         ref = None
         try:

@@ -47,7 +47,7 @@ def main():
         _C.set_exact(False)
         runs["fast"] = harness.run_ours(sc, dev)
         _C.set_exact(old)
-        if sc.P <= 5000:
+        if sc.P <= 200000:
             runs["f64"] = harness.run_oracle(sc, "f64")
         base = runs.get("refA", runs["exact"])
         emit(f"== {name}: P={sc.P} R={int(base['num_rendered'])} visible={int((base['radii'] > 0).sum())} rich={sc.rich_info} gamma={sc.gamma}")

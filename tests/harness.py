@@ -123,8 +123,7 @@ def run_ours(sc: Scene, dev, backward: bool = True) -> dict:
 
 # ------------------------------------------------------------------------------- live reference
 def load_reference():
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import build_ref
+    from oracle import build_ref
 
     return build_ref.load()
 

@@ -192,8 +192,8 @@ int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
 int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
                                 ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s);
 // The fast kernels cover the gamma range the trainer schedules (1..50, VanillaTS_model.py:549-554) with margin;
-// outside it (gamma -> 0 makes ecc^(2 gamma) degenerate) the exact mirror kernels are used.
-static inline bool ts2d_use_fast(const ts2d_geometry *g, const ts2d_flags *f) { return !f->exact && g->gamma >= 0.05f && g->gamma <= 64.0f; }
+// outside it (for gamma < 0.6 the ecc <= 10 cut starts to matter; gamma -> 0 makes ecc^(2 gamma) degenerate) the exact mirror kernels are used.
+static inline bool ts2d_use_fast(const ts2d_geometry *g, const ts2d_flags *f) { return !f->exact && g->gamma >= 0.6f && g->gamma <= 64.0f; }
 int ts2d_launch_render_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
                            ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s);
 int ts2d_launch_preprocess_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, const int32_t *radii, GeomState gs,

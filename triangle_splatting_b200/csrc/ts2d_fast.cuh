@@ -49,7 +49,6 @@ struct GammaK {
     float terr_c0;   // rel. error bound of a fast alpha = terr_c0 + terr_c1 * |power|
     float terr_c1;
     bool is_one;     // gamma == 1: ecc^(2 gamma) = ecc*ecc
-    bool ecc10;      // gamma < 0.6: a pair at ecc ~ 10 can still reach alpha >= 1/255, so the ecc <= 10 cut matters
 };
 
 // Error model (eps = 2^-24 = 6e-8).  The fast a_i differ from the reference's by <= 1.5 ulp (reciprocal-multiply
@@ -65,8 +64,7 @@ __device__ __forceinline__ GammaK make_gamma(float gamma)
     g.two_gamma = 2.0f * gamma;
     g.inv_two_gamma = gamma > 0.0f ? 1.0f / (2.0f * gamma) : 0.0f;
     g.is_one = (gamma == 1.0f);
-    g.ecc10 = gamma < 0.6f;  // for gamma >= 0.6: ecc >= 9.9 => alpha <= exp(-0.5 * 9.9^1.2) < 1/255 even at op = 1
-    const float lg = g.is_one ? 0.0f : 3.3e-7f * gamma;
+    const float lg = g.is_one ? 0.0f : 2.0e-7f * gamma;  // log2f (1 ulp of |log2 ecc| <= 3.4) * 2 gamma * ln 2 + exp2f (2 ulp)
     g.terr_c0 = 1.8e-6f * gamma + 4.0e-7f;
     g.terr_c1 = 3.6e-6f * gamma + 2.4e-7f + lg;
     g.band = 1.5f * (g.terr_c0 + g.terr_c1 * 5.6f) + 2.0e-6f;
@@ -141,17 +139,14 @@ __device__ __forceinline__ bool eval_fast(const float4 e1, const float4 e2, floa
     if (gk.is_one)
         pw = f.ecc * f.ecc;
     else
-        pw = ex2_approx(gk.two_gamma * lg2_approx(fmaxf(f.ecc, 1.0e-30f)));
+        pw = exp2f(gk.two_gamma * log2f(fmaxf(f.ecc, 1.0e-30f)));  // full-precision log2f/exp2f: the error is multiplied by 2 gamma |power|
     f.power = -0.5f * pw;
     f.G = ex2_approx(f.power * TS2D_LOG2E);
     f.og = e2.w * f.G;
     f.alpha = fminf(0.99f, f.og);
     const float d = fmaf(f.alpha, 255.0f, -1.0f);  // alpha * 255 - 1
     uncertain = (fabsf(d) <= gk.band) || (f.ecc < 1.0e-4f);
-    bool ok = d >= 0.0f;
-    if (gk.ecc10) {
-        uncertain = uncertain || (f.ecc > 9.9f && f.ecc < 10.1f);
-        ok = ok && (f.ecc <= 10.0f);
-    }
-    return ok;
+    // The reference's ecc > 10 cut needs no test here: the fast kernels only run for gamma >= 0.6 (ts2d_use_fast), where
+    // ecc >= 9.9 implies alpha <= exp(-0.5 * 9.9^1.2) << 1/255, i.e. d < -band: skipped by both.
+    return d >= 0.0f;
 }

@@ -1,90 +1,76 @@
 // ts2d_render_bwd_fast.cu -- fast reverse-walk gradient accumulation (K8, flags.exact == 0).
 //
 // Same contract as k_render_bwd (ts2d_render_bwd.cu, the mirror of R2D/src/backward.cu:265-493) with the
-// forward fast kernel's machinery (sub-tile masks, pixel-relative fast barycentrics, decision bands with
-// eval_exact fallback -- so the set of contributing pairs is the one the forward pass blended) plus:
+// forward fast kernel's machinery (sub-tile masks, reference-shaped fast barycentrics, decision bands with
+// eval_exact fallback -- so the set of contributing pairs is exactly the one the forward pass blended).
 //
-//   * Vertex gradients as MOMENTS.  The reference evaluates nine 2-vector Jacobians d a_i / d v_j per
-//     (pixel, triangle) pair (backward.cu:464-479).  a_1, a_2 are affine in the pixel position, so
-//     sum_p g_i(p) d a_i(p)/d v_j is a fixed linear map of the six moments
-//         S_k = sum ga_k,  Q_k = sum ga_k * (p - v1),   ga_k = dL/da_k - dL/da_3,  k = 1, 2
-//     taken relative to the triangle's own vertex v1 (well conditioned, tile independent, and p - v1 is
-//     already in registers).  A pixel only forms 6 products; the 6 -> 6 map is applied once per triangle
-//     in the preprocess-backward kernel (moments_to_vertex_grads, ts2d_preprocess.cu).
-//   * 16 components reduced over the warp by a recursive-halving butterfly (16 SHFL + 16 FADD), then one
-//     coalesced 64 B RED burst per (warp, triangle) into the triangle's accumulator line.
+// What is different from the reference is how the per-pair contributions are summed over pixels.  The reference
+// issues 10-16 global atomics per contributing (pixel, triangle) pair.  Here every one of the 16 per-triangle
+// outputs is written as  sum_p w(p) * f(p)  where w is one of only THREE per-pair scalars that depend on the
+// sequential walk (contrib = alpha T, dL/dalpha * G, and D = dL/d ecc routed to the arg-min barycentric) and
+// f is a per-pixel constant (upstream gradients, pixel offsets) -- the barycentrics being affine in the pixel,
+// their Jacobians reduce to first moments (see ts2d_preprocess.cu: the moments -> vertex-gradient map).
+//   phase 1 (lane = pixel):    walk the warp's covered entries back to front, run the T / colour recurrences,
+//                              park the three scalars of each pair in a 16-slot shared-memory panel W[slot][pixel];
+//   phase 2 (lane = triangle): every 16 slots, each lane owns (slot, half of the 32 pixels) and accumulates the
+//                              16 sums with plain FFMAs from W and the per-pixel table F -- no shuffles, no
+//                              selects -- then one xor-16 combine and four 16-byte REDs per triangle.
+// This replaces a 16-value warp butterfly per pair-iteration (16 SHFL + 16 FADD + 30 SEL) by 3 STS + ~30
+// amortised instructions, and moves all Jacobian arithmetic out of the per-pixel loop.
 #include "ts2d_fast.cuh"
 
 namespace {
 
-__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane)
+constexpr int BW_BATCH = 128;   // list entries staged per batch
+constexpr int BW_SLOTS = 16;    // triangles per phase-2 panel
+constexpr int BW_WROW = 97;     // 3 scalars x 32 pixels + 1 pad word: conflict-free for both phases
+constexpr int BW_FCOLS = 12;
+
+struct __align__(16) BwdEntry {
+    float4 e1;   // v1.x, v1.y, v2.x, v2.y
+    float4 e2;   // v3.x, v3.y, 1/area2, opacity
+    float4 col;  // r, g, b, triangle id (bits)
+    float4 q0;   // n.x, n.y, n.z, vd1
+    float4 q1;   // vd2, vd3, -, -
+};
+
+struct BwdSmem {
+    BwdEntry ent[BW_BATCH];
+    float F[8][32][BW_FCOLS];        // per warp, per pixel: gp0 gp1 gp2 gd | gn0 gn1 gn2 dx | dy gd*dx gd*dy -
+    float W[8][BW_SLOTS][BW_WROW];   // per warp panel: [slot][scalar * 32 + pixel]
+    uint8_t mask[BW_BATCH];
+    uint32_t tile_last;
+};
+
+__device__ __forceinline__ void red_add4(float *addr, float a, float b, float c, float d)
 {
-    float w8[8], w4[4], w2[2];
-    {
-        const bool up = lane & 16;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const float keep = up ? v[i + 8] : v[i];
-            const float send = up ? v[i] : v[i + 8];
-            w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-    }
-    {
-        const bool up = lane & 8;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const float keep = up ? w8[i + 4] : w8[i];
-            const float send = up ? w8[i] : w8[i + 4];
-            w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    }
-    {
-        const bool up = lane & 4;
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const float keep = up ? w4[i + 2] : w4[i];
-            const float send = up ? w4[i] : w4[i + 2];
-            w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-    }
-    float r;
-    {
-        const bool up = lane & 2;
-        const float keep = up ? w2[1] : w2[0];
-        const float send = up ? w2[0] : w2[1];
-        r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    r += __shfl_xor_sync(0xffffffffu, r, 1);
-    return r;  // lane L holds component (L >> 1) & 15
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <bool RICH>
+template <bool RICH, bool GAMMA1>
 __global__ void __launch_bounds__(TS2D_BLOCK)
-k_render_bwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, int n_tiles, float gamma, const uint2 *__restrict__ ranges,
+k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world, int n_tiles, float gamma, const uint2 *__restrict__ ranges,
                   const uint32_t *__restrict__ list, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1, float bg_depth,
                   const float *__restrict__ background, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
                   const float *__restrict__ dL_dout_feature, const float *__restrict__ dL_dout_depth,
                   const float *__restrict__ dL_dout_normal, float *__restrict__ gacc)
 {
-    __shared__ float4 s_e1[TS2D_BLOCK];   // v1.x, v1.y, v2.x, v2.y
-    __shared__ float4 s_e2[TS2D_BLOCK];   // v3.x, v3.y, 1/area2, opacity
-    __shared__ float4 s_col[TS2D_BLOCK];  // r, g, b, triangle id (bits)
-    __shared__ float4 s_q0[RICH ? TS2D_BLOCK : 1];
-    __shared__ float4 s_q1[RICH ? TS2D_BLOCK : 1];
-    __shared__ uint8_t s_mask[TS2D_BLOCK];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BwdSmem &S = *reinterpret_cast<BwdSmem *>(smem_raw);
 
     const int tile = blockIdx.x * shard_world + shard_rank;
     if (tile >= n_tiles) return;
     const int tile_x = tile % gx, tile_y = tile / gx;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int px = tile_x * TS2D_TILE + (warp & 1) * 8 + (lane & 7);
-    const int py = tile_y * TS2D_TILE + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = px < W && py < H;
+    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
+    const int px = tile_x * TS2D_TILE + lx, py = tile_y * TS2D_TILE + ly;
+    const bool inside = px < W_ && py < H;
     const float pxf = (float)px, pyf = (float)py;
     const float ox = (float)(tile_x * TS2D_TILE), oy = (float)(tile_y * TS2D_TILE);
-    const size_t pix = (size_t)W * py + px;
-    const size_t HW = (size_t)H * W;
-    const GammaK gk = make_gamma(gamma);
+    const size_t pix = (size_t)W_ * py + px;
+    const size_t HW = (size_t)H * W_;
+    GammaK gk = make_gamma(gamma);
+    gk.is_one = GAMMA1;
 
     const uint2 range = ranges[tile];
     const uint32_t len = range.y - range.x;
@@ -105,124 +91,203 @@ k_render_bwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
             gd = dL_dout_depth[pix];
         }
     }
+    {   // per-pixel table for phase 2
+        float *f = S.F[warp][lane];
+        const float dxl = (float)lx, dyl = (float)ly;  // pixel offset from the tile origin
+        *reinterpret_cast<float4 *>(f) = make_float4(gp0, gp1, gp2, gd);
+        *reinterpret_cast<float4 *>(f + 4) = make_float4(gn0, gn1, gn2, dxl);
+        *reinterpret_cast<float4 *>(f + 8) = make_float4(dyl, gd * dxl, gd * dyl, 0.0f);
+    }
     const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last);
-    // list positions >= tile_last were visited by no pixel of the tile: skip their batches entirely
-    __shared__ uint32_t s_tile_last;
-    if (tid == 0) s_tile_last = 0;
+    if (tid == 0) S.tile_last = 0;
     __syncthreads();
-    if (lane == 0) atomicMax(&s_tile_last, warp_last);
+    // geometry upstream gradients all zero in this tile (w_geometry = 0 training configs): the normal / depth
+    // terms are exactly zero for the reference too, so skipping them changes no bit of the result
+    const bool geo = RICH && __syncthreads_or(gd != 0.0f || gn0 != 0.0f || gn1 != 0.0f || gn2 != 0.0f);
+    if (lane == 0) atomicMax(&S.tile_last, warp_last);
     __syncthreads();
-    const uint32_t tile_last = s_tile_last;
+    const uint32_t tile_last = S.tile_last;
 
-    // batches are staged in REVERSE list order: staged slot t of the batch starting at `top` is list position top - t
-    for (uint32_t done_cnt = len - tile_last; done_cnt < len; done_cnt += TS2D_BLOCK) {
+    float(*Wp)[BW_WROW] = S.W[warp];
+    int slot = 0;        // next free slot of the panel
+    int my_j = 0;        // staged index of the triangle parked in slot (lane & 15)
+    const int k = lane & 15, half = lane >> 4;
+
+    // phase 2: lane (k, half) sums the panel row k over pixels half*16 .. half*16+15 and flushes the triangle
+    auto flush_panel = [&](int filled) {
+        __syncwarp();
+        float s_c0 = 0.f, s_c1 = 0.f, s_c2 = 0.f, s_n0 = 0.f, s_n1 = 0.f, s_n2 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
+        float u10 = 0.f, u1x = 0.f, u1y = 0.f, u20 = 0.f, u2x = 0.f, u2y = 0.f, s_op = 0.f;
+        if (k < filled) {
+            const float *row = Wp[k];
+#pragma unroll 4
+            for (int i = 0; i < 16; i++) {
+                const int p = half * 16 + i;
+                const float c = row[p], w1 = row[32 + p], Dp = row[64 + p];
+                const float *f = S.F[warp][p];
+                const float4 f0 = *reinterpret_cast<const float4 *>(f);
+                const float4 f1 = *reinterpret_cast<const float4 *>(f + 4);
+                s_c0 = fmaf(c, f0.x, s_c0);
+                s_c1 = fmaf(c, f0.y, s_c1);
+                s_c2 = fmaf(c, f0.z, s_c2);
+                s_op += w1;
+                const uint32_t sel = __float_as_uint(Dp) & 3u;     // arg-min barycentric (1, 2, 3) packed in the two LSBs
+                const float u1 = sel == 1u ? Dp : (sel == 3u ? -Dp : 0.0f);
+                const float u2 = sel == 2u ? Dp : (sel == 3u ? -Dp : 0.0f);
+                float dyp = 0.f;
+                if (geo) {
+                    const float4 f2 = *reinterpret_cast<const float4 *>(f + 8);
+                    dyp = f2.x;
+                    s_n0 = fmaf(c, f1.x, s_n0);
+                    s_n1 = fmaf(c, f1.y, s_n1);
+                    s_n2 = fmaf(c, f1.z, s_n2);
+                    m0 = fmaf(c, f0.w, m0);
+                    m1 = fmaf(c, f2.y, m1);
+                    m2 = fmaf(c, f2.z, m2);
+                } else {
+                    dyp = f[8];
+                }
+                u10 += u1;
+                u1x = fmaf(u1, f1.w, u1x);
+                u1y = fmaf(u1, dyp, u1y);
+                u20 += u2;
+                u2x = fmaf(u2, f1.w, u2x);
+                u2y = fmaf(u2, dyp, u2y);
+            }
+        }
+#define XH(v) v += __shfl_xor_sync(0xffffffffu, v, 16)
+        XH(s_c0); XH(s_c1); XH(s_c2); XH(s_op); XH(u10); XH(u1x); XH(u1y); XH(u20); XH(u2x); XH(u2y);
+        if (geo) { XH(s_n0); XH(s_n1); XH(s_n2); XH(m0); XH(m1); XH(m2); }
+#undef XH
+        if (k < filled) {
+            const BwdEntry &E = S.ent[my_j];
+            const float4 e1 = E.e1, e2 = E.e2;
+            float *g = gacc + (size_t)__float_as_uint(E.col.w) * GACC_STRIDE;
+            const float inv = e2.z;
+            // affine barycentrics about the tile origin: a_i(d) = a_io + A_i dx + B_i dy
+            const float p1x = e1.x - ox, p1y = e1.y - oy, p2x = e1.z - ox, p2y = e1.w - oy, p3x = e2.x - ox, p3y = e2.y - oy;
+            float S1 = u10, M1x = u1x, M1y = u1y, S2 = u20, M2x = u2x, M2y = u2y;
+            float gv0 = 0.f, gv1 = 0.f, gv2 = 0.f;
+            if (geo) {
+                const float a1o = (p2x * p3y - p2y * p3x) * inv, A1 = (e1.w - e2.y) * inv, B1 = (e2.x - e1.z) * inv;
+                const float a2o = (p3x * p1y - p3y * p1x) * inv, A2 = (e2.y - e1.y) * inv, B2 = (e1.x - e2.x) * inv;
+                const float a3o = 1.0f - a1o - a2o, A3 = -A1 - A2, B3 = -B1 - B2;
+                const float vd1 = E.q0.w, vd2 = E.q1.x, vd3 = E.q1.y;
+                gv0 = fmaf(B1, m2, fmaf(A1, m1, a1o * m0));   // sum gd contrib a_1
+                gv1 = fmaf(B2, m2, fmaf(A2, m1, a2o * m0));
+                gv2 = fmaf(B3, m2, fmaf(A3, m1, a3o * m0));
+                const float d13 = vd1 - vd3, d23 = vd2 - vd3;   // depth term of ga_k = (vd_k - vd_3) gd contrib
+                S1 = fmaf(d13, m0, S1); M1x = fmaf(d13, m1, M1x); M1y = fmaf(d13, m2, M1y);
+                S2 = fmaf(d23, m0, S2); M2x = fmaf(d23, m1, M2x); M2y = fmaf(d23, m2, M2y);
+            }
+            // moments about v1: q = p - v1 = d - (v1 - o)
+            const float Q1x = fmaf(-p1x, S1, M1x), Q1y = fmaf(-p1y, S1, M1y), Q2x = fmaf(-p1x, S2, M2x), Q2y = fmaf(-p1y, S2, M2y);
+            if (half == 0) {
+                red_add4(g, S1, Q1x, Q1y, S2);
+                red_add4(g + 4, Q2x, Q2y, s_op, s_n0);
+            } else {
+                red_add4(g + 8, s_c0, s_c1, s_c2, s_n1);
+                if (geo) red_add4(g + 12, s_n2, gv0, gv1, gv2);
+            }
+        }
+        __syncwarp();
+    };
+
+    // batches are staged in REVERSE list order: staged slot t of a batch is list position (top - t)
+    for (uint32_t done_cnt = len - tile_last; done_cnt < len; done_cnt += BW_BATCH) {
         __syncthreads();
-        const int n = min((uint32_t)TS2D_BLOCK, len - done_cnt);
+        const int n = min((uint32_t)BW_BATCH, len - done_cnt);
         if (tid < n) {
             const uint32_t id = list[range.y - 1 - done_cnt - tid];
             const float4 *r = rec0 + 3 * (size_t)id;
             const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
             const float inv = 1.0f / r1.z;
-            s_e1[tid] = r0;
-            s_e2[tid] = make_float4(r1.x, r1.y, inv, r1.w);
-            s_col[tid] = make_float4(r2.x, r2.y, r2.z, __uint_as_float(id));
-            s_mask[tid] = (uint8_t)subtile_mask(r0, r1, inv, ox, oy, gk);
+            BwdEntry &E = S.ent[tid];
+            E.e1 = r0;
+            E.e2 = make_float4(r1.x, r1.y, inv, r1.w);
+            E.col = make_float4(r2.x, r2.y, r2.z, __uint_as_float(id));
             if (RICH) {
                 const float4 *q = rec1 + 2 * (size_t)id;
-                s_q0[tid] = __ldg(q);
-                s_q1[tid] = __ldg(q + 1);
+                E.q0 = __ldg(q);
+                E.q1 = __ldg(q + 1);
             }
+            S.mask[tid] = (uint8_t)subtile_mask(r0, r1, inv, ox, oy, gk);
         }
         __syncthreads();
 
         for (int c = 0; c * 32 < n; c++) {
             const int idx = c * 32 + lane;
-            const uint32_t mine = (idx < n) ? (uint32_t)s_mask[idx] : 0u;
+            const uint32_t mine = (idx < n) ? (uint32_t)S.mask[idx] : 0u;
             uint32_t bits = __ballot_sync(0xffffffffu, (mine >> warp) & 1u);
             while (bits) {
                 const int j = c * 32 + (__ffs(bits) - 1);
                 bits &= bits - 1;
                 const uint32_t pos = len - 1 - done_cnt - j;  // 0-based list position
                 if (pos >= warp_last) continue;                // warp-uniform
-                const float4 e1 = s_e1[j], e2 = s_e2[j];
-                float v[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) v[k] = 0.0f;
-                bool hit = false;
+                const BwdEntry &E = S.ent[j];
+                const float4 e1 = E.e1, e2 = E.e2;
+                float w_c = 0.0f, w_op = 0.0f, w_D = 0.0f;
                 if (pos < last) {
                     FastPair f;
                     bool unc;
-                    hit = eval_fast(e1, e2, pxf, pyf, gk, f, unc);
+                    bool hit = eval_fast(e1, e2, pxf, pyf, gk, f, unc);
                     // one more reference decision lives in the backward pass: op*G < 0.99 (clamp not active)
                     unc = unc || (fabsf(f.og - 0.99f) <= 0.99f * gk.band);
                     if (unc) {
-                        const uint32_t id = __float_as_uint(s_col[j].w);
-                        const float area2 = __ldg(&rec0[3 * (size_t)id + 1].z);
+                        const float area2 = __ldg(&rec0[3 * (size_t)__float_as_uint(E.col.w) + 1].z);
                         PairEval e;
                         hit = eval_exact(e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, area2, e2.w, gk.two_gamma, pxf, pyf, e);
                         f.a1 = e.a1; f.a2 = e.a2; f.a3 = e.a3; f.ecc = e.ecc;
                         if (hit) { f.power = e.power; f.G = e.G; f.og = __fmul_rn(e2.w, e.G); f.alpha = e.alpha; }
                     }
                     if (hit) {
-                        const float4 col = s_col[j];
+                        const float4 col = E.col;
                         const float om = 1.0f - f.alpha;
                         T = T * rcp_approx(om);
-                        const float contrib = f.alpha * T;
-                        float dL_dcontrib;
-                        v[8] = gp0 * contrib;
-                        v[9] = gp1 * contrib;
-                        v[10] = gp2 * contrib;
-                        dL_dcontrib = gp0 * (col.x - acc0);
+                        w_c = f.alpha * T;
+                        float dL_dcontrib = gp0 * (col.x - acc0);
                         dL_dcontrib = fmaf(gp1, col.y - acc1, dL_dcontrib);
                         dL_dcontrib = fmaf(gp2, col.z - acc2, dL_dcontrib);
                         acc0 = fmaf(f.alpha, col.x, om * acc0);
                         acc1 = fmaf(f.alpha, col.y, om * acc1);
                         acc2 = fmaf(f.alpha, col.z, om * acc2);
-                        float da1 = 0.f, da2 = 0.f, da3 = 0.f;
-                        if (RICH) {
-                            const float4 q0 = s_q0[j], q1 = s_q1[j];
-                            v[7] = gn0 * contrib;
-                            v[11] = gn1 * contrib;
-                            v[12] = gn2 * contrib;
+                        if (geo) {
+                            const float4 q0 = E.q0, q1 = E.q1;
                             dL_dcontrib = fmaf(gn0, q0.x - accn0, dL_dcontrib);
                             dL_dcontrib = fmaf(gn1, q0.y - accn1, dL_dcontrib);
                             dL_dcontrib = fmaf(gn2, q0.z - accn2, dL_dcontrib);
                             accn0 = fmaf(f.alpha, q0.x, om * accn0);
                             accn1 = fmaf(f.alpha, q0.y, om * accn1);
                             accn2 = fmaf(f.alpha, q0.z, om * accn2);
-                            const float dL_ddepth = gd * contrib;
-                            v[13] = dL_ddepth * f.a1;
-                            v[14] = dL_ddepth * f.a2;
-                            v[15] = dL_ddepth * f.a3;
-                            da1 = dL_ddepth * q0.w;
-                            da2 = dL_ddepth * q1.x;
-                            da3 = dL_ddepth * q1.y;
                             const float depth = fmaf(q1.y, f.a3, fmaf(q0.w, f.a1, q1.x * f.a2));
                             dL_dcontrib = fmaf(gd, depth - accd, dL_dcontrib);
                             accd = fmaf(f.alpha, depth, om * accd);
                         }
                         const float dL_dalpha = dL_dcontrib * T;
-                        v[6] = dL_dalpha * f.G;  // unconditional (backward.cu:490)
+                        w_op = dL_dalpha * f.G;  // unconditional (backward.cu:490)
                         const float dL_dpower = (f.og < 0.99f) ? dL_dalpha * f.alpha : 0.0f;
-                        const float dL_decc3 = -3.0f * dL_dpower * gk.two_gamma * f.power * rcp_approx(f.ecc + TS2D_EPS);
+                        const float D = -3.0f * dL_dpower * gk.two_gamma * f.power * rcp_approx(f.ecc + TS2D_EPS);
                         // sub-gradient of min: first arg-min in the order a1, a2, a3 (backward.cu:449-461)
-                        if (f.a1 <= f.a2 && f.a1 <= f.a3) da1 += dL_decc3;
-                        else if (f.a2 <= f.a1 && f.a2 <= f.a3) da2 += dL_decc3;
-                        else da3 += dL_decc3;
-                        const float ga1 = da1 - da3, ga2 = da2 - da3;
-                        // moments about v1: q = p - v1 = -pv1
-                        v[0] = ga1;
-                        v[1] = -ga1 * f.pv1x;
-                        v[2] = -ga1 * f.pv1y;
-                        v[3] = ga2;
-                        v[4] = -ga2 * f.pv1x;
-                        v[5] = -ga2 * f.pv1y;
+                        const uint32_t sel = (f.a1 <= f.a2 && f.a1 <= f.a3) ? 1u : ((f.a2 <= f.a1 && f.a2 <= f.a3) ? 2u : 3u);
+                        w_D = __uint_as_float((__float_as_uint(D) & ~3u) | sel);
                     }
                 }
-                if (__ballot_sync(0xffffffffu, hit) == 0u) continue;
-                const float r = warp_reduce16(v, lane);
-                if ((lane & 1) == 0) atomicAdd(gacc + (size_t)__float_as_uint(s_col[j].w) * GACC_STRIDE + (lane >> 1), r);
+                if (__ballot_sync(0xffffffffu, w_c != 0.0f) == 0u) continue;
+                float *row = Wp[slot];
+                row[lane] = w_c;
+                row[32 + lane] = w_op;
+                row[64 + lane] = w_D;
+                if (k == slot) my_j = j;
+                if (++slot == BW_SLOTS) {
+                    flush_panel(BW_SLOTS);
+                    slot = 0;
+                }
             }
+        }
+        // the staging buffer is about to be overwritten: flush triangles that still live in the panel
+        if (slot) {
+            flush_panel(slot);
+            slot = 0;
         }
     }
 }
@@ -238,14 +303,24 @@ int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
     const int owned = (n_tiles - f->shard_rank + f->shard_world - 1) / f->shard_world;
     TS2D_CUDA_TRY(cudaMemsetAsync(gacc, 0, sizeof(float) * GACC_STRIDE * (size_t)g->P, s));
     if (owned <= 0) return 0;
+    const bool g1 = g->gamma == 1.0f;
+    const size_t smem = sizeof(BwdSmem);
+#define TS2D_BWD_ARGS                                                                                                                      \
+    W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, list, gs.rec0, gs.rec1, g->background_depth, g->background, \
+        is.final_T, is.n_contrib, loss->dL_dout_feature
+#define TS2D_BWD_LAUNCH(R, G, ...)                                                                                          \
+    do {                                                                                                                    \
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_bwd_fast<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_render_bwd_fast<R, G><<<owned, TS2D_BLOCK, smem, s>>>(TS2D_BWD_ARGS, __VA_ARGS__, gacc);                          \
+    } while (0)
     if (f->rich_info) {
-        k_render_bwd_fast<true><<<owned, TS2D_BLOCK, 0, s>>>(W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, list,
-                                                             gs.rec0, gs.rec1, g->background_depth, g->background, is.final_T, is.n_contrib,
-                                                             loss->dL_dout_feature, loss->dL_dout_depth, loss->dL_dout_normal, gacc);
+        if (g1) TS2D_BWD_LAUNCH(true, true, loss->dL_dout_depth, loss->dL_dout_normal);
+        else TS2D_BWD_LAUNCH(true, false, loss->dL_dout_depth, loss->dL_dout_normal);
     } else {
-        k_render_bwd_fast<false><<<owned, TS2D_BLOCK, 0, s>>>(W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, list,
-                                                              gs.rec0, gs.rec1, g->background_depth, g->background, is.final_T, is.n_contrib,
-                                                              loss->dL_dout_feature, nullptr, nullptr, gacc);
+        if (g1) TS2D_BWD_LAUNCH(false, true, nullptr, nullptr);
+        else TS2D_BWD_LAUNCH(false, false, nullptr, nullptr);
     }
+#undef TS2D_BWD_LAUNCH
+#undef TS2D_BWD_ARGS
     return (int)cudaGetLastError();
 }
