@@ -19,6 +19,43 @@ __constant__ float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.457045
 
 __device__ __forceinline__ f3 ld3(const float *p) { return mk3(p[0], p[1], p[2]); }
 
+// ---- warp-cooperative staging of per-triangle rows (SH coefficients / SH gradients) ----------------------------
+// A thread owns one triangle but its row is 3M floats (192 B at M = 16): per-thread scalar access puts 32 different
+// cache lines behind every load/store instruction.  Instead the warp moves its 32 rows -- one contiguous 32*3M-float
+// block -- with coalesced 16-byte accesses through a shared-memory tile whose row stride (3M + 4 floats) makes the
+// per-thread float4 accesses bank-conflict free.  Used when 3M is a multiple of 4 (M = 4, 8, 12, 16).
+__device__ __forceinline__ void warp_rows_load(const float *__restrict__ g, float *tile, int q /*float4 per row*/, int rs4 /*tile row stride in float4*/,
+                                               int nrows, int lane)
+{
+    const float4 *g4 = reinterpret_cast<const float4 *>(g);
+    float4 *t4 = reinterpret_cast<float4 *>(tile);
+    int r = lane / q, c = lane - r * q;
+    const int dr = 32 / q, dc = 32 - dr * q;
+    for (int e = lane; e < nrows * q; e += 32) {
+        t4[r * rs4 + c] = __ldg(g4 + e);
+        r += dr;
+        c += dc;
+        if (c >= q) { c -= q; r++; }
+    }
+}
+__device__ __forceinline__ void warp_rows_store(float *__restrict__ g, const float *tile, int q, int rs4, int nrows, int lane)
+{
+    float4 *g4 = reinterpret_cast<float4 *>(g);
+    const float4 *t4 = reinterpret_cast<const float4 *>(tile);
+    int r = lane / q, c = lane - r * q;
+    const int dr = 32 / q, dc = 32 - dr * q;
+    for (int e = lane; e < nrows * q; e += 32) {
+        g4[e] = t4[r * rs4 + c];
+        r += dr;
+        c += dc;
+        if (c >= q) { c -= q; r++; }
+    }
+}
+static inline bool ts2d_rows_tileable(int M, const void *a, const void *b)
+{
+    return M > 0 && (3 * M) % 4 == 0 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0;
+}
+
 // Real SH basis (degree <= 3) times per-triangle coefficients, +0.5, clamp at 0 with mask.
 __device__ __forceinline__ f3 sh_colour(int deg, const float *sh, f3 pos, f3 cam, uint8_t &mask)
 {
@@ -265,6 +302,7 @@ __device__ __forceinline__ f3 sh_colour_bwd(int deg, int M, const float *sh, f3 
     return grad_norm3(dir_orig, gdir);
 }
 
+template <bool TILED>
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool rich, float tfx, float tfy, const float *__restrict__ view,
                  const float *__restrict__ proj, const float *__restrict__ campos, const float *__restrict__ vertex,
@@ -272,18 +310,35 @@ k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool ri
                  const float4 *__restrict__ gacc, bool moments, const float4 *__restrict__ rec0, float *__restrict__ dL_dvertex, float *__restrict__ dL_dcenter2D, float *__restrict__ dL_dshs,
                  float *__restrict__ dL_dfeature, float *__restrict__ dL_dopacity)
 {
+    extern __shared__ __align__(16) float s_rows[];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    float *ov = dL_dvertex + 9 * (size_t)idx;
-    if (radii[idx] <= 0) {  // reference leaves its zero-initialised outputs untouched here (backward.cu:165)
-        for (int k = 0; k < 9; k++) ov[k] = 0.0f;
-        dL_dcenter2D[2 * idx] = 0.0f;
-        dL_dcenter2D[2 * idx + 1] = 0.0f;
-        for (int k = 0; k < 3 * M; k++) dL_dshs[(size_t)idx * M * 3 + k] = 0.0f;
-        for (int k = 0; k < C; k++) dL_dfeature[(size_t)idx * C + k] = 0.0f;
-        dL_dopacity[idx] = 0.0f;
-        return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row0 = idx - lane;                       // first triangle of this warp
+    const int nrows = min(32, P - row0);               // <= 0: the whole warp is past the end
+    const int q = (3 * M) / 4, rs4 = q + 1;            // float4 per row / tile row stride
+    float *tile_in = s_rows + (size_t)(2 * warp) * 32 * rs4 * 4, *tile_out = tile_in + 32 * rs4 * 4;
+    const float *sh_row = shs + (size_t)idx * M * 3;
+    float *gsh_row = dL_dshs + (size_t)idx * M * 3;
+    if (TILED) {
+        if (nrows <= 0) return;
+        if (use_shs && D > 0) warp_rows_load(shs + (size_t)row0 * M * 3, tile_in, q, rs4, nrows, lane);
+        __syncwarp();
+        sh_row = tile_in + lane * rs4 * 4;
+        gsh_row = tile_out + lane * rs4 * 4;
     }
+    const bool live = idx < P && radii[idx] > 0;
+    if (!live) {  // reference leaves its zero-initialised outputs untouched here (backward.cu:165)
+        if (idx < P) {
+            float *ov = dL_dvertex + 9 * (size_t)idx;
+            for (int k = 0; k < 9; k++) ov[k] = 0.0f;
+            dL_dcenter2D[2 * idx] = 0.0f;
+            dL_dcenter2D[2 * idx + 1] = 0.0f;
+            for (int k = 0; k < 3 * M; k++) gsh_row[k] = 0.0f;
+            for (int k = 0; k < C; k++) dL_dfeature[(size_t)idx * C + k] = 0.0f;
+            dL_dopacity[idx] = 0.0f;
+        }
+    } else {
+    float *ov = dL_dvertex + 9 * (size_t)idx;
     const float4 A0 = gacc[4 * (size_t)idx + 0], A1 = gacc[4 * (size_t)idx + 1], A2 = gacc[4 * (size_t)idx + 2], A3 = gacc[4 * (size_t)idx + 3];
     f2 g1 = mk2(A0.x, A0.y), g2 = mk2(A0.z, A0.w), g3 = mk2(A1.x, A1.y);
     if (moments) {
@@ -359,10 +414,10 @@ k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool ri
     const f3 gr1 = xf_vec_T(view, gr1v), gr2 = xf_vec_T(view, gr2v), gr3 = xf_vec_T(view, gr3v);
 
     if (use_shs) {
-        const f3 gsh = sh_colour_bwd(D, M, shs + (size_t)idx * M * 3, t.center, ld3(campos), clamp[idx], g_rgb, dL_dshs + (size_t)idx * M * 3);
+        const f3 gsh = sh_colour_bwd(D, M, sh_row, t.center, ld3(campos), clamp[idx], g_rgb, gsh_row);
         gcenter = gcenter + gsh;
     } else {
-        for (int k = 0; k < 3 * M; k++) dL_dshs[(size_t)idx * M * 3 + k] = 0.0f;
+        for (int k = 0; k < 3 * M; k++) gsh_row[k] = 0.0f;
     }
     st3(ov, (2 * gr1 - gr2 - gr3 + gcenter) / 3.0f);
     st3(ov + 3, (2 * gr2 - gr1 - gr3 + gcenter) / 3.0f);
@@ -373,15 +428,29 @@ k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool ri
     if (C > 1) dL_dfeature[(size_t)idx * C + 1] = g_rgb.y;
     if (C > 2) dL_dfeature[(size_t)idx * C + 2] = g_rgb.z;
     dL_dopacity[idx] = g_op;
+    }  // live
+    if (TILED) {
+        __syncwarp();
+        warp_rows_store(dL_dshs + (size_t)row0 * M * 3, tile_out, q, rs4, nrows, lane);
+    }
 }
 
 int ts2d_launch_preprocess_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, const int32_t *radii, GeomState gs,
                                const float *gacc, const ts2d_backward_out *out, cudaStream_t s)
 {
     const int P = g->P;
-    k_preprocess_bwd<<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(
-        cam->width, cam->height, P, g->sh_degree, g->M, g->C, g->use_shs != 0, f->rich_info != 0, cam->tan_fovx, cam->tan_fovy, cam->viewmatrix,
-        cam->projmatrix, cam->campos, g->vertex, g->shs, radii, gs.clamp, (const float4 *)gacc, ts2d_use_fast(g, f), gs.rec0, out->dL_dvertex, out->dL_dcenter2D, out->dL_dshs,
-        out->dL_dfeature, out->dL_dopacity);
+    const bool tiled = ts2d_rows_tileable(g->M, g->shs ? (const void *)g->shs : (const void *)out->dL_dshs, out->dL_dshs);
+#define TS2D_K9_ARGS                                                                                                                         \
+    cam->width, cam->height, P, g->sh_degree, g->M, g->C, g->use_shs != 0, f->rich_info != 0, cam->tan_fovx, cam->tan_fovy, cam->viewmatrix, \
+        cam->projmatrix, cam->campos, g->vertex, g->shs, radii, gs.clamp, (const float4 *)gacc, ts2d_use_fast(g, f), gs.rec0, out->dL_dvertex, \
+        out->dL_dcenter2D, out->dL_dshs, out->dL_dfeature, out->dL_dopacity
+    if (tiled) {
+        const size_t smem = (size_t)(TS2D_BLOCK / 32) * 2 * 32 * ((3 * g->M) / 4 + 1) * 16;
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_preprocess_bwd<true><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K9_ARGS);
+    } else {
+        k_preprocess_bwd<false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(TS2D_K9_ARGS);
+    }
+#undef TS2D_K9_ARGS
     return (int)cudaGetLastError();
 }

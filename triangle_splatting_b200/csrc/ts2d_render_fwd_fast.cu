@@ -16,6 +16,8 @@
 
 namespace {
 
+constexpr int FW_SLOTS = 16;  // triangles per contrib-statistics panel
+
 template <bool RICH>
 struct __align__(16) FwdEntry {
     float4 e1;   // v1.x, v1.y, v2.x, v2.y
