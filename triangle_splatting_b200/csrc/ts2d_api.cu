@@ -163,10 +163,10 @@ __global__ void k_export_geometry(int P, const float4 *rec0, const float4 *rec1,
         }
     }
     if (v2d) { float *o = v2d + 6 * (size_t)i; o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; }
-    if (area2) area2[i] = b.z;
+    if (area2) area2[i] = c.w;
     if (normal_view) { normal_view[3 * i] = q0.x; normal_view[3 * i + 1] = q0.y; normal_view[3 * i + 2] = q0.z; }
     if (v_depth) { v_depth[3 * i] = q0.w; v_depth[3 * i + 1] = q1.x; v_depth[3 * i + 2] = q1.y; }
-    if (depth) depth[i] = c.w;
+    if (depth) depth[i] = vis ? __uint_as_float(dkey[i]) : 0.0f;  // the depth sort key IS the fp32 bit pattern of the view depth
     if (rgb) { rgb[3 * i] = c.x; rgb[3 * i + 1] = c.y; rgb[3 * i + 2] = c.z; }
     const uint8_t m = vis ? clamp[i] : 0;
     if (clamped) { clamped[3 * i] = m & 1; clamped[3 * i + 1] = (m >> 1) & 1; clamped[3 * i + 2] = (m >> 2) & 1; }

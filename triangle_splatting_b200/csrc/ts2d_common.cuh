@@ -3,7 +3,7 @@
 // State layout in HBM (all private to this library, decoded only by ts2d_export_*):
 //
 //   geometry state (per triangle, P entries; written by k_preprocess)
-//     rec0   float4[3P]   48 B "raster record": {v1.x v1.y v2.x v2.y} {v3.x v3.y area2 opacity} {r g b depth}
+//     rec0   float4[3P]   48 B "raster record": {v1.x v1.y v2.x v2.y} {v3.x v3.y 1/area2 opacity} {r g b area2}
 //     rec1   float4[2P]   32 B rich record    : {n.x n.y n.z vd1} {vd2 vd3 0 0}        (rich_info only)
 //     dkey   u32[P]       fp32 bit pattern of view depth, 0xFFFFFFFF for culled triangles
 //     ids    u32[P]       iota (value input of the depth sort)

@@ -173,8 +173,8 @@ k_preprocess(int W, int H, int P, int D, int M, int C, bool rich, bool use_shs, 
             clamp[idx] = mask;
             const float depth = t.center_view.z;
             rec0[3 * (size_t)idx + 0] = make_float4(s1.x, s1.y, s2.x, s2.y);
-            rec0[3 * (size_t)idx + 1] = make_float4(s3.x, s3.y, area2, opacity[idx]);
-            rec0[3 * (size_t)idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, depth);
+            rec0[3 * (size_t)idx + 1] = make_float4(s3.x, s3.y, 1.0f / area2, opacity[idx]);  // reciprocal once per triangle, not per (tile, triangle)
+            rec0[3 * (size_t)idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, area2);
             if (rich) {
                 f3 n = cross3(t.r1v, t.r2v);
                 n = n / len3(n);
@@ -347,7 +347,7 @@ k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool ri
         // Jacobians (backward.cu:464-479) summed over pixels collapse to the fixed 6 -> 6 map below.
         const float4 r0 = rec0[3 * (size_t)idx], r1 = rec0[3 * (size_t)idx + 1];
         const f2 s1 = mk2(r0.x, r0.y), s2 = mk2(r0.z, r0.w), s3 = mk2(r1.x, r1.y);
-        const float inv = 1.0f / r1.z;
+        const float inv = r1.z;
         const f2 e12 = s2 - s1, e23 = s3 - s2, e31 = s1 - s3, w = s3 - s1;
         const float S1 = A0.x, S2 = A0.w;
         const f2 Q1 = mk2(A0.y, A0.z), Q2 = mk2(A1.x, A1.y);

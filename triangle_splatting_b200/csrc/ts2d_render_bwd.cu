@@ -125,12 +125,11 @@ k_render_bwd(int W, int H, int C, int gx, int shard_rank, int shard_world, int n
             for (int k = 0; k < 16; k++) v[k] = 0.0f;
             bool hit = false;
             if (pos < last) {
-                const float4 r0 = s_rec0[3 * j], r1 = s_rec0[3 * j + 1];
+                const float4 r0 = s_rec0[3 * j], r1 = s_rec0[3 * j + 1], r2 = s_rec0[3 * j + 2];
                 PairEval e;
-                if (eval_exact(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, two_gamma, pxf, pyf, e)) {
+                if (eval_exact(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r2.w, r1.w, two_gamma, pxf, pyf, e)) {
                     hit = true;
-                    const float4 r2 = s_rec0[3 * j + 2];
-                    const float area2 = r1.z, op = r1.w;
+                    const float area2 = r2.w, op = r1.w;
                     T = T / (1.0f - e.alpha);
                     const float contrib = e.alpha * T;
                     const float om = 1.0f - e.alpha;

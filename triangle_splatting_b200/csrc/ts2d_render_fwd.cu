@@ -67,12 +67,11 @@ k_render_fwd(int W, int H, int C, int gx, int shard_rank, int shard_world, int n
             float contrib = 0.0f;
             if (!done) {
                 last = base - range.x + j + 1;
-                const float4 r0 = s_rec0[3 * j], r1 = s_rec0[3 * j + 1];
+                const float4 r0 = s_rec0[3 * j], r1 = s_rec0[3 * j + 1], r2 = s_rec0[3 * j + 2];  // r1.z = 1/area2 (fast kernels), r2.w = area2
                 PairEval e;
-                if (eval_exact(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, two_gamma, pxf, pyf, e)) {
+                if (eval_exact(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r2.w, r1.w, two_gamma, pxf, pyf, e)) {
                     hit = true;
                     contrib = __fmul_rn(e.alpha, T);
-                    const float4 r2 = s_rec0[3 * j + 2];
                     acc0 = __fmaf_rn(contrib, r2.x, acc0);
                     acc1 = __fmaf_rn(contrib, r2.y, acc1);
                     acc2 = __fmaf_rn(contrib, r2.z, acc2);
