@@ -4,8 +4,8 @@
 // cooperatively (every thread loads one record, __syncthreads, everybody consumes) couples the 8 pixel
 // warps of a tile at every batch: ncu attributed 22 % of all warp-stall samples of the backward kernel to
 // those CTA barriers (warps cover sub-tiles with different amounts of surviving work).  Here a 9th warp
-// is a dedicated PRODUCER: its lanes read the list entries and issue one TMA bulk copy
-// (cp.async.bulk.shared.global, completion counted on an mbarrier) per 48-byte / 32-byte raster record
+// is a dedicated PRODUCER: its lanes read the list entries and issue asynchronous 16-byte copies
+// (cp.async / LDGSTS, completion counted on an mbarrier) of the 48-byte / 32-byte raster records
 // into a ring of shared-memory slots; the 8 CONSUMER warps wait on a slot's "full" mbarrier, work through
 // it at their own pace and arrive on its "empty" mbarrier.  No __syncthreads in the steady state; a fast
 // warp can run ahead of a slow one by the depth of the ring.
@@ -43,12 +43,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// Ampere-style asynchronous 16-byte copy global -> shared (LDGSTS, L2-only caching) and its mbarrier hook: the
+// arrive fires once all earlier cp.async of the executing thread have landed (.noinc: the arrival is pre-counted in
+// the barrier's init count).  Measured on B200: for 48/32-byte raster records the LDGSTS path sustains the ring while
+// one cp.async.bulk (TMA) per record does not -- three CTAs per SM x 256 tiny bulk copies per batch serialise in the
+// TMA unit and the consumer warps starve (profiles/README.md, "TMA vs LDGSTS staging").
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // TMA 1-D bulk copy global -> shared; bytes % 16 == 0, both addresses 16-byte aligned.
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// Out-of-line copy of the exact pair evaluation for the rare in-band fallback of the fast kernels (powf + expf + two IEEE
+// divides are ~250 instructions: inlined they would sit in the middle of the hot loop's instruction-cache footprint).
+static __device__ __noinline__ bool eval_exact_slow(const float4 e1, float v3x, float v3y, float area2, float op, float two_gamma, float px,
+                                                    float py, PairEval &e)
+{
+    return eval_exact(e1.x, e1.y, e1.z, e1.w, v3x, v3y, area2, op, two_gamma, px, py, e);
 }
 
 // Conservative coverage test of one triangle against ONE sub-tile rectangle [x0, x0+7] x [y0, y0+3] (pixel offsets

@@ -1,9 +1,8 @@
 // ts2d_render_bwd_fast.cu -- fast reverse-walk gradient accumulation (K8, flags.exact == 0).
 //
 // Same contract as k_render_bwd (ts2d_render_bwd.cu, the mirror of R2D/src/backward.cu:265-493) with the
-// forward fast kernel's machinery (TMA/mbarrier ring fed by a producer warp, per-warp sub-tile coverage test,
-// reference-shaped fast barycentrics, decision bands with eval_exact fallback -- so the set of contributing
-// pairs is exactly the one the forward pass blended).
+// forward fast kernel's machinery (sub-tile masks, reference-shaped fast barycentrics, decision bands with
+// eval_exact fallback -- so the set of contributing pairs is exactly the one the forward pass blended).
 //
 // What is different from the reference is how the per-pair contributions are summed over pixels.  The reference
 // issues 10-16 global atomics per contributing (pixel, triangle) pair.  Here every one of the 16 per-triangle
@@ -12,37 +11,34 @@
 // f is a per-pixel constant (upstream gradients, pixel offsets) -- the barycentrics being affine in the pixel,
 // their Jacobians reduce to first moments (see ts2d_preprocess.cu: the moments -> vertex-gradient map).
 //   phase 1 (lane = pixel):    walk the warp's covered entries back to front, run the T / colour recurrences,
-//                              park the three scalars of each pair in an 8-row shared-memory panel W[row][pixel];
-//   phase 2 (lane = triangle): every 8 rows, each lane owns (row, quarter of the 32 pixels) and accumulates the
-//                              16 sums with plain FFMAs from W and the per-pixel table F -- no per-pair shuffles,
-//                              no selects -- then two xor-combines and one 16-byte RED per lane.
-// This replaces a 16-value warp butterfly per pair-iteration (16 SHFL + 16 FADD + 30 SEL) by 3 STS + ~40
+//                              park the three scalars of each pair in a 16-slot shared-memory panel W[slot][pixel];
+//   phase 2 (lane = triangle): every 16 slots, each lane owns (slot, half of the 32 pixels) and accumulates the
+//                              16 sums with plain FFMAs from W and the per-pixel table F -- no shuffles, no
+//                              selects -- then one xor-16 combine and four 16-byte REDs per triangle.
+// This replaces a 16-value warp butterfly per pair-iteration (16 SHFL + 16 FADD + 30 SEL) by 3 STS + ~30
 // amortised instructions, and moves all Jacobian arithmetic out of the per-pixel loop.
-#include "ts2d_pipe.cuh"
+#include "ts2d_fast.cuh"
 
 namespace {
 
-constexpr int BW_NB = 128;      // list entries per ring slot
-constexpr int BW_NS = 3;        // ring depth
-constexpr int BW_ROWS = 8;      // triangles per phase-2 panel
+constexpr int BW_BATCH = 128;   // list entries staged per batch
+constexpr int BW_SLOTS = 16;    // triangles per phase-2 panel
 constexpr int BW_WROW = 97;     // 3 scalars x 32 pixels + 1 pad word: conflict-free for both phases
-constexpr int BW_THREADS = 288; // 8 consumer warps + 1 producer warp
+constexpr int BW_FCOLS = 12;
 
-struct __align__(16) RowInfo {  // what phase 2 needs to know about the triangle parked in a panel row
+struct __align__(16) BwdEntry {
     float4 e1;   // v1.x, v1.y, v2.x, v2.y
     float4 e2;   // v3.x, v3.y, 1/area2, opacity
-    float4 x;    // vd1, vd2, vd3, triangle id (bits)
+    float4 col;  // r, g, b, triangle id (bits)
+    float4 q0;   // n.x, n.y, n.z, vd1
+    float4 q1;   // vd2, vd3, -, -
 };
 
-template <bool RICH>
-struct __align__(16) BwdSmem {
-    float4 rec0[BW_NS][BW_NB][3];
-    float4 rec1[BW_NS][RICH ? BW_NB : 1][2];
-    uint32_t id[BW_NS][BW_NB];
-    float4 F[8][32][2];              // per warp, per pixel: {gp0 gp1 gp2 gd} {gn0 gn1 gn2 -}
-    float W[8][BW_ROWS][BW_WROW];    // per warp panel: [row][scalar * 32 + pixel]
-    RowInfo info[8][BW_ROWS];
-    uint64_t full[BW_NS], empty[BW_NS];
+struct BwdSmem {
+    BwdEntry ent[BW_BATCH];
+    float F[8][32][BW_FCOLS];        // per warp, per pixel: gp0 gp1 gp2 gd | gn0 gn1 gn2 dx | dy gd*dx gd*dy -
+    float W[8][BW_SLOTS][BW_WROW];   // per warp panel: [slot][scalar * 32 + pixel]
+    uint8_t mask[BW_BATCH];
     uint32_t tile_last;
 };
 
@@ -52,7 +48,7 @@ __device__ __forceinline__ void red_add4(float *addr, float a, float b, float c,
 }
 
 template <bool RICH, bool GAMMA1>
-__global__ void __launch_bounds__(BW_THREADS, 3)
+__global__ void __launch_bounds__(TS2D_BLOCK)
 k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world, int n_tiles, float gamma, const uint2 *__restrict__ ranges,
                   const uint32_t *__restrict__ list, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1, float bg_depth,
                   const float *__restrict__ background, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
@@ -60,19 +56,17 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                   const float *__restrict__ dL_dout_normal, float *__restrict__ gacc)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BwdSmem<RICH> &S = *reinterpret_cast<BwdSmem<RICH> *>(smem_raw);
+    BwdSmem &S = *reinterpret_cast<BwdSmem *>(smem_raw);
 
     const int tile = blockIdx.x * shard_world + shard_rank;
     if (tile >= n_tiles) return;
     const int tile_x = tile % gx, tile_y = tile / gx;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int cw = warp & 7;  // consumer index (the producer warp computes harmless duplicates of warp 0's pixel set-up)
-    const int lx = (cw & 1) * 8 + (lane & 7), ly = (cw >> 1) * 4 + (lane >> 3);
+    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
     const int px = tile_x * TS2D_TILE + lx, py = tile_y * TS2D_TILE + ly;
-    const bool inside = px < W_ && py < H && warp < 8;
+    const bool inside = px < W_ && py < H;
     const float pxf = (float)px, pyf = (float)py;
     const float ox = (float)(tile_x * TS2D_TILE), oy = (float)(tile_y * TS2D_TILE);
-    const float sub_x0 = (float)((cw & 1) * 8), sub_y0 = (float)((cw >> 1) * 4);
     const size_t pix = (size_t)W_ * py + px;
     const size_t HW = (size_t)H * W_;
     GammaK gk = make_gamma(gamma);
@@ -97,233 +91,205 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
             gd = dL_dout_depth[pix];
         }
     }
-    if (warp < 8) {  // per-pixel table for phase 2
-        S.F[warp][lane][0] = make_float4(gp0, gp1, gp2, gd);
-        S.F[warp][lane][1] = make_float4(gn0, gn1, gn2, 0.0f);
+    {   // per-pixel table for phase 2
+        float *f = S.F[warp][lane];
+        const float dxl = (float)lx, dyl = (float)ly;  // pixel offset from the tile origin
+        *reinterpret_cast<float4 *>(f) = make_float4(gp0, gp1, gp2, gd);
+        *reinterpret_cast<float4 *>(f + 4) = make_float4(gn0, gn1, gn2, dxl);
+        *reinterpret_cast<float4 *>(f + 8) = make_float4(dyl, gd * dxl, gd * dyl, 0.0f);
     }
     const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last);
-    if (tid == 0) {
-        for (int s = 0; s < BW_NS; s++) {
-            mbar_init(&S.full[s], 32);
-            mbar_init(&S.empty[s], 8);
-        }
-        S.tile_last = 0;
-        mbar_fence_init();
-    }
+    if (tid == 0) S.tile_last = 0;
     __syncthreads();
     // geometry upstream gradients all zero in this tile (w_geometry = 0 training configs): the normal / depth
     // terms are exactly zero for the reference too, so skipping them changes no bit of the result
     const bool geo = RICH && __syncthreads_or(gd != 0.0f || gn0 != 0.0f || gn1 != 0.0f || gn2 != 0.0f);
-    if (lane == 0 && warp < 8) atomicMax(&S.tile_last, warp_last);
+    if (lane == 0) atomicMax(&S.tile_last, warp_last);
     __syncthreads();
-    // list positions >= tile_last were visited by no pixel of the tile: never staged.
-    // Entries are streamed in REVERSE list order: entry t of batch b is list position tile_last - 1 - (b * NB + t).
     const uint32_t tile_last = S.tile_last;
-    const int nb = (int)((tile_last + BW_NB - 1) / BW_NB);
 
-    if (warp == 8) {
-        // ------------------------------------------------------------------ producer warp
-        constexpr uint32_t kBytes = 48u + (RICH ? 32u : 0u);
-        for (int b = 0; b < nb; b++) {
-            const int slot = b % BW_NS;
-            if (b >= BW_NS) mbar_wait(&S.empty[slot], ((b / BW_NS) - 1) & 1);
-            const int n = min((uint32_t)BW_NB, tile_last - (uint32_t)b * BW_NB);
-            uint32_t ids[BW_NB / 32];
-            uint32_t cnt = 0;
-#pragma unroll
-            for (int i = 0; i < BW_NB / 32; i++) {
-                const int t = i * 32 + lane;
-                if (t < n) {
-                    ids[i] = list[range.x + tile_last - 1 - ((uint32_t)b * BW_NB + t)];
-                    S.id[slot][t] = ids[i];
-                    cnt++;
-                }
-            }
-            mbar_arrive_expect_tx(&S.full[slot], cnt * kBytes);
-#pragma unroll
-            for (int i = 0; i < BW_NB / 32; i++) {
-                const int t = i * 32 + lane;
-                if (t < n) {
-                    bulk_g2s(&S.rec0[slot][t][0], rec0 + 3 * (size_t)ids[i], 48, &S.full[slot]);
-                    if (RICH) bulk_g2s(&S.rec1[slot][t][0], rec1 + 2 * (size_t)ids[i], 32, &S.full[slot]);
-                }
-            }
-        }
-        return;
-    }
-
-    // ---------------------------------------------------------------------- consumer warps
     float(*Wp)[BW_WROW] = S.W[warp];
-    RowInfo *info = S.info[warp];
-    int prow = 0;  // next free panel row
-    const int k = lane & 7, quarter = lane >> 3;
+    int slot = 0;        // next free slot of the panel
+    int my_j = 0;        // staged index of the triangle parked in slot (lane & 15)
+    const int k = lane & 15, half = lane >> 4;
 
-    // phase 2: lane (k, quarter) sums panel row k over pixels quarter*8 .. quarter*8+7, then flushes the triangle
+    // phase 2: lane (k, half) sums the panel row k over pixels half*16 .. half*16+15 and flushes the triangle
     auto flush_panel = [&](int filled) {
         __syncwarp();
         float s_c0 = 0.f, s_c1 = 0.f, s_c2 = 0.f, s_n0 = 0.f, s_n1 = 0.f, s_n2 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
         float u10 = 0.f, u1x = 0.f, u1y = 0.f, u20 = 0.f, u2x = 0.f, u2y = 0.f, s_op = 0.f;
         if (k < filled) {
             const float *row = Wp[k];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int p = quarter * 8 + i;                       // pixel (lane index of phase 1) inside the sub-tile
-                const float dxp = sub_x0 + (float)i;                 // its offset from the tile origin: x = p & 7 = i
-                const float dyp = sub_y0 + (float)quarter;           //                                 y = p >> 3 = quarter
+#pragma unroll 4
+            for (int i = 0; i < 16; i++) {
+                const int p = half * 16 + i;
                 const float c = row[p], w1 = row[32 + p], Dp = row[64 + p];
-                const float4 f0 = S.F[warp][p][0];
+                const float *f = S.F[warp][p];
+                const float4 f0 = *reinterpret_cast<const float4 *>(f);
+                const float4 f1 = *reinterpret_cast<const float4 *>(f + 4);
                 s_c0 = fmaf(c, f0.x, s_c0);
                 s_c1 = fmaf(c, f0.y, s_c1);
                 s_c2 = fmaf(c, f0.z, s_c2);
                 s_op += w1;
-                const uint32_t sel = __float_as_uint(Dp) & 3u;       // arg-min barycentric (1, 2, 3) packed in the two LSBs
+                const uint32_t sel = __float_as_uint(Dp) & 3u;     // arg-min barycentric (1, 2, 3) packed in the two LSBs
                 const float u1 = sel == 1u ? Dp : (sel == 3u ? -Dp : 0.0f);
                 const float u2 = sel == 2u ? Dp : (sel == 3u ? -Dp : 0.0f);
+                float dyp = 0.f;
                 if (geo) {
-                    const float4 f1 = S.F[warp][p][1];
-                    const float cg = c * f0.w;                       // contrib * gd
+                    const float4 f2 = *reinterpret_cast<const float4 *>(f + 8);
+                    dyp = f2.x;
                     s_n0 = fmaf(c, f1.x, s_n0);
                     s_n1 = fmaf(c, f1.y, s_n1);
                     s_n2 = fmaf(c, f1.z, s_n2);
-                    m0 += cg;
-                    m1 = fmaf(cg, dxp, m1);
-                    m2 = fmaf(cg, dyp, m2);
+                    m0 = fmaf(c, f0.w, m0);
+                    m1 = fmaf(c, f2.y, m1);
+                    m2 = fmaf(c, f2.z, m2);
+                } else {
+                    dyp = f[8];
                 }
                 u10 += u1;
-                u1x = fmaf(u1, dxp, u1x);
+                u1x = fmaf(u1, f1.w, u1x);
                 u1y = fmaf(u1, dyp, u1y);
                 u20 += u2;
-                u2x = fmaf(u2, dxp, u2x);
+                u2x = fmaf(u2, f1.w, u2x);
                 u2y = fmaf(u2, dyp, u2y);
             }
         }
-#define XQ(v) v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16)
-        XQ(s_c0); XQ(s_c1); XQ(s_c2); XQ(s_op); XQ(u10); XQ(u1x); XQ(u1y); XQ(u20); XQ(u2x); XQ(u2y);
-        if (geo) { XQ(s_n0); XQ(s_n1); XQ(s_n2); XQ(m0); XQ(m1); XQ(m2); }
-#undef XQ
+#define XH(v) v += __shfl_xor_sync(0xffffffffu, v, 16)
+        XH(s_c0); XH(s_c1); XH(s_c2); XH(s_op); XH(u10); XH(u1x); XH(u1y); XH(u20); XH(u2x); XH(u2y);
+        if (geo) { XH(s_n0); XH(s_n1); XH(s_n2); XH(m0); XH(m1); XH(m2); }
+#undef XH
         if (k < filled) {
-            const float4 e1 = info[k].e1, e2 = info[k].e2, ex = info[k].x;
-            float *g = gacc + (size_t)__float_as_uint(ex.w) * GACC_STRIDE;
+            const BwdEntry &E = S.ent[my_j];
+            const float4 e1 = E.e1, e2 = E.e2;
+            float *g = gacc + (size_t)__float_as_uint(E.col.w) * GACC_STRIDE;
             const float inv = e2.z;
+            // affine barycentrics about the tile origin: a_i(d) = a_io + A_i dx + B_i dy
             const float p1x = e1.x - ox, p1y = e1.y - oy, p2x = e1.z - ox, p2y = e1.w - oy, p3x = e2.x - ox, p3y = e2.y - oy;
             float S1 = u10, M1x = u1x, M1y = u1y, S2 = u20, M2x = u2x, M2y = u2y;
             float gv0 = 0.f, gv1 = 0.f, gv2 = 0.f;
             if (geo) {
-                // affine barycentrics about the tile origin: a_i(d) = a_io + A_i dx + B_i dy
                 const float a1o = (p2x * p3y - p2y * p3x) * inv, A1 = (e1.w - e2.y) * inv, B1 = (e2.x - e1.z) * inv;
                 const float a2o = (p3x * p1y - p3y * p1x) * inv, A2 = (e2.y - e1.y) * inv, B2 = (e1.x - e2.x) * inv;
                 const float a3o = 1.0f - a1o - a2o, A3 = -A1 - A2, B3 = -B1 - B2;
+                const float vd1 = E.q0.w, vd2 = E.q1.x, vd3 = E.q1.y;
                 gv0 = fmaf(B1, m2, fmaf(A1, m1, a1o * m0));   // sum gd contrib a_1
                 gv1 = fmaf(B2, m2, fmaf(A2, m1, a2o * m0));
                 gv2 = fmaf(B3, m2, fmaf(A3, m1, a3o * m0));
-                const float d13 = ex.x - ex.z, d23 = ex.y - ex.z;   // depth term of ga_k = (vd_k - vd_3) gd contrib
+                const float d13 = vd1 - vd3, d23 = vd2 - vd3;   // depth term of ga_k = (vd_k - vd_3) gd contrib
                 S1 = fmaf(d13, m0, S1); M1x = fmaf(d13, m1, M1x); M1y = fmaf(d13, m2, M1y);
                 S2 = fmaf(d23, m0, S2); M2x = fmaf(d23, m1, M2x); M2y = fmaf(d23, m2, M2y);
             }
             // moments about v1: q = p - v1 = d - (v1 - o)
             const float Q1x = fmaf(-p1x, S1, M1x), Q1y = fmaf(-p1y, S1, M1y), Q2x = fmaf(-p1x, S2, M2x), Q2y = fmaf(-p1y, S2, M2y);
-            if (quarter == 0) red_add4(g, S1, Q1x, Q1y, S2);
-            else if (quarter == 1) red_add4(g + 4, Q2x, Q2y, s_op, s_n0);
-            else if (quarter == 2) red_add4(g + 8, s_c0, s_c1, s_c2, s_n1);
-            else if (geo) red_add4(g + 12, s_n2, gv0, gv1, gv2);
+            if (half == 0) {
+                red_add4(g, S1, Q1x, Q1y, S2);
+                red_add4(g + 4, Q2x, Q2y, s_op, s_n0);
+            } else {
+                red_add4(g + 8, s_c0, s_c1, s_c2, s_n1);
+                if (geo) red_add4(g + 12, s_n2, gv0, gv1, gv2);
+            }
         }
         __syncwarp();
     };
 
-    for (int b = 0; b < nb; b++) {
-        const int slot = b % BW_NS;
-        mbar_wait(&S.full[slot], (b / BW_NS) & 1);
-        const uint32_t first = tile_last - 1 - (uint32_t)b * BW_NB;   // list position of the slot's entry 0
-        if (first < warp_last + BW_NB) {                              // otherwise the whole slot is beyond this warp's pixels
-            const int n = min((uint32_t)BW_NB, tile_last - (uint32_t)b * BW_NB);
-            uint32_t bits[BW_NB / 32];
-#pragma unroll
-            for (int g = 0; g < BW_NB / 32; g++) {
-                const int t = g * 32 + lane;
-                bool c = false;
-                if (t < n && first - t < warp_last) c = subtile_covers(S.rec0[slot][t][0], S.rec0[slot][t][1], ox, oy, sub_x0, sub_y0, gk);
-                bits[g] = __ballot_sync(0xffffffffu, c);
+    // batches are staged in REVERSE list order: staged slot t of a batch is list position (top - t)
+    for (uint32_t done_cnt = len - tile_last; done_cnt < len; done_cnt += BW_BATCH) {
+        __syncthreads();
+        const int n = min((uint32_t)BW_BATCH, len - done_cnt);
+        if (tid < n) {
+            const uint32_t id = list[range.y - 1 - done_cnt - tid];
+            const float4 *r = rec0 + 3 * (size_t)id;
+            const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+            const float inv = r1.z;  // the record carries 1/area2 (K1 computes it once per triangle)
+            BwdEntry &E = S.ent[tid];
+            E.e1 = r0;
+            E.e2 = r1;
+            E.col = make_float4(r2.x, r2.y, r2.z, __uint_as_float(id));
+            if (RICH) {
+                const float4 *q = rec1 + 2 * (size_t)id;
+                E.q0 = __ldg(q);
+                E.q1 = __ldg(q + 1);
             }
-#pragma unroll
-            for (int g = 0; g < BW_NB / 32; g++) {
-                uint32_t rem = bits[g];
-                while (rem) {
-                    const int j = g * 32 + (__ffs(rem) - 1);
-                    rem &= rem - 1;
-                    const uint32_t pos = first - j;  // 0-based list position
-                    const float4 *E = S.rec0[slot][j];
-                    const float4 e1 = E[0], e2 = E[1];
-                    float w_c = 0.0f, w_op = 0.0f, w_D = 0.0f;
-                    if (pos < last) {
-                        FastPair f;
-                        bool unc;
-                        bool hit = eval_fast(e1, e2, pxf, pyf, gk, f, unc);
-                        // one more reference decision lives in the backward pass: op*G < 0.99 (clamp not active)
-                        unc = unc || (fabsf(f.og - 0.99f) <= 0.99f * gk.band);
-                        if (unc) {
-                            PairEval e;
-                            hit = eval_exact(e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, E[2].w, e2.w, gk.two_gamma, pxf, pyf, e);
-                            f.a1 = e.a1; f.a2 = e.a2; f.a3 = e.a3; f.ecc = e.ecc;
-                            if (hit) { f.power = e.power; f.G = e.G; f.og = __fmul_rn(e2.w, e.G); f.alpha = e.alpha; }
-                        }
-                        if (hit) {
-                            const float4 col = E[2];
-                            const float om = 1.0f - f.alpha;
-                            T = T * rcp_approx(om);
-                            w_c = f.alpha * T;
-                            float dL_dcontrib = gp0 * (col.x - acc0);
-                            dL_dcontrib = fmaf(gp1, col.y - acc1, dL_dcontrib);
-                            dL_dcontrib = fmaf(gp2, col.z - acc2, dL_dcontrib);
-                            acc0 = fmaf(f.alpha, col.x, om * acc0);
-                            acc1 = fmaf(f.alpha, col.y, om * acc1);
-                            acc2 = fmaf(f.alpha, col.z, om * acc2);
-                            if (geo) {
-                                const float4 q0 = S.rec1[slot][j][0], q1 = S.rec1[slot][j][1];
-                                dL_dcontrib = fmaf(gn0, q0.x - accn0, dL_dcontrib);
-                                dL_dcontrib = fmaf(gn1, q0.y - accn1, dL_dcontrib);
-                                dL_dcontrib = fmaf(gn2, q0.z - accn2, dL_dcontrib);
-                                accn0 = fmaf(f.alpha, q0.x, om * accn0);
-                                accn1 = fmaf(f.alpha, q0.y, om * accn1);
-                                accn2 = fmaf(f.alpha, q0.z, om * accn2);
-                                const float depth = fmaf(q1.y, f.a3, fmaf(q0.w, f.a1, q1.x * f.a2));
-                                dL_dcontrib = fmaf(gd, depth - accd, dL_dcontrib);
-                                accd = fmaf(f.alpha, depth, om * accd);
-                            }
-                            const float dL_dalpha = dL_dcontrib * T;
-                            w_op = dL_dalpha * f.G;  // unconditional (backward.cu:490)
-                            const float dL_dpower = (f.og < 0.99f) ? dL_dalpha * f.alpha : 0.0f;
-                            const float D = -3.0f * dL_dpower * gk.two_gamma * f.power * rcp_approx(f.ecc + TS2D_EPS);
-                            // sub-gradient of min: first arg-min in the order a1, a2, a3 (backward.cu:449-461)
-                            const uint32_t sel = (f.a1 <= f.a2 && f.a1 <= f.a3) ? 1u : ((f.a2 <= f.a1 && f.a2 <= f.a3) ? 2u : 3u);
-                            w_D = __uint_as_float((__float_as_uint(D) & ~3u) | sel);
-                        }
+            S.mask[tid] = (uint8_t)subtile_mask(r0, r1, inv, ox, oy, gk);
+        }
+        __syncthreads();
+
+        for (int c = 0; c * 32 < n; c++) {
+            const int idx = c * 32 + lane;
+            const uint32_t mine = (idx < n) ? (uint32_t)S.mask[idx] : 0u;
+            uint32_t bits = __ballot_sync(0xffffffffu, (mine >> warp) & 1u);
+            while (bits) {
+                const int j = c * 32 + (__ffs(bits) - 1);
+                bits &= bits - 1;
+                const uint32_t pos = len - 1 - done_cnt - j;  // 0-based list position
+                if (pos >= warp_last) continue;                // warp-uniform
+                const BwdEntry &E = S.ent[j];
+                const float4 e1 = E.e1, e2 = E.e2;
+                float w_c = 0.0f, w_op = 0.0f, w_D = 0.0f;
+                if (pos < last) {
+                    FastPair f;
+                    bool unc;
+                    bool hit = eval_fast(e1, e2, pxf, pyf, gk, f, unc);
+                    // one more reference decision lives in the backward pass: op*G < 0.99 (clamp not active)
+                    unc = unc || (fabsf(f.og - 0.99f) <= 0.99f * gk.band);
+                    if (unc) {
+                        const float area2 = __ldg(&rec0[3 * (size_t)__float_as_uint(E.col.w) + 2].w);
+                        PairEval e;
+                        hit = eval_exact(e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, area2, e2.w, gk.two_gamma, pxf, pyf, e);
+                        f.a1 = e.a1; f.a2 = e.a2; f.a3 = e.a3; f.ecc = e.ecc;
+                        if (hit) { f.power = e.power; f.G = e.G; f.og = __fmul_rn(e2.w, e.G); f.alpha = e.alpha; }
                     }
-                    if (__ballot_sync(0xffffffffu, w_c != 0.0f) == 0u) continue;
-                    float *row = Wp[prow];
-                    row[lane] = w_c;
-                    row[32 + lane] = w_op;
-                    row[64 + lane] = w_D;
-                    if (lane == 0) {
-                        float vd1 = 0.f, vd2 = 0.f, vd3 = 0.f;
-                        if (RICH) {
-                            const float4 q0 = S.rec1[slot][j][0], q1 = S.rec1[slot][j][1];
-                            vd1 = q0.w; vd2 = q1.x; vd3 = q1.y;
+                    if (hit) {
+                        const float4 col = E.col;
+                        const float om = 1.0f - f.alpha;
+                        T = T * rcp_approx(om);
+                        w_c = f.alpha * T;
+                        float dL_dcontrib = gp0 * (col.x - acc0);
+                        dL_dcontrib = fmaf(gp1, col.y - acc1, dL_dcontrib);
+                        dL_dcontrib = fmaf(gp2, col.z - acc2, dL_dcontrib);
+                        acc0 = fmaf(f.alpha, col.x, om * acc0);
+                        acc1 = fmaf(f.alpha, col.y, om * acc1);
+                        acc2 = fmaf(f.alpha, col.z, om * acc2);
+                        if (geo) {
+                            const float4 q0 = E.q0, q1 = E.q1;
+                            dL_dcontrib = fmaf(gn0, q0.x - accn0, dL_dcontrib);
+                            dL_dcontrib = fmaf(gn1, q0.y - accn1, dL_dcontrib);
+                            dL_dcontrib = fmaf(gn2, q0.z - accn2, dL_dcontrib);
+                            accn0 = fmaf(f.alpha, q0.x, om * accn0);
+                            accn1 = fmaf(f.alpha, q0.y, om * accn1);
+                            accn2 = fmaf(f.alpha, q0.z, om * accn2);
+                            const float depth = fmaf(q1.y, f.a3, fmaf(q0.w, f.a1, q1.x * f.a2));
+                            dL_dcontrib = fmaf(gd, depth - accd, dL_dcontrib);
+                            accd = fmaf(f.alpha, depth, om * accd);
                         }
-                        info[prow].e1 = e1;
-                        info[prow].e2 = e2;
-                        info[prow].x = make_float4(vd1, vd2, vd3, __uint_as_float(S.id[slot][j]));
+                        const float dL_dalpha = dL_dcontrib * T;
+                        w_op = dL_dalpha * f.G;  // unconditional (backward.cu:490)
+                        const float dL_dpower = (f.og < 0.99f) ? dL_dalpha * f.alpha : 0.0f;
+                        const float D = -3.0f * dL_dpower * gk.two_gamma * f.power * rcp_approx(f.ecc + TS2D_EPS);
+                        // sub-gradient of min: first arg-min in the order a1, a2, a3 (backward.cu:449-461)
+                        const uint32_t sel = (f.a1 <= f.a2 && f.a1 <= f.a3) ? 1u : ((f.a2 <= f.a1 && f.a2 <= f.a3) ? 2u : 3u);
+                        w_D = __uint_as_float((__float_as_uint(D) & ~3u) | sel);
                     }
-                    if (++prow == BW_ROWS) {
-                        flush_panel(BW_ROWS);
-                        prow = 0;
-                    }
+                }
+                if (__ballot_sync(0xffffffffu, w_c != 0.0f) == 0u) continue;
+                float *row = Wp[slot];
+                row[lane] = w_c;
+                row[32 + lane] = w_op;
+                row[64 + lane] = w_D;
+                if (k == slot) my_j = j;
+                if (++slot == BW_SLOTS) {
+                    flush_panel(BW_SLOTS);
+                    slot = 0;
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.empty[slot]);
+        // the staging buffer is about to be overwritten: flush triangles that still live in the panel
+        if (slot) {
+            flush_panel(slot);
+            slot = 0;
+        }
     }
-    if (prow) flush_panel(prow);
 }
 
 }  // namespace
@@ -338,14 +304,14 @@ int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
     TS2D_CUDA_TRY(cudaMemsetAsync(gacc, 0, sizeof(float) * GACC_STRIDE * (size_t)g->P, s));
     if (owned <= 0) return 0;
     const bool g1 = g->gamma == 1.0f;
+    const size_t smem = sizeof(BwdSmem);
 #define TS2D_BWD_ARGS                                                                                                                      \
     W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, list, gs.rec0, gs.rec1, g->background_depth, g->background, \
         is.final_T, is.n_contrib, loss->dL_dout_feature
 #define TS2D_BWD_LAUNCH(R, G, ...)                                                                                          \
     do {                                                                                                                    \
-        const size_t smem = sizeof(BwdSmem<R>);                                                                             \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_bwd_fast<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_render_bwd_fast<R, G><<<owned, BW_THREADS, smem, s>>>(TS2D_BWD_ARGS, __VA_ARGS__, gacc);                          \
+        k_render_bwd_fast<R, G><<<owned, TS2D_BLOCK, smem, s>>>(TS2D_BWD_ARGS, __VA_ARGS__, gacc);                          \
     } while (0)
     if (f->rich_info) {
         if (g1) TS2D_BWD_LAUNCH(true, true, loss->dL_dout_depth, loss->dL_dout_normal);
