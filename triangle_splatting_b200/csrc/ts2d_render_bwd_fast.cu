@@ -11,10 +11,10 @@
 // f is a per-pixel constant (upstream gradients, pixel offsets) -- the barycentrics being affine in the pixel,
 // their Jacobians reduce to first moments (see ts2d_preprocess.cu: the moments -> vertex-gradient map).
 //   phase 1 (lane = pixel):    walk the warp's covered entries back to front, run the T / colour recurrences,
-//                              park the three scalars of each pair in a 16-slot shared-memory panel W[slot][pixel];
-//   phase 2 (lane = triangle): every 16 slots, each lane owns (slot, half of the 32 pixels) and accumulates the
-//                              16 sums with plain FFMAs from W and the per-pixel table F -- no shuffles, no
-//                              selects -- then one xor-16 combine and four 16-byte REDs per triangle.
+//                              park the three scalars of each pair in an 8-row shared-memory panel W[row][pixel];
+//   phase 2 (lane = triangle): every 8 rows, each lane owns (row, quarter of the 32 pixels) and accumulates the
+//                              16 sums with plain FFMAs from W and the per-pixel table F -- no per-pair shuffles,
+//                              no selects -- then two xor-combines and one 16-byte RED per lane (out of line).
 // This replaces a 16-value warp butterfly per pair-iteration (16 SHFL + 16 FADD + 30 SEL) by 3 STS + ~30
 // amortised instructions, and moves all Jacobian arithmetic out of the per-pixel loop.
 #include "ts2d_fast.cuh"
@@ -22,9 +22,8 @@
 namespace {
 
 constexpr int BW_BATCH = 128;   // list entries staged per batch
-constexpr int BW_SLOTS = 16;    // triangles per phase-2 panel
+constexpr int BW_ROWS = 8;      // triangles per phase-2 panel
 constexpr int BW_WROW = 97;     // 3 scalars x 32 pixels + 1 pad word: conflict-free for both phases
-constexpr int BW_FCOLS = 12;
 
 struct __align__(16) BwdEntry {
     float4 e1;   // v1.x, v1.y, v2.x, v2.y
@@ -34,10 +33,17 @@ struct __align__(16) BwdEntry {
     float4 q1;   // vd2, vd3, -, -
 };
 
-struct BwdSmem {
+struct __align__(16) RowInfo {  // what phase 2 needs to know about the triangle parked in a panel row
+    float4 e1;   // v1.x, v1.y, v2.x, v2.y
+    float4 e2;   // v3.x, v3.y, 1/area2, opacity
+    float4 x;    // vd1, vd2, vd3, triangle id (bits)
+};
+
+struct __align__(16) BwdSmem {
     BwdEntry ent[BW_BATCH];
-    float F[8][32][BW_FCOLS];        // per warp, per pixel: gp0 gp1 gp2 gd | gn0 gn1 gn2 dx | dy gd*dx gd*dy -
-    float W[8][BW_SLOTS][BW_WROW];   // per warp panel: [slot][scalar * 32 + pixel]
+    float4 F[8][32][2];              // per warp, per pixel: {gp0 gp1 gp2 gd} {gn0 gn1 gn2 -}
+    float W[8][BW_ROWS][BW_WROW];    // per warp panel: [row][scalar * 32 + pixel]
+    RowInfo info[8][BW_ROWS];
     uint8_t mask[BW_BATCH];
     uint32_t tile_last;
 };
@@ -47,8 +53,84 @@ __device__ __forceinline__ void red_add4(float *addr, float a, float b, float c,
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// phase 2 (out of line: one copy keeps the kernel inside the instruction cache and out of the walk loop's register budget).
+// lane (k, quarter) sums panel row k over pixels quarter*8 .. quarter*8+7, then flushes the triangle.
+static __device__ __noinline__ void bwd_flush_panel(const float (*Wp)[BW_WROW], const RowInfo *info, const float4 (*F)[2], float *__restrict__ gacc,
+                                                    float ox, float oy, float sub_x0, float sub_y0, bool geo, int filled, int lane)
+{
+    const int k = lane & 7, quarter = lane >> 3;
+        __syncwarp();
+        float s_c0 = 0.f, s_c1 = 0.f, s_c2 = 0.f, s_n0 = 0.f, s_n1 = 0.f, s_n2 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
+        float u10 = 0.f, u1x = 0.f, u1y = 0.f, u20 = 0.f, u2x = 0.f, u2y = 0.f, s_op = 0.f;
+        if (k < filled) {
+            const float *row = Wp[k];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int p = quarter * 8 + i;                       // pixel (lane index of phase 1) inside the sub-tile
+                const float dxp = sub_x0 + (float)i;                 // its offset from the tile origin: x = p & 7 = i
+                const float dyp = sub_y0 + (float)quarter;           //                                 y = p >> 3 = quarter
+                const float c = row[p], w1 = row[32 + p], Dp = row[64 + p];
+                const float4 f0 = F[p][0];
+                s_c0 = fmaf(c, f0.x, s_c0);
+                s_c1 = fmaf(c, f0.y, s_c1);
+                s_c2 = fmaf(c, f0.z, s_c2);
+                s_op += w1;
+                const uint32_t sel = __float_as_uint(Dp) & 3u;       // arg-min barycentric (1, 2, 3) packed in the two LSBs
+                const float u1 = sel == 1u ? Dp : (sel == 3u ? -Dp : 0.0f);
+                const float u2 = sel == 2u ? Dp : (sel == 3u ? -Dp : 0.0f);
+                if (geo) {
+                    const float4 f1 = F[p][1];
+                    const float cg = c * f0.w;                       // contrib * gd
+                    s_n0 = fmaf(c, f1.x, s_n0);
+                    s_n1 = fmaf(c, f1.y, s_n1);
+                    s_n2 = fmaf(c, f1.z, s_n2);
+                    m0 += cg;
+                    m1 = fmaf(cg, dxp, m1);
+                    m2 = fmaf(cg, dyp, m2);
+                }
+                u10 += u1;
+                u1x = fmaf(u1, dxp, u1x);
+                u1y = fmaf(u1, dyp, u1y);
+                u20 += u2;
+                u2x = fmaf(u2, dxp, u2x);
+                u2y = fmaf(u2, dyp, u2y);
+            }
+        }
+#define XQ(v) v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16)
+        XQ(s_c0); XQ(s_c1); XQ(s_c2); XQ(s_op); XQ(u10); XQ(u1x); XQ(u1y); XQ(u20); XQ(u2x); XQ(u2y);
+        if (geo) { XQ(s_n0); XQ(s_n1); XQ(s_n2); XQ(m0); XQ(m1); XQ(m2); }
+#undef XQ
+        if (k < filled) {
+            const float4 e1 = info[k].e1, e2 = info[k].e2, ex = info[k].x;
+            float *g = gacc + (size_t)__float_as_uint(ex.w) * GACC_STRIDE;
+            const float inv = e2.z;
+            const float p1x = e1.x - ox, p1y = e1.y - oy, p2x = e1.z - ox, p2y = e1.w - oy, p3x = e2.x - ox, p3y = e2.y - oy;
+            float S1 = u10, M1x = u1x, M1y = u1y, S2 = u20, M2x = u2x, M2y = u2y;
+            float gv0 = 0.f, gv1 = 0.f, gv2 = 0.f;
+            if (geo) {
+                // affine barycentrics about the tile origin: a_i(d) = a_io + A_i dx + B_i dy
+                const float a1o = (p2x * p3y - p2y * p3x) * inv, A1 = (e1.w - e2.y) * inv, B1 = (e2.x - e1.z) * inv;
+                const float a2o = (p3x * p1y - p3y * p1x) * inv, A2 = (e2.y - e1.y) * inv, B2 = (e1.x - e2.x) * inv;
+                const float a3o = 1.0f - a1o - a2o, A3 = -A1 - A2, B3 = -B1 - B2;
+                gv0 = fmaf(B1, m2, fmaf(A1, m1, a1o * m0));   // sum gd contrib a_1
+                gv1 = fmaf(B2, m2, fmaf(A2, m1, a2o * m0));
+                gv2 = fmaf(B3, m2, fmaf(A3, m1, a3o * m0));
+                const float d13 = ex.x - ex.z, d23 = ex.y - ex.z;   // depth term of ga_k = (vd_k - vd_3) gd contrib
+                S1 = fmaf(d13, m0, S1); M1x = fmaf(d13, m1, M1x); M1y = fmaf(d13, m2, M1y);
+                S2 = fmaf(d23, m0, S2); M2x = fmaf(d23, m1, M2x); M2y = fmaf(d23, m2, M2y);
+            }
+            // moments about v1: q = p - v1 = d - (v1 - o)
+            const float Q1x = fmaf(-p1x, S1, M1x), Q1y = fmaf(-p1y, S1, M1y), Q2x = fmaf(-p1x, S2, M2x), Q2y = fmaf(-p1y, S2, M2y);
+            if (quarter == 0) red_add4(g, S1, Q1x, Q1y, S2);
+            else if (quarter == 1) red_add4(g + 4, Q2x, Q2y, s_op, s_n0);
+            else if (quarter == 2) red_add4(g + 8, s_c0, s_c1, s_c2, s_n1);
+            else if (geo) red_add4(g + 12, s_n2, gv0, gv1, gv2);
+        }
+        __syncwarp();
+}
+
 template <bool RICH, bool GAMMA1>
-__global__ void __launch_bounds__(TS2D_BLOCK)
+__global__ void __launch_bounds__(TS2D_BLOCK, 4)
 k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world, int n_tiles, float gamma, const uint2 *__restrict__ ranges,
                   const uint32_t *__restrict__ list, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1, float bg_depth,
                   const float *__restrict__ background, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
@@ -91,13 +173,8 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
             gd = dL_dout_depth[pix];
         }
     }
-    {   // per-pixel table for phase 2
-        float *f = S.F[warp][lane];
-        const float dxl = (float)lx, dyl = (float)ly;  // pixel offset from the tile origin
-        *reinterpret_cast<float4 *>(f) = make_float4(gp0, gp1, gp2, gd);
-        *reinterpret_cast<float4 *>(f + 4) = make_float4(gn0, gn1, gn2, dxl);
-        *reinterpret_cast<float4 *>(f + 8) = make_float4(dyl, gd * dxl, gd * dyl, 0.0f);
-    }
+    S.F[warp][lane][0] = make_float4(gp0, gp1, gp2, gd);  // per-pixel table for phase 2
+    S.F[warp][lane][1] = make_float4(gn0, gn1, gn2, 0.0f);
     const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last);
     if (tid == 0) S.tile_last = 0;
     __syncthreads();
@@ -109,89 +186,10 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
     const uint32_t tile_last = S.tile_last;
 
     float(*Wp)[BW_WROW] = S.W[warp];
-    int slot = 0;        // next free slot of the panel
-    int my_j = 0;        // staged index of the triangle parked in slot (lane & 15)
-    const int k = lane & 15, half = lane >> 4;
-
-    // phase 2: lane (k, half) sums the panel row k over pixels half*16 .. half*16+15 and flushes the triangle
-    auto flush_panel = [&](int filled) {
-        __syncwarp();
-        float s_c0 = 0.f, s_c1 = 0.f, s_c2 = 0.f, s_n0 = 0.f, s_n1 = 0.f, s_n2 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
-        float u10 = 0.f, u1x = 0.f, u1y = 0.f, u20 = 0.f, u2x = 0.f, u2y = 0.f, s_op = 0.f;
-        if (k < filled) {
-            const float *row = Wp[k];
-#pragma unroll 4
-            for (int i = 0; i < 16; i++) {
-                const int p = half * 16 + i;
-                const float c = row[p], w1 = row[32 + p], Dp = row[64 + p];
-                const float *f = S.F[warp][p];
-                const float4 f0 = *reinterpret_cast<const float4 *>(f);
-                const float4 f1 = *reinterpret_cast<const float4 *>(f + 4);
-                s_c0 = fmaf(c, f0.x, s_c0);
-                s_c1 = fmaf(c, f0.y, s_c1);
-                s_c2 = fmaf(c, f0.z, s_c2);
-                s_op += w1;
-                const uint32_t sel = __float_as_uint(Dp) & 3u;     // arg-min barycentric (1, 2, 3) packed in the two LSBs
-                const float u1 = sel == 1u ? Dp : (sel == 3u ? -Dp : 0.0f);
-                const float u2 = sel == 2u ? Dp : (sel == 3u ? -Dp : 0.0f);
-                float dyp = 0.f;
-                if (geo) {
-                    const float4 f2 = *reinterpret_cast<const float4 *>(f + 8);
-                    dyp = f2.x;
-                    s_n0 = fmaf(c, f1.x, s_n0);
-                    s_n1 = fmaf(c, f1.y, s_n1);
-                    s_n2 = fmaf(c, f1.z, s_n2);
-                    m0 = fmaf(c, f0.w, m0);
-                    m1 = fmaf(c, f2.y, m1);
-                    m2 = fmaf(c, f2.z, m2);
-                } else {
-                    dyp = f[8];
-                }
-                u10 += u1;
-                u1x = fmaf(u1, f1.w, u1x);
-                u1y = fmaf(u1, dyp, u1y);
-                u20 += u2;
-                u2x = fmaf(u2, f1.w, u2x);
-                u2y = fmaf(u2, dyp, u2y);
-            }
-        }
-#define XH(v) v += __shfl_xor_sync(0xffffffffu, v, 16)
-        XH(s_c0); XH(s_c1); XH(s_c2); XH(s_op); XH(u10); XH(u1x); XH(u1y); XH(u20); XH(u2x); XH(u2y);
-        if (geo) { XH(s_n0); XH(s_n1); XH(s_n2); XH(m0); XH(m1); XH(m2); }
-#undef XH
-        if (k < filled) {
-            const BwdEntry &E = S.ent[my_j];
-            const float4 e1 = E.e1, e2 = E.e2;
-            float *g = gacc + (size_t)__float_as_uint(E.col.w) * GACC_STRIDE;
-            const float inv = e2.z;
-            // affine barycentrics about the tile origin: a_i(d) = a_io + A_i dx + B_i dy
-            const float p1x = e1.x - ox, p1y = e1.y - oy, p2x = e1.z - ox, p2y = e1.w - oy, p3x = e2.x - ox, p3y = e2.y - oy;
-            float S1 = u10, M1x = u1x, M1y = u1y, S2 = u20, M2x = u2x, M2y = u2y;
-            float gv0 = 0.f, gv1 = 0.f, gv2 = 0.f;
-            if (geo) {
-                const float a1o = (p2x * p3y - p2y * p3x) * inv, A1 = (e1.w - e2.y) * inv, B1 = (e2.x - e1.z) * inv;
-                const float a2o = (p3x * p1y - p3y * p1x) * inv, A2 = (e2.y - e1.y) * inv, B2 = (e1.x - e2.x) * inv;
-                const float a3o = 1.0f - a1o - a2o, A3 = -A1 - A2, B3 = -B1 - B2;
-                const float vd1 = E.q0.w, vd2 = E.q1.x, vd3 = E.q1.y;
-                gv0 = fmaf(B1, m2, fmaf(A1, m1, a1o * m0));   // sum gd contrib a_1
-                gv1 = fmaf(B2, m2, fmaf(A2, m1, a2o * m0));
-                gv2 = fmaf(B3, m2, fmaf(A3, m1, a3o * m0));
-                const float d13 = vd1 - vd3, d23 = vd2 - vd3;   // depth term of ga_k = (vd_k - vd_3) gd contrib
-                S1 = fmaf(d13, m0, S1); M1x = fmaf(d13, m1, M1x); M1y = fmaf(d13, m2, M1y);
-                S2 = fmaf(d23, m0, S2); M2x = fmaf(d23, m1, M2x); M2y = fmaf(d23, m2, M2y);
-            }
-            // moments about v1: q = p - v1 = d - (v1 - o)
-            const float Q1x = fmaf(-p1x, S1, M1x), Q1y = fmaf(-p1y, S1, M1y), Q2x = fmaf(-p1x, S2, M2x), Q2y = fmaf(-p1y, S2, M2y);
-            if (half == 0) {
-                red_add4(g, S1, Q1x, Q1y, S2);
-                red_add4(g + 4, Q2x, Q2y, s_op, s_n0);
-            } else {
-                red_add4(g + 8, s_c0, s_c1, s_c2, s_n1);
-                if (geo) red_add4(g + 12, s_n2, gv0, gv1, gv2);
-            }
-        }
-        __syncwarp();
-    };
+    RowInfo *info = S.info[warp];
+    int prow = 0;  // next free panel row (rows persist across batches: RowInfo carries what phase 2 needs)
+    const float sub_x0 = (float)((warp & 1) * 8), sub_y0 = (float)((warp >> 1) * 4);
+    auto flush_panel = [&](int filled) { bwd_flush_panel(Wp, info, S.F[warp], gacc, ox, oy, sub_x0, sub_y0, geo, filled, lane); };
 
     // batches are staged in REVERSE list order: staged slot t of a batch is list position (top - t)
     for (uint32_t done_cnt = len - tile_last; done_cnt < len; done_cnt += BW_BATCH) {
@@ -273,23 +271,23 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                     }
                 }
                 if (__ballot_sync(0xffffffffu, w_c != 0.0f) == 0u) continue;
-                float *row = Wp[slot];
+                float *row = Wp[prow];
                 row[lane] = w_c;
                 row[32 + lane] = w_op;
                 row[64 + lane] = w_D;
-                if (k == slot) my_j = j;
-                if (++slot == BW_SLOTS) {
-                    flush_panel(BW_SLOTS);
-                    slot = 0;
+                if (lane == 0) {
+                    info[prow].e1 = e1;
+                    info[prow].e2 = e2;
+                    info[prow].x = make_float4(E.q0.w, E.q1.x, E.q1.y, E.col.w);
+                }
+                if (++prow == BW_ROWS) {
+                    flush_panel(BW_ROWS);
+                    prow = 0;
                 }
             }
         }
-        // the staging buffer is about to be overwritten: flush triangles that still live in the panel
-        if (slot) {
-            flush_panel(slot);
-            slot = 0;
-        }
     }
+    if (prow) flush_panel(prow);
 }
 
 }  // namespace
