@@ -160,6 +160,17 @@ int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_
                   const int32_t *radii, const void *geometry_state, const void *binning_state, const void *image_state,
                   const ts2d_loss_in *loss, const ts2d_backward_out *out, void *scratch, size_t scratch_bytes, void *stream);
 
+/* ts2d_backward split in two for tile-sharded multi-GPU (no counterpart in the reference): each rank runs the composite
+ * backward over its own tiles into `scratch` (16 floats per triangle: the reference's dL_dv*_2D / dL_dnormal_view /
+ * dL_dv_depth / dL_drgb / dL_dopacity temporaries, rasterizer.cu:289-300, in this library's layout), the caller sum-reduces
+ * `scratch` across ranks (ts2d_backward_scratch_bytes(P) bytes of fp32), then every rank runs the per-triangle stage. */
+int ts2d_backward_composite(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int64_t num_rendered,
+                            const void *geometry_state, const void *binning_state, const void *image_state, const ts2d_loss_in *loss,
+                            void *scratch, size_t scratch_bytes, void *stream);
+int ts2d_backward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, const int32_t *radii,
+                           const void *geometry_state, const ts2d_backward_out *out, const void *scratch, size_t scratch_bytes,
+                           void *stream);
+
 /* ---- state decoding, for parity tests against the reference's buffers ----
  * Each writes arrays in the reference's own element types/order.  Any output pointer may be NULL. */
 int ts2d_export_geometry(const void *geometry_state, int32_t P,

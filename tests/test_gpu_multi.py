@@ -1,0 +1,83 @@
+"""Multi-GPU parity (needs >= 2 GPUs; `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`).
+
+One process per GPU over NCCL: every rank composites only the tiles it owns (tile % world == rank), the frame is
+assembled with an all-reduce, the per-triangle gradient accumulators are all-reduced between the composite and the
+per-triangle backward.  Every rank must end up with the single-GPU result: forward outputs to fp32 rounding of the
+all-reduce (exact for disjoint tiles: x + 0), gradients up to the summation order of the atomics."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import harness
+from harness import mismatch_count, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(sc, dev):
+    from triangle_splatting_b200 import TriangleRasterizationSettings, TriangleRasterizer
+
+    s = sc.to(dev)
+    vertex = s.vertex.clone().requires_grad_(True)
+    shs = s.shs.clone().requires_grad_(True)
+    opacity = s.opacity.clone().requires_grad_(True)
+    c2d = torch.zeros((s.P, 2), device=dev, requires_grad=True)
+    out = TriangleRasterizer(TriangleRasterizationSettings(**s.settings_kwargs())).forward(vertex=vertex, center2D=c2d, opacity=opacity, shs=shs)
+    loss = (out[0] * s.grads["dL_dout_feature"]).sum() + (out[2] * s.grads["dL_dout_depth"]).sum() + (out[3] * s.grads["dL_dout_normal"]).sum()
+    loss.backward()
+    res = dict(out_feature=out[0], radii=out[1], depth=out[2], normal=out[3], contrib_sum=out[4], contrib_max=out[5], dL_dvertex=vertex.grad,
+               dL_dshs=shs.grad, dL_dopacity=opacity.grad, dL_dcenter2D=c2d.grad)
+    return {k: v.detach().cpu().numpy() for k, v in res.items()}
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+
+    from triangle_splatting_b200 import distributed as tsd
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        sc = harness.golden_scene("sh3_rich")
+        single = _run(sc, dev)  # sharding off: the single-GPU answer, computed on this very GPU
+        tsd.enable_tile_sharding()
+        sharded = _run(sc, dev)
+        tsd.disable_tile_sharding()
+        ret[rank] = (single, sharded)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_tile_sharded_render_matches_single_gpu(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for rank in range(world):
+        single, sharded = ret[rank]
+        assert mismatch_count(single["radii"], sharded["radii"]) == 0
+        for k in ("out_feature", "depth", "normal", "contrib_max"):
+            assert np.array_equal(single[k], sharded[k]), f"rank {rank}: {k} (disjoint tiles: the all-reduce adds zeros)"
+        assert rel_err(sharded["contrib_sum"], single["contrib_sum"]) <= 1e-5
+        for k in ("dL_dvertex", "dL_dshs", "dL_dopacity", "dL_dcenter2D"):
+            assert rel_err(sharded[k], single[k]) <= 1e-1 and harness.frac_above(sharded[k], single[k], 1e-4, 1e-3) <= 0.03, f"rank {rank}: {k}"
+    # all ranks hold the same frame and the same gradients
+    for k in ret[0][1]:
+        assert np.array_equal(ret[0][1][k], ret[1][1][k]), f"ranks disagree on {k}"

@@ -187,7 +187,19 @@ def rasterize_triangles_backward(tan_fovx: float, tan_fovy: float, viewmatrix: t
         scratch = torch.empty((sbytes,), device=dev, dtype=torch.uint8)
         loss = _lib.LossIn(_ptr(dL_dout_feature), _ptr(dL_dout_depth) if rich_info else None, _ptr(dL_dout_normal) if rich_info else None)
         out = _lib.BackwardOut(_ptr(dL_dvertex), _ptr(dL_dcenter2D), _ptr(dL_dshs), _ptr(dL_dfeature), _ptr(dL_dopacity))
-        _lib.check(lib.ts2d_backward(C.byref(cam), C.byref(geom), C.byref(flags), int(num_rendered), _ptr(radii), _ptr(geometryBuffer),
-                                     _ptr(binningBuffer), _ptr(imageBuffer), C.byref(loss), C.byref(out), _ptr(scratch), sbytes, stream),
-                   "ts2d_backward")
+        if shard[1] > 1:
+            # tile-sharded: composite over this rank's tiles, sum the 64 B/triangle accumulators over the ranks (NCCL on the
+            # current stream), then the per-triangle stage runs replicated on identical data -> identical gradients everywhere
+            from . import distributed
+
+            _lib.check(lib.ts2d_backward_composite(C.byref(cam), C.byref(geom), C.byref(flags), int(num_rendered), _ptr(geometryBuffer),
+                                                   _ptr(binningBuffer), _ptr(imageBuffer), C.byref(loss), _ptr(scratch), sbytes, stream),
+                       "ts2d_backward_composite")
+            distributed.reduce_accumulators(scratch.view(torch.float32))
+            _lib.check(lib.ts2d_backward_geometry(C.byref(cam), C.byref(geom), C.byref(flags), _ptr(radii), _ptr(geometryBuffer),
+                                                  C.byref(out), _ptr(scratch), sbytes, stream), "ts2d_backward_geometry")
+        else:
+            _lib.check(lib.ts2d_backward(C.byref(cam), C.byref(geom), C.byref(flags), int(num_rendered), _ptr(radii), _ptr(geometryBuffer),
+                                         _ptr(binningBuffer), _ptr(imageBuffer), C.byref(loss), C.byref(out), _ptr(scratch), sbytes, stream),
+                       "ts2d_backward")
     return dL_dvertex, dL_dcenter2D, dL_dshs, dL_dfeature, dL_dopacity

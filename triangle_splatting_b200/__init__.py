@@ -116,10 +116,8 @@ class _RasterizeTriangles(torch.autograd.Function):
         )
         grad_vertex, grad_center2D, grad_shs, grad_feature, grad_opacity = debug_run(
             _C.rasterize_triangles_backward, *args, debug=s.debug, shard=ctx.shard)
-        if ctx.shard[1] > 1:
-            from . import distributed
-
-            distributed.reduce_gradients(grad_vertex, grad_center2D, grad_shs, grad_feature, grad_opacity)
+        # tile-sharded runs: _C.rasterize_triangles_backward already all-reduced the per-triangle accumulators between the
+        # composite and the per-triangle stage, so the five gradients are complete and identical on every rank here
         use_shs = feature.dim() <= 1 or (feature.size(0) == 0 and shs.size(0) > 0)
         return (grad_vertex, grad_center2D, grad_shs if use_shs else None, None if use_shs else grad_feature, grad_opacity, None)
 

@@ -59,6 +59,10 @@ SYMBOLS = {
                                       C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(ForwardOut), C.c_void_p]),
     "ts2d_backward": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.POINTER(LossIn), C.POINTER(BackwardOut), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ts2d_backward_composite": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_int64, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.POINTER(LossIn), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ts2d_backward_geometry": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_void_p, C.c_void_p,
+                                         C.POINTER(BackwardOut), C.c_void_p, C.c_size_t, C.c_void_p]),
     "ts2d_export_geometry": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 10 + [C.c_void_p]),
     "ts2d_export_binning": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),

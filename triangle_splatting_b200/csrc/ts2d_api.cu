@@ -286,6 +286,50 @@ int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_
     return 0;
 }
 
+// The two halves of ts2d_backward, for tile-sharded multi-GPU: the per-triangle accumulators in `scratch` (16 floats per
+// triangle) are what the ranks all-reduce between the two calls -- 64 B/triangle instead of the 240+ B/triangle of the
+// final gradients, and K9 then runs replicated on identical data.
+int ts2d_backward_composite(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int64_t num_rendered,
+                            const void *geometry_state, const void *binning_state, const void *image_state, const ts2d_loss_in *loss,
+                            void *scratch, size_t scratch_bytes, void *stream)
+{
+    int rc = validate(cam, geom, flags);
+    if (rc) return rc;
+    if (geom->P == 0) return 0;
+    if (!geometry_state || !binning_state || !image_state || !loss || !scratch || !loss->dL_dout_feature) return TS2D_E_NULL;
+    if (flags->rich_info && (!loss->dL_dout_depth || !loss->dL_dout_normal)) return TS2D_E_NULL;
+    if (scratch_bytes < ts2d_backward_scratch_bytes(geom->P)) return TS2D_E_STATE_SIZE;
+    GeomState gs;
+    BinState bs;
+    ImageState is;
+    carve_geometry(const_cast<void *>(geometry_state), geom->P, &gs);
+    carve_binning(const_cast<void *>(binning_state), num_rendered, &bs);
+    carve_image(const_cast<void *>(image_state), cam->width, cam->height, &is);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ts2d_use_fast(geom, flags))
+        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd_fast(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
+    else
+        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
+    return 0;
+}
+
+int ts2d_backward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, const int32_t *radii,
+                           const void *geometry_state, const ts2d_backward_out *out, const void *scratch, size_t scratch_bytes, void *stream)
+{
+    int rc = validate(cam, geom, flags);
+    if (rc) return rc;
+    if (geom->P == 0) return 0;
+    if (!radii || !geometry_state || !out || !scratch) return TS2D_E_NULL;
+    if (!out->dL_dvertex || !out->dL_dcenter2D || !out->dL_dfeature || !out->dL_dopacity) return TS2D_E_NULL;
+    if (geom->M > 0 && !out->dL_dshs) return TS2D_E_NULL;
+    if (scratch_bytes < ts2d_backward_scratch_bytes(geom->P)) return TS2D_E_STATE_SIZE;
+    GeomState gs;
+    carve_geometry(const_cast<void *>(geometry_state), geom->P, &gs);
+    cudaStream_t s = (cudaStream_t)stream;
+    TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
+    return 0;
+}
+
 int ts2d_export_geometry(const void *geometry_state, int32_t P, float *v2d, float *area2, float *normal_view, float *v_depth, float *depth,
                          float *rgb, uint8_t *clamped, uint32_t *tiles_touched, uint32_t *rect_min, uint32_t *rect_max, void *stream)
 {

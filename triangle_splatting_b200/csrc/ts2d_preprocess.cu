@@ -102,6 +102,9 @@ __device__ __forceinline__ void tri_geom_view(const float *vp, const float *view
     r3 = c - t.center;
 }
 
+// TILED: the warp stages its 32 SH rows through shared memory with coalesced 16-byte loads (see warp_rows_load);
+// only the data movement changes -- the arithmetic on the coefficients is the same expression tree either way.
+template <bool TILED>
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_preprocess(int W, int H, int P, int D, int M, int C, bool rich, bool use_shs, int gx, int gy, bool back_culling, float tfx, float tfy,
              int shard_rank, int shard_world, const float *__restrict__ view, const float *__restrict__ proj, const float *__restrict__ campos,
@@ -110,7 +113,19 @@ k_preprocess(int W, int H, int P, int D, int M, int C, bool rich, bool use_shs, 
              uint32_t *__restrict__ dkey, uint32_t *__restrict__ ids, uint32_t *__restrict__ tiles, ushort4 *__restrict__ rect,
              uint8_t *__restrict__ clamp)
 {
+    extern __shared__ __align__(16) float s_rows[];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const float *sh_row = shs + (size_t)idx * M * 3;
+    if (TILED) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int row0 = idx - lane, nrows = min(32, P - row0);
+        if (nrows <= 0) return;
+        const int q = (3 * M) / 4, rs4 = q + 1;
+        float *tile = s_rows + (size_t)warp * 32 * rs4 * 4;
+        warp_rows_load(shs + (size_t)row0 * M * 3, tile, q, rs4, nrows, lane);
+        __syncwarp();
+        sh_row = tile + lane * rs4 * 4;
+    }
     if (idx >= P) return;
 
     int out_radius = 0;
@@ -165,7 +180,7 @@ k_preprocess(int W, int H, int P, int D, int M, int C, bool rich, bool use_shs, 
             f3 rgb;
             uint8_t mask = 0;
             if (use_shs) {
-                rgb = sh_colour(D, shs + (size_t)idx * M * 3, center, ld3(campos), mask);
+                rgb = sh_colour(D, sh_row, center, ld3(campos), mask);
             } else {
                 const float *fp = feature + (size_t)idx * C;
                 rgb = mk3(fp[0], C > 1 ? fp[1] : 0.0f, C > 2 ? fp[2] : 0.0f);
@@ -207,10 +222,20 @@ int ts2d_launch_preprocess(const ts2d_camera *cam, const ts2d_geometry *g, const
 {
     const int P = g->P;
     const int gx = (cam->width + TS2D_TILE - 1) / TS2D_TILE, gy = (cam->height + TS2D_TILE - 1) / TS2D_TILE;
-    k_preprocess<<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(
-        cam->width, cam->height, P, g->sh_degree, g->M, g->C, f->rich_info != 0, g->use_shs != 0, gx, gy, f->back_culling != 0, cam->tan_fovx,
-        cam->tan_fovy, f->shard_rank, f->shard_world, cam->viewmatrix, cam->projmatrix, cam->campos, g->vertex, g->shs, g->feature, g->opacity,
-        radii, gs.rec0, gs.rec1, gs.dkey, gs.ids, gs.tiles, gs.rect, gs.clamp);
+#define TS2D_K1_ARGS                                                                                                                          \
+    cam->width, cam->height, P, g->sh_degree, g->M, g->C, f->rich_info != 0, g->use_shs != 0, gx, gy, f->back_culling != 0, cam->tan_fovx,    \
+        cam->tan_fovy, f->shard_rank, f->shard_world, cam->viewmatrix, cam->projmatrix, cam->campos, g->vertex, g->shs, g->feature, g->opacity, \
+        radii, gs.rec0, gs.rec1, gs.dkey, gs.ids, gs.tiles, gs.rect, gs.clamp
+    // stage whole SH rows only when at least half of each row is actually read ((D+1)^2 of M coefficients)
+    const int K = (g->sh_degree + 1) * (g->sh_degree + 1);
+    if (g->use_shs && ts2d_rows_tileable(g->M, g->shs, g->shs) && 2 * K >= g->M) {
+        const size_t smem = (size_t)(TS2D_BLOCK / 32) * 32 * ((3 * g->M) / 4 + 1) * 16;
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_preprocess<true><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K1_ARGS);
+    } else {
+        k_preprocess<false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(TS2D_K1_ARGS);
+    }
+#undef TS2D_K1_ARGS
     return (int)cudaGetLastError();
 }
 

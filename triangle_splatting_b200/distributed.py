@@ -71,6 +71,13 @@ def assemble_forward(out_feature, depth=None, normal=None, contrib_sum=None, con
         dist.all_reduce(contrib_max, op=dist.ReduceOp.MAX, group=_STATE["group"])
 
 
+def reduce_accumulators(acc: torch.Tensor) -> None:
+    """All-reduce(sum) of the per-triangle screen-space gradient accumulators (16 fp32 per triangle) between the composite
+    backward and the per-triangle backward: 64 B/triangle on the wire instead of the 240+ B/triangle of the final gradients
+    (vertex 36 + SH 192 + opacity 4 + center2D 8), and the per-triangle stage then runs replicated on identical data."""
+    dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=_STATE["group"])
+
+
 def reduce_gradients(*grads) -> None:
     """NCCL all-reduce(sum) of the per-triangle gradient tensors (partial sums over each rank's tiles)."""
     _bucket_all_reduce(list(grads), dist.ReduceOp.SUM)
