@@ -399,6 +399,7 @@ def main():
 
     # ------------------------------------------------------------------------------------ our arm
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
         from triangle_splatting_b200 import distributed as tsd
 

@@ -108,11 +108,18 @@ __device__ __forceinline__ uint32_t subtile_mask(const float4 r0, const float4 r
         my2[sy] = fmaxf(B2 * lo, B2 * hi);
         my3[sy] = fmaxf(B3 * lo, B3 * hi);
     }
+    // The footprint {min a_i >= thr} is the triangle scaled by Ec about its centroid c: vertices c + Ec (v_i - c).  The three edge
+    // tests above separate a rectangle from it only along the edge normals; its bounding box adds the two axis-aligned separating
+    // directions (rectangles that sit beyond an acute corner pass all three edge tests but can never be touched).
+    const float cx = (p1x + p2x + p3x) * (1.0f / 3.0f), cy = (p1y + p2y + p3y) * (1.0f / 3.0f);
+    const float bx0 = fmaf(Ec, fminf(fminf(p1x, p2x), p3x) - cx, cx) - 0.02f, bx1 = fmaf(Ec, fmaxf(fmaxf(p1x, p2x), p3x) - cx, cx) + 0.02f;
+    const float by0 = fmaf(Ec, fminf(fminf(p1y, p2y), p3y) - cy, cy) - 0.02f, by1 = fmaf(Ec, fmaxf(fmaxf(p1y, p2y), p3y) - cy, cy) + 0.02f;
     uint32_t m = 0;
 #pragma unroll
     for (int w = 0; w < 8; w++) {
         const int sx = w & 1, sy = w >> 1;
-        const bool ok = (a10 + mx1[sx] + my1[sy] >= thr) && (a20 + mx2[sx] + my2[sy] >= thr) && (a30 + mx3[sx] + my3[sy] >= thr);
+        const bool ok = (a10 + mx1[sx] + my1[sy] >= thr) && (a20 + mx2[sx] + my2[sy] >= thr) && (a30 + mx3[sx] + my3[sy] >= thr) &&
+                        (bx0 <= 8.0f * sx + 7.0f) && (bx1 >= 8.0f * sx) && (by0 <= 4.0f * sy + 3.0f) && (by1 >= 4.0f * sy);
         m |= ok ? (1u << w) : 0u;
     }
     return m;
