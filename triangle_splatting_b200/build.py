@@ -43,7 +43,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def one(src: str) -> Path:
         obj = objdir / (src + ".o")
-        cmd = [nvcc(), "-c", str(CSRC / src), "-o", str(obj)] + NVCC_FLAGS
+        # TS2D_NVCC_EXTRA: extra defines for tuning experiments (e.g. "-DTS2D_FWD_MINB=4"); empty for the shipped build
+        cmd = [nvcc(), "-c", str(CSRC / src), "-o", str(obj)] + NVCC_FLAGS + os.environ.get("TS2D_NVCC_EXTRA", "").split()
         r = subprocess.run(cmd, capture_output=True, text=True)
         (objdir / (src + ".log")).write_text(r.stdout + r.stderr)
         if r.returncode != 0:

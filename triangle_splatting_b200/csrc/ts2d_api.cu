@@ -181,7 +181,7 @@ __global__ void k_export_keys(int64_t R, const uint32_t *tkey, const uint32_t *t
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
     const uint32_t id = tval[i];
-    if (keys) keys[i] = ((uint64_t)tkey[i] << 32) | dkey[id];  // rasterizer.cu:67-69
+    if (keys) keys[i] = ((uint64_t)(tkey[i] >> TS2D_MASK_BITS) << 32) | dkey[id];  // rasterizer.cu:67-69
     if (list) list[i] = id;
 }
 
@@ -251,9 +251,9 @@ int ts2d_forward_render(const ts2d_camera *cam, const ts2d_geometry *geom, const
     if (carve_binning(binning_state, num_rendered, &bs) > binning_state_bytes) return TS2D_E_STATE_SIZE;
     if (carve_image(image_state, cam->width, cam->height, &is) > image_state_bytes) return TS2D_E_STATE_SIZE;
     cudaStream_t s = (cudaStream_t)stream;
-    TS2D_STAGE(TS2D_STAGE_BINNING, ts2d_launch_binning(cam, flags, geom->P, num_rendered, gs, bs, is, s));
+    TS2D_STAGE(TS2D_STAGE_BINNING, ts2d_launch_binning(cam, geom, flags, num_rendered, gs, bs, is, s));
     if (ts2d_use_fast(geom, flags))
-        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd_fast(cam, geom, flags, gs, bs.tval[1], is, out, s));
+        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, out, s));
     else
         TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd(cam, geom, flags, gs, bs.tval[1], is, out, s));
     return 0;
@@ -279,7 +279,7 @@ int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_
     carve_image(const_cast<void *>(image_state), cam->width, cam->height, &is);
     cudaStream_t s = (cudaStream_t)stream;
     if (ts2d_use_fast(geom, flags))
-        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd_fast(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
+        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, loss, (float *)scratch, s));
     else
         TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
     TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
@@ -307,7 +307,7 @@ int ts2d_backward_composite(const ts2d_camera *cam, const ts2d_geometry *geom, c
     carve_image(const_cast<void *>(image_state), cam->width, cam->height, &is);
     cudaStream_t s = (cudaStream_t)stream;
     if (ts2d_use_fast(geom, flags))
-        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd_fast(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
+        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, loss, (float *)scratch, s));
     else
         TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
     return 0;

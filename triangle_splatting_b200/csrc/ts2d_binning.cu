@@ -11,12 +11,13 @@
 //      ceil(log2(tiles)) tile-id bits (2 passes over 8 B/instance at 1080p).
 // Stability of step 2 preserves (depth, id) order inside every tile, so the resulting list is
 // bit-identical to the reference's point_list (ts2d_export_binning rebuilds the 64-bit keys).
+// The 8 key bits below the tile id carry each instance's sub-tile coverage mask through the sort.
 //
 // The radix passes and the scan are CUB device primitives from the CUDA toolkit (the reference uses
 // the same library for its sort/scan, rasterizer.cu:186,211); everything else is hand-written.
 #include <cub/cub.cuh>
 
-#include "ts2d_common.cuh"
+#include "ts2d_fast.cuh"
 
 namespace {
 
@@ -25,23 +26,85 @@ struct GatherTiles {
     __host__ __device__ __forceinline__ uint32_t operator()(uint32_t id) const { return tiles[id]; }
 };
 
-// One thread per depth rank: write the (owned) tiles of the triangle's rect, row-major, like
-// rasterizer.cu:63-74 but in depth order and with the tile id alone as key.
+// Instance key = (tile id << 8) | sub-tile coverage mask.  The tile sort orders on the tile bits only and carries the mask
+// along for free; the fast composite kernels read it instead of re-deriving coverage from the raster record (once per
+// instance here instead of once per instance per pass there).  With MASKS == false (mirror kernels) the mask byte is 0xFF.
+template <bool MASKS>
+__device__ __forceinline__ uint32_t instance_key(uint32_t tile, int gx, uint32_t id, const float4 *__restrict__ rec0, const GammaK gk)
+{
+    if (!MASKS) return (tile << TS2D_MASK_BITS) | 0xFFu;
+    const float4 r0 = __ldg(rec0 + 3 * (size_t)id), r1 = __ldg(rec0 + 3 * (size_t)id + 1);
+    const uint32_t ty = tile / (uint32_t)gx, tx = tile - ty * (uint32_t)gx;
+    return (tile << TS2D_MASK_BITS) | subtile_mask(r0, r1, r1.z, (float)(tx * TS2D_TILE), (float)(ty * TS2D_TILE), gk);
+}
+
+// Unsharded emission, one warp per 32 consecutive depth ranks: the warp's instances [start of rank r0, end of rank r0+31) are
+// dealt to lanes round-robin, each lane finding its (triangle, k-th tile of the rect, row-major) by a 5-step search over the
+// 32 scan values held in the warp.  Same output as rasterizer.cu:63-74 in depth order, with coalesced stores and no
+// divergence on the rect size.
+template <bool MASKS>
 __global__ void __launch_bounds__(TS2D_BLOCK)
-k_emit(int P, int gx, int shard_rank, int shard_world, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
-       const ushort4 *__restrict__ rect, const uint32_t *__restrict__ offs, uint32_t *__restrict__ tkey, uint32_t *__restrict__ tval)
+k_emit_warp(int P, int gx, float gamma, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles, const ushort4 *__restrict__ rect,
+            const uint32_t *__restrict__ offs, const float4 *__restrict__ rec0, uint32_t *__restrict__ tkey, uint32_t *__restrict__ tval)
+{
+    const int lane = threadIdx.x & 31;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x);
+    const GammaK gk = make_gamma(gamma);
+    uint32_t id = 0, n = 0, end = 0;
+    uint32_t rc_lo = 0, rc_hi = 0;  // {min.x | min.y << 16}, {max.x | max.y << 16}
+    if (r < P) {
+        id = order[r];
+        n = tiles[id];
+        end = offs[r];
+        const ushort4 rc = rect[id];
+        rc_lo = (uint32_t)rc.x | ((uint32_t)rc.y << 16);
+        rc_hi = (uint32_t)rc.z | ((uint32_t)rc.w << 16);
+    } else {
+        end = offs[P - 1];
+    }
+    const uint32_t start = end - n;
+    const uint32_t w_start = __shfl_sync(0xffffffffu, start, 0), w_end = __shfl_sync(0xffffffffu, end, 31);
+    for (uint32_t base = w_start; base < w_end; base += 32) {
+        const uint32_t i = base + lane;
+        // t = number of lanes whose end <= i (ends are non-decreasing)
+        int t = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const uint32_t e = __shfl_sync(0xffffffffu, end, t + step - 1);
+            if (e <= i) t += step;
+        }
+        t = min(t, 31);  // lanes past w_end
+        const uint32_t t_start = __shfl_sync(0xffffffffu, start, t), t_id = __shfl_sync(0xffffffffu, id, t);
+        const uint32_t lo = __shfl_sync(0xffffffffu, rc_lo, t), hi = __shfl_sync(0xffffffffu, rc_hi, t);
+        if (i < w_end) {
+            const uint32_t k = i - t_start, w = (hi & 0xffffu) - (lo & 0xffffu);
+            const uint32_t dy = k / w, dx = k - dy * w;
+            const uint32_t tile = ((lo >> 16) + dy) * (uint32_t)gx + (lo & 0xffffu) + dx;
+            tkey[i] = instance_key<MASKS>(tile, gx, t_id, rec0, gk);
+            tval[i] = t_id;
+        }
+    }
+}
+
+// Tile-sharded emission (one thread per depth rank): only the tiles this rank owns.
+template <bool MASKS>
+__global__ void __launch_bounds__(TS2D_BLOCK)
+k_emit_sharded(int P, int gx, float gamma, int shard_rank, int shard_world, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
+               const ushort4 *__restrict__ rect, const uint32_t *__restrict__ offs, const float4 *__restrict__ rec0, uint32_t *__restrict__ tkey,
+               uint32_t *__restrict__ tval)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= P) return;
     const uint32_t id = order[r];
     if (tiles[id] == 0) return;
+    const GammaK gk = make_gamma(gamma);
     uint32_t off = (r == 0) ? 0u : offs[r - 1];
     const ushort4 rc = rect[id];
     for (uint32_t y = rc.y; y < rc.w; y++)
         for (uint32_t x = rc.x; x < rc.z; x++) {
             const uint32_t t = y * (uint32_t)gx + x;
-            if (shard_world > 1 && (t % (uint32_t)shard_world) != (uint32_t)shard_rank) continue;
-            tkey[off] = t;
+            if ((t % (uint32_t)shard_world) != (uint32_t)shard_rank) continue;
+            tkey[off] = instance_key<MASKS>(t, gx, id, rec0, gk);
             tval[off] = id;
             off++;
         }
@@ -52,11 +115,11 @@ __global__ void __launch_bounds__(TS2D_BLOCK) k_ranges(int64_t R, const uint32_t
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
-    const uint32_t cur = tkey[i];
+    const uint32_t cur = tkey[i] >> TS2D_MASK_BITS;
     if (i == 0)
         ranges[cur].x = 0;
     else {
-        const uint32_t prev = tkey[i - 1];
+        const uint32_t prev = tkey[i - 1] >> TS2D_MASK_BITS;
         if (cur != prev) {
             ranges[prev].y = (uint32_t)i;
             ranges[cur].x = (uint32_t)i;
@@ -127,19 +190,33 @@ static int bits_for(uint32_t n_tiles)
 }
 
 // K4-K6.
-int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_flags *f, int32_t P, int64_t R, GeomState gs, BinState bs, ImageState is,
+int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, int64_t R, GeomState gs, BinState bs, ImageState is,
                         cudaStream_t s)
 {
     const int gx = (cam->width + TS2D_TILE - 1) / TS2D_TILE, gy = (cam->height + TS2D_TILE - 1) / TS2D_TILE;
     const int n_tiles = gx * gy;
+    const int P = g->P;
     TS2D_CUDA_TRY(cudaMemsetAsync(is.ranges, 0, sizeof(uint2) * (size_t)n_tiles, s));
     if (R == 0) return 0;
-    k_emit<<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(P, gx, f->shard_rank, f->shard_world, gs.ids2, gs.tiles, gs.rect, gs.offs,
-                                                                  bs.tkey[0], bs.tval[0]);
+    const bool masks = ts2d_use_fast(g, f);
+    const int blocks = (P + TS2D_BLOCK - 1) / TS2D_BLOCK;
+    if (f->shard_world > 1) {
+        if (masks)
+            k_emit_sharded<true><<<blocks, TS2D_BLOCK, 0, s>>>(P, gx, g->gamma, f->shard_rank, f->shard_world, gs.ids2, gs.tiles, gs.rect, gs.offs,
+                                                                gs.rec0, bs.tkey[0], bs.tval[0]);
+        else
+            k_emit_sharded<false><<<blocks, TS2D_BLOCK, 0, s>>>(P, gx, g->gamma, f->shard_rank, f->shard_world, gs.ids2, gs.tiles, gs.rect, gs.offs,
+                                                                 gs.rec0, bs.tkey[0], bs.tval[0]);
+    } else {
+        if (masks)
+            k_emit_warp<true><<<blocks, TS2D_BLOCK, 0, s>>>(P, gx, g->gamma, gs.ids2, gs.tiles, gs.rect, gs.offs, gs.rec0, bs.tkey[0], bs.tval[0]);
+        else
+            k_emit_warp<false><<<blocks, TS2D_BLOCK, 0, s>>>(P, gx, g->gamma, gs.ids2, gs.tiles, gs.rect, gs.offs, gs.rec0, bs.tkey[0], bs.tval[0]);
+    }
     TS2D_CUDA_TRY(cudaGetLastError());
     size_t tb = bs.cub_temp_bytes;
     TS2D_CUDA_TRY(cub::DeviceRadixSort::SortPairs(bs.cub_temp, tb, (const uint32_t *)bs.tkey[0], bs.tkey[1], (const uint32_t *)bs.tval[0],
-                                                  bs.tval[1], R, 0, bits_for((uint32_t)n_tiles), s));
+                                                  bs.tval[1], R, TS2D_MASK_BITS, TS2D_MASK_BITS + bits_for((uint32_t)n_tiles), s));
     k_ranges<<<(unsigned)((R + TS2D_BLOCK - 1) / TS2D_BLOCK), TS2D_BLOCK, 0, s>>>(R, bs.tkey[1], is.ranges);
     return (int)cudaGetLastError();
 }

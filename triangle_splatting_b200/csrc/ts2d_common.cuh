@@ -14,7 +14,7 @@
 //     clamp  u8[P]        SH clamp mask (bit c set <=> channel c clamped at 0)
 //     hdr    GeomHeader   R (num_rendered)
 //   binning state (per instance, R entries)
-//     tkey[0]/tval[0] u32[R]  tile id / triangle id of each instance in emission (depth-rank) order
+//     tkey[0]/tval[0] u32[R]  (tile id << 8 | sub-tile mask) / triangle id of each instance in emission (depth-rank) order
 //     tkey[1]/tval[1] u32[R]  the same after the stable tile sort; tval[1] is the per-tile list
 //   image state
 //     ranges  uint2[tiles]  [start,end) of each tile in the sorted list
@@ -30,6 +30,7 @@
 
 #define TS2D_BLOCK 256
 #define TS2D_EPS 1e-8f  // R2D/src/auxiliary.h:8
+#define TS2D_MASK_BITS 8  // low bits of an instance key: coverage of the tile's eight 8x4 sub-tiles (ts2d_fast.cuh)
 
 struct GeomHeader {
     int64_t num_rendered;
@@ -184,13 +185,15 @@ size_t ts2d_tile_sort_temp_bytes(int64_t R);
 // stage launchers (each returns 0 / cudaError_t)
 int ts2d_launch_preprocess(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, int32_t *radii, GeomState gs, cudaStream_t s);
 int ts2d_launch_order_and_scan(int32_t P, GeomState gs, int64_t *R_host, cudaStream_t s);
-int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_flags *f, int32_t P, int64_t R, GeomState gs, BinState bs, ImageState is, cudaStream_t s);
+int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, int64_t R, GeomState gs, BinState bs, ImageState is,
+                        cudaStream_t s);
 int ts2d_launch_render_fwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
                            ImageState is, const ts2d_forward_out *out, cudaStream_t s);
-int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
-                                ImageState is, const ts2d_forward_out *out, cudaStream_t s);
-int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
-                                ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s);
+// fast kernels: `keys` = sorted instance keys (tile << 8 | sub-tile mask), `list` = triangle ids, both in tile-list order
+int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
+                                const uint32_t *list, ImageState is, const ts2d_forward_out *out, cudaStream_t s);
+int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
+                                const uint32_t *list, ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s);
 // The fast kernels cover the gamma range the trainer schedules (1..50, VanillaTS_model.py:549-554) with margin;
 // outside it (for gamma < 0.6 the ecc <= 10 cut starts to matter; gamma -> 0 makes ecc^(2 gamma) degenerate) the exact mirror kernels are used.
 static inline bool ts2d_use_fast(const ts2d_geometry *g, const ts2d_flags *f) { return !f->exact && g->gamma >= 0.6f && g->gamma <= 64.0f; }

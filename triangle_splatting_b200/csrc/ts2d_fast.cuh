@@ -42,6 +42,47 @@ __device__ __forceinline__ float rcp_approx(float x)
     return y;
 }
 
+// Shared memory through explicit 32-bit shared-space addresses.  ptxas (sm_100a) lowers "address of a __shared__ symbol" to
+// S2R SR_CgaCtaId + MOV + LEA (the shared::cluster window) and, under a tight register bound, re-materialises that triple in
+// front of every access inside the walk loops (3 issue slots + an S2R scoreboard wait per access group).  smem_base() pins
+// the address in one register; all hot accesses are ld/st.shared relative to it.
+__device__ __forceinline__ uint32_t smem_base(const void *p)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("mov.u32 %0, %0;" : "+r"(a));  // opaque: cannot be re-derived from the symbol
+    return a;
+}
+__device__ __forceinline__ float4 lds128(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t a)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds32f(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 // gamma-dependent constants (kernel-uniform)
 struct GammaK {
     float gamma, two_gamma, inv_two_gamma;

@@ -1,8 +1,10 @@
 // ts2d_render_bwd_fast.cu -- fast reverse-walk gradient accumulation (K8, flags.exact == 0).
 //
 // Same contract as k_render_bwd (ts2d_render_bwd.cu, the mirror of R2D/src/backward.cu:265-493) with the
-// forward fast kernel's machinery (sub-tile masks, reference-shaped fast barycentrics, decision bands with
-// eval_exact fallback -- so the set of contributing pairs is exactly the one the forward pass blended).
+// forward fast kernel's machinery (warp-autonomous gather / stage / walk over the instance keys' sub-tile masks,
+// reference-shaped fast barycentrics, decision bands with eval_exact fallback -- so the set of contributing pairs
+// is exactly the one the forward pass blended).  The walk runs back to front and starts at the sub-tile's own
+// last contributor (max n_contrib over the warp's 32 pixels), not at the end of the tile's list.
 //
 // What is different from the reference is how the per-pair contributions are summed over pixels.  The reference
 // issues 10-16 global atomics per contributing (pixel, triangle) pair.  Here every one of the 16 per-triangle
@@ -10,8 +12,8 @@
 // sequential walk (contrib = alpha T, dL/dalpha * G, and D = dL/d ecc routed to the arg-min barycentric) and
 // f is a per-pixel constant (upstream gradients, pixel offsets) -- the barycentrics being affine in the pixel,
 // their Jacobians reduce to first moments (see ts2d_preprocess.cu: the moments -> vertex-gradient map).
-//   phase 1 (lane = pixel):    walk the warp's covered entries back to front, run the T / colour recurrences,
-//                              park the three scalars of each pair in an 8-row shared-memory panel W[row][pixel];
+//   phase 1 (lane = pixel):    walk the staged entries, run the T / colour recurrences, park the three scalars of
+//                              each pair in an 8-row shared-memory panel W[row][pixel];
 //   phase 2 (lane = triangle): every 8 rows, each lane owns (row, quarter of the 32 pixels) and accumulates the
 //                              16 sums with plain FFMAs from W and the per-pixel table F -- no per-pair shuffles,
 //                              no selects -- then two xor-combines and one 16-byte RED per lane (out of line).
@@ -21,31 +23,24 @@
 
 namespace {
 
-constexpr int BW_BATCH = 128;   // list entries staged per batch
 constexpr int BW_ROWS = 8;      // triangles per phase-2 panel
 constexpr int BW_WROW = 97;     // 3 scalars x 32 pixels + 1 pad word: conflict-free for both phases
 
-struct __align__(16) BwdEntry {
-    float4 e1;   // v1.x, v1.y, v2.x, v2.y
-    float4 e2;   // v3.x, v3.y, 1/area2, opacity
-    float4 col;  // r, g, b, triangle id (bits)
-    float4 q0;   // n.x, n.y, n.z, vd1
-    float4 q1;   // vd2, vd3, -, -
-};
-
-struct __align__(16) RowInfo {  // what phase 2 needs to know about the triangle parked in a panel row
-    float4 e1;   // v1.x, v1.y, v2.x, v2.y
-    float4 e2;   // v3.x, v3.y, 1/area2, opacity
-    float4 x;    // vd1, vd2, vd3, triangle id (bits)
-};
-
-struct __align__(16) BwdSmem {
-    BwdEntry ent[BW_BATCH];
-    float4 F[8][32][2];              // per warp, per pixel: {gp0 gp1 gp2 gd} {gn0 gn1 gn2 -}
-    float W[8][BW_ROWS][BW_WROW];    // per warp panel: [row][scalar * 32 + pixel]
-    RowInfo info[8][BW_ROWS];
-    uint8_t mask[BW_BATCH];
-    uint32_t tile_last;
+// Per-warp shared-memory block (byte offsets from the warp's base address):
+//   ENT   entry j at j * EB: {v1.x v1.y v2.x v2.y} {v3.x v3.y 1/area2 op} {r g b id} [RICH: {n.x n.y n.z vd1} {vd2 vd3 pos -}]
+//   POS   non-RICH only: u32[32] list positions (RICH keeps them in the entry's spare word)
+//   F     per pixel {gp0 gp1 gp2 gd} {gn0 gn1 gn2 -}
+//   W     panel [8 rows][97]: [scalar * 32 + pixel]
+//   INFO  per panel row {v1 v2} {v3 1/area2 op} {vd1 vd2 vd3 id}: what phase 2 needs to know about the triangle
+template <bool RICH>
+struct BwdLayout {
+    static constexpr int EB = RICH ? 80 : 48;
+    static constexpr int POS = RICH ? 72 : 32 * 48;
+    static constexpr int POS_STRIDE = RICH ? 80 : 4;
+    static constexpr int F = RICH ? 32 * 80 : 32 * 48 + 128;
+    static constexpr int W = F + 32 * 32;
+    static constexpr int INFO = W + ((BW_ROWS * BW_WROW * 4 + 15) / 16) * 16;
+    static constexpr int BYTES = INFO + BW_ROWS * 48;
 };
 
 __device__ __forceinline__ void red_add4(float *addr, float a, float b, float c, float d)
@@ -55,90 +50,92 @@ __device__ __forceinline__ void red_add4(float *addr, float a, float b, float c,
 
 // phase 2 (out of line: one copy keeps the kernel inside the instruction cache and out of the walk loop's register budget).
 // lane (k, quarter) sums panel row k over pixels quarter*8 .. quarter*8+7, then flushes the triangle.
-static __device__ __noinline__ void bwd_flush_panel(const float (*Wp)[BW_WROW], const RowInfo *info, const float4 (*F)[2], float *__restrict__ gacc,
-                                                    float ox, float oy, float sub_x0, float sub_y0, bool geo, int filled, int lane)
+// wb / ib / fb: shared-space addresses of the warp's W panel, row infos and F table.
+static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, uint32_t fb, float *__restrict__ gacc, float ox, float oy,
+                                                    float sub_x0, float sub_y0, bool geo, int filled, int lane)
 {
     const int k = lane & 7, quarter = lane >> 3;
-        __syncwarp();
-        float s_c0 = 0.f, s_c1 = 0.f, s_c2 = 0.f, s_n0 = 0.f, s_n1 = 0.f, s_n2 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
-        float u10 = 0.f, u1x = 0.f, u1y = 0.f, u20 = 0.f, u2x = 0.f, u2y = 0.f, s_op = 0.f;
-        if (k < filled) {
-            const float *row = Wp[k];
+    __syncwarp();
+    float s_c0 = 0.f, s_c1 = 0.f, s_c2 = 0.f, s_n0 = 0.f, s_n1 = 0.f, s_n2 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
+    float u10 = 0.f, u1x = 0.f, u1y = 0.f, u20 = 0.f, u2x = 0.f, u2y = 0.f, s_op = 0.f;
+    if (k < filled) {
+        const uint32_t row = wb + (k * BW_WROW + quarter * 8) * 4;
+        const uint32_t frow = fb + quarter * 8 * 32;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int p = quarter * 8 + i;                       // pixel (lane index of phase 1) inside the sub-tile
-                const float dxp = sub_x0 + (float)i;                 // its offset from the tile origin: x = p & 7 = i
-                const float dyp = sub_y0 + (float)quarter;           //                                 y = p >> 3 = quarter
-                const float c = row[p], w1 = row[32 + p], Dp = row[64 + p];
-                const float4 f0 = F[p][0];
-                s_c0 = fmaf(c, f0.x, s_c0);
-                s_c1 = fmaf(c, f0.y, s_c1);
-                s_c2 = fmaf(c, f0.z, s_c2);
-                s_op += w1;
-                const uint32_t sel = __float_as_uint(Dp) & 3u;       // arg-min barycentric (1, 2, 3) packed in the two LSBs
-                const float u1 = sel == 1u ? Dp : (sel == 3u ? -Dp : 0.0f);
-                const float u2 = sel == 2u ? Dp : (sel == 3u ? -Dp : 0.0f);
-                if (geo) {
-                    const float4 f1 = F[p][1];
-                    const float cg = c * f0.w;                       // contrib * gd
-                    s_n0 = fmaf(c, f1.x, s_n0);
-                    s_n1 = fmaf(c, f1.y, s_n1);
-                    s_n2 = fmaf(c, f1.z, s_n2);
-                    m0 += cg;
-                    m1 = fmaf(cg, dxp, m1);
-                    m2 = fmaf(cg, dyp, m2);
-                }
-                u10 += u1;
-                u1x = fmaf(u1, dxp, u1x);
-                u1y = fmaf(u1, dyp, u1y);
-                u20 += u2;
-                u2x = fmaf(u2, dxp, u2x);
-                u2y = fmaf(u2, dyp, u2y);
-            }
-        }
-#define XQ(v) v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16)
-        XQ(s_c0); XQ(s_c1); XQ(s_c2); XQ(s_op); XQ(u10); XQ(u1x); XQ(u1y); XQ(u20); XQ(u2x); XQ(u2y);
-        if (geo) { XQ(s_n0); XQ(s_n1); XQ(s_n2); XQ(m0); XQ(m1); XQ(m2); }
-#undef XQ
-        if (k < filled) {
-            const float4 e1 = info[k].e1, e2 = info[k].e2, ex = info[k].x;
-            float *g = gacc + (size_t)__float_as_uint(ex.w) * GACC_STRIDE;
-            const float inv = e2.z;
-            const float p1x = e1.x - ox, p1y = e1.y - oy, p2x = e1.z - ox, p2y = e1.w - oy, p3x = e2.x - ox, p3y = e2.y - oy;
-            float S1 = u10, M1x = u1x, M1y = u1y, S2 = u20, M2x = u2x, M2y = u2y;
-            float gv0 = 0.f, gv1 = 0.f, gv2 = 0.f;
+        for (int i = 0; i < 8; i++) {
+            // pixel p = quarter * 8 + i (lane index of phase 1) inside the sub-tile: x = p & 7 = i, y = p >> 3 = quarter
+            const float dxp = sub_x0 + (float)i;
+            const float dyp = sub_y0 + (float)quarter;
+            const float c = lds32f(row + 4 * i), w1 = lds32f(row + 4 * (32 + i)), Dp = lds32f(row + 4 * (64 + i));
+            const float4 f0 = lds128(frow + 32 * i);
+            s_c0 = fmaf(c, f0.x, s_c0);
+            s_c1 = fmaf(c, f0.y, s_c1);
+            s_c2 = fmaf(c, f0.z, s_c2);
+            s_op += w1;
+            const uint32_t sel = __float_as_uint(Dp) & 3u;       // arg-min barycentric (1, 2, 3) packed in the two LSBs
+            const float u1 = sel == 1u ? Dp : (sel == 3u ? -Dp : 0.0f);
+            const float u2 = sel == 2u ? Dp : (sel == 3u ? -Dp : 0.0f);
             if (geo) {
-                // affine barycentrics about the tile origin: a_i(d) = a_io + A_i dx + B_i dy
-                const float a1o = (p2x * p3y - p2y * p3x) * inv, A1 = (e1.w - e2.y) * inv, B1 = (e2.x - e1.z) * inv;
-                const float a2o = (p3x * p1y - p3y * p1x) * inv, A2 = (e2.y - e1.y) * inv, B2 = (e1.x - e2.x) * inv;
-                const float a3o = 1.0f - a1o - a2o, A3 = -A1 - A2, B3 = -B1 - B2;
-                gv0 = fmaf(B1, m2, fmaf(A1, m1, a1o * m0));   // sum gd contrib a_1
-                gv1 = fmaf(B2, m2, fmaf(A2, m1, a2o * m0));
-                gv2 = fmaf(B3, m2, fmaf(A3, m1, a3o * m0));
-                const float d13 = ex.x - ex.z, d23 = ex.y - ex.z;   // depth term of ga_k = (vd_k - vd_3) gd contrib
-                S1 = fmaf(d13, m0, S1); M1x = fmaf(d13, m1, M1x); M1y = fmaf(d13, m2, M1y);
-                S2 = fmaf(d23, m0, S2); M2x = fmaf(d23, m1, M2x); M2y = fmaf(d23, m2, M2y);
+                const float4 f1 = lds128(frow + 32 * i + 16);
+                const float cg = c * f0.w;                       // contrib * gd
+                s_n0 = fmaf(c, f1.x, s_n0);
+                s_n1 = fmaf(c, f1.y, s_n1);
+                s_n2 = fmaf(c, f1.z, s_n2);
+                m0 += cg;
+                m1 = fmaf(cg, dxp, m1);
+                m2 = fmaf(cg, dyp, m2);
             }
-            // moments about v1: q = p - v1 = d - (v1 - o)
-            const float Q1x = fmaf(-p1x, S1, M1x), Q1y = fmaf(-p1y, S1, M1y), Q2x = fmaf(-p1x, S2, M2x), Q2y = fmaf(-p1y, S2, M2y);
-            if (quarter == 0) red_add4(g, S1, Q1x, Q1y, S2);
-            else if (quarter == 1) red_add4(g + 4, Q2x, Q2y, s_op, s_n0);
-            else if (quarter == 2) red_add4(g + 8, s_c0, s_c1, s_c2, s_n1);
-            else if (geo) red_add4(g + 12, s_n2, gv0, gv1, gv2);
+            u10 += u1;
+            u1x = fmaf(u1, dxp, u1x);
+            u1y = fmaf(u1, dyp, u1y);
+            u20 += u2;
+            u2x = fmaf(u2, dxp, u2x);
+            u2y = fmaf(u2, dyp, u2y);
         }
-        __syncwarp();
+    }
+#define XQ(v) v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16)
+    XQ(s_c0); XQ(s_c1); XQ(s_c2); XQ(s_op); XQ(u10); XQ(u1x); XQ(u1y); XQ(u20); XQ(u2x); XQ(u2y);
+    if (geo) { XQ(s_n0); XQ(s_n1); XQ(s_n2); XQ(m0); XQ(m1); XQ(m2); }
+#undef XQ
+    if (k < filled) {
+        const float4 e1 = lds128(ib + 48 * k), e2 = lds128(ib + 48 * k + 16), ex = lds128(ib + 48 * k + 32);
+        float *g = gacc + (size_t)__float_as_uint(ex.w) * GACC_STRIDE;
+        const float inv = e2.z;
+        const float p1x = e1.x - ox, p1y = e1.y - oy, p2x = e1.z - ox, p2y = e1.w - oy, p3x = e2.x - ox, p3y = e2.y - oy;
+        float S1 = u10, M1x = u1x, M1y = u1y, S2 = u20, M2x = u2x, M2y = u2y;
+        float gv0 = 0.f, gv1 = 0.f, gv2 = 0.f;
+        if (geo) {
+            // affine barycentrics about the tile origin: a_i(d) = a_io + A_i dx + B_i dy
+            const float a1o = (p2x * p3y - p2y * p3x) * inv, A1 = (e1.w - e2.y) * inv, B1 = (e2.x - e1.z) * inv;
+            const float a2o = (p3x * p1y - p3y * p1x) * inv, A2 = (e2.y - e1.y) * inv, B2 = (e1.x - e2.x) * inv;
+            const float a3o = 1.0f - a1o - a2o, A3 = -A1 - A2, B3 = -B1 - B2;
+            gv0 = fmaf(B1, m2, fmaf(A1, m1, a1o * m0));   // sum gd contrib a_1
+            gv1 = fmaf(B2, m2, fmaf(A2, m1, a2o * m0));
+            gv2 = fmaf(B3, m2, fmaf(A3, m1, a3o * m0));
+            const float d13 = ex.x - ex.z, d23 = ex.y - ex.z;   // depth term of ga_k = (vd_k - vd_3) gd contrib
+            S1 = fmaf(d13, m0, S1); M1x = fmaf(d13, m1, M1x); M1y = fmaf(d13, m2, M1y);
+            S2 = fmaf(d23, m0, S2); M2x = fmaf(d23, m1, M2x); M2y = fmaf(d23, m2, M2y);
+        }
+        // moments about v1: q = p - v1 = d - (v1 - o)
+        const float Q1x = fmaf(-p1x, S1, M1x), Q1y = fmaf(-p1y, S1, M1y), Q2x = fmaf(-p1x, S2, M2x), Q2y = fmaf(-p1y, S2, M2y);
+        if (quarter == 0) red_add4(g, S1, Q1x, Q1y, S2);
+        else if (quarter == 1) red_add4(g + 4, Q2x, Q2y, s_op, s_n0);
+        else if (quarter == 2) red_add4(g + 8, s_c0, s_c1, s_c2, s_n1);
+        else if (geo) red_add4(g + 12, s_n2, gv0, gv1, gv2);
+    }
+    __syncwarp();
 }
 
 template <bool RICH, bool GAMMA1>
 __global__ void __launch_bounds__(TS2D_BLOCK, 4)
 k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world, int n_tiles, float gamma, const uint2 *__restrict__ ranges,
-                  const uint32_t *__restrict__ list, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1, float bg_depth,
-                  const float *__restrict__ background, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
-                  const float *__restrict__ dL_dout_feature, const float *__restrict__ dL_dout_depth,
+                  const uint32_t *__restrict__ keys, const uint32_t *__restrict__ list, const float4 *__restrict__ rec0,
+                  const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ background, const float *__restrict__ final_T,
+                  const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dout_feature, const float *__restrict__ dL_dout_depth,
                   const float *__restrict__ dL_dout_normal, float *__restrict__ gacc)
 {
+    using L = BwdLayout<RICH>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BwdSmem &S = *reinterpret_cast<BwdSmem *>(smem_raw);
 
     const int tile = blockIdx.x * shard_world + shard_rank;
     if (tile >= n_tiles) return;
@@ -153,9 +150,10 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
     const size_t HW = (size_t)H * W_;
     GammaK gk = make_gamma(gamma);
     gk.is_one = GAMMA1;
+    const uint32_t sb = smem_base(smem_raw + warp * L::BYTES);  // this warp's block
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     const uint2 range = ranges[tile];
-    const uint32_t len = range.y - range.x;
     float T = inside ? final_T[pix] : 0.0f;
     const uint32_t last = inside ? n_contrib[pix] : 0u;
 
@@ -173,127 +171,139 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
             gd = dL_dout_depth[pix];
         }
     }
-    S.F[warp][lane][0] = make_float4(gp0, gp1, gp2, gd);  // per-pixel table for phase 2
-    S.F[warp][lane][1] = make_float4(gn0, gn1, gn2, 0.0f);
-    const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last);
-    if (tid == 0) S.tile_last = 0;
-    __syncthreads();
-    // geometry upstream gradients all zero in this tile (w_geometry = 0 training configs): the normal / depth
+    sts128(sb + L::F + 32 * lane, make_float4(gp0, gp1, gp2, gd));  // per-pixel table for phase 2
+    sts128(sb + L::F + 32 * lane + 16, make_float4(gn0, gn1, gn2, 0.0f));
+    // geometry upstream gradients all zero in this sub-tile (w_geometry = 0 training configs): the normal / depth
     // terms are exactly zero for the reference too, so skipping them changes no bit of the result
-    const bool geo = RICH && __syncthreads_or(gd != 0.0f || gn0 != 0.0f || gn1 != 0.0f || gn2 != 0.0f);
-    if (lane == 0) atomicMax(&S.tile_last, warp_last);
-    __syncthreads();
-    const uint32_t tile_last = S.tile_last;
+    const bool geo = RICH && __any_sync(0xffffffffu, gd != 0.0f || gn0 != 0.0f || gn1 != 0.0f || gn2 != 0.0f);
+    const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last);
+    __syncwarp();
 
-    float(*Wp)[BW_WROW] = S.W[warp];
-    RowInfo *info = S.info[warp];
-    int prow = 0;  // next free panel row (rows persist across batches: RowInfo carries what phase 2 needs)
+    int prow = 0;  // next free panel row (rows persist across rounds: the row info carries what phase 2 needs)
     const float sub_x0 = (float)((warp & 1) * 8), sub_y0 = (float)((warp >> 1) * 4);
-    auto flush_panel = [&](int filled) { bwd_flush_panel(Wp, info, S.F[warp], gacc, ox, oy, sub_x0, sub_y0, geo, filled, lane); };
+    auto flush_panel = [&](int filled) { bwd_flush_panel(sb + L::W, sb + L::INFO, sb + L::F, gacc, ox, oy, sub_x0, sub_y0, geo, filled, lane); };
 
-    // batches are staged in REVERSE list order: staged slot t of a batch is list position (top - t)
-    for (uint32_t done_cnt = len - tile_last; done_cnt < len; done_cnt += BW_BATCH) {
-        __syncthreads();
-        const int n = min((uint32_t)BW_BATCH, len - done_cnt);
-        if (tid < n) {
-            const uint32_t id = list[range.y - 1 - done_cnt - tid];
+    // Back to front: `rem` list positions [range.x, range.x + rem) are still to be scanned; a chunk is the 32 positions
+    // below range.x + rem, lane l looking at position range.x + rem - 1 - l (so ballot order == visiting order).
+    uint32_t rem = warp_last;
+    uint32_t kreg = (lane < rem) ? __ldg(keys + range.x + rem - 1 - lane) : 0u;  // always one chunk ahead
+    while (rem > 0) {
+        // ---- gather
+        int count = 0;
+        while (rem > 0) {
+            const bool cov = (kreg >> warp) & 1u;
+            const uint32_t b = __ballot_sync(0xffffffffu, cov);
+            const int n = __popc(b);
+            if (count + n > 32) break;  // this chunk opens the next round (kreg still holds it)
+            if (cov) sts32(sb + L::POS + (count + __popc(b & lt_mask)) * L::POS_STRIDE, rem - 1 - lane);  // tile-relative position
+            count += n;
+            rem -= min(rem, 32u);
+            kreg = (lane < rem) ? __ldg(keys + range.x + rem - 1 - lane) : 0u;
+        }
+        if (count == 0) break;
+        __syncwarp();
+        // ---- stage
+        if (lane < count) {
+            const uint32_t ea = sb + lane * L::EB;
+            const uint32_t id = list[range.x + lds32(sb + L::POS + lane * L::POS_STRIDE)];
             const float4 *r = rec0 + 3 * (size_t)id;
             const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
-            const float inv = r1.z;  // the record carries 1/area2 (K1 computes it once per triangle)
-            BwdEntry &E = S.ent[tid];
-            E.e1 = r0;
-            E.e2 = r1;
-            E.col = make_float4(r2.x, r2.y, r2.z, __uint_as_float(id));
+            sts128(ea, r0);
+            sts128(ea + 16, r1);
+            sts128(ea + 32, make_float4(r2.x, r2.y, r2.z, __uint_as_float(id)));
             if (RICH) {
                 const float4 *q = rec1 + 2 * (size_t)id;
-                E.q0 = __ldg(q);
-                E.q1 = __ldg(q + 1);
-            }
-            S.mask[tid] = (uint8_t)subtile_mask(r0, r1, inv, ox, oy, gk);
-        }
-        __syncthreads();
-
-        for (int c = 0; c * 32 < n; c++) {
-            const int idx = c * 32 + lane;
-            const uint32_t mine = (idx < n) ? (uint32_t)S.mask[idx] : 0u;
-            uint32_t bits = __ballot_sync(0xffffffffu, (mine >> warp) & 1u);
-            while (bits) {
-                const int j = c * 32 + (__ffs(bits) - 1);
-                bits &= bits - 1;
-                const uint32_t pos = len - 1 - done_cnt - j;  // 0-based list position
-                if (pos >= warp_last) continue;                // warp-uniform
-                const BwdEntry &E = S.ent[j];
-                const float4 e1 = E.e1, e2 = E.e2;
-                float w_c = 0.0f, w_op = 0.0f, w_D = 0.0f;
-                if (pos < last) {
-                    FastPair f;
-                    bool unc;
-                    bool hit = eval_fast(e1, e2, pxf, pyf, gk, f, unc);
-                    // one more reference decision lives in the backward pass: op*G < 0.99 (clamp not active)
-                    unc = unc || (fabsf(f.og - 0.99f) <= 0.99f * gk.band);
-                    if (unc) {
-                        const float area2 = __ldg(&rec0[3 * (size_t)__float_as_uint(E.col.w) + 2].w);
-                        PairEval e;
-                        hit = eval_exact(e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, area2, e2.w, gk.two_gamma, pxf, pyf, e);
-                        f.a1 = e.a1; f.a2 = e.a2; f.a3 = e.a3; f.ecc = e.ecc;
-                        if (hit) { f.power = e.power; f.G = e.G; f.og = __fmul_rn(e2.w, e.G); f.alpha = e.alpha; }
-                    }
-                    if (hit) {
-                        const float4 col = E.col;
-                        const float om = 1.0f - f.alpha;
-                        T = T * rcp_approx(om);
-                        w_c = f.alpha * T;
-                        float dL_dcontrib = gp0 * (col.x - acc0);
-                        dL_dcontrib = fmaf(gp1, col.y - acc1, dL_dcontrib);
-                        dL_dcontrib = fmaf(gp2, col.z - acc2, dL_dcontrib);
-                        acc0 = fmaf(f.alpha, col.x, om * acc0);
-                        acc1 = fmaf(f.alpha, col.y, om * acc1);
-                        acc2 = fmaf(f.alpha, col.z, om * acc2);
-                        if (geo) {
-                            const float4 q0 = E.q0, q1 = E.q1;
-                            dL_dcontrib = fmaf(gn0, q0.x - accn0, dL_dcontrib);
-                            dL_dcontrib = fmaf(gn1, q0.y - accn1, dL_dcontrib);
-                            dL_dcontrib = fmaf(gn2, q0.z - accn2, dL_dcontrib);
-                            accn0 = fmaf(f.alpha, q0.x, om * accn0);
-                            accn1 = fmaf(f.alpha, q0.y, om * accn1);
-                            accn2 = fmaf(f.alpha, q0.z, om * accn2);
-                            const float depth = fmaf(q1.y, f.a3, fmaf(q0.w, f.a1, q1.x * f.a2));
-                            dL_dcontrib = fmaf(gd, depth - accd, dL_dcontrib);
-                            accd = fmaf(f.alpha, depth, om * accd);
-                        }
-                        const float dL_dalpha = dL_dcontrib * T;
-                        w_op = dL_dalpha * f.G;  // unconditional (backward.cu:490)
-                        const float dL_dpower = (f.og < 0.99f) ? dL_dalpha * f.alpha : 0.0f;
-                        const float D = -3.0f * dL_dpower * gk.two_gamma * f.power * rcp_approx(f.ecc + TS2D_EPS);
-                        // sub-gradient of min: first arg-min in the order a1, a2, a3 (backward.cu:449-461)
-                        const uint32_t sel = (f.a1 <= f.a2 && f.a1 <= f.a3) ? 1u : ((f.a2 <= f.a1 && f.a2 <= f.a3) ? 2u : 3u);
-                        w_D = __uint_as_float((__float_as_uint(D) & ~3u) | sel);
-                    }
-                }
-                if (__ballot_sync(0xffffffffu, w_c != 0.0f) == 0u) continue;
-                float *row = Wp[prow];
-                row[lane] = w_c;
-                row[32 + lane] = w_op;
-                row[64 + lane] = w_D;
-                if (lane == 0) {
-                    info[prow].e1 = e1;
-                    info[prow].e2 = e2;
-                    info[prow].x = make_float4(E.q0.w, E.q1.x, E.q1.y, E.col.w);
-                }
-                if (++prow == BW_ROWS) {
-                    flush_panel(BW_ROWS);
-                    prow = 0;
-                }
+                const float4 q0 = __ldg(q), q1 = __ldg(q + 1);
+                sts128(ea + 48, q0);
+                sts32f(ea + 64, q1.x);  // +72 holds the list position
+                sts32f(ea + 68, q1.y);
             }
         }
+        __syncwarp();
+        // ---- walk
+        uint32_t ea = sb;
+        for (int j = 0; j < count; j++, ea += L::EB) {
+            const float4 e1 = lds128(ea), e2 = lds128(ea + 16);
+            const uint32_t pos = lds32(sb + L::POS + j * L::POS_STRIDE);
+            float w_c = 0.0f, w_op = 0.0f, w_D = 0.0f;
+            if (pos < last) {
+                FastPair f;
+                bool unc;
+                bool hit = eval_fast(e1, e2, pxf, pyf, gk, f, unc);
+                // one more reference decision lives in the backward pass: op*G < 0.99 (clamp not active)
+                unc = unc || (fabsf(f.og - 0.99f) <= 0.99f * gk.band);
+                if (unc) {
+                    const float area2 = __ldg(&rec0[3 * (size_t)lds32(ea + 44) + 2].w);
+                    PairEval e;
+                    hit = eval_exact(e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, area2, e2.w, gk.two_gamma, pxf, pyf, e);
+                    f.a1 = e.a1; f.a2 = e.a2; f.a3 = e.a3; f.ecc = e.ecc;
+                    if (hit) { f.power = e.power; f.G = e.G; f.og = __fmul_rn(e2.w, e.G); f.alpha = e.alpha; }
+                }
+                if (hit) {
+                    const float4 col = lds128(ea + 32);
+                    const float om = 1.0f - f.alpha;
+                    T = T * rcp_approx(om);
+                    w_c = f.alpha * T;
+                    float dL_dcontrib = gp0 * (col.x - acc0);
+                    dL_dcontrib = fmaf(gp1, col.y - acc1, dL_dcontrib);
+                    dL_dcontrib = fmaf(gp2, col.z - acc2, dL_dcontrib);
+                    acc0 = fmaf(f.alpha, col.x, om * acc0);
+                    acc1 = fmaf(f.alpha, col.y, om * acc1);
+                    acc2 = fmaf(f.alpha, col.z, om * acc2);
+                    if (geo) {
+                        const float4 q0 = lds128(ea + 48);
+                        const float2 q1 = lds64(ea + 64);
+                        dL_dcontrib = fmaf(gn0, q0.x - accn0, dL_dcontrib);
+                        dL_dcontrib = fmaf(gn1, q0.y - accn1, dL_dcontrib);
+                        dL_dcontrib = fmaf(gn2, q0.z - accn2, dL_dcontrib);
+                        accn0 = fmaf(f.alpha, q0.x, om * accn0);
+                        accn1 = fmaf(f.alpha, q0.y, om * accn1);
+                        accn2 = fmaf(f.alpha, q0.z, om * accn2);
+                        const float depth = fmaf(q1.y, f.a3, fmaf(q0.w, f.a1, q1.x * f.a2));
+                        dL_dcontrib = fmaf(gd, depth - accd, dL_dcontrib);
+                        accd = fmaf(f.alpha, depth, om * accd);
+                    }
+                    const float dL_dalpha = dL_dcontrib * T;
+                    w_op = dL_dalpha * f.G;  // unconditional (backward.cu:490)
+                    const float dL_dpower = (f.og < 0.99f) ? dL_dalpha * f.alpha : 0.0f;
+                    const float D = -3.0f * dL_dpower * gk.two_gamma * f.power * rcp_approx(f.ecc + TS2D_EPS);
+                    // sub-gradient of min: first arg-min in the order a1, a2, a3 (backward.cu:449-461)
+                    const uint32_t sel = (f.a1 <= f.a2 && f.a1 <= f.a3) ? 1u : ((f.a2 <= f.a1 && f.a2 <= f.a3) ? 2u : 3u);
+                    w_D = __uint_as_float((__float_as_uint(D) & ~3u) | sel);
+                }
+            }
+            if (!__any_sync(0xffffffffu, w_c != 0.0f)) continue;
+            const uint32_t row = sb + L::W + (prow * BW_WROW + lane) * 4;
+            sts32f(row, w_c);
+            sts32f(row + 128, w_op);
+            sts32f(row + 256, w_D);
+            if (lane == 0) {
+                const uint32_t ia = sb + L::INFO + prow * 48;
+                sts128(ia, e1);
+                sts128(ia + 16, e2);
+                float4 x = make_float4(0.f, 0.f, 0.f, lds32f(ea + 44));
+                if (RICH) {
+                    const float2 q1 = lds64(ea + 64);
+                    x.x = lds32f(ea + 60);
+                    x.y = q1.x;
+                    x.z = q1.y;
+                }
+                sts128(ia + 32, x);
+            }
+            if (++prow == BW_ROWS) {
+                flush_panel(BW_ROWS);
+                prow = 0;
+            }
+        }
+        __syncwarp();  // the next gather overwrites positions / entries
     }
     if (prow) flush_panel(prow);
 }
 
 }  // namespace
 
-int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
-                                ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s)
+int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
+                                const uint32_t *list, ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s)
 {
     const int W = cam->width, H = cam->height;
     const int gx = (W + TS2D_TILE - 1) / TS2D_TILE, gy = (H + TS2D_TILE - 1) / TS2D_TILE;
@@ -302,14 +312,15 @@ int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
     TS2D_CUDA_TRY(cudaMemsetAsync(gacc, 0, sizeof(float) * GACC_STRIDE * (size_t)g->P, s));
     if (owned <= 0) return 0;
     const bool g1 = g->gamma == 1.0f;
-    const size_t smem = sizeof(BwdSmem);
-#define TS2D_BWD_ARGS                                                                                                                      \
-    W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, list, gs.rec0, gs.rec1, g->background_depth, g->background, \
-        is.final_T, is.n_contrib, loss->dL_dout_feature
-#define TS2D_BWD_LAUNCH(R, G, ...)                                                                                          \
-    do {                                                                                                                    \
-        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_bwd_fast<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_render_bwd_fast<R, G><<<owned, TS2D_BLOCK, smem, s>>>(TS2D_BWD_ARGS, __VA_ARGS__, gacc);                          \
+#define TS2D_BWD_ARGS                                                                                                                 \
+    W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, keys, list, gs.rec0, gs.rec1, g->background_depth,   \
+        g->background, is.final_T, is.n_contrib, loss->dL_dout_feature
+#define TS2D_BWD_LAUNCH(R, G, ...)                                                                                                      \
+    do {                                                                                                                                \
+        const size_t smem = 8 * (size_t)BwdLayout<R>::BYTES;                                                                            \
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_bwd_fast<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_bwd_fast<R, G>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));              \
+        k_render_bwd_fast<R, G><<<owned, TS2D_BLOCK, smem, s>>>(TS2D_BWD_ARGS, __VA_ARGS__, gacc);                                      \
     } while (0)
     if (f->rich_info) {
         if (g1) TS2D_BWD_LAUNCH(true, true, loss->dL_dout_depth, loss->dL_dout_normal);

@@ -2,33 +2,40 @@
 //
 // Same contract as k_render_fwd (ts2d_render_fwd.cu) -- which stays as the op-for-op mirror of
 // R2D/src/forward.cu:198-355 -- but organised for instruction throughput on sm_100a (the kernel is
-// FP32-issue bound, not HBM bound: ncu shows ~80 % issue-slot utilisation at 2 % DRAM throughput):
-//   * staging thread = one list entry: 3(+2) LDG.128 of the raster record, reciprocal of area2,
-//     8-bit sub-tile coverage mask (ts2d_fast.cuh), one 80-byte shared-memory entry;
-//   * each warp walks only the entries whose mask bit is set for its 8x4 sub-tile (ballot + ffs);
-//   * per pixel: reference-shaped barycentrics with one reciprocal multiply, min3, 1 MUFU.EX2;
-//     decisions inside the rounding band are re-taken with eval_exact(); the T <= 1e-4 cut is re-taken
-//     with an exact transmittance re-walk done cooperatively by the warp (exact_T_upto) when T lands
-//     inside its running error bound;
-//   * contrib_sum / contrib_max: one REDUX.SUM (fixed-point 2^-26) + one REDUX.MAX per (warp, triangle),
-//     then a single lane issues the two REDs.
+// FP32-issue bound, not HBM bound: ncu shows ~80 % issue-slot utilisation at 2 % DRAM throughput).
+//
+// Warp-autonomous walk.  Each warp owns one 8x4-pixel sub-tile of a 16x16 tile and never synchronises with the
+// other warps of its CTA (the cooperative-staging version of this kernel lost 20 % of its warp time at the
+// per-batch __syncthreads: the number of list entries that touch a sub-tile differs from warp to warp):
+//   gather   the warp scans the tile's instance keys 32 at a time (one coalesced load, prefetched one chunk ahead),
+//            keeps the entries whose sub-tile bit is set (ts2d_binning.cu computes the 8-bit coverage mask once per
+//            instance) and compacts their list positions until up to 32 are collected;
+//   stage    lane i loads the raster record of collected entry i (3(+2) LDG.128) into the warp's private
+//            shared-memory buffer -- only records that the sub-tile really needs are read;
+//   walk     a plain counted loop over the staged entries: reference-shaped barycentrics with one reciprocal
+//            multiply, min3, 1 MUFU.EX2 per pixel; decisions inside the rounding band are re-taken with
+//            eval_exact(); the T <= 1e-4 cut is re-taken with an exact transmittance re-walk done cooperatively
+//            by the warp (exact_T_upto) when T lands inside its running error bound.  One REDUX.OR per entry
+//            carries the three warp-level facts (somebody blended / somebody needs the re-walk / somebody is alive).
+//   contrib_sum / contrib_max: blended rows are parked in a 16-row panel; every 16 rows the lanes switch roles
+//            (lane = triangle slot x pixel half), reduce with plain FADD / FMNMX and issue one RED pair per triangle.
 #include "ts2d_fast.cuh"
 
 namespace {
 
-constexpr int FW_SLOTS = 16;  // triangles per contrib-statistics panel
+constexpr int FW_SLOTS = 16;   // triangles per contrib-statistics panel
+constexpr int FW_PROW = 33;    // panel row stride in words: conflict-free for both access patterns
 
+// Per-warp shared-memory block (byte offsets from the warp's base address):
+//   entry j at j * EB:  {v1.x v1.y v2.x v2.y} {v3.x v3.y 1/area2 op} {r g b id} [RICH: {n.x n.y n.z vd1} {vd2 vd3 pos -}]
+//   non-RICH: list positions in a separate u32[32] after the entries;  RICH: contrib panel [16][33] floats after that.
 template <bool RICH>
-struct __align__(16) FwdEntry {
-    float4 e1;   // v1.x, v1.y, v2.x, v2.y
-    float4 e2;   // v3.x, v3.y, 1/area2, opacity
-    float4 col;  // r, g, b, triangle id (bits)
-    float4 q0;   // n.x, n.y, n.z, vd1   (rich)
-    float4 q1;   // vd2, vd3, -, -       (rich)
-};
-template <>
-struct __align__(16) FwdEntry<false> {
-    float4 e1, e2, col;
+struct FwdLayout {
+    static constexpr int EB = RICH ? 80 : 48;
+    static constexpr int POS = RICH ? 72 : 32 * 48;      // position of entry j: POS + j * POS_STRIDE
+    static constexpr int POS_STRIDE = RICH ? 80 : 4;
+    static constexpr int PANEL = RICH ? 32 * 80 : 0;
+    static constexpr int BYTES = RICH ? 32 * 80 + FW_SLOTS * FW_PROW * 4 : 32 * 48 + 128;
 };
 
 // Exact transmittance of pixel (px, py) after visiting list positions [start, upto] (inclusive), computed with the
@@ -54,9 +61,9 @@ __device__ __noinline__ float exact_T_upto(const uint32_t *__restrict__ list, co
     return T;
 }
 
-// Out-of-line slow path: the reference's own decision and alpha for one pair.
+// The reference's own decision and alpha for one pair.
 __device__ __forceinline__ bool exact_pair(const float4 e1, const float4 e2, const float4 *__restrict__ rec0, uint32_t id, float two_gamma,
-                                        float px, float py, float &alpha, float &power, float &a1, float &a2, float &a3)
+                                           float px, float py, float &alpha, float &power, float &a1, float &a2, float &a3)
 {
     const float area2 = __ldg(&rec0[3 * (size_t)id + 2].w);
     PairEval e;
@@ -69,16 +76,20 @@ __device__ __forceinline__ bool exact_pair(const float4 e1, const float4 e2, con
     return hit;
 }
 
+#ifndef TS2D_FWD_MINB
+#define TS2D_FWD_MINB 5  // resident CTAs per SM the register allocation targets (5 -> 48 registers)
+#endif
+
 template <bool RICH, bool GAMMA1>
-__global__ void __launch_bounds__(TS2D_BLOCK)
+__global__ void __launch_bounds__(TS2D_BLOCK, TS2D_FWD_MINB)
 k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, int n_tiles, float gamma, const uint2 *__restrict__ ranges,
-                  const uint32_t *__restrict__ list, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1, float bg_depth,
-                  const float *__restrict__ background, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
-                  float *__restrict__ out_feature, float *__restrict__ out_depth, float *__restrict__ out_normal,
-                  float *__restrict__ contrib_sum, float *__restrict__ contrib_max)
+                  const uint32_t *__restrict__ keys, const uint32_t *__restrict__ list, const float4 *__restrict__ rec0,
+                  const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ background, float *__restrict__ final_T,
+                  uint32_t *__restrict__ n_contrib, float *__restrict__ out_feature, float *__restrict__ out_depth,
+                  float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max)
 {
-    __shared__ FwdEntry<RICH> s_ent[TS2D_BLOCK];
-    __shared__ uint8_t s_mask[TS2D_BLOCK];
+    using L = FwdLayout<RICH>;
+    __shared__ __align__(16) unsigned char s_raw[8 * L::BYTES];
 
     const int tile = blockIdx.x * shard_world + shard_rank;
     if (tile >= n_tiles) return;
@@ -88,9 +99,10 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
     const int py = tile_y * TS2D_TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
-    const float ox = (float)(tile_x * TS2D_TILE), oy = (float)(tile_y * TS2D_TILE);
     GammaK gk = make_gamma(gamma);
     gk.is_one = GAMMA1;
+    const uint32_t sb = smem_base(s_raw + warp * L::BYTES);  // this warp's block
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     const uint2 range = ranges[tile];
     float T = 1.0f, Terr = 0.0f;  // Terr: bound on |T - (the reference's T)|
@@ -98,8 +110,7 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
     uint32_t last = range.y - range.x;  // n_contrib if the pixel never saturates
     bool done = !inside;
 
-    // contrib statistics panel (RICH): s_panel[warp][slot][pixel]; 33-word rows are conflict-free for both access patterns
-    __shared__ float s_panel[RICH ? 8 : 1][RICH ? FW_SLOTS : 1][RICH ? 33 : 1];
+    // contrib statistics panel (RICH)
     int slot = 0;
     uint32_t my_id = 0;
     const int k = lane & 15, half = lane >> 4;
@@ -107,10 +118,10 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
         __syncwarp();
         float s = 0.0f, m = 0.0f;
         if (k < filled) {
-            const float *row = s_panel[warp][k] + half * 16;
+            const uint32_t row = sb + L::PANEL + (k * FW_PROW + half * 16) * 4;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                const float v = row[i];
+                const float v = lds32f(row + 4 * i);
                 s += v;
                 m = fmaxf(m, v);
             }
@@ -124,97 +135,112 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
         __syncwarp();
     };
 
-    for (uint32_t base = range.x; base < range.y; base += TS2D_BLOCK) {
-        if (__syncthreads_and(done)) break;
-        const int n = min((uint32_t)TS2D_BLOCK, range.y - base);
-        if (tid < n) {
-            const uint32_t id = list[base + tid];
+    uint32_t cur = range.x;  // next list position to scan
+    uint32_t kreg = (cur + lane < range.y) ? __ldg(keys + cur + lane) : 0u;  // keys[cur + lane], always one chunk ahead
+    while (true) {
+        if (__all_sync(0xffffffffu, done)) break;
+        // ---- gather: list positions of up to 32 entries that cover this sub-tile
+        int count = 0;
+        while (cur < range.y) {
+            const bool cov = (kreg >> warp) & 1u;
+            const uint32_t b = __ballot_sync(0xffffffffu, cov);
+            const int n = __popc(b);
+            if (count + n > 32) break;  // this chunk opens the next round (kreg still holds it)
+            if (cov) sts32(sb + L::POS + (count + __popc(b & lt_mask)) * L::POS_STRIDE, cur + lane);
+            count += n;
+            cur += 32;
+            kreg = (cur + lane < range.y) ? __ldg(keys + cur + lane) : 0u;
+        }
+        if (count == 0) break;  // list exhausted
+        __syncwarp();
+        // ---- stage: lane i fetches entry i
+        if (lane < count) {
+            const uint32_t ea = sb + lane * L::EB;
+            const uint32_t id = list[lds32(sb + L::POS + lane * L::POS_STRIDE)];
             const float4 *r = rec0 + 3 * (size_t)id;
             const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
-            const float inv = r1.z;  // the record carries 1/area2 (K1 computes it once per triangle)
-            FwdEntry<RICH> &E = s_ent[tid];
-            E.e1 = r0;
-            E.e2 = r1;
-            E.col = make_float4(r2.x, r2.y, r2.z, __uint_as_float(id));
+            sts128(ea, r0);
+            sts128(ea + 16, r1);
+            sts128(ea + 32, make_float4(r2.x, r2.y, r2.z, __uint_as_float(id)));
             if constexpr (RICH) {
                 const float4 *q = rec1 + 2 * (size_t)id;
-                E.q0 = __ldg(q);
-                E.q1 = __ldg(q + 1);
+                const float4 q0 = __ldg(q), q1 = __ldg(q + 1);
+                sts128(ea + 48, q0);
+                sts32f(ea + 64, q1.x);  // +72 holds the list position
+                sts32f(ea + 68, q1.y);
             }
-            s_mask[tid] = (uint8_t)subtile_mask(r0, r1, inv, ox, oy, gk);
         }
-        __syncthreads();
-
-        for (int c = 0; c * 32 < n; c++) {
-            if (__all_sync(0xffffffffu, done)) break;
-            const int idx = c * 32 + lane;
-            const uint32_t mine = (idx < n) ? (uint32_t)s_mask[idx] : 0u;
-            uint32_t bits = __ballot_sync(0xffffffffu, (mine >> warp) & 1u);
-            while (bits) {
-                const int j = c * 32 + (__ffs(bits) - 1);
-                bits &= bits - 1;
-                const FwdEntry<RICH> &E = s_ent[j];
-                const float4 e1 = E.e1, e2 = E.e2;
-                float contrib = 0.0f;  // > 0 <=> this lane blended the triangle
-                bool tband = false;
-                if (!done) {
-                    FastPair f;
-                    bool unc;
-                    bool hit = eval_fast(e1, e2, pxf, pyf, gk, f, unc);
-                    if (unc) hit = exact_pair(e1, e2, rec0, __float_as_uint(E.col.w), gk.two_gamma, pxf, pyf, f.alpha, f.power, f.a1, f.a2, f.a3);
-                    if (hit) {
-                        contrib = f.alpha * T;
-                        const float4 col = E.col;
-                        acc0 = fmaf(contrib, col.x, acc0);
-                        acc1 = fmaf(contrib, col.y, acc1);
-                        acc2 = fmaf(contrib, col.z, acc2);
-                        if constexpr (RICH) {
-                            const float4 q0 = E.q0, q1 = E.q1;
-                            accn0 = fmaf(contrib, q0.x, accn0);
-                            accn1 = fmaf(contrib, q0.y, accn1);
-                            accn2 = fmaf(contrib, q0.z, accn2);
-                            accd = fmaf(contrib, fmaf(f.a3, q1.y, fmaf(q0.w, f.a1, q1.x * f.a2)), accd);
-                        }
-                        const float om = 1.0f - f.alpha;
-                        // |T_new - T_ref_new| <= |T - T_ref| * om + T * |d alpha| + rounding of the two product chains
-                        Terr = fmaf(Terr, om, contrib * (unc ? 0.0f : fmaf(gk.terr_c1, fabsf(f.power), gk.terr_c0)));
-                        T *= om;
-                        Terr = fmaf(T, 1.3e-7f, Terr);
-                        const float dT = T - 0.0001f;
-                        tband = fabsf(dT) <= Terr;
-                        if (dT <= 0.0f) {  // provisional when tband: re-decided below on the exact transmittance
-                            done = true;
-                            last = base - range.x + j + 1;
-                        }
+        __syncwarp();
+        // ---- walk
+        uint32_t ea = sb;
+        for (int j = 0; j < count; j++, ea += L::EB) {
+            const float4 e1 = lds128(ea), e2 = lds128(ea + 16);
+            float contrib = 0.0f;  // > 0 <=> this lane blended the triangle
+            bool tband = false;
+            if (!done) {
+                FastPair f;
+                bool unc;
+                bool hit = eval_fast(e1, e2, pxf, pyf, gk, f, unc);
+                if (unc) hit = exact_pair(e1, e2, rec0, lds32(ea + 44), gk.two_gamma, pxf, pyf, f.alpha, f.power, f.a1, f.a2, f.a3);
+                if (hit) {
+                    contrib = f.alpha * T;
+                    const float4 col = lds128(ea + 32);
+                    acc0 = fmaf(contrib, col.x, acc0);
+                    acc1 = fmaf(contrib, col.y, acc1);
+                    acc2 = fmaf(contrib, col.z, acc2);
+                    if constexpr (RICH) {
+                        const float4 q0 = lds128(ea + 48);
+                        const float2 q1 = lds64(ea + 64);
+                        accn0 = fmaf(contrib, q0.x, accn0);
+                        accn1 = fmaf(contrib, q0.y, accn1);
+                        accn2 = fmaf(contrib, q0.z, accn2);
+                        accd = fmaf(contrib, fmaf(f.a3, q1.y, fmaf(q0.w, f.a1, q1.x * f.a2)), accd);
+                    }
+                    const float om = 1.0f - f.alpha;
+                    // |T_new - T_ref_new| <= |T - T_ref| * om + T * |d alpha| + rounding of the two product chains
+                    Terr = fmaf(Terr, om, contrib * (unc ? 0.0f : fmaf(gk.terr_c1, fabsf(f.power), gk.terr_c0)));
+                    T *= om;
+                    Terr = fmaf(T, 1.3e-7f, Terr);
+                    const float dT = T - 0.0001f;
+                    tband = fabsf(dT) <= Terr;
+                    if (dT <= 0.0f) {  // provisional when tband: re-decided below on the exact transmittance
+                        done = true;
+                        last = lds32(sb + L::POS + j * L::POS_STRIDE) - range.x + 1;
                     }
                 }
+            }
+            // bit 0: somebody blended; bit 1: somebody's T sits inside its error bound; bit 2: somebody is still alive
+            const uint32_t facts = __reduce_or_sync(0xffffffffu, (contrib > 0.0f ? 1u : 0u) | (tband ? 2u : 0u) | (done ? 0u : 4u));
+            if (facts & 2u) {  // rare: exact transmittance re-walk for one pixel at a time, whole warp cooperating
                 uint32_t need = __ballot_sync(0xffffffffu, tband);
-                while (need) {  // rare: exact transmittance re-walk for one pixel at a time, whole warp cooperating
+                const uint32_t pos = lds32(sb + L::POS + j * L::POS_STRIDE);
+                while (need) {
                     const int src = __ffs(need) - 1;
                     need &= need - 1;
                     const float spx = __shfl_sync(0xffffffffu, pxf, src), spy = __shfl_sync(0xffffffffu, pyf, src);
-                    const float Te = exact_T_upto(list, rec0, range.x, base + j, spx, spy, gk.two_gamma, lane);
+                    const float Te = exact_T_upto(list, rec0, range.x, pos, spx, spy, gk.two_gamma, lane);
                     if (lane == src) {
                         done = (Te <= 0.0001f);
-                        last = done ? (base - range.x + j + 1) : (range.y - range.x);
+                        last = done ? (pos - range.x + 1) : (range.y - range.x);
                         T = Te;
                         Terr = 0.0f;
                     }
                 }
-                if constexpr (RICH) {
-                    // contrib_sum / contrib_max (forward.cu:323-324): park this pair-row in the warp's panel; every 16 rows the
-                    // lanes switch roles (lane = triangle slot x pixel half) and reduce with plain FADD / FMNMX
-                    if (__ballot_sync(0xffffffffu, contrib > 0.0f)) {
-                        s_panel[warp][slot][lane] = contrib;
-                        if (k == slot) my_id = __float_as_uint(E.col.w);
-                        if (++slot == FW_SLOTS) {
-                            flush_panel(FW_SLOTS);
-                            slot = 0;
-                        }
+            }
+            if constexpr (RICH) {
+                // contrib_sum / contrib_max (forward.cu:323-324): park this pair-row in the warp's panel
+                if (facts & 1u) {
+                    sts32f(sb + L::PANEL + (slot * FW_PROW + lane) * 4, contrib);
+                    if (k == slot) my_id = lds32(ea + 44);
+                    if (++slot == FW_SLOTS) {
+                        flush_panel(FW_SLOTS);
+                        slot = 0;
                     }
                 }
             }
+            if ((facts & 6u) == 0u) break;  // every pixel of the sub-tile has saturated (and none is being re-decided)
         }
+        __syncwarp();  // the next gather overwrites positions / entries
     }
     if constexpr (RICH) {
         if (slot) flush_panel(slot);
@@ -240,8 +266,8 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
 
 }  // namespace
 
-int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
-                                ImageState is, const ts2d_forward_out *out, cudaStream_t s)
+int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
+                                const uint32_t *list, ImageState is, const ts2d_forward_out *out, cudaStream_t s)
 {
     const int W = cam->width, H = cam->height;
     const int gx = (W + TS2D_TILE - 1) / TS2D_TILE, gy = (H + TS2D_TILE - 1) / TS2D_TILE;
@@ -249,9 +275,9 @@ int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
     const int owned = (n_tiles - f->shard_rank + f->shard_world - 1) / f->shard_world;
     if (owned <= 0) return 0;
     const bool g1 = g->gamma == 1.0f;
-#define TS2D_FWD_ARGS                                                                                                                      \
-    W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, list, gs.rec0, gs.rec1, g->background_depth, g->background, \
-        is.final_T, is.n_contrib, out->out_feature
+#define TS2D_FWD_ARGS                                                                                                                       \
+    W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, keys, list, gs.rec0, gs.rec1, g->background_depth,         \
+        g->background, is.final_T, is.n_contrib, out->out_feature
     if (f->rich_info) {
         TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_sum, 0, sizeof(float) * (size_t)g->P, s));
         TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
