@@ -31,7 +31,7 @@ constexpr int BW_WROW = 97;     // 3 scalars x 32 pixels + 1 pad word: conflict-
 //   POS   non-RICH only: u32[32] list positions (RICH keeps them in the entry's spare word)
 //   F     per pixel {gp0 gp1 gp2 gd} {gn0 gn1 gn2 -}
 //   W     panel [8 rows][97]: [scalar * 32 + pixel]
-//   INFO  per panel row {v1 v2} {v3 1/area2 op} {vd1 vd2 vd3 id}: what phase 2 needs to know about the triangle
+//   INFO  per panel row {v1 v2} {v3 1/area2 op} {id}: what phase 2 needs to know about the triangle (48 B stride)
 template <bool RICH>
 struct BwdLayout {
     static constexpr int EB = RICH ? 80 : 48;
@@ -50,15 +50,25 @@ __device__ __forceinline__ void red_add4(float *addr, float a, float b, float c,
 
 // phase 2 (out of line: one copy keeps the kernel inside the instruction cache and out of the walk loop's register budget).
 // lane (k, quarter) sums panel row k over pixels quarter*8 .. quarter*8+7, then flushes the triangle.
-// wb / ib / fb: shared-space addresses of the warp's W panel, row infos and F table.
-static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, uint32_t fb, float *__restrict__ gacc, float ox, float oy,
+// wb / ib / fb: shared-space addresses of the warp's W panel, row ids and F table.
+static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, uint32_t fb, const float4 *__restrict__ rec1,
+                                                    float *__restrict__ gacc, float ox, float oy,
                                                     float sub_x0, float sub_y0, bool geo, int filled, int lane)
 {
     const int k = lane & 7, quarter = lane >> 3;
     __syncwarp();
     float s_c0 = 0.f, s_c1 = 0.f, s_c2 = 0.f, s_n0 = 0.f, s_n1 = 0.f, s_n2 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
     float u10 = 0.f, u1x = 0.f, u1y = 0.f, u20 = 0.f, u2x = 0.f, u2y = 0.f, s_op = 0.f;
+    uint32_t id = 0;
+    float vd1 = 0.f, vd2 = 0.f, vd3 = 0.f;
     if (k < filled) {
+        id = lds32(ib + 48 * k + 32);
+        if (geo) {  // vertex depths: re-read from L1/L2, in flight during the panel sums
+            vd1 = __ldg(&rec1[2 * (size_t)id].w);
+            const float2 q = __ldg(reinterpret_cast<const float2 *>(rec1 + 2 * (size_t)id + 1));
+            vd2 = q.x;
+            vd3 = q.y;
+        }
         const uint32_t row = wb + (k * BW_WROW + quarter * 8) * 4;
         const uint32_t frow = fb + quarter * 8 * 32;
 #pragma unroll
@@ -98,8 +108,8 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
     if (geo) { XQ(s_n0); XQ(s_n1); XQ(s_n2); XQ(m0); XQ(m1); XQ(m2); }
 #undef XQ
     if (k < filled) {
-        const float4 e1 = lds128(ib + 48 * k), e2 = lds128(ib + 48 * k + 16), ex = lds128(ib + 48 * k + 32);
-        float *g = gacc + (size_t)__float_as_uint(ex.w) * GACC_STRIDE;
+        const float4 e1 = lds128(ib + 48 * k), e2 = lds128(ib + 48 * k + 16);
+        float *g = gacc + (size_t)id * GACC_STRIDE;
         const float inv = e2.z;
         const float p1x = e1.x - ox, p1y = e1.y - oy, p2x = e1.z - ox, p2y = e1.w - oy, p3x = e2.x - ox, p3y = e2.y - oy;
         float S1 = u10, M1x = u1x, M1y = u1y, S2 = u20, M2x = u2x, M2y = u2y;
@@ -112,7 +122,7 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
             gv0 = fmaf(B1, m2, fmaf(A1, m1, a1o * m0));   // sum gd contrib a_1
             gv1 = fmaf(B2, m2, fmaf(A2, m1, a2o * m0));
             gv2 = fmaf(B3, m2, fmaf(A3, m1, a3o * m0));
-            const float d13 = ex.x - ex.z, d23 = ex.y - ex.z;   // depth term of ga_k = (vd_k - vd_3) gd contrib
+            const float d13 = vd1 - vd3, d23 = vd2 - vd3;   // depth term of ga_k = (vd_k - vd_3) gd contrib
             S1 = fmaf(d13, m0, S1); M1x = fmaf(d13, m1, M1x); M1y = fmaf(d13, m2, M1y);
             S2 = fmaf(d23, m0, S2); M2x = fmaf(d23, m1, M2x); M2y = fmaf(d23, m2, M2y);
         }
@@ -148,7 +158,7 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
     const float ox = (float)(tile_x * TS2D_TILE), oy = (float)(tile_y * TS2D_TILE);
     const size_t pix = (size_t)W_ * py + px;
     const size_t HW = (size_t)H * W_;
-    GammaK gk = make_gamma(gamma);
+    GammaK gk = make_gamma(GAMMA1 ? 1.0f : gamma);  // gamma == 1: every constant of the error model folds to an immediate
     gk.is_one = GAMMA1;
     const uint32_t sb = smem_base(smem_raw + warp * L::BYTES);  // this warp's block
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -179,9 +189,11 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
     const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last);
     __syncwarp();
 
-    int prow = 0;  // next free panel row (rows persist across rounds: the row info carries what phase 2 needs)
+    int prow = 0;  // next free panel row (rows persist across rounds: phase 2 only needs the triangle id)
     const float sub_x0 = (float)((warp & 1) * 8), sub_y0 = (float)((warp >> 1) * 4);
-    auto flush_panel = [&](int filled) { bwd_flush_panel(sb + L::W, sb + L::INFO, sb + L::F, gacc, ox, oy, sub_x0, sub_y0, geo, filled, lane); };
+    auto flush_panel = [&](int filled) {
+        bwd_flush_panel(sb + L::W, sb + L::INFO, sb + L::F, rec1, gacc, ox, oy, sub_x0, sub_y0, geo, filled, lane);
+    };
 
     // Back to front: `rem` list positions [range.x, range.x + rem) are still to be scanned; a chunk is the 32 positions
     // below range.x + rem, lane l looking at position range.x + rem - 1 - l (so ballot order == visiting order).
@@ -277,18 +289,11 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
             sts32f(row, w_c);
             sts32f(row + 128, w_op);
             sts32f(row + 256, w_D);
-            if (lane == 0) {
+            {   // row info for phase 2; every lane stores the same words (cheaper than electing one: no lane id, no predicate)
                 const uint32_t ia = sb + L::INFO + prow * 48;
                 sts128(ia, e1);
                 sts128(ia + 16, e2);
-                float4 x = make_float4(0.f, 0.f, 0.f, lds32f(ea + 44));
-                if (RICH) {
-                    const float2 q1 = lds64(ea + 64);
-                    x.x = lds32f(ea + 60);
-                    x.y = q1.x;
-                    x.z = q1.y;
-                }
-                sts128(ia + 32, x);
+                sts32(ia + 32, lds32(ea + 44));
             }
             if (++prow == BW_ROWS) {
                 flush_panel(BW_ROWS);

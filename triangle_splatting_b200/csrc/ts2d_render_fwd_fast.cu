@@ -15,27 +15,27 @@
 //   walk     a plain counted loop over the staged entries: reference-shaped barycentrics with one reciprocal
 //            multiply, min3, 1 MUFU.EX2 per pixel; decisions inside the rounding band are re-taken with
 //            eval_exact(); the T <= 1e-4 cut is re-taken with an exact transmittance re-walk done cooperatively
-//            by the warp (exact_T_upto) when T lands inside its running error bound.  One REDUX.OR per entry
-//            carries the three warp-level facts (somebody blended / somebody needs the re-walk / somebody is alive).
-//   contrib_sum / contrib_max: blended rows are parked in a 16-row panel; every 16 rows the lanes switch roles
-//            (lane = triangle slot x pixel half), reduce with plain FADD / FMNMX and issue one RED pair per triangle.
+//            by the warp (exact_T_upto) when T lands inside its running error bound.
+//   contrib_sum / contrib_max: each visited entry leaves its 32 per-pixel contrib values in one row of a 32-row panel
+//            (a single STS in the walk); after the walk the lanes switch roles (lane = entry), reduce their row with
+//            plain FADD / FMNMX and issue one RED pair per triangle that was blended anywhere in the sub-tile.
 #include "ts2d_fast.cuh"
 
 namespace {
 
-constexpr int FW_SLOTS = 16;   // triangles per contrib-statistics panel
 constexpr int FW_PROW = 33;    // panel row stride in words: conflict-free for both access patterns
 
 // Per-warp shared-memory block (byte offsets from the warp's base address):
 //   entry j at j * EB:  {v1.x v1.y v2.x v2.y} {v3.x v3.y 1/area2 op} {r g b id} [RICH: {n.x n.y n.z vd1} {vd2 vd3 pos -}]
-//   non-RICH: list positions in a separate u32[32] after the entries;  RICH: contrib panel [16][33] floats after that.
+//   non-RICH: list positions in a separate u32[32] after the entries;
+//   RICH: contrib panel [32 entries][33] floats after that (row j = the 32 pixels' contrib of staged entry j).
 template <bool RICH>
 struct FwdLayout {
     static constexpr int EB = RICH ? 80 : 48;
     static constexpr int POS = RICH ? 72 : 32 * 48;      // position of entry j: POS + j * POS_STRIDE
     static constexpr int POS_STRIDE = RICH ? 80 : 4;
     static constexpr int PANEL = RICH ? 32 * 80 : 0;
-    static constexpr int BYTES = RICH ? 32 * 80 + FW_SLOTS * FW_PROW * 4 : 32 * 48 + 128;
+    static constexpr int BYTES = RICH ? 32 * 80 + 32 * FW_PROW * 4 : 32 * 48 + 128;
 };
 
 // Exact transmittance of pixel (px, py) after visiting list positions [start, upto] (inclusive), computed with the
@@ -77,7 +77,7 @@ __device__ __forceinline__ bool exact_pair(const float4 e1, const float4 e2, con
 }
 
 #ifndef TS2D_FWD_MINB
-#define TS2D_FWD_MINB 5  // resident CTAs per SM the register allocation targets (5 -> 48 registers)
+#define TS2D_FWD_MINB 4  // resident CTAs per SM the register allocation targets (4 -> 64 registers; 5 -> 48 spills the accumulators)
 #endif
 
 template <bool RICH, bool GAMMA1>
@@ -89,7 +89,7 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                   float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max)
 {
     using L = FwdLayout<RICH>;
-    __shared__ __align__(16) unsigned char s_raw[8 * L::BYTES];
+    extern __shared__ __align__(16) unsigned char s_raw[];
 
     const int tile = blockIdx.x * shard_world + shard_rank;
     if (tile >= n_tiles) return;
@@ -99,7 +99,7 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
     const int py = tile_y * TS2D_TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
-    GammaK gk = make_gamma(gamma);
+    GammaK gk = make_gamma(GAMMA1 ? 1.0f : gamma);  // gamma == 1: every constant of the error model folds to an immediate
     gk.is_one = GAMMA1;
     const uint32_t sb = smem_base(s_raw + warp * L::BYTES);  // this warp's block
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -110,29 +110,26 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
     uint32_t last = range.y - range.x;  // n_contrib if the pixel never saturates
     bool done = !inside;
 
-    // contrib statistics panel (RICH)
-    int slot = 0;
-    uint32_t my_id = 0;
-    const int k = lane & 15, half = lane >> 4;
-    auto flush_panel = [&](int filled) {
+    // contrib_sum / contrib_max (forward.cu:323-324), RICH: every visited entry j leaves its 32 per-pixel contrib values in panel
+    // row j (zeros where the pixel skipped it); after the walk lane j reduces row j with plain FADD / FMNMX and issues the
+    // triangle's RED pair -- one flush per round of up to 32 entries, nothing but a single STS inside the walk.
+    auto flush_panel = [&](int visited) {
         __syncwarp();
-        float s = 0.0f, m = 0.0f;
-        if (k < filled) {
-            const uint32_t row = sb + L::PANEL + (k * FW_PROW + half * 16) * 4;
+        if (lane < visited) {
+            const uint32_t row = sb + L::PANEL + lane * (FW_PROW * 4);
+            float s = 0.0f, m = 0.0f;
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
+            for (int i = 0; i < 32; i++) {
                 const float v = lds32f(row + 4 * i);
                 s += v;
                 m = fmaxf(m, v);
             }
+            if (m > 0.0f) {
+                const uint32_t id = lds32(sb + lane * L::EB + 44);
+                atomicAdd(contrib_sum + id, s);
+                atomicMax((unsigned int *)contrib_max + id, __float_as_uint(m));  // contrib >= 0: bit order == value order
+            }
         }
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
-        if (k < filled && half == 0) {
-            atomicAdd(contrib_sum + my_id, s);
-            atomicMax((unsigned int *)contrib_max + my_id, __float_as_uint(m));  // contrib >= 0: bit order == value order
-        }
-        __syncwarp();
     };
 
     uint32_t cur = range.x;  // next list position to scan
@@ -172,8 +169,9 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
         }
         __syncwarp();
         // ---- walk
-        uint32_t ea = sb;
-        for (int j = 0; j < count; j++, ea += L::EB) {
+        uint32_t ea = sb, prow = sb + L::PANEL;
+        int visited = count;
+        for (int j = 0; j < count; j++, ea += L::EB, prow += FW_PROW * 4) {
             const float4 e1 = lds128(ea), e2 = lds128(ea + 16);
             float contrib = 0.0f;  // > 0 <=> this lane blended the triangle
             bool tband = false;
@@ -209,10 +207,9 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                     }
                 }
             }
-            // bit 0: somebody blended; bit 1: somebody's T sits inside its error bound; bit 2: somebody is still alive
-            const uint32_t facts = __reduce_or_sync(0xffffffffu, (contrib > 0.0f ? 1u : 0u) | (tband ? 2u : 0u) | (done ? 0u : 4u));
-            if (facts & 2u) {  // rare: exact transmittance re-walk for one pixel at a time, whole warp cooperating
-                uint32_t need = __ballot_sync(0xffffffffu, tband);
+            if constexpr (RICH) sts32f(prow + lane * 4, contrib);
+            uint32_t need = __ballot_sync(0xffffffffu, tband);
+            if (need) {  // rare: exact transmittance re-walk for one pixel at a time, whole warp cooperating
                 const uint32_t pos = lds32(sb + L::POS + j * L::POS_STRIDE);
                 while (need) {
                     const int src = __ffs(need) - 1;
@@ -227,23 +224,13 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                     }
                 }
             }
-            if constexpr (RICH) {
-                // contrib_sum / contrib_max (forward.cu:323-324): park this pair-row in the warp's panel
-                if (facts & 1u) {
-                    sts32f(sb + L::PANEL + (slot * FW_PROW + lane) * 4, contrib);
-                    if (k == slot) my_id = lds32(ea + 44);
-                    if (++slot == FW_SLOTS) {
-                        flush_panel(FW_SLOTS);
-                        slot = 0;
-                    }
-                }
+            if (__all_sync(0xffffffffu, done)) {  // every pixel of the sub-tile has saturated
+                visited = j + 1;
+                break;
             }
-            if ((facts & 6u) == 0u) break;  // every pixel of the sub-tile has saturated (and none is being re-decided)
         }
-        __syncwarp();  // the next gather overwrites positions / entries
-    }
-    if constexpr (RICH) {
-        if (slot) flush_panel(slot);
+        if constexpr (RICH) flush_panel(visited);
+        __syncwarp();  // the next gather overwrites positions / entries / panel rows
     }
 
     if (inside) {
@@ -278,19 +265,23 @@ int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
 #define TS2D_FWD_ARGS                                                                                                                       \
     W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, keys, list, gs.rec0, gs.rec1, g->background_depth,         \
         g->background, is.final_T, is.n_contrib, out->out_feature
+#define TS2D_FWD_LAUNCH(R, G, ...)                                                                                                     \
+    do {                                                                                                                               \
+        const size_t smem = 8 * (size_t)FwdLayout<R>::BYTES;                                                                           \
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_fwd_fast<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_fwd_fast<R, G>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));             \
+        k_render_fwd_fast<R, G><<<owned, TS2D_BLOCK, smem, s>>>(TS2D_FWD_ARGS, __VA_ARGS__);                                           \
+    } while (0)
     if (f->rich_info) {
         TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_sum, 0, sizeof(float) * (size_t)g->P, s));
         TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
-        if (g1)
-            k_render_fwd_fast<true, true><<<owned, TS2D_BLOCK, 0, s>>>(TS2D_FWD_ARGS, out->depth, out->normal, out->contrib_sum, out->contrib_max);
-        else
-            k_render_fwd_fast<true, false><<<owned, TS2D_BLOCK, 0, s>>>(TS2D_FWD_ARGS, out->depth, out->normal, out->contrib_sum, out->contrib_max);
+        if (g1) TS2D_FWD_LAUNCH(true, true, out->depth, out->normal, out->contrib_sum, out->contrib_max);
+        else TS2D_FWD_LAUNCH(true, false, out->depth, out->normal, out->contrib_sum, out->contrib_max);
     } else {
-        if (g1)
-            k_render_fwd_fast<false, true><<<owned, TS2D_BLOCK, 0, s>>>(TS2D_FWD_ARGS, nullptr, nullptr, nullptr, nullptr);
-        else
-            k_render_fwd_fast<false, false><<<owned, TS2D_BLOCK, 0, s>>>(TS2D_FWD_ARGS, nullptr, nullptr, nullptr, nullptr);
+        if (g1) TS2D_FWD_LAUNCH(false, true, nullptr, nullptr, nullptr, nullptr);
+        else TS2D_FWD_LAUNCH(false, false, nullptr, nullptr, nullptr, nullptr);
     }
+#undef TS2D_FWD_LAUNCH
 #undef TS2D_FWD_ARGS
     return (int)cudaGetLastError();
 }
