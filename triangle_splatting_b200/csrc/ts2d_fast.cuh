@@ -11,12 +11,12 @@
 // contributing (pixel, triangle) pairs, n_contrib and the early-termination point are the
 // reference's, while values differ by fp32 rounding only.
 //
-// Sub-tile culling.  Each warp owns an 8x4-pixel sub-tile.  The staging thread tests its triangle's
+// Sub-tile culling.  Each warp owns an 8x4-pixel sub-tile.  At emission (ts2d_binning.cu) every instance's
 // alpha >= 1/255 footprint (the triangle scaled about its centroid by E = (2 ln(255 op))^(1/(2 gamma)),
-// clipped to ecc <= 10) against the 8 sub-tile rectangles with a conservative 3-edge test on affine
-// edge functions and stores an 8-bit mask; a warp only evaluates list entries whose bit is set
-// (ballot + ffs walk).  Margins cover the rounding of both the affine form and the reference's
-// form, so culled pairs are exactly pairs the reference would have skipped.
+// clipped to ecc <= 10) is tested against the tile's 8 sub-tile rectangles with a conservative 3-edge + bounding-box
+// test on affine edge functions; the 8-bit mask travels in the low bits of the instance key through the tile sort,
+// and a warp only gathers list entries whose bit is set.  Margins cover the rounding of both the affine form
+// and the reference's form, so culled pairs are exactly pairs the reference would have skipped.
 #pragma once
 #include "ts2d_common.cuh"
 
