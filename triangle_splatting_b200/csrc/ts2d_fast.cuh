@@ -83,6 +83,54 @@ __device__ __forceinline__ void sts128(uint32_t a, float4 v)
 __device__ __forceinline__ void sts32f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
+// Packed fp32: sm_100 executes add/mul/fma.rn.f32x2 as ONE FADD2 / FMUL2 / FFMA2 issue slot for two independent IEEE fp32
+// operations; an operand may be a register pair, one register broadcast to both halves (bc()), or an immediate -- ptxas folds
+// the pack / broadcast into the operand form, no MOVs.  Used where two sums share their multiplier (the issue-bound kernels).
+struct v2 {
+    float a, b;
+};
+__device__ __forceinline__ v2 mk2v(float a, float b)
+{
+    v2 r;
+    r.a = a;
+    r.b = b;
+    return r;
+}
+__device__ __forceinline__ v2 bc(float x) { return mk2v(x, x); }
+__device__ __forceinline__ v2 fma2(v2 x, v2 y, v2 z)
+{
+    v2 d;
+    asm("{.reg .b64 rx, ry, rz, rd;\n mov.b64 rx, {%2, %3};\n mov.b64 ry, {%4, %5};\n mov.b64 rz, {%6, %7};\n"
+        " fma.rn.f32x2 rd, rx, ry, rz;\n mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.a), "=f"(d.b)
+        : "f"(x.a), "f"(x.b), "f"(y.a), "f"(y.b), "f"(z.a), "f"(z.b));
+    return d;
+}
+__device__ __forceinline__ v2 mul2(v2 x, v2 y)
+{
+    v2 d;
+    asm("{.reg .b64 rx, ry, rd;\n mov.b64 rx, {%2, %3};\n mov.b64 ry, {%4, %5};\n mul.rn.f32x2 rd, rx, ry;\n mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.a), "=f"(d.b)
+        : "f"(x.a), "f"(x.b), "f"(y.a), "f"(y.b));
+    return d;
+}
+__device__ __forceinline__ v2 add2(v2 x, v2 y)
+{
+    v2 d;
+    asm("{.reg .b64 rx, ry, rd;\n mov.b64 rx, {%2, %3};\n mov.b64 ry, {%4, %5};\n add.rn.f32x2 rd, rx, ry;\n mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.a), "=f"(d.b)
+        : "f"(x.a), "f"(x.b), "f"(y.a), "f"(y.b));
+    return d;
+}
+__device__ __forceinline__ v2 sub2(v2 x, v2 y)
+{
+    v2 d;
+    asm("{.reg .b64 rx, ry, rd;\n mov.b64 rx, {%2, %3};\n mov.b64 ry, {%4, %5};\n sub.rn.f32x2 rd, rx, ry;\n mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.a), "=f"(d.b)
+        : "f"(x.a), "f"(x.b), "f"(y.a), "f"(y.b));
+    return d;
+}
+
 // gamma-dependent constants (kernel-uniform)
 struct GammaK {
     float gamma, two_gamma, inv_two_gamma;
@@ -176,9 +224,13 @@ struct FastPair {
 
 __device__ __forceinline__ bool eval_fast(const float4 e1, const float4 e2, float px, float py, const GammaK gk, FastPair &f, bool &uncertain)
 {
-    f.pv1x = e1.x - px; f.pv1y = e1.y - py;
-    f.pv2x = e1.z - px; f.pv2y = e1.w - py;
-    f.pv3x = e2.x - px; f.pv3y = e2.y - py;
+    {   // the three vertex - pixel differences: each (x, y) pair is one packed subtract
+        const v2 p = mk2v(px, py);
+        const v2 d1 = sub2(mk2v(e1.x, e1.y), p), d2 = sub2(mk2v(e1.z, e1.w), p), d3 = sub2(mk2v(e2.x, e2.y), p);
+        f.pv1x = d1.a; f.pv1y = d1.b;
+        f.pv2x = d2.a; f.pv2y = d2.b;
+        f.pv3x = d3.a; f.pv3y = d3.b;
+    }
     f.a1 = fmaf(f.pv2x, f.pv3y, -(f.pv2y * f.pv3x)) * e2.z;
     f.a2 = fmaf(f.pv3x, f.pv1y, -(f.pv3y * f.pv1x)) * e2.z;
     f.a3 = 1.0f - f.a1 - f.a2;

@@ -280,29 +280,33 @@ __device__ __forceinline__ f3 sh_colour_bwd(int deg, int M, const float *sh, f3 
     g.z *= (mask & 4) ? 0.0f : 1.0f;
     f3 dx = mk3(0, 0, 0), dy = mk3(0, 0, 0), dz = mk3(0, 0, 0);
     const float x = dir.x, y = dir.y, z = dir.z;
+    // `out` may alias `sh` (the tiled kernel back-propagates in place in shared memory): within every band the
+    // coefficients are read before the band's gradients are written.
     st3(out, kC0 * g);
     int written = 1;
     if (deg > 0) {
-        st3(out + 3, (-kC1 * y) * g);
-        st3(out + 6, (kC1 * z) * g);
-        st3(out + 9, (-kC1 * x) * g);
         dx = -kC1 * ld3(sh + 9);
         dy = -kC1 * ld3(sh + 3);
         dz = kC1 * ld3(sh + 6);
+        st3(out + 3, (-kC1 * y) * g);
+        st3(out + 6, (kC1 * z) * g);
+        st3(out + 9, (-kC1 * x) * g);
         written = 4;
         if (deg > 1) {
             const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            const f3 s4 = ld3(sh + 12), s5 = ld3(sh + 15), s6 = ld3(sh + 18), s7 = ld3(sh + 21), s8 = ld3(sh + 24);
             st3(out + 12, (kC2[0] * xy) * g);
             st3(out + 15, (kC2[1] * yz) * g);
             st3(out + 18, (kC2[2] * (2.f * zz - xx - yy)) * g);
             st3(out + 21, (kC2[3] * xz) * g);
             st3(out + 24, (kC2[4] * (xx - yy)) * g);
-            const f3 s4 = ld3(sh + 12), s5 = ld3(sh + 15), s6 = ld3(sh + 18), s7 = ld3(sh + 21), s8 = ld3(sh + 24);
             dx = dx + (kC2[0] * y * s4 + kC2[2] * 2.f * -x * s6 + kC2[3] * z * s7 + kC2[4] * 2.f * x * s8);
             dy = dy + (kC2[0] * x * s4 + kC2[1] * z * s5 + kC2[2] * 2.f * -y * s6 + kC2[4] * 2.f * -y * s8);
             dz = dz + (kC2[1] * y * s5 + kC2[2] * 2.f * 2.f * z * s6 + kC2[3] * x * s7);
             written = 9;
             if (deg > 2) {
+                const f3 s9 = ld3(sh + 27), s10 = ld3(sh + 30), s11 = ld3(sh + 33), s12 = ld3(sh + 36), s13 = ld3(sh + 39), s14 = ld3(sh + 42),
+                         s15 = ld3(sh + 45);
                 st3(out + 27, (kC3[0] * y * (3.f * xx - yy)) * g);
                 st3(out + 30, (kC3[1] * xy * z) * g);
                 st3(out + 33, (kC3[2] * y * (4.f * zz - xx - yy)) * g);
@@ -310,8 +314,6 @@ __device__ __forceinline__ f3 sh_colour_bwd(int deg, int M, const float *sh, f3 
                 st3(out + 39, (kC3[4] * x * (4.f * zz - xx - yy)) * g);
                 st3(out + 42, (kC3[5] * z * (xx - yy)) * g);
                 st3(out + 45, (kC3[6] * x * (xx - 3.f * yy)) * g);
-                const f3 s9 = ld3(sh + 27), s10 = ld3(sh + 30), s11 = ld3(sh + 33), s12 = ld3(sh + 36), s13 = ld3(sh + 39), s14 = ld3(sh + 42),
-                         s15 = ld3(sh + 45);
                 dx = dx + (kC3[0] * s9 * 3.f * 2.f * xy + kC3[1] * s10 * yz + kC3[2] * s11 * -2.f * xy + kC3[3] * s12 * -3.f * 2.f * xz +
                            kC3[4] * s13 * (-3.f * xx + 4.f * zz - yy) + kC3[5] * s14 * 2.f * xz + kC3[6] * s15 * 3.f * (xx - yy));
                 dy = dy + (kC3[0] * s9 * 3.f * (xx - yy) + kC3[1] * s10 * xz + kC3[2] * s11 * (-3.f * yy + 4.f * zz - xx) +
@@ -341,7 +343,7 @@ k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool ri
     const int row0 = idx - lane;                       // first triangle of this warp
     const int nrows = min(32, P - row0);               // <= 0: the whole warp is past the end
     const int q = (3 * M) / 4, rs4 = q + 1;            // float4 per row / tile row stride
-    float *tile_in = s_rows + (size_t)(2 * warp) * 32 * rs4 * 4, *tile_out = tile_in + 32 * rs4 * 4;
+    float *tile_in = s_rows + (size_t)warp * 32 * rs4 * 4, *tile_out = tile_in;  // one tile: SH rows in, their gradients out, in place
     const float *sh_row = shs + (size_t)idx * M * 3;
     float *gsh_row = dL_dshs + (size_t)idx * M * 3;
     if (TILED) {
@@ -470,8 +472,9 @@ int ts2d_launch_preprocess_bwd(const ts2d_camera *cam, const ts2d_geometry *g, c
         cam->projmatrix, cam->campos, g->vertex, g->shs, radii, gs.clamp, (const float4 *)gacc, ts2d_use_fast(g, f), gs.rec0, out->dL_dvertex, \
         out->dL_dcenter2D, out->dL_dshs, out->dL_dfeature, out->dL_dopacity
     if (tiled) {
-        const size_t smem = (size_t)(TS2D_BLOCK / 32) * 2 * 32 * ((3 * g->M) / 4 + 1) * 16;
+        const size_t smem = (size_t)(TS2D_BLOCK / 32) * 32 * ((3 * g->M) / 4 + 1) * 16;
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess_bwd<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         k_preprocess_bwd<true><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K9_ARGS);
     } else {
         k_preprocess_bwd<false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(TS2D_K9_ARGS);

@@ -57,8 +57,11 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
 {
     const int k = lane & 7, quarter = lane >> 3;
     __syncwarp();
-    float s_c0 = 0.f, s_c1 = 0.f, s_c2 = 0.f, s_n0 = 0.f, s_n1 = 0.f, s_n2 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
-    float u10 = 0.f, u1x = 0.f, u1y = 0.f, u20 = 0.f, u2x = 0.f, u2y = 0.f, s_op = 0.f;
+    // sums that share their multiplier ride in pairs on the packed pipe: {c0, c1}, {n0, n1}, {u1, u2} and their x-moments;
+    // the y-moments need no loop term at all: the lane's 8 pixels share one row, M_y = dy * S
+    v2 s_c01 = bc(0.f), s_n01 = bc(0.f), U0 = bc(0.f), Ux = bc(0.f);
+    float s_c2 = 0.f, s_n2 = 0.f, m0 = 0.f, m1 = 0.f, s_op = 0.f;
+    const float dyp = sub_y0 + (float)quarter;
     uint32_t id = 0;
     float vd1 = 0.f, vd2 = 0.f, vd3 = 0.f;
     if (k < filled) {
@@ -74,35 +77,29 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             // pixel p = quarter * 8 + i (lane index of phase 1) inside the sub-tile: x = p & 7 = i, y = p >> 3 = quarter
-            const float dxp = sub_x0 + (float)i;
-            const float dyp = sub_y0 + (float)quarter;
+            const float dxp = (float)i;  // x offset inside the sub-tile (an immediate); sub_x0 is added once after the loop
             const float c = lds32f(row + 4 * i), w1 = lds32f(row + 4 * (32 + i)), Dp = lds32f(row + 4 * (64 + i));
             const float4 f0 = lds128(frow + 32 * i);
-            s_c0 = fmaf(c, f0.x, s_c0);
-            s_c1 = fmaf(c, f0.y, s_c1);
+            s_c01 = fma2(bc(c), mk2v(f0.x, f0.y), s_c01);
             s_c2 = fmaf(c, f0.z, s_c2);
             s_op += w1;
             const uint32_t sel = __float_as_uint(Dp) & 3u;       // arg-min barycentric (1, 2, 3) packed in the two LSBs
-            const float u1 = sel == 1u ? Dp : (sel == 3u ? -Dp : 0.0f);
-            const float u2 = sel == 2u ? Dp : (sel == 3u ? -Dp : 0.0f);
+            const v2 u = mk2v(sel == 1u ? Dp : (sel == 3u ? -Dp : 0.0f), sel == 2u ? Dp : (sel == 3u ? -Dp : 0.0f));
             if (geo) {
                 const float4 f1 = lds128(frow + 32 * i + 16);
                 const float cg = c * f0.w;                       // contrib * gd
-                s_n0 = fmaf(c, f1.x, s_n0);
-                s_n1 = fmaf(c, f1.y, s_n1);
+                s_n01 = fma2(bc(c), mk2v(f1.x, f1.y), s_n01);
                 s_n2 = fmaf(c, f1.z, s_n2);
                 m0 += cg;
                 m1 = fmaf(cg, dxp, m1);
-                m2 = fmaf(cg, dyp, m2);
             }
-            u10 += u1;
-            u1x = fmaf(u1, dxp, u1x);
-            u1y = fmaf(u1, dyp, u1y);
-            u20 += u2;
-            u2x = fmaf(u2, dxp, u2x);
-            u2y = fmaf(u2, dyp, u2y);
+            U0 = add2(U0, u);
+            Ux = fma2(u, bc(dxp), Ux);
         }
     }
+    m1 = fmaf(sub_x0, m0, m1);
+    float s_c0 = s_c01.a, s_c1 = s_c01.b, s_n0 = s_n01.a, s_n1 = s_n01.b, m2 = dyp * m0;
+    float u10 = U0.a, u20 = U0.b, u1x = fmaf(sub_x0, U0.a, Ux.a), u2x = fmaf(sub_x0, U0.b, Ux.b), u1y = dyp * U0.a, u2y = dyp * U0.b;
 #define XQ(v) v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16)
     XQ(s_c0); XQ(s_c1); XQ(s_c2); XQ(s_op); XQ(u10); XQ(u1x); XQ(u1y); XQ(u20); XQ(u2x); XQ(u2y);
     if (geo) { XQ(s_n0); XQ(s_n1); XQ(s_n2); XQ(m0); XQ(m1); XQ(m2); }
@@ -174,6 +171,10 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
         gp0 = dL_dout_feature[pix];
         if (C > 1) { acc1 = background[1]; gp1 = dL_dout_feature[HW + pix]; }
         if (C > 2) { acc2 = background[2]; gp2 = dL_dout_feature[2 * HW + pix]; }
+    }
+    v2 acc01 = mk2v(acc0, acc1);       // running colour behind the current entry, channels {0, 1}
+    const v2 gp01 = mk2v(gp0, gp1);
+    if (inside) {
         if (RICH) {
             gn0 = dL_dout_normal[pix];
             gn1 = dL_dout_normal[HW + pix];
@@ -256,11 +257,11 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                     const float om = 1.0f - f.alpha;
                     T = T * rcp_approx(om);
                     w_c = f.alpha * T;
-                    float dL_dcontrib = gp0 * (col.x - acc0);
-                    dL_dcontrib = fmaf(gp1, col.y - acc1, dL_dcontrib);
-                    dL_dcontrib = fmaf(gp2, col.z - acc2, dL_dcontrib);
-                    acc0 = fmaf(f.alpha, col.x, om * acc0);
-                    acc1 = fmaf(f.alpha, col.y, om * acc1);
+                    // channels 0 and 1 ride in one packed instruction each
+                    const v2 col01 = mk2v(col.x, col.y);
+                    const v2 t01 = mul2(gp01, sub2(col01, acc01));
+                    float dL_dcontrib = fmaf(gp2, col.z - acc2, t01.a + t01.b);
+                    acc01 = fma2(bc(f.alpha), col01, mul2(bc(om), acc01));
                     acc2 = fmaf(f.alpha, col.z, om * acc2);
                     if (geo) {
                         const float4 q0 = lds128(ea + 48);

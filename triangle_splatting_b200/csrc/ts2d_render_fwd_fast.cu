@@ -106,7 +106,8 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
 
     const uint2 range = ranges[tile];
     float T = 1.0f, Terr = 0.0f;  // Terr: bound on |T - (the reference's T)|
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accd = 0.f, accn0 = 0.f, accn1 = 0.f, accn2 = 0.f;
+    v2 acc01 = bc(0.f), accn01 = bc(0.f);  // {channel 0, channel 1} and {n.x, n.y}: one FFMA2 each per blend
+    float acc2 = 0.f, accd = 0.f, accn2 = 0.f;
     uint32_t last = range.y - range.x;  // n_contrib if the pixel never saturates
     bool done = !inside;
 
@@ -183,14 +184,12 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                 if (hit) {
                     contrib = f.alpha * T;
                     const float4 col = lds128(ea + 32);
-                    acc0 = fmaf(contrib, col.x, acc0);
-                    acc1 = fmaf(contrib, col.y, acc1);
+                    acc01 = fma2(bc(contrib), mk2v(col.x, col.y), acc01);
                     acc2 = fmaf(contrib, col.z, acc2);
                     if constexpr (RICH) {
                         const float4 q0 = lds128(ea + 48);
                         const float2 q1 = lds64(ea + 64);
-                        accn0 = fmaf(contrib, q0.x, accn0);
-                        accn1 = fmaf(contrib, q0.y, accn1);
+                        accn01 = fma2(bc(contrib), mk2v(q0.x, q0.y), accn01);
                         accn2 = fmaf(contrib, q0.z, accn2);
                         accd = fmaf(contrib, fmaf(f.a3, q1.y, fmaf(q0.w, f.a1, q1.x * f.a2)), accd);
                     }
@@ -239,13 +238,13 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
         const size_t HW = (size_t)H * W;
         final_T[pix] = T;
         n_contrib[pix] = last;
-        out_feature[pix] = fmaf(T, bg0, acc0);
-        if (C > 1) out_feature[HW + pix] = fmaf(T, bg1, acc1);
+        out_feature[pix] = fmaf(T, bg0, acc01.a);
+        if (C > 1) out_feature[HW + pix] = fmaf(T, bg1, acc01.b);
         if (C > 2) out_feature[2 * HW + pix] = fmaf(T, bg2, acc2);
         if constexpr (RICH) {
             out_depth[pix] = fmaf(T, bg_depth, accd);
-            out_normal[pix] = accn0;
-            out_normal[HW + pix] = accn1;
+            out_normal[pix] = accn01.a;
+            out_normal[HW + pix] = accn01.b;
             out_normal[2 * HW + pix] = accn2;
         }
     }
