@@ -83,8 +83,11 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
             s_c01 = fma2(bc(c), mk2v(f0.x, f0.y), s_c01);
             s_c2 = fmaf(c, f0.z, s_c2);
             s_op += w1;
-            const uint32_t sel = __float_as_uint(Dp) & 3u;       // arg-min barycentric (1, 2, 3) packed in the two LSBs
-            const v2 u = mk2v(sel == 1u ? Dp : (sel == 3u ? -Dp : 0.0f), sel == 2u ? Dp : (sel == 3u ? -Dp : 0.0f));
+            // arg-min barycentric (1, 2, 3) packed in the two LSBs: D goes to a1 (bit 0) and / or a2 (bit 1), negated when to a3 (both)
+            const uint32_t db = __float_as_uint(Dp);
+            const bool to1 = (db & 1u) != 0u, to2 = (db & 2u) != 0u;
+            const float Ds = (to1 && to2) ? -Dp : Dp;
+            const v2 u = mk2v(to1 ? Ds : 0.0f, to2 ? Ds : 0.0f);
             if (geo) {
                 const float4 f1 = lds128(frow + 32 * i + 16);
                 const float cg = c * f0.w;                       // contrib * gd
