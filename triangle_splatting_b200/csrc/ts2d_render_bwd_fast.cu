@@ -51,10 +51,14 @@ __device__ __forceinline__ void red_add4(float *addr, float a, float b, float c,
 // phase 2 (out of line: one copy keeps the kernel inside the instruction cache and out of the walk loop's register budget).
 // lane (k, quarter) sums panel row k over pixels quarter*8 .. quarter*8+7, then flushes the triangle.
 // wb / ib / fb: shared-space addresses of the warp's W panel, row ids and F table.
+// GEO: some pixel of the sub-tile has a non-zero normal / depth upstream gradient (a template parameter, so that the common
+// colour-only case does not even issue the geometry terms as predicated-off instructions).
+template <bool GEO>
 static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, uint32_t fb, const float4 *__restrict__ rec1,
                                                     float *__restrict__ gacc, float ox, float oy,
-                                                    float sub_x0, float sub_y0, bool geo, int filled, int lane)
+                                                    float sub_x0, float sub_y0, int filled, int lane)
 {
+    constexpr bool geo = GEO;
     const int k = lane & 7, quarter = lane >> 3;
     __syncwarp();
     // sums that share their multiplier ride in pairs on the packed pipe: {c0, c1}, {n0, n1}, {u1, u2} and their x-moments;
@@ -196,7 +200,8 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
     int prow = 0;  // next free panel row (rows persist across rounds: phase 2 only needs the triangle id)
     const float sub_x0 = (float)((warp & 1) * 8), sub_y0 = (float)((warp >> 1) * 4);
     auto flush_panel = [&](int filled) {
-        bwd_flush_panel(sb + L::W, sb + L::INFO, sb + L::F, rec1, gacc, ox, oy, sub_x0, sub_y0, geo, filled, lane);
+        if (geo) bwd_flush_panel<true>(sb + L::W, sb + L::INFO, sb + L::F, rec1, gacc, ox, oy, sub_x0, sub_y0, filled, lane);
+        else bwd_flush_panel<false>(sb + L::W, sb + L::INFO, sb + L::F, rec1, gacc, ox, oy, sub_x0, sub_y0, filled, lane);
     };
 
     // Back to front: `rem` list positions [range.x, range.x + rem) are still to be scanned; a chunk is the 32 positions
