@@ -416,8 +416,20 @@ def main():
 
     # ------------------------------------------------------------------------------------ our arm
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # rank 0 must print exactly one JSON line on stdout: NCCL writes its version banner to fd 1 at communicator creation
+        # whenever NCCL_DEBUG >= VERSION, so fd 1 points at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
         from triangle_splatting_b200 import distributed as tsd
 
         tsd.enable_tile_sharding()

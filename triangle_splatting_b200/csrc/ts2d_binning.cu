@@ -38,14 +38,16 @@ __device__ __forceinline__ uint32_t instance_key(uint32_t tile, int gx, uint32_t
     return (tile << TS2D_MASK_BITS) | subtile_mask(r0, r1, r1.z, (float)(tx * TS2D_TILE), (float)(ty * TS2D_TILE), gk);
 }
 
-// Unsharded emission, one warp per 32 consecutive depth ranks: the warp's instances [start of rank r0, end of rank r0+31) are
+// Emission, one warp per 32 consecutive depth ranks: the warp's instances [start of rank r0, end of rank r0+31) are
 // dealt to lanes round-robin, each lane finding its (triangle, k-th tile of the rect, row-major) by a 5-step search over the
 // 32 scan values held in the warp.  Same output as rasterizer.cu:63-74 in depth order, with coalesced stores and no
-// divergence on the rect size.
-template <bool MASKS>
+// divergence on the rect size.  SHARDED: only the tiles this rank owns (tile % world == rank) count and are written; the
+// k-th owned tile is found row by row (each row holds every world-th tile starting at a closed-form first column).
+template <bool MASKS, bool SHARDED>
 __global__ void __launch_bounds__(TS2D_BLOCK)
-k_emit_warp(int P, int gx, float gamma, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles, const ushort4 *__restrict__ rect,
-            const uint32_t *__restrict__ offs, const float4 *__restrict__ rec0, uint32_t *__restrict__ tkey, uint32_t *__restrict__ tval)
+k_emit_warp(int P, int gx, float gamma, int shard_rank, int shard_world, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
+            const ushort4 *__restrict__ rect, const uint32_t *__restrict__ offs, const float4 *__restrict__ rec0, uint32_t *__restrict__ tkey,
+            uint32_t *__restrict__ tval)
 {
     const int lane = threadIdx.x & 31;
     const int r = (blockIdx.x * blockDim.x + threadIdx.x);
@@ -77,37 +79,31 @@ k_emit_warp(int P, int gx, float gamma, const uint32_t *__restrict__ order, cons
         const uint32_t t_start = __shfl_sync(0xffffffffu, start, t), t_id = __shfl_sync(0xffffffffu, id, t);
         const uint32_t lo = __shfl_sync(0xffffffffu, rc_lo, t), hi = __shfl_sync(0xffffffffu, rc_hi, t);
         if (i < w_end) {
-            const uint32_t k = i - t_start, w = (hi & 0xffffu) - (lo & 0xffffu);
-            const uint32_t dy = k / w, dx = k - dy * w;
-            const uint32_t tile = ((lo >> 16) + dy) * (uint32_t)gx + (lo & 0xffffu) + dx;
+            uint32_t k = i - t_start;
+            const uint32_t x_lo = lo & 0xffffu, x_hi = hi & 0xffffu;
+            uint32_t tile;
+            if (!SHARDED) {
+                const uint32_t w = x_hi - x_lo;
+                const uint32_t dy = k / w, dx = k - dy * w;
+                tile = ((lo >> 16) + dy) * (uint32_t)gx + x_lo + dx;
+            } else {
+                const uint32_t world = (uint32_t)shard_world, rank = (uint32_t)shard_rank;
+                uint32_t y = lo >> 16;
+                for (;; y++) {  // the instance exists, so the loop ends inside the rect
+                    const uint32_t first = y * (uint32_t)gx + x_lo;                   // first tile of the row
+                    const uint32_t x0 = x_lo + (rank + world - first % world) % world;  // first owned column
+                    const uint32_t cnt = x0 < x_hi ? (x_hi - x0 + world - 1) / world : 0u;
+                    if (k < cnt) {
+                        tile = y * (uint32_t)gx + x0 + k * world;
+                        break;
+                    }
+                    k -= cnt;
+                }
+            }
             tkey[i] = instance_key<MASKS>(tile, gx, t_id, rec0, gk);
             tval[i] = t_id;
         }
     }
-}
-
-// Tile-sharded emission (one thread per depth rank): only the tiles this rank owns.
-template <bool MASKS>
-__global__ void __launch_bounds__(TS2D_BLOCK)
-k_emit_sharded(int P, int gx, float gamma, int shard_rank, int shard_world, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
-               const ushort4 *__restrict__ rect, const uint32_t *__restrict__ offs, const float4 *__restrict__ rec0, uint32_t *__restrict__ tkey,
-               uint32_t *__restrict__ tval)
-{
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= P) return;
-    const uint32_t id = order[r];
-    if (tiles[id] == 0) return;
-    const GammaK gk = make_gamma(gamma);
-    uint32_t off = (r == 0) ? 0u : offs[r - 1];
-    const ushort4 rc = rect[id];
-    for (uint32_t y = rc.y; y < rc.w; y++)
-        for (uint32_t x = rc.x; x < rc.z; x++) {
-            const uint32_t t = y * (uint32_t)gx + x;
-            if ((t % (uint32_t)shard_world) != (uint32_t)shard_rank) continue;
-            tkey[off] = instance_key<MASKS>(t, gx, id, rec0, gk);
-            tval[off] = id;
-            off++;
-        }
 }
 
 // rasterizer.cu:79-99 on 32-bit tile keys.
@@ -200,19 +196,15 @@ int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts
     if (R == 0) return 0;
     const bool masks = ts2d_use_fast(g, f);
     const int blocks = (P + TS2D_BLOCK - 1) / TS2D_BLOCK;
+#define TS2D_EMIT_ARGS P, gx, g->gamma, f->shard_rank, f->shard_world, gs.ids2, gs.tiles, gs.rect, gs.offs, gs.rec0, bs.tkey[0], bs.tval[0]
     if (f->shard_world > 1) {
-        if (masks)
-            k_emit_sharded<true><<<blocks, TS2D_BLOCK, 0, s>>>(P, gx, g->gamma, f->shard_rank, f->shard_world, gs.ids2, gs.tiles, gs.rect, gs.offs,
-                                                                gs.rec0, bs.tkey[0], bs.tval[0]);
-        else
-            k_emit_sharded<false><<<blocks, TS2D_BLOCK, 0, s>>>(P, gx, g->gamma, f->shard_rank, f->shard_world, gs.ids2, gs.tiles, gs.rect, gs.offs,
-                                                                 gs.rec0, bs.tkey[0], bs.tval[0]);
+        if (masks) k_emit_warp<true, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
+        else k_emit_warp<false, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
     } else {
-        if (masks)
-            k_emit_warp<true><<<blocks, TS2D_BLOCK, 0, s>>>(P, gx, g->gamma, gs.ids2, gs.tiles, gs.rect, gs.offs, gs.rec0, bs.tkey[0], bs.tval[0]);
-        else
-            k_emit_warp<false><<<blocks, TS2D_BLOCK, 0, s>>>(P, gx, g->gamma, gs.ids2, gs.tiles, gs.rect, gs.offs, gs.rec0, bs.tkey[0], bs.tval[0]);
+        if (masks) k_emit_warp<true, false><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
+        else k_emit_warp<false, false><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
     }
+#undef TS2D_EMIT_ARGS
     TS2D_CUDA_TRY(cudaGetLastError());
     size_t tb = bs.cub_temp_bytes;
     TS2D_CUDA_TRY(cub::DeviceRadixSort::SortPairs(bs.cub_temp, tb, (const uint32_t *)bs.tkey[0], bs.tkey[1], (const uint32_t *)bs.tval[0],

@@ -202,9 +202,13 @@ k_preprocess(int W, int H, int P, int D, int M, int C, bool rich, bool use_shs, 
             if (shard_world == 1) {
                 out_tiles = (rx1 - rx0) * (ry1 - ry0);
             } else {
-                uint32_t n = 0;  // tiles of the rect this rank owns (tile_id % world == rank)
-                for (uint32_t y = ry0; y < ry1; y++)
-                    for (uint32_t x = rx0; x < rx1; x++) n += ((y * (uint32_t)gx + x) % (uint32_t)shard_world == (uint32_t)shard_rank);
+                // tiles of the rect this rank owns (tile_id % world == rank): per row, every world-th tile from a closed-form first column
+                const uint32_t world = (uint32_t)shard_world, rank = (uint32_t)shard_rank;
+                uint32_t n = 0;
+                for (uint32_t y = ry0; y < ry1; y++) {
+                    const uint32_t x0 = rx0 + (rank + world - (y * (uint32_t)gx + rx0) % world) % world;
+                    n += x0 < rx1 ? (rx1 - x0 + world - 1) / world : 0u;
+                }
                 out_tiles = n;
             }
             out_radius = max(ceilf((vmax.x - vmin.x) * 0.5f), ceilf((vmax.y - vmin.y) * 0.5f));
