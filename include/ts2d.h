@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define TS2D_ABI_VERSION 1
+#define TS2D_ABI_VERSION 2
 #define TS2D_TILE 16          /* R2D/src/config.h:4-5  BLOCK_X = BLOCK_Y = 16 */
 #define TS2D_MAX_CHANNELS 3   /* R2D/src/config.h:3 */
 
@@ -64,7 +64,8 @@ enum {
     TS2D_E_STATE_SIZE = -8,    /* state blob smaller than ts2d_*_state_bytes() */
     TS2D_E_SH_DEGREE = -9,     /* (sh_degree+1)^2 > M or sh_degree > 3 */
     TS2D_E_SHARD = -10,        /* shard_rank/shard_world invalid */
-    TS2D_E_SIZE = -11          /* image or primitive count out of range */
+    TS2D_E_SIZE = -11,         /* image or primitive count out of range */
+    TS2D_E_PRIMITIVE = -12     /* flags.primitive is neither TS2D_PRIMITIVE_2D nor TS2D_PRIMITIVE_3D */
 };
 
 /* R2D/src/param_struct.h:127-137 (CameraInfo).  Matrices are the 16 floats of the (contiguous)
@@ -103,7 +104,17 @@ typedef struct ts2d_flags {
     int32_t shard_world;       /* 1 = all tiles */
     int32_t exact;             /* 1: per-pair arithmetic mirrors the reference op-for-op (IEEE div, powf,
                                   expf); 0: fast path with exact re-evaluation inside the decision bands */
+    int32_t primitive;         /* TS2D_PRIMITIVE_2D: screen-space triangles (R2D, the north-star path);
+                                  TS2D_PRIMITIVE_3D: ray / triangle-plane intersection in view space, the
+                                  reference's second rasterizer package R3D = submodules/diff-triangle-rasterization-3D
+                                  (same pybind API: R3D/ext.cpp:4-9, R3D/src/extension_interface.h:7-62; kernels
+                                  R3D/src/forward.cu:61-306, R3D/src/backward.cu:144-454).  Same entry points, same
+                                  state blobs, same outputs; dL_dcenter2D is then the view-space xy of the summed
+                                  vertex gradients (R3D/src/backward.cu:211-213). */
 } ts2d_flags;
+
+#define TS2D_PRIMITIVE_2D 0
+#define TS2D_PRIMITIVE_3D 1
 
 /* R2D/src/param_struct.h:157-169 (ForwardOutput), minus the three state tensors. */
 typedef struct ts2d_forward_out {
@@ -177,6 +188,11 @@ int ts2d_export_geometry(const void *geometry_state, int32_t P,
                          float *v2d /*[P][3][2]*/, float *area2 /*[P]*/, float *normal_view /*[P][3]*/, float *v_depth /*[P][3]*/,
                          float *depth /*[P]*/, float *rgb /*[P][3]*/, uint8_t *clamped /*[P][3]*/, uint32_t *tiles_touched /*[P]*/,
                          uint32_t *rect_min /*[P][2]*/, uint32_t *rect_max /*[P][2]*/, void *stream);
+/* 3D primitive (R3D/src/param_struct.h:44-75): view-space vertices, UN-normalised plane normal. */
+int ts2d_export_geometry3d(const void *geometry_state, int32_t P,
+                           float *v_view /*[P][3][3]*/, float *normal_view /*[P][3]*/, float *depth /*[P]*/, float *rgb /*[P][3]*/,
+                           uint8_t *clamped /*[P][3]*/, uint32_t *tiles_touched /*[P]*/, uint32_t *rect_min /*[P][2]*/,
+                           uint32_t *rect_max /*[P][2]*/, void *stream);
 int ts2d_export_binning(const void *geometry_state, const void *binning_state, const void *image_state, int32_t P, int64_t num_rendered,
                         int32_t width, int32_t height, uint64_t *keys_sorted /*[R]*/, uint32_t *point_list /*[R]*/,
                         uint32_t *ranges /*[tiles][2]*/, void *stream);

@@ -28,21 +28,27 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 OUT = HERE / "_ref"
-REF = Path(os.environ.get("TS2D_REFERENCE_ROOT", "/root/reference")) / "submodules" / "diff-triangle-rasterization-2D"
+REF_ROOT = Path(os.environ.get("TS2D_REFERENCE_ROOT", "/root/reference")) / "submodules"
 SOURCES = ["src/rasterizer.cu", "src/forward.cu", "src/backward.cu", "src/extension_interface.cu", "ext.cpp"]
-MODNAME = "ts2d_ref_C"
+# which -> (reference directory, pybind module name).  "3D" is the reference's second per-pixel primitive
+# (submodules/diff-triangle-rasterization-3D: same host code and API, ray/plane barycentrics in view space).
+VARIANTS = {"2D": ("diff-triangle-rasterization-2D", "ts2d_ref_C"), "3D": ("diff-triangle-rasterization-3D", "ts3d_ref_C")}
+REF = REF_ROOT / VARIANTS["2D"][0]
+MODNAME = VARIANTS["2D"][1]
 
 
-def so_path() -> Path:
-    return OUT / f"{MODNAME}{sysconfig.get_config_var('EXT_SUFFIX')}"
+def so_path(which: str = "2D") -> Path:
+    return OUT / f"{VARIANTS[which][1]}{sysconfig.get_config_var('EXT_SUFFIX')}"
 
 
-def available() -> bool:
-    return so_path().exists()
+def available(which: str = "2D") -> bool:
+    return so_path(which).exists()
 
 
-def build(force: bool = False, verbose: bool = True) -> Path | None:
-    target = so_path()
+def build(force: bool = False, verbose: bool = True, which: str = "2D") -> Path | None:
+    REF = REF_ROOT / VARIANTS[which][0]  # noqa: N806
+    MODNAME = VARIANTS[which][1]  # noqa: N806
+    target = so_path(which)
     if not REF.exists():
         if verbose:
             print(f"[oracle/build_ref] {REF} not present; using prebuilt {target if target.exists() else '(none)'}")
@@ -57,7 +63,7 @@ def build(force: bool = False, verbose: bool = True) -> Path | None:
     from torch.utils import cpp_extension as ce
 
     OUT.mkdir(parents=True, exist_ok=True)
-    objdir = OUT / "obj"
+    objdir = OUT / ("obj" if which == "2D" else "obj" + which)
     objdir.mkdir(exist_ok=True)
     inc = [f"-I{p}" for p in ce.include_paths("cuda")] + [f"-I{sysconfig.get_paths()['include']}"]
     common = [
@@ -100,9 +106,10 @@ def build(force: bool = False, verbose: bool = True) -> Path | None:
     return target
 
 
-def load():
+def load(which: str = "2D"):
     """Import the reference pybind module (needs torch imported first). Returns module or None."""
-    p = so_path()
+    MODNAME = VARIANTS[which][1]  # noqa: N806
+    p = so_path(which)
     if not p.exists():
         return None
     import importlib.util
@@ -115,5 +122,5 @@ def load():
 
 
 if __name__ == "__main__":
-    r = build(force="--force" in sys.argv)
-    print(r)
+    for w in ("2D", "3D"):
+        print(build(force="--force" in sys.argv, which=w))

@@ -63,7 +63,9 @@ class Oracle:
     # ------------------------------------------------------------------ forward
     def forward(self, *, image_width, image_height, tanfovx, tanfovy, viewmatrix, projmatrix, campos, sh_degree, gamma,
                 background_depth, background, vertex, shs, feature, opacity, back_culling=False, rich_info=False,
-                scale_modifier=1.0, debug=False, stages="all", tile_step=1, tile_offset=0) -> dict:
+                scale_modifier=1.0, debug=False, stages="all", tile_step=1, tile_offset=0, primitive="2D") -> dict:
+        """primitive="3D": the reference's diff_triangle_rasterization_3D package (ts3d_oracle_* in ts2d_oracle.c)."""
+        assert primitive in ("2D", "3D")
         W, H = int(image_width), int(image_height)
         vertex = self._r(vertex)
         P = vertex.shape[0]
@@ -79,7 +81,8 @@ class Oracle:
         real = self.real
         st = dict(W=W, H=H, P=P, C=C, M=M, D=int(sh_degree), use_shs=bool(use_shs), rich_info=bool(rich_info), gamma=float(gamma),
                   tanfovx=float(tanfovx), tanfovy=float(tanfovy), viewmatrix=vm, projmatrix=pm, campos=cp, vertex=vertex, shs=shs_a,
-                  opacity=opacity, background=bg, background_depth=float(background_depth), back_culling=bool(back_culling))
+                  opacity=opacity, background=bg, background_depth=float(background_depth), back_culling=bool(back_culling),
+                  primitive=primitive)
         st["radii"] = np.zeros(P, np.int32)
         st["v2d"] = np.zeros((P, 3, 2), real)
         st["area2"] = np.zeros(P, real)
@@ -92,7 +95,14 @@ class Oracle:
         st["rect_min"] = np.zeros((P, 2), np.uint32)
         st["rect_max"] = np.zeros((P, 2), np.uint32)
         cr = self.creal
-        if P > 0:
+        if primitive == "3D":
+            st["v_view"] = np.zeros((P, 3, 3), real)
+            if P > 0:
+                self.lib.ts3d_oracle_preprocess(
+                    W, H, P, int(sh_degree), M, int(bool(use_shs)), int(bool(back_culling)), _p(vm), _p(pm), _p(cp), _p(vertex), _p(shs_a),
+                    _p(st["radii"]), _p(st["v_view"]), _p(st["normal_view"]), _p(st["depth"]), _p(st["rgb"]), _p(st["clamped"]),
+                    _p(st["tiles_touched"]), _p(st["rect_min"]), _p(st["rect_max"]))
+        elif P > 0:
             self.lib.ts2d_oracle_preprocess(
                 W, H, P, int(sh_degree), M, int(bool(rich_info)), int(bool(use_shs)), int(bool(back_culling)), cr(tanfovx), cr(tanfovy),
                 _p(vm), _p(pm), _p(cp), _p(vertex), _p(shs_a), _p(st["radii"]), _p(st["v2d"]), _p(st["area2"]), _p(st["normal_view"]),
@@ -125,6 +135,14 @@ class Oracle:
         st["contrib_max"] = np.zeros(P, real)
         if P == 0:  # extension_interface.cu:130: zero outputs
             return st
+        st["tile_step"], st["tile_offset"] = int(tile_step), int(tile_offset)
+        if primitive == "3D":
+            self.lib.ts3d_oracle_render(
+                W, H, C, cr(gamma), int(bool(rich_info)), cr(tanfovx), cr(tanfovy), _p(st["ranges"]), _p(st["point_list"]), _p(st["v_view"]),
+                _p(st["normal_view"]), _p(np.ascontiguousarray(st["feature"])), _p(opacity), cr(background_depth), _p(bg), _p(st["final_T"]),
+                _p(st["n_contrib"]), _p(st["out_feature"]), _p(st["out_depth"]), _p(st["out_normal"]), _p(st["contrib_sum"]),
+                _p(st["contrib_max"]), P, int(tile_step), int(tile_offset))
+            return st
         self.lib.ts2d_oracle_render(
             W, H, C, cr(gamma), int(bool(rich_info)), _p(st["ranges"]), _p(st["point_list"]), _p(st["v2d"]), _p(st["area2"]),
             _p(st["normal_view"]), _p(st["v_depth"]), _p(np.ascontiguousarray(st["feature"])), _p(opacity), cr(background_depth), _p(bg),
@@ -151,6 +169,21 @@ class Oracle:
             out["dL_dopacity"] = np.zeros((P, 1), real)
             return out
         feat = np.ascontiguousarray(st["feature"])
+        if st.get("primitive", "2D") == "3D":
+            out["g_vview"] = np.zeros((P, 3, 3))
+            self.lib.ts3d_oracle_render_bwd(
+                W, H, C, cr(st["gamma"]), int(rich), cr(st["tanfovx"]), cr(st["tanfovy"]), _p(st["ranges"]), _p(st["point_list"]),
+                _p(st["v_view"]), _p(st["normal_view"]), _p(feat), _p(st["opacity"]), cr(st["background_depth"]), _p(st["background"]),
+                _p(st["final_T"]), _p(st["n_contrib"]), _p(g_img), _p(g_dep), _p(g_nrm), P, _p(out["g_vview"]), _p(out["g_normal"]),
+                _p(out["g_feature"]), _p(out["g_opacity"]), int(st.get("tile_step", 1)), int(st.get("tile_offset", 0)))
+            g_rgb = out["g_feature"] if st["use_shs"] else np.zeros((P, 3))
+            self.lib.ts3d_oracle_preprocess_bwd(
+                P, st["D"], M, int(st["use_shs"]), _p(st["viewmatrix"]), _p(st["campos"]), _p(st["vertex"]), _p(st["shs"]), _p(st["radii"]),
+                _p(st["clamped"]), _p(st["v_view"]), _p(out["g_vview"]), _p(out["g_normal"]), _p(np.ascontiguousarray(g_rgb)),
+                _p(out["dL_dvertex"]), _p(out["dL_dcenter2D"]), _p(out["dL_dshs"]))
+            out["dL_dfeature"] = out["g_feature"].astype(real)
+            out["dL_dopacity"] = out["g_opacity"].astype(real).reshape(P, 1)
+            return out
         self.lib.ts2d_oracle_render_bwd(
             W, H, C, cr(st["gamma"]), int(rich), _p(st["ranges"]), _p(st["point_list"]), _p(st["v2d"]), _p(st["area2"]), _p(st["normal_view"]),
             _p(st["v_depth"]), _p(feat), _p(st["opacity"]), cr(st["background_depth"]), _p(st["background"]), _p(st["final_T"]),

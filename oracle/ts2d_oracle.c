@@ -1,5 +1,6 @@
 /*
- * ts2d_oracle.c -- CPU restatement of the reference 2D triangle-splatting rasterizer.
+ * ts2d_oracle.c -- CPU restatement of the reference 2D triangle-splatting rasterizer (and, in its last section,
+ * of the reference's 3D-primitive package on the same pipeline).
  *
  * TEST INFRASTRUCTURE ONLY.  Nothing under triangle_splatting_b200/ may include, link or call
  * this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
@@ -540,6 +541,64 @@ int ts2d_oracle_render_bwd(int W, int H, int C, real gamma, int rich_info, const
     return 0;
 }
 
+/* computeRGBFromSHBackward (backward.cu:9-119; R3D/src/backward.cu:9-119 is byte-identical): writes dL/dsh of triangle i,
+ * returns dL/d(centre) through the view direction. */
+static v3 sh_backward(int D, int M, v3 center, v3 cam, const real *shs, int i, const uint8_t *clamped, const double *g_rgb, real *dL_dshs)
+{
+        const v3 dir_orig = v3_sub(center, cam);
+        const v3 dir = v3_div(dir_orig, v3_norm(dir_orig));
+        const real *s = shs + (size_t)i * M * 3;
+        real *o = dL_dshs + (size_t)i * M * 3;
+#define SH(k) v3_make(s[3 * (k)], s[3 * (k) + 1], s[3 * (k) + 2])
+#define OUT(k, w) do { o[3 * (k)] = (w) * g.x; o[3 * (k) + 1] = (w) * g.y; o[3 * (k) + 2] = (w) * g.z; } while (0)
+        v3 g = v3_make((real)g_rgb[3 * i], (real)g_rgb[3 * i + 1], (real)g_rgb[3 * i + 2]);
+        g.x *= clamped[3 * i] ? 0 : 1; g.y *= clamped[3 * i + 1] ? 0 : 1; g.z *= clamped[3 * i + 2] ? 0 : 1;
+        v3 dx = v3_make(0, 0, 0), dy = v3_make(0, 0, 0), dz = v3_make(0, 0, 0);
+        const real x = dir.x, y = dir.y, z = dir.z;
+        OUT(0, SH_C0);
+        if (D > 0) {
+            OUT(1, -SH_C1 * y); OUT(2, SH_C1 * z); OUT(3, -SH_C1 * x);
+            dx = v3_scale(SH(3), -SH_C1); dy = v3_scale(SH(1), -SH_C1); dz = v3_scale(SH(2), SH_C1);
+            if (D > 1) {
+                const real xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                OUT(4, SH_C2[0] * xy); OUT(5, SH_C2[1] * yz); OUT(6, SH_C2[2] * ((real)2.f * zz - xx - yy)); OUT(7, SH_C2[3] * xz); OUT(8, SH_C2[4] * (xx - yy));
+                dx = v3_add(dx, v3_add(v3_add(v3_add(v3_scale(SH(4), SH_C2[0] * y), v3_scale(SH(6), SH_C2[2] * (real)2.f * -x)), v3_scale(SH(7), SH_C2[3] * z)), v3_scale(SH(8), SH_C2[4] * (real)2.f * x)));
+                dy = v3_add(dy, v3_add(v3_add(v3_add(v3_scale(SH(4), SH_C2[0] * x), v3_scale(SH(5), SH_C2[1] * z)), v3_scale(SH(6), SH_C2[2] * (real)2.f * -y)), v3_scale(SH(8), SH_C2[4] * (real)2.f * -y)));
+                dz = v3_add(dz, v3_add(v3_add(v3_scale(SH(5), SH_C2[1] * y), v3_scale(SH(6), SH_C2[2] * (real)2.f * (real)2.f * z)), v3_scale(SH(7), SH_C2[3] * x)));
+                if (D > 2) {
+                    OUT(9, SH_C3[0] * y * ((real)3.f * xx - yy)); OUT(10, SH_C3[1] * xy * z); OUT(11, SH_C3[2] * y * ((real)4.f * zz - xx - yy));
+                    OUT(12, SH_C3[3] * z * ((real)2.f * zz - (real)3.f * xx - (real)3.f * yy)); OUT(13, SH_C3[4] * x * ((real)4.f * zz - xx - yy));
+                    OUT(14, SH_C3[5] * z * (xx - yy)); OUT(15, SH_C3[6] * x * (xx - (real)3.f * yy));
+                    v3 t = v3_scale(SH(9), SH_C3[0] * (real)3.f * (real)2.f * xy);
+                    t = v3_add(t, v3_scale(SH(10), SH_C3[1] * yz));
+                    t = v3_add(t, v3_scale(SH(11), SH_C3[2] * (real)-2.f * xy));
+                    t = v3_add(t, v3_scale(SH(12), SH_C3[3] * (real)-3.f * (real)2.f * xz));
+                    t = v3_add(t, v3_scale(SH(13), SH_C3[4] * ((real)-3.f * xx + (real)4.f * zz - yy)));
+                    t = v3_add(t, v3_scale(SH(14), SH_C3[5] * (real)2.f * xz));
+                    t = v3_add(t, v3_scale(SH(15), SH_C3[6] * (real)3.f * (xx - yy)));
+                    dx = v3_add(dx, t);
+                    t = v3_scale(SH(9), SH_C3[0] * (real)3.f * (xx - yy));
+                    t = v3_add(t, v3_scale(SH(10), SH_C3[1] * xz));
+                    t = v3_add(t, v3_scale(SH(11), SH_C3[2] * ((real)-3.f * yy + (real)4.f * zz - xx)));
+                    t = v3_add(t, v3_scale(SH(12), SH_C3[3] * (real)-3.f * (real)2.f * yz));
+                    t = v3_add(t, v3_scale(SH(13), SH_C3[4] * (real)-2.f * xy));
+                    t = v3_add(t, v3_scale(SH(14), SH_C3[5] * (real)-2.f * yz));
+                    t = v3_add(t, v3_scale(SH(15), SH_C3[6] * (real)-3.f * (real)2.f * xy));
+                    dy = v3_add(dy, t);
+                    t = v3_scale(SH(10), SH_C3[1] * xy);
+                    t = v3_add(t, v3_scale(SH(11), SH_C3[2] * (real)4.f * (real)2.f * yz));
+                    t = v3_add(t, v3_scale(SH(12), SH_C3[3] * (real)3.f * ((real)2.f * zz - xx - yy)));
+                    t = v3_add(t, v3_scale(SH(13), SH_C3[4] * (real)4.f * (real)2.f * xz));
+                    t = v3_add(t, v3_scale(SH(14), SH_C3[5] * (xx - yy)));
+                    dz = v3_add(dz, t);
+                }
+            }
+        }
+#undef SH
+#undef OUT
+        const v3 gdir = v3_make(v3_dot(g, dx), v3_dot(g, dy), v3_dot(g, dz));
+    return dnorm3(dir_orig, gdir);
+}
 /* ------------------------------------------- preprocess backward (backward.cu:9-263)
  * Inputs g_* are the per-triangle screen-space sums from ts2d_oracle_render_bwd (rounded to REAL
  * here, as the reference holds them in fp32).  g_rgb is dL_drgb (== dL_dfeature scratch in SH mode,
@@ -620,67 +679,337 @@ int ts2d_oracle_preprocess_bwd(int W, int H, int P, int D, int M, int use_shs, i
         gcenter = v3_add(gcenter, xform_vec43_T(gcv, viewmatrix));
         const v3 gr1 = xform_vec43_T(grv[0], viewmatrix), gr2 = xform_vec43_T(grv[1], viewmatrix), gr3 = xform_vec43_T(grv[2], viewmatrix);
 
-        if (use_shs) { /* computeRGBFromSHBackward, backward.cu:9-119 */
-            const v3 dir_orig = v3_sub(center, cam);
-            const v3 dir = v3_div(dir_orig, v3_norm(dir_orig));
-            const real *s = shs + (size_t)i * M * 3;
-            real *o = dL_dshs + (size_t)i * M * 3;
-#define SH(k) v3_make(s[3 * (k)], s[3 * (k) + 1], s[3 * (k) + 2])
-#define OUT(k, w) do { o[3 * (k)] = (w) * g.x; o[3 * (k) + 1] = (w) * g.y; o[3 * (k) + 2] = (w) * g.z; } while (0)
-            v3 g = v3_make((real)g_rgb[3 * i], (real)g_rgb[3 * i + 1], (real)g_rgb[3 * i + 2]);
-            g.x *= clamped[3 * i] ? 0 : 1; g.y *= clamped[3 * i + 1] ? 0 : 1; g.z *= clamped[3 * i + 2] ? 0 : 1;
-            v3 dx = v3_make(0, 0, 0), dy = v3_make(0, 0, 0), dz = v3_make(0, 0, 0);
-            const real x = dir.x, y = dir.y, z = dir.z;
-            OUT(0, SH_C0);
-            if (D > 0) {
-                OUT(1, -SH_C1 * y); OUT(2, SH_C1 * z); OUT(3, -SH_C1 * x);
-                dx = v3_scale(SH(3), -SH_C1); dy = v3_scale(SH(1), -SH_C1); dz = v3_scale(SH(2), SH_C1);
-                if (D > 1) {
-                    const real xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                    OUT(4, SH_C2[0] * xy); OUT(5, SH_C2[1] * yz); OUT(6, SH_C2[2] * ((real)2.f * zz - xx - yy)); OUT(7, SH_C2[3] * xz); OUT(8, SH_C2[4] * (xx - yy));
-                    dx = v3_add(dx, v3_add(v3_add(v3_add(v3_scale(SH(4), SH_C2[0] * y), v3_scale(SH(6), SH_C2[2] * (real)2.f * -x)), v3_scale(SH(7), SH_C2[3] * z)), v3_scale(SH(8), SH_C2[4] * (real)2.f * x)));
-                    dy = v3_add(dy, v3_add(v3_add(v3_add(v3_scale(SH(4), SH_C2[0] * x), v3_scale(SH(5), SH_C2[1] * z)), v3_scale(SH(6), SH_C2[2] * (real)2.f * -y)), v3_scale(SH(8), SH_C2[4] * (real)2.f * -y)));
-                    dz = v3_add(dz, v3_add(v3_add(v3_scale(SH(5), SH_C2[1] * y), v3_scale(SH(6), SH_C2[2] * (real)2.f * (real)2.f * z)), v3_scale(SH(7), SH_C2[3] * x)));
-                    if (D > 2) {
-                        OUT(9, SH_C3[0] * y * ((real)3.f * xx - yy)); OUT(10, SH_C3[1] * xy * z); OUT(11, SH_C3[2] * y * ((real)4.f * zz - xx - yy));
-                        OUT(12, SH_C3[3] * z * ((real)2.f * zz - (real)3.f * xx - (real)3.f * yy)); OUT(13, SH_C3[4] * x * ((real)4.f * zz - xx - yy));
-                        OUT(14, SH_C3[5] * z * (xx - yy)); OUT(15, SH_C3[6] * x * (xx - (real)3.f * yy));
-                        v3 t = v3_scale(SH(9), SH_C3[0] * (real)3.f * (real)2.f * xy);
-                        t = v3_add(t, v3_scale(SH(10), SH_C3[1] * yz));
-                        t = v3_add(t, v3_scale(SH(11), SH_C3[2] * (real)-2.f * xy));
-                        t = v3_add(t, v3_scale(SH(12), SH_C3[3] * (real)-3.f * (real)2.f * xz));
-                        t = v3_add(t, v3_scale(SH(13), SH_C3[4] * ((real)-3.f * xx + (real)4.f * zz - yy)));
-                        t = v3_add(t, v3_scale(SH(14), SH_C3[5] * (real)2.f * xz));
-                        t = v3_add(t, v3_scale(SH(15), SH_C3[6] * (real)3.f * (xx - yy)));
-                        dx = v3_add(dx, t);
-                        t = v3_scale(SH(9), SH_C3[0] * (real)3.f * (xx - yy));
-                        t = v3_add(t, v3_scale(SH(10), SH_C3[1] * xz));
-                        t = v3_add(t, v3_scale(SH(11), SH_C3[2] * ((real)-3.f * yy + (real)4.f * zz - xx)));
-                        t = v3_add(t, v3_scale(SH(12), SH_C3[3] * (real)-3.f * (real)2.f * yz));
-                        t = v3_add(t, v3_scale(SH(13), SH_C3[4] * (real)-2.f * xy));
-                        t = v3_add(t, v3_scale(SH(14), SH_C3[5] * (real)-2.f * yz));
-                        t = v3_add(t, v3_scale(SH(15), SH_C3[6] * (real)-3.f * (real)2.f * xy));
-                        dy = v3_add(dy, t);
-                        t = v3_scale(SH(10), SH_C3[1] * xy);
-                        t = v3_add(t, v3_scale(SH(11), SH_C3[2] * (real)4.f * (real)2.f * yz));
-                        t = v3_add(t, v3_scale(SH(12), SH_C3[3] * (real)3.f * ((real)2.f * zz - xx - yy)));
-                        t = v3_add(t, v3_scale(SH(13), SH_C3[4] * (real)4.f * (real)2.f * xz));
-                        t = v3_add(t, v3_scale(SH(14), SH_C3[5] * (xx - yy)));
-                        dz = v3_add(dz, t);
-                    }
-                }
-            }
-#undef SH
-#undef OUT
-            const v3 gdir = v3_make(v3_dot(g, dx), v3_dot(g, dy), v3_dot(g, dz));
-            gcenter = v3_add(gcenter, dnorm3(dir_orig, gdir));
-        }
+        if (use_shs) gcenter = v3_add(gcenter, sh_backward(D, M, center, cam, shs, i, clamped, g_rgb, dL_dshs));
         const v3 gv1 = v3_div(v3_add(v3_sub(v3_sub(v3_scale(gr1, 2), gr2), gr3), gcenter), (real)3.0f);
         const v3 gv2 = v3_div(v3_add(v3_sub(v3_sub(v3_scale(gr2, 2), gr1), gr3), gcenter), (real)3.0f);
         const v3 gv3 = v3_div(v3_add(v3_sub(v3_sub(v3_scale(gr3, 2), gr1), gr2), gcenter), (real)3.0f);
         real *ov = dL_dvertex + 9 * (size_t)i;
         ov[0] = gv1.x; ov[1] = gv1.y; ov[2] = gv1.z; ov[3] = gv2.x; ov[4] = gv2.y; ov[5] = gv2.z; ov[6] = gv3.x; ov[7] = gv3.y; ov[8] = gv3.z;
         dL_dcenter2D[2 * i] = gc2d.x; dL_dcenter2D[2 * i + 1] = gc2d.y;
+    }
+    return 0;
+}
+
+
+/* =====================================================================================================================
+ * 3D primitive: the reference's second rasterizer package, R3D = /root/reference/submodules/diff-triangle-rasterization-3D
+ * (same binning: ts2d_oracle_bin above restates R3D/src/rasterizer.cu:37-99 too -- the files are identical there).
+ *   ts3d_oracle_preprocess       R3D/src/forward.cu:61-146    (FORWARD::preprocessCUDA), helpers R3D/src/auxiliary.h:35-100
+ *   ts3d_oracle_render           R3D/src/forward.cu:151-306   (FORWARD::renderCUDA)
+ *   ts3d_oracle_render_bwd       R3D/src/backward.cu:215-454  (BACKWARD::renderCUDA)
+ *   ts3d_oracle_preprocess_bwd   R3D/src/backward.cu:144-213  (BACKWARD::preprocessCUDA)
+ * Pinned the same way as the 2D part: against outputs of the reference's own CUDA build (oracle/_ref/ts3d_ref_C*.so)
+ * on seeded scenes, committed as tests/golden/r3d_*.npz.
+ * ===================================================================================================================== */
+/* R3D/src/auxiliary.h:35-43 (fp32, unlike the 2D package's fp64 ndc2Pix) */
+static inline real proj_to_pix(real v, int S) { return (v + (real)1.0f) * (real)S * (real)0.5f - (real)0.5f; }
+static inline real pix_to_proj(real v, int S) { return ((real)2.0f * v - (real)S + (real)1.0f) / (real)S; }
+
+int ts3d_oracle_preprocess(int W, int H, int P, int D, int M, int use_shs, int back_culling, const real *viewmatrix, const real *projmatrix,
+                           const real *campos, const real *vertex, const real *shs, int32_t *radii, real *v_view /*[P][3][3]*/,
+                           real *normal_view /*[P][3], un-normalised*/, real *depth, real *rgb /*[P][3]*/, uint8_t *clamped /*[P][3]*/,
+                           uint32_t *tiles_touched, uint32_t *rect_min /*[P][2]*/, uint32_t *rect_max /*[P][2]*/)
+{
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    const v3 cam = v3_make(campos[0], campos[1], campos[2]);
+    memset(radii, 0, sizeof(int32_t) * P);
+    memset(v_view, 0, sizeof(real) * 9 * P);
+    memset(normal_view, 0, sizeof(real) * 3 * P);
+    memset(depth, 0, sizeof(real) * P);
+    memset(rgb, 0, sizeof(real) * 3 * P);
+    memset(clamped, 0, 3 * (size_t)P);
+    memset(tiles_touched, 0, sizeof(uint32_t) * P);
+    memset(rect_min, 0, sizeof(uint32_t) * 2 * P);
+    memset(rect_max, 0, sizeof(uint32_t) * 2 * P);
+    for (int i = 0; i < P; i++) {
+        const real *vp = vertex + 9 * (size_t)i;
+        const v3 a = v3_make(vp[0], vp[1], vp[2]), b = v3_make(vp[3], vp[4], vp[5]), c = v3_make(vp[6], vp[7], vp[8]);
+        const v3 av = xform_point43(a, viewmatrix), bv = xform_point43(b, viewmatrix), cv = xform_point43(c, viewmatrix);
+        const v3 cview = v3_div(v3_add(v3_add(av, bv), cv), (real)3.0f);
+        const v3 n = v3_cross(v3_sub(bv, av), v3_sub(cv, av));
+        if (v3_norm(n) < EPSF) continue;          /* degenerate, :96 */
+        if (back_culling && n.z >= 0) continue;   /* :98 */
+        const real dil = (real)3.0f;
+        const v3 center = v3_div(v3_add(v3_add(a, b), c), (real)3.0f);
+        const v3 d1 = v3_add(center, v3_scale(v3_sub(a, center), dil)), d2 = v3_add(center, v3_scale(v3_sub(b, center), dil)),
+                 d3 = v3_add(center, v3_scale(v3_sub(c, center), dil));
+        const v3 p1 = project_point(d1, projmatrix), p2 = project_point(d2, projmatrix), p3 = project_point(d3, projmatrix);
+        if (p1.z <= 0 || p2.z <= 0 || p3.z <= 0) continue; /* near culling on the dilated vertices, :111 */
+        const v2 s1 = v2_make(proj_to_pix(p1.x, W), proj_to_pix(p1.y, H)), s2 = v2_make(proj_to_pix(p2.x, W), proj_to_pix(p2.y, H)),
+                 s3 = v2_make(proj_to_pix(p3.x, W), proj_to_pix(p3.y, H));
+        const v2 vmin = v2_make(r_min(r_min(s1.x, s2.x), s3.x), r_min(r_min(s1.y, s2.y), s3.y));
+        const v2 vmax = v2_make(r_max(r_max(s1.x, s2.x), s3.x), r_max(r_max(s1.y, s2.y), s3.y));
+        int ix0 = f2i(vmin.x / (real)TILE), iy0 = f2i(vmin.y / (real)TILE);
+        int ix1 = f2i((vmax.x + (real)(TILE - 1)) / (real)TILE), iy1 = f2i((vmax.y + (real)(TILE - 1)) / (real)TILE);
+        uint32_t rx0 = (uint32_t)(ix0 < 0 ? 0 : ix0), ry0 = (uint32_t)(iy0 < 0 ? 0 : iy0);
+        uint32_t rx1 = (uint32_t)(ix1 < 0 ? 0 : ix1), ry1 = (uint32_t)(iy1 < 0 ? 0 : iy1);
+        if (rx0 > (uint32_t)gx) rx0 = gx;
+        if (ry0 > (uint32_t)gy) ry0 = gy;
+        if (rx1 > (uint32_t)gx) rx1 = gx;
+        if (ry1 > (uint32_t)gy) ry1 = gy;
+        if (rx1 <= rx0 || ry1 <= ry0) continue; /* :124 */
+        if (use_shs) {
+            v3 col = sh_to_rgb(D, M, center, cam, shs, i, clamped);
+            rgb[3 * i] = col.x; rgb[3 * i + 1] = col.y; rgb[3 * i + 2] = col.z;
+        }
+        real *o = v_view + 9 * (size_t)i;
+        o[0] = av.x; o[1] = av.y; o[2] = av.z; o[3] = bv.x; o[4] = bv.y; o[5] = bv.z; o[6] = cv.x; o[7] = cv.y; o[8] = cv.z;
+        normal_view[3 * i] = n.x; normal_view[3 * i + 1] = n.y; normal_view[3 * i + 2] = n.z;
+        depth[i] = cview.z;
+        tiles_touched[i] = (rx1 - rx0) * (ry1 - ry0);
+        rect_min[2 * i] = rx0; rect_min[2 * i + 1] = ry0;
+        rect_max[2 * i] = rx1; rect_max[2 * i + 1] = ry1;
+        radii[i] = (int32_t)r_max(r_ceil((vmax.x - vmin.x) * (real)0.5f), r_ceil((vmax.y - vmin.y) * (real)0.5f)); /* :145 */
+    }
+    return 0;
+}
+
+/* per-pair evaluation, R3D/src/forward.cu:243-276 (bwd == 0) / R3D/src/backward.cu:330-352 (bwd == 1).  The two differ:
+ * forward divides by ray.n and skips on alpha < 1/255; backward multiplies by 1/(ray.n) and skips on G < 1/255. */
+typedef struct { real depth, inv_pn, inv_nn, a1, a2, a3, ecc, power, G, alpha; v3 pv1, pv2, pv3; } pair3_t;
+static inline int eval_pair3(const real *vv, const real *nv, real op, real gamma, v3 ray, int bwd, pair3_t *o)
+{
+    const v3 v1 = v3_make(vv[0], vv[1], vv[2]), v2 = v3_make(vv[3], vv[4], vv[5]), v3v = v3_make(vv[6], vv[7], vv[8]);
+    const v3 n = v3_make(nv[0], nv[1], nv[2]);
+    const real pn = v3_dot(ray, n);
+    if (r_abs(pn) < EPSF) return 0;
+    if (bwd) { o->inv_pn = (real)1.0f / pn; o->depth = v3_dot(v1, n) * o->inv_pn; }
+    else { o->inv_pn = (real)1.0f / pn; o->depth = v3_dot(v1, n) / pn; }
+    const v3 pview = v3_scale(ray, o->depth);
+    o->pv1 = v3_sub(v1, pview); o->pv2 = v3_sub(v2, pview); o->pv3 = v3_sub(v3v, pview);
+    o->inv_nn = (real)1.0f / v3_dot(n, n);
+    o->a1 = v3_dot(v3_cross(o->pv2, o->pv3), n) * o->inv_nn;
+    o->a2 = v3_dot(v3_cross(o->pv3, o->pv1), n) * o->inv_nn;
+    o->a3 = (real)1.0f - o->a1 - o->a2;
+    o->ecc = (real)1.0f - (real)3.0f * r_min(r_min(o->a1, o->a2), o->a3);
+    if (o->ecc < 0 || o->ecc > (real)10.0f) return 0;
+    o->power = (real)-0.5f * r_pow(o->ecc, (real)2.0f * gamma);
+    o->G = r_exp(o->power);
+    o->alpha = r_min((real)0.99f, op * o->G);
+    if (bwd) return !(o->G < (real)1.0f / (real)255.0f);
+    return !(o->alpha < (real)1.0f / (real)255.0f);
+}
+
+int ts3d_oracle_render(int W, int H, int C, real gamma, int rich_info, real tfx, real tfy, const uint32_t *ranges, const uint32_t *list,
+                       const real *v_view, const real *normal_view, const real *feature, const real *opacity, real background_depth,
+                       const real *background, real *final_T, uint32_t *n_contrib, real *out_feature, real *out_depth, real *out_normal,
+                       real *contrib_sum, real *contrib_max, int P, int tile_step, int tile_offset)
+{
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    double *csum = NULL;
+    uint32_t *cmax_bits = NULL;
+    if (rich_info) {
+        csum = (double *)calloc((size_t)(P ? P : 1), sizeof(double));
+        cmax_bits = (uint32_t *)calloc((size_t)(P ? P : 1), sizeof(uint32_t));
+    }
+    if (tile_step < 1) tile_step = 1;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int tile = 0; tile < gx * gy; tile++) {
+        const int ty = tile / gx, tx = tile % gx;
+        if (tile % tile_step != tile_offset) continue;
+        const uint32_t beg = ranges[2 * tile], end = ranges[2 * tile + 1];
+        for (int ly = 0; ly < TILE; ly++)
+            for (int lx = 0; lx < TILE; lx++) {
+                const int px = tx * TILE + lx, py = ty * TILE + ly;
+                if (px >= W || py >= H) continue;
+                const size_t pix = (size_t)W * py + px;
+                const v3 ray = v3_make(tfx * pix_to_proj((real)px, W), tfy * pix_to_proj((real)py, H), (real)1.0f);
+                real T = 1, acc[3] = {0, 0, 0}, accd = 0;
+                v3 accn = v3_make(0, 0, 0);
+                uint32_t contributor = 0, last = 0;
+                int done = 0;
+                for (uint32_t k = beg; k < end && !done; k++) {
+                    contributor++;
+                    last = contributor;
+                    const uint32_t id = list[k];
+                    pair3_t pr;
+                    if (!eval_pair3(v_view + 9 * (size_t)id, normal_view + 3 * (size_t)id, opacity[id], gamma, ray, 0, &pr)) continue;
+                    const real contrib = pr.alpha * T;
+                    T *= ((real)1.0f - pr.alpha);
+                    for (int ch = 0; ch < C; ch++) acc[ch] += feature[(size_t)id * C + ch] * contrib;
+                    if (rich_info) {
+#pragma omp atomic
+                        csum[id] += (double)contrib;
+                        {
+                            float cf = (float)contrib;
+                            uint32_t nb, ob;
+                            memcpy(&nb, &cf, 4);
+                            uint32_t *slot = cmax_bits + id;
+                            ob = __atomic_load_n(slot, __ATOMIC_RELAXED);
+                            while (nb > ob && !__atomic_compare_exchange_n(slot, &ob, nb, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+                        }
+                        accn.x += normal_view[3 * id] * contrib; accn.y += normal_view[3 * id + 1] * contrib; accn.z += normal_view[3 * id + 2] * contrib;
+                        accd += pr.depth * contrib;
+                    }
+                    if (T <= (real)0.0001f) done = 1;
+                }
+                final_T[pix] = T;
+                n_contrib[pix] = last;
+                for (int ch = 0; ch < C; ch++) out_feature[(size_t)ch * H * W + pix] = acc[ch] + T * background[ch];
+                if (rich_info) {
+                    out_depth[pix] = accd + T * background_depth;
+                    out_normal[pix] = accn.x; out_normal[(size_t)H * W + pix] = accn.y; out_normal[2 * (size_t)H * W + pix] = accn.z;
+                }
+            }
+    }
+    if (rich_info) {
+        for (int i = 0; i < P; i++) { contrib_sum[i] = (real)csum[i]; float mf; memcpy(&mf, cmax_bits + i, 4); contrib_max[i] = (real)mf; }
+        free(cmax_bits);
+        free(csum);
+    }
+    return 0;
+}
+
+static inline void atomic_add3(double *dst, v3 g)
+{
+#pragma omp atomic
+    dst[0] += (double)g.x;
+#pragma omp atomic
+    dst[1] += (double)g.y;
+#pragma omp atomic
+    dst[2] += (double)g.z;
+}
+static inline v3 v3_neg(v3 a) { return v3_make(-a.x, -a.y, -a.z); }
+static inline v3 v3_comb3(real a, v3 x, real b, v3 y, real c, v3 z) { return v3_add(v3_add(v3_scale(x, a), v3_scale(y, b)), v3_scale(z, c)); }
+
+int ts3d_oracle_render_bwd(int W, int H, int C, real gamma, int rich_info, real tfx, real tfy, const uint32_t *ranges, const uint32_t *list,
+                           const real *v_view, const real *normal_view, const real *feature, const real *opacity, real background_depth,
+                           const real *background, const real *final_T, const uint32_t *n_contrib, const real *dL_dout_feature,
+                           const real *dL_dout_depth, const real *dL_dout_normal, int P, double *g_vview /*[P][3][3]*/,
+                           double *g_normal /*[P][3]*/, double *g_feature /*[P][C]*/, double *g_opacity /*[P]*/, int tile_step, int tile_offset)
+{
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    if (tile_step < 1) tile_step = 1;
+    memset(g_vview, 0, sizeof(double) * 9 * P);
+    memset(g_normal, 0, sizeof(double) * 3 * P);
+    memset(g_feature, 0, sizeof(double) * (size_t)C * P);
+    memset(g_opacity, 0, sizeof(double) * P);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int tile = 0; tile < gx * gy; tile++) {
+        const int ty = tile / gx, tx = tile % gx;
+        if (tile % tile_step != tile_offset) continue;
+        const uint32_t beg = ranges[2 * tile], end = ranges[2 * tile + 1];
+        for (int ly = 0; ly < TILE; ly++)
+            for (int lx = 0; lx < TILE; lx++) {
+                const int px = tx * TILE + lx, py = ty * TILE + ly;
+                if (px >= W || py >= H) continue;
+                const size_t pix = (size_t)W * py + px;
+                const v3 ray = v3_make(tfx * pix_to_proj((real)px, W), tfy * pix_to_proj((real)py, H), (real)1.0f);
+                real T = final_T[pix];
+                const uint32_t last = n_contrib[pix];
+                uint32_t contributor = end - beg;
+                real acc[3] = {0, 0, 0}, gpix[3] = {0, 0, 0};
+                for (int ch = 0; ch < C; ch++) { acc[ch] = background[ch]; gpix[ch] = dL_dout_feature[(size_t)ch * H * W + pix]; }
+                v3 accn = v3_make(0, 0, 0), gn = v3_make(0, 0, 0);
+                real accd = background_depth, gd = 0;
+                if (rich_info) {
+                    gn = v3_make(dL_dout_normal[pix], dL_dout_normal[(size_t)W * H + pix], dL_dout_normal[2 * (size_t)W * H + pix]);
+                    gd = dL_dout_depth[pix];
+                }
+                for (uint32_t k = end; k-- > beg;) {
+                    contributor--;
+                    if (contributor >= last) continue;
+                    const uint32_t id = list[k];
+                    const real *vv = v_view + 9 * (size_t)id, *nv = normal_view + 3 * (size_t)id;
+                    pair3_t pr;
+                    const real op = opacity[id];
+                    if (!eval_pair3(vv, nv, op, gamma, ray, 1, &pr)) continue;
+                    const v3 v1 = v3_make(vv[0], vv[1], vv[2]), v2 = v3_make(vv[3], vv[4], vv[5]), v3v = v3_make(vv[6], vv[7], vv[8]);
+                    const v3 n = v3_make(nv[0], nv[1], nv[2]);
+                    T /= ((real)1.0f - pr.alpha);
+                    const real contrib = pr.alpha * T;
+                    real dL_dcontrib = 0, dL_ddepth = 0;
+                    v3 dL_dnormal = v3_make(0, 0, 0);
+                    for (int ch = 0; ch < C; ch++) {
+#pragma omp atomic
+                        g_feature[(size_t)id * C + ch] += (double)(gpix[ch] * contrib);
+                        const real feat = feature[(size_t)id * C + ch];
+                        dL_dcontrib += gpix[ch] * (feat - acc[ch]);
+                        acc[ch] = pr.alpha * feat + ((real)1.0f - pr.alpha) * acc[ch];
+                    }
+                    if (rich_info) {
+                        dL_dnormal = v3_add(dL_dnormal, v3_scale(gn, contrib));
+                        dL_dcontrib += v3_dot(gn, v3_sub(n, accn));
+                        accn = v3_add(v3_scale(n, pr.alpha), v3_scale(accn, (real)1.0f - pr.alpha));
+                        dL_ddepth += gd * contrib;
+                        dL_dcontrib += gd * (pr.depth - accd);
+                        accd = pr.alpha * pr.depth + ((real)1.0f - pr.alpha) * accd;
+                    }
+                    const real dL_dalpha = dL_dcontrib * T;
+                    const real dL_dpower = (op * pr.G < (real)0.99f) ? dL_dalpha * pr.alpha : 0;
+                    const real dL_decc = dL_dpower * 2 * gamma * pr.power / (pr.ecc + EPSF);
+                    v3 dda = v3_make(0, 0, 0);
+                    if (pr.a1 <= pr.a2 && pr.a1 <= pr.a3) dda.x = (real)-3.0f;
+                    else if (pr.a2 <= pr.a1 && pr.a2 <= pr.a3) dda.y = (real)-3.0f;
+                    else dda.z = (real)-3.0f;
+                    const v3 dL_da = v3_scale(dda, dL_decc);
+                    /* R3D/src/backward.cu:401-428 */
+                    const v3 z3 = v3_make(0, 0, 0);
+                    const v3 da1_dv1 = z3;
+                    const v3 da1_dv2 = v3_scale(v3_cross(pr.pv3, n), pr.inv_nn);
+                    const v3 da1_dv3 = v3_scale(v3_cross(n, pr.pv2), pr.inv_nn);
+                    const v3 da1_dn = v3_scale(v3_sub(v3_cross(pr.pv2, pr.pv3), v3_scale(n, (real)2.0f * pr.a1)), pr.inv_nn);
+                    const real da1_dd = v3_dot(n, v3_cross(v3_sub(v3v, v2), ray)) * pr.inv_nn;
+                    const v3 da2_dv1 = v3_scale(v3_cross(n, pr.pv3), pr.inv_nn);
+                    const v3 da2_dv2 = z3;
+                    const v3 da2_dv3 = v3_scale(v3_cross(pr.pv1, n), pr.inv_nn);
+                    const v3 da2_dn = v3_scale(v3_sub(v3_cross(pr.pv3, pr.pv1), v3_scale(n, (real)2.0f * pr.a2)), pr.inv_nn);
+                    const real da2_dd = v3_dot(n, v3_cross(v3_sub(v1, v3v), ray)) * pr.inv_nn;
+                    const v3 da3_dv1 = v3_sub(v3_neg(da1_dv1), da2_dv1), da3_dv2 = v3_sub(v3_neg(da1_dv2), da2_dv2),
+                             da3_dv3 = v3_sub(v3_neg(da1_dv3), da2_dv3), da3_dn = v3_sub(v3_neg(da1_dn), da2_dn);
+                    const real da3_dd = -da1_dd - da2_dd;
+                    dL_ddepth += dL_da.x * da1_dd + dL_da.y * da2_dd + dL_da.z * da3_dd;
+                    const v3 dd_dv1 = v3_scale(n, pr.inv_pn);
+                    const v3 dd_dn = v3_scale(v3_sub(v1, v3_scale(ray, pr.depth)), pr.inv_pn);
+                    const v3 g1 = v3_add(v3_comb3(dL_da.x, da1_dv1, dL_da.y, da2_dv1, dL_da.z, da3_dv1), v3_scale(dd_dv1, dL_ddepth));
+                    const v3 g2 = v3_comb3(dL_da.x, da1_dv2, dL_da.y, da2_dv2, dL_da.z, da3_dv2);
+                    const v3 g3 = v3_comb3(dL_da.x, da1_dv3, dL_da.y, da2_dv3, dL_da.z, da3_dv3);
+                    dL_dnormal = v3_add(dL_dnormal, v3_add(v3_comb3(dL_da.x, da1_dn, dL_da.y, da2_dn, dL_da.z, da3_dn), v3_scale(dd_dn, dL_ddepth)));
+                    atomic_add3(g_vview + 9 * (size_t)id, g1);
+                    atomic_add3(g_vview + 9 * (size_t)id + 3, g2);
+                    atomic_add3(g_vview + 9 * (size_t)id + 6, g3);
+                    atomic_add3(g_normal + 3 * (size_t)id, dL_dnormal);
+#pragma omp atomic
+                    g_opacity[id] += (double)(dL_dalpha * pr.G);
+                }
+            }
+    }
+    return 0;
+}
+
+int ts3d_oracle_preprocess_bwd(int P, int D, int M, int use_shs, const real *viewmatrix, const real *campos, const real *vertex, const real *shs,
+                               const int32_t *radii, const uint8_t *clamped, const real *v_view, const double *g_vview, const double *g_normal,
+                               const double *g_rgb, real *dL_dvertex /*[P][9]*/, real *dL_dcenter2D /*[P][2]*/, real *dL_dshs /*[P][M][3]*/)
+{
+    memset(dL_dvertex, 0, sizeof(real) * 9 * P);
+    memset(dL_dcenter2D, 0, sizeof(real) * 2 * P);
+    if (M > 0) memset(dL_dshs, 0, sizeof(real) * 3 * (size_t)M * P);
+    const v3 cam = v3_make(campos[0], campos[1], campos[2]);
+    for (int i = 0; i < P; i++) {
+        if (radii[i] <= 0) continue;
+        const real *vv = v_view + 9 * (size_t)i;
+        const v3 av = v3_make(vv[0], vv[1], vv[2]), bv = v3_make(vv[3], vv[4], vv[5]), cv = v3_make(vv[6], vv[7], vv[8]);
+        const double *g = g_vview + 9 * (size_t)i;
+        v3 g1v = v3_make((real)g[0], (real)g[1], (real)g[2]), g2v = v3_make((real)g[3], (real)g[4], (real)g[5]),
+           g3v = v3_make((real)g[6], (real)g[7], (real)g[8]);
+        const v3 gN = v3_make((real)g_normal[3 * i], (real)g_normal[3 * i + 1], (real)g_normal[3 * i + 2]);
+        g1v = v3_add(g1v, v3_cross(v3_sub(bv, cv), gN)); /* :179-181 */
+        g2v = v3_add(g2v, v3_cross(v3_sub(cv, av), gN));
+        g3v = v3_add(g3v, v3_cross(v3_sub(av, bv), gN));
+        v3 g1 = xform_vec43_T(g1v, viewmatrix), g2 = xform_vec43_T(g2v, viewmatrix), g3 = xform_vec43_T(g3v, viewmatrix);
+        if (use_shs) {
+            const real *vp = vertex + 9 * (size_t)i;
+            const v3 a = v3_make(vp[0], vp[1], vp[2]), b = v3_make(vp[3], vp[4], vp[5]), c = v3_make(vp[6], vp[7], vp[8]);
+            const v3 center = v3_div(v3_add(v3_add(a, b), c), (real)3.0f);
+            const v3 gsh = sh_backward(D, M, center, cam, shs, i, clamped, g_rgb, dL_dshs);
+            g1 = v3_add(g1, v3_div(gsh, (real)3.0f));
+            g2 = v3_add(g2, v3_div(gsh, (real)3.0f));
+            g3 = v3_add(g3, v3_div(gsh, (real)3.0f));
+        }
+        real *ov = dL_dvertex + 9 * (size_t)i;
+        ov[0] = g1.x; ov[1] = g1.y; ov[2] = g1.z; ov[3] = g2.x; ov[4] = g2.y; ov[5] = g2.z; ov[6] = g3.x; ov[7] = g3.y; ov[8] = g3.z;
+        const v3 gcv = xform_vec43(v3_add(v3_add(g1, g2), g3), viewmatrix); /* :211-213 */
+        dL_dcenter2D[2 * i] = gcv.x; dL_dcenter2D[2 * i + 1] = gcv.y;
     }
     return 0;
 }

@@ -7,6 +7,10 @@ state tensors), the current CUDA stream and the device guard.
 
 Extra keyword-only arguments (no counterpart in the reference):
     shard=(rank, world)  image-space tile sharding for multi-GPU (see distributed.py)
+    primitive="2D"|"3D"  which of the reference's two rasterizer packages the call stands in for: "2D" =
+                         diff_triangle_rasterization_2D (screen-space triangles, the north-star path), "3D" =
+                         diff_triangle_rasterization_3D (ray / plane intersection in view space; identical pybind
+                         signatures, R3D/ext.cpp:4-9 / R3D/src/extension_interface.cu:19-246)
 """
 from __future__ import annotations
 
@@ -75,18 +79,21 @@ def _require_cuda_f32(name, t):
 
 
 def _structs(image_width, image_height, tan_fovx, tan_fovy, viewmatrix, projmatrix, campos, sh_degree, gamma, scale_modifier,
-             background_depth, background, vertex, shs, feature, opacity, P, use_shs, Cn, M, back_culling, rich_info, debug, shard):
+             background_depth, background, vertex, shs, feature, opacity, P, use_shs, Cn, M, back_culling, rich_info, debug, shard,
+             primitive="2D"):
     cam = _lib.Camera(int(image_width), int(image_height), float(tan_fovx), float(tan_fovy), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos))
     geom = _lib.Geometry(int(P), int(sh_degree), int(M), int(Cn), int(use_shs), float(gamma), float(scale_modifier), float(background_depth),
                          _ptr(background), _ptr(vertex), _ptr(shs) if use_shs else None, None if use_shs else _ptr(feature), _ptr(opacity))
-    flags = _lib.Flags(int(bool(back_culling)), int(bool(rich_info)), int(bool(debug)), int(shard[0]), int(shard[1]), int(EXACT))
+    flags = _lib.Flags(int(bool(back_culling)), int(bool(rich_info)), int(bool(debug)), int(shard[0]), int(shard[1]), int(EXACT),
+                       _lib.PRIMITIVES[primitive])
     return cam, geom, flags
 
 
 def rasterize_triangles(image_width: int, image_height: int, tan_fovx: float, tan_fovy: float, viewmatrix: torch.Tensor,
                         projmatrix: torch.Tensor, campos: torch.Tensor, sh_degree: int, gamma: float, scale_modifier: float,
                         background_depth: float, background: torch.Tensor, vertex: torch.Tensor, shs: torch.Tensor, feature: torch.Tensor,
-                        opacity: torch.Tensor, back_culling: bool, rich_info: bool, debug: bool, *, shard: Tuple[int, int] = (0, 1)):
+                        opacity: torch.Tensor, back_culling: bool, rich_info: bool, debug: bool, *, shard: Tuple[int, int] = (0, 1),
+                        primitive: str = "2D"):
     """-> (num_rendered:int, out_feature, radii, depth, normal, contrib_sum, contrib_max, geometryBuffer, binningBuffer, imageBuffer)
 
     Mirrors rasterizeTrianglesForward (extension_interface.cu:19-152)."""
@@ -130,7 +137,7 @@ def rasterize_triangles(image_width: int, image_height: int, tan_fovx: float, ta
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         cam, geom, flags = _structs(W, H, tan_fovx, tan_fovy, viewmatrix, projmatrix, campos, sh_degree, gamma, scale_modifier,
                                     background_depth, background, vertex, shs, feature, opacity, P, use_shs, Cn, M, back_culling, rich_info,
-                                    debug, shard)
+                                    debug, shard, primitive)
         gbytes = lib.ts2d_geometry_state_bytes(P)
         geometryBuffer = torch.empty((gbytes,), **u8)
         num_rendered = C.c_int64(0)
@@ -152,7 +159,7 @@ def rasterize_triangles_backward(tan_fovx: float, tan_fovy: float, viewmatrix: t
                                  vertex: torch.Tensor, shs: torch.Tensor, feature: torch.Tensor, opacity: torch.Tensor, num_rendered: int,
                                  radii: torch.Tensor, geometryBuffer: torch.Tensor, binningBuffer: torch.Tensor, imageBuffer: torch.Tensor,
                                  dL_dout_feature: torch.Tensor, dL_dout_depth: torch.Tensor | None, dL_dout_normal: torch.Tensor | None,
-                                 rich_info: bool, debug: bool, *, shard: Tuple[int, int] = (0, 1)):
+                                 rich_info: bool, debug: bool, *, shard: Tuple[int, int] = (0, 1), primitive: str = "2D"):
     """-> (dL_dvertex (P,3,3), dL_dcenter2D (P,2), dL_dshs (P,M,3), dL_dfeature (P,C), dL_dopacity (P,1))
 
     Mirrors rasterizeTrianglesBackward (extension_interface.cu:154-260).  Unlike the reference's
@@ -182,7 +189,7 @@ def rasterize_triangles_backward(tan_fovx: float, tan_fovy: float, viewmatrix: t
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         cam, geom, flags = _structs(W, H, tan_fovx, tan_fovy, viewmatrix, projmatrix, campos, sh_degree, gamma, scale_modifier,
                                     background_depth, background, vertex, shs, feature, opacity, P, use_shs, Cn, M, False, rich_info, debug,
-                                    shard)
+                                    shard, primitive)
         sbytes = lib.ts2d_backward_scratch_bytes(P)
         scratch = torch.empty((sbytes,), device=dev, dtype=torch.uint8)
         loss = _lib.LossIn(_ptr(dL_dout_feature), _ptr(dL_dout_depth) if rich_info else None, _ptr(dL_dout_normal) if rich_info else None)

@@ -19,7 +19,7 @@ import torch.nn as nn
 
 from . import _C
 
-__all__ = ["TriangleRasterizationSettings", "TriangleRasterizer", "_RasterizeTriangles", "_C"]
+__all__ = ["TriangleRasterizationSettings", "TriangleRasterizer", "_RasterizeTriangles", "TriangleRasterizer3D", "_RasterizeTriangles3D", "_C"]
 
 
 def _cpu_deep_copy_tuple(input_tuple):
@@ -68,17 +68,26 @@ def _shard():
 
 
 class _RasterizeTriangles(torch.autograd.Function):
+    PRIMITIVE = "2D"  # which reference package this Function stands in for (see _C.rasterize_triangles)
+
+    @classmethod
+    def apply(cls, *args, **kwargs):  # noqa: D102  -- tags the call with the primitive; staticmethods below read it from ctx
+        return super().apply(*args, cls.PRIMITIVE, **kwargs)
+
     @staticmethod
-    def forward(ctx, vertex, center2D, shs, feature, opacity, raster_settings: TriangleRasterizationSettings):
+    def forward(ctx, vertex, center2D, shs, feature, opacity, raster_settings: TriangleRasterizationSettings, primitive="2D"):
         s = raster_settings
         shard = _shard()
+        ctx.primitive = primitive
+        if primitive == "3D":  # the 3D package makes its inputs contiguous in C++ (R3D/src/extension_interface.cu:82-92) instead of raising
+            vertex, shs, feature, opacity = vertex.contiguous(), shs.contiguous(), feature.contiguous(), opacity.contiguous()
         args = (
             s.image_width, s.image_height, s.tanfovx, s.tanfovy, s.viewmatrix.contiguous(), s.projmatrix.contiguous(), s.campos.contiguous(),
             s.sh_degree, s.gamma, s.scale_modifier, float(s.background_depth), s.background.contiguous(), vertex, shs, feature, opacity,
             s.back_culling, s.rich_info, s.debug,
         )
         (num_rendered, out_feature, radii, depth, normal, contrib_sum, contrib_max, geometryBuffer, binningBuffer,
-         imageBuffer) = debug_run(_C.rasterize_triangles, *args, debug=s.debug, shard=shard)
+         imageBuffer) = debug_run(_C.rasterize_triangles, *args, debug=s.debug, shard=shard, primitive=primitive)
 
         ctx.raster_settings = s
         ctx.num_rendered = num_rendered
@@ -115,14 +124,23 @@ class _RasterizeTriangles(torch.autograd.Function):
             geometryBuffer, binningBuffer, imageBuffer, grad_out_feature.contiguous(), grad_out_depth, grad_out_normal, s.rich_info, s.debug,
         )
         grad_vertex, grad_center2D, grad_shs, grad_feature, grad_opacity = debug_run(
-            _C.rasterize_triangles_backward, *args, debug=s.debug, shard=ctx.shard)
+            _C.rasterize_triangles_backward, *args, debug=s.debug, shard=ctx.shard, primitive=ctx.primitive)
         # tile-sharded runs: _C.rasterize_triangles_backward already all-reduced the per-triangle accumulators between the
         # composite and the per-triangle stage, so the five gradients are complete and identical on every rank here
         use_shs = feature.dim() <= 1 or (feature.size(0) == 0 and shs.size(0) > 0)
-        return (grad_vertex, grad_center2D, grad_shs if use_shs else None, None if use_shs else grad_feature, grad_opacity, None)
+        return (grad_vertex, grad_center2D, grad_shs if use_shs else None, None if use_shs else grad_feature, grad_opacity, None, None)
+
+
+class _RasterizeTriangles3D(_RasterizeTriangles):
+    """Stands in for diff_triangle_rasterization_3D._RasterizeTriangles (R3D/diff_triangle_rasterization_3D/__init__.py:49-164):
+    same arguments and return tuples; the per-pixel primitive is the ray / triangle-plane intersection of R3D/src/forward.cu:243-276."""
+
+    PRIMITIVE = "3D"
 
 
 class TriangleRasterizer(nn.Module):
+    _function = _RasterizeTriangles
+
     def __init__(self, raster_settings: TriangleRasterizationSettings):
         super().__init__()
         self.raster_settings = raster_settings
@@ -133,4 +151,10 @@ class TriangleRasterizer(nn.Module):
             raise Exception("Please provide excatly one of either SHs or feature!")
         shs = torch.Tensor([]) if shs is None else shs
         feature = torch.Tensor([]) if feature is None else feature
-        return _RasterizeTriangles.apply(vertex, center2D, shs, feature, opacity, self.raster_settings)
+        return self._function.apply(vertex, center2D, shs, feature, opacity, self.raster_settings)
+
+
+class TriangleRasterizer3D(TriangleRasterizer):
+    """diff_triangle_rasterization_3D.TriangleRasterizer (R3D/diff_triangle_rasterization_3D/__init__.py:167-187)."""
+
+    _function = _RasterizeTriangles3D

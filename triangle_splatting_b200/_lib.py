@@ -28,7 +28,7 @@ class Geometry(C.Structure):
 
 class Flags(C.Structure):
     _fields_ = [("back_culling", C.c_int32), ("rich_info", C.c_int32), ("debug", C.c_int32), ("shard_rank", C.c_int32),
-                ("shard_world", C.c_int32), ("exact", C.c_int32)]
+                ("shard_world", C.c_int32), ("exact", C.c_int32), ("primitive", C.c_int32)]
 
 
 class ForwardOut(C.Structure):
@@ -64,6 +64,7 @@ SYMBOLS = {
     "ts2d_backward_geometry": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_void_p, C.c_void_p,
                                          C.POINTER(BackwardOut), C.c_void_p, C.c_size_t, C.c_void_p]),
     "ts2d_export_geometry": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 10 + [C.c_void_p]),
+    "ts2d_export_geometry3d": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 8 + [C.c_void_p]),
     "ts2d_export_binning": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "ts2d_export_image": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -71,6 +72,8 @@ SYMBOLS = {
     "ts2d_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
 
+ABI_VERSION = 2  # TS2D_ABI_VERSION (include/ts2d.h)
+PRIMITIVES = {"2D": 0, "3D": 1}  # TS2D_PRIMITIVE_* (include/ts2d.h)
 STAGES = ("preprocess", "order_scan", "binning", "render_fwd", "render_bwd", "preprocess_bwd")
 
 

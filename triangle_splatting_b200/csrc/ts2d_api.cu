@@ -112,6 +112,7 @@ int validate(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f
     if (g->C < 1 || g->C > TS2D_MAX_CHANNELS) return TS2D_E_CHANNELS;
     if (g->gamma < 0.0f) return TS2D_E_GAMMA;
     if (f->shard_world < 1 || f->shard_rank < 0 || f->shard_rank >= f->shard_world) return TS2D_E_SHARD;
+    if (f->primitive != TS2D_PRIMITIVE_2D && f->primitive != TS2D_PRIMITIVE_3D) return TS2D_E_PRIMITIVE;
     if (g->P == 0) return 0;
     if (!cam->viewmatrix || !cam->projmatrix || !cam->campos || !g->background || !g->vertex || !g->opacity) return TS2D_E_NULL;
     if (g->use_shs) {
@@ -206,6 +207,7 @@ const char *ts2d_error_string(int code)
     case TS2D_E_SH_DEGREE: return "sh_degree must be in 0..3 and (sh_degree + 1) ** 2 <= shs.size(1)";
     case TS2D_E_SHARD: return "invalid shard_rank / shard_world";
     case TS2D_E_SIZE: return "image size or primitive count out of range";
+    case TS2D_E_PRIMITIVE: return "flags.primitive must be TS2D_PRIMITIVE_2D or TS2D_PRIMITIVE_3D";
     default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
@@ -229,7 +231,10 @@ int ts2d_forward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, con
     GeomState gs;
     if (carve_geometry(geometry_state, geom->P, &gs) > geometry_state_bytes) return TS2D_E_STATE_SIZE;
     cudaStream_t s = (cudaStream_t)stream;
-    TS2D_STAGE(TS2D_STAGE_PREPROCESS, ts2d_launch_preprocess(cam, geom, flags, radii, gs, s));
+    if (flags->primitive == TS2D_PRIMITIVE_3D)
+        TS2D_STAGE(TS2D_STAGE_PREPROCESS, ts2d_launch_preprocess3d(cam, geom, flags, radii, gs, s));
+    else
+        TS2D_STAGE(TS2D_STAGE_PREPROCESS, ts2d_launch_preprocess(cam, geom, flags, radii, gs, s));
     TS2D_STAGE(TS2D_STAGE_ORDER_SCAN, ts2d_launch_order_and_scan(geom->P, gs, num_rendered_host, s));
     return 0;
 }
@@ -252,7 +257,9 @@ int ts2d_forward_render(const ts2d_camera *cam, const ts2d_geometry *geom, const
     if (carve_image(image_state, cam->width, cam->height, &is) > image_state_bytes) return TS2D_E_STATE_SIZE;
     cudaStream_t s = (cudaStream_t)stream;
     TS2D_STAGE(TS2D_STAGE_BINNING, ts2d_launch_binning(cam, geom, flags, num_rendered, gs, bs, is, s));
-    if (ts2d_use_fast(geom, flags))
+    if (flags->primitive == TS2D_PRIMITIVE_3D)
+        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render3d_fwd(cam, geom, flags, gs, bs.tval[1], is, out, s));
+    else if (ts2d_use_fast(geom, flags))
         TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, out, s));
     else
         TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd(cam, geom, flags, gs, bs.tval[1], is, out, s));
@@ -278,11 +285,16 @@ int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_
     carve_binning(const_cast<void *>(binning_state), num_rendered, &bs);
     carve_image(const_cast<void *>(image_state), cam->width, cam->height, &is);
     cudaStream_t s = (cudaStream_t)stream;
-    if (ts2d_use_fast(geom, flags))
+    if (flags->primitive == TS2D_PRIMITIVE_3D)
+        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render3d_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
+    else if (ts2d_use_fast(geom, flags))
         TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, loss, (float *)scratch, s));
     else
         TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
-    TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
+    if (flags->primitive == TS2D_PRIMITIVE_3D)
+        TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess3d_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
+    else
+        TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
     return 0;
 }
 
@@ -306,7 +318,9 @@ int ts2d_backward_composite(const ts2d_camera *cam, const ts2d_geometry *geom, c
     carve_binning(const_cast<void *>(binning_state), num_rendered, &bs);
     carve_image(const_cast<void *>(image_state), cam->width, cam->height, &is);
     cudaStream_t s = (cudaStream_t)stream;
-    if (ts2d_use_fast(geom, flags))
+    if (flags->primitive == TS2D_PRIMITIVE_3D)
+        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render3d_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
+    else if (ts2d_use_fast(geom, flags))
         TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, loss, (float *)scratch, s));
     else
         TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
@@ -326,7 +340,10 @@ int ts2d_backward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, co
     GeomState gs;
     carve_geometry(const_cast<void *>(geometry_state), geom->P, &gs);
     cudaStream_t s = (cudaStream_t)stream;
-    TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
+    if (flags->primitive == TS2D_PRIMITIVE_3D)
+        TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess3d_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
+    else
+        TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
     return 0;
 }
 
@@ -341,6 +358,16 @@ int ts2d_export_geometry(const void *geometry_state, int32_t P, float *v2d, floa
                                                                         gs.tiles, gs.rect, gs.clamp, v2d, area2, normal_view, v_depth, depth,
                                                                         rgb, clamped, tiles_touched, rect_min, rect_max);
     return (int)cudaGetLastError();
+}
+
+int ts2d_export_geometry3d(const void *geometry_state, int32_t P, float *v_view, float *normal_view, float *depth, float *rgb, uint8_t *clamped,
+                           uint32_t *tiles_touched, uint32_t *rect_min, uint32_t *rect_max, void *stream)
+{
+    if (P <= 0) return 0;
+    if (!geometry_state) return TS2D_E_NULL;
+    GeomState gs;
+    carve_geometry(const_cast<void *>(geometry_state), P, &gs);
+    return ts2d_launch_export_geometry3d(P, gs, v_view, normal_view, depth, rgb, clamped, tiles_touched, rect_min, rect_max, (cudaStream_t)stream);
 }
 
 int ts2d_export_binning(const void *geometry_state, const void *binning_state, const void *image_state, int32_t P, int64_t R, int32_t W,

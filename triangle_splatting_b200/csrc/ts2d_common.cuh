@@ -76,6 +76,7 @@ __device__ __forceinline__ f2 operator*(float s, f2 a) { return mk2(s * a.x, s *
 __device__ __forceinline__ f2 operator+(f2 a, float s) { return mk2(a.x + s, a.y + s); }
 __device__ __forceinline__ f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
 __device__ __forceinline__ f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ f3 operator*(float s, f3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
 __device__ __forceinline__ f3 operator/(f3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
@@ -196,7 +197,20 @@ int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
                                 const uint32_t *list, ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s);
 // The fast kernels cover the gamma range the trainer schedules (1..50, VanillaTS_model.py:549-554) with margin;
 // outside it (for gamma < 0.6 the ecc <= 10 cut starts to matter; gamma -> 0 makes ecc^(2 gamma) degenerate) the exact mirror kernels are used.
-static inline bool ts2d_use_fast(const ts2d_geometry *g, const ts2d_flags *f) { return !f->exact && g->gamma >= 0.6f && g->gamma <= 64.0f; }
+static inline bool ts2d_use_fast(const ts2d_geometry *g, const ts2d_flags *f)
+{
+    return f->primitive == TS2D_PRIMITIVE_2D && !f->exact && g->gamma >= 0.6f && g->gamma <= 64.0f;
+}
+// 3D primitive (ts2d_prim3d.cu)
+int ts2d_launch_preprocess3d(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, int32_t *radii, GeomState gs, cudaStream_t s);
+int ts2d_launch_render3d_fwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
+                             ImageState is, const ts2d_forward_out *out, cudaStream_t s);
+int ts2d_launch_render3d_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
+                             ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s);
+int ts2d_launch_preprocess3d_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, const int32_t *radii, GeomState gs,
+                                 const float *gacc, const ts2d_backward_out *out, cudaStream_t s);
+int ts2d_launch_export_geometry3d(int P, GeomState gs, float *v_view, float *normal_view, float *depth, float *rgb, uint8_t *clamped,
+                                  uint32_t *tiles_touched, uint32_t *rect_min, uint32_t *rect_max, cudaStream_t s);
 int ts2d_launch_render_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
                            ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s);
 int ts2d_launch_preprocess_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, const int32_t *radii, GeomState gs,

@@ -1,0 +1,148 @@
+// ts2d_sh.cuh -- spherical-harmonics colour (forward + backward) and the warp-cooperative row staging shared by the
+// per-triangle kernels of both primitives (ts2d_preprocess.cu: 2D, ts2d_prim3d.cu: 3D).
+// Replaces computeRGBFromSH / computeRGBFromSHBackward (R2D/src/forward.cu:9-59, R2D/src/backward.cu:9-119; the 3D package
+// carries byte-identical copies, R3D/src/forward.cu:9-59, R3D/src/backward.cu:9-119).
+#pragma once
+#include "ts2d_common.cuh"
+
+static __constant__ float kC0 = 0.28209479177387814f;
+static __constant__ float kC1 = 0.4886025119029199f;
+static __constant__ float kC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f, 0.5462742152960396f};
+static __constant__ float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                             -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+__device__ __forceinline__ f3 ld3(const float *p) { return mk3(p[0], p[1], p[2]); }
+
+// ---- warp-cooperative staging of per-triangle rows (SH coefficients / SH gradients) ----------------------------
+// A thread owns one triangle but its row is 3M floats (192 B at M = 16): per-thread scalar access puts 32 different
+// cache lines behind every load/store instruction.  Instead the warp moves its 32 rows -- one contiguous 32*3M-float
+// block -- with coalesced 16-byte accesses through a shared-memory tile whose row stride (3M + 4 floats) makes the
+// per-thread float4 accesses bank-conflict free.  Used when 3M is a multiple of 4 (M = 4, 8, 12, 16).
+__device__ __forceinline__ void warp_rows_load(const float *__restrict__ g, float *tile, int q /*float4 per row*/, int rs4 /*tile row stride in float4*/,
+                                               int nrows, int lane)
+{
+    const float4 *g4 = reinterpret_cast<const float4 *>(g);
+    float4 *t4 = reinterpret_cast<float4 *>(tile);
+    int r = lane / q, c = lane - r * q;
+    const int dr = 32 / q, dc = 32 - dr * q;
+    for (int e = lane; e < nrows * q; e += 32) {
+        t4[r * rs4 + c] = __ldg(g4 + e);
+        r += dr;
+        c += dc;
+        if (c >= q) { c -= q; r++; }
+    }
+}
+__device__ __forceinline__ void warp_rows_store(float *__restrict__ g, const float *tile, int q, int rs4, int nrows, int lane)
+{
+    float4 *g4 = reinterpret_cast<float4 *>(g);
+    const float4 *t4 = reinterpret_cast<const float4 *>(tile);
+    int r = lane / q, c = lane - r * q;
+    const int dr = 32 / q, dc = 32 - dr * q;
+    for (int e = lane; e < nrows * q; e += 32) {
+        g4[e] = t4[r * rs4 + c];
+        r += dr;
+        c += dc;
+        if (c >= q) { c -= q; r++; }
+    }
+}
+static inline bool ts2d_rows_tileable(int M, const void *a, const void *b)
+{
+    return M > 0 && (3 * M) % 4 == 0 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0;
+}
+
+// Real SH basis (degree <= 3) times per-triangle coefficients, +0.5, clamp at 0 with mask.
+__device__ __forceinline__ f3 sh_colour(int deg, const float *sh, f3 pos, f3 cam, uint8_t &mask)
+{
+    f3 dir = pos - cam;
+    dir = dir / len3(dir);
+    f3 rgb = kC0 * ld3(sh);
+    if (deg > 0) {
+        const float x = dir.x, y = dir.y, z = dir.z;
+        rgb = rgb - kC1 * y * ld3(sh + 3) + kC1 * z * ld3(sh + 6) - kC1 * x * ld3(sh + 9);
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            rgb = rgb + kC2[0] * xy * ld3(sh + 12) + kC2[1] * yz * ld3(sh + 15) + kC2[2] * (2.0f * zz - xx - yy) * ld3(sh + 18) +
+                  kC2[3] * xz * ld3(sh + 21) + kC2[4] * (xx - yy) * ld3(sh + 24);
+            if (deg > 2) {
+                rgb = rgb + kC3[0] * y * (3.0f * xx - yy) * ld3(sh + 27) + kC3[1] * xy * z * ld3(sh + 30) +
+                      kC3[2] * y * (4.0f * zz - xx - yy) * ld3(sh + 33) + kC3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * ld3(sh + 36) +
+                      kC3[4] * x * (4.0f * zz - xx - yy) * ld3(sh + 39) + kC3[5] * z * (xx - yy) * ld3(sh + 42) +
+                      kC3[6] * x * (xx - 3.0f * yy) * ld3(sh + 45);
+            }
+        }
+    }
+    rgb = rgb + 0.5f;
+    mask = (uint8_t)((rgb.x < 0 ? 1 : 0) | (rgb.y < 0 ? 2 : 0) | (rgb.z < 0 ? 4 : 0));
+    return mk3(fmaxf(rgb.x, 0.0f), fmaxf(rgb.y, 0.0f), fmaxf(rgb.z, 0.0f));
+}
+
+__device__ __forceinline__ f3 grad_norm3(f3 v, f3 dv)
+{
+    const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
+    const float n = sqrtf(sum2);
+    const float inv = 1.0f / (n * n * n);
+    return mk3(((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * inv,
+               (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * inv,
+               (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * inv);
+}
+
+__device__ __forceinline__ void st3(float *p, f3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+
+// SH backward: writes dL/dsh for the active coefficients, zero for the inactive ones, returns dL/dcentre.
+__device__ __forceinline__ f3 sh_colour_bwd(int deg, int M, const float *sh, f3 pos, f3 cam, uint8_t mask, f3 g, float *out)
+{
+    const f3 dir_orig = pos - cam;
+    const f3 dir = dir_orig / len3(dir_orig);
+    g.x *= (mask & 1) ? 0.0f : 1.0f;
+    g.y *= (mask & 2) ? 0.0f : 1.0f;
+    g.z *= (mask & 4) ? 0.0f : 1.0f;
+    f3 dx = mk3(0, 0, 0), dy = mk3(0, 0, 0), dz = mk3(0, 0, 0);
+    const float x = dir.x, y = dir.y, z = dir.z;
+    // `out` may alias `sh` (the tiled kernel back-propagates in place in shared memory): within every band the
+    // coefficients are read before the band's gradients are written.
+    st3(out, kC0 * g);
+    int written = 1;
+    if (deg > 0) {
+        dx = -kC1 * ld3(sh + 9);
+        dy = -kC1 * ld3(sh + 3);
+        dz = kC1 * ld3(sh + 6);
+        st3(out + 3, (-kC1 * y) * g);
+        st3(out + 6, (kC1 * z) * g);
+        st3(out + 9, (-kC1 * x) * g);
+        written = 4;
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            const f3 s4 = ld3(sh + 12), s5 = ld3(sh + 15), s6 = ld3(sh + 18), s7 = ld3(sh + 21), s8 = ld3(sh + 24);
+            st3(out + 12, (kC2[0] * xy) * g);
+            st3(out + 15, (kC2[1] * yz) * g);
+            st3(out + 18, (kC2[2] * (2.f * zz - xx - yy)) * g);
+            st3(out + 21, (kC2[3] * xz) * g);
+            st3(out + 24, (kC2[4] * (xx - yy)) * g);
+            dx = dx + (kC2[0] * y * s4 + kC2[2] * 2.f * -x * s6 + kC2[3] * z * s7 + kC2[4] * 2.f * x * s8);
+            dy = dy + (kC2[0] * x * s4 + kC2[1] * z * s5 + kC2[2] * 2.f * -y * s6 + kC2[4] * 2.f * -y * s8);
+            dz = dz + (kC2[1] * y * s5 + kC2[2] * 2.f * 2.f * z * s6 + kC2[3] * x * s7);
+            written = 9;
+            if (deg > 2) {
+                const f3 s9 = ld3(sh + 27), s10 = ld3(sh + 30), s11 = ld3(sh + 33), s12 = ld3(sh + 36), s13 = ld3(sh + 39), s14 = ld3(sh + 42),
+                         s15 = ld3(sh + 45);
+                st3(out + 27, (kC3[0] * y * (3.f * xx - yy)) * g);
+                st3(out + 30, (kC3[1] * xy * z) * g);
+                st3(out + 33, (kC3[2] * y * (4.f * zz - xx - yy)) * g);
+                st3(out + 36, (kC3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * g);
+                st3(out + 39, (kC3[4] * x * (4.f * zz - xx - yy)) * g);
+                st3(out + 42, (kC3[5] * z * (xx - yy)) * g);
+                st3(out + 45, (kC3[6] * x * (xx - 3.f * yy)) * g);
+                dx = dx + (kC3[0] * s9 * 3.f * 2.f * xy + kC3[1] * s10 * yz + kC3[2] * s11 * -2.f * xy + kC3[3] * s12 * -3.f * 2.f * xz +
+                           kC3[4] * s13 * (-3.f * xx + 4.f * zz - yy) + kC3[5] * s14 * 2.f * xz + kC3[6] * s15 * 3.f * (xx - yy));
+                dy = dy + (kC3[0] * s9 * 3.f * (xx - yy) + kC3[1] * s10 * xz + kC3[2] * s11 * (-3.f * yy + 4.f * zz - xx) +
+                           kC3[3] * s12 * -3.f * 2.f * yz + kC3[4] * s13 * -2.f * xy + kC3[5] * s14 * -2.f * yz + kC3[6] * s15 * -3.f * 2.f * xy);
+                dz = dz + (kC3[1] * s10 * xy + kC3[2] * s11 * 4.f * 2.f * yz + kC3[3] * s12 * 3.f * (2.f * zz - xx - yy) +
+                           kC3[4] * s13 * 4.f * 2.f * xz + kC3[5] * s14 * (xx - yy));
+                written = 16;
+            }
+        }
+    }
+    for (int k = 3 * written; k < 3 * M; k++) out[k] = 0.0f;
+    const f3 gdir = mk3(dot3(g, dx), dot3(g, dy), dot3(g, dz));
+    return grad_norm3(dir_orig, gdir);
+}
