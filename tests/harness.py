@@ -33,8 +33,23 @@ GOLDEN_SCENES = {
 }
 
 
-def golden_scene(name: str) -> Scene:
-    return make_scene(name, **GOLDEN_SCENES[name])
+# Scenes the reference's SECOND rasterizer package (diff_triangle_rasterization_3D) was run on:
+# tests/golden/3d_<name>.npz.  The 3D primitive is what the shipped *_mesh configs use (BASELINE configs[3], configs[4]).
+GOLDEN_SCENES_3D = {
+    "sh0_plain": dict(P=2000, width=128, height=96, sh_degree=0, rich_info=False, seed=21),
+    "sh3_rich": dict(P=2500, width=160, height=112, sh_degree=3, rich_info=True, geometry_grads=True, seed=22, rho_px=3.5),
+    "feat_cull_gamma": dict(P=1500, width=100, height=70, use_feature=True, channels=3, rich_info=True, geometry_grads=True,
+                            back_culling=True, gamma=2.5, seed=23, rho_px=4.0),
+    "mesh_gamma7_dense": dict(P=3000, width=80, height=64, sh_degree=0, rich_info=True, geometry_grads=True, gamma=7.0, seed=24, rho_px=6.0),
+}
+
+
+def golden_scene(name: str, primitive: str = "2D") -> Scene:
+    return make_scene(name, **(GOLDEN_SCENES if primitive == "2D" else GOLDEN_SCENES_3D)[name])
+
+
+def golden_path(name: str, primitive: str = "2D") -> str:
+    return os.path.join(GOLDEN_DIR, (name if primitive == "2D" else "3d_" + name) + ".npz")
 
 
 def _np(t):
@@ -76,14 +91,14 @@ def _pack_common(sc, fwd, bwd):
 
 
 # ------------------------------------------------------------------------------------------ ours
-def run_ours(sc: Scene, dev, backward: bool = True) -> dict:
+def run_ours(sc: Scene, dev, backward: bool = True, primitive: str = "2D") -> dict:
     import ctypes as C
 
     from triangle_splatting_b200 import _C, _lib
 
     s = sc.to(dev)
-    fwd = _C.rasterize_triangles(*_fwd_args(s))
-    bwd = _C.rasterize_triangles_backward(*_bwd_args(s, fwd, dev)) if backward else None
+    fwd = _C.rasterize_triangles(*_fwd_args(s), primitive=primitive)
+    bwd = _C.rasterize_triangles_backward(*_bwd_args(s, fwd, dev), primitive=primitive) if backward else None
     out = _pack_common(s, fwd, bwd)
     # decode our opaque state through the C ABI export calls
     lib = _lib.load()
@@ -93,16 +108,21 @@ def run_ours(sc: Scene, dev, backward: bool = True) -> dict:
     if P == 0:
         return out
     mk = lambda shape, dt: torch.zeros(shape, device=dev, dtype=dt)
-    t = dict(v2d=mk((P, 3, 2), torch.float32), area2=mk((P,), torch.float32), normal_view=mk((P, 3), torch.float32),
-             v_depth=mk((P, 3), torch.float32), tri_depth=mk((P,), torch.float32), rgb=mk((P, 3), torch.float32),
+    t = dict(normal_view=mk((P, 3), torch.float32), tri_depth=mk((P,), torch.float32), rgb=mk((P, 3), torch.float32),
              clamped=mk((P, 3), torch.uint8), tiles_touched=mk((P,), torch.int32), rect_min=mk((P, 2), torch.int32),
              rect_max=mk((P, 2), torch.int32))
     p = lambda x: C.c_void_p(x.data_ptr()) if x.numel() else None
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     rich = s.rich_info
-    _lib.check(lib.ts2d_export_geometry(p(gb), P, p(t["v2d"]), p(t["area2"]), p(t["normal_view"]) if rich else None,
-                                        p(t["v_depth"]) if rich else None, p(t["tri_depth"]), p(t["rgb"]), p(t["clamped"]), p(t["tiles_touched"]),
-                                        p(t["rect_min"]), p(t["rect_max"]), stream), "export_geometry")
+    if primitive == "3D":
+        t["v_view"] = mk((P, 3, 3), torch.float32)
+        _lib.check(lib.ts2d_export_geometry3d(p(gb), P, p(t["v_view"]), p(t["normal_view"]), p(t["tri_depth"]), p(t["rgb"]), p(t["clamped"]),
+                                              p(t["tiles_touched"]), p(t["rect_min"]), p(t["rect_max"]), stream), "export_geometry3d")
+    else:
+        t.update(v2d=mk((P, 3, 2), torch.float32), area2=mk((P,), torch.float32), v_depth=mk((P, 3), torch.float32))
+        _lib.check(lib.ts2d_export_geometry(p(gb), P, p(t["v2d"]), p(t["area2"]), p(t["normal_view"]) if rich else None,
+                                            p(t["v_depth"]) if rich else None, p(t["tri_depth"]), p(t["rgb"]), p(t["clamped"]), p(t["tiles_touched"]),
+                                            p(t["rect_min"]), p(t["rect_max"]), stream), "export_geometry")
     gx, gy = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
     keys = torch.zeros((max(R, 1),), device=dev, dtype=torch.int64)
     plist = torch.zeros((max(R, 1),), device=dev, dtype=torch.int32)
@@ -122,10 +142,10 @@ def run_ours(sc: Scene, dev, backward: bool = True) -> dict:
 
 
 # ------------------------------------------------------------------------------- live reference
-def load_reference():
+def load_reference(primitive: str = "2D"):
     from oracle import build_ref
 
-    return build_ref.load()
+    return build_ref.load(primitive)
 
 
 def _carve(buf: torch.Tensor, specs):
@@ -143,9 +163,16 @@ def _carve(buf: torch.Tensor, specs):
     return out
 
 
-def run_reference(sc: Scene, dev, backward: bool = True, ref=None) -> dict:
-    ref = ref or load_reference()
+def run_reference(sc: Scene, dev, backward: bool = True, ref=None, primitive: str = "2D") -> dict:
+    """`ref` must be the module of the matching package (load_reference(primitive))."""
+    ref = ref or load_reference(primitive)
     assert ref is not None, "oracle/_ref not built"
+    if primitive == "3D" and not sc.rich_info:
+        # Reference bug: with rich_info=False the 3D backward reads dL_dnormal_view from an EMPTY tensor
+        # (R3D/src/rasterizer.cu:279-283 allocates {0}, R3D/src/backward.cu:176 dereferences it unconditionally)
+        # -> cudaErrorIllegalAddress on a B200.  Training always sets rich_info=True, so it is never hit there;
+        # for the non-rich scene only the reference's forward is run (ours supports the non-rich backward).
+        backward = False
     s = sc.to(dev)
     fwd = ref.rasterize_triangles(*_fwd_args(s))
     torch.cuda.synchronize(dev)
@@ -165,15 +192,21 @@ def run_reference(sc: Scene, dev, backward: bool = True, ref=None) -> dict:
         return out
     gb, bb, ib = fwd[7], fwd[8], fwd[9]
     f32, u32, u8 = torch.float32, torch.int32, torch.uint8
-    g = _carve(gb, [("v1", f32, 2 * P), ("v2", f32, 2 * P), ("v3", f32, 2 * P), ("area2", f32, P), ("normal_view", f32, 3 * P),
-                    ("v_depth", f32, 3 * P), ("depth", f32, P), ("rgb", f32, 3 * P), ("clamped", u8, 3 * P), ("point_offsets", u32, P),
-                    ("tiles_touched", u32, P), ("rect_min", u32, 2 * P), ("rect_max", u32, 2 * P)])
+    if primitive == "3D":  # R3D/src/param_struct.h:44-75
+        g = _carve(gb, [("v1", f32, 3 * P), ("v2", f32, 3 * P), ("v3", f32, 3 * P), ("normal_view", f32, 3 * P), ("depth", f32, P),
+                        ("rgb", f32, 3 * P), ("clamped", u8, 3 * P), ("point_offsets", u32, P), ("tiles_touched", u32, P),
+                        ("rect_min", u32, 2 * P), ("rect_max", u32, 2 * P)])
+        out["v_view"] = np.stack([_np(g["v1"]).reshape(P, 3), _np(g["v2"]).reshape(P, 3), _np(g["v3"]).reshape(P, 3)], axis=1)
+    else:
+        g = _carve(gb, [("v1", f32, 2 * P), ("v2", f32, 2 * P), ("v3", f32, 2 * P), ("area2", f32, P), ("normal_view", f32, 3 * P),
+                        ("v_depth", f32, 3 * P), ("depth", f32, P), ("rgb", f32, 3 * P), ("clamped", u8, 3 * P), ("point_offsets", u32, P),
+                        ("tiles_touched", u32, P), ("rect_min", u32, 2 * P), ("rect_max", u32, 2 * P)])
+        out["v2d"] = np.stack([_np(g["v1"]).reshape(P, 2), _np(g["v2"]).reshape(P, 2), _np(g["v3"]).reshape(P, 2)], axis=1)
+        out["area2"] = _np(g["area2"])
+        out["v_depth"] = _np(g["v_depth"]).reshape(P, 3)
     N = W * H
     im = _carve(ib, [("ranges", u32, 2 * N), ("n_contrib", u32, N), ("final_T", f32, N)])
-    out["v2d"] = np.stack([_np(g["v1"]).reshape(P, 2), _np(g["v2"]).reshape(P, 2), _np(g["v3"]).reshape(P, 2)], axis=1)
-    out["area2"] = _np(g["area2"])
     out["normal_view"] = _np(g["normal_view"]).reshape(P, 3)
-    out["v_depth"] = _np(g["v_depth"]).reshape(P, 3)
     out["tri_depth"] = _np(g["depth"])
     out["rgb"] = _np(g["rgb"]).reshape(P, 3)
     out["clamped"] = _np(g["clamped"]).reshape(P, 3)
@@ -195,7 +228,7 @@ def run_reference(sc: Scene, dev, backward: bool = True, ref=None) -> dict:
 
 
 # --------------------------------------------------------------------------------------- oracle
-def run_oracle(sc: Scene, kind: str = "f32", backward: bool = True) -> dict:
+def run_oracle(sc: Scene, kind: str = "f32", backward: bool = True, primitive: str = "2D") -> dict:
     from oracle.oracle import Oracle
 
     o = Oracle(kind)
@@ -203,12 +236,12 @@ def run_oracle(sc: Scene, kind: str = "f32", backward: bool = True) -> dict:
     kw.pop("debug")
     kw = {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in kw.items()}
     st = o.forward(**kw, vertex=sc.vertex.numpy(), shs=None if sc.shs is None else sc.shs.numpy(),
-                   feature=None if sc.feature is None else sc.feature.numpy(), opacity=sc.opacity.numpy())
+                   feature=None if sc.feature is None else sc.feature.numpy(), opacity=sc.opacity.numpy(), primitive=primitive)
     out = dict(num_rendered=np.int64(st["num_rendered"]), out_feature=st["out_feature"], radii=st["radii"])
     if sc.rich_info:
         out.update(depth=st["out_depth"], normal=st["out_normal"], contrib_sum=st["contrib_sum"], contrib_max=st["contrib_max"])
-    for k in ("v2d", "area2", "normal_view", "v_depth", "rgb", "clamped", "tiles_touched", "rect_min", "rect_max", "keys", "point_list",
-              "ranges", "n_contrib", "final_T"):
+    for k in (("v_view",) if primitive == "3D" else ("v2d", "area2", "v_depth")) + (
+            "normal_view", "rgb", "clamped", "tiles_touched", "rect_min", "rect_max", "keys", "point_list", "ranges", "n_contrib", "final_T"):
         out[k] = st[k]
     out["tri_depth"] = st["depth"]
     if backward:
@@ -222,7 +255,7 @@ def run_oracle(sc: Scene, kind: str = "f32", backward: bool = True) -> dict:
 
 # ------------------------------------------------------------------------------------ comparing
 INT_KEYS = ("num_rendered", "radii", "tiles_touched", "rect_min", "rect_max", "keys", "point_list", "ranges", "n_contrib", "clamped")
-STATE_FLOAT_KEYS = ("v2d", "area2", "normal_view", "v_depth", "tri_depth", "rgb")
+STATE_FLOAT_KEYS = ("v2d", "area2", "v_view", "normal_view", "v_depth", "tri_depth", "rgb")
 IMAGE_KEYS = ("out_feature", "depth", "normal", "contrib_sum", "contrib_max", "final_T")
 GRAD_KEYS = ("dL_dvertex", "dL_dcenter2D", "dL_dshs", "dL_dfeature", "dL_dopacity")
 
