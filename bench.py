@@ -119,8 +119,12 @@ def scene_for(config: str):
 class OursStep:
     """fwd+bwd through TriangleRasterizer (autograd) exactly as diff_recon's TriangleRenderer calls it."""
 
-    def __init__(self, sc, dev):
-        from triangle_splatting_b200 import TriangleRasterizationSettings, TriangleRasterizer
+    def __init__(self, sc, dev, primitive="2D"):
+        from triangle_splatting_b200 import TriangleRasterizationSettings
+        if primitive == "3D":
+            from triangle_splatting_b200 import TriangleRasterizer3D as TriangleRasterizer
+        else:
+            from triangle_splatting_b200 import TriangleRasterizer
 
         self.sc = sc.to(dev)
         self.dev = dev
@@ -249,7 +253,7 @@ def pinned_host_buffers(sc, all_host: bool):
 
 
 # --------------------------------------------------------------------------------------------- CPU baseline
-def cpu_oracle_baseline(sc, tile_step=None, budget_s=20.0):
+def cpu_oracle_baseline(sc, tile_step=None, budget_s=20.0, primitive="2D"):
     """Oracle port (oracle/ts2d_oracle.c, OpenMP over tiles) on a bounded sample: full per-triangle stages + binning,
     composite fwd+bwd on every `tile_step`-th tile, extrapolated to the whole frame."""
     import numpy as np
@@ -260,7 +264,7 @@ def cpu_oracle_baseline(sc, tile_step=None, budget_s=20.0):
     kw = sc.settings_kwargs()
     kw.pop("debug")
     kw = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in kw.items()}
-    arrs = dict(vertex=sc.vertex.cpu().numpy(), shs=sc.shs.cpu().numpy(), feature=None, opacity=sc.opacity.cpu().numpy())
+    arrs = dict(vertex=sc.vertex.cpu().numpy(), shs=sc.shs.cpu().numpy(), feature=None, opacity=sc.opacity.cpu().numpy(), primitive=primitive)
     t0 = time.perf_counter()
     st = o.forward(**kw, **arrs, stages="bin")
     t_geom = time.perf_counter() - t0
@@ -345,6 +349,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3")
+    ap.add_argument("--primitive", default="2D", choices=["2D", "3D"],
+                    help="2D: diff_triangle_rasterization_2D (the north-star path); 3D: diff_triangle_rasterization_3D (the *_mesh configs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
@@ -360,13 +366,13 @@ def main():
     sc = scene_for(a.config)
     cfg = {"workload": f"{a.config}: P={sc.P} triangles, {sc.cam['image_width']}x{sc.cam['image_height']}, SH degree {sc.sh_degree} "
                        f"(M={sc.shs.shape[1]}), rich_info={sc.rich_info}, gamma={sc.gamma}, fwd+bwd",
-           "P": sc.P, "width": sc.cam["image_width"], "height": sc.cam["image_height"], "sh_degree": sc.sh_degree,
+           "primitive": a.primitive, "P": sc.P, "width": sc.cam["image_width"], "height": sc.cam["image_height"], "sh_degree": sc.sh_degree,
            "l2_policy": "inputs larger than L2 (SH 288 MB + 120 MB raster records + instance lists >> 126 MB L2); no explicit flush",
            "parallelism": "single GPU" if a.gpus == 1 else f"image-space tile sharding x{a.gpus} (tile % N == rank) + NCCL all-reduce"}
 
     if not torch.cuda.is_available():
         if a.impl == "reference" and rank == 0:
-            cb = cpu_oracle_baseline(sc)
+            cb = cpu_oracle_baseline(sc, primitive=a.primitive)
             line = dict(base, impl="reference", value=cb["value"], ms_per_step=1e3 / cb["value"], config=cfg, cpu_baseline=cb,
                         e2e={"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0,
                         note="no CUDA device and no loadable reference extension: CPU oracle port on a bounded sample")
@@ -385,11 +391,11 @@ def main():
 
         ref = None
         try:
-            ref = build_ref.load()
+            ref = build_ref.load(a.primitive)
         except Exception as ex:  # noqa: BLE001
             print(f"[bench] reference extension failed to load: {ex}", file=sys.stderr)
         if ref is None:
-            cb = cpu_oracle_baseline(sc)
+            cb = cpu_oracle_baseline(sc, primitive=a.primitive)
             line = dict(base, impl="reference", value=cb["value"], ms_per_step=1e3 / cb["value"], config=cfg, cpu_baseline=cb, n_gpus=1,
                         e2e={"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0,
                         note="oracle/_ref not loadable: CPU oracle port on a bounded sample")
@@ -436,7 +442,7 @@ def main():
     from triangle_splatting_b200 import _lib
 
     lib = _lib.load()
-    step = OursStep(sc, dev)
+    step = OursStep(sc, dev, a.primitive)
     out = step()  # first call: also gives V, R for the byte model
     torch.cuda.synchronize(dev)
     radii = out[1]
@@ -465,7 +471,7 @@ def main():
         s, c = step.sc, step.sc.cam
         fa = (c["image_width"], c["image_height"], c["tanfovx"], c["tanfovy"], c["viewmatrix"], c["projmatrix"], c["campos"], s.sh_degree,
               s.gamma, 1.0, s.background_depth, s.background, s.vertex, s.shs, torch.Tensor([]), s.opacity, s.back_culling, s.rich_info, False)
-        R_local = int(tsC.rasterize_triangles(*fa, shard=(rank, world) if world > 1 else (0, 1))[0])
+        R_local = int(tsC.rasterize_triangles(*fa, shard=(rank, world) if world > 1 else (0, 1), primitive=a.primitive)[0])
     R_total = R_local * world if R_local is not None else None  # interleaved tiles: shards are balanced to <1%
 
     line = None
@@ -480,7 +486,7 @@ def main():
         traffic, traffic_src = None, None  # DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this build
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            if world == 1 and cfg["workload"].startswith(tj["workload"]):
+            if world == 1 and a.primitive == "2D" and cfg["workload"].startswith(tj["workload"]):
                 traffic, traffic_src = tj["bytes_per_launch"].get(dom), tj["source"]
         except (OSError, KeyError, ValueError):
             pass
@@ -521,7 +527,7 @@ def main():
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = cpu_oracle_baseline(sc)
+            line["cpu_baseline"] = cpu_oracle_baseline(sc, primitive=a.primitive)
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
     if rank == 0:

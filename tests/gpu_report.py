@@ -26,29 +26,32 @@ KEYS = ("out_feature", "depth", "normal", "contrib_sum", "contrib_max", "final_T
 
 def main():
     dev = torch.device("cuda:0")
-    ref = harness.load_reference()
-    out = open(os.path.join(ROOT, "gpurun_out", "report.txt"), "w")
+    prim = "3D" if "3D" in sys.argv[1:] else "2D"  # `python tests/gpu_report.py 3D` -> gpurun_out/report_3d.txt
+    ref = harness.load_reference(prim)
+    out = open(os.path.join(ROOT, "gpurun_out", "report.txt" if prim == "2D" else "report_3d.txt"), "w")
 
     def emit(*a):
         s = " ".join(str(x) for x in a)
         print(s)
         out.write(s + "\n")
 
-    scenes = {n: harness.golden_scene(n) for n in harness.GOLDEN_SCENES}
+    scenes = {n: harness.golden_scene(n, prim) for n in (harness.GOLDEN_SCENES if prim == "2D" else harness.GOLDEN_SCENES_3D)}
+    if prim == "3D":
+        scenes.pop("sh0_plain")  # rich_info=False: the reference's 3D backward crashes (harness.run_reference)
     scenes["mid_sh3_rich_200k_800x600"] = make_scene("mid", 200_000, 800, 600, sh_degree=3, rich_info=True, geometry_grads=True, seed=21)
     scenes["gamma7_ste_50k_640x480"] = make_scene("g7", 50_000, 640, 480, sh_degree=0, rich_info=True, gamma=7.0, opacity_ste=0.3, seed=22)
     for name, sc in scenes.items():
         runs = {}
         if ref is not None:
-            runs["refA"] = harness.run_reference(sc, dev, ref=ref)
-            runs["refB"] = harness.run_reference(sc, dev, ref=ref)
+            runs["refA"] = harness.run_reference(sc, dev, ref=ref, primitive=prim)
+            runs["refB"] = harness.run_reference(sc, dev, ref=ref, primitive=prim)
         old = _C.set_exact(True)
-        runs["exact"] = harness.run_ours(sc, dev)
+        runs["exact"] = harness.run_ours(sc, dev, primitive=prim)
         _C.set_exact(False)
-        runs["fast"] = harness.run_ours(sc, dev)
+        runs["fast"] = harness.run_ours(sc, dev, primitive=prim)
         _C.set_exact(old)
         if sc.P <= 200000:
-            runs["f64"] = harness.run_oracle(sc, "f64")
+            runs["f64"] = harness.run_oracle(sc, "f64", primitive=prim)
         base = runs.get("refA", runs["exact"])
         emit(f"== {name}: P={sc.P} R={int(base['num_rendered'])} visible={int((base['radii'] > 0).sum())} rich={sc.rich_info} gamma={sc.gamma}")
         for who in ("exact", "fast"):

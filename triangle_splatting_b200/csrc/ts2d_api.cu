@@ -257,7 +257,9 @@ int ts2d_forward_render(const ts2d_camera *cam, const ts2d_geometry *geom, const
     if (carve_image(image_state, cam->width, cam->height, &is) > image_state_bytes) return TS2D_E_STATE_SIZE;
     cudaStream_t s = (cudaStream_t)stream;
     TS2D_STAGE(TS2D_STAGE_BINNING, ts2d_launch_binning(cam, geom, flags, num_rendered, gs, bs, is, s));
-    if (flags->primitive == TS2D_PRIMITIVE_3D)
+    if (flags->primitive == TS2D_PRIMITIVE_3D && ts2d_use_fast(geom, flags))
+        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render3d_fwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, out, s));
+    else if (flags->primitive == TS2D_PRIMITIVE_3D)
         TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render3d_fwd(cam, geom, flags, gs, bs.tval[1], is, out, s));
     else if (ts2d_use_fast(geom, flags))
         TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, out, s));
@@ -285,7 +287,9 @@ int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_
     carve_binning(const_cast<void *>(binning_state), num_rendered, &bs);
     carve_image(const_cast<void *>(image_state), cam->width, cam->height, &is);
     cudaStream_t s = (cudaStream_t)stream;
-    if (flags->primitive == TS2D_PRIMITIVE_3D)
+    if (flags->primitive == TS2D_PRIMITIVE_3D && ts2d_use_fast(geom, flags))
+        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render3d_bwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, loss, (float *)scratch, s));
+    else if (flags->primitive == TS2D_PRIMITIVE_3D)
         TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render3d_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
     else if (ts2d_use_fast(geom, flags))
         TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, loss, (float *)scratch, s));
@@ -318,7 +322,9 @@ int ts2d_backward_composite(const ts2d_camera *cam, const ts2d_geometry *geom, c
     carve_binning(const_cast<void *>(binning_state), num_rendered, &bs);
     carve_image(const_cast<void *>(image_state), cam->width, cam->height, &is);
     cudaStream_t s = (cudaStream_t)stream;
-    if (flags->primitive == TS2D_PRIMITIVE_3D)
+    if (flags->primitive == TS2D_PRIMITIVE_3D && ts2d_use_fast(geom, flags))
+        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render3d_bwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, loss, (float *)scratch, s));
+    else if (flags->primitive == TS2D_PRIMITIVE_3D)
         TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render3d_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
     else if (ts2d_use_fast(geom, flags))
         TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, loss, (float *)scratch, s));

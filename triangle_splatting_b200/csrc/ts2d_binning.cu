@@ -17,7 +17,7 @@
 // the same library for its sort/scan, rasterizer.cu:186,211); everything else is hand-written.
 #include <cub/cub.cuh>
 
-#include "ts2d_fast.cuh"
+#include "ts2d_prim3d.cuh"
 
 namespace {
 
@@ -29,12 +29,22 @@ struct GatherTiles {
 // Instance key = (tile id << 8) | sub-tile coverage mask.  The tile sort orders on the tile bits only and carries the mask
 // along for free; the fast composite kernels read it instead of re-deriving coverage from the raster record (once per
 // instance here instead of once per instance per pass there).  With MASKS == false (mirror kernels) the mask byte is 0xFF.
-template <bool MASKS>
-__device__ __forceinline__ uint32_t instance_key(uint32_t tile, int gx, uint32_t id, const float4 *__restrict__ rec0, const GammaK gk)
+// MASKS: 0 = none (mirror kernels), 1 = 2D primitive (subtile_mask, ts2d_fast.cuh), 2 = 3D primitive (subtile_mask3d, ts2d_prim3d.cuh)
+struct EmitCam {
+    int W, H;
+    float tfx, tfy;
+};
+template <int MASKS>
+__device__ __forceinline__ uint32_t instance_key(uint32_t tile, int gx, uint32_t id, const float4 *__restrict__ rec0, const GammaK gk, const EmitCam cam)
 {
-    if (!MASKS) return (tile << TS2D_MASK_BITS) | 0xFFu;
+    if (MASKS == 0) return (tile << TS2D_MASK_BITS) | 0xFFu;
     const float4 r0 = __ldg(rec0 + 3 * (size_t)id), r1 = __ldg(rec0 + 3 * (size_t)id + 1);
     const uint32_t ty = tile / (uint32_t)gx, tx = tile - ty * (uint32_t)gx;
+    if (MASKS == 2) {
+        const Tri3 t = unpack3(r0, r1, __ldg(rec0 + 3 * (size_t)id + 2));
+        return (tile << TS2D_MASK_BITS) |
+               subtile_mask3d(t, (float)(tx * TS2D_TILE), (float)(ty * TS2D_TILE), cam.W, cam.H, cam.tfx, cam.tfy, gk.gamma, gk.is_one);
+    }
     return (tile << TS2D_MASK_BITS) | subtile_mask(r0, r1, r1.z, (float)(tx * TS2D_TILE), (float)(ty * TS2D_TILE), gk);
 }
 
@@ -43,9 +53,9 @@ __device__ __forceinline__ uint32_t instance_key(uint32_t tile, int gx, uint32_t
 // 32 scan values held in the warp.  Same output as rasterizer.cu:63-74 in depth order, with coalesced stores and no
 // divergence on the rect size.  SHARDED: only the tiles this rank owns (tile % world == rank) count and are written; the
 // k-th owned tile is found row by row (each row holds every world-th tile starting at a closed-form first column).
-template <bool MASKS, bool SHARDED>
+template <int MASKS, bool SHARDED>
 __global__ void __launch_bounds__(TS2D_BLOCK)
-k_emit_warp(int P, int gx, float gamma, int shard_rank, int shard_world, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
+k_emit_warp(int P, int gx, float gamma, EmitCam cam, int shard_rank, int shard_world, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
             const ushort4 *__restrict__ rect, const uint32_t *__restrict__ offs, const float4 *__restrict__ rec0, uint32_t *__restrict__ tkey,
             uint32_t *__restrict__ tval)
 {
@@ -100,7 +110,7 @@ k_emit_warp(int P, int gx, float gamma, int shard_rank, int shard_world, const u
                     k -= cnt;
                 }
             }
-            tkey[i] = instance_key<MASKS>(tile, gx, t_id, rec0, gk);
+            tkey[i] = instance_key<MASKS>(tile, gx, t_id, rec0, gk, cam);
             tval[i] = t_id;
         }
     }
@@ -194,15 +204,18 @@ int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts
     const int P = g->P;
     TS2D_CUDA_TRY(cudaMemsetAsync(is.ranges, 0, sizeof(uint2) * (size_t)n_tiles, s));
     if (R == 0) return 0;
-    const bool masks = ts2d_use_fast(g, f);
+    const int masks = !ts2d_use_fast(g, f) ? 0 : (f->primitive == TS2D_PRIMITIVE_3D ? 2 : 1);
     const int blocks = (P + TS2D_BLOCK - 1) / TS2D_BLOCK;
-#define TS2D_EMIT_ARGS P, gx, g->gamma, f->shard_rank, f->shard_world, gs.ids2, gs.tiles, gs.rect, gs.offs, gs.rec0, bs.tkey[0], bs.tval[0]
+    const EmitCam ec = {cam->width, cam->height, cam->tan_fovx, cam->tan_fovy};
+#define TS2D_EMIT_ARGS P, gx, g->gamma, ec, f->shard_rank, f->shard_world, gs.ids2, gs.tiles, gs.rect, gs.offs, gs.rec0, bs.tkey[0], bs.tval[0]
     if (f->shard_world > 1) {
-        if (masks) k_emit_warp<true, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
-        else k_emit_warp<false, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
+        if (masks == 2) k_emit_warp<2, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
+        else if (masks == 1) k_emit_warp<1, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
+        else k_emit_warp<0, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
     } else {
-        if (masks) k_emit_warp<true, false><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
-        else k_emit_warp<false, false><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
+        if (masks == 2) k_emit_warp<2, false><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
+        else if (masks == 1) k_emit_warp<1, false><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
+        else k_emit_warp<0, false><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
     }
 #undef TS2D_EMIT_ARGS
     TS2D_CUDA_TRY(cudaGetLastError());

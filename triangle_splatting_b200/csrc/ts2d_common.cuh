@@ -197,10 +197,7 @@ int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
                                 const uint32_t *list, ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s);
 // The fast kernels cover the gamma range the trainer schedules (1..50, VanillaTS_model.py:549-554) with margin;
 // outside it (for gamma < 0.6 the ecc <= 10 cut starts to matter; gamma -> 0 makes ecc^(2 gamma) degenerate) the exact mirror kernels are used.
-static inline bool ts2d_use_fast(const ts2d_geometry *g, const ts2d_flags *f)
-{
-    return f->primitive == TS2D_PRIMITIVE_2D && !f->exact && g->gamma >= 0.6f && g->gamma <= 64.0f;
-}
+static inline bool ts2d_use_fast(const ts2d_geometry *g, const ts2d_flags *f) { return !f->exact && g->gamma >= 0.6f && g->gamma <= 64.0f; }
 // 3D primitive (ts2d_prim3d.cu)
 int ts2d_launch_preprocess3d(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, int32_t *radii, GeomState gs, cudaStream_t s);
 int ts2d_launch_render3d_fwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
@@ -209,6 +206,11 @@ int ts2d_launch_render3d_bwd(const ts2d_camera *cam, const ts2d_geometry *g, con
                              ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s);
 int ts2d_launch_preprocess3d_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, const int32_t *radii, GeomState gs,
                                  const float *gacc, const ts2d_backward_out *out, cudaStream_t s);
+// fast kernels of the 3D primitive (ts2d_prim3d_fast.cu); same roles as ts2d_launch_render_{fwd,bwd}_fast
+int ts2d_launch_render3d_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
+                                  const uint32_t *list, ImageState is, const ts2d_forward_out *out, cudaStream_t s);
+int ts2d_launch_render3d_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
+                                  const uint32_t *list, ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s);
 int ts2d_launch_export_geometry3d(int P, GeomState gs, float *v_view, float *normal_view, float *depth, float *rgb, uint8_t *clamped,
                                   uint32_t *tiles_touched, uint32_t *rect_min, uint32_t *rect_max, cudaStream_t s);
 int ts2d_launch_render_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,

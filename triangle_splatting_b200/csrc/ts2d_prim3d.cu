@@ -11,7 +11,7 @@
 //
 // Record layout (geometry state; 64 B per triangle in the two record arrays of GeomState):
 //   rec0[3i+0] = {v1v.x v1v.y v1v.z v2v.x}   rec0[3i+1] = {v2v.y v2v.z v3v.x v3v.y}   rec0[3i+2] = {v3v.z n.x n.y n.z}
-//   rec1[2i+0] = {r g b opacity}              (rec1[2i+1] unused)
+//   rec1[2i+0] = {r g b opacity}              rec1[2i+1] = {K_fwd, 1 / dot(n, n), K_bwd, -}  (fast kernels only; ts2d_prim3d.cuh)
 // with v_k_view = W2C v_k and n = (v2v - v1v) x (v3v - v1v), NOT normalised (R3D/src/forward.cu:94).
 //
 // Quirks of the reference that are kept on purpose (a drop-in must reproduce the reference's numbers):
@@ -23,13 +23,10 @@
 // (9 view-space vertex, 3 normal, 3 colour, 1 opacity -- exactly one 64 B accumulator line) are summed over the warp's
 // 32 pixels with a recursive-halving butterfly and leave as one 64 B RED burst per (warp, triangle) instead of the
 // reference's 16 scalar atomics per (pixel, triangle) (R3D/src/backward.cu:365,430-451).
+#include "ts2d_prim3d.cuh"
 #include "ts2d_sh.cuh"
 
 namespace {
-
-// R3D/src/auxiliary.h:35-43
-__device__ __forceinline__ float proj_to_pix(float v, int S) { return (v + 1.0f) * S * 0.5f - 0.5f; }
-__device__ __forceinline__ float pix_to_proj(float v, int S) { return (2.0f * v - S + 1.0f) / (float)(S); }
 
 // tiles of the rect [rx0, rx1) x [ry0, ry1) this rank owns (tile_id % world == rank)
 __device__ __forceinline__ uint32_t owned_tiles(uint32_t rx0, uint32_t ry0, uint32_t rx1, uint32_t ry1, int gx, int shard_rank, int shard_world)
@@ -109,6 +106,11 @@ k_preprocess3d(int W, int H, int P, int D, int M, int C, bool use_shs, int gx, i
         rec0[3 * (size_t)idx + 1] = make_float4(v2v.y, v2v.z, v3v.x, v3v.y);
         rec0[3 * (size_t)idx + 2] = make_float4(v3v.z, n.x, n.y, n.z);
         rec1[2 * (size_t)idx + 0] = make_float4(rgb.x, rgb.y, rgb.z, opacity[idx]);
+        {   // the two per-triangle subexpressions of the per-pair arithmetic (ts2d_prim3d.cuh: geo3), from the STORED values
+            Tri3 t;
+            t.v1 = v1v; t.v2 = v2v; t.v3 = v3v; t.n = n;
+            rec1[2 * (size_t)idx + 1] = make_float4(tri3_K<false>(t), tri3_inv_nn(t), tri3_K<true>(t), 0.0f);
+        }
         out_key = __float_as_uint(center_view.z);
         out_rect = make_ushort4((unsigned short)rx0, (unsigned short)ry0, (unsigned short)rx1, (unsigned short)ry1);
         out_tiles = owned_tiles(rx0, ry0, rx1, ry1, gx, shard_rank, shard_world);
@@ -120,55 +122,6 @@ k_preprocess3d(int W, int H, int P, int D, int M, int C, bool use_shs, int gx, i
     rect[idx] = out_rect;
     dkey[idx] = out_key;
     ids[idx] = (uint32_t)idx;
-}
-
-// ------------------------------------------------------------------------------------------------ per-pair evaluation
-struct Tri3 {
-    f3 v1, v2, v3, n;
-};
-__device__ __forceinline__ Tri3 unpack3(const float4 a, const float4 b, const float4 c)
-{
-    Tri3 t;
-    t.v1 = mk3(a.x, a.y, a.z);
-    t.v2 = mk3(a.w, b.x, b.y);
-    t.v3 = mk3(b.z, b.w, c.x);
-    t.n = mk3(c.y, c.z, c.w);
-    return t;
-}
-
-struct Pair3 {
-    float depth, inv_pn, inv_nn, a1, a2, a3, ecc, power, G, alpha;
-    f3 pv1, pv2, pv3;
-};
-
-// R3D/src/forward.cu:243-276 (BWD == false) and R3D/src/backward.cu:330-352 (BWD == true); same expression trees, so nvcc's
-// default FMA contraction treats them like the reference build.  Returns false where the reference `continue`s.
-template <bool BWD>
-__device__ __forceinline__ bool eval_pair3(const Tri3 &t, float op, float two_gamma, f3 ray, Pair3 &e)
-{
-    const float pn = dot3(ray, t.n);
-    if (fabsf(pn) < TS2D_EPS) return false;
-    if (BWD) {
-        e.inv_pn = 1.0f / pn;
-        e.depth = dot3(t.v1, t.n) * e.inv_pn;
-    } else {
-        e.depth = dot3(t.v1, t.n) / pn;
-    }
-    const f3 pview = e.depth * ray;
-    e.pv1 = t.v1 - pview;
-    e.pv2 = t.v2 - pview;
-    e.pv3 = t.v3 - pview;
-    e.inv_nn = 1.0f / dot3(t.n, t.n);
-    e.a1 = dot3(cross3(e.pv2, e.pv3), t.n) * e.inv_nn;
-    e.a2 = dot3(cross3(e.pv3, e.pv1), t.n) * e.inv_nn;
-    e.a3 = 1.0f - e.a1 - e.a2;
-    e.ecc = 1.0f - 3.0f * fminf(fminf(e.a1, e.a2), e.a3);
-    if (e.ecc < 0.0f || e.ecc > 10.0f) return false;
-    e.power = -0.5f * powf(e.ecc, two_gamma);
-    e.G = expf(e.power);
-    e.alpha = fminf(0.99f, op * e.G);
-    if (BWD) return !(e.G < 1.0f / 255.0f);
-    return !(e.alpha < 1.0f / 255.0f);
 }
 
 // ------------------------------------------------------------------------------------------------ K7 (3D)
@@ -223,7 +176,7 @@ k_render3d_fwd(int W, int H, int C, int gx, int shard_rank, int shard_world, int
                 const Tri3 t = unpack3(s_rec[4 * j], s_rec[4 * j + 1], s_rec[4 * j + 2]);
                 const float4 col = s_rec[4 * j + 3];
                 Pair3 e;
-                if (eval_pair3<false>(t, col.w, two_gamma, ray, e)) {
+                if (eval_pair3<false>(t, tri3_K<false>(t), tri3_inv_nn(t), col.w, two_gamma, ray, e)) {
                     hit = true;
                     contrib = e.alpha * T;
                     T *= (1.0f - e.alpha);
@@ -384,7 +337,7 @@ k_render3d_bwd(int W, int H, int C, int gx, int shard_rank, int shard_world, int
                 const float4 col = s_rec[4 * j + 3];
                 const float op = col.w;
                 Pair3 e;
-                if (eval_pair3<true>(t, op, two_gamma, ray, e)) {
+                if (eval_pair3<true>(t, tri3_K<true>(t), tri3_inv_nn(t), op, two_gamma, ray, e)) {
                     hit = true;
                     T /= (1.0f - e.alpha);
                     const float contrib = e.alpha * T;
