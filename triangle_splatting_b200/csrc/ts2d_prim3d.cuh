@@ -38,7 +38,7 @@ __device__ __forceinline__ Tri3 unpack3(const float4 a, const float4 b, const fl
 // The two per-triangle subexpressions of the per-pair arithmetic.  nvcc's FMA contraction of a 3-term dot product depends on
 // the surrounding code: the reference's sm_100 build computes dot(v1, n) as fma(n.z, v1.z, fma(n.y, v1.y, n.x * v1.x)) in the
 // forward kernel but as fma(v1.z, n.z, fma(v1.x, n.x, v1.y * n.y)) in the backward kernel, and dot(n, n) as
-// fma(n.z, n.z, fma(n.x, n.x, n.y * n.y)) in both (cuobjdump -sass of oracle/_ref/ts3d_ref_C*.so, FORWARD::renderCUDA /
+// fma(n.z, n.z, fma(n.x, n.x, n.y * n.y)) in both (cuobjdump -sass of the reference's own sm_100 build, FORWARD::renderCUDA /
 // BACKWARD::renderCUDA).  Everything here is therefore written with explicit round-to-nearest intrinsics.
 template <bool BWD>
 __device__ __forceinline__ float tri3_K(const Tri3 &t)

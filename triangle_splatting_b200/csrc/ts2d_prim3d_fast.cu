@@ -271,15 +271,18 @@ constexpr int B3_WROW = B3_NS * 32 + 1;
 
 // Per-warp shared-memory block:
 //   ENT   B3_CAP staged entries (F3_EB bytes each)
-//   F     per pixel {gp0 gp1 gp2 gd} {gn0 gn1 gn2 -}
+//   F     per pixel {gp0 gp1 gp2 gd} {gn0 gn1 gn2 -}; pixel p at p * 32 + (p >> 3) * 16 (the four quarters of phase 2 read
+//         four different rows with one LDS.128: the 16 B skew per quarter puts them on disjoint banks)
 //   W     panel [B3_ROWS][B3_WROW]: [scalar * 32 + pixel]
-//   INFO  per panel row {v1 v2.x}{v2.yz v3.xy}{v3.z n}{K 1/nn id -}   (64 B)
+//   INFO  per panel row {v1 v2.x}{v2.yz v3.xy}{v3.z n}{K 1/nn id -}   (64 B used, 80 B stride: conflict-free LDS.128 across rows)
+constexpr int B3_INFO = 80;
 struct Bwd3Layout {
     static constexpr int F = B3_CAP * F3_EB;
-    static constexpr int W = F + 32 * 32;
+    static constexpr int W = F + 32 * 32 + 64;
     static constexpr int INFO = W + ((B3_ROWS * B3_WROW * 4 + 15) / 16) * 16;
-    static constexpr int BYTES = INFO + B3_ROWS * 64;
+    static constexpr int BYTES = INFO + B3_ROWS * B3_INFO;
 };
+__device__ __forceinline__ uint32_t f_row(int p) { return (uint32_t)(p * 32 + (p >> 3) * 16); }
 
 __device__ __forceinline__ void red_add4_3d(float *addr, float a, float b, float c, float d)
 {
@@ -302,7 +305,7 @@ static __device__ __noinline__ void bwd3_flush_panel(uint32_t wb, uint32_t ib, u
     uint32_t id = 0;
     f3 e2 = mk3(0.f, 0.f, 0.f), e3 = e2, f2 = e2, f3v = e2;
     if (k < filled) {
-        const uint32_t ia = ib + 64 * k;
+        const uint32_t ia = ib + B3_INFO * k;
         t = unpack3(lds128(ia), lds128(ia + 16), lds128(ia + 32));
         const float4 kq = lds128(ia + 48);
         inv_nn = kq.y;
@@ -314,7 +317,7 @@ static __device__ __noinline__ void bwd3_flush_panel(uint32_t wb, uint32_t ib, u
         f3v = cross3(e3, t.n) * inv_nn;
         const float k2 = dot3(t.v1, f2), k3 = dot3(t.v1, f3v), k23 = k2 - k3;
         const uint32_t row = wb + (k * B3_WROW + quarter * 8) * 4;
-        const uint32_t frow = fb + quarter * 8 * 32;
+        const uint32_t frow = fb + f_row(quarter * 8);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const float c = lds32f(row + 4 * i), w1 = lds32f(row + 4 * (32 + i)), Dp = lds32f(row + 4 * (64 + i));
@@ -418,8 +421,8 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
             gd = dL_dout_depth[pix];
         }
     }
-    sts128(sb + L::F + 32 * lane, make_float4(gp0, gp1, gp2, gd));  // per-pixel table for phase 2
-    sts128(sb + L::F + 32 * lane + 16, make_float4(gn0, gn1, gn2, 0.0f));
+    sts128(sb + L::F + f_row(lane), make_float4(gp0, gp1, gp2, gd));  // per-pixel table for phase 2
+    sts128(sb + L::F + f_row(lane) + 16, make_float4(gn0, gn1, gn2, 0.0f));
     // upstream normal / depth gradients all zero in this sub-tile: their terms are exactly zero for the reference too
     const bool geo = RICH && __any_sync(0xffffffffu, gd != 0.0f || gn0 != 0.0f || gn1 != 0.0f || gn2 != 0.0f);
     const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last);
@@ -509,7 +512,7 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
             sts32f(row + 384, w_a1);
             sts32f(row + 512, w_a2);
             {   // row info for phase 2; every lane stores the same words
-                const uint32_t ia = sb + L::INFO + prow * 64;
+                const uint32_t ia = sb + L::INFO + prow * B3_INFO;
                 sts128(ia, e0);
                 sts128(ia + 16, e1);
                 sts128(ia + 32, e2);
