@@ -116,6 +116,31 @@ def scene_for(config: str):
 
 
 # --------------------------------------------------------------------------------------------- step builders
+_COPY_STREAMS = {}
+
+
+def prefetch_gt(host, dev):
+    """H2D copy of this step's ground-truth image on a side stream (inside the timed region, both arms): the image is not
+    needed before the loss, so the PCIe transfer overlaps the forward pass.  Returns a callable that makes the current
+    stream wait for the copy and hands back the device tensor."""
+    cs = _COPY_STREAMS.get(dev)
+    if cs is None:
+        cs = _COPY_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    cur = torch.cuda.current_stream(dev)
+    cs.wait_stream(cur)  # ordered after the previous step's consumers of the buffer the allocator may hand back
+    with torch.cuda.stream(cs):
+        gt = host["gt"].to(dev, non_blocking=True)
+    done = torch.cuda.Event()
+    done.record(cs)
+
+    def wait():
+        cur.wait_event(done)
+        gt.record_stream(cur)
+        return gt
+
+    return wait
+
+
 class OursStep:
     """fwd+bwd through TriangleRasterizer (autograd) exactly as diff_recon's TriangleRenderer calls it."""
 
@@ -149,10 +174,11 @@ class OursStep:
         """camera + GT image from pinned host memory -> forward -> L1 loss -> backward -> loss to host."""
         self.vertex.grad = self.shs.grad = self.opacity.grad = None
         cam = {k: host[k].to(self.dev, non_blocking=True) for k in ("viewmatrix", "projmatrix", "campos", "background")}
-        gt = host["gt"].to(self.dev, non_blocking=True)
+        gt = prefetch_gt(host, self.dev)
         kw = self.sc.settings_kwargs()
         kw.update(cam)
         out = self.forward(self.rast_cls(raster_settings=self.settings_cls(**kw)))
+        gt = gt()
         loss = (out[0] - gt).abs().mean()
         loss.backward()
         return float(loss.item())
@@ -228,13 +254,83 @@ class ReferenceStep:
     def e2e_step(self, host):
         self.vertex.grad = self.shs.grad = self.opacity.grad = None
         cam = {k: host[k].to(self.dev, non_blocking=True) for k in ("viewmatrix", "projmatrix", "campos", "background")}
-        gt = host["gt"].to(self.dev, non_blocking=True)
+        gt = prefetch_gt(host, self.dev)
         kw = self.sc.settings_kwargs()
         kw.update(cam)
         out = self.forward(kw)
+        gt = gt()
         loss = (out[0] - gt).abs().mean()
         loss.backward()
         return float(loss.item())
+
+
+def model_params(sc, dev):
+    """Raw model parameters for a scene (what VanillaTSModel holds): _vertex, _f_dc, _f_rest, _opacity (logits)."""
+    s = sc.to(dev)
+    leaf = lambda t: t.contiguous().clone().requires_grad_(True)
+    return dict(vertex=leaf(s.vertex), f_dc=leaf(s.shs[:, :1, :]), f_rest=leaf(s.shs[:, 1:, :]),
+                opacity=leaf(torch.logit(s.opacity.clamp(1e-6, 1 - 1e-6))))
+
+
+class ModelStepOurs:
+    """Model-level step through the fused front-end (SURVEY.md section 8f rank 2/3): raw parameters in, gradients w.r.t. them out;
+    sigmoid, SH concat, background depth and the training statistics happen inside K1 / K9 -- no host sync besides num_rendered."""
+
+    def __init__(self, sc, dev, primitive):
+        from triangle_splatting_b200 import TrainingStatistics, TriangleModelRasterizer, TriangleRasterizationSettings
+
+        self.sc, self.dev = sc.to(dev), dev
+        self.p = model_params(sc, dev)
+        self.stats = TrainingStatistics(sc.P, dev)
+        self.rast = TriangleModelRasterizer(TriangleRasterizationSettings(**self.sc.settings_kwargs()), primitive=primitive, statistics=self.stats)
+        self.g = [self.sc.grads["dL_dout_feature"], self.sc.grads["dL_dout_depth"], self.sc.grads["dL_dout_normal"]]
+
+    def __call__(self):
+        p = self.p
+        for t in p.values():
+            t.grad = None
+        c2d = torch.zeros((self.sc.P, 2), device=self.dev, requires_grad=True)
+        out = self.rast.forward(p["vertex"], c2d, p["opacity"], p["f_dc"], p["f_rest"] if p["f_rest"].shape[1] else None)
+        torch.autograd.backward([out[0], out[2], out[3]], self.g)
+
+
+class ModelStepReference:
+    """The reference's own flow for the same step: VanillaTS_model.py:608-647 preamble in torch (cat, sigmoid, bg_depth with its
+    implicit .item()), the unmodified reference extension, and _training_statistic (:347-363)."""
+
+    def __init__(self, sc, dev, ref, primitive):
+        self.inner = ReferenceStep(sc, dev, ref)
+        self.sc, self.dev = self.inner.sc, dev
+        self.p = model_params(sc, dev)
+        self.st = {k: torch.zeros(sc.P, device=dev) for k in ("gradient_accum", "gradient_denom", "max_radii2D", "contrib_sum", "contrib_max",
+                                                              "contrib_denom")}
+        self.g = self.inner.g
+
+    def __call__(self):
+        p, st = self.p, self.st
+        for t in p.values():
+            t.grad = None
+        vertex = p["vertex"]
+        shs = torch.cat((p["f_dc"], p["f_rest"]), dim=1)
+        opacity = torch.sigmoid(p["opacity"])
+        bg_depth = (self.sc.cam["campos"].view(1, 1, 3) - vertex).norm(dim=-1).max()
+        kw = self.sc.settings_kwargs()
+        kw["background_depth"] = bg_depth  # float(...) inside the op wrapper: the host sync the reference has
+        center2D = torch.zeros((self.sc.P, 2), device=self.dev, requires_grad=True)
+        out = self.inner.fn.apply(vertex, center2D, shs, self.inner.empty, opacity, kw)
+        torch.autograd.backward([out[0], out[2], out[3]], self.g)
+        radii, contrib_sum, contrib_max = out[1], out[4], out[5]
+        visible_mask = radii > 0
+        st["gradient_accum"][visible_mask] += torch.norm(center2D.grad[visible_mask, :2], dim=-1)
+        st["gradient_denom"][visible_mask] += 1
+        st["contrib_sum"][visible_mask] = torch.max(st["contrib_sum"][visible_mask], contrib_sum[visible_mask])
+        st["contrib_max"][visible_mask] = torch.max(st["contrib_max"][visible_mask], contrib_max[visible_mask])
+        st["contrib_denom"][visible_mask] += 1
+        st["max_radii2D"][visible_mask] = torch.max(st["max_radii2D"][visible_mask], radii[visible_mask])
+
+
+MODEL_STEP_WHAT = ("raw parameters (_vertex, _f_dc, _f_rest, _opacity logits) -> opacity activation, SH concat, background depth -> "
+                   "rasterizer fwd + bwd -> gradients w.r.t. the raw parameters + _training_statistic; CUDA events, parameters resident")
 
 
 def pinned_host_buffers(sc, all_host: bool):
@@ -353,6 +449,7 @@ def main():
                     help="2D: diff_triangle_rasterization_2D (the north-star path); 3D: diff_triangle_rasterization_3D (the *_mesh configs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-model-step", action="store_true", help="skip the model-level step (fused parameter-space front-end)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
 
@@ -411,7 +508,14 @@ def main():
         ms_e = wall_region(lambda: step.e2e_step(host), max(3, a.steps // 2), 2, dev)
         e2e_fps = max(3, a.steps // 2) / (ms_e / 1e3)
         h2d = sum(host[k].numel() * 4 for k in ("viewmatrix", "projmatrix", "campos", "background", "gt"))
-        line = dict(base, impl="reference", n_gpus=1, value=fps, ms_per_step=ms / a.steps, config=cfg, clocks=clocks,
+        model_step = None
+        if sc.rich_info and sc.shs is not None and not a.no_model_step:
+            mstep = ModelStepReference(sc, dev, ref, a.primitive)
+            k_m = max(3, a.steps // 2)
+            ms_m = timed_region(mstep, k_m, 3, dev, 1)
+            model_step = {"value": k_m / (ms_m / 1e3), "unit": "frames/s", "ms_per_step": ms_m / k_m, "what": MODEL_STEP_WHAT}
+            del mstep
+        line = dict(base, impl="reference", n_gpus=1, value=fps, ms_per_step=ms / a.steps, config=cfg, clocks=clocks, model_step=model_step,
                     e2e={"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                     cpu_baseline={"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference",
                                   "sample": "full workload on the reference's own CUDA build (oracle/_ref, sm_100): the reference has no CPU "
@@ -516,7 +620,7 @@ def main():
         if rank == 0:
             h2d = sum(host[k].numel() * 4 for k in ("viewmatrix", "projmatrix", "campos", "background", "gt"))
             line["e2e"] = {"value": k_e / (ms_e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                           "what": "camera + GT image H2D (pinned) -> TriangleRasterizer fwd -> L1 loss -> backward -> loss.item()"}
+                           "what": "camera H2D + GT image H2D (pinned, on a copy stream overlapping the forward) -> TriangleRasterizer fwd -> L1 loss -> backward -> loss.item()"}
         if world == 1:
             ms_a = wall_region(lambda: step.e2e_all_host_step(host), 3, 1, dev)
             h2d_all = sum(host[k].numel() * 4 for k in ("viewmatrix", "projmatrix", "campos", "background", "vertex", "shs", "opacity",
@@ -524,6 +628,15 @@ def main():
             d2h_all = sum(host[k].numel() * 4 for k in ("o_image", "o_gv", "o_gs", "o_go", "o_gc"))
             line["e2e_all_host"] = {"value": 3 / (ms_a / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
                                     "what": "every parameter + upstream gradient H2D, image + all gradients D2H, per step (PCIe bound)"}
+
+    # model-level step through the fused front-end (all ranks: sharded steps contain collectives)
+    if sc.rich_info and sc.shs is not None and not a.no_model_step:
+        mstep = ModelStepOurs(sc, dev, a.primitive)
+        k_m = max(3, a.steps // 2)
+        ms_m = timed_region(mstep, k_m, 3, dev, world)
+        if rank == 0:
+            line["model_step"] = {"value": k_m / (ms_m / 1e3), "unit": "frames/s", "ms_per_step": ms_m / k_m, "what": MODEL_STEP_WHAT}
+        del mstep
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:

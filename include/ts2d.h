@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define TS2D_ABI_VERSION 2
+#define TS2D_ABI_VERSION 3
 #define TS2D_TILE 16          /* R2D/src/config.h:4-5  BLOCK_X = BLOCK_Y = 16 */
 #define TS2D_MAX_CHANNELS 3   /* R2D/src/config.h:3 */
 
@@ -65,7 +65,8 @@ enum {
     TS2D_E_SH_DEGREE = -9,     /* (sh_degree+1)^2 > M or sh_degree > 3 */
     TS2D_E_SHARD = -10,        /* shard_rank/shard_world invalid */
     TS2D_E_SIZE = -11,         /* image or primitive count out of range */
-    TS2D_E_PRIMITIVE = -12     /* flags.primitive is neither TS2D_PRIMITIVE_2D nor TS2D_PRIMITIVE_3D */
+    TS2D_E_PRIMITIVE = -12,    /* flags.primitive is neither TS2D_PRIMITIVE_2D nor TS2D_PRIMITIVE_3D */
+    TS2D_E_MODEL = -13         /* geometry.model / backward_out.model inconsistent (missing pointer, use_shs == 0, M == 0) */
 };
 
 /* R2D/src/param_struct.h:127-137 (CameraInfo).  Matrices are the 16 floats of the (contiguous)
@@ -94,7 +95,44 @@ typedef struct ts2d_geometry {
     const float *shs;          /* [P][M][3] or NULL */
     const float *feature;      /* [P][C]   or NULL */
     const float *opacity;      /* [P] (post-activation) */
+    const struct ts2d_model_inputs *model;  /* NULL: the reference-shaped call above.  Non-NULL: parameter-space inputs, see below */
 } ts2d_geometry;
+
+/* Parameter-space inputs.  diff_recon's model runs a Python preamble in front of every
+ * rasterizer call (src/diff_recon/models/VanillaTS_model.py:608-647): opacity = sigmoid(_opacity) (:84,:612), optional
+ * straight-through binarisation (:620-621), shs = cat(_f_dc, _f_rest) (:80,:611), optional rescale of every triangle about
+ * its centre (gamma_rescale, :615-618 + _rescale_triangles :431-447) and background_depth = max ||campos - vertex|| (:623,
+ * followed by an implicit device->host read when the 0-dim tensor is converted to the `float` the pybind call takes).
+ * With `model` set the per-triangle kernels read the raw parameters directly and do that arithmetic in registers -- same
+ * operation order as the torch kernels the preamble launches -- so nothing is materialised and nothing is read back:
+ *   geometry.vertex  = _vertex (raw), geometry.shs / geometry.opacity are ignored (use_shs must be 1, C == 3),
+ *   backward writes dL/d_vertex, dL/d_f_dc, dL/d_f_rest, dL/d_opacity (the LOGIT) through ts2d_model_grads. */
+typedef struct ts2d_model_inputs {
+    const float *f_dc;           /* [P][1][3]    SH coefficient 0 */
+    const float *f_rest;         /* [P][M-1][3]  SH coefficients 1..M-1; NULL iff M == 1 */
+    const float *opacity_logit;  /* [P]          pre-activation */
+    float ste_threshold;         /* >= 0: forward uses ((sigmoid > thr) - sigmoid) + sigmoid, gradient passes straight through; < 0: off */
+    float rescale_ratio;         /* v' = (v - mean(v)) * ratio + mean(v); 1 = off */
+    int32_t bg_depth_from_vertices; /* 1: background_depth = max over all vertices of ||campos - v|| (un-rescaled v), computed on
+                                       the device and consumed by the composite kernels from device memory; 0: geometry.background_depth */
+} ts2d_model_inputs;
+
+/* Gradients w.r.t. the raw parameters (autograd through the preamble: CatBackward = split, SigmoidBackward, the linear
+ * rescale map) + the optional training statistics of VanillaTS_model.py:347-363, updated in place
+ * for the triangles with radii > 0 (`visible_mask`, :674).  Any of the six statistics pointers may be NULL. */
+typedef struct ts2d_model_grads {
+    float *dL_df_dc;           /* [P][1][3] */
+    float *dL_df_rest;         /* [P][M-1][3] */
+    float *gradient_accum;     /* [P]  += ||dL_dcenter2D||   (:358) */
+    float *gradient_denom;     /* [P]  += 1                  (:359) */
+    float *contrib_sum;        /* [P]  = max(., forward contrib_sum)  (:360) */
+    float *contrib_max;        /* [P]  = max(., forward contrib_max)  (:361) */
+    float *contrib_denom;      /* [P]  += 1                  (:362) */
+    float *max_radii2D;        /* [P]  = max(., radii / radii_div)    (:363; radii // render_up_scale, :651) */
+    const float *fwd_contrib_sum;  /* [P] forward outputs feeding :360-361 (required when contrib_sum / contrib_max are set) */
+    const float *fwd_contrib_max;
+    int32_t radii_div;         /* render_up_scale (>= 1) */
+} ts2d_model_grads;
 
 typedef struct ts2d_flags {
     int32_t back_culling;
@@ -141,7 +179,8 @@ typedef struct ts2d_backward_out {
     float *dL_dcenter2D;   /* [P][2] */
     float *dL_dshs;        /* [P][M][3] (M may be 0) */
     float *dL_dfeature;    /* [P][C]   (SH mode: dL/d rgb, like the reference's scratch use) */
-    float *dL_dopacity;    /* [P] */
+    float *dL_dopacity;    /* [P]  (model inputs: gradient w.r.t. the logit) */
+    const ts2d_model_grads *model;  /* required iff geometry.model is set; dL_dshs is then ignored */
 } ts2d_backward_out;
 
 int ts2d_abi_version(void);
@@ -182,6 +221,14 @@ int ts2d_backward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, co
                            const void *geometry_state, const ts2d_backward_out *out, const void *scratch, size_t scratch_bytes,
                            void *stream);
 
+/* render_up_scale epilogue (VanillaTS_model.py:647-655): F.interpolate(x, size=(H/s, W/s), mode="bilinear") of `planes`
+ * planar images rendered at s times the target resolution, align_corners = False, no antialiasing -- i.e. each output
+ * pixel samples the source at s * (d + 0.5) - 0.5: the mean of the two middle source rows/columns for even s, the
+ * middle one for odd s (same lerp order as torch's upsample_bilinear2d kernel).  `in` is [planes][H*s][W*s], `out` is
+ * [planes][H][W].  ts2d_downsample_bwd is its adjoint (writes every element of dL_din). */
+int ts2d_downsample(const float *in, float *out, int32_t planes, int32_t out_width, int32_t out_height, int32_t s, void *stream);
+int ts2d_downsample_bwd(const float *dL_dout, float *dL_din, int32_t planes, int32_t out_width, int32_t out_height, int32_t s, void *stream);
+
 /* ---- state decoding, for parity tests against the reference's buffers ----
  * Each writes arrays in the reference's own element types/order.  Any output pointer may be NULL. */
 int ts2d_export_geometry(const void *geometry_state, int32_t P,
@@ -193,6 +240,8 @@ int ts2d_export_geometry3d(const void *geometry_state, int32_t P,
                            float *v_view /*[P][3][3]*/, float *normal_view /*[P][3]*/, float *depth /*[P]*/, float *rgb /*[P][3]*/,
                            uint8_t *clamped /*[P][3]*/, uint32_t *tiles_touched /*[P]*/, uint32_t *rect_min /*[P][2]*/,
                            uint32_t *rect_max /*[P][2]*/, void *stream);
+/* model inputs: the activated (sigmoid / STE) opacity the kernels used, and the device-computed background depth */
+int ts2d_export_model(const void *geometry_state, int32_t P, int32_t primitive, float *opacity /*[P]*/, float *background_depth /*[1]*/, void *stream);
 int ts2d_export_binning(const void *geometry_state, const void *binning_state, const void *image_state, int32_t P, int64_t num_rendered,
                         int32_t width, int32_t height, uint64_t *keys_sorted /*[R]*/, uint32_t *point_list /*[R]*/,
                         uint32_t *ranges /*[tiles][2]*/, void *stream);

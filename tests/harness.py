@@ -100,7 +100,17 @@ def run_ours(sc: Scene, dev, backward: bool = True, primitive: str = "2D") -> di
     fwd = _C.rasterize_triangles(*_fwd_args(s), primitive=primitive)
     bwd = _C.rasterize_triangles_backward(*_bwd_args(s, fwd, dev), primitive=primitive) if backward else None
     out = _pack_common(s, fwd, bwd)
-    # decode our opaque state through the C ABI export calls
+    out.update(decode_state(s, fwd, dev, primitive))
+    return out
+
+
+def decode_state(s: Scene, fwd, dev, primitive: str = "2D") -> dict:
+    """Decode our opaque state blobs (forward tuple of _C.rasterize_triangles) through the C ABI export calls."""
+    import ctypes as C
+
+    from triangle_splatting_b200 import _lib
+
+    out = {}
     lib = _lib.load()
     P, W, H = s.P, s.cam["image_width"], s.cam["image_height"]
     R = int(fwd[0])

@@ -25,9 +25,29 @@ def test_library_loads_and_exports_everything():
     lib = _lib.load()
     for name in _declared():
         assert hasattr(lib, name), name
-    assert lib.ts2d_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.ts2d_abi_version() == _lib.ABI_VERSION == 3
     assert b"vertex must have dimensions" in lib.ts2d_error_string(-1)
     assert lib.ts2d_error_string(0) == b"ok"
+
+
+def test_ctypes_structs_match_the_header_layout():
+    """The ctypes mirrors must have the C layout of include/ts2d.h (checked by compiling the header with gcc)."""
+    import ctypes
+    import subprocess
+    import tempfile
+
+    names = {"ts2d_camera": _lib.Camera, "ts2d_geometry": _lib.Geometry, "ts2d_flags": _lib.Flags, "ts2d_forward_out": _lib.ForwardOut,
+             "ts2d_loss_in": _lib.LossIn, "ts2d_backward_out": _lib.BackwardOut, "ts2d_model_inputs": _lib.ModelInputs,
+             "ts2d_model_grads": _lib.ModelGrads}
+    body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in names)
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.c")
+        open(src, "w").write(f'#include <stdio.h>\n#include "ts2d.h"\nint main(void){{{body} return 0;}}')
+        subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", os.path.join(d, "t")], check=True)
+        out = subprocess.run([os.path.join(d, "t")], check=True, capture_output=True, text=True).stdout
+    sizes = dict(ln.split() for ln in out.strip().splitlines())
+    for n, cls in names.items():
+        assert int(sizes[n]) == ctypes.sizeof(cls), n
 
 
 def test_state_sizes_are_monotone_and_aligned():

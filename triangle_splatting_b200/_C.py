@@ -7,6 +7,11 @@ state tensors), the current CUDA stream and the device guard.
 
 Extra keyword-only arguments (no counterpart in the reference):
     shard=(rank, world)  image-space tile sharding for multi-GPU (see distributed.py)
+    model=ModelInputs    parameter-space inputs: raw _f_dc / _f_rest / _opacity logits, STE
+                         threshold, gamma_rescale ratio, device-side background depth -- the Python preamble of
+                         src/diff_recon/models/VanillaTS_model.py:608-647 done inside the per-triangle kernels; `shs` and
+                         `opacity` are then passed as None.  `stats=` (backward) adds the in-place training statistics
+                         of VanillaTS_model.py:347-363 (rank 3)
     primitive="2D"|"3D"  which of the reference's two rasterizer packages the call stands in for: "2D" =
                          diff_triangle_rasterization_2D (screen-space triangles, the north-star path), "3D" =
                          diff_triangle_rasterization_3D (ray / plane intersection in view space; identical pybind
@@ -34,6 +39,43 @@ def set_exact(flag: bool) -> bool:
     global EXACT
     old, EXACT = EXACT, bool(flag)
     return old
+
+
+class ModelInputs:
+    """Host-side mirror of ts2d_model_inputs (include/ts2d.h)."""
+
+    def __init__(self, f_dc: torch.Tensor, f_rest: torch.Tensor | None, opacity_logit: torch.Tensor, ste_threshold: float | None = None,
+                 rescale_ratio: float = 1.0, bg_depth_from_vertices: bool = True):
+        self.f_dc, self.f_rest, self.opacity_logit = f_dc, f_rest, opacity_logit
+        self.ste_threshold = -1.0 if ste_threshold is None else float(ste_threshold)
+        self.rescale_ratio = float(rescale_ratio)
+        self.bg_depth_from_vertices = bool(bg_depth_from_vertices)
+
+    @property
+    def M(self) -> int:
+        return 1 + (0 if self.f_rest is None or self.f_rest.numel() == 0 else int(self.f_rest.size(1)))
+
+    def check(self, P: int):
+        if self.f_dc.dim() != 3 or tuple(self.f_dc.shape) != (P, 1, 3):
+            raise RuntimeError("f_dc must have dimensions (num_points, 1, 3)")
+        if self.M > 1 and (self.f_rest.dim() != 3 or self.f_rest.size(0) != P or self.f_rest.size(2) != 3):
+            raise RuntimeError("f_rest must have dimensions (num_points, (1 + sh_degree) ** 2 - 1, 3)")
+        if self.opacity_logit.numel() != P:
+            raise RuntimeError("opacity must have dimensions (num_points, 1)")
+        if not self.rescale_ratio > 0.0:
+            raise RuntimeError("rescale_ratio must be positive")
+        ts = [self.f_dc, self.opacity_logit] + ([self.f_rest] if self.M > 1 else [])
+        if not all(t.is_contiguous() for t in ts):
+            raise RuntimeError("input tensors must be contiguous")
+        for t in ts:
+            _require_cuda_f32("model input", t)
+
+    def struct(self):
+        return _lib.ModelInputs(_ptr(self.f_dc), _ptr(self.f_rest) if self.M > 1 else None, _ptr(self.opacity_logit), self.ste_threshold,
+                                self.rescale_ratio, int(self.bg_depth_from_vertices))
+
+
+STAT_FIELDS = ("gradient_accum", "gradient_denom", "contrib_sum", "contrib_max", "contrib_denom", "max_radii2D")
 
 
 def _ptr(t: torch.Tensor | None):
@@ -80,27 +122,43 @@ def _require_cuda_f32(name, t):
 
 def _structs(image_width, image_height, tan_fovx, tan_fovy, viewmatrix, projmatrix, campos, sh_degree, gamma, scale_modifier,
              background_depth, background, vertex, shs, feature, opacity, P, use_shs, Cn, M, back_culling, rich_info, debug, shard,
-             primitive="2D"):
+             primitive="2D", model=None):
+    """-> (camera, geometry, flags, keepalive): `keepalive` holds the ctypes objects the structs point to."""
+    mstruct = model.struct() if model is not None else None
     cam = _lib.Camera(int(image_width), int(image_height), float(tan_fovx), float(tan_fovy), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos))
     geom = _lib.Geometry(int(P), int(sh_degree), int(M), int(Cn), int(use_shs), float(gamma), float(scale_modifier), float(background_depth),
-                         _ptr(background), _ptr(vertex), _ptr(shs) if use_shs else None, None if use_shs else _ptr(feature), _ptr(opacity))
+                         _ptr(background), _ptr(vertex), _ptr(shs) if (use_shs and model is None) else None,
+                         None if use_shs else _ptr(feature), _ptr(opacity) if model is None else None,
+                         C.cast(C.pointer(mstruct), C.c_void_p) if mstruct is not None else None)
     flags = _lib.Flags(int(bool(back_culling)), int(bool(rich_info)), int(bool(debug)), int(shard[0]), int(shard[1]), int(EXACT),
                        _lib.PRIMITIVES[primitive])
-    return cam, geom, flags
+    return cam, geom, flags, mstruct
 
 
 def rasterize_triangles(image_width: int, image_height: int, tan_fovx: float, tan_fovy: float, viewmatrix: torch.Tensor,
                         projmatrix: torch.Tensor, campos: torch.Tensor, sh_degree: int, gamma: float, scale_modifier: float,
                         background_depth: float, background: torch.Tensor, vertex: torch.Tensor, shs: torch.Tensor, feature: torch.Tensor,
                         opacity: torch.Tensor, back_culling: bool, rich_info: bool, debug: bool, *, shard: Tuple[int, int] = (0, 1),
-                        primitive: str = "2D"):
+                        primitive: str = "2D", model: ModelInputs | None = None):
     """-> (num_rendered:int, out_feature, radii, depth, normal, contrib_sum, contrib_max, geometryBuffer, binningBuffer, imageBuffer)
 
     Mirrors rasterizeTrianglesForward (extension_interface.cu:19-152)."""
     lib = _lib.load()
-    P, use_shs, Cn, M = _derive(vertex, shs, feature)
+    if model is not None:  # parameter-space inputs: shs / opacity come from the model's raw tensors
+        shs = feature = opacity = torch.empty(0)
+        P, use_shs, Cn, M = (vertex.size(0) if vertex.dim() > 0 else 0), True, 3, model.M
+        if vertex.dim() != 3 or vertex.size(1) != 3 or vertex.size(2) != 3:
+            raise RuntimeError("vertex must have dimensions (num_points, 3, 3)")
+        if Cn != background.size(0):
+            raise RuntimeError("background must have the same number of channels as feature")
+        if gamma < 0.0:
+            raise RuntimeError("gamma must be larger than 0")
+        if P > 0:
+            model.check(P)
+    else:
+        P, use_shs, Cn, M = _derive(vertex, shs, feature)
+        _check_inputs(vertex, shs, feature, background, gamma, use_shs, Cn)
     H, W = int(image_height), int(image_width)
-    _check_inputs(vertex, shs, feature, background, gamma, use_shs, Cn)
     tensors = dict(viewmatrix=viewmatrix, projmatrix=projmatrix, campos=campos, background=background, vertex=vertex, shs=shs,
                    feature=feature, opacity=opacity)
     if not all(t.is_contiguous() for t in tensors.values()):
@@ -109,7 +167,7 @@ def rasterize_triangles(image_width: int, image_height: int, tan_fovx: float, ta
         _require_cuda_f32(k, t)
     if use_shs and P > 0 and (sh_degree < 0 or sh_degree > 3 or (sh_degree + 1) ** 2 > M):
         raise RuntimeError(_lib.error_string(-9))
-    if P > 0 and opacity.numel() != P:
+    if P > 0 and model is None and opacity.numel() != P:
         raise RuntimeError("opacity must have dimensions (num_points, 1)")
 
     dev = vertex.device if vertex.is_cuda else background.device
@@ -135,9 +193,9 @@ def rasterize_triangles(image_width: int, image_height: int, tan_fovx: float, ta
 
     with torch.cuda.device(dev):
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        cam, geom, flags = _structs(W, H, tan_fovx, tan_fovy, viewmatrix, projmatrix, campos, sh_degree, gamma, scale_modifier,
-                                    background_depth, background, vertex, shs, feature, opacity, P, use_shs, Cn, M, back_culling, rich_info,
-                                    debug, shard, primitive)
+        cam, geom, flags, _keep = _structs(W, H, tan_fovx, tan_fovy, viewmatrix, projmatrix, campos, sh_degree, gamma, scale_modifier,
+                                           background_depth, background, vertex, shs, feature, opacity, P, use_shs, Cn, M, back_culling,
+                                           rich_info, debug, shard, primitive, model)
         gbytes = lib.ts2d_geometry_state_bytes(P)
         geometryBuffer = torch.empty((gbytes,), **u8)
         num_rendered = C.c_int64(0)
@@ -159,14 +217,23 @@ def rasterize_triangles_backward(tan_fovx: float, tan_fovy: float, viewmatrix: t
                                  vertex: torch.Tensor, shs: torch.Tensor, feature: torch.Tensor, opacity: torch.Tensor, num_rendered: int,
                                  radii: torch.Tensor, geometryBuffer: torch.Tensor, binningBuffer: torch.Tensor, imageBuffer: torch.Tensor,
                                  dL_dout_feature: torch.Tensor, dL_dout_depth: torch.Tensor | None, dL_dout_normal: torch.Tensor | None,
-                                 rich_info: bool, debug: bool, *, shard: Tuple[int, int] = (0, 1), primitive: str = "2D"):
+                                 rich_info: bool, debug: bool, *, shard: Tuple[int, int] = (0, 1), primitive: str = "2D",
+                                 model: ModelInputs | None = None, stats: dict | None = None, fwd_contrib=None, radii_div: int = 1):
     """-> (dL_dvertex (P,3,3), dL_dcenter2D (P,2), dL_dshs (P,M,3), dL_dfeature (P,C), dL_dopacity (P,1))
 
     Mirrors rasterizeTrianglesBackward (extension_interface.cu:154-260).  Unlike the reference's
     Python wrapper (which raises UnboundLocalError, __init__.py:114-142) rich_info=False is accepted:
-    pass None for dL_dout_depth / dL_dout_normal."""
+    pass None for dL_dout_depth / dL_dout_normal.
+
+    With `model` (parameter-space inputs) the tuple is (dL_d_vertex, dL_dcenter2D, dL_d_f_dc (P,1,3), dL_d_f_rest (P,M-1,3),
+    dL_d_opacity_logit (P,1)); `stats` (dict of the six (P,) tensors of VanillaTS_model.py:196-201, any subset) is updated in
+    place for the visible triangles, `fwd_contrib` = (contrib_sum, contrib_max) of the forward pass."""
     lib = _lib.load()
-    P, use_shs, Cn, M = _derive(vertex, shs, feature)
+    if model is not None:
+        shs = feature = opacity = torch.empty(0, device=vertex.device)
+        P, use_shs, Cn, M = vertex.size(0), True, 3, model.M
+    else:
+        P, use_shs, Cn, M = _derive(vertex, shs, feature)
     H, W = int(dL_dout_feature.size(1)), int(dL_dout_feature.size(2))
     ts = [viewmatrix, projmatrix, campos, background, vertex, shs, feature, opacity, radii, geometryBuffer, binningBuffer, imageBuffer,
           dL_dout_feature]
@@ -177,23 +244,45 @@ def rasterize_triangles_backward(tan_fovx: float, tan_fovy: float, viewmatrix: t
     dev = vertex.device
     f32 = dict(device=dev, dtype=torch.float32)
     if P == 0:
+        if model is not None:
+            return (torch.zeros((P, 3, 3), **f32), torch.zeros((P, 2), **f32), torch.zeros((P, 1, 3), **f32),
+                    torch.zeros((P, M - 1, 3), **f32), torch.zeros((P, 1), **f32))
         return (torch.zeros((P, 3, 3), **f32), torch.zeros((P, 2), **f32), torch.zeros((P, M, 3), **f32), torch.zeros((P, Cn), **f32),
                 torch.zeros((P, 1), **f32))
     _require_cuda_f32("dL_dout_feature", dL_dout_feature)
     dL_dvertex = torch.empty((P, 3, 3), **f32)
     dL_dcenter2D = torch.empty((P, 2), **f32)
-    dL_dshs = torch.empty((P, M, 3), **f32)
+    mgrads = None
+    if model is not None:
+        dL_df_dc = torch.empty((P, 1, 3), **f32)
+        dL_df_rest = torch.empty((P, M - 1, 3), **f32)
+        dL_dshs = None
+        st = dict(stats or {})
+        for k, t in st.items():
+            if k not in STAT_FIELDS:
+                raise RuntimeError(f"unknown statistics tensor {k!r}")
+            if t.numel() != P or not t.is_contiguous():
+                raise RuntimeError(f"statistics tensor {k} must be a contiguous (num_points,) tensor")
+            _require_cuda_f32(k, t)
+        if ("contrib_sum" in st or "contrib_max" in st) and fwd_contrib is None:
+            raise RuntimeError("contrib statistics need the forward pass's contrib_sum / contrib_max")
+        mgrads = _lib.ModelGrads(_ptr(dL_df_dc), _ptr(dL_df_rest), *[_ptr(st.get(k)) for k in STAT_FIELDS],
+                                 _ptr(fwd_contrib[0]) if fwd_contrib is not None else None,
+                                 _ptr(fwd_contrib[1]) if fwd_contrib is not None else None, int(radii_div))
+    else:
+        dL_dshs = torch.empty((P, M, 3), **f32)
     dL_dfeature = torch.empty((P, Cn), **f32)
     dL_dopacity = torch.empty((P, 1), **f32)
     with torch.cuda.device(dev):
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        cam, geom, flags = _structs(W, H, tan_fovx, tan_fovy, viewmatrix, projmatrix, campos, sh_degree, gamma, scale_modifier,
-                                    background_depth, background, vertex, shs, feature, opacity, P, use_shs, Cn, M, False, rich_info, debug,
-                                    shard, primitive)
+        cam, geom, flags, _keep = _structs(W, H, tan_fovx, tan_fovy, viewmatrix, projmatrix, campos, sh_degree, gamma, scale_modifier,
+                                           background_depth, background, vertex, shs, feature, opacity, P, use_shs, Cn, M, False, rich_info,
+                                           debug, shard, primitive, model)
         sbytes = lib.ts2d_backward_scratch_bytes(P)
         scratch = torch.empty((sbytes,), device=dev, dtype=torch.uint8)
         loss = _lib.LossIn(_ptr(dL_dout_feature), _ptr(dL_dout_depth) if rich_info else None, _ptr(dL_dout_normal) if rich_info else None)
-        out = _lib.BackwardOut(_ptr(dL_dvertex), _ptr(dL_dcenter2D), _ptr(dL_dshs), _ptr(dL_dfeature), _ptr(dL_dopacity))
+        out = _lib.BackwardOut(_ptr(dL_dvertex), _ptr(dL_dcenter2D), _ptr(dL_dshs), _ptr(dL_dfeature), _ptr(dL_dopacity),
+                               C.cast(C.pointer(mgrads), C.c_void_p) if mgrads is not None else None)
         if shard[1] > 1:
             # tile-sharded: composite over this rank's tiles, sum the 64 B/triangle accumulators over the ranks (NCCL on the
             # current stream), then the per-triangle stage runs replicated on identical data -> identical gradients everywhere
@@ -209,4 +298,28 @@ def rasterize_triangles_backward(tan_fovx: float, tan_fovy: float, viewmatrix: t
             _lib.check(lib.ts2d_backward(C.byref(cam), C.byref(geom), C.byref(flags), int(num_rendered), _ptr(radii), _ptr(geometryBuffer),
                                          _ptr(binningBuffer), _ptr(imageBuffer), C.byref(loss), C.byref(out), _ptr(scratch), sbytes, stream),
                        "ts2d_backward")
+    if model is not None:
+        return dL_dvertex, dL_dcenter2D, dL_df_dc, dL_df_rest, dL_dopacity
     return dL_dvertex, dL_dcenter2D, dL_dshs, dL_dfeature, dL_dopacity
+
+
+def downsample(x: torch.Tensor, s: int, backward: bool = False) -> torch.Tensor:
+    """render_up_scale epilogue (VanillaTS_model.py:647-655): F.interpolate(x, size=(H/s, W/s), mode="bilinear") of a planar
+    (planes, H, W) image by an integer factor, or (backward=True) its adjoint applied to a (planes, H/s, W/s) gradient."""
+    lib = _lib.load()
+    _require_cuda_f32("image", x)
+    if x.dim() != 3 or not x.is_contiguous():
+        raise RuntimeError("downsample expects a contiguous (planes, H, W) tensor")
+    planes, h, w = x.shape
+    s = int(s)
+    if not backward and (h % s or w % s):
+        raise RuntimeError("image size must be a multiple of render_up_scale")
+    oh, ow = (h * s, w * s) if backward else (h // s, w // s)
+    out = torch.empty((planes, oh, ow), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        if backward:
+            _lib.check(lib.ts2d_downsample_bwd(_ptr(x), _ptr(out), planes, w, h, s, stream), "ts2d_downsample_bwd")
+        else:
+            _lib.check(lib.ts2d_downsample(_ptr(x), _ptr(out), planes, ow, oh, s, stream), "ts2d_downsample")
+    return out

@@ -158,3 +158,8 @@ class TriangleRasterizer3D(TriangleRasterizer):
     """diff_triangle_rasterization_3D.TriangleRasterizer (R3D/diff_triangle_rasterization_3D/__init__.py:167-187)."""
 
     _function = _RasterizeTriangles3D
+
+
+from .frontend import TriangleModelRasterizer, TrainingStatistics, bilinear_downsample, gamma_rescale_ratio  # noqa: E402
+
+__all__ += ["TriangleModelRasterizer", "TrainingStatistics", "bilinear_downsample", "gamma_rescale_ratio"]

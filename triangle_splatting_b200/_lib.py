@@ -23,7 +23,20 @@ class Geometry(C.Structure):
     _fields_ = [("P", C.c_int32), ("sh_degree", C.c_int32), ("M", C.c_int32), ("C", C.c_int32), ("use_shs", C.c_int32),
                 ("gamma", C.c_float), ("scale_modifier", C.c_float), ("background_depth", C.c_float),
                 ("background", C.c_void_p), ("vertex", C.c_void_p), ("shs", C.c_void_p), ("feature", C.c_void_p),
-                ("opacity", C.c_void_p)]
+                ("opacity", C.c_void_p), ("model", C.c_void_p)]  # model: POINTER(ModelInputs) or NULL
+
+
+class ModelInputs(C.Structure):
+    """ts2d_model_inputs: parameter-space inputs (VanillaTS_model.py:608-647 done inside the per-triangle kernels)."""
+    _fields_ = [("f_dc", C.c_void_p), ("f_rest", C.c_void_p), ("opacity_logit", C.c_void_p), ("ste_threshold", C.c_float),
+                ("rescale_ratio", C.c_float), ("bg_depth_from_vertices", C.c_int32)]
+
+
+class ModelGrads(C.Structure):
+    """ts2d_model_grads: gradients w.r.t. the raw parameters + the in-place training statistics (VanillaTS_model.py:347-363)."""
+    _fields_ = [("dL_df_dc", C.c_void_p), ("dL_df_rest", C.c_void_p), ("gradient_accum", C.c_void_p), ("gradient_denom", C.c_void_p),
+                ("contrib_sum", C.c_void_p), ("contrib_max", C.c_void_p), ("contrib_denom", C.c_void_p), ("max_radii2D", C.c_void_p),
+                ("fwd_contrib_sum", C.c_void_p), ("fwd_contrib_max", C.c_void_p), ("radii_div", C.c_int32)]
 
 
 class Flags(C.Structure):
@@ -42,7 +55,7 @@ class LossIn(C.Structure):
 
 class BackwardOut(C.Structure):
     _fields_ = [("dL_dvertex", C.c_void_p), ("dL_dcenter2D", C.c_void_p), ("dL_dshs", C.c_void_p), ("dL_dfeature", C.c_void_p),
-                ("dL_dopacity", C.c_void_p)]
+                ("dL_dopacity", C.c_void_p), ("model", C.c_void_p)]  # model: POINTER(ModelGrads) or NULL
 
 
 # every symbol include/ts2d.h declares (tests/test_abi.py checks the header against this list)
@@ -65,6 +78,9 @@ SYMBOLS = {
                                          C.POINTER(BackwardOut), C.c_void_p, C.c_size_t, C.c_void_p]),
     "ts2d_export_geometry": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 10 + [C.c_void_p]),
     "ts2d_export_geometry3d": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 8 + [C.c_void_p]),
+    "ts2d_export_model": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ts2d_downsample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "ts2d_downsample_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "ts2d_export_binning": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "ts2d_export_image": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -72,7 +88,7 @@ SYMBOLS = {
     "ts2d_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
 
-ABI_VERSION = 2  # TS2D_ABI_VERSION (include/ts2d.h)
+ABI_VERSION = 3  # TS2D_ABI_VERSION (include/ts2d.h)
 PRIMITIVES = {"2D": 0, "3D": 1}  # TS2D_PRIMITIVE_* (include/ts2d.h)
 STAGES = ("preprocess", "order_scan", "binning", "render_fwd", "render_bwd", "preprocess_bwd")
 

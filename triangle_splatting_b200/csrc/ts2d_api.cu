@@ -114,13 +114,34 @@ int validate(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f
     if (f->shard_world < 1 || f->shard_rank < 0 || f->shard_rank >= f->shard_world) return TS2D_E_SHARD;
     if (f->primitive != TS2D_PRIMITIVE_2D && f->primitive != TS2D_PRIMITIVE_3D) return TS2D_E_PRIMITIVE;
     if (g->P == 0) return 0;
-    if (!cam->viewmatrix || !cam->projmatrix || !cam->campos || !g->background || !g->vertex || !g->opacity) return TS2D_E_NULL;
+    if (!cam->viewmatrix || !cam->projmatrix || !cam->campos || !g->background || !g->vertex) return TS2D_E_NULL;
+    if (g->model) {  // parameter-space inputs replace shs / opacity
+        const ts2d_model_inputs *m = g->model;
+        if (!g->use_shs || g->M < 1 || !m->f_dc || !m->opacity_logit || (g->M > 1 && !m->f_rest)) return TS2D_E_MODEL;
+        if (!(m->rescale_ratio > 0.0f)) return TS2D_E_MODEL;
+    } else if (!g->opacity) {
+        return TS2D_E_NULL;
+    }
     if (g->use_shs) {
-        if (!g->shs) return TS2D_E_BAD_SHS;
+        if (!g->model && !g->shs) return TS2D_E_BAD_SHS;
         if (g->C != 3) return TS2D_E_BACKGROUND;
         if (g->sh_degree < 0 || g->sh_degree > 3 || (g->sh_degree + 1) * (g->sh_degree + 1) > g->M) return TS2D_E_SH_DEGREE;
     } else {
         if (!g->feature) return TS2D_E_BAD_FEATURE;
+    }
+    return 0;
+}
+
+int validate_backward_out(const ts2d_geometry *g, const ts2d_backward_out *out)
+{
+    if (!out->dL_dvertex || !out->dL_dcenter2D || !out->dL_dfeature || !out->dL_dopacity) return TS2D_E_NULL;
+    if ((g->model != nullptr) != (out->model != nullptr)) return TS2D_E_MODEL;
+    if (g->model) {
+        const ts2d_model_grads *q = out->model;
+        if (!q->dL_df_dc || (g->M > 1 && !q->dL_df_rest)) return TS2D_E_MODEL;
+        if ((q->contrib_sum && !q->fwd_contrib_sum) || (q->contrib_max && !q->fwd_contrib_max)) return TS2D_E_MODEL;
+    } else if (g->M > 0 && !out->dL_dshs) {
+        return TS2D_E_NULL;
     }
     return 0;
 }
@@ -186,6 +207,43 @@ __global__ void k_export_keys(int64_t R, const uint32_t *tkey, const uint32_t *t
     if (list) list[i] = id;
 }
 
+__global__ void k_export_opacity(int P, const float4 *rec, int stride, int slot, const uint32_t *dkey, float *opacity)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    opacity[i] = dkey[i] != 0xFFFFFFFFu ? rec[(size_t)stride * i + slot].w : 0.0f;
+}
+
+// ---- render_up_scale epilogue: bilinear resize by an integer factor, align_corners = False (torch upsample_bilinear2d) ----
+// Source index of output pixel d: sc * (d + 0.5) - 0.5 = sc*d + (sc-1)/2: integral for odd sc (one tap), half-way between the two
+// middle source pixels for even sc (two taps, weights 0.5 / 0.5).  torch evaluates w_y0 * (w_x0 * a + w_x1 * b) + w_y1 * (w_x0 * c + w_x1 * d).
+__global__ void k_downsample(const float *__restrict__ in, float *__restrict__ out, int W, int H, int sc)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int Wi = W * sc, Hi = H * sc;
+    const float *src = in + (size_t)blockIdx.z * Wi * Hi;
+    const int x0 = sc * x + (sc - 1) / 2, y0 = sc * y + (sc - 1) / 2;
+    const float l1 = (sc & 1) ? 0.0f : 0.5f, l0 = 1.0f - l1;
+    const int x1 = min(x0 + 1, Wi - 1), y1 = min(y0 + 1, Hi - 1);
+    const float a = src[(size_t)y0 * Wi + x0], b = src[(size_t)y0 * Wi + x1], c = src[(size_t)y1 * Wi + x0], d = src[(size_t)y1 * Wi + x1];
+    const float top = __fadd_rn(__fmul_rn(l0, a), __fmul_rn(l1, b)), bot = __fadd_rn(__fmul_rn(l0, c), __fmul_rn(l1, d));
+    out[((size_t)blockIdx.z * H + y) * W + x] = __fadd_rn(__fmul_rn(l0, top), __fmul_rn(l1, bot));
+}
+// adjoint: source pixel (xi, yi) receives w_y * w_x * dL_dout[yi / sc][xi / sc] when it is one of that output pixel's taps, else 0
+__global__ void k_downsample_bwd(const float *__restrict__ g_out, float *__restrict__ g_in, int W, int H, int sc)
+{
+    const int xi = blockIdx.x * blockDim.x + threadIdx.x, yi = blockIdx.y * blockDim.y + threadIdx.y;
+    const int Wi = W * sc, Hi = H * sc;
+    if (xi >= Wi || yi >= Hi) return;
+    const int x = xi / sc, y = yi / sc, rx = xi - x * sc, ry = yi - y * sc, t0 = (sc - 1) / 2;
+    const bool odd = sc & 1;
+    const float wx = odd ? (rx == t0 ? 1.0f : 0.0f) : ((rx == t0 || rx == t0 + 1) ? 0.5f : 0.0f);
+    const float wy = odd ? (ry == t0 ? 1.0f : 0.0f) : ((ry == t0 || ry == t0 + 1) ? 0.5f : 0.0f);
+    const float w = wx * wy;
+    g_in[((size_t)blockIdx.z * Hi + yi) * Wi + xi] = w != 0.0f ? w * g_out[((size_t)blockIdx.z * H + y) * W + x] : 0.0f;
+}
+
 }  // namespace
 
 extern "C" {
@@ -208,6 +266,7 @@ const char *ts2d_error_string(int code)
     case TS2D_E_SHARD: return "invalid shard_rank / shard_world";
     case TS2D_E_SIZE: return "image size or primitive count out of range";
     case TS2D_E_PRIMITIVE: return "flags.primitive must be TS2D_PRIMITIVE_2D or TS2D_PRIMITIVE_3D";
+    case TS2D_E_MODEL: return "model inputs / model gradients inconsistent (need use_shs, f_dc, f_rest for M > 1, opacity_logit, ratio > 0)";
     default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
@@ -276,8 +335,8 @@ int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_
     if (rc) return rc;
     if (geom->P == 0) return 0;
     if (!radii || !geometry_state || !binning_state || !image_state || !loss || !out || !scratch) return TS2D_E_NULL;
-    if (!loss->dL_dout_feature || !out->dL_dvertex || !out->dL_dcenter2D || !out->dL_dfeature || !out->dL_dopacity) return TS2D_E_NULL;
-    if (geom->M > 0 && !out->dL_dshs) return TS2D_E_NULL;
+    if (!loss->dL_dout_feature) return TS2D_E_NULL;
+    if ((rc = validate_backward_out(geom, out)) != 0) return rc;
     if (flags->rich_info && (!loss->dL_dout_depth || !loss->dL_dout_normal)) return TS2D_E_NULL;
     if (scratch_bytes < ts2d_backward_scratch_bytes(geom->P)) return TS2D_E_STATE_SIZE;
     GeomState gs;
@@ -340,8 +399,7 @@ int ts2d_backward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, co
     if (rc) return rc;
     if (geom->P == 0) return 0;
     if (!radii || !geometry_state || !out || !scratch) return TS2D_E_NULL;
-    if (!out->dL_dvertex || !out->dL_dcenter2D || !out->dL_dfeature || !out->dL_dopacity) return TS2D_E_NULL;
-    if (geom->M > 0 && !out->dL_dshs) return TS2D_E_NULL;
+    if ((rc = validate_backward_out(geom, out)) != 0) return rc;
     if (scratch_bytes < ts2d_backward_scratch_bytes(geom->P)) return TS2D_E_STATE_SIZE;
     GeomState gs;
     carve_geometry(const_cast<void *>(geometry_state), geom->P, &gs);
@@ -374,6 +432,41 @@ int ts2d_export_geometry3d(const void *geometry_state, int32_t P, float *v_view,
     GeomState gs;
     carve_geometry(const_cast<void *>(geometry_state), P, &gs);
     return ts2d_launch_export_geometry3d(P, gs, v_view, normal_view, depth, rgb, clamped, tiles_touched, rect_min, rect_max, (cudaStream_t)stream);
+}
+
+int ts2d_export_model(const void *geometry_state, int32_t P, int32_t primitive, float *opacity, float *background_depth, void *stream)
+{
+    if (P <= 0) return 0;
+    if (!geometry_state) return TS2D_E_NULL;
+    GeomState gs;
+    carve_geometry(const_cast<void *>(geometry_state), P, &gs);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (opacity) {
+        // the activated opacity sits in the raster record: rec0[3i+1].w (2D) / rec1[2i].w (3D); only visible triangles have one
+        k_export_opacity<<<(P + 255) / 256, 256, 0, s>>>(P, primitive == TS2D_PRIMITIVE_3D ? gs.rec1 : gs.rec0, primitive == TS2D_PRIMITIVE_3D ? 2 : 3,
+                                                         primitive == TS2D_PRIMITIVE_3D ? 0 : 1, gs.dkey, opacity);
+        TS2D_CUDA_TRY(cudaGetLastError());
+    }
+    if (background_depth) TS2D_CUDA_TRY(cudaMemcpyAsync(background_depth, &gs.hdr->bg_bits, sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int ts2d_downsample(const float *in, float *out, int32_t planes, int32_t out_width, int32_t out_height, int32_t sc, void *stream)
+{
+    if (!in || !out) return TS2D_E_NULL;
+    if (planes < 1 || out_width < 1 || out_height < 1 || sc < 1 || (int64_t)out_width * sc * out_height * sc > ((int64_t)1 << 30)) return TS2D_E_SIZE;
+    const dim3 grid((out_width + 31) / 32, (out_height + 7) / 8, planes), block(32, 8);
+    k_downsample<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, out_width, out_height, sc);
+    return (int)cudaGetLastError();
+}
+
+int ts2d_downsample_bwd(const float *dL_dout, float *dL_din, int32_t planes, int32_t out_width, int32_t out_height, int32_t sc, void *stream)
+{
+    if (!dL_dout || !dL_din) return TS2D_E_NULL;
+    if (planes < 1 || out_width < 1 || out_height < 1 || sc < 1 || (int64_t)out_width * sc * out_height * sc > ((int64_t)1 << 30)) return TS2D_E_SIZE;
+    const dim3 grid((out_width * sc + 31) / 32, (out_height * sc + 7) / 8, planes), block(32, 8);
+    k_downsample_bwd<<<grid, block, 0, (cudaStream_t)stream>>>(dL_dout, dL_din, out_width, out_height, sc);
+    return (int)cudaGetLastError();
 }
 
 int ts2d_export_binning(const void *geometry_state, const void *binning_state, const void *image_state, int32_t P, int64_t R, int32_t W,

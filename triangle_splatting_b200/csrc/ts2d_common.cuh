@@ -34,7 +34,23 @@
 
 struct GeomHeader {
     int64_t num_rendered;
-    int64_t pad;
+    uint32_t bg_bits;  // model inputs: fp32 bit pattern of max ||campos - v|| (norms are >= 0, so unsigned order == float order)
+    uint32_t pad;
+};
+
+// Device-side view of ts2d_model_inputs (include/ts2d.h); `on == 0` is the reference-shaped call.
+struct ModelIn {
+    const float *f_dc, *f_rest, *logit;
+    float ste_thr, ratio;
+    uint32_t *bg_bits;  // non-NULL: K1 maxes ||campos - v|| into it
+    int on;
+};
+// Device-side view of ts2d_model_grads.
+struct ModelOut {
+    float *g_dc, *g_rest;
+    float *grad_accum, *grad_denom, *csum, *cmax, *cdenom, *max_radii;
+    const float *fwd_csum, *fwd_cmax;
+    int radii_div;
 };
 
 struct GeomState {
@@ -179,6 +195,44 @@ __device__ __forceinline__ float warp_sum(float v)
 
 // Host-side helpers shared by the .cu translation units
 static inline size_t ts2d_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline ModelIn ts2d_model_in(const ts2d_geometry *g, const GeomHeader *hdr)
+{
+    ModelIn m = {nullptr, nullptr, nullptr, -1.0f, 1.0f, nullptr, 0};
+    if (g->model) {
+        m.f_dc = g->model->f_dc;
+        m.f_rest = g->model->f_rest;
+        m.logit = g->model->opacity_logit;
+        m.ste_thr = g->model->ste_threshold;
+        m.ratio = g->model->rescale_ratio;
+        m.bg_bits = g->model->bg_depth_from_vertices ? const_cast<uint32_t *>(&hdr->bg_bits) : nullptr;
+        m.on = 1;
+    }
+    return m;
+}
+static inline ModelOut ts2d_model_out(const ts2d_backward_out *o)
+{
+    ModelOut m = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1};
+    if (o->model) {
+        const ts2d_model_grads *q = o->model;
+        m.g_dc = q->dL_df_dc;
+        m.g_rest = q->dL_df_rest;
+        m.grad_accum = q->gradient_accum;
+        m.grad_denom = q->gradient_denom;
+        m.csum = q->contrib_sum;
+        m.cmax = q->contrib_max;
+        m.cdenom = q->contrib_denom;
+        m.max_radii = q->max_radii2D;
+        m.fwd_csum = q->fwd_contrib_sum;
+        m.fwd_cmax = q->fwd_contrib_max;
+        m.radii_div = q->radii_div > 0 ? q->radii_div : 1;
+    }
+    return m;
+}
+// background depth the composite kernels use: the scalar of the reference-shaped call, or the device-computed maximum
+static inline const float *ts2d_bg_ptr(const ts2d_geometry *g, const GeomState &gs)
+{
+    return (g->model && g->model->bg_depth_from_vertices) ? reinterpret_cast<const float *>(&gs.hdr->bg_bits) : nullptr;
+}
 
 size_t ts2d_depth_sort_temp_bytes(int32_t P);
 size_t ts2d_tile_sort_temp_bytes(int64_t R);

@@ -19,9 +19,8 @@ struct TriGeom {
     float limx, limy;
 };
 
-__device__ __forceinline__ void tri_geom_view(const float *vp, const float *view, float tfx, float tfy, TriGeom &t, f3 &r1, f3 &r2, f3 &r3)
+__device__ __forceinline__ void tri_geom_view(f3 a, f3 b, f3 c, const float *view, float tfx, float tfy, TriGeom &t, f3 &r1, f3 &r2, f3 &r3)
 {
-    const f3 a = ld3(vp), b = ld3(vp + 3), c = ld3(vp + 6);
     t.center = (a + b + c) / 3.0f;
     t.center_view = xf_point(view, t.center);
     t.limx = 1.3f * tfx * t.center_view.z;
@@ -34,19 +33,31 @@ __device__ __forceinline__ void tri_geom_view(const float *vp, const float *view
 
 // TILED: the warp stages its 32 SH rows through shared memory with coalesced 16-byte loads (see warp_rows_load);
 // only the data movement changes -- the arithmetic on the coefficients is the same expression tree either way.
-template <bool TILED>
+// MODEL: parameter-space inputs (ts2d_model_inputs) -- raw vertices rescaled in registers, sigmoid / STE opacity, SH rows staged
+// from the split f_dc / f_rest tensors, background depth maxed into the header.  Same expression trees downstream.
+template <bool TILED, bool MODEL>
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_preprocess(int W, int H, int P, int D, int M, int C, bool rich, bool use_shs, int gx, int gy, bool back_culling, float tfx, float tfy,
              int shard_rank, int shard_world, const float *__restrict__ view, const float *__restrict__ proj, const float *__restrict__ campos,
              const float *__restrict__ vertex, const float *__restrict__ shs, const float *__restrict__ feature,
              const float *__restrict__ opacity, int32_t *__restrict__ radii, float4 *__restrict__ rec0, float4 *__restrict__ rec1,
              uint32_t *__restrict__ dkey, uint32_t *__restrict__ ids, uint32_t *__restrict__ tiles, ushort4 *__restrict__ rect,
-             uint8_t *__restrict__ clamp)
+             uint8_t *__restrict__ clamp, ModelIn mi)
 {
     extern __shared__ __align__(16) float s_rows[];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const float *sh_row = shs + (size_t)idx * M * 3;
-    if (TILED) {
+    if (MODEL) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int row0 = idx - lane, nrows = min(32, P - row0);
+        if (nrows <= 0) return;
+        const int rsf = (3 * M) | 1;
+        float *tile = s_rows + (size_t)warp * 32 * rsf;
+        warp_rows_load_split(mi.f_dc, mi.f_rest, tile, M, rsf, row0, nrows, lane);
+        if (mi.bg_bits) bg_depth_max(mi, vertex + 9 * (size_t)min(idx, P - 1), idx < P, ld3(campos));
+        __syncwarp();
+        sh_row = tile + lane * rsf;
+    } else if (TILED) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int row0 = idx - lane, nrows = min(32, P - row0);
         if (nrows <= 0) return;
@@ -69,11 +80,12 @@ k_preprocess(int W, int H, int P, int D, int M, int C, bool rich, bool use_shs, 
         {
             // near culling on the projected centre happens before the view transform in the reference;
             // order of evaluation does not change values.
-            const f3 a = ld3(vp), b = ld3(vp + 3), c = ld3(vp + 6);
+            f3 a, b, c;
+            load_tri<MODEL>(vp, mi, a, b, c);
             const f3 center = (a + b + c) / 3.0f;
             const f3 cproj = project_center(proj, center);
             if (cproj.z <= 0) break;
-            tri_geom_view(vp, view, tfx, tfy, t, r1, r2, r3);
+            tri_geom_view(a, b, c, view, tfx, tfy, t, r1, r2, r3);
             t.r1v = xf_vec(view, r1);
             t.r2v = xf_vec(view, r2);
             if (len3(cross3(t.r1v, t.r2v)) < TS2D_EPS) break;
@@ -118,7 +130,9 @@ k_preprocess(int W, int H, int P, int D, int M, int C, bool rich, bool use_shs, 
             clamp[idx] = mask;
             const float depth = t.center_view.z;
             rec0[3 * (size_t)idx + 0] = make_float4(s1.x, s1.y, s2.x, s2.y);
-            rec0[3 * (size_t)idx + 1] = make_float4(s3.x, s3.y, 1.0f / area2, opacity[idx]);  // reciprocal once per triangle, not per (tile, triangle)
+            float sig;
+            const float op = MODEL ? model_opacity(mi, idx, sig) : opacity[idx];
+            rec0[3 * (size_t)idx + 1] = make_float4(s3.x, s3.y, 1.0f / area2, op);  // reciprocal once per triangle, not per (tile, triangle)
             rec0[3 * (size_t)idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, area2);
             if (rich) {
                 f3 n = cross3(t.r1v, t.r2v);
@@ -159,15 +173,21 @@ int ts2d_launch_preprocess(const ts2d_camera *cam, const ts2d_geometry *g, const
 #define TS2D_K1_ARGS                                                                                                                          \
     cam->width, cam->height, P, g->sh_degree, g->M, g->C, f->rich_info != 0, g->use_shs != 0, gx, gy, f->back_culling != 0, cam->tan_fovx,    \
         cam->tan_fovy, f->shard_rank, f->shard_world, cam->viewmatrix, cam->projmatrix, cam->campos, g->vertex, g->shs, g->feature, g->opacity, \
-        radii, gs.rec0, gs.rec1, gs.dkey, gs.ids, gs.tiles, gs.rect, gs.clamp
+        radii, gs.rec0, gs.rec1, gs.dkey, gs.ids, gs.tiles, gs.rect, gs.clamp, mi
     // stage whole SH rows only when at least half of each row is actually read ((D+1)^2 of M coefficients)
     const int K = (g->sh_degree + 1) * (g->sh_degree + 1);
-    if (g->use_shs && ts2d_rows_tileable(g->M, g->shs, g->shs) && 2 * K >= g->M) {
+    const ModelIn mi = ts2d_model_in(g, gs.hdr);
+    if (mi.on) {
+        if (mi.bg_bits) TS2D_CUDA_TRY(cudaMemsetAsync(mi.bg_bits, 0, sizeof(uint32_t), s));
+        const size_t smem = (size_t)(TS2D_BLOCK / 32) * 32 * ts2d_split_row_stride(g->M) * sizeof(float);
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_preprocess<true, true><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K1_ARGS);
+    } else if (g->use_shs && ts2d_rows_tileable(g->M, g->shs, g->shs) && 2 * K >= g->M) {
         const size_t smem = (size_t)(TS2D_BLOCK / 32) * 32 * ((3 * g->M) / 4 + 1) * 16;
-        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_preprocess<true><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K1_ARGS);
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_preprocess<true, false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K1_ARGS);
     } else {
-        k_preprocess<false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(TS2D_K1_ARGS);
+        k_preprocess<false, false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(TS2D_K1_ARGS);
     }
 #undef TS2D_K1_ARGS
     return (int)cudaGetLastError();
@@ -195,13 +215,13 @@ __device__ __forceinline__ void project_offset_bwd(f3 p, f3 d, float tfx, float 
 
 
 
-template <bool TILED>
+template <bool TILED, bool MODEL>
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool rich, float tfx, float tfy, const float *__restrict__ view,
                  const float *__restrict__ proj, const float *__restrict__ campos, const float *__restrict__ vertex,
                  const float *__restrict__ shs, const int32_t *__restrict__ radii, const uint8_t *__restrict__ clamp,
                  const float4 *__restrict__ gacc, bool moments, const float4 *__restrict__ rec0, float *__restrict__ dL_dvertex, float *__restrict__ dL_dcenter2D, float *__restrict__ dL_dshs,
-                 float *__restrict__ dL_dfeature, float *__restrict__ dL_dopacity)
+                 float *__restrict__ dL_dfeature, float *__restrict__ dL_dopacity, ModelIn mi, ModelOut mo)
 {
     extern __shared__ __align__(16) float s_rows[];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -209,10 +229,17 @@ k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool ri
     const int row0 = idx - lane;                       // first triangle of this warp
     const int nrows = min(32, P - row0);               // <= 0: the whole warp is past the end
     const int q = (3 * M) / 4, rs4 = q + 1;            // float4 per row / tile row stride
-    float *tile_in = s_rows + (size_t)warp * 32 * rs4 * 4, *tile_out = tile_in;  // one tile: SH rows in, their gradients out, in place
+    const int rsf = (3 * M) | 1;                       // MODEL: row stride in floats
+    float *tile_in = s_rows + (size_t)warp * 32 * (MODEL ? rsf : rs4 * 4), *tile_out = tile_in;  // one tile: SH rows in, their gradients out, in place
     const float *sh_row = shs + (size_t)idx * M * 3;
     float *gsh_row = dL_dshs + (size_t)idx * M * 3;
-    if (TILED) {
+    if (MODEL) {
+        if (nrows <= 0) return;
+        if (D > 0) warp_rows_load_split(mi.f_dc, mi.f_rest, tile_in, M, rsf, row0, nrows, lane);
+        __syncwarp();
+        sh_row = tile_in + lane * rsf;
+        gsh_row = tile_out + lane * rsf;
+    } else if (TILED) {
         if (nrows <= 0) return;
         if (use_shs && D > 0) warp_rows_load(shs + (size_t)row0 * M * 3, tile_in, q, rs4, nrows, lane);
         __syncwarp();
@@ -257,7 +284,11 @@ k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool ri
     TriGeom t;
     f3 r1, r2, r3;
     const float *vp = vertex + 9 * (size_t)idx;
-    tri_geom_view(vp, view, tfx, tfy, t, r1, r2, r3);
+    {
+        f3 a, b, c;
+        load_tri<MODEL>(vp, mi, a, b, c);
+        tri_geom_view(a, b, c, view, tfx, tfy, t, r1, r2, r3);
+    }
     t.r1v = xf_vec(view, r1);
     t.r2v = xf_vec(view, r2);
     t.r3v = xf_vec(view, r3);
@@ -312,17 +343,30 @@ k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool ri
     } else {
         for (int k = 0; k < 3 * M; k++) gsh_row[k] = 0.0f;
     }
-    st3(ov, (2 * gr1 - gr2 - gr3 + gcenter) / 3.0f);
-    st3(ov + 3, (2 * gr2 - gr1 - gr3 + gcenter) / 3.0f);
-    st3(ov + 6, (2 * gr3 - gr1 - gr2 + gcenter) / 3.0f);
+    {
+        f3 gv1 = (2 * gr1 - gr2 - gr3 + gcenter) / 3.0f, gv2 = (2 * gr2 - gr1 - gr3 + gcenter) / 3.0f, gv3 = (2 * gr3 - gr1 - gr2 + gcenter) / 3.0f;
+        if (MODEL) rescale_bwd(mi, gv1, gv2, gv3);
+        st3(ov, gv1);
+        st3(ov + 3, gv2);
+        st3(ov + 6, gv3);
+    }
     dL_dcenter2D[2 * idx] = gc2d.x;
     dL_dcenter2D[2 * idx + 1] = gc2d.y;
     dL_dfeature[(size_t)idx * C + 0] = g_rgb.x;
     if (C > 1) dL_dfeature[(size_t)idx * C + 1] = g_rgb.y;
     if (C > 2) dL_dfeature[(size_t)idx * C + 2] = g_rgb.z;
-    dL_dopacity[idx] = g_op;
+    if (MODEL) {  // SigmoidBackward: grad * (1 - y) * y; the straight-through term passes the gradient unchanged
+        const float y = sigmoid_rn(mi.logit[idx]);
+        dL_dopacity[idx] = g_op * (1.0f - y) * y;
+        model_statistics(mo, idx, gc2d.x, gc2d.y, radii[idx]);
+    } else {
+        dL_dopacity[idx] = g_op;
+    }
     }  // live
-    if (TILED) {
+    if (MODEL) {
+        __syncwarp();
+        warp_rows_store_split(mo.g_dc, mo.g_rest, tile_out, M, rsf, row0, nrows, lane);
+    } else if (TILED) {
         __syncwarp();
         warp_rows_store(dL_dshs + (size_t)row0 * M * 3, tile_out, q, rs4, nrows, lane);
     }
@@ -332,18 +376,25 @@ int ts2d_launch_preprocess_bwd(const ts2d_camera *cam, const ts2d_geometry *g, c
                                const float *gacc, const ts2d_backward_out *out, cudaStream_t s)
 {
     const int P = g->P;
-    const bool tiled = ts2d_rows_tileable(g->M, g->shs ? (const void *)g->shs : (const void *)out->dL_dshs, out->dL_dshs);
+    const ModelIn mi = ts2d_model_in(g, gs.hdr);
+    const ModelOut mo = ts2d_model_out(out);
+    const bool tiled = !mi.on && ts2d_rows_tileable(g->M, g->shs ? (const void *)g->shs : (const void *)out->dL_dshs, out->dL_dshs);
 #define TS2D_K9_ARGS                                                                                                                         \
     cam->width, cam->height, P, g->sh_degree, g->M, g->C, g->use_shs != 0, f->rich_info != 0, cam->tan_fovx, cam->tan_fovy, cam->viewmatrix, \
         cam->projmatrix, cam->campos, g->vertex, g->shs, radii, gs.clamp, (const float4 *)gacc, ts2d_use_fast(g, f), gs.rec0, out->dL_dvertex, \
-        out->dL_dcenter2D, out->dL_dshs, out->dL_dfeature, out->dL_dopacity
-    if (tiled) {
+        out->dL_dcenter2D, out->dL_dshs, out->dL_dfeature, out->dL_dopacity, mi, mo
+    if (mi.on) {
+        const size_t smem = (size_t)(TS2D_BLOCK / 32) * 32 * ts2d_split_row_stride(g->M) * sizeof(float);
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess_bwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess_bwd<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        k_preprocess_bwd<true, true><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K9_ARGS);
+    } else if (tiled) {
         const size_t smem = (size_t)(TS2D_BLOCK / 32) * 32 * ((3 * g->M) / 4 + 1) * 16;
-        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess_bwd<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        k_preprocess_bwd<true><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K9_ARGS);
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess_bwd<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess_bwd<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        k_preprocess_bwd<true, false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K9_ARGS);
     } else {
-        k_preprocess_bwd<false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(TS2D_K9_ARGS);
+        k_preprocess_bwd<false, false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(TS2D_K9_ARGS);
     }
 #undef TS2D_K9_ARGS
     return (int)cudaGetLastError();

@@ -42,19 +42,29 @@ __device__ __forceinline__ uint32_t owned_tiles(uint32_t rx0, uint32_t ry0, uint
 }
 
 // ------------------------------------------------------------------------------------------------ K1 (3D)
-template <bool TILED>
+template <bool TILED, bool MODEL>  // MODEL: parameter-space inputs, see ts2d_preprocess.cu / ts2d_sh.cuh
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_preprocess3d(int W, int H, int P, int D, int M, int C, bool use_shs, int gx, int gy, bool back_culling, int shard_rank, int shard_world,
                const float *__restrict__ view, const float *__restrict__ proj, const float *__restrict__ campos,
                const float *__restrict__ vertex, const float *__restrict__ shs, const float *__restrict__ feature,
                const float *__restrict__ opacity, int32_t *__restrict__ radii, float4 *__restrict__ rec0, float4 *__restrict__ rec1,
                uint32_t *__restrict__ dkey, uint32_t *__restrict__ ids, uint32_t *__restrict__ tiles, ushort4 *__restrict__ rect,
-               uint8_t *__restrict__ clamp)
+               uint8_t *__restrict__ clamp, ModelIn mi)
 {
     extern __shared__ __align__(16) float s_rows[];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const float *sh_row = shs + (size_t)idx * M * 3;
-    if (TILED) {
+    if (MODEL) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int row0 = idx - lane, nrows = min(32, P - row0);
+        if (nrows <= 0) return;
+        const int rsf = (3 * M) | 1;
+        float *tile = s_rows + (size_t)warp * 32 * rsf;
+        warp_rows_load_split(mi.f_dc, mi.f_rest, tile, M, rsf, row0, nrows, lane);
+        if (mi.bg_bits) bg_depth_max(mi, vertex + 9 * (size_t)min(idx, P - 1), idx < P, ld3(campos));
+        __syncwarp();
+        sh_row = tile + lane * rsf;
+    } else if (TILED) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int row0 = idx - lane, nrows = min(32, P - row0);
         if (nrows <= 0) return;
@@ -71,7 +81,8 @@ k_preprocess3d(int W, int H, int P, int D, int M, int C, bool use_shs, int gx, i
     ushort4 out_rect = make_ushort4(0, 0, 0, 0);
     do {
         const float *vp = vertex + 9 * (size_t)idx;
-        const f3 v1 = ld3(vp), v2 = ld3(vp + 3), v3 = ld3(vp + 6);
+        f3 v1, v2, v3;
+        load_tri<MODEL>(vp, mi, v1, v2, v3);
         const f3 v1v = xf_point(view, v1), v2v = xf_point(view, v2), v3v = xf_point(view, v3);
         const f3 center_view = (v1v + v2v + v3v) / 3.0f;
         const f3 n = cross3(v2v - v1v, v3v - v1v);
@@ -105,7 +116,8 @@ k_preprocess3d(int W, int H, int P, int D, int M, int C, bool use_shs, int gx, i
         rec0[3 * (size_t)idx + 0] = make_float4(v1v.x, v1v.y, v1v.z, v2v.x);
         rec0[3 * (size_t)idx + 1] = make_float4(v2v.y, v2v.z, v3v.x, v3v.y);
         rec0[3 * (size_t)idx + 2] = make_float4(v3v.z, n.x, n.y, n.z);
-        rec1[2 * (size_t)idx + 0] = make_float4(rgb.x, rgb.y, rgb.z, opacity[idx]);
+        float sig;
+        rec1[2 * (size_t)idx + 0] = make_float4(rgb.x, rgb.y, rgb.z, MODEL ? model_opacity(mi, idx, sig) : opacity[idx]);
         {   // the two per-triangle subexpressions of the per-pair arithmetic (ts2d_prim3d.cuh: geo3), from the STORED values
             Tri3 t;
             t.v1 = v1v; t.v2 = v2v; t.v3 = v3v; t.n = n;
@@ -129,10 +141,11 @@ template <bool RICH>
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_render3d_fwd(int W, int H, int C, int gx, int shard_rank, int shard_world, int n_tiles, float two_gamma, float tfx, float tfy,
                const uint2 *__restrict__ ranges, const uint32_t *__restrict__ list, const float4 *__restrict__ rec0,
-               const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ background, float *__restrict__ final_T,
+               const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr, const float *__restrict__ background, float *__restrict__ final_T,
                uint32_t *__restrict__ n_contrib, float *__restrict__ out_feature, float *__restrict__ out_depth,
                float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max)
 {
+    if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     __shared__ float4 s_rec[TS2D_BLOCK * 4];
     __shared__ uint32_t s_id[TS2D_BLOCK];
 
@@ -271,10 +284,11 @@ template <bool RICH>
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_render3d_bwd(int W, int H, int C, int gx, int shard_rank, int shard_world, int n_tiles, float gamma, float tfx, float tfy,
                const uint2 *__restrict__ ranges, const uint32_t *__restrict__ list, const float4 *__restrict__ rec0,
-               const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ background, const float *__restrict__ final_T,
+               const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr, const float *__restrict__ background, const float *__restrict__ final_T,
                const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dout_feature, const float *__restrict__ dL_dout_depth,
                const float *__restrict__ dL_dout_normal, float *__restrict__ gacc)
 {
+    if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     __shared__ float4 s_rec[TS2D_BLOCK * 4];
     __shared__ uint32_t s_id[TS2D_BLOCK];
 
@@ -420,13 +434,13 @@ k_render3d_bwd(int W, int H, int C, int gx, int shard_rank, int shard_world, int
 }
 
 // ------------------------------------------------------------------------------------------------ K9 (3D)
-template <bool TILED>
+template <bool TILED, bool MODEL>
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_preprocess3d_bwd(int P, int D, int M, int C, bool use_shs, const float *__restrict__ view, const float *__restrict__ campos,
                    const float *__restrict__ vertex, const float *__restrict__ shs, const int32_t *__restrict__ radii,
                    const uint8_t *__restrict__ clamp, const float4 *__restrict__ gacc, const float4 *__restrict__ rec0,
                    float *__restrict__ dL_dvertex, float *__restrict__ dL_dcenter2D, float *__restrict__ dL_dshs,
-                   float *__restrict__ dL_dfeature, float *__restrict__ dL_dopacity)
+                   float *__restrict__ dL_dfeature, float *__restrict__ dL_dopacity, ModelIn mi, ModelOut mo)
 {
     extern __shared__ __align__(16) float s_rows[];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -434,10 +448,17 @@ k_preprocess3d_bwd(int P, int D, int M, int C, bool use_shs, const float *__rest
     const int row0 = idx - lane;
     const int nrows = min(32, P - row0);
     const int q = (3 * M) / 4, rs4 = q + 1;
-    float *tile = s_rows + (size_t)warp * 32 * rs4 * 4;  // SH rows in, their gradients out, in place
+    const int rsf = (3 * M) | 1;
+    float *tile = s_rows + (size_t)warp * 32 * (MODEL ? rsf : rs4 * 4);  // SH rows in, their gradients out, in place
     const float *sh_row = shs + (size_t)idx * M * 3;
     float *gsh_row = dL_dshs + (size_t)idx * M * 3;
-    if (TILED) {
+    if (MODEL) {
+        if (nrows <= 0) return;
+        if (D > 0) warp_rows_load_split(mi.f_dc, mi.f_rest, tile, M, rsf, row0, nrows, lane);
+        __syncwarp();
+        sh_row = tile + lane * rsf;
+        gsh_row = tile + lane * rsf;
+    } else if (TILED) {
         if (nrows <= 0) return;
         if (use_shs && D > 0) warp_rows_load(shs + (size_t)row0 * M * 3, tile, q, rs4, nrows, lane);
         __syncwarp();
@@ -468,7 +489,9 @@ k_preprocess3d_bwd(int P, int D, int M, int C, bool use_shs, const float *__rest
         f3 g1 = xf_vec_T(view, g1v), g2 = xf_vec_T(view, g2v), g3 = xf_vec_T(view, g3v);
         if (use_shs) {
             const float *vp = vertex + 9 * (size_t)idx;
-            const f3 center = (ld3(vp) + ld3(vp + 3) + ld3(vp + 6)) / 3.0f;
+            f3 w1, w2, w3;
+            load_tri<MODEL>(vp, mi, w1, w2, w3);
+            const f3 center = (w1 + w2 + w3) / 3.0f;
             const f3 gsh = sh_colour_bwd(D, M, sh_row, center, ld3(campos), clamp[idx], g_rgb, gsh_row);
             g1 = g1 + gsh / 3.0f;
             g2 = g2 + gsh / 3.0f;
@@ -477,18 +500,28 @@ k_preprocess3d_bwd(int P, int D, int M, int C, bool use_shs, const float *__rest
             for (int k = 0; k < 3 * M; k++) gsh_row[k] = 0.0f;
         }
         float *ov = dL_dvertex + 9 * (size_t)idx;
+        const f3 gcv = xf_vec(view, g1 + g2 + g3);  // w.r.t. the vertices the rasterizer saw (the rescaled ones with model inputs)
+        if (MODEL) rescale_bwd(mi, g1, g2, g3);
         st3(ov, g1);
         st3(ov + 3, g2);
         st3(ov + 6, g3);
-        const f3 gcv = xf_vec(view, g1 + g2 + g3);
         dL_dcenter2D[2 * idx] = gcv.x;
         dL_dcenter2D[2 * idx + 1] = gcv.y;
         dL_dfeature[(size_t)idx * C + 0] = g_rgb.x;
         if (C > 1) dL_dfeature[(size_t)idx * C + 1] = g_rgb.y;
         if (C > 2) dL_dfeature[(size_t)idx * C + 2] = g_rgb.z;
-        dL_dopacity[idx] = g_op;
+        if (MODEL) {
+            const float y = sigmoid_rn(mi.logit[idx]);
+            dL_dopacity[idx] = g_op * (1.0f - y) * y;
+            model_statistics(mo, idx, gcv.x, gcv.y, radii[idx]);
+        } else {
+            dL_dopacity[idx] = g_op;
+        }
     }
-    if (TILED) {
+    if (MODEL) {
+        __syncwarp();
+        warp_rows_store_split(mo.g_dc, mo.g_rest, tile, M, rsf, row0, nrows, lane);
+    } else if (TILED) {
         __syncwarp();
         warp_rows_store(dL_dshs + (size_t)row0 * M * 3, tile, q, rs4, nrows, lane);
     }
@@ -532,14 +565,20 @@ int ts2d_launch_preprocess3d(const ts2d_camera *cam, const ts2d_geometry *g, con
 #define TS2D_K1_ARGS                                                                                                                      \
     cam->width, cam->height, P, g->sh_degree, g->M, g->C, g->use_shs != 0, gx, gy, f->back_culling != 0, f->shard_rank, f->shard_world,    \
         cam->viewmatrix, cam->projmatrix, cam->campos, g->vertex, g->shs, g->feature, g->opacity, radii, gs.rec0, gs.rec1, gs.dkey, gs.ids, \
-        gs.tiles, gs.rect, gs.clamp
+        gs.tiles, gs.rect, gs.clamp, mi
     const int K = (g->sh_degree + 1) * (g->sh_degree + 1);
-    if (g->use_shs && ts2d_rows_tileable(g->M, g->shs, g->shs) && 2 * K >= g->M) {
+    const ModelIn mi = ts2d_model_in(g, gs.hdr);
+    if (mi.on) {
+        if (mi.bg_bits) TS2D_CUDA_TRY(cudaMemsetAsync(mi.bg_bits, 0, sizeof(uint32_t), s));
+        const size_t smem = (size_t)(TS2D_BLOCK / 32) * 32 * ts2d_split_row_stride(g->M) * sizeof(float);
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess3d<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_preprocess3d<true, true><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K1_ARGS);
+    } else if (g->use_shs && ts2d_rows_tileable(g->M, g->shs, g->shs) && 2 * K >= g->M) {
         const size_t smem = (size_t)(TS2D_BLOCK / 32) * 32 * ((3 * g->M) / 4 + 1) * 16;
-        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_preprocess3d<true><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K1_ARGS);
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess3d<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_preprocess3d<true, false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K1_ARGS);
     } else {
-        k_preprocess3d<false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(TS2D_K1_ARGS);
+        k_preprocess3d<false, false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(TS2D_K1_ARGS);
     }
 #undef TS2D_K1_ARGS
     return (int)cudaGetLastError();
@@ -556,7 +595,7 @@ int ts2d_launch_render3d_fwd(const ts2d_camera *cam, const ts2d_geometry *g, con
     const float two_gamma = 2.0f * g->gamma;
 #define TS2D_F3_ARGS                                                                                                                        \
     W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, two_gamma, cam->tan_fovx, cam->tan_fovy, is.ranges, list, gs.rec0, gs.rec1,      \
-        g->background_depth, g->background, is.final_T, is.n_contrib, out->out_feature
+        g->background_depth, ts2d_bg_ptr(g, gs), g->background, is.final_T, is.n_contrib, out->out_feature
     if (f->rich_info) {
         TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_sum, 0, sizeof(float) * (size_t)g->P, s));
         TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
@@ -579,7 +618,7 @@ int ts2d_launch_render3d_bwd(const ts2d_camera *cam, const ts2d_geometry *g, con
     if (owned <= 0) return 0;
 #define TS2D_B3_ARGS                                                                                                                        \
     W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, cam->tan_fovx, cam->tan_fovy, is.ranges, list, gs.rec0, gs.rec1,       \
-        g->background_depth, g->background, is.final_T, is.n_contrib, loss->dL_dout_feature
+        g->background_depth, ts2d_bg_ptr(g, gs), g->background, is.final_T, is.n_contrib, loss->dL_dout_feature
     if (f->rich_info) k_render3d_bwd<true><<<owned, TS2D_BLOCK, 0, s>>>(TS2D_B3_ARGS, loss->dL_dout_depth, loss->dL_dout_normal, gacc);
     else k_render3d_bwd<false><<<owned, TS2D_BLOCK, 0, s>>>(TS2D_B3_ARGS, nullptr, nullptr, gacc);
 #undef TS2D_B3_ARGS
@@ -591,17 +630,24 @@ int ts2d_launch_preprocess3d_bwd(const ts2d_camera *cam, const ts2d_geometry *g,
 {
     (void)f;
     const int P = g->P;
-    const bool tiled = ts2d_rows_tileable(g->M, g->shs ? (const void *)g->shs : (const void *)out->dL_dshs, out->dL_dshs);
+    const ModelIn mi = ts2d_model_in(g, gs.hdr);
+    const ModelOut mo = ts2d_model_out(out);
+    const bool tiled = !mi.on && ts2d_rows_tileable(g->M, g->shs ? (const void *)g->shs : (const void *)out->dL_dshs, out->dL_dshs);
 #define TS2D_K9_ARGS                                                                                                                   \
     P, g->sh_degree, g->M, g->C, g->use_shs != 0, cam->viewmatrix, cam->campos, g->vertex, g->shs, radii, gs.clamp, (const float4 *)gacc, \
-        gs.rec0, out->dL_dvertex, out->dL_dcenter2D, out->dL_dshs, out->dL_dfeature, out->dL_dopacity
-    if (tiled) {
+        gs.rec0, out->dL_dvertex, out->dL_dcenter2D, out->dL_dshs, out->dL_dfeature, out->dL_dopacity, mi, mo
+    if (mi.on) {
+        const size_t smem = (size_t)(TS2D_BLOCK / 32) * 32 * ts2d_split_row_stride(g->M) * sizeof(float);
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess3d_bwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess3d_bwd<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        k_preprocess3d_bwd<true, true><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K9_ARGS);
+    } else if (tiled) {
         const size_t smem = (size_t)(TS2D_BLOCK / 32) * 32 * ((3 * g->M) / 4 + 1) * 16;
-        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess3d_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess3d_bwd<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        k_preprocess3d_bwd<true><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K9_ARGS);
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess3d_bwd<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess3d_bwd<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        k_preprocess3d_bwd<true, false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K9_ARGS);
     } else {
-        k_preprocess3d_bwd<false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(TS2D_K9_ARGS);
+        k_preprocess3d_bwd<false, false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(TS2D_K9_ARGS);
     }
 #undef TS2D_K9_ARGS
     return (int)cudaGetLastError();

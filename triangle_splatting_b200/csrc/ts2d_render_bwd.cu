@@ -56,11 +56,12 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane)
 template <bool RICH>
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_render_bwd(int W, int H, int C, int gx, int shard_rank, int shard_world, int n_tiles, float gamma, const uint2 *__restrict__ ranges,
-             const uint32_t *__restrict__ list, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1, float bg_depth,
+             const uint32_t *__restrict__ list, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr,
              const float *__restrict__ background, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
              const float *__restrict__ dL_dout_feature, const float *__restrict__ dL_dout_depth, const float *__restrict__ dL_dout_normal,
              float *__restrict__ gacc)
 {
+    if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     __shared__ float4 s_rec0[TS2D_BLOCK * 3];
     __shared__ float4 s_rec1[RICH ? TS2D_BLOCK * 2 : 1];
     __shared__ uint32_t s_id[TS2D_BLOCK];
@@ -209,11 +210,11 @@ int ts2d_launch_render_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const
     if (owned <= 0) return 0;
     if (f->rich_info) {
         k_render_bwd<true><<<owned, TS2D_BLOCK, 0, s>>>(W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, list, gs.rec0,
-                                                        gs.rec1, g->background_depth, g->background, is.final_T, is.n_contrib,
+                                                        gs.rec1, g->background_depth, ts2d_bg_ptr(g, gs), g->background, is.final_T, is.n_contrib,
                                                         loss->dL_dout_feature, loss->dL_dout_depth, loss->dL_dout_normal, gacc);
     } else {
         k_render_bwd<false><<<owned, TS2D_BLOCK, 0, s>>>(W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, list, gs.rec0,
-                                                         gs.rec1, g->background_depth, g->background, is.final_T, is.n_contrib,
+                                                         gs.rec1, g->background_depth, ts2d_bg_ptr(g, gs), g->background, is.final_T, is.n_contrib,
                                                          loss->dL_dout_feature, nullptr, nullptr, gacc);
     }
     return (int)cudaGetLastError();

@@ -144,10 +144,11 @@ template <bool RICH, bool GAMMA1>
 __global__ void __launch_bounds__(TS2D_BLOCK, 4)
 k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world, int n_tiles, float gamma, const uint2 *__restrict__ ranges,
                   const uint32_t *__restrict__ keys, const uint32_t *__restrict__ list, const float4 *__restrict__ rec0,
-                  const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ background, const float *__restrict__ final_T,
+                  const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr, const float *__restrict__ background, const float *__restrict__ final_T,
                   const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dout_feature, const float *__restrict__ dL_dout_depth,
                   const float *__restrict__ dL_dout_normal, float *__restrict__ gacc)
 {
+    if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     using L = BwdLayout<RICH>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -327,7 +328,7 @@ int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
     if (owned <= 0) return 0;
     const bool g1 = g->gamma == 1.0f;
 #define TS2D_BWD_ARGS                                                                                                                 \
-    W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, keys, list, gs.rec0, gs.rec1, g->background_depth,   \
+    W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, keys, list, gs.rec0, gs.rec1, g->background_depth, ts2d_bg_ptr(g, gs),   \
         g->background, is.final_T, is.n_contrib, loss->dL_dout_feature
 #define TS2D_BWD_LAUNCH(R, G, ...)                                                                                                      \
     do {                                                                                                                                \

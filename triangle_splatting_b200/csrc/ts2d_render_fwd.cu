@@ -18,10 +18,11 @@
 template <bool RICH>
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_render_fwd(int W, int H, int C, int gx, int shard_rank, int shard_world, int n_tiles, float two_gamma, const uint2 *__restrict__ ranges,
-             const uint32_t *__restrict__ list, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1, float bg_depth,
+             const uint32_t *__restrict__ list, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr,
              const float *__restrict__ background, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib, float *__restrict__ out_feature,
              float *__restrict__ out_depth, float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max)
 {
+    if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     __shared__ float4 s_rec0[TS2D_BLOCK * 3];
     __shared__ float4 s_rec1[RICH ? TS2D_BLOCK * 2 : 1];
     __shared__ uint32_t s_id[TS2D_BLOCK];
@@ -133,11 +134,11 @@ int ts2d_launch_render_fwd(const ts2d_camera *cam, const ts2d_geometry *g, const
         TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_sum, 0, sizeof(float) * (size_t)g->P, s));
         TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
         k_render_fwd<true><<<owned, TS2D_BLOCK, 0, s>>>(W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, two_gamma, is.ranges, list,
-                                                        gs.rec0, gs.rec1, g->background_depth, g->background, is.final_T, is.n_contrib,
+                                                        gs.rec0, gs.rec1, g->background_depth, ts2d_bg_ptr(g, gs), g->background, is.final_T, is.n_contrib,
                                                         out->out_feature, out->depth, out->normal, out->contrib_sum, out->contrib_max);
     } else {
         k_render_fwd<false><<<owned, TS2D_BLOCK, 0, s>>>(W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, two_gamma, is.ranges, list,
-                                                         gs.rec0, gs.rec1, g->background_depth, g->background, is.final_T, is.n_contrib,
+                                                         gs.rec0, gs.rec1, g->background_depth, ts2d_bg_ptr(g, gs), g->background, is.final_T, is.n_contrib,
                                                          out->out_feature, nullptr, nullptr, nullptr, nullptr);
     }
     return (int)cudaGetLastError();

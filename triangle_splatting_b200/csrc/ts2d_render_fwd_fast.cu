@@ -84,10 +84,11 @@ template <bool RICH, bool GAMMA1>
 __global__ void __launch_bounds__(TS2D_BLOCK, TS2D_FWD_MINB)
 k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, int n_tiles, float gamma, const uint2 *__restrict__ ranges,
                   const uint32_t *__restrict__ keys, const uint32_t *__restrict__ list, const float4 *__restrict__ rec0,
-                  const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ background, float *__restrict__ final_T,
+                  const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr, const float *__restrict__ background, float *__restrict__ final_T,
                   uint32_t *__restrict__ n_contrib, float *__restrict__ out_feature, float *__restrict__ out_depth,
                   float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max)
 {
+    if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     using L = FwdLayout<RICH>;
     extern __shared__ __align__(16) unsigned char s_raw[];
 
@@ -262,7 +263,7 @@ int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
     if (owned <= 0) return 0;
     const bool g1 = g->gamma == 1.0f;
 #define TS2D_FWD_ARGS                                                                                                                       \
-    W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, keys, list, gs.rec0, gs.rec1, g->background_depth,         \
+    W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, keys, list, gs.rec0, gs.rec1, g->background_depth, ts2d_bg_ptr(g, gs),         \
         g->background, is.final_T, is.n_contrib, out->out_feature
 #define TS2D_FWD_LAUNCH(R, G, ...)                                                                                                     \
     do {                                                                                                                               \

@@ -45,6 +45,125 @@ __device__ __forceinline__ void warp_rows_store(float *__restrict__ g, const flo
         if (c >= q) { c -= q; r++; }
     }
 }
+// ---- parameter-space inputs (ts2d_model_inputs): the model's Python preamble done in registers -------------------
+// Every helper keeps the operation order of the torch kernels the preamble launches (src/diff_recon/models/VanillaTS_model.py),
+// with explicit round-to-nearest intrinsics so that no neighbouring code can be contracted into it: the values that reach the
+// reference-order geometry code are bit-identical to the tensors the reference would have materialised.
+
+// _rescale_triangles (:431-447): t_center = vertex.mean(dim=1, keepdim=True) -- torch's reduce kernel sums the three vertices in
+// order in one thread and multiplies by float(1/3); (vertex - t_center) * ratio + t_center is three separate elementwise kernels.
+__device__ __forceinline__ float rescale1(float v, float c, float ratio) { return __fadd_rn(__fmul_rn(__fsub_rn(v, c), ratio), c); }
+template <bool MODEL>
+__device__ __forceinline__ void load_tri(const float *vp, const ModelIn &mi, f3 &a, f3 &b, f3 &c)
+{
+    a = ld3(vp);
+    b = ld3(vp + 3);
+    c = ld3(vp + 6);
+    if (MODEL && mi.ratio != 1.0f) {
+        const float third = 1.0f / 3.0f;
+        const f3 m = mk3(__fmul_rn(__fadd_rn(__fadd_rn(a.x, b.x), c.x), third), __fmul_rn(__fadd_rn(__fadd_rn(a.y, b.y), c.y), third),
+                         __fmul_rn(__fadd_rn(__fadd_rn(a.z, b.z), c.z), third));
+        a = mk3(rescale1(a.x, m.x, mi.ratio), rescale1(a.y, m.y, mi.ratio), rescale1(a.z, m.z, mi.ratio));
+        b = mk3(rescale1(b.x, m.x, mi.ratio), rescale1(b.y, m.y, mi.ratio), rescale1(b.z, m.z, mi.ratio));
+        c = mk3(rescale1(c.x, m.x, mi.ratio), rescale1(c.y, m.y, mi.ratio), rescale1(c.z, m.z, mi.ratio));
+    }
+}
+// adjoint of the rescale map: g_i -> ratio * g_i + (1 - ratio) / 3 * (g_1 + g_2 + g_3)
+__device__ __forceinline__ void rescale_bwd(const ModelIn &mi, f3 &g1, f3 &g2, f3 &g3)
+{
+    if (mi.ratio != 1.0f) {
+        const f3 sum = (g1 + g2) + g3;
+        const f3 gc = (sum - mi.ratio * sum) / 3.0f;
+        g1 = mi.ratio * g1 + gc;
+        g2 = mi.ratio * g2 + gc;
+        g3 = mi.ratio * g3 + gc;
+    }
+}
+// get_opacity (:84) = torch.sigmoid: 1 / (1 + exp(-x)) in fp32 with the accurate expf and an IEEE divide;
+// straight-through binarisation (:620-621): ((opacity > thr).float() - opacity).detach() + opacity.
+__device__ __forceinline__ float sigmoid_rn(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+__device__ __forceinline__ float model_opacity(const ModelIn &mi, int idx, float &sig)
+{
+    sig = sigmoid_rn(mi.logit[idx]);
+    if (mi.ste_thr >= 0.0f) return __fadd_rn(__fsub_rn(sig > mi.ste_thr ? 1.0f : 0.0f, sig), sig);
+    return sig;
+}
+// bg_depth = (camera_center - vertex).norm(dim=-1).max() (:623) over the UN-rescaled vertices of every triangle (culled or not).
+// One atomic per warp at most, and only while the running maximum is still below the warp's.
+__device__ __forceinline__ void bg_depth_max(const ModelIn &mi, const float *vp, bool valid, f3 cam)
+{
+    float m = 0.0f;
+    if (valid) {
+        const f3 a = cam - ld3(vp), b = cam - ld3(vp + 3), c = cam - ld3(vp + 6);
+        m = fmaxf(fmaxf(len3(a), len3(b)), len3(c));
+    }
+    const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0 && w > *(volatile uint32_t *)mi.bg_bits) atomicMax(mi.bg_bits, w);
+}
+
+// SH rows from the split parameters: tile row r = [f_dc[r] (3 floats) | f_rest[r] (3(M-1) floats)], row stride rsf floats (odd,
+// so the per-thread scalar reads of sh_colour are bank-conflict free).  Both sources are contiguous 32-row blocks; the f_rest
+// block starts 16-byte aligned (row0 is a multiple of 32) and is moved with 16-byte loads, scattered element-wise.
+__device__ __forceinline__ void warp_rows_load_split(const float *__restrict__ f_dc, const float *__restrict__ f_rest, float *tile, int M,
+                                                     int rsf, int row0, int nrows, int lane)
+{
+    for (int i = lane; i < 3 * nrows; i += 32) tile[(i / 3) * rsf + (i % 3)] = __ldg(f_dc + 3 * (size_t)row0 + i);
+    const int L = 3 * (M - 1), n = nrows * L;
+    if (L == 0) return;
+    const float *src = f_rest + (size_t)row0 * L;
+    const int n4 = (((uintptr_t)src & 15) == 0) ? n / 4 : 0;
+    int r = (4 * lane) / L, c = 4 * lane - r * L;
+    const int dr = 128 / L, dc = 128 - dr * L;
+    for (int e = lane; e < n4; e += 32) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + e);
+        int rr = r, cc = c;
+        tile[rr * rsf + 3 + cc] = v.x; if (++cc == L) { cc = 0; rr++; }
+        tile[rr * rsf + 3 + cc] = v.y; if (++cc == L) { cc = 0; rr++; }
+        tile[rr * rsf + 3 + cc] = v.z; if (++cc == L) { cc = 0; rr++; }
+        tile[rr * rsf + 3 + cc] = v.w;
+        r += dr;
+        c += dc;
+        if (c >= L) { c -= L; r++; }
+    }
+    for (int i = 4 * n4 + lane; i < n; i += 32) tile[(i / L) * rsf + 3 + (i % L)] = __ldg(src + i);
+}
+__device__ __forceinline__ void warp_rows_store_split(float *__restrict__ g_dc, float *__restrict__ g_rest, const float *tile, int M, int rsf,
+                                                      int row0, int nrows, int lane)
+{
+    for (int i = lane; i < 3 * nrows; i += 32) g_dc[3 * (size_t)row0 + i] = tile[(i / 3) * rsf + (i % 3)];
+    const int L = 3 * (M - 1), n = nrows * L;
+    if (L == 0) return;
+    float *dst = g_rest + (size_t)row0 * L;
+    const int n4 = (((uintptr_t)dst & 15) == 0) ? n / 4 : 0;
+    int r = (4 * lane) / L, c = 4 * lane - r * L;
+    const int dr = 128 / L, dc = 128 - dr * L;
+    for (int e = lane; e < n4; e += 32) {
+        float4 v;
+        int rr = r, cc = c;
+        v.x = tile[rr * rsf + 3 + cc]; if (++cc == L) { cc = 0; rr++; }
+        v.y = tile[rr * rsf + 3 + cc]; if (++cc == L) { cc = 0; rr++; }
+        v.z = tile[rr * rsf + 3 + cc]; if (++cc == L) { cc = 0; rr++; }
+        v.w = tile[rr * rsf + 3 + cc];
+        reinterpret_cast<float4 *>(dst)[e] = v;
+        r += dr;
+        c += dc;
+        if (c >= L) { c -= L; r++; }
+    }
+    for (int i = 4 * n4 + lane; i < n; i += 32) dst[i] = tile[(i / L) * rsf + 3 + (i % L)];
+}
+static inline int ts2d_split_row_stride(int M) { return (3 * M) | 1; }
+
+// VanillaTS_model.py:347-363 (_training_statistic) for one visible triangle (radii > 0), fused into the K9 tail.
+__device__ __forceinline__ void model_statistics(const ModelOut &mo, int idx, float gcx, float gcy, int radius)
+{
+    if (mo.grad_accum) mo.grad_accum[idx] += sqrtf(gcx * gcx + gcy * gcy);
+    if (mo.grad_denom) mo.grad_denom[idx] += 1.0f;
+    if (mo.csum) mo.csum[idx] = fmaxf(mo.csum[idx], mo.fwd_csum[idx]);
+    if (mo.cmax) mo.cmax[idx] = fmaxf(mo.cmax[idx], mo.fwd_cmax[idx]);
+    if (mo.cdenom) mo.cdenom[idx] += 1.0f;
+    if (mo.max_radii) mo.max_radii[idx] = fmaxf(mo.max_radii[idx], (float)(radius / mo.radii_div));
+}
+
 static inline bool ts2d_rows_tileable(int M, const void *a, const void *b)
 {
     return M > 0 && (3 * M) % 4 == 0 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0;
