@@ -25,10 +25,12 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/ts2d.h"
 
 #define TS2D_BLOCK 256
+#define TS2D_DEFAULT_CTA_WARPS 1
 #define TS2D_EPS 1e-8f  // R2D/src/auxiliary.h:8
 #define TS2D_MASK_BITS 8  // low bits of an instance key: coverage of the tile's eight 8x4 sub-tiles (ts2d_fast.cuh)
 
@@ -227,6 +229,17 @@ static inline ModelOut ts2d_model_out(const ts2d_backward_out *o)
         m.radii_div = q->radii_div > 0 ? q->radii_div : 1;
     }
     return m;
+}
+// warps per CTA of the fast composite kernels (tuning knob for experiments: TS2D_CTA_WARPS = 1 | 2 | 4 | 8)
+static inline int ts2d_cta_warps()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("TS2D_CTA_WARPS");
+        v = e ? atoi(e) : TS2D_DEFAULT_CTA_WARPS;
+        if (v != 1 && v != 2 && v != 4 && v != 8) v = TS2D_DEFAULT_CTA_WARPS;
+    }
+    return v;
 }
 // background depth the composite kernels use: the scalar of the reference-shaped call, or the device-computed maximum
 static inline const float *ts2d_bg_ptr(const ts2d_geometry *g, const GeomState &gs)

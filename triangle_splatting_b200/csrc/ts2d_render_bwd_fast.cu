@@ -140,8 +140,8 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
     __syncwarp();
 }
 
-template <bool RICH, bool GAMMA1>
-__global__ void __launch_bounds__(TS2D_BLOCK, 4)
+template <bool RICH, bool GAMMA1, int CW>  // CW = warps per CTA, see k_render_fwd_fast
+__global__ void __launch_bounds__(32 * CW, 32 / CW)
 k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world, int n_tiles, float gamma, const uint2 *__restrict__ ranges,
                   const uint32_t *__restrict__ keys, const uint32_t *__restrict__ list, const float4 *__restrict__ rec0,
                   const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr, const float *__restrict__ background, const float *__restrict__ final_T,
@@ -152,10 +152,11 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
     using L = BwdLayout<RICH>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
-    const int tile = blockIdx.x * shard_world + shard_rank;
+    constexpr int PARTS = 8 / CW;
+    const int tile = (blockIdx.x / PARTS) * shard_world + shard_rank;
     if (tile >= n_tiles) return;
     const int tile_x = tile % gx, tile_y = tile / gx;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lwarp = tid >> 5, warp = (blockIdx.x % PARTS) * CW + lwarp, lane = tid & 31;
     const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
     const int px = tile_x * TS2D_TILE + lx, py = tile_y * TS2D_TILE + ly;
     const bool inside = px < W_ && py < H;
@@ -165,7 +166,7 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
     const size_t HW = (size_t)H * W_;
     GammaK gk = make_gamma(GAMMA1 ? 1.0f : gamma);  // gamma == 1: every constant of the error model folds to an immediate
     gk.is_one = GAMMA1;
-    const uint32_t sb = smem_base(smem_raw + warp * L::BYTES);  // this warp's block
+    const uint32_t sb = smem_base(smem_raw + lwarp * L::BYTES);  // this warp's block
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     const uint2 range = ranges[tile];
@@ -330,12 +331,21 @@ int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
 #define TS2D_BWD_ARGS                                                                                                                 \
     W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, keys, list, gs.rec0, gs.rec1, g->background_depth, ts2d_bg_ptr(g, gs),   \
         g->background, is.final_T, is.n_contrib, loss->dL_dout_feature
+#define TS2D_BWD_LAUNCH_CW(R, G, CW, ...)                                                                                               \
+    do {                                                                                                                                \
+        const size_t smem = CW * (size_t)BwdLayout<R>::BYTES;                                                                           \
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_bwd_fast<R, G, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_bwd_fast<R, G, CW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));          \
+        k_render_bwd_fast<R, G, CW><<<owned * (8 / CW), 32 * CW, smem, s>>>(TS2D_BWD_ARGS, __VA_ARGS__, gacc);                          \
+    } while (0)
 #define TS2D_BWD_LAUNCH(R, G, ...)                                                                                                      \
     do {                                                                                                                                \
-        const size_t smem = 8 * (size_t)BwdLayout<R>::BYTES;                                                                            \
-        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_bwd_fast<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_bwd_fast<R, G>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));              \
-        k_render_bwd_fast<R, G><<<owned, TS2D_BLOCK, smem, s>>>(TS2D_BWD_ARGS, __VA_ARGS__, gacc);                                      \
+        switch (ts2d_cta_warps()) {                                                                                                     \
+        case 1: TS2D_BWD_LAUNCH_CW(R, G, 1, __VA_ARGS__); break;                                                                        \
+        case 2: TS2D_BWD_LAUNCH_CW(R, G, 2, __VA_ARGS__); break;                                                                        \
+        case 4: TS2D_BWD_LAUNCH_CW(R, G, 4, __VA_ARGS__); break;                                                                        \
+        default: TS2D_BWD_LAUNCH_CW(R, G, 8, __VA_ARGS__); break;                                                                       \
+        }                                                                                                                               \
     } while (0)
     if (f->rich_info) {
         if (g1) TS2D_BWD_LAUNCH(true, true, loss->dL_dout_depth, loss->dL_dout_normal);
@@ -345,6 +355,7 @@ int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
         else TS2D_BWD_LAUNCH(false, false, nullptr, nullptr);
     }
 #undef TS2D_BWD_LAUNCH
+#undef TS2D_BWD_LAUNCH_CW
 #undef TS2D_BWD_ARGS
     return (int)cudaGetLastError();
 }
