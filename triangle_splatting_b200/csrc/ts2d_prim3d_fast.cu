@@ -112,10 +112,10 @@ __device__ __noinline__ float exact_T_upto3(const uint32_t *__restrict__ list, c
 }
 
 // ------------------------------------------------------------------------------------------------ K7 (3D, fast)
-template <bool RICH, bool GAMMA1>
-__global__ void __launch_bounds__(TS2D_BLOCK, 3)
+template <bool RICH, bool GAMMA1, int CW>  // CW = warps per CTA (see k_render_fwd_fast): a CTA is only a unit of residency here
+__global__ void __launch_bounds__(32 * CW, 24 / CW)
 k_render3d_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, int n_tiles, float gamma, float tfx, float tfy,
-                    const uint2 *__restrict__ ranges, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ list,
+                    const uint2 *__restrict__ ranges, const uint32_t *keys, const uint32_t *__restrict__ list,
                     const float4 *__restrict__ rec0, const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr, const float *__restrict__ background,
                     float *__restrict__ final_T, uint32_t *__restrict__ n_contrib, float *__restrict__ out_feature, float *__restrict__ out_depth,
                     float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max)
@@ -124,16 +124,17 @@ k_render3d_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world
     using L = Fwd3Layout<RICH>;
     extern __shared__ __align__(16) unsigned char s_raw[];
 
-    const int tile = blockIdx.x * shard_world + shard_rank;
+    constexpr int PARTS = 8 / CW;
+    const int tile = (blockIdx.x / PARTS) * shard_world + shard_rank;
     if (tile >= n_tiles) return;
     const int tile_x = tile % gx, tile_y = tile / gx;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lwarp = tid >> 5, warp = (blockIdx.x % PARTS) * CW + lwarp, lane = tid & 31;
     const int px = tile_x * TS2D_TILE + (warp & 1) * 8 + (lane & 7);
     const int py = tile_y * TS2D_TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < W && py < H;
     const f3 ray = pixel_ray(px, py, W, H, tfx, tfy);
     const Gamma3 gk = make_gamma3(GAMMA1 ? 1.0f : gamma, GAMMA1);
-    const uint32_t sb = smem_base(s_raw + warp * L::BYTES);
+    const uint32_t sb = smem_base(s_raw + lwarp * L::BYTES);
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     const uint2 range = ranges[tile];
@@ -158,6 +159,8 @@ k_render3d_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world
                 atomicAdd(contrib_sum + id, s);
                 atomicMax((unsigned int *)contrib_max + id, __float_as_uint(m));  // contrib >= 0: bit order == value order
             }
+            // (No coverage-bit clearing here, unlike the 2D kernel: the 3D reference's backward takes its skip decision on
+            // G < 1/255 instead of alpha < 1/255 (R3D/src/backward.cu:351), so it visits pairs the forward never blended.)
         }
     };
 
@@ -380,8 +383,8 @@ static __device__ __noinline__ void bwd3_flush_panel(uint32_t wb, uint32_t ib, u
     __syncwarp();
 }
 
-template <bool RICH, bool GAMMA1>
-__global__ void __launch_bounds__(TS2D_BLOCK, 3)
+template <bool RICH, bool GAMMA1, int CW>
+__global__ void __launch_bounds__(32 * CW, 24 / CW)
 k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world, int n_tiles, float gamma, float tfx, float tfy,
                     const uint2 *__restrict__ ranges, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ list,
                     const float4 *__restrict__ rec0, const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr, const float *__restrict__ background,
@@ -392,17 +395,18 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
     using L = Bwd3Layout;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
-    const int tile = blockIdx.x * shard_world + shard_rank;
+    constexpr int PARTS = 8 / CW;
+    const int tile = (blockIdx.x / PARTS) * shard_world + shard_rank;
     if (tile >= n_tiles) return;
     const int tile_x = tile % gx, tile_y = tile / gx;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lwarp = tid >> 5, warp = (blockIdx.x % PARTS) * CW + lwarp, lane = tid & 31;
     const int px = tile_x * TS2D_TILE + (warp & 1) * 8 + (lane & 7), py = tile_y * TS2D_TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < W_ && py < H;
     const size_t pix = (size_t)W_ * py + px;
     const size_t HW = (size_t)H * W_;
     const f3 ray = pixel_ray(px, py, W_, H, tfx, tfy);
     const Gamma3 gk = make_gamma3(GAMMA1 ? 1.0f : gamma, GAMMA1);
-    const uint32_t sb = smem_base(smem_raw + warp * L::BYTES);
+    const uint32_t sb = smem_base(smem_raw + lwarp * L::BYTES);
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     const uint2 range = ranges[tile];
@@ -544,12 +548,17 @@ int ts2d_launch_render3d_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g
 #define TS2D_F3_ARGS                                                                                                                     \
     W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, cam->tan_fovx, cam->tan_fovy, is.ranges, keys, list, gs.rec0,       \
         gs.rec1, g->background_depth, ts2d_bg_ptr(g, gs), g->background, is.final_T, is.n_contrib, out->out_feature
+#define TS2D_F3_LAUNCH_CW(R, G, CW, ...)                                                                                               \
+    do {                                                                                                                               \
+        const size_t smem = CW * (size_t)Fwd3Layout<R>::BYTES;                                                                         \
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_fwd_fast<R, G, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_fwd_fast<R, G, CW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));       \
+        k_render3d_fwd_fast<R, G, CW><<<owned * (8 / CW), 32 * CW, smem, s>>>(TS2D_F3_ARGS, __VA_ARGS__);                              \
+    } while (0)
 #define TS2D_F3_LAUNCH(R, G, ...)                                                                                                      \
     do {                                                                                                                               \
-        const size_t smem = 8 * (size_t)Fwd3Layout<R>::BYTES;                                                                          \
-        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_fwd_fast<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_fwd_fast<R, G>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));           \
-        k_render3d_fwd_fast<R, G><<<owned, TS2D_BLOCK, smem, s>>>(TS2D_F3_ARGS, __VA_ARGS__);                                          \
+        if (ts2d_cta_warps() == 8) TS2D_F3_LAUNCH_CW(R, G, 8, __VA_ARGS__);                                                            \
+        else TS2D_F3_LAUNCH_CW(R, G, 1, __VA_ARGS__);                                                                                  \
     } while (0)
     if (f->rich_info) {
         TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_sum, 0, sizeof(float) * (size_t)g->P, s));
@@ -561,6 +570,7 @@ int ts2d_launch_render3d_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g
         else TS2D_F3_LAUNCH(false, false, nullptr, nullptr, nullptr, nullptr);
     }
 #undef TS2D_F3_LAUNCH
+#undef TS2D_F3_LAUNCH_CW
 #undef TS2D_F3_ARGS
     return (int)cudaGetLastError();
 }
@@ -578,12 +588,17 @@ int ts2d_launch_render3d_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g
 #define TS2D_B3_ARGS                                                                                                                     \
     W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, cam->tan_fovx, cam->tan_fovy, is.ranges, keys, list, gs.rec0,       \
         gs.rec1, g->background_depth, ts2d_bg_ptr(g, gs), g->background, is.final_T, is.n_contrib, loss->dL_dout_feature
+#define TS2D_B3_LAUNCH_CW(R, G, CW, ...)                                                                                               \
+    do {                                                                                                                               \
+        const size_t smem = CW * (size_t)Bwd3Layout::BYTES;                                                                            \
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_bwd_fast<R, G, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_bwd_fast<R, G, CW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));       \
+        k_render3d_bwd_fast<R, G, CW><<<owned * (8 / CW), 32 * CW, smem, s>>>(TS2D_B3_ARGS, __VA_ARGS__, gacc);                        \
+    } while (0)
 #define TS2D_B3_LAUNCH(R, G, ...)                                                                                                      \
     do {                                                                                                                               \
-        const size_t smem = 8 * (size_t)Bwd3Layout::BYTES;                                                                             \
-        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_bwd_fast<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-        TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_bwd_fast<R, G>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));           \
-        k_render3d_bwd_fast<R, G><<<owned, TS2D_BLOCK, smem, s>>>(TS2D_B3_ARGS, __VA_ARGS__, gacc);                                    \
+        if (ts2d_cta_warps() == 8) TS2D_B3_LAUNCH_CW(R, G, 8, __VA_ARGS__);                                                            \
+        else TS2D_B3_LAUNCH_CW(R, G, 1, __VA_ARGS__);                                                                                  \
     } while (0)
     if (f->rich_info) {
         if (g1) TS2D_B3_LAUNCH(true, true, loss->dL_dout_depth, loss->dL_dout_normal);
@@ -593,6 +608,7 @@ int ts2d_launch_render3d_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g
         else TS2D_B3_LAUNCH(false, false, nullptr, nullptr);
     }
 #undef TS2D_B3_LAUNCH
+#undef TS2D_B3_LAUNCH_CW
 #undef TS2D_B3_ARGS
     return (int)cudaGetLastError();
 }
