@@ -197,6 +197,9 @@ int ts2d_launch_preprocess(const ts2d_camera *cam, const ts2d_geometry *g, const
 // K9: per-triangle backward.  gacc holds, per triangle, the 16 screen-space sums produced by the
 // composite backward: [0..5] dL/d(v1,v2,v3)_2D, [6] dL/d opacity, [7] pad, [8..10] dL/d rgb, [11] pad... see GACC_* below.
 // ------------------------------------------------------------------------------------------------
+#ifndef TS2D_K9_MINB
+#define TS2D_K9_MINB 3
+#endif
 __device__ __forceinline__ f2 grad_norm2(f2 v, f2 dv)
 {
     const float sum2 = v.x * v.x + v.y * v.y;
@@ -216,7 +219,7 @@ __device__ __forceinline__ void project_offset_bwd(f3 p, f3 d, float tfx, float 
 
 
 template <bool TILED, bool MODEL>
-__global__ void __launch_bounds__(TS2D_BLOCK)
+__global__ void __launch_bounds__(TS2D_BLOCK, TS2D_K9_MINB)
 k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool rich, float tfx, float tfy, const float *__restrict__ view,
                  const float *__restrict__ proj, const float *__restrict__ campos, const float *__restrict__ vertex,
                  const float *__restrict__ shs, const int32_t *__restrict__ radii, const uint8_t *__restrict__ clamp,

@@ -103,7 +103,8 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
     const int px = tile_x * TS2D_TILE + (warp & 1) * 8 + (lane & 7);
     const int py = tile_y * TS2D_TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
+    float pxf = (float)px, pyf = (float)py;
+    asm volatile("" : "+f"(pxf), "+f"(pyf));  // opaque: keep them in registers (ptxas re-materialised two I2FP per walk iteration)
     GammaK gk = make_gamma(GAMMA1 ? 1.0f : gamma);  // gamma == 1: every constant of the error model folds to an immediate
     gk.is_one = GAMMA1;
     const uint32_t sb = smem_base(s_raw + lwarp * L::BYTES);  // this warp's block
@@ -186,7 +187,7 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
         for (int j = 0; j < count; j++, ea += L::EB, prow += FW_PROW * 4) {
             const float4 e1 = lds128(ea), e2 = lds128(ea + 16);
             float contrib = 0.0f;  // > 0 <=> this lane blended the triangle
-            bool tband = false;
+            bool evt = false;      // this lane's transmittance reached the 1e-4 cut or its error band: handled out of line below
             if (!done) {
                 FastPair f;
                 bool unc;
@@ -209,19 +210,19 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                     Terr = fmaf(Terr, om, contrib * (unc ? 0.0f : fmaf(gk.terr_c1, fabsf(f.power), gk.terr_c0)));
                     T *= om;
                     Terr = fmaf(T, 1.3e-7f, Terr);
-                    const float dT = T - 0.0001f;
-                    tband = fabsf(dT) <= Terr;
-                    if (dT <= 0.0f) {  // provisional when tband: re-decided below on the exact transmittance
-                        done = true;
-                        last = lds32(sb + L::POS + j * L::POS_STRIDE) - range.x + 1;
-                    }
+                    evt = (T - 0.0001f) <= Terr;  // saturated (T <= 1e-4) or within the error band of the cut
                 }
             }
             if constexpr (RICH) sts32f(prow + lane * 4, contrib);
-            uint32_t need = __ballot_sync(0xffffffffu, tband);
-            if (need) {  // rare: exact transmittance re-walk for one pixel at a time, whole warp cooperating
+            if (__any_sync(0xffffffffu, evt)) {  // at most a few times per pixel: everything about saturation lives here
                 const uint32_t pos = lds32(sb + L::POS + j * L::POS_STRIDE);
-                while (need) {
+                const float dT = T - 0.0001f;
+                if (evt && dT <= 0.0f) {  // provisional when inside the band: re-decided below on the exact transmittance
+                    done = true;
+                    last = pos - range.x + 1;
+                }
+                uint32_t need = __ballot_sync(0xffffffffu, evt && fabsf(dT) <= Terr);
+                while (need) {  // rare: exact transmittance re-walk for one pixel at a time, whole warp cooperating
                     const int src = __ffs(need) - 1;
                     need &= need - 1;
                     const float spx = __shfl_sync(0xffffffffu, pxf, src), spy = __shfl_sync(0xffffffffu, pyf, src);
@@ -233,10 +234,10 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                         Terr = 0.0f;
                     }
                 }
-            }
-            if (__all_sync(0xffffffffu, done)) {  // every pixel of the sub-tile has saturated
-                visited = j + 1;
-                break;
+                if (__all_sync(0xffffffffu, done)) {  // every pixel of the sub-tile has saturated
+                    visited = j + 1;
+                    break;
+                }
             }
         }
         if constexpr (RICH) flush_panel(visited);
