@@ -187,7 +187,7 @@ k_render3d_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world
         int visited = count;
         for (int j = 0; j < count; j++, ea += F3_EB, prow += FW3_PROW * 4) {
             float contrib = 0.0f;  // > 0 <=> this lane blended the triangle
-            bool tband = false;
+            bool evt = false;      // this lane's transmittance reached the 1e-4 cut or its error band: handled out of line below
             if (!done) {
                 const Tri3 t = unpack3(lds128(ea), lds128(ea + 16), lds128(ea + 32));
                 const float2 kq = lds64(ea + 64);
@@ -214,20 +214,20 @@ k_render3d_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world
                         Terr = fmaf(Terr, om, contrib * (unc ? 0.0f : fmaf(gk.c1, fabsf(e.power), gk.c0)));
                         T *= om;
                         Terr = fmaf(T, 1.3e-7f, Terr);
-                        const float dT = T - 0.0001f;
-                        tband = fabsf(dT) <= Terr;
-                        if (dT <= 0.0f) {  // provisional when tband: re-decided below on the exact transmittance
-                            done = true;
-                            last = lds32(ea + 76) + 1;
-                        }
+                        evt = (T - 0.0001f) <= Terr;  // saturated (T <= 1e-4) or within the error band of the cut
                     }
                 }
             }
             if constexpr (RICH) sts32f(prow + lane * 4, contrib);
-            uint32_t need = __ballot_sync(0xffffffffu, tband);
-            if (need) {  // rare: exact transmittance re-walk for one pixel at a time, whole warp cooperating
+            if (__any_sync(0xffffffffu, evt)) {  // at most a few times per pixel: everything about saturation lives here
                 const uint32_t pos = lds32(ea + 76);
-                while (need) {
+                const float dT = T - 0.0001f;
+                if (evt && dT <= 0.0f) {  // provisional when inside the band: re-decided below on the exact transmittance
+                    done = true;
+                    last = pos + 1;
+                }
+                uint32_t need = __ballot_sync(0xffffffffu, evt && fabsf(dT) <= Terr);
+                while (need) {  // rare: exact transmittance re-walk for one pixel at a time, whole warp cooperating
                     const int src = __ffs(need) - 1;
                     need &= need - 1;
                     const float srx = __shfl_sync(0xffffffffu, ray.x, src), sry = __shfl_sync(0xffffffffu, ray.y, src);
@@ -239,10 +239,10 @@ k_render3d_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world
                         Terr = 0.0f;
                     }
                 }
-            }
-            if (__all_sync(0xffffffffu, done)) {  // every pixel of the sub-tile has saturated
-                visited = j + 1;
-                break;
+                if (__all_sync(0xffffffffu, done)) {  // every pixel of the sub-tile has saturated
+                    visited = j + 1;
+                    break;
+                }
             }
         }
         if constexpr (RICH) flush_panel(visited);
