@@ -64,6 +64,17 @@ def _worker(rank, port, ret):
         img, dep, nrm = (torch.from_numpy(st[k].copy()) for k in ("out_feature", "out_depth", "out_normal"))
         cs, cm = torch.from_numpy(st["contrib_sum"].copy()), torch.from_numpy(st["contrib_max"].copy())
         tsd.assemble_forward(img, dep, nrm, cs, cm)
+        # the sharded CUDA forward carves image | depth | normal | contrib_sum back to back out of one buffer so that the frame
+        # is assembled by ONE in-place all-reduce: same answer as the packed path above
+        parts = [torch.from_numpy(st[k].copy()) for k in ("out_feature", "out_depth", "out_normal", "contrib_sum")]
+        flat = torch.cat([t.reshape(-1) for t in parts])
+        views, off = [], 0
+        for t in parts:
+            views.append(flat[off:off + t.numel()].view(t.shape))
+            off += t.numel()
+        tsd.assemble_forward(*views, torch.from_numpy(st["contrib_max"].copy()))
+        for v, full in zip(views, (img, dep, nrm, cs)):
+            assert torch.equal(v, full)
         grads = [torch.from_numpy(g[k].copy()) for k in ("dL_dvertex", "dL_dcenter2D", "dL_dshs", "dL_dfeature", "dL_dopacity")]
         tsd.reduce_gradients(*grads)
         if rank == 0:

@@ -175,14 +175,24 @@ def rasterize_triangles(image_width: int, image_height: int, tan_fovx: float, ta
     u8 = dict(device=dev, dtype=torch.uint8)
     sharded = shard[1] > 1
     alloc = torch.zeros if (P == 0 or sharded) else torch.empty  # every owned pixel is written by the composite kernel
-    out_feature = alloc((Cn, H, W), **f32)
     radii = torch.zeros((P,), device=dev, dtype=torch.int32) if P == 0 else torch.empty((P,), device=dev, dtype=torch.int32)
-    if rich_info:
+    if sharded and rich_info and P > 0:
+        # one buffer [image | depth | normal | contrib_sum]: the ranks' partial frames are summed with ONE in-place all-reduce
+        n_img, n_pix = Cn * H * W, H * W
+        flat = torch.zeros((n_img + n_pix + 3 * n_pix + P,), **f32)
+        out_feature = flat[:n_img].view(Cn, H, W)
+        depth = flat[n_img:n_img + n_pix].view(H, W)
+        normal = flat[n_img + n_pix:n_img + 4 * n_pix].view(3, H, W)
+        contrib_sum = flat[n_img + 4 * n_pix:]
+        contrib_max = torch.empty((P,), **f32)
+    elif rich_info:
+        out_feature = alloc((Cn, H, W), **f32)
         depth = alloc((H, W), **f32)
         normal = alloc((3, H, W), **f32)
         contrib_sum = torch.empty((P,), **f32) if P else torch.zeros((0,), **f32)
         contrib_max = torch.empty((P,), **f32) if P else torch.zeros((0,), **f32)
     else:
+        out_feature = alloc((Cn, H, W), **f32)
         depth = torch.empty((0,), **f32)
         normal = torch.empty((0,), **f32)
         contrib_sum = torch.empty((0,), **f32)

@@ -55,6 +55,14 @@ def _bucket_all_reduce(tensors, op) -> None:
     if len(tensors) == 1:
         dist.all_reduce(tensors[0], op=op, group=_STATE["group"])
         return
+    # tensors carved back to back out of one buffer (the sharded forward allocates its image planes that way): reduce in place
+    adjacent = all(t.is_contiguous() and t.dtype == tensors[0].dtype for t in tensors) and all(
+        b.untyped_storage().data_ptr() == a.untyped_storage().data_ptr() and b.data_ptr() == a.data_ptr() + a.numel() * a.element_size()
+        for a, b in zip(tensors, tensors[1:]))
+    if adjacent:
+        total = sum(t.numel() for t in tensors)
+        dist.all_reduce(torch.as_strided(tensors[0], (total,), (1,)), op=op, group=_STATE["group"])
+        return
     flat = torch.cat([t.reshape(-1) for t in tensors])
     dist.all_reduce(flat, op=op, group=_STATE["group"])
     off = 0
