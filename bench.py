@@ -570,8 +570,9 @@ def main():
     stage_ms = {s: st_ms[i] / max(1, st_n[i]) for i, s in enumerate(_lib.STAGES)}
     fps = a.steps / (ms / 1e3)
 
-    if rank == 0:
-        # R (num_rendered) of this rank's shard: one forward through the raw _C API
+    if True:
+        # R (num_rendered) of this rank's shard: one forward through the raw _C API.  Every rank makes the call: a tile-sharded
+        # forward is collective (barriers of the peer-memory fabric, or the NCCL assembly in the autograd wrapper)
         s, c = step.sc, step.sc.cam
         fa = (c["image_width"], c["image_height"], c["tanfovx"], c["tanfovy"], c["viewmatrix"], c["projmatrix"], c["campos"], s.sh_degree,
               s.gamma, 1.0, s.background_depth, s.background, s.vertex, s.shs, torch.Tensor([]), s.opacity, s.back_culling, s.rich_info, False)
@@ -644,10 +645,23 @@ def main():
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # release the symmetric (peer-memory) buffers while the process group is still alive, then leave without running
+        # interpreter-exit destructors: a rank that tears its CUDA context down early must not stall the others
+        import gc
+
+        from triangle_splatting_b200 import distributed as tsd
+
+        del step
+        tsd.disable_tile_sharding()
+        gc.collect()
+        torch.cuda.synchronize(dev)
         dist.barrier()
         dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define TS2D_ABI_VERSION 3
+#define TS2D_ABI_VERSION 4
 #define TS2D_TILE 16          /* R2D/src/config.h:4-5  BLOCK_X = BLOCK_Y = 16 */
 #define TS2D_MAX_CHANNELS 3   /* R2D/src/config.h:3 */
 
@@ -66,7 +66,8 @@ enum {
     TS2D_E_SHARD = -10,        /* shard_rank/shard_world invalid */
     TS2D_E_SIZE = -11,         /* image or primitive count out of range */
     TS2D_E_PRIMITIVE = -12,    /* flags.primitive is neither TS2D_PRIMITIVE_2D nor TS2D_PRIMITIVE_3D */
-    TS2D_E_MODEL = -13         /* geometry.model / backward_out.model inconsistent (missing pointer, use_shs == 0, M == 0) */
+    TS2D_E_MODEL = -13,        /* geometry.model / backward_out.model inconsistent (missing pointer, use_shs == 0, M == 0) */
+    TS2D_E_FABRIC = -14        /* flags.fabric with the mirror kernels / ts2d_backward(), bad world / home_chunk, or a required address missing */
 };
 
 /* R2D/src/param_struct.h:127-137 (CameraInfo).  Matrices are the 16 floats of the (contiguous)
@@ -149,7 +150,30 @@ typedef struct ts2d_flags {
                                   R3D/src/forward.cu:61-306, R3D/src/backward.cu:144-454).  Same entry points, same
                                   state blobs, same outputs; dL_dcenter2D is then the view-space xy of the summed
                                   vertex gradients (R3D/src/backward.cu:211-213). */
+    const struct ts2d_fabric *fabric;  /* NULL unless the ranks exchange through NVLink peer memory, see below */
 } ts2d_flags;
+
+/* Multi-GPU over NVLink peer memory (no counterpart in the reference).  The ranks of a tile-sharded render hold SYMMETRIC buffers
+ * (same layout on every rank; cuMem + cuMulticast, e.g. torch symmetric memory) and the fast composite kernels exchange through them
+ * while they run, instead of a collective afterwards:
+ *   pixels        every rank stores the pixels of its own tiles into ALL replicas with multimem.st on the NVSwitch multicast alias
+ *                 (*_mc) -- disjoint tiles, plain stores, bit-identical frames everywhere;
+ *   reductions    contrib_sum / contrib_max (forward) and the 16-float gradient accumulators (backward) of triangle i are reduced
+ *                 on ONE rank, its home  min(i / home_chunk, world - 1),  with red.global over that rank's peer mapping (peer
+ *                 tables below, index = rank): a single copy receives every rank's partial sums, so all ranks later read the same
+ *                 bits (a multicast RED would round differently on every replica and let replicated optimizers drift apart);
+ *   publish       ts2d_fabric_publish(): the home rank copies its finished slice to every replica (multimem.st).
+ * The caller owns the protocol: zero the reduced arrays on every replica, rendezvous, run the kernel, rendezvous, publish, rendezvous.
+ * ts2d_forward_out then only carries `radii`; ts2d_backward_composite()'s `scratch` is the local replica.  Only the fast kernels
+ * (flags.exact == 0, gamma in their range) take this path; ts2d_backward() (no place for the rendezvous) refuses it. */
+#define TS2D_MAX_RANKS 8
+typedef struct ts2d_fabric {
+    int32_t world;                 /* ranks sharing the render, <= TS2D_MAX_RANKS */
+    int32_t home_chunk;            /* triangles per home slice (a multiple of 32) */
+    float *out_feature_mc, *depth_mc, *normal_mc;              /* multicast aliases of the image planes */
+    float *contrib_sum[TS2D_MAX_RANKS], *contrib_max[TS2D_MAX_RANKS];  /* peer addresses of every rank's replica */
+    float *scratch[TS2D_MAX_RANKS];                            /* peer addresses of every rank's backward scratch */
+} ts2d_fabric;
 
 #define TS2D_PRIMITIVE_2D 0
 #define TS2D_PRIMITIVE_3D 1
@@ -228,6 +252,10 @@ int ts2d_backward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, co
  * [planes][H][W].  ts2d_downsample_bwd is its adjoint (writes every element of dL_din). */
 int ts2d_downsample(const float *in, float *out, int32_t planes, int32_t out_width, int32_t out_height, int32_t s, void *stream);
 int ts2d_downsample_bwd(const float *dL_dout, float *dL_din, int32_t planes, int32_t out_width, int32_t out_height, int32_t s, void *stream);
+
+/* Copy local[first .. first + count) to the same range of every replica through the multicast alias (multimem.st); `first` and
+ * `count` in floats, both multiples of 4, both pointers 16-byte aligned.  See ts2d_fabric. */
+int ts2d_fabric_publish(const float *local, float *multicast, int64_t first, int64_t count, void *stream);
 
 /* ---- state decoding, for parity tests against the reference's buffers ----
  * Each writes arrays in the reference's own element types/order.  Any output pointer may be NULL. */

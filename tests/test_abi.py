@@ -25,7 +25,7 @@ def test_library_loads_and_exports_everything():
     lib = _lib.load()
     for name in _declared():
         assert hasattr(lib, name), name
-    assert lib.ts2d_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.ts2d_abi_version() == _lib.ABI_VERSION == 4
     assert b"vertex must have dimensions" in lib.ts2d_error_string(-1)
     assert lib.ts2d_error_string(0) == b"ok"
 
@@ -38,7 +38,7 @@ def test_ctypes_structs_match_the_header_layout():
 
     names = {"ts2d_camera": _lib.Camera, "ts2d_geometry": _lib.Geometry, "ts2d_flags": _lib.Flags, "ts2d_forward_out": _lib.ForwardOut,
              "ts2d_loss_in": _lib.LossIn, "ts2d_backward_out": _lib.BackwardOut, "ts2d_model_inputs": _lib.ModelInputs,
-             "ts2d_model_grads": _lib.ModelGrads}
+             "ts2d_model_grads": _lib.ModelGrads, "ts2d_fabric": _lib.FabricC}
     body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in names)
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "t.c")

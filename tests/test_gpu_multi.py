@@ -53,10 +53,16 @@ def _worker(rank, world, port, ret):
     try:
         sc = harness.golden_scene("sh3_rich")
         single = _run(sc, dev)  # sharding off: the single-GPU answer, computed on this very GPU
-        tsd.enable_tile_sharding()
-        sharded = _run(sc, dev)
-        tsd.disable_tile_sharding()
-        ret[rank] = (single, sharded)
+        res = {}
+        for mode in ("0", "auto"):  # NCCL collectives / NVLink peer memory (multicast pixel stores + home-rank reductions)
+            os.environ["TS2D_FABRIC"] = mode
+            tsd.enable_tile_sharding()
+            sharded = _run(sc, dev)
+            sharded2 = _run(sc, dev)  # a second frame through the same persistent buffers
+            used = tsd.fabric(dev) is not None
+            tsd.disable_tile_sharding()
+            res[mode] = (sharded, sharded2, used)
+        ret[rank] = (single, res)
     finally:
         dist.destroy_process_group()
 
@@ -70,14 +76,20 @@ def test_tile_sharded_render_matches_single_gpu(world):
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
-    for rank in range(world):
-        single, sharded = ret[rank]
-        assert mismatch_count(single["radii"], sharded["radii"]) == 0
-        for k in ("out_feature", "depth", "normal", "contrib_max"):
-            assert np.array_equal(single[k], sharded[k]), f"rank {rank}: {k} (disjoint tiles: the all-reduce adds zeros)"
-        assert rel_err(sharded["contrib_sum"], single["contrib_sum"]) <= 1e-5
-        for k in ("dL_dvertex", "dL_dshs", "dL_dopacity", "dL_dcenter2D"):
-            assert rel_err(sharded[k], single[k]) <= 1e-1 and harness.frac_above(sharded[k], single[k], 1e-4, 1e-3) <= 0.03, f"rank {rank}: {k}"
-    # all ranks hold the same frame and the same gradients
-    for k in ret[0][1]:
-        assert np.array_equal(ret[0][1][k], ret[1][1][k]), f"ranks disagree on {k}"
+    assert not ret[0][1]["0"][2], "TS2D_FABRIC=0 must use the NCCL path"
+    print("peer-memory fabric used:", ret[0][1]["auto"][2])
+    for mode in ("0", "auto"):
+        for frame in (0, 1):
+            for rank in range(world):
+                single, sharded = ret[rank][0], ret[rank][1][mode][frame]
+                what = f"mode {mode} frame {frame} rank {rank}"
+                assert mismatch_count(single["radii"], sharded["radii"]) == 0, what
+                for k in ("out_feature", "depth", "normal", "contrib_max"):
+                    assert np.array_equal(single[k], sharded[k]), f"{what}: {k} (disjoint tiles: stores / sums with zeros)"
+                assert rel_err(sharded["contrib_sum"], single["contrib_sum"]) <= 1e-5, what
+                for k in ("dL_dvertex", "dL_dshs", "dL_dopacity", "dL_dcenter2D"):
+                    assert rel_err(sharded[k], single[k]) <= 1e-1 and harness.frac_above(sharded[k], single[k], 1e-4, 1e-3) <= 0.03, f"{what}: {k}"
+            # all ranks hold the same frame and the same gradients, bit for bit (replicated optimizers must not drift apart)
+            a, b = ret[0][1][mode][frame], ret[1][1][mode][frame]
+            for k in a:
+                assert np.array_equal(a[k], b[k]), f"mode {mode} frame {frame}: ranks disagree on {k}"

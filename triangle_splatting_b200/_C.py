@@ -78,6 +78,16 @@ class ModelInputs:
 STAT_FIELDS = ("gradient_accum", "gradient_denom", "contrib_sum", "contrib_max", "contrib_denom", "max_radii2D")
 
 
+def _fabric_for(shard, gamma, dev):
+    """NVLink peer-memory fabric for a tile-sharded call, or None (then NCCL collectives above this module do the exchange).
+    Only the fast kernels write through multicast addresses (same condition as ts2d_use_fast in ts2d_common.cuh)."""
+    if shard[1] <= 1 or EXACT or not (0.6 <= float(gamma) <= 64.0):
+        return None
+    from . import distributed
+
+    return distributed.fabric(dev)
+
+
 def _ptr(t: torch.Tensor | None):
     if t is None or t.numel() == 0:
         return None
@@ -176,7 +186,19 @@ def rasterize_triangles(image_width: int, image_height: int, tan_fovx: float, ta
     sharded = shard[1] > 1
     alloc = torch.zeros if (P == 0 or sharded) else torch.empty  # every owned pixel is written by the composite kernel
     radii = torch.zeros((P,), device=dev, dtype=torch.int32) if P == 0 else torch.empty((P,), device=dev, dtype=torch.int32)
-    if sharded and rich_info and P > 0:
+    fab = _fabric_for(shard, gamma, dev) if (sharded and P > 0) else None
+    if fab is not None:
+        # NVLink peer memory (include/ts2d.h: ts2d_fabric): one symmetric buffer [image | depth | normal | contrib_sum | contrib_max]
+        # per rank.  K7 stores its tiles' pixels into every replica through the multicast alias and REDs contrib_sum / contrib_max
+        # into each triangle's home replica, which is then published to all: the frame is complete without a collective.
+        n_img, n_pix = Cn * H * W, H * W
+        pad4 = lambda n: (n + 3) // 4 * 4
+        sizes = [pad4(n_img), pad4(n_pix), pad4(3 * n_pix), pad4(P), pad4(P)] if rich_info else [pad4(n_img)]
+        offs = [sum(sizes[:i]) for i in range(len(sizes) + 1)]
+        frame, mc_base, fab_h = fab.buffer("frame", offs[-1])
+        home_chunk = ((P + shard[1] - 1) // shard[1] + 31) // 32 * 32
+        out_feature = depth = normal = contrib_sum = contrib_max = None  # carved from a private copy of the replica after the render
+    elif sharded and rich_info and P > 0:
         # one buffer [image | depth | normal | contrib_sum]: the ranks' partial frames are summed with ONE in-place all-reduce
         n_img, n_pix = Cn * H * W, H * W
         flat = torch.zeros((n_img + n_pix + 3 * n_pix + P,), **f32)
@@ -216,9 +238,39 @@ def rasterize_triangles(image_width: int, image_height: int, tan_fovx: float, ta
         ibytes = lib.ts2d_image_state_bytes(W, H)
         binningBuffer = torch.empty((bbytes,), **u8)
         imageBuffer = torch.empty((ibytes,), **u8)
-        out = _lib.ForwardOut(_ptr(out_feature), _ptr(radii), _ptr(depth), _ptr(normal), _ptr(contrib_sum), _ptr(contrib_max))
+        if fab is not None:
+            if rich_info:
+                frame[offs[3]:].zero_()  # contrib_sum / contrib_max: the home slices receive REDs from every rank
+            fab_h.barrier(channel=0)     # every replica zeroed, and nobody still reads the previous frame
+            peers = [int(a) for a in fab_h.buffer_ptrs]
+            fc = _lib.FabricC(world=shard[1], home_chunk=home_chunk, out_feature_mc=mc_base)
+            if rich_info:
+                fc.depth_mc, fc.normal_mc = mc_base + 4 * offs[1], mc_base + 4 * offs[2]
+                for r in range(shard[1]):
+                    fc.contrib_sum[r], fc.contrib_max[r] = peers[r] + 4 * offs[3], peers[r] + 4 * offs[4]
+            flags.fabric = C.cast(C.pointer(fc), C.c_void_p)
+            out = _lib.ForwardOut(None, _ptr(radii), None, None, None, None)
+        else:
+            out = _lib.ForwardOut(_ptr(out_feature), _ptr(radii), _ptr(depth), _ptr(normal), _ptr(contrib_sum), _ptr(contrib_max))
         _lib.check(lib.ts2d_forward_render(C.byref(cam), C.byref(geom), C.byref(flags), R, _ptr(geometryBuffer), _ptr(binningBuffer), bbytes,
                                            _ptr(imageBuffer), ibytes, C.byref(out), stream), "ts2d_forward_render")
+        if fab is not None:
+            fab_h.barrier(channel=0)     # every rank's pixel stores and REDs have landed
+            if rich_info:                # publish this rank's home slice of contrib_sum / contrib_max to every replica
+                first = shard[0] * home_chunk
+                count = pad4(min(home_chunk, P - first)) if first < P else 0
+                for o in (offs[3], offs[4]):
+                    _lib.check(lib.ts2d_fabric_publish(C.c_void_p(frame.data_ptr() + 4 * o), C.c_void_p(mc_base + 4 * o), first, count, stream),
+                               "ts2d_fabric_publish")
+                fab_h.barrier(channel=0)
+            mine = frame.clone()         # the symmetric buffer is reused by the next frame
+            out_feature = mine[:n_img].view(Cn, H, W)
+            if rich_info:
+                depth, normal = mine[offs[1]:offs[1] + n_pix].view(H, W), mine[offs[2]:offs[2] + 3 * n_pix].view(3, H, W)
+                contrib_sum, contrib_max = mine[offs[3]:offs[3] + P], mine[offs[4]:offs[4] + P]
+            else:
+                depth = normal = contrib_sum = contrib_max = torch.empty((0,), **f32)
+            out_feature._ts2d_assembled = True  # tells the autograd wrapper that no collective is needed
     return R, out_feature, radii, depth, normal, contrib_sum, contrib_max, geometryBuffer, binningBuffer, imageBuffer
 
 
@@ -289,7 +341,12 @@ def rasterize_triangles_backward(tan_fovx: float, tan_fovy: float, viewmatrix: t
                                            background_depth, background, vertex, shs, feature, opacity, P, use_shs, Cn, M, False, rich_info,
                                            debug, shard, primitive, model)
         sbytes = lib.ts2d_backward_scratch_bytes(P)
-        scratch = torch.empty((sbytes,), device=dev, dtype=torch.uint8)
+        fab = _fabric_for(shard, gamma, dev)
+        if fab is not None:
+            scratch_f, scratch_mc, fab_h = fab.buffer("scratch", sbytes // 4)
+            scratch = scratch_f.view(torch.uint8)
+        else:
+            scratch = torch.empty((sbytes,), device=dev, dtype=torch.uint8)
         loss = _lib.LossIn(_ptr(dL_dout_feature), _ptr(dL_dout_depth) if rich_info else None, _ptr(dL_dout_normal) if rich_info else None)
         out = _lib.BackwardOut(_ptr(dL_dvertex), _ptr(dL_dcenter2D), _ptr(dL_dshs), _ptr(dL_dfeature), _ptr(dL_dopacity),
                                C.cast(C.pointer(mgrads), C.c_void_p) if mgrads is not None else None)
@@ -298,10 +355,29 @@ def rasterize_triangles_backward(tan_fovx: float, tan_fovy: float, viewmatrix: t
             # current stream), then the per-triangle stage runs replicated on identical data -> identical gradients everywhere
             from . import distributed
 
+            if fab is not None:
+                # NVLink peer memory: K8 REDs each triangle's sums into its home rank's replica of the scratch while it runs; the
+                # homes then publish their slices to every replica -- two small steps instead of a 64 B/triangle all-reduce
+                home_chunk = ((P + shard[1] - 1) // shard[1] + 31) // 32 * 32
+                scratch_f.zero_()
+                fab_h.barrier(channel=0)
+                fc = _lib.FabricC(world=shard[1], home_chunk=home_chunk)
+                for r, a in enumerate(fab_h.buffer_ptrs):
+                    fc.scratch[r] = int(a)
+                flags.fabric = C.cast(C.pointer(fc), C.c_void_p)
             _lib.check(lib.ts2d_backward_composite(C.byref(cam), C.byref(geom), C.byref(flags), int(num_rendered), _ptr(geometryBuffer),
                                                    _ptr(binningBuffer), _ptr(imageBuffer), C.byref(loss), _ptr(scratch), sbytes, stream),
                        "ts2d_backward_composite")
-            distributed.reduce_accumulators(scratch.view(torch.float32))
+            if fab is not None:
+                fab_h.barrier(channel=0)
+                flags.fabric = None
+                first = shard[0] * home_chunk
+                if first < P:
+                    _lib.check(lib.ts2d_fabric_publish(_ptr(scratch_f), C.c_void_p(scratch_mc), 16 * first, 16 * min(home_chunk, P - first), stream),
+                               "ts2d_fabric_publish")
+                fab_h.barrier(channel=0)
+            else:
+                distributed.reduce_accumulators(scratch.view(torch.float32))
             _lib.check(lib.ts2d_backward_geometry(C.byref(cam), C.byref(geom), C.byref(flags), _ptr(radii), _ptr(geometryBuffer),
                                                   C.byref(out), _ptr(scratch), sbytes, stream), "ts2d_backward_geometry")
         else:

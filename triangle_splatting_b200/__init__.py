@@ -96,12 +96,12 @@ class _RasterizeTriangles(torch.autograd.Function):
         ctx.mark_non_differentiable(radii)
         if s.rich_info:
             ctx.mark_non_differentiable(contrib_sum, contrib_max)
-            if shard[1] > 1:
+            if shard[1] > 1 and not getattr(out_feature, "_ts2d_assembled", False):
                 from . import distributed
 
                 distributed.assemble_forward(out_feature, depth, normal, contrib_sum, contrib_max)
             return out_feature, radii, depth, normal, contrib_sum, contrib_max
-        if shard[1] > 1:
+        if shard[1] > 1 and not getattr(out_feature, "_ts2d_assembled", False):
             from . import distributed
 
             distributed.assemble_forward(out_feature)

@@ -132,6 +132,8 @@ int validate(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f
     return 0;
 }
 
+bool fabric_ok(const ts2d_fabric *m) { return m->world >= 2 && m->world <= TS2D_MAX_RANKS && m->home_chunk > 0 && m->home_chunk % 32 == 0; }
+
 int validate_backward_out(const ts2d_geometry *g, const ts2d_backward_out *out)
 {
     if (!out->dL_dvertex || !out->dL_dcenter2D || !out->dL_dfeature || !out->dL_dopacity) return TS2D_E_NULL;
@@ -244,6 +246,15 @@ __global__ void k_downsample_bwd(const float *__restrict__ g_out, float *__restr
     g_in[((size_t)blockIdx.z * Hi + yi) * Wi + xi] = w != 0.0f ? w * g_out[((size_t)blockIdx.z * H + y) * W + x] : 0.0f;
 }
 
+// ts2d_fabric_publish: local slice -> every replica (one multimem.st.v4 per 16 bytes)
+__global__ void k_fabric_publish(const float4 *__restrict__ local, float4 *mc, int64_t n4)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = local[i];
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -266,6 +277,7 @@ const char *ts2d_error_string(int code)
     case TS2D_E_SHARD: return "invalid shard_rank / shard_world";
     case TS2D_E_SIZE: return "image size or primitive count out of range";
     case TS2D_E_PRIMITIVE: return "flags.primitive must be TS2D_PRIMITIVE_2D or TS2D_PRIMITIVE_3D";
+    case TS2D_E_FABRIC: return "flags.fabric needs the fast kernels, the split backward, 2 <= world <= 8, home_chunk % 32 == 0 and every address the call writes";
     case TS2D_E_MODEL: return "model inputs / model gradients inconsistent (need use_shs, f_dc, f_rest for M > 1, opacity_logit, ratio > 0)";
     default: break;
     }
@@ -305,9 +317,20 @@ int ts2d_forward_render(const ts2d_camera *cam, const ts2d_geometry *geom, const
     int rc = validate(cam, geom, flags);
     if (rc) return rc;
     if (geom->P == 0) return 0;
-    if (!geometry_state || !binning_state || !image_state || !out || !out->out_feature) return TS2D_E_NULL;
-    if (flags->rich_info && (!out->depth || !out->normal || !out->contrib_sum || !out->contrib_max)) return TS2D_E_NULL;
+    if (!geometry_state || !binning_state || !image_state || !out) return TS2D_E_NULL;
+    if (!flags->fabric) {
+        if (!out->out_feature) return TS2D_E_NULL;
+        if (flags->rich_info && (!out->depth || !out->normal || !out->contrib_sum || !out->contrib_max)) return TS2D_E_NULL;
+    }
     if (num_rendered < 0 || num_rendered >= ((int64_t)1 << 31)) return TS2D_E_SIZE;
+    if (const ts2d_fabric *m = flags->fabric) {
+        if (!ts2d_use_fast(geom, flags) || !fabric_ok(m) || !m->out_feature_mc) return TS2D_E_FABRIC;
+        if (flags->rich_info) {
+            if (!m->depth_mc || !m->normal_mc) return TS2D_E_FABRIC;
+            for (int r = 0; r < m->world; r++)
+                if (!m->contrib_sum[r] || !m->contrib_max[r]) return TS2D_E_FABRIC;
+        }
+    }
     GeomState gs;
     BinState bs;
     ImageState is;
@@ -336,6 +359,7 @@ int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_
     if (geom->P == 0) return 0;
     if (!radii || !geometry_state || !binning_state || !image_state || !loss || !out || !scratch) return TS2D_E_NULL;
     if (!loss->dL_dout_feature) return TS2D_E_NULL;
+    if (flags->fabric && flags->fabric->scratch[0]) return TS2D_E_FABRIC;  // no place for the rendezvous between K8 and K9
     if ((rc = validate_backward_out(geom, out)) != 0) return rc;
     if (flags->rich_info && (!loss->dL_dout_depth || !loss->dL_dout_normal)) return TS2D_E_NULL;
     if (scratch_bytes < ts2d_backward_scratch_bytes(geom->P)) return TS2D_E_STATE_SIZE;
@@ -374,6 +398,11 @@ int ts2d_backward_composite(const ts2d_camera *cam, const ts2d_geometry *geom, c
     if (!geometry_state || !binning_state || !image_state || !loss || !scratch || !loss->dL_dout_feature) return TS2D_E_NULL;
     if (flags->rich_info && (!loss->dL_dout_depth || !loss->dL_dout_normal)) return TS2D_E_NULL;
     if (scratch_bytes < ts2d_backward_scratch_bytes(geom->P)) return TS2D_E_STATE_SIZE;
+    if (flags->fabric && flags->fabric->scratch[0]) {
+        if (!ts2d_use_fast(geom, flags) || !fabric_ok(flags->fabric)) return TS2D_E_FABRIC;
+        for (int r = 0; r < flags->fabric->world; r++)
+            if (!flags->fabric->scratch[r]) return TS2D_E_FABRIC;
+    }
     GeomState gs;
     BinState bs;
     ImageState is;
@@ -449,6 +478,17 @@ int ts2d_export_model(const void *geometry_state, int32_t P, int32_t primitive, 
     }
     if (background_depth) TS2D_CUDA_TRY(cudaMemcpyAsync(background_depth, &gs.hdr->bg_bits, sizeof(float), cudaMemcpyDeviceToDevice, s));
     return 0;
+}
+
+int ts2d_fabric_publish(const float *local, float *multicast, int64_t first, int64_t count, void *stream)
+{
+    if (count <= 0) return 0;
+    if (!local || !multicast) return TS2D_E_NULL;
+    if (first < 0 || (first & 3) || (count & 3) || ((uintptr_t)local & 15) || ((uintptr_t)multicast & 15)) return TS2D_E_FABRIC;
+    const int64_t n4 = count / 4;
+    const int blocks = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+    k_fabric_publish<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(local + first), reinterpret_cast<float4 *>(multicast + first), n4);
+    return (int)cudaGetLastError();
 }
 
 int ts2d_downsample(const float *in, float *out, int32_t planes, int32_t out_width, int32_t out_height, int32_t sc, void *stream)

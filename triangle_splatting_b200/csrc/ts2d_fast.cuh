@@ -83,6 +83,67 @@ __device__ __forceinline__ void sts128(uint32_t a, float4 v)
 __device__ __forceinline__ void sts32f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
+// Multi-GPU over NVLink peer memory (include/ts2d.h: ts2d_fabric).  Pixels: `mc` != 0 means the output plane pointers are NVSwitch
+// multicast aliases and one multimem.st lands in every rank's replica.  Reductions: PeerSet holds every rank's mapping of a
+// symmetric array; triangle id is reduced on its home rank only (one copy => the same bits for every reader).
+struct PeerTab {
+    float *a[TS2D_MAX_RANKS];  // contrib_sum replicas (forward) / scratch replicas (backward), index = rank
+    float *b[TS2D_MAX_RANKS];  // contrib_max replicas (forward)
+    int world;                 // <= 1: single copy, the kernels' plain pointer parameters are the arrays
+    uint32_t chunk;            // triangles per home slice
+};
+// One table per translation unit, written stream-ordered in front of a fabric launch and cleared in front of the next plain launch.
+// (A kernel-parameter table would be copied to local memory by every thread for the dynamic index, and anything handed to the
+// out-of-line flush functions costs registers across the walk loop: the constant bank costs neither.)  The host side of a
+// translation unit is single-stream as far as fabric launches are concerned (the protocol around them is stream-ordered anyway).
+static __constant__ PeerTab c_peers;
+static bool g_peers_set = false;
+__device__ __forceinline__ float *home_select(float *const (&tab)[TS2D_MAX_RANKS], uint32_t id, float *local)
+{
+    if (c_peers.world <= 1) return local;
+    const uint32_t r = min(id / c_peers.chunk, (uint32_t)c_peers.world - 1u);
+    float *p = tab[0];
+#pragma unroll
+    for (int k = 1; k < TS2D_MAX_RANKS; k++) p = (r == (uint32_t)k) ? tab[k] : p;
+    return p;
+}
+static inline cudaError_t ts2d_set_peers(const ts2d_fabric *fb, bool forward, cudaStream_t s)
+{
+    if (!fb && !g_peers_set) return cudaSuccess;  // the table is zero-initialised: world == 0
+    PeerTab t = {};
+    if (fb) {
+        for (int r = 0; r < fb->world && r < TS2D_MAX_RANKS; r++) {
+            t.a[r] = forward ? fb->contrib_sum[r] : fb->scratch[r];
+            t.b[r] = forward ? fb->contrib_max[r] : nullptr;
+        }
+        t.world = fb->world;
+        t.chunk = (uint32_t)fb->home_chunk;
+    }
+    g_peers_set = fb != nullptr;
+    return cudaMemcpyToSymbolAsync(c_peers, &t, sizeof(t), 0, cudaMemcpyHostToDevice, s);
+}
+__device__ __forceinline__ void st_out(float *p, float v, int mc)
+{
+    if (mc) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+    else *p = v;
+}
+// REDs into a home replica: system scope when the target may be a peer GPU's memory (the operation is performed at the owner's L2)
+__device__ __forceinline__ void red_add4_out(float *addr, float a, float b, float c, float d, bool sys)
+{
+    if (sys) asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+    else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_out(float *p, float v, bool sys)
+{
+    if (sys) asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+    else atomicAdd(p, v);
+}
+__device__ __forceinline__ void red_max_out(unsigned int *p, unsigned int v, bool sys)
+{
+    if (sys) asm volatile("red.relaxed.sys.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else atomicMax(p, v);
+}
+
 // Packed fp32: sm_100 executes add/mul/fma.rn.f32x2 as ONE FADD2 / FMUL2 / FFMA2 issue slot for two independent IEEE fp32
 // operations; an operand may be a register pair, one register broadcast to both halves (bc()), or an immediate -- ptxas folds
 // the pack / broadcast into the operand form, no MOVs.  Used where two sums share their multiplier (the issue-bound kernels).

@@ -118,7 +118,7 @@ k_render3d_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world
                     const uint2 *__restrict__ ranges, const uint32_t *keys, const uint32_t *__restrict__ list,
                     const float4 *__restrict__ rec0, const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr, const float *__restrict__ background,
                     float *__restrict__ final_T, uint32_t *__restrict__ n_contrib, float *__restrict__ out_feature, float *__restrict__ out_depth,
-                    float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max)
+                    float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max, int mc)
 {
     if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     using L = Fwd3Layout<RICH>;
@@ -156,8 +156,8 @@ k_render3d_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world
             }
             if (m > 0.0f) {
                 const uint32_t id = lds32(sb + lane * F3_EB + 72);
-                atomicAdd(contrib_sum + id, s);
-                atomicMax((unsigned int *)contrib_max + id, __float_as_uint(m));  // contrib >= 0: bit order == value order
+                red_add_out(home_select(c_peers.a, id, contrib_sum) + id, s, mc);
+                red_max_out((unsigned int *)home_select(c_peers.b, id, contrib_max) + id, __float_as_uint(m), mc);  // contrib >= 0: bit order == value order
             }
             // (No coverage-bit clearing here, unlike the 2D kernel: the 3D reference's backward takes its skip decision on
             // G < 1/255 instead of alpha < 1/255 (R3D/src/backward.cu:351), so it visits pairs the forward never blended.)
@@ -255,14 +255,14 @@ k_render3d_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world
         const size_t HW = (size_t)H * W;
         final_T[pix] = T;
         n_contrib[pix] = last;
-        out_feature[pix] = fmaf(T, bg0, acc0);
-        if (C > 1) out_feature[HW + pix] = fmaf(T, bg1, acc1);
-        if (C > 2) out_feature[2 * HW + pix] = fmaf(T, bg2, acc2);
+        st_out(out_feature + pix, fmaf(T, bg0, acc0), mc);
+        if (C > 1) st_out(out_feature + HW + pix, fmaf(T, bg1, acc1), mc);
+        if (C > 2) st_out(out_feature + 2 * HW + pix, fmaf(T, bg2, acc2), mc);
         if constexpr (RICH) {
-            out_depth[pix] = fmaf(T, bg_depth, accd);
-            out_normal[pix] = accn0;
-            out_normal[HW + pix] = accn1;
-            out_normal[2 * HW + pix] = accn2;
+            st_out(out_depth + pix, fmaf(T, bg_depth, accd), mc);
+            st_out(out_normal + pix, accn0, mc);
+            st_out(out_normal + HW + pix, accn1, mc);
+            st_out(out_normal + 2 * HW + pix, accn2, mc);
         }
     }
 }
@@ -287,11 +287,6 @@ struct Bwd3Layout {
     static constexpr int BYTES = INFO + B3_ROWS * B3_INFO;
 };
 __device__ __forceinline__ uint32_t f_row(int p) { return (uint32_t)(p * 32 + (p >> 3) * 16); }
-
-__device__ __forceinline__ void red_add4_3d(float *addr, float a, float b, float c, float d)
-{
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 // Phase 2 (out of line).  Lane (k, quarter) sums panel row k over pixels quarter*8 .. quarter*8+7, the four quarters are
 // combined with two xor-shuffles, every lane maps the moments to the 16 accumulator components and issues one 16 B RED.
@@ -363,21 +358,22 @@ static __device__ __noinline__ void bwd3_flush_panel(uint32_t wb, uint32_t ib, u
     if (GEO) { XQ(s_n0); XQ(s_n1); XQ(s_n2); }
 #undef XQ
     if (k < filled) {
-        float *g = gacc + (size_t)id * GACC_STRIDE;
+        float *g = home_select(c_peers.a, id, gacc) + (size_t)id * GACC_STRIDE;  // the triangle's home replica (local when single-GPU)
+        const bool mc = c_peers.world > 1;
         const float cA2 = -U1a2, cB2 = U1a1 + U1a2;                                       // G2 = cA2 f2 + cB2 f3
         const float cA3 = -(U1 - U1a2 + U2a2), cB3 = U1 - U1a1 - U1a2 - U2 + U2a1 + U2a2; // G3
         const float cA1 = U2a2, cB1 = -(U2a1 + U2a2);                                      // G1 (+ E0 n)
         if (quarter == 0) {
             const f3 G1 = cA1 * f2 + cB1 * f3v + E0 * t.n;
-            red_add4_3d(g, G1.x, G1.y, G1.z, fmaf(cA2, f2.x, cB2 * f3v.x));
+            red_add4_out(g, G1.x, G1.y, G1.z, fmaf(cA2, f2.x, cB2 * f3v.x), mc);
         } else if (quarter == 1) {
-            red_add4_3d(g + 4, fmaf(cA2, f2.y, cB2 * f3v.y), fmaf(cA2, f2.z, cB2 * f3v.z), fmaf(cA3, f2.x, cB3 * f3v.x), fmaf(cA3, f2.y, cB3 * f3v.y));
+            red_add4_out(g + 4, fmaf(cA2, f2.y, cB2 * f3v.y), fmaf(cA2, f2.z, cB2 * f3v.z), fmaf(cA3, f2.x, cB3 * f3v.x), fmaf(cA3, f2.y, cB3 * f3v.y), mc);
         } else if (quarter == 2) {
             const float cn = -inv_nn * (U1a1 + U2a2);
             const f3 GN = mk3(s_n0, s_n1, s_n2) + cn * t.n - (Ea2 * e2 + Ea3 * e3);
-            red_add4_3d(g + 8, fmaf(cA3, f2.z, cB3 * f3v.z), GN.x, GN.y, GN.z);
+            red_add4_out(g + 8, fmaf(cA3, f2.z, cB3 * f3v.z), GN.x, GN.y, GN.z, mc);
         } else {
-            red_add4_3d(g + 12, s_c0, s_c1, s_c2, s_op);
+            red_add4_out(g + 12, s_c0, s_c1, s_c2, s_op, mc);
         }
     }
     __syncwarp();
@@ -547,7 +543,12 @@ int ts2d_launch_render3d_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g
     const bool g1 = g->gamma == 1.0f;
 #define TS2D_F3_ARGS                                                                                                                     \
     W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, cam->tan_fovx, cam->tan_fovy, is.ranges, keys, list, gs.rec0,       \
-        gs.rec1, g->background_depth, ts2d_bg_ptr(g, gs), g->background, is.final_T, is.n_contrib, out->out_feature
+        gs.rec1, g->background_depth, ts2d_bg_ptr(g, gs), g->background, is.final_T, is.n_contrib, o_feature
+    const ts2d_fabric *fb = f->fabric;  // multi-GPU over peer memory, see ts2d_launch_render_fwd_fast
+    const int mc = fb != nullptr;
+    float *o_feature = mc ? fb->out_feature_mc : out->out_feature, *o_depth = mc ? fb->depth_mc : out->depth, *o_normal = mc ? fb->normal_mc : out->normal;
+    float *o_csum = mc ? nullptr : out->contrib_sum, *o_cmax = mc ? nullptr : out->contrib_max;
+    TS2D_CUDA_TRY(ts2d_set_peers(fb, true, s));
 #define TS2D_F3_LAUNCH_CW(R, G, CW, ...)                                                                                               \
     do {                                                                                                                               \
         const size_t smem = CW * (size_t)Fwd3Layout<R>::BYTES;                                                                         \
@@ -561,13 +562,15 @@ int ts2d_launch_render3d_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g
         else TS2D_F3_LAUNCH_CW(R, G, 1, __VA_ARGS__);                                                                                  \
     } while (0)
     if (f->rich_info) {
-        TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_sum, 0, sizeof(float) * (size_t)g->P, s));
-        TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
-        if (g1) TS2D_F3_LAUNCH(true, true, out->depth, out->normal, out->contrib_sum, out->contrib_max);
-        else TS2D_F3_LAUNCH(true, false, out->depth, out->normal, out->contrib_sum, out->contrib_max);
+        if (!mc) {
+            TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_sum, 0, sizeof(float) * (size_t)g->P, s));
+            TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
+        }
+        if (g1) TS2D_F3_LAUNCH(true, true, o_depth, o_normal, o_csum, o_cmax, mc);
+        else TS2D_F3_LAUNCH(true, false, o_depth, o_normal, o_csum, o_cmax, mc);
     } else {
-        if (g1) TS2D_F3_LAUNCH(false, true, nullptr, nullptr, nullptr, nullptr);
-        else TS2D_F3_LAUNCH(false, false, nullptr, nullptr, nullptr, nullptr);
+        if (g1) TS2D_F3_LAUNCH(false, true, nullptr, nullptr, o_csum, o_cmax, mc);
+        else TS2D_F3_LAUNCH(false, false, nullptr, nullptr, o_csum, o_cmax, mc);
     }
 #undef TS2D_F3_LAUNCH
 #undef TS2D_F3_LAUNCH_CW
@@ -582,7 +585,9 @@ int ts2d_launch_render3d_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g
     const int gx = (W + TS2D_TILE - 1) / TS2D_TILE, gy = (H + TS2D_TILE - 1) / TS2D_TILE;
     const int n_tiles = gx * gy;
     const int owned = (n_tiles - f->shard_rank + f->shard_world - 1) / f->shard_world;
-    TS2D_CUDA_TRY(cudaMemsetAsync(gacc, 0, sizeof(float) * GACC_STRIDE * (size_t)g->P, s));
+    const ts2d_fabric *fb = (f->fabric && f->fabric->scratch[0]) ? f->fabric : nullptr;  // see ts2d_launch_render_bwd_fast
+    TS2D_CUDA_TRY(ts2d_set_peers(fb, false, s));
+    if (!fb) TS2D_CUDA_TRY(cudaMemsetAsync(gacc, 0, sizeof(float) * GACC_STRIDE * (size_t)g->P, s));
     if (owned <= 0) return 0;
     const bool g1 = g->gamma == 1.0f;
 #define TS2D_B3_ARGS                                                                                                                     \
@@ -593,7 +598,7 @@ int ts2d_launch_render3d_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g
         const size_t smem = CW * (size_t)Bwd3Layout::BYTES;                                                                            \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_bwd_fast<R, G, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_bwd_fast<R, G, CW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));       \
-        k_render3d_bwd_fast<R, G, CW><<<owned * (8 / CW), 32 * CW, smem, s>>>(TS2D_B3_ARGS, __VA_ARGS__, gacc);                        \
+        k_render3d_bwd_fast<R, G, CW><<<owned * (8 / CW), 32 * CW, smem, s>>>(TS2D_B3_ARGS, __VA_ARGS__, gacc);                     \
     } while (0)
 #define TS2D_B3_LAUNCH(R, G, ...)                                                                                                      \
     do {                                                                                                                               \

@@ -43,11 +43,6 @@ struct BwdLayout {
     static constexpr int BYTES = INFO + BW_ROWS * 48;
 };
 
-__device__ __forceinline__ void red_add4(float *addr, float a, float b, float c, float d)
-{
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 // phase 2 (out of line: one copy keeps the kernel inside the instruction cache and out of the walk loop's register budget).
 // lane (k, quarter) sums panel row k over pixels quarter*8 .. quarter*8+7, then flushes the triangle.
 // wb / ib / fb: shared-space addresses of the warp's W panel, row ids and F table.
@@ -113,7 +108,8 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
 #undef XQ
     if (k < filled) {
         const float4 e1 = lds128(ib + 48 * k), e2 = lds128(ib + 48 * k + 16);
-        float *g = gacc + (size_t)id * GACC_STRIDE;
+        float *g = home_select(c_peers.a, id, gacc) + (size_t)id * GACC_STRIDE;  // the triangle's home replica (local when single-GPU)
+        const bool mc = c_peers.world > 1;
         const float inv = e2.z;
         const float p1x = e1.x - ox, p1y = e1.y - oy, p2x = e1.z - ox, p2y = e1.w - oy, p3x = e2.x - ox, p3y = e2.y - oy;
         float S1 = u10, M1x = u1x, M1y = u1y, S2 = u20, M2x = u2x, M2y = u2y;
@@ -132,10 +128,10 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
         }
         // moments about v1: q = p - v1 = d - (v1 - o)
         const float Q1x = fmaf(-p1x, S1, M1x), Q1y = fmaf(-p1y, S1, M1y), Q2x = fmaf(-p1x, S2, M2x), Q2y = fmaf(-p1y, S2, M2y);
-        if (quarter == 0) red_add4(g, S1, Q1x, Q1y, S2);
-        else if (quarter == 1) red_add4(g + 4, Q2x, Q2y, s_op, s_n0);
-        else if (quarter == 2) red_add4(g + 8, s_c0, s_c1, s_c2, s_n1);
-        else if (geo) red_add4(g + 12, s_n2, gv0, gv1, gv2);
+        if (quarter == 0) red_add4_out(g, S1, Q1x, Q1y, S2, mc);
+        else if (quarter == 1) red_add4_out(g + 4, Q2x, Q2y, s_op, s_n0, mc);
+        else if (quarter == 2) red_add4_out(g + 8, s_c0, s_c1, s_c2, s_n1, mc);
+        else if (geo) red_add4_out(g + 12, s_n2, gv0, gv1, gv2, mc);
     }
     __syncwarp();
 }
@@ -325,7 +321,11 @@ int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
     const int gx = (W + TS2D_TILE - 1) / TS2D_TILE, gy = (H + TS2D_TILE - 1) / TS2D_TILE;
     const int n_tiles = gx * gy;
     const int owned = (n_tiles - f->shard_rank + f->shard_world - 1) / f->shard_world;
-    TS2D_CUDA_TRY(cudaMemsetAsync(gacc, 0, sizeof(float) * GACC_STRIDE * (size_t)g->P, s));
+    // multi-GPU over peer memory (ts2d_fabric): the REDs of triangle i go to its home rank's replica of the scratch;
+    // the caller has zeroed every replica and synchronised the ranks
+    const ts2d_fabric *fb = (f->fabric && f->fabric->scratch[0]) ? f->fabric : nullptr;
+    TS2D_CUDA_TRY(ts2d_set_peers(fb, false, s));
+    if (!fb) TS2D_CUDA_TRY(cudaMemsetAsync(gacc, 0, sizeof(float) * GACC_STRIDE * (size_t)g->P, s));
     if (owned <= 0) return 0;
     const bool g1 = g->gamma == 1.0f;
 #define TS2D_BWD_ARGS                                                                                                                 \
@@ -336,15 +336,13 @@ int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
         const size_t smem = CW * (size_t)BwdLayout<R>::BYTES;                                                                           \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_bwd_fast<R, G, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_bwd_fast<R, G, CW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));          \
-        k_render_bwd_fast<R, G, CW><<<owned * (8 / CW), 32 * CW, smem, s>>>(TS2D_BWD_ARGS, __VA_ARGS__, gacc);                          \
+        k_render_bwd_fast<R, G, CW><<<owned * (8 / CW), 32 * CW, smem, s>>>(TS2D_BWD_ARGS, __VA_ARGS__, gacc);                       \
     } while (0)
 #define TS2D_BWD_LAUNCH(R, G, ...)                                                                                                      \
     do {                                                                                                                                \
         switch (ts2d_cta_warps()) {                                                                                                     \
-        case 1: TS2D_BWD_LAUNCH_CW(R, G, 1, __VA_ARGS__); break;                                                                        \
-        case 2: TS2D_BWD_LAUNCH_CW(R, G, 2, __VA_ARGS__); break;                                                                        \
-        case 4: TS2D_BWD_LAUNCH_CW(R, G, 4, __VA_ARGS__); break;                                                                        \
-        default: TS2D_BWD_LAUNCH_CW(R, G, 8, __VA_ARGS__); break;                                                                       \
+        case 8: TS2D_BWD_LAUNCH_CW(R, G, 8, __VA_ARGS__); break;                                                                        \
+        default: TS2D_BWD_LAUNCH_CW(R, G, 1, __VA_ARGS__); break;                                                                       \
         }                                                                                                                               \
     } while (0)
     if (f->rich_info) {

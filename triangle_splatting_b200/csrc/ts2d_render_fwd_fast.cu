@@ -89,7 +89,7 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                   const uint32_t *keys, const uint32_t *__restrict__ list, const float4 *__restrict__ rec0,
                   const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr, const float *__restrict__ background, float *__restrict__ final_T,
                   uint32_t *__restrict__ n_contrib, float *__restrict__ out_feature, float *__restrict__ out_depth,
-                  float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max)
+                  float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max, int mc)
 {
     if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     using L = FwdLayout<RICH>;
@@ -134,8 +134,8 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
             }
             if (m > 0.0f) {
                 const uint32_t id = lds32(sb + lane * L::EB + 44);
-                atomicAdd(contrib_sum + id, s);
-                atomicMax((unsigned int *)contrib_max + id, __float_as_uint(m));  // contrib >= 0: bit order == value order
+                red_add_out(home_select(c_peers.a, id, contrib_sum) + id, s, mc);
+                red_max_out((unsigned int *)home_select(c_peers.b, id, contrib_max) + id, __float_as_uint(m), mc);  // contrib >= 0: bit order == value order
             } else {
                 // No pixel of this sub-tile blended the entry (footprint between pixel centres, or every pixel under it already
                 // saturated): clear the sub-tile's coverage bit in the instance key, so the backward pass -- whose per-pair decisions
@@ -250,14 +250,14 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
         const size_t HW = (size_t)H * W;
         final_T[pix] = T;
         n_contrib[pix] = last;
-        out_feature[pix] = fmaf(T, bg0, acc01.a);
-        if (C > 1) out_feature[HW + pix] = fmaf(T, bg1, acc01.b);
-        if (C > 2) out_feature[2 * HW + pix] = fmaf(T, bg2, acc2);
+        st_out(out_feature + pix, fmaf(T, bg0, acc01.a), mc);
+        if (C > 1) st_out(out_feature + HW + pix, fmaf(T, bg1, acc01.b), mc);
+        if (C > 2) st_out(out_feature + 2 * HW + pix, fmaf(T, bg2, acc2), mc);
         if constexpr (RICH) {
-            out_depth[pix] = fmaf(T, bg_depth, accd);
-            out_normal[pix] = accn01.a;
-            out_normal[HW + pix] = accn01.b;
-            out_normal[2 * HW + pix] = accn2;
+            st_out(out_depth + pix, fmaf(T, bg_depth, accd), mc);
+            st_out(out_normal + pix, accn01.a, mc);
+            st_out(out_normal + HW + pix, accn01.b, mc);
+            st_out(out_normal + 2 * HW + pix, accn2, mc);
         }
     }
 }
@@ -275,7 +275,14 @@ int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
     const bool g1 = g->gamma == 1.0f;
 #define TS2D_FWD_ARGS                                                                                                                       \
     W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, keys, list, gs.rec0, gs.rec1, g->background_depth, ts2d_bg_ptr(g, gs),         \
-        g->background, is.final_T, is.n_contrib, out->out_feature
+        g->background, is.final_T, is.n_contrib, o_feature
+    // multi-GPU over peer memory (ts2d_fabric): pixels go through the multicast aliases of the image planes (every rank's replica at
+    // once), contrib_sum / contrib_max REDs to the triangle's home replica; the caller zeroed those and synchronised the ranks
+    const ts2d_fabric *fb = f->fabric;
+    const int mc = fb != nullptr;
+    float *o_feature = mc ? fb->out_feature_mc : out->out_feature, *o_depth = mc ? fb->depth_mc : out->depth, *o_normal = mc ? fb->normal_mc : out->normal;
+    float *o_csum = mc ? nullptr : out->contrib_sum, *o_cmax = mc ? nullptr : out->contrib_max;
+    TS2D_CUDA_TRY(ts2d_set_peers(fb, true, s));
 #define TS2D_FWD_LAUNCH_CW(R, G, CW, ...)                                                                                              \
     do {                                                                                                                               \
         const size_t smem = CW * (size_t)FwdLayout<R>::BYTES;                                                                          \
@@ -286,20 +293,20 @@ int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
 #define TS2D_FWD_LAUNCH(R, G, ...)                                                                                                     \
     do {                                                                                                                               \
         switch (ts2d_cta_warps()) {                                                                                                    \
-        case 1: TS2D_FWD_LAUNCH_CW(R, G, 1, __VA_ARGS__); break;                                                                       \
-        case 2: TS2D_FWD_LAUNCH_CW(R, G, 2, __VA_ARGS__); break;                                                                       \
-        case 4: TS2D_FWD_LAUNCH_CW(R, G, 4, __VA_ARGS__); break;                                                                       \
-        default: TS2D_FWD_LAUNCH_CW(R, G, 8, __VA_ARGS__); break;                                                                      \
+        case 8: TS2D_FWD_LAUNCH_CW(R, G, 8, __VA_ARGS__); break;                                                                       \
+        default: TS2D_FWD_LAUNCH_CW(R, G, 1, __VA_ARGS__); break;                                                                      \
         }                                                                                                                              \
     } while (0)
     if (f->rich_info) {
-        TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_sum, 0, sizeof(float) * (size_t)g->P, s));
-        TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
-        if (g1) TS2D_FWD_LAUNCH(true, true, out->depth, out->normal, out->contrib_sum, out->contrib_max);
-        else TS2D_FWD_LAUNCH(true, false, out->depth, out->normal, out->contrib_sum, out->contrib_max);
+        if (!mc) {
+            TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_sum, 0, sizeof(float) * (size_t)g->P, s));
+            TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
+        }
+        if (g1) TS2D_FWD_LAUNCH(true, true, o_depth, o_normal, o_csum, o_cmax, mc);
+        else TS2D_FWD_LAUNCH(true, false, o_depth, o_normal, o_csum, o_cmax, mc);
     } else {
-        if (g1) TS2D_FWD_LAUNCH(false, true, nullptr, nullptr, nullptr, nullptr);
-        else TS2D_FWD_LAUNCH(false, false, nullptr, nullptr, nullptr, nullptr);
+        if (g1) TS2D_FWD_LAUNCH(false, true, nullptr, nullptr, o_csum, o_cmax, mc);
+        else TS2D_FWD_LAUNCH(false, false, nullptr, nullptr, o_csum, o_cmax, mc);
     }
 #undef TS2D_FWD_LAUNCH
 #undef TS2D_FWD_LAUNCH_CW

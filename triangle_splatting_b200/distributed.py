@@ -21,19 +21,73 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
-_STATE = {"enabled": False, "group": None, "rank": 0, "world": 1}
+_STATE = {"enabled": False, "group": None, "rank": 0, "world": 1, "fabric": None, "fabric_mode": "auto"}
+
+
+class Fabric:
+    """Symmetric buffers over NVLink peer memory with NVSwitch multicast aliases (torch symmetric memory: cuMem + cuMulticast).
+
+    The fast composite kernels exchange through them while they run (include/ts2d.h: ts2d_fabric): the pixels of a rank's tiles are
+    stored into every replica with multimem.st, per-triangle sums are reduced on the triangle's home rank over its peer mapping and
+    the home then publishes its slice to every replica -- so a tile-sharded frame is assembled and its gradient sums are completed
+    without a collective, bit-identically on every rank; what is left between ranks are signal-pad barriers.
+    Buffers are persistent (allocation + rendezvous is a collective): one per role, grown on demand."""
+
+    def __init__(self, group, device):
+        import torch.distributed._symmetric_memory as symm
+
+        self.symm, self.group, self.device = symm, (group if group is not None else dist.group.WORLD), device
+        self.buffers = {}
+
+    def buffer(self, role: str, numel: int):
+        """-> (local fp32 tensor of `numel` elements, multicast base address, handle).  Collective when it has to (re)allocate:
+        every rank asks for the same roles and sizes in the same order (parameters are replicated)."""
+        ent = self.buffers.get(role)
+        if ent is None or ent[0].numel() < numel:
+            cap = max(int(numel * 1.25), 1 << 16) if ent is not None else max(int(numel), 1 << 16)
+            t = self.symm.empty(cap, dtype=torch.float32, device=self.device)
+            h = self.symm.rendezvous(t, self.group)
+            if not int(h.multicast_ptr):
+                raise RuntimeError("symmetric memory has no multicast mapping on this system")
+            ent = (t, h)
+            self.buffers[role] = ent
+        t, h = ent
+        return t[:numel], int(h.multicast_ptr), h
+
+
+def fabric(device) -> Optional["Fabric"]:
+    """The peer-memory fabric of the current sharding group, or None (then the NCCL collectives below carry the exchange).
+    TS2D_FABRIC=0 disables it, TS2D_FABRIC=1 makes a failure to set it up an error instead of a silent NCCL path."""
+    import os
+
+    if not _STATE["enabled"] or _STATE["world"] == 1 or device.type != "cuda":
+        return None
+    mode = os.environ.get("TS2D_FABRIC", "auto")
+    if mode == "0":
+        return None
+    f = _STATE["fabric"]
+    if f is None:
+        try:
+            f = Fabric(_STATE["group"], device)
+            f.buffer("probe", 1 << 16)  # allocation + rendezvous + multicast mapping must all work (collective: same on all ranks)
+        except Exception:  # noqa: BLE001
+            if mode == "1":
+                raise
+            f = False
+        _STATE["fabric"] = f
+    return f or None
 
 
 def enable_tile_sharding(group: Optional["dist.ProcessGroup"] = None) -> Tuple[int, int]:
     """Turn on tile sharding over ``group`` (default: the WORLD group). Returns (rank, world)."""
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
-    _STATE.update(enabled=True, group=group, rank=dist.get_rank(group), world=dist.get_world_size(group))
+    _STATE.update(enabled=True, group=group, rank=dist.get_rank(group), world=dist.get_world_size(group), fabric=None)
     return _STATE["rank"], _STATE["world"]
 
 
 def disable_tile_sharding() -> None:
-    _STATE.update(enabled=False, group=None, rank=0, world=1)
+    _STATE.update(enabled=False, group=None, rank=0, world=1, fabric=None)
 
 
 def current_shard() -> Tuple[int, int]:
