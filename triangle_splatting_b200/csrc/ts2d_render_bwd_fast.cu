@@ -38,10 +38,14 @@ struct BwdLayout {
     static constexpr int POS = RICH ? 72 : 32 * 48;
     static constexpr int POS_STRIDE = RICH ? 80 : 4;
     static constexpr int F = RICH ? 32 * 80 : 32 * 48 + 128;
-    static constexpr int W = F + 32 * 32;
+    static constexpr int W = F + 32 * 32 + 64;  // F rows are skewed by 16 B per group of 8 pixels, see f_row()
     static constexpr int INFO = W + ((BW_ROWS * BW_WROW * 4 + 15) / 16) * 16;
     static constexpr int BYTES = INFO + BW_ROWS * 48;
 };
+
+// F table: pixel p at p * 32 + (p >> 3) * 16.  In phase 2 the four pixel-quarters of a warp read four different rows with one
+// LDS.128; rows 8 apart would sit 256 B apart = on the same banks (4-way conflict), the 16 B skew per quarter separates them.
+__device__ __forceinline__ uint32_t f_row(int p) { return (uint32_t)(p * 32 + (p >> 3) * 16); }
 
 // phase 2 (out of line: one copy keeps the kernel inside the instruction cache and out of the walk loop's register budget).
 // lane (k, quarter) sums panel row k over pixels quarter*8 .. quarter*8+7, then flushes the triangle.
@@ -72,7 +76,7 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
             vd3 = q.y;
         }
         const uint32_t row = wb + (k * BW_WROW + quarter * 8) * 4;
-        const uint32_t frow = fb + quarter * 8 * 32;
+        const uint32_t frow = fb + f_row(quarter * 8);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             // pixel p = quarter * 8 + i (lane index of phase 1) inside the sub-tile: x = p & 7 = i, y = p >> 3 = quarter
@@ -187,8 +191,8 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
             gd = dL_dout_depth[pix];
         }
     }
-    sts128(sb + L::F + 32 * lane, make_float4(gp0, gp1, gp2, gd));  // per-pixel table for phase 2
-    sts128(sb + L::F + 32 * lane + 16, make_float4(gn0, gn1, gn2, 0.0f));
+    sts128(sb + L::F + f_row(lane), make_float4(gp0, gp1, gp2, gd));  // per-pixel table for phase 2
+    sts128(sb + L::F + f_row(lane) + 16, make_float4(gn0, gn1, gn2, 0.0f));
     // geometry upstream gradients all zero in this sub-tile (w_geometry = 0 training configs): the normal / depth
     // terms are exactly zero for the reference too, so skipping them changes no bit of the result
     const bool geo = RICH && __any_sync(0xffffffffu, gd != 0.0f || gn0 != 0.0f || gn1 != 0.0f || gn2 != 0.0f);
