@@ -365,13 +365,14 @@ def cpu_oracle_baseline(sc, tile_step=None, budget_s=20.0, primitive="2D"):
     st = o.forward(**kw, **arrs, stages="bin")
     t_geom = time.perf_counter() - t0
     R = st["num_rendered"]
-    if tile_step is None:  # pilot on every 256th tile, then size the sample for ~budget_s of composite work
+    if tile_step is None:  # pilot on every 16th tile, then size the sample for ~budget_s of composite work
+        PILOT = 16
         t0 = time.perf_counter()
-        stp = o.forward(**kw, **arrs, tile_step=256, tile_offset=0)
+        stp = o.forward(**kw, **arrs, tile_step=PILOT, tile_offset=0)
         o.backward(stp, sc.grads["dL_dout_feature"].cpu().numpy(), sc.grads["dL_dout_depth"].cpu().numpy() if sc.rich_info else None,
                    sc.grads["dL_dout_normal"].cpu().numpy() if sc.rich_info else None)
         t_pilot = max(1e-3, time.perf_counter() - t0 - t_geom)
-        tile_step = int(min(256, max(1, round(256.0 * t_pilot / max(1.0, budget_s - 2 * t_geom)))))
+        tile_step = int(min(256, max(1, round(PILOT * t_pilot / max(1.0, budget_s - 2 * t_geom)))))
     t0 = time.perf_counter()
     st = o.forward(**kw, **arrs, tile_step=tile_step, tile_offset=0)
     t_fwd_all = time.perf_counter() - t0  # includes the geometry stages again
@@ -383,7 +384,7 @@ def cpu_oracle_baseline(sc, tile_step=None, budget_s=20.0, primitive="2D"):
     frame_s = t_geom + tile_step * t_comp_f + tile_step * t_bwd
     return {"value": 1.0 / frame_s, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
             "sample": f"CPU oracle port (C, OpenMP): per-triangle stages + binning of the full scene ({t_geom:.1f}s) + composite fwd+bwd on "
-                      f"every {tile_step}-th tile ({t_comp_f:.1f}s + {t_bwd:.1f}s), extrapolated x{tile_step}",
+                      f"every {tile_step}-th tile ({t_comp_f:.1f}s + {t_bwd:.1f}s)" + (f", extrapolated x{tile_step}" if tile_step > 1 else " = the whole frame"),
             "seconds_measured": t_geom + t_fwd_all + t_bwd}
 
 
@@ -570,13 +571,12 @@ def main():
     stage_ms = {s: st_ms[i] / max(1, st_n[i]) for i, s in enumerate(_lib.STAGES)}
     fps = a.steps / (ms / 1e3)
 
-    if True:
-        # R (num_rendered) of this rank's shard: one forward through the raw _C API.  Every rank makes the call: a tile-sharded
-        # forward is collective (barriers of the peer-memory fabric, or the NCCL assembly in the autograd wrapper)
-        s, c = step.sc, step.sc.cam
-        fa = (c["image_width"], c["image_height"], c["tanfovx"], c["tanfovy"], c["viewmatrix"], c["projmatrix"], c["campos"], s.sh_degree,
-              s.gamma, 1.0, s.background_depth, s.background, s.vertex, s.shs, torch.Tensor([]), s.opacity, s.back_culling, s.rich_info, False)
-        R_local = int(tsC.rasterize_triangles(*fa, shard=(rank, world) if world > 1 else (0, 1), primitive=a.primitive)[0])
+    # R (num_rendered) of this rank's shard: one forward through the raw _C API.  Every rank makes the call: a tile-sharded
+    # forward is collective (barriers of the peer-memory fabric, or the NCCL assembly in the autograd wrapper)
+    s, c = step.sc, step.sc.cam
+    fa = (c["image_width"], c["image_height"], c["tanfovx"], c["tanfovy"], c["viewmatrix"], c["projmatrix"], c["campos"], s.sh_degree,
+          s.gamma, 1.0, s.background_depth, s.background, s.vertex, s.shs, torch.Tensor([]), s.opacity, s.back_culling, s.rich_info, False)
+    R_local = int(tsC.rasterize_triangles(*fa, shard=(rank, world) if world > 1 else (0, 1), primitive=a.primitive)[0])
     R_total = R_local * world if R_local is not None else None  # interleaved tiles: shards are balanced to <1%
 
     line = None

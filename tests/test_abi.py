@@ -67,3 +67,74 @@ def test_no_oracle_in_product_path():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no CPU or PyTorch fallback", ""), f"{f} mentions the oracle"
+
+
+def _dummy_call_structs(P=4, **geom_over):
+    """Camera / geometry / flags with non-NULL (never dereferenced) pointers: argument validation happens before any device work."""
+    import ctypes as C
+
+    fake = C.c_void_p(0x1000)
+    cam = _lib.Camera(64, 64, 0.5, 0.5, fake, fake, fake)
+    g = dict(P=P, sh_degree=0, M=1, C=3, use_shs=1, gamma=1.0, scale_modifier=1.0, background_depth=1.0, background=fake, vertex=fake,
+             shs=fake, feature=None, opacity=fake, model=None)
+    g.update(geom_over)
+    geom = _lib.Geometry(**g)
+    flags = _lib.Flags(0, 1, 0, 0, 1, 0, 0, None)
+    return cam, geom, flags, fake
+
+
+def test_argument_errors_are_reported_before_any_device_work():
+    """No GPU here: every call below must fail in validation (negative TS2D_E_* code), not in the CUDA runtime."""
+    import ctypes as C
+
+    lib = _lib.load()
+    R = C.c_int64(0)
+    cam, geom, flags, fake = _dummy_call_structs()
+    # reference-shaped errors (extension_interface.cu:53-76)
+    for over, code in ((dict(C=4), -4), (dict(gamma=-1.0), -6), (dict(shs=None), -3), (dict(sh_degree=2), -9), (dict(vertex=None), -7),
+                       (dict(use_shs=0, feature=None), -2)):
+        cam, geom, flags, fake = _dummy_call_structs(**over)
+        assert lib.ts2d_forward_geometry(C.byref(cam), C.byref(geom), C.byref(flags), fake, fake, 1 << 30, C.byref(R), None) == code, over
+    # shard / primitive
+    cam, geom, flags, fake = _dummy_call_structs()
+    flags.shard_rank, flags.shard_world = 2, 2
+    assert lib.ts2d_forward_geometry(C.byref(cam), C.byref(geom), C.byref(flags), fake, fake, 1 << 30, C.byref(R), None) == -10
+    flags.shard_rank, flags.primitive = 0, 7
+    assert lib.ts2d_forward_geometry(C.byref(cam), C.byref(geom), C.byref(flags), fake, fake, 1 << 30, C.byref(R), None) == -12
+    # parameter-space inputs: f_dc / logits required, f_rest required for M > 1, ratio > 0, SH mode only
+    for mi, M, use_shs in ((_lib.ModelInputs(None, None, fake, -1.0, 1.0, 1), 1, 1), (_lib.ModelInputs(fake, None, fake, -1.0, 1.0, 1), 4, 1),
+                           (_lib.ModelInputs(fake, fake, None, -1.0, 1.0, 1), 4, 1), (_lib.ModelInputs(fake, fake, fake, -1.0, 0.0, 1), 4, 1),
+                           (_lib.ModelInputs(fake, fake, fake, -1.0, 1.0, 1), 4, 0)):
+        cam, geom, flags, fake = _dummy_call_structs(M=M, use_shs=use_shs, shs=None, opacity=None, feature=fake if not use_shs else None,
+                                                     model=C.cast(C.pointer(mi), C.c_void_p))
+        assert lib.ts2d_forward_geometry(C.byref(cam), C.byref(geom), C.byref(flags), fake, fake, 1 << 30, C.byref(R), None) == -13
+    assert b"model inputs" in lib.ts2d_error_string(-13)
+    # peer-memory fabric: needs the fast kernels, 2 <= world <= 8, home_chunk % 32 == 0, the aliases the call writes; not ts2d_backward()
+    out = _lib.ForwardOut(None, fake, None, None, None, None)
+    for fab, exact in ((_lib.FabricC(world=2, home_chunk=32, out_feature_mc=0x2000), 1), (_lib.FabricC(world=1, home_chunk=32, out_feature_mc=0x2000), 0),
+                       (_lib.FabricC(world=2, home_chunk=33, out_feature_mc=0x2000), 0), (_lib.FabricC(world=2, home_chunk=32), 0),
+                       (_lib.FabricC(world=2, home_chunk=32, out_feature_mc=0x2000), 0)):  # last: rich_info without depth / normal aliases
+        cam, geom, flags, fake = _dummy_call_structs()
+        flags.exact, flags.fabric = exact, C.cast(C.pointer(fab), C.c_void_p)
+        assert lib.ts2d_forward_render(C.byref(cam), C.byref(geom), C.byref(flags), 10, fake, fake, 1 << 30, fake, 1 << 30, C.byref(out), None) == -14
+    fab = _lib.FabricC(world=2, home_chunk=32)
+    fab.scratch[0] = fab.scratch[1] = 0x3000
+    cam, geom, flags, fake = _dummy_call_structs()
+    flags.fabric = C.cast(C.pointer(fab), C.c_void_p)
+    loss = _lib.LossIn(fake, fake, fake)
+    bout = _lib.BackwardOut(fake, fake, fake, fake, fake, None)
+    assert lib.ts2d_backward(C.byref(cam), C.byref(geom), C.byref(flags), 10, fake, fake, fake, fake, C.byref(loss), C.byref(bout), fake, 1 << 30, None) == -14
+    assert b"fabric" in lib.ts2d_error_string(-14)
+    # model gradients must come with model inputs and vice versa
+    mg = _lib.ModelGrads(fake, None, *([None] * 8), 1)
+    bout = _lib.BackwardOut(fake, fake, fake, fake, fake, C.cast(C.pointer(mg), C.c_void_p))
+    cam, geom, flags, fake = _dummy_call_structs()
+    assert lib.ts2d_backward(C.byref(cam), C.byref(geom), C.byref(flags), 10, fake, fake, fake, fake, C.byref(loss), C.byref(bout), fake, 1 << 30, None) == -13
+    # small utilities
+    assert lib.ts2d_fabric_publish(None, fake, 0, 16, None) == -7
+    assert lib.ts2d_fabric_publish(fake, fake, 2, 16, None) == -14 and lib.ts2d_fabric_publish(fake, fake, 0, 0, None) == 0
+    assert lib.ts2d_downsample(None, fake, 1, 8, 8, 2, None) == -7 and lib.ts2d_downsample(fake, fake, 0, 8, 8, 2, None) == -11
+    assert lib.ts2d_downsample_bwd(fake, fake, 1, 8, 8, 0, None) == -11
+    # P == 0 short-circuits (extension_interface.cu:130)
+    cam, geom, flags, fake = _dummy_call_structs(P=0)
+    assert lib.ts2d_forward_geometry(C.byref(cam), C.byref(geom), C.byref(flags), None, None, 0, C.byref(R), None) == 0 and R.value == 0
