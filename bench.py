@@ -588,18 +588,21 @@ def main():
         stages = {k: {"ms": round(stage_ms[k], 4), "alg_bytes": ab[k], "gbs": round(ab[k] / (stage_ms[k] * 1e-3) / 1e9, 1) if stage_ms[k] > 0 else None,
                       "share": round(stage_ms[k] / max(1e-9, sum(stage_ms.values())), 3)} for k in stage_ms}
         ach = ab[dom] / (stage_ms[dom] * 1e-3) / 1e9
-        traffic, traffic_src = None, None  # DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this build
+        traffic, traffic_src, issue_pct = None, None, None  # DRAM bytes per launch / issue-slot use of the dominant kernel, from the committed ncu capture of this build
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             if world == 1 and a.primitive == "2D" and cfg["workload"].startswith(tj["workload"]):
                 traffic, traffic_src = tj["bytes_per_launch"].get(dom), tj["source"]
+                issue_pct = tj.get("issue_active_pct", {}).get(dom)
         except (OSError, KeyError, ValueError):
             pass
         roof = {"bound": "hbm", "traffic_source": traffic_src, "kernel": {"render_fwd": "k_render_fwd", "render_bwd": "k_render_bwd", "preprocess": "k_preprocess",
                                             "preprocess_bwd": "k_preprocess_bwd", "binning": "k_emit + cub radix + k_ranges",
                                             "order_scan": "cub radix + scan"}[dom],
                 "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5), "traffic": traffic, "peak_source": peak_src,
-                "note": "per-pixel composite is FP32/MUFU-issue bound, not HBM bound (SURVEY.md section 8d); per-stage figures in `stages`",
+                "issue_active_pct": issue_pct,
+                "note": "per-pixel composite is FP32/MUFU-issue bound, not HBM bound (SURVEY.md section 8d): issue_active_pct (ncu, same capture as "
+                        "`traffic`) is the fraction of its real ceiling; per-stage figures in `stages`",
                 "whole_frame_gbs": round(sum(ab.values()) / (ms / a.steps * 1e-3) / 1e9, 1)}
         own_per_step = 7  # k_preprocess, k_set_header, k_emit, k_ranges, k_render_fwd, k_render_bwd, k_preprocess_bwd
         line = dict(base, impl="ours", value=fps, ms_per_step=ms / a.steps, config=cfg, clocks=clocks, roofline=roof, stages=stages,
