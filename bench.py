@@ -329,6 +329,55 @@ class ModelStepReference:
         st["max_radii2D"][visible_mask] = torch.max(st["max_radii2D"][visible_mask], radii[visible_mask])
 
 
+def reference_image_loss(image, gt, w_ssim, kernel_cache={}):
+    """The trainer's pixel-wise loss as the reference computes it (trainer_utils.py:9-103 SSIMLoss with its 11x11 Gaussian window,
+    :323-324 L1; weights as VanillaTS_trainer.py:71-75,108), torch ops with torch's default TF32 setting for convolutions."""
+    import torch.nn.functional as F
+
+    ch = image.shape[0]
+    key = (ch, image.device)
+    if key not in kernel_cache:
+        x_grid = torch.arange(11).unsqueeze(0).repeat(11, 1)
+        xy = torch.stack([x_grid, x_grid.T], dim=-1).float()
+        k = torch.exp(-(xy - 5.0).pow(2).sum(dim=-1) / (2 * 1.5**2.0))
+        kernel_cache[key] = (k / k.sum()).unsqueeze(0).unsqueeze(0).float().repeat(ch, 1, 1, 1).to(image.device)
+    kernel = kernel_cache[key]
+    img1, img2 = image.unsqueeze(0), gt.unsqueeze(0)
+    window = lambda t: F.conv2d(t, kernel, padding=5, groups=ch)
+    mu1, mu2 = window(img1), window(img2)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    sigma1_sq = window(img1 * img1) - mu1_sq
+    sigma2_sq = window(img2 * img2) - mu2_sq
+    sigma12 = window(img1 * img2) - mu1_mu2
+    C1, C2 = 0.01**2, 0.03**2
+    ssim_map = ((2 * mu1_mu2 + C1) * (2 * sigma12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2))
+    return (1.0 - w_ssim) * torch.abs(image - gt).mean() + w_ssim * (1 - ssim_map.mean())
+
+
+def image_loss_ms(sc, dev, fused: bool, steps=10, w_ssim=0.2):
+    """fwd + bwd of the pixel-wise image loss on a frame of the workload's size (median of per-step CUDA-event times)."""
+    g = torch.Generator().manual_seed(4321)
+    h, w = sc.cam["image_height"], sc.cam["image_width"]
+    gt = torch.rand(3, h, w, generator=g).to(dev)
+    img = (gt + 0.1 * torch.randn(3, h, w, generator=g).to(dev)).clamp(0, 1).requires_grad_(True)
+    if fused:
+        from triangle_splatting_b200 import image_loss
+
+        fn = lambda: image_loss(img, gt, w_ssim)
+    else:
+        fn = lambda: reference_image_loss(img, gt, w_ssim)
+
+    def step():
+        img.grad = None
+        fn().backward()
+
+    med, mean = median_step_ms(step, steps, 3, dev, 1)
+    return {"ms": med, "mean_ms": mean, "steps": steps, "w_ssim": w_ssim,
+            "what": ("fused L1 + SSIM kernels of libts2d (ts2d_image_loss_forward / _backward)" if fused else
+                     "the reference's torch composition (L1 + SSIMLoss, five depth-wise 11x11 convolutions; cuDNN, TF32 allowed)") +
+                    f", fwd + bwd on a 3x{h}x{w} frame"}
+
+
 MODEL_STEP_WHAT = ("raw parameters (_vertex, _f_dc, _f_rest, _opacity logits) -> opacity activation, SH concat, background depth -> "
                    "rasterizer fwd + bwd -> gradients w.r.t. the raw parameters + _training_statistic; CUDA events, parameters resident")
 
@@ -538,7 +587,14 @@ def main():
             model_step = {"value": 1e3 / med, "unit": "frames/s", "ms_per_step": med, "mean_ms_per_step": mean, "steps": k_m,
                           "statistic": "median of per-step CUDA-event times", "what": MODEL_STEP_WHAT}
             del mstep
+        img_loss = None
+        if not a.no_model_step:
+            try:
+                img_loss = image_loss_ms(sc, dev, fused=False)
+            except Exception as ex:  # noqa: BLE001
+                img_loss = {"ms": None, "what": f"failed: {ex}"}
         line = dict(base, impl="reference", n_gpus=1, value=fps, ms_per_step=ms / a.steps, config=cfg, clocks=clocks, model_step=model_step,
+                    image_loss=img_loss,
                     e2e={"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                     cpu_baseline={"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference",
                                   "sample": "full workload on the reference's own CUDA build (oracle/_ref, sm_100): the reference has no CPU "
@@ -664,6 +720,9 @@ def main():
             line["model_step"] = {"value": 1e3 / med, "unit": "frames/s", "ms_per_step": med, "mean_ms_per_step": mean, "steps": k_m,
                                   "statistic": "median of per-step CUDA-event times", "what": MODEL_STEP_WHAT}
         del mstep
+
+    if rank == 0 and world == 1 and not a.no_model_step:
+        line["image_loss"] = image_loss_ms(sc, dev, fused=True)
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:

@@ -257,6 +257,19 @@ int ts2d_downsample_bwd(const float *dL_dout, float *dL_din, int32_t planes, int
  * `count` in floats, both multiples of 4, both pointers 16-byte aligned.  See ts2d_fabric. */
 int ts2d_fabric_publish(const float *local, float *multicast, int64_t first, int64_t count, void *stream);
 
+/* Fused image loss on the rendered frame (first step):
+ *     loss = w_l1 * mean|image - gt| + w_ssim * (1 - mean SSIM(image, gt))
+ * i.e. w_L1 * L1(image, gt) + w_ssim * SSIMLoss()(image, gt) of the trainer (src/diff_recon/trainers/VanillaTS_trainer.py:74-75,108;
+ * trainer_utils.py:323-324 and :9-103: 11x11 Gaussian window, sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2) in one forward and one
+ * backward kernel instead of ~30 torch kernels and ten depth-wise convolutions.  `image`, `gt`: planar [channels][height][width].
+ * forward writes loss[0] (and terms = {L1, 1 - SSIM} when non-NULL) and keeps three derivative maps in `scratch`
+ * (ts2d_image_loss_scratch_bytes()); backward turns them into dL/d image, scaled by the device scalar *grad_loss (NULL = 1). */
+size_t ts2d_image_loss_scratch_bytes(int32_t channels, int32_t width, int32_t height);
+int ts2d_image_loss_forward(const float *image, const float *gt, int32_t channels, int32_t width, int32_t height, float w_l1, float w_ssim,
+                            float *loss, float *terms, void *scratch, size_t scratch_bytes, void *stream);
+int ts2d_image_loss_backward(const float *image, const float *gt, int32_t channels, int32_t width, int32_t height, float w_l1, float w_ssim,
+                             const float *grad_loss, const void *scratch, size_t scratch_bytes, float *dL_dimage, void *stream);
+
 /* ---- state decoding, for parity tests against the reference's buffers ----
  * Each writes arrays in the reference's own element types/order.  Any output pointer may be NULL. */
 int ts2d_export_geometry(const void *geometry_state, int32_t P,
