@@ -75,3 +75,40 @@ def test_camera_follows_reference_conventions():
     h = torch.tensor([0.0, 0.0, 0.0, 1.0]) @ full
     assert h[3] == pytest.approx(4.0) and 0 < float(h[2] / h[3]) < 1
     assert cam["tanfovx"] == pytest.approx(1 / 2.4)
+
+
+def test_front_end_and_loss_host_checks_without_a_gpu():
+    """Parameter-space front-end and fused image loss: constructor / argument checks and the no-CPU-path rule (nothing reaches the device)."""
+    import math
+
+    from triangle_splatting_b200 import ImageLoss, TrainingStatistics, TriangleModelRasterizer, bilinear_downsample, gamma_rescale_ratio, image_loss
+
+    sc = make_scene("x", 8, 32, 32, sh_degree=1)
+    s = TriangleRasterizationSettings(**sc.settings_kwargs())
+    assert abs(gamma_rescale_ratio(1.0) - 1 / math.sqrt(2.0)) < 1e-15  # VanillaTS_model.py:616-617 at gamma = 1: 1 / sqrt(2 * 1 * Gamma(1))
+    with pytest.raises(ValueError, match="rasterizer type"):
+        TriangleModelRasterizer(s, primitive="4D")  # triangle_renderer.py:35-36
+    for bad in (0, 1.5):
+        with pytest.raises(ValueError):
+            TriangleModelRasterizer(s, render_up_scale=bad)
+    r = TriangleModelRasterizer(s, ste_threshold=0.3, rescale_ratio=0.9, render_up_scale=2)
+    assert r.raster_settings is s and r.render_up_scale == 2
+    f_dc, f_rest = sc.shs[:, :1].contiguous(), sc.shs[:, 1:].contiguous()
+    with pytest.raises(RuntimeError, match="no CPU path|CUDA"):
+        r.forward(sc.vertex, torch.zeros(sc.P, 2), torch.zeros(sc.P, 1), f_dc, f_rest)
+    st = TrainingStatistics(5, "cpu")
+    assert tuple(st.as_dict()) == _C.STAT_FIELDS and all(t.shape == (5,) for t in st.as_dict().values())
+    x = torch.rand(3, 8, 8)
+    assert bilinear_downsample(x, 1) is x
+    with pytest.raises(RuntimeError, match="no CPU path|CUDA"):
+        bilinear_downsample(x, 2)
+    with pytest.raises(RuntimeError, match="no CPU path|CUDA"):
+        image_loss(x, x.clone(), 0.2)
+    assert ImageLoss(0.2).w_ssim == 0.2
+    # model inputs are validated before any device work
+    mi = _C.ModelInputs(f_dc[:, 0], f_rest, torch.zeros(sc.P, 1))
+    with pytest.raises(RuntimeError, match="f_dc must have dimensions"):
+        mi.check(sc.P)
+    with pytest.raises(RuntimeError, match="rescale_ratio"):
+        _C.ModelInputs(f_dc, f_rest, torch.zeros(sc.P, 1), rescale_ratio=0.0).check(sc.P)
+    assert _C.ModelInputs(f_dc, f_rest, torch.zeros(sc.P, 1)).M == 4 and _C.ModelInputs(f_dc, None, torch.zeros(sc.P, 1)).M == 1
