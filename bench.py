@@ -401,7 +401,6 @@ def pinned_host_buffers(sc, all_host: bool):
 def cpu_oracle_baseline(sc, tile_step=None, budget_s=20.0, primitive="2D"):
     """Oracle port (oracle/ts2d_oracle.c, OpenMP over tiles) on a bounded sample: full per-triangle stages + binning,
     composite fwd+bwd on every `tile_step`-th tile, extrapolated to the whole frame."""
-    import numpy as np
 
     from oracle.oracle import Oracle
 

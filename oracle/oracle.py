@@ -11,7 +11,6 @@ opaque state buffers (R2D/src/param_struct.h:44-123), so parity tests can compar
 from __future__ import annotations
 
 import ctypes
-import os
 import subprocess
 from pathlib import Path
 

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import harness
-from harness import GRAD_KEYS, IMAGE_KEYS, assert_close_modulo_flips, mismatch_count, rel_err
+from harness import GRAD_KEYS, IMAGE_KEYS, assert_close_modulo_flips, mismatch_count
 from oracle.oracle import Oracle
 from triangle_splatting_b200.scenes import make_scene
 
