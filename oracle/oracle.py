@@ -29,11 +29,11 @@ def lib_path(kind: str) -> Path:
 def build(force: bool = False) -> None:
     """gcc the C restatement twice (REAL=float / REAL=double). No FMA contraction, no fast-math."""
     BUILD.mkdir(exist_ok=True)
-    for kind, real in (("f32", "float"), ("f64", "double")):
+    for kind, real, extra in (("f32", "float", []), ("f64", "double", []), ("f64d", "double", ["-DDECIDE_F32"])):
         out = lib_path(kind)
         if out.exists() and not force and out.stat().st_mtime >= SRC.stat().st_mtime:
             continue
-        cmd = ["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-std=c11", "-ffp-contract=off", "-fno-fast-math", f"-DREAL={real}",
+        cmd = ["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-std=c11", "-ffp-contract=off", "-fno-fast-math", f"-DREAL={real}", *extra,
                str(SRC), "-o", str(out), "-lm"]
         subprocess.run(cmd, check=True)
 
@@ -44,7 +44,7 @@ def _p(a: np.ndarray | None):
 
 class Oracle:
     def __init__(self, kind: str = "f32"):
-        assert kind in ("f32", "f64")
+        assert kind in ("f32", "f64", "f64d")  # f64d: fp64 values, the reference's fp32 decisions (header of ts2d_oracle.c)
         build()
         self.kind = kind
         self.real = np.float32 if kind == "f32" else np.float64
@@ -62,9 +62,13 @@ class Oracle:
     # ------------------------------------------------------------------ forward
     def forward(self, *, image_width, image_height, tanfovx, tanfovy, viewmatrix, projmatrix, campos, sh_degree, gamma,
                 background_depth, background, vertex, shs, feature, opacity, back_culling=False, rich_info=False,
-                scale_modifier=1.0, debug=False, stages="all", tile_step=1, tile_offset=0, primitive="2D") -> dict:
-        """primitive="3D": the reference's diff_triangle_rasterization_3D package (ts3d_oracle_* in ts2d_oracle.c)."""
+                scale_modifier=1.0, debug=False, stages="all", tile_step=1, tile_offset=0, primitive="2D", forced=None) -> dict:
+        """primitive="3D": the reference's diff_triangle_rasterization_3D package (ts3d_oracle_* in ts2d_oracle.c).
+        forced (kind "f64d" only): dict with the fp32 per-triangle state, lists and n_contrib of a GPU run of the reference (or of
+        our bit-identical state): radii, clamped, v2d/area2/v_depth or v_view, normal_view, rgb, point_list, ranges, n_contrib.
+        The composite then evaluates exactly that computation in double, taking every decision the way fp32 takes it."""
         assert primitive in ("2D", "3D")
+        assert (forced is not None) == (self.kind == "f64d"), "the f64d oracle needs (and only it takes) a forced fp32 state"
         W, H = int(image_width), int(image_height)
         vertex = self._r(vertex)
         P = vertex.shape[0]
@@ -107,6 +111,14 @@ class Oracle:
                 _p(vm), _p(pm), _p(cp), _p(vertex), _p(shs_a), _p(st["radii"]), _p(st["v2d"]), _p(st["area2"]), _p(st["normal_view"]),
                 _p(st["v_depth"]), _p(st["depth"]), _p(st["rgb"]), _p(st["clamped"]), _p(st["tiles_touched"]), _p(st["rect_min"]),
                 _p(st["rect_max"]))
+        if forced is not None and P > 0:
+            for k in ("v_view",) if primitive == "3D" else ("v2d", "area2", "v_depth"):
+                st[k] = np.ascontiguousarray(np.asarray(forced[k], dtype=real).reshape(st[k].shape))
+            st["normal_view"] = np.ascontiguousarray(np.asarray(forced["normal_view"], dtype=real).reshape(P, 3))
+            if use_shs:
+                st["rgb"] = np.ascontiguousarray(np.asarray(forced["rgb"], dtype=real).reshape(P, 3))
+            st["radii"] = np.ascontiguousarray(np.asarray(forced["radii"], dtype=np.int32))
+            st["clamped"] = np.ascontiguousarray(np.asarray(forced["clamped"], dtype=np.uint8).reshape(P, 3))
         st["feature"] = st["rgb"] if use_shs else feat_a.reshape(P, C)
         if stages == "preprocess":
             return st
@@ -123,10 +135,15 @@ class Oracle:
         if R > 0:
             self.lib.ts2d_oracle_bin(W, H, P, _p(st["tiles_touched"]), _p(st["rect_min"]), _p(st["rect_max"]), _p(depth32),
                                      _p(st["point_offsets"]), _p(st["keys"]), _p(st["point_list"]), _p(st["ranges"]))
+        if forced is not None:
+            st["num_rendered"] = int(np.asarray(forced["point_list"]).size)
+            st["point_list"] = np.ascontiguousarray(np.asarray(forced["point_list"], dtype=np.uint32))
+            st["ranges"] = np.ascontiguousarray(np.asarray(forced["ranges"], dtype=np.uint32).reshape(gx * gy, 2))
         if stages == "bin":
             return st
         st["final_T"] = np.ones((H, W), real)
-        st["n_contrib"] = np.zeros((H, W), np.uint32)
+        st["n_contrib"] = (np.ascontiguousarray(np.asarray(forced["n_contrib"], dtype=np.uint32).reshape(H, W)) if forced is not None
+                           else np.zeros((H, W), np.uint32))
         st["out_feature"] = np.zeros((C, H, W), real)
         st["out_depth"] = np.zeros((H, W), real)
         st["out_normal"] = np.zeros((3, H, W), real)

@@ -24,6 +24,15 @@
  * -DREAL=double ("truth" for accuracy comparisons).  Per-triangle gradient sums are accumulated in
  * double in both builds (the reference sums them with fp32 atomics in a non-deterministic order).
  * The one fp64 hop of the reference (ndc2Pix, auxiliary.h:35-38) is kept in double in both builds.
+ *
+ * Third build, -DREAL=double -DDECIDE_F32 ("f64d": truth GIVEN the reference's decisions).  At the benchmarked sizes a pure
+ * fp64 evaluation takes a handful of different per-pair / per-pixel decisions (alpha < 1/255, T <= 1e-4) than any fp32
+ * implementation, so its outputs are not comparable entry by entry.  In this build every decision is taken from an fp32
+ * shadow evaluation with the reference's arithmetic (fmaf where the reference's sm_100 SASS contracts, IEEE divide, powf,
+ * expf) on the fp32 per-triangle state handed in by the caller, the early termination is FORCED to the n_contrib handed in
+ * (the reference's own, bit-exact on the GPU), and every value is computed in double: the exact-arithmetic result of the very
+ * computation the reference performs.  tests/ use it to hold gradient accuracy at C2/C3 scale (ours vs truth <= k * reference
+ * vs truth).
  */
 #include <math.h>
 #include <stdint.h>
@@ -337,6 +346,39 @@ static inline int eval_pair(const real *v, real area2, real op, real gamma, real
     return 1;
 }
 
+#ifdef DECIDE_F32
+/* fp32 shadow of forward.cu:299-314 with the contraction of the reference's sm_100 build (cross products as
+ * fma(a, b, -(c * d)), ecc as fma(min, -3, 1)).  *unclamped: op * G < 0.99 (backward.cu:442). */
+static inline int decide_pair(const real *v, real area2, real op, real gamma, real px, real py, int *unclamped)
+{
+    const float fx = (float)px, fy = (float)py, A = (float)area2;
+    const float p1x = (float)v[0] - fx, p1y = (float)v[1] - fy, p2x = (float)v[2] - fx, p2y = (float)v[3] - fy, p3x = (float)v[4] - fx,
+                p3y = (float)v[5] - fy;
+    const float a1 = fmaf(p2x, p3y, -(p2y * p3x)) / A, a2 = fmaf(p3x, p1y, -(p3y * p1x)) / A, a3 = (1.0f - a1) - a2;
+    const float ecc = fmaf(fminf(fminf(a1, a2), a3), -3.0f, 1.0f);
+    if (ecc < 0.0f || ecc > 10.0f) return 0;
+    const float G = expf(-0.5f * powf(ecc, 2.0f * (float)gamma));
+    const float og = (float)op * G;
+    *unclamped = og < 0.99f;
+    return !(fminf(0.99f, og) < 1.0f / 255.0f);
+}
+#endif
+
+/* values of one pair that the shadow decided to keep (no tests; ecc is clamped at 0 where the double value dips below it) */
+static inline void eval_pair_values(const real *v, real area2, real op, real gamma, real px, real py, pair_t *o)
+{
+    o->pv1 = v2_make(v[0] - px, v[1] - py);
+    o->pv2 = v2_make(v[2] - px, v[3] - py);
+    o->pv3 = v2_make(v[4] - px, v[5] - py);
+    o->a1 = v2_cross(o->pv2, o->pv3) / area2;
+    o->a2 = v2_cross(o->pv3, o->pv1) / area2;
+    o->a3 = (real)1.0f - o->a1 - o->a2;
+    o->ecc = r_max((real)0, (real)1.0f - (real)3.0f * r_min(r_min(o->a1, o->a2), o->a3));
+    o->power = (real)-0.5f * r_pow(o->ecc, (real)2.0f * gamma);
+    o->G = r_exp(o->power);
+    o->alpha = r_min((real)0.99f, op * o->G);
+}
+
 /* ------------------------------------------------------- forward composite (forward.cu:198-355)
  * feature: [P][C] (the SH colours when use_shs).  out_feature planar [C][H][W].  contrib_* may be
  * NULL unless rich_info.  contrib_sum is accumulated in double internally. */
@@ -371,12 +413,24 @@ int ts2d_oracle_render(int W, int H, int C, real gamma, int rich_info, const uin
                     v3 accn = v3_make(0, 0, 0);
                     uint32_t contributor = 0, last = 0;
                     int done = 0;
+#ifdef DECIDE_F32
+                    const uint32_t forced = n_contrib[pix]; /* INPUT in this build: the reference's own stopping point */
+#endif
                     for (uint32_t k = beg; k < end && !done; k++) {
+#ifdef DECIDE_F32
+                        if (contributor >= forced) break;
+#endif
                         contributor++;
                         last = contributor;
                         const uint32_t id = list[k];
                         pair_t pr;
+#ifdef DECIDE_F32
+                        int unclamped_;
+                        if (!decide_pair(v2d + 6 * (size_t)id, area2[id], opacity[id], gamma, (real)px, (real)py, &unclamped_)) continue;
+                        eval_pair_values(v2d + 6 * (size_t)id, area2[id], opacity[id], gamma, (real)px, (real)py, &pr);
+#else
                         if (!eval_pair(v2d + 6 * (size_t)id, area2[id], opacity[id], gamma, (real)px, (real)py, &pr)) continue;
+#endif
                         const real contrib = pr.alpha * T;
                         for (int ch = 0; ch < C; ch++) acc[ch] += feature[(size_t)id * C + ch] * contrib;
                         if (rich_info) {
@@ -395,10 +449,16 @@ int ts2d_oracle_render(int W, int H, int C, real gamma, int rich_info, const uin
                             accd += d * contrib;
                         }
                         T *= ((real)1.0f - pr.alpha);
+#ifndef DECIDE_F32
                         if (T <= (real)0.0001f) done = 1; /* the terminating triangle IS blended, forward.cu:332-334 */
+#endif
                     }
                     final_T[pix] = T;
+#ifndef DECIDE_F32
                     n_contrib[pix] = last;
+#else
+                    (void)last;
+#endif
                     for (int ch = 0; ch < C; ch++) out_feature[(size_t)ch * H * W + pix] = acc[ch] + T * background[ch];
                     if (rich_info) {
                         out_depth[pix] = accd + T * background_depth;
@@ -459,7 +519,13 @@ int ts2d_oracle_render_bwd(int W, int H, int C, real gamma, int rich_info, const
                         const uint32_t id = list[k];
                         const real *v = v2d + 6 * (size_t)id;
                         pair_t pr;
+#ifdef DECIDE_F32
+                        int unclamped_;
+                        if (!decide_pair(v, area2[id], opacity[id], gamma, (real)px, (real)py, &unclamped_)) continue;
+                        eval_pair_values(v, area2[id], opacity[id], gamma, (real)px, (real)py, &pr);
+#else
                         if (!eval_pair(v, area2[id], opacity[id], gamma, (real)px, (real)py, &pr)) continue;
+#endif
                         const real op = opacity[id];
                         T /= ((real)1.0f - pr.alpha);
                         const real contrib = pr.alpha * T;
@@ -497,7 +563,11 @@ int ts2d_oracle_render_bwd(int W, int H, int C, real gamma, int rich_info, const
                         }
                         const real dL_dalpha = dL_dcontrib * T;
                         real dL_dpower = 0;
+#ifdef DECIDE_F32
+                        if (unclamped_) dL_dpower = dL_dalpha * pr.alpha;
+#else
                         if (op * pr.G < (real)0.99f) dL_dpower = dL_dalpha * pr.alpha; /* :442-446 */
+#endif
                         const real dL_decc = dL_dpower * 2 * gamma * pr.power / (pr.ecc + EPSF);
                         /* sub-gradient of min: first arg-min in order a1,a2,a3 with <=, :449-461 */
                         if (pr.a1 <= pr.a2 && pr.a1 <= pr.a3) dL_da.x += dL_decc * (real)-3.0f;
@@ -790,6 +860,58 @@ static inline int eval_pair3(const real *vv, const real *nv, real op, real gamma
     return !(o->alpha < (real)1.0f / (real)255.0f);
 }
 
+#ifdef DECIDE_F32
+/* fp32 shadow of the 3D per-pair decisions (R3D/src/forward.cu:243-276, backward.cu:330-352), plain fp32 without contraction:
+ * a pair within an ulp of a threshold may be decided differently from the GPU build; the tests that use this build compare
+ * error quantiles, not single entries. */
+static inline int decide_pair3(const real *vv, const real *nv, real op, real gamma, v3 ray, int bwd, int *unclamped)
+{
+    const float r[3] = {(float)ray.x, (float)ray.y, (float)ray.z}, n[3] = {(float)nv[0], (float)nv[1], (float)nv[2]};
+    float v[9];
+    for (int i = 0; i < 9; i++) v[i] = (float)vv[i];
+    const float pn = r[0] * n[0] + r[1] * n[1] + r[2] * n[2];
+    if (fabsf(pn) < (float)1e-8) return 0;
+    const float v1n = v[0] * n[0] + v[1] * n[1] + v[2] * n[2];
+    const float depth = bwd ? v1n * (1.0f / pn) : v1n / pn;
+    float pv[9];
+    for (int k = 0; k < 3; k++)
+        for (int c = 0; c < 3; c++) pv[3 * k + c] = v[3 * k + c] - r[c] * depth;
+    const float inv_nn = 1.0f / (n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+#define CR(a, b, o) { o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; }
+    float c1[3], c2[3];
+    CR((pv + 3), (pv + 6), c1);
+    CR((pv + 6), (pv + 0), c2);
+#undef CR
+    const float a1 = (c1[0] * n[0] + c1[1] * n[1] + c1[2] * n[2]) * inv_nn, a2 = (c2[0] * n[0] + c2[1] * n[1] + c2[2] * n[2]) * inv_nn;
+    const float a3 = 1.0f - a1 - a2;
+    const float ecc = 1.0f - 3.0f * fminf(fminf(a1, a2), a3);
+    if (ecc < 0.0f || ecc > 10.0f) return 0;
+    const float G = expf(-0.5f * powf(ecc, 2.0f * (float)gamma));
+    const float og = (float)op * G;
+    *unclamped = og < 0.99f;
+    if (bwd) return !(G < 1.0f / 255.0f);
+    return !(fminf(0.99f, og) < 1.0f / 255.0f);
+}
+static inline void eval_pair3_values(const real *vv, const real *nv, real op, real gamma, v3 ray, pair3_t *o)
+{
+    const v3 v1 = v3_make(vv[0], vv[1], vv[2]), v2 = v3_make(vv[3], vv[4], vv[5]), v3v = v3_make(vv[6], vv[7], vv[8]);
+    const v3 n = v3_make(nv[0], nv[1], nv[2]);
+    const real pn = v3_dot(ray, n);
+    o->inv_pn = (real)1.0f / pn;
+    o->depth = v3_dot(v1, n) / pn;
+    const v3 pview = v3_scale(ray, o->depth);
+    o->pv1 = v3_sub(v1, pview); o->pv2 = v3_sub(v2, pview); o->pv3 = v3_sub(v3v, pview);
+    o->inv_nn = (real)1.0f / v3_dot(n, n);
+    o->a1 = v3_dot(v3_cross(o->pv2, o->pv3), n) * o->inv_nn;
+    o->a2 = v3_dot(v3_cross(o->pv3, o->pv1), n) * o->inv_nn;
+    o->a3 = (real)1.0f - o->a1 - o->a2;
+    o->ecc = r_max((real)0, (real)1.0f - (real)3.0f * r_min(r_min(o->a1, o->a2), o->a3));
+    o->power = (real)-0.5f * r_pow(o->ecc, (real)2.0f * gamma);
+    o->G = r_exp(o->power);
+    o->alpha = r_min((real)0.99f, op * o->G);
+}
+#endif
+
 int ts3d_oracle_render(int W, int H, int C, real gamma, int rich_info, real tfx, real tfy, const uint32_t *ranges, const uint32_t *list,
                        const real *v_view, const real *normal_view, const real *feature, const real *opacity, real background_depth,
                        const real *background, real *final_T, uint32_t *n_contrib, real *out_feature, real *out_depth, real *out_normal,
@@ -818,12 +940,24 @@ int ts3d_oracle_render(int W, int H, int C, real gamma, int rich_info, real tfx,
                 v3 accn = v3_make(0, 0, 0);
                 uint32_t contributor = 0, last = 0;
                 int done = 0;
+#ifdef DECIDE_F32
+                const uint32_t forced = n_contrib[pix];
+#endif
                 for (uint32_t k = beg; k < end && !done; k++) {
+#ifdef DECIDE_F32
+                    if (contributor >= forced) break;
+#endif
                     contributor++;
                     last = contributor;
                     const uint32_t id = list[k];
                     pair3_t pr;
+#ifdef DECIDE_F32
+                    int unclamped_;
+                    if (!decide_pair3(v_view + 9 * (size_t)id, normal_view + 3 * (size_t)id, opacity[id], gamma, ray, 0, &unclamped_)) continue;
+                    eval_pair3_values(v_view + 9 * (size_t)id, normal_view + 3 * (size_t)id, opacity[id], gamma, ray, &pr);
+#else
                     if (!eval_pair3(v_view + 9 * (size_t)id, normal_view + 3 * (size_t)id, opacity[id], gamma, ray, 0, &pr)) continue;
+#endif
                     const real contrib = pr.alpha * T;
                     T *= ((real)1.0f - pr.alpha);
                     for (int ch = 0; ch < C; ch++) acc[ch] += feature[(size_t)id * C + ch] * contrib;
@@ -841,10 +975,16 @@ int ts3d_oracle_render(int W, int H, int C, real gamma, int rich_info, real tfx,
                         accn.x += normal_view[3 * id] * contrib; accn.y += normal_view[3 * id + 1] * contrib; accn.z += normal_view[3 * id + 2] * contrib;
                         accd += pr.depth * contrib;
                     }
+#ifndef DECIDE_F32
                     if (T <= (real)0.0001f) done = 1;
+#endif
                 }
                 final_T[pix] = T;
+#ifndef DECIDE_F32
                 n_contrib[pix] = last;
+#else
+                (void)last;
+#endif
                 for (int ch = 0; ch < C; ch++) out_feature[(size_t)ch * H * W + pix] = acc[ch] + T * background[ch];
                 if (rich_info) {
                     out_depth[pix] = accd + T * background_depth;
@@ -913,7 +1053,13 @@ int ts3d_oracle_render_bwd(int W, int H, int C, real gamma, int rich_info, real 
                     const real *vv = v_view + 9 * (size_t)id, *nv = normal_view + 3 * (size_t)id;
                     pair3_t pr;
                     const real op = opacity[id];
+#ifdef DECIDE_F32
+                    int unclamped_;
+                    if (!decide_pair3(vv, nv, op, gamma, ray, 1, &unclamped_)) continue;
+                    eval_pair3_values(vv, nv, op, gamma, ray, &pr);
+#else
                     if (!eval_pair3(vv, nv, op, gamma, ray, 1, &pr)) continue;
+#endif
                     const v3 v1 = v3_make(vv[0], vv[1], vv[2]), v2 = v3_make(vv[3], vv[4], vv[5]), v3v = v3_make(vv[6], vv[7], vv[8]);
                     const v3 n = v3_make(nv[0], nv[1], nv[2]);
                     T /= ((real)1.0f - pr.alpha);
@@ -936,7 +1082,11 @@ int ts3d_oracle_render_bwd(int W, int H, int C, real gamma, int rich_info, real 
                         accd = pr.alpha * pr.depth + ((real)1.0f - pr.alpha) * accd;
                     }
                     const real dL_dalpha = dL_dcontrib * T;
+#ifdef DECIDE_F32
+                    const real dL_dpower = unclamped_ ? dL_dalpha * pr.alpha : 0;
+#else
                     const real dL_dpower = (op * pr.G < (real)0.99f) ? dL_dalpha * pr.alpha : 0;
+#endif
                     const real dL_decc = dL_dpower * 2 * gamma * pr.power / (pr.ecc + EPSF);
                     v3 dda = v3_make(0, 0, 0);
                     if (pr.a1 <= pr.a2 && pr.a1 <= pr.a3) dda.x = (real)-3.0f;

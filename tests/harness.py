@@ -263,6 +263,41 @@ def run_oracle(sc: Scene, kind: str = "f32", backward: bool = True, primitive: s
     return out
 
 
+def run_truth(sc: Scene, base: dict, primitive: str = "2D", backward: bool = True) -> dict:
+    """fp64 values, the reference's fp32 decisions (oracle kind "f64d"): the exact-arithmetic result of the computation whose
+    per-triangle fp32 state, tile lists and per-pixel stopping points are those of `base` (a run_reference / run_ours / golden
+    dict -- these fields are bit-identical between the reference and ours).  Comparable entry by entry at ANY scene size."""
+    from oracle.oracle import Oracle
+
+    o = Oracle("f64d")
+    kw = sc.settings_kwargs()
+    kw.pop("debug")
+    kw = {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in kw.items()}
+    st = o.forward(**kw, vertex=sc.vertex.numpy(), shs=None if sc.shs is None else sc.shs.numpy(),
+                   feature=None if sc.feature is None else sc.feature.numpy(), opacity=sc.opacity.numpy(), primitive=primitive, forced=base)
+    out = dict(out_feature=st["out_feature"], final_T=st["final_T"])
+    if sc.rich_info:
+        out.update(depth=st["out_depth"], normal=st["out_normal"], contrib_sum=st["contrib_sum"], contrib_max=st["contrib_max"])
+    if backward:
+        g = o.backward(st, sc.grads["dL_dout_feature"].numpy(),
+                       sc.grads["dL_dout_depth"].numpy() if "dL_dout_depth" in sc.grads else None,
+                       sc.grads["dL_dout_normal"].numpy() if "dL_dout_normal" in sc.grads else None)
+        for k in GRAD_KEYS:
+            out[k] = g[k]
+    return out
+
+
+def err_quantiles(a, b, qs=(0.5, 0.99, 0.9999, 1.0), rel_floor: float = 1e-3):
+    """Quantiles of |a-b| / max(|b|, rel_floor * RMS(b)) (the SURVEY 8(d) metric is the q = 1 entry)."""
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    if b.size == 0:
+        return [0.0] * len(qs)
+    eps = rel_floor * float(np.sqrt(np.mean(b * b))) + 1e-30
+    e = np.abs(a - b) / np.maximum(np.abs(b), eps)
+    return [float(x) for x in np.quantile(e, qs)]
+
+
 # ------------------------------------------------------------------------------------ comparing
 INT_KEYS = ("num_rendered", "radii", "tiles_touched", "rect_min", "rect_max", "keys", "point_list", "ranges", "n_contrib", "clamped")
 STATE_FLOAT_KEYS = ("v2d", "area2", "v_view", "normal_view", "v_depth", "tri_depth", "rgb")

@@ -210,16 +210,19 @@ def test_downsample_is_interpolate_bilinear(s, cuda_device):
     assert torch.allclose(x.grad, g_ref, rtol=1e-6, atol=1e-9)
 
 
-def test_render_up_scale_ste_rescale_and_statistics(cuda_device):
+@pytest.mark.parametrize("k,rho_px", [(2, 6.0), (2, 0.5), (3, 0.8)])
+def test_render_up_scale_ste_rescale_and_statistics(k, rho_px, cuda_device):
     """The NerfSynthetic *_mesh recipe (config/NerfSynthetic_VanillaTS_mesh.yaml:26-28: ste 0.3, gamma_rescale, up-scale 2, 3D
     rasterizer): fused module vs VanillaTS_model.py:615-656 + :347-363 in torch around the reference-shaped op."""
     from triangle_splatting_b200 import TrainingStatistics, TriangleModelRasterizer, TriangleRasterizer3D, gamma_rescale_ratio
     from triangle_splatting_b200.scenes import make_scene
 
     dev = cuda_device
-    gamma, k, ste = 7.0, 2, 0.3
+    gamma, ste = 7.0, 0.3
     ratio = gamma_rescale_ratio(gamma)
-    sc = make_scene("mesh", 30000, 200, 152, sh_degree=0, rich_info=True, gamma=gamma, seed=5, geometry_grads=True, rho_px=6.0)
+    # rho_px < 1: many triangles whose full-resolution radius is below the up-scale factor -- rendered, but hidden from the
+    # statistics by `radii // render_up_scale` (the 3D primitive's radius has no half-pixel floor)
+    sc = make_scene("mesh", 30000, 200, 152, sh_degree=0, rich_info=True, gamma=gamma, seed=5, geometry_grads=True, rho_px=rho_px)
     s, p0 = _params(sc, dev)
     w, h = s.cam["image_width"], s.cam["image_height"]
     g = torch.Generator().manual_seed(9)
@@ -258,6 +261,9 @@ def test_render_up_scale_ste_rescale_and_statistics(cuda_device):
 
     assert render_b.shape == (3, h, w) and depth_b.shape == (h, w) and normal_b.shape == (3, h, w)
     assert torch.equal(radii, radii_b)
+    if rho_px < 1.0:  # the case this parametrisation exists for must really occur
+        full = rast.forward(vertex=vertex_in.detach(), center2D=c2d_a.detach(), opacity=opacity.detach(), shs=shs.detach(), feature=None)[1]
+        assert int(((full > 0) & (full // k == 0)).sum()) > 50, "scene has no triangles with 0 < radius < render_up_scale"
     assert torch.equal(render, render_b) and torch.equal(normal, normal_b)
     assert rel_err(depth_b.detach().cpu().numpy(), depth.detach().cpu().numpy()) <= 1e-6
     # radii // k can hide triangles whose radius is below the up-scale factor from `visible_mask`; the statistics follow the

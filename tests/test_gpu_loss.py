@@ -103,3 +103,30 @@ def test_image_loss_upstream_gradient_batches_and_errors(cuda_device):
         image_loss(img.float(), gt.float().to(dev), 0.2)  # no CPU path
     with pytest.raises(ValueError):
         image_loss(img.float().to(dev), gt[:, :-1].float().to(dev), 0.2)
+
+
+@pytest.mark.parametrize("shape", ["2d", "4d"])
+def test_image_loss_backward_keeps_the_callers_shape(shape, cuda_device):
+    """(H, W) and (B, C, H, W) inputs: the gradient comes back in the input's own shape and equals the (planes, H, W) result."""
+    from triangle_splatting_b200 import image_loss
+
+    dev = cuda_device
+    img, gt = _pair(3, 33, 47, seed=21)
+    if shape == "2d":
+        x_in, y_in = img[0].float().to(dev), gt[0].float().to(dev)
+        x3, y3 = img[:1].float().to(dev), gt[:1].float().to(dev)
+    else:
+        x_in = torch.stack([img, img.flip(-1)]).float().to(dev)
+        y_in = torch.stack([gt, gt.flip(-1)]).float().to(dev)
+        x3, y3 = x_in.reshape(-1, 33, 47).clone(), y_in.reshape(-1, 33, 47).clone()
+    x_in.requires_grad_(True)
+    x3.requires_grad_(True)
+    (3.0 * image_loss(x_in, y_in, 0.2)).backward()
+    (3.0 * image_loss(x3, y3, 0.2)).backward()
+    assert x_in.grad.shape == x_in.shape
+    assert torch.equal(x_in.grad.reshape(x3.shape), x3.grad)
+    # and against torch running the reference's lines on the flattened planes
+    x64 = x3.detach().double().requires_grad_(True)
+    (3.0 * reference_loss(x64, y3.double(), 0.8, 0.2)).backward()
+    g64 = x64.grad.cpu().numpy()
+    assert np.abs(x_in.grad.reshape(x3.shape).cpu().numpy() - g64).max() <= GRAD_MAX * np.abs(g64).max()

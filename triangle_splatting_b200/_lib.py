@@ -119,13 +119,14 @@ def load() -> C.CDLL:
     if _LIB is not None:
         return _LIB
     path = lib_path()
-    if os.environ.get("TS2D_NO_AUTOBUILD", "0") != "1":
+    if os.environ.get("TS2D_NO_AUTOBUILD", "0") != "1" and _build.needs_build():
         try:
-            if _build.needs_build():
-                _build.build()
-        except Exception as ex:  # nvcc missing etc.: fall through to the explicit error below if no .so
+            _build.build()
+        except FileNotFoundError as ex:  # no nvcc on this box: an existing .so is used as it is (its ABI version is checked below)
             if not path.exists():
                 raise RuntimeError(f"libts2d.so is missing and could not be built: {ex}") from ex
+        # a compile / link error with newer sources is NOT swallowed: running a stale library against current struct layouts
+        # would corrupt memory silently
     if not path.exists():
         raise RuntimeError(f"{path} not found: run `python -m triangle_splatting_b200.build` (needs nvcc); there is no CPU fallback")
     lib = C.CDLL(str(path))
@@ -133,6 +134,10 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # raises AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    have = int(lib.ts2d_abi_version())
+    if have != ABI_VERSION:
+        raise RuntimeError(f"{path} has ABI version {have}, this package binds version {ABI_VERSION}: rebuild it "
+                           "(python -m triangle_splatting_b200.build --force)")
     _LIB = lib
     return lib
 

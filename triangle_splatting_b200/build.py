@@ -41,8 +41,17 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     objdir = LIBDIR / "obj"
     objdir.mkdir(exist_ok=True)
 
+    headers = list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "ts2d.h", Path(__file__)]
+    newest_header = max(p.stat().st_mtime for p in headers)
+    extra = os.environ.get("TS2D_NVCC_EXTRA", "")
+    stamp = objdir / "flags.txt"
+    flags_changed = (not stamp.exists()) or stamp.read_text() != extra
+    stamp.write_text(extra)
+
     def one(src: str) -> Path:
         obj = objdir / (src + ".o")
+        if not force and not flags_changed and obj.exists() and obj.stat().st_mtime > max(newest_header, (CSRC / src).stat().st_mtime):
+            return obj  # up to date: only the translation units that changed are recompiled
         # TS2D_NVCC_EXTRA: extra defines for tuning experiments (e.g. "-DTS2D_FWD_MINB=4"); empty for the shipped build
         cmd = [nvcc(), "-c", str(CSRC / src), "-o", str(obj)] + NVCC_FLAGS + os.environ.get("TS2D_NVCC_EXTRA", "").split()
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -153,9 +153,12 @@ __device__ __forceinline__ void warp_rows_store_split(float *__restrict__ g_dc, 
 }
 static inline int ts2d_split_row_stride(int M) { return (3 * M) | 1; }
 
-// VanillaTS_model.py:347-363 (_training_statistic) for one visible triangle (radii > 0), fused into the K9 tail.
+// VanillaTS_model.py:347-363 (_training_statistic) for one visible triangle, fused into the K9 tail.  The model builds
+// visible_mask from the radii it RETURNS, i.e. after `radii // render_up_scale` (:651, :674): a triangle whose full-resolution
+// radius is below the up-scale factor is rendered (and gets gradients) but is not "visible" for the statistics.
 __device__ __forceinline__ void model_statistics(const ModelOut &mo, int idx, float gcx, float gcy, int radius)
 {
+    if (radius / mo.radii_div <= 0) return;
     if (mo.grad_accum) mo.grad_accum[idx] += sqrtf(gcx * gcx + gcy * gcy);
     if (mo.grad_denom) mo.grad_denom[idx] += 1.0f;
     if (mo.csum) mo.csum[idx] = fmaxf(mo.csum[idx], mo.fwd_csum[idx]);

@@ -29,6 +29,7 @@ class _ImageLoss(torch.autograd.Function):
             _require_cuda_f32(name, t)
         if image.shape != gt.shape:
             raise ValueError("Input images must have the same dimensions.")  # trainer_utils.py:84-85
+        ctx.in_shape = image.shape  # the gradient goes back in the caller's shape, not in the flattened (planes, H, W) one
         if image.dim() == 2:
             image, gt = image.unsqueeze(0), gt.unsqueeze(0)
         if image.dim() == 4:  # (B, C, H, W): every plane is an independent SSIM plane and both means run over all of them
@@ -63,7 +64,7 @@ class _ImageLoss(torch.autograd.Function):
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(lib.ts2d_image_loss_backward(_ptr(image), _ptr(gt), ch, w, h, ctx.w[0], ctx.w[1], _ptr(g), _ptr(scratch), scratch.numel(),
                                                     _ptr(out), stream), "ts2d_image_loss_backward")
-        return out, None, None, None
+        return out.view(ctx.in_shape), None, None, None
 
 
 def image_loss(image: torch.Tensor, gt_image: torch.Tensor, w_ssim: float, w_l1: float | None = None, return_terms: bool = False):
