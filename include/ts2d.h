@@ -18,21 +18,31 @@
  * exactly like the reference, __init__.py:100), and passes them to forward and again to backward.
  * Their internal layout is private to this library (ts2d_export_* decode them for parity tests).
  *
- * Forward is split in two calls because the size of the binning state depends on the number of
- * (triangle, tile) instances R (`num_rendered`), which is only known after the per-triangle
- * preprocess -- the reference resizes its binningBuffer tensor at the same point
- * (rasterizer.cu:189-195):
- *     ts2d_forward_geometry()  -> K1 preprocess + SH colour, depth sort, scan; returns R on the host
+ * The size of the binning state depends on the number of (triangle, tile) instances R (`num_rendered`), which is only known
+ * after the per-triangle preprocess -- the reference blocks on a device->host copy of R at that point and resizes its
+ * binningBuffer tensor (rasterizer.cu:189-195).  Two ways to drive the forward pass:
+ *     ts2d_forward()           -> ONE enqueue, no host synchronisation: the caller sizes the binning state for a capacity it
+ *                                 expects to suffice (e.g. R of the previous frame plus a margin); every kernel takes R from device
+ *                                 memory.  R comes back asynchronously in ts2d_frame_counters; if it exceeds the capacity the frame is
+ *                                 invalid (nothing is written out of bounds) and the caller repeats ts2d_forward_render() with a
+ *                                 larger state -- the geometry state of the first attempt stays valid.
+ *     ts2d_forward_geometry()  -> K1 preprocess + SH colour, depth sort, scan; returns R on the host (one synchronisation)
  *     ts2d_forward_render()    -> key emission, tile binning, tile ranges, front-to-back composite
  * Backward is one call:
  *     ts2d_backward()          -> reverse-walk composite gradients + preprocess/SH backward
+ * The capacity of a binning state is a function of its size in bytes (ts2d_binning_capacity()); forward and backward both
+ * derive the array layout from that, so the instance count itself never has to cross the ABI.
  *
  * Error convention: every entry point returns 0 on success; a negative TS2D_E_* code for argument
  * errors (the cases where the reference raises via AT_ERROR, extension_interface.cu:53-81); or a
  * positive cudaError_t.  ts2d_error_string() explains either.  When `debug` is non-zero every
  * launch is followed by a stream synchronisation + error check (reference: CHECK_CUDA,
  * auxiliary.h:358-367).  All work is enqueued on `stream` (a cudaStream_t passed as void*); the
- * only host synchronisation is the one inside ts2d_forward_geometry() that returns R.
+ * only host synchronisation is the one inside ts2d_forward_geometry() that returns R (ts2d_forward() has none).
+ *
+ * Gradients are bit-reproducible: the fast composite backward writes no atomics (every (sub-tile, list entry) pair owns a 64 B
+ * row of the scratch, rows are summed per triangle in a fixed order), unlike the reference's fp32 atomicAdd accumulation
+ * (backward.cu:412,482-490).
  *
  * Multi-GPU (image-space tile sharding, no counterpart in the reference): `shard_rank`/`shard_world`
  * restrict key emission and compositing to the tiles with tile_id % shard_world == shard_rank.
@@ -48,7 +58,7 @@
 extern "C" {
 #endif
 
-#define TS2D_ABI_VERSION 4
+#define TS2D_ABI_VERSION 5
 #define TS2D_TILE 16          /* R2D/src/config.h:4-5  BLOCK_X = BLOCK_Y = 16 */
 #define TS2D_MAX_CHANNELS 3   /* R2D/src/config.h:3 */
 
@@ -158,21 +168,19 @@ typedef struct ts2d_flags {
  * while they run, instead of a collective afterwards:
  *   pixels        every rank stores the pixels of its own tiles into ALL replicas with multimem.st on the NVSwitch multicast alias
  *                 (*_mc) -- disjoint tiles, plain stores, bit-identical frames everywhere;
- *   reductions    contrib_sum / contrib_max (forward) and the 16-float gradient accumulators (backward) of triangle i are reduced
- *                 on ONE rank, its home  min(i / home_chunk, world - 1),  with red.global over that rank's peer mapping (peer
- *                 tables below, index = rank): a single copy receives every rank's partial sums, so all ranks later read the same
- *                 bits (a multicast RED would round differently on every replica and let replicated optimizers drift apart);
+ *   reductions    contrib_sum / contrib_max of triangle i are reduced on ONE rank, its home  min(i / home_chunk, world - 1),
+ *                 with red.global over that rank's peer mapping (peer tables below, index = rank): a single copy receives every
+ *                 rank's partial values, so all ranks later read the same bits;
  *   publish       ts2d_fabric_publish(): the home rank copies its finished slice to every replica (multimem.st).
  * The caller owns the protocol: zero the reduced arrays on every replica, rendezvous, run the kernel, rendezvous, publish, rendezvous.
- * ts2d_forward_out then only carries `radii`; ts2d_backward_composite()'s `scratch` is the local replica.  Only the fast kernels
- * (flags.exact == 0, gamma in their range) take this path; ts2d_backward() (no place for the rendezvous) refuses it. */
+ * ts2d_forward_out then only carries `radii`.  Only the fast kernels (flags.exact == 0, gamma in their range) take this path.
+ * The backward exchange is a sum of each rank's per-triangle accumulators in rank order (ts2d_backward_composite), see distributed.py. */
 #define TS2D_MAX_RANKS 8
 typedef struct ts2d_fabric {
     int32_t world;                 /* ranks sharing the render, <= TS2D_MAX_RANKS */
     int32_t home_chunk;            /* triangles per home slice (a multiple of 32) */
     float *out_feature_mc, *depth_mc, *normal_mc;              /* multicast aliases of the image planes */
     float *contrib_sum[TS2D_MAX_RANKS], *contrib_max[TS2D_MAX_RANKS];  /* peer addresses of every rank's replica */
-    float *scratch[TS2D_MAX_RANKS];                            /* peer addresses of every rank's backward scratch */
 } ts2d_fabric;
 
 #define TS2D_PRIMITIVE_2D 0
@@ -207,16 +215,44 @@ typedef struct ts2d_backward_out {
     const ts2d_model_grads *model;  /* required iff geometry.model is set; dL_dshs is then ignored */
 } ts2d_backward_out;
 
+/* Device-side counters of a frame.  A ts2d_counters object owns pinned host memory for them plus the events that say when the
+ * asynchronous copies have landed; pass one to ts2d_forward() / ts2d_forward_render() and ask it afterwards:
+ *   ts2d_counters_num_rendered()   waits only for the scan (the rest of the frame is still queued on the GPU: no bubble),
+ *   ts2d_counters_backward_rows()  waits for the end of that forward pass.
+ * One object per forward pass in flight; not thread-safe.  ts2d_read_counters() is the blocking alternative (reads the geometry
+ * state, synchronises the stream). */
+typedef struct ts2d_counters ts2d_counters;
+typedef struct ts2d_frame_counters {
+    int64_t num_rendered;    /* R: (triangle, tile) instances of the frame (the reference's return value, rasterizer.cu:190-193).
+                                R > ts2d_binning_capacity(binning_state_bytes): the frame is invalid, render again with a larger state */
+    int64_t backward_rows;   /* (sub-tile, list entry) pairs the composite backward will write a 64 B row for: sizes its scratch
+                                (ts2d_backward_scratch_bytes).  0 with the mirror kernels (flags.exact), which use the reference's atomics */
+} ts2d_frame_counters;
+
+int ts2d_counters_create(ts2d_counters **out);
+void ts2d_counters_destroy(ts2d_counters *c);
+int ts2d_counters_num_rendered(ts2d_counters *c, int64_t *num_rendered);
+int ts2d_counters_backward_rows(ts2d_counters *c, int64_t *backward_rows);
+int ts2d_read_counters(const void *geometry_state, int32_t P, ts2d_frame_counters *out_host, void *stream);
+
 int ts2d_abi_version(void);
 const char *ts2d_error_string(int code);
 
 /* Sizes of the opaque state blobs (bytes).  cf. BaseDataBuffer::requiredSize, param_struct.h:36-40. */
 size_t ts2d_geometry_state_bytes(int32_t P);
-size_t ts2d_binning_state_bytes(int64_t num_rendered, int32_t width, int32_t height);
+size_t ts2d_binning_state_bytes(int64_t capacity /* instances */, int32_t width, int32_t height);
+int64_t ts2d_binning_capacity(size_t binning_state_bytes);  /* instances a binning state of that size holds (>= the capacity it was sized for) */
 size_t ts2d_image_state_bytes(int32_t width, int32_t height);
-/* Scratch for backward: per-triangle screen-space gradient accumulators (the reference's dL_dv*_2D,
- * dL_dnormal_view, dL_dv_depth temporaries, rasterizer.cu:289-300). */
-size_t ts2d_backward_scratch_bytes(int32_t P);
+/* Scratch for backward: per-triangle screen-space gradient accumulators (the reference's dL_dv*_2D, dL_dnormal_view, dL_dv_depth
+ * temporaries, rasterizer.cu:289-300) at its START (16 floats per triangle), followed by the row storage of the atomics-free
+ * write-back: `backward_rows` from ts2d_frame_counters (the mirror kernels need no rows: pass 0). */
+size_t ts2d_backward_scratch_bytes(int32_t P, size_t binning_state_bytes, int64_t backward_rows);
+
+/* Replaces rasterizer.cu:116-267 in ONE enqueue without host synchronisation (see the header comment).  Writes radii[P] and
+ * every array of `out`. */
+int ts2d_forward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int32_t *radii, void *geometry_state,
+                 size_t geometry_state_bytes, void *binning_state, size_t binning_state_bytes, void *image_state, size_t image_state_bytes,
+                 const ts2d_forward_out *out, ts2d_counters *counters /* may be NULL */, void *stream);
 
 /* Replaces rasterizer.cu:116-193: preprocess (forward.cu:61-193), then ordering + scan.
  * Writes radii[P]; returns num_rendered through *num_rendered_host (one stream synchronisation). */
@@ -224,23 +260,27 @@ int ts2d_forward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, con
                           int32_t *radii, void *geometry_state, size_t geometry_state_bytes,
                           int64_t *num_rendered_host, void *stream);
 
-/* Replaces rasterizer.cu:195-266: duplicateWithKeys, SortPairs, identifyTileRanges, FORWARD::renderCUDA. */
+/* Replaces rasterizer.cu:195-266: duplicateWithKeys, SortPairs, identifyTileRanges, FORWARD::renderCUDA.
+ * num_rendered: what ts2d_forward_geometry() returned, or -1 when only the device knows it (then the grids are sized for the
+ * capacity of the binning state).  `counters` may be NULL. */
 int ts2d_forward_render(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags,
                         int64_t num_rendered, const void *geometry_state, void *binning_state, size_t binning_state_bytes,
-                        void *image_state, size_t image_state_bytes, const ts2d_forward_out *out, void *stream);
+                        void *image_state, size_t image_state_bytes, const ts2d_forward_out *out, ts2d_counters *counters,
+                        void *stream);
 
-/* Replaces rasterizer.cu:269-358: BACKWARD::renderCUDA + BACKWARD::preprocessCUDA. */
-int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int64_t num_rendered,
-                  const int32_t *radii, const void *geometry_state, const void *binning_state, const void *image_state,
+/* Replaces rasterizer.cu:269-358: BACKWARD::renderCUDA + BACKWARD::preprocessCUDA.  The binning state is not const: the backward
+ * pass narrows the sub-tile coverage bits of the instance keys to the pairs it visits (idempotent). */
+int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags,
+                  const int32_t *radii, const void *geometry_state, void *binning_state, size_t binning_state_bytes, const void *image_state,
                   const ts2d_loss_in *loss, const ts2d_backward_out *out, void *scratch, size_t scratch_bytes, void *stream);
 
 /* ts2d_backward split in two for tile-sharded multi-GPU (no counterpart in the reference): each rank runs the composite
- * backward over its own tiles into `scratch` (16 floats per triangle: the reference's dL_dv*_2D / dL_dnormal_view /
- * dL_dv_depth / dL_drgb / dL_dopacity temporaries, rasterizer.cu:289-300, in this library's layout), the caller sum-reduces
- * `scratch` across ranks (ts2d_backward_scratch_bytes(P) bytes of fp32), then every rank runs the per-triangle stage. */
-int ts2d_backward_composite(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int64_t num_rendered,
-                            const void *geometry_state, const void *binning_state, const void *image_state, const ts2d_loss_in *loss,
-                            void *scratch, size_t scratch_bytes, void *stream);
+ * backward over its own tiles; the first 16 * P floats of `scratch` then hold its per-triangle partial sums (the reference's
+ * dL_dv*_2D / dL_dnormal_view / dL_dv_depth / dL_drgb / dL_dopacity temporaries, rasterizer.cu:289-300, in this library's layout),
+ * the caller sum-reduces those across ranks, then every rank runs the per-triangle stage on the sums. */
+int ts2d_backward_composite(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags,
+                            const void *geometry_state, void *binning_state, size_t binning_state_bytes, const void *image_state,
+                            const ts2d_loss_in *loss, void *scratch, size_t scratch_bytes, void *stream);
 int ts2d_backward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, const int32_t *radii,
                            const void *geometry_state, const ts2d_backward_out *out, const void *scratch, size_t scratch_bytes,
                            void *stream);
@@ -283,8 +323,8 @@ int ts2d_export_geometry3d(const void *geometry_state, int32_t P,
                            uint32_t *rect_max /*[P][2]*/, void *stream);
 /* model inputs: the activated (sigmoid / STE) opacity the kernels used, and the device-computed background depth */
 int ts2d_export_model(const void *geometry_state, int32_t P, int32_t primitive, float *opacity /*[P]*/, float *background_depth /*[1]*/, void *stream);
-int ts2d_export_binning(const void *geometry_state, const void *binning_state, const void *image_state, int32_t P, int64_t num_rendered,
-                        int32_t width, int32_t height, uint64_t *keys_sorted /*[R]*/, uint32_t *point_list /*[R]*/,
+int ts2d_export_binning(const void *geometry_state, const void *binning_state, size_t binning_state_bytes, const void *image_state, int32_t P,
+                        int64_t num_rendered, int32_t width, int32_t height, uint64_t *keys_sorted /*[R]*/, uint32_t *point_list /*[R]*/,
                         uint32_t *ranges /*[tiles][2]*/, void *stream);
 int ts2d_export_image(const void *image_state, int32_t width, int32_t height, uint32_t *n_contrib /*[H][W]*/, float *final_T /*[H][W]*/,
                       void *stream);
@@ -298,7 +338,7 @@ enum {
     TS2D_STAGE_ORDER_SCAN = 1,     /* K2/K3 depth sort of P keys + scan */
     TS2D_STAGE_BINNING = 2,        /* K4-K6 emit, tile radix sort, ranges */
     TS2D_STAGE_RENDER_FWD = 3,     /* K7 */
-    TS2D_STAGE_RENDER_BWD = 4,     /* K8 */
+    TS2D_STAGE_RENDER_BWD = 4,     /* K8: row marking + scan, composite backward, per-triangle row reduction */
     TS2D_STAGE_PREPROCESS_BWD = 5, /* K9 */
     TS2D_NUM_STAGES = 6
 };

@@ -137,7 +137,7 @@ def decode_state(s: Scene, fwd, dev, primitive: str = "2D") -> dict:
     keys = torch.zeros((max(R, 1),), device=dev, dtype=torch.int64)
     plist = torch.zeros((max(R, 1),), device=dev, dtype=torch.int32)
     ranges = torch.zeros((gx * gy, 2), device=dev, dtype=torch.int32)
-    _lib.check(lib.ts2d_export_binning(p(gb), p(bb), p(ib), P, R, W, H, p(keys), p(plist), p(ranges), stream), "export_binning")
+    _lib.check(lib.ts2d_export_binning(p(gb), p(bb), bb.numel(), p(ib), P, R, W, H, p(keys), p(plist), p(ranges), stream), "export_binning")
     ncon = torch.zeros((H, W), device=dev, dtype=torch.int32)
     fT = torch.zeros((H, W), device=dev, dtype=torch.float32)
     _lib.check(lib.ts2d_export_image(p(ib), W, H, p(ncon), p(fT), stream), "export_image")
@@ -149,6 +149,26 @@ def decode_state(s: Scene, fwd, dev, primitive: str = "2D") -> dict:
     out.update(keys=_np(keys)[:R].view(np.uint64), point_list=_np(plist)[:R].view(np.uint32), ranges=_np(ranges).view(np.uint32),
                n_contrib=_np(ncon).view(np.uint32), final_T=_np(fT))
     return out
+
+
+def sorted_instance_keys(fwd, W: int, H: int) -> np.ndarray:
+    """Our sorted instance keys (tile id << 8 | sub-tile coverage bits) decoded from the binning blob of a forward tuple:
+    [look-back words | tkey0 | tkey1 | tval0 | tval1], every array 256-byte aligned and sized for the blob's capacity; the
+    radix passes ping-pong between the two key buffers starting from 0 (csrc/ts2d_api.cu: carve_binning, ts2d_sorted_buf)."""
+    from triangle_splatting_b200 import _lib
+
+    lib = _lib.load()
+    R, bb = int(fwd[0]), fwd[8]
+    cap = int(lib.ts2d_binning_capacity(bb.numel()))
+    al = lambda v: (v + 255) // 256 * 256
+    status = al(((cap + 3071) // 3072) * 256 * 8)
+    n_tiles = ((W + TILE - 1) // TILE) * ((H + TILE - 1) // TILE)
+    bits = 1
+    while bits < 24 and (1 << bits) < n_tiles:
+        bits += 1
+    sbuf = ((bits + 7) // 8) & 1
+    off = status + sbuf * al(4 * cap)
+    return bb[off:off + 4 * R].view(torch.int32).cpu().numpy().view(np.uint32)
 
 
 # ------------------------------------------------------------------------------- live reference

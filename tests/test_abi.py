@@ -25,7 +25,7 @@ def test_library_loads_and_exports_everything():
     lib = _lib.load()
     for name in _declared():
         assert hasattr(lib, name), name
-    assert lib.ts2d_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.ts2d_abi_version() == _lib.ABI_VERSION == 5
     assert b"vertex must have dimensions" in lib.ts2d_error_string(-1)
     assert lib.ts2d_error_string(0) == b"ok"
 
@@ -38,7 +38,7 @@ def test_ctypes_structs_match_the_header_layout():
 
     names = {"ts2d_camera": _lib.Camera, "ts2d_geometry": _lib.Geometry, "ts2d_flags": _lib.Flags, "ts2d_forward_out": _lib.ForwardOut,
              "ts2d_loss_in": _lib.LossIn, "ts2d_backward_out": _lib.BackwardOut, "ts2d_model_inputs": _lib.ModelInputs,
-             "ts2d_model_grads": _lib.ModelGrads, "ts2d_fabric": _lib.FabricC}
+             "ts2d_model_grads": _lib.ModelGrads, "ts2d_fabric": _lib.FabricC, "ts2d_frame_counters": _lib.FrameCounters}
     body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in names)
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "t.c")
@@ -56,7 +56,16 @@ def test_state_sizes_are_monotone_and_aligned():
     assert 0 < a < b and a % 256 == 0
     assert lib.ts2d_image_state_bytes(1920, 1080) >= 1920 * 1080 * 8
     assert lib.ts2d_binning_state_bytes(10**6, 1920, 1080) >= 16 * 10**6
-    assert lib.ts2d_backward_scratch_bytes(1000) >= 64 * 1000
+    # capacity is the inverse of the size function (forward and backward derive the array layout from the blob size alone)
+    for cap in (1, 2, 3071, 3072, 3073, 10**6, 6946149, 23 * 10**6):
+        b = lib.ts2d_binning_state_bytes(cap, 1920, 1080)
+        got = lib.ts2d_binning_capacity(b)
+        assert got >= cap and lib.ts2d_binning_state_bytes(got, 1920, 1080) <= b, (cap, got)
+        assert lib.ts2d_binning_capacity(b - 256) < got
+    assert lib.ts2d_binning_capacity(0) == 0
+    bb = lib.ts2d_binning_state_bytes(5000, 64, 64)
+    assert lib.ts2d_backward_scratch_bytes(1000, bb, 0) >= 64 * 1000
+    assert lib.ts2d_backward_scratch_bytes(1000, bb, 300) >= lib.ts2d_backward_scratch_bytes(1000, bb, 0) + 64 * 290
 
 
 def test_no_oracle_in_product_path():
@@ -109,27 +118,29 @@ def test_argument_errors_are_reported_before_any_device_work():
                                                      model=C.cast(C.pointer(mi), C.c_void_p))
         assert lib.ts2d_forward_geometry(C.byref(cam), C.byref(geom), C.byref(flags), fake, fake, 1 << 30, C.byref(R), None) == -13
     assert b"model inputs" in lib.ts2d_error_string(-13)
-    # peer-memory fabric: needs the fast kernels, 2 <= world <= 8, home_chunk % 32 == 0, the aliases the call writes; not ts2d_backward()
+    # peer-memory fabric: needs the fast kernels, 2 <= world <= 8, home_chunk % 32 == 0, the aliases the call writes
     out = _lib.ForwardOut(None, fake, None, None, None, None)
     for fab, exact in ((_lib.FabricC(world=2, home_chunk=32, out_feature_mc=0x2000), 1), (_lib.FabricC(world=1, home_chunk=32, out_feature_mc=0x2000), 0),
                        (_lib.FabricC(world=2, home_chunk=33, out_feature_mc=0x2000), 0), (_lib.FabricC(world=2, home_chunk=32), 0),
                        (_lib.FabricC(world=2, home_chunk=32, out_feature_mc=0x2000), 0)):  # last: rich_info without depth / normal aliases
         cam, geom, flags, fake = _dummy_call_structs()
         flags.exact, flags.fabric = exact, C.cast(C.pointer(fab), C.c_void_p)
-        assert lib.ts2d_forward_render(C.byref(cam), C.byref(geom), C.byref(flags), 10, fake, fake, 1 << 30, fake, 1 << 30, C.byref(out), None) == -14
-    fab = _lib.FabricC(world=2, home_chunk=32)
-    fab.scratch[0] = fab.scratch[1] = 0x3000
-    cam, geom, flags, fake = _dummy_call_structs()
-    flags.fabric = C.cast(C.pointer(fab), C.c_void_p)
+        assert lib.ts2d_forward_render(C.byref(cam), C.byref(geom), C.byref(flags), 10, fake, fake, 1 << 30, fake, 1 << 30, C.byref(out), None, None) == -14
+        assert lib.ts2d_forward(C.byref(cam), C.byref(geom), C.byref(flags), fake, fake, 1 << 30, fake, 1 << 30, fake, 1 << 30, C.byref(out), None, None) == -14
     loss = _lib.LossIn(fake, fake, fake)
-    bout = _lib.BackwardOut(fake, fake, fake, fake, fake, None)
-    assert lib.ts2d_backward(C.byref(cam), C.byref(geom), C.byref(flags), 10, fake, fake, fake, fake, C.byref(loss), C.byref(bout), fake, 1 << 30, None) == -14
     assert b"fabric" in lib.ts2d_error_string(-14)
+    # state blobs too small for what they must hold
+    cam, geom, flags, fake = _dummy_call_structs()
+    out = _lib.ForwardOut(fake, fake, fake, fake, fake, fake)
+    assert lib.ts2d_forward_render(C.byref(cam), C.byref(geom), C.byref(flags), 10**6, fake, fake, 4096, fake, 1 << 30, C.byref(out), None, None) == -8
+    assert lib.ts2d_forward(C.byref(cam), C.byref(geom), C.byref(flags), fake, fake, 16, fake, 1 << 30, fake, 1 << 30, C.byref(out), None, None) == -8
+    bout = _lib.BackwardOut(fake, fake, fake, fake, fake, None)
+    assert lib.ts2d_backward(C.byref(cam), C.byref(geom), C.byref(flags), fake, fake, fake, 1 << 20, fake, C.byref(loss), C.byref(bout), fake, 64, None) == -8
     # model gradients must come with model inputs and vice versa
     mg = _lib.ModelGrads(fake, None, *([None] * 8), 1)
     bout = _lib.BackwardOut(fake, fake, fake, fake, fake, C.cast(C.pointer(mg), C.c_void_p))
     cam, geom, flags, fake = _dummy_call_structs()
-    assert lib.ts2d_backward(C.byref(cam), C.byref(geom), C.byref(flags), 10, fake, fake, fake, fake, C.byref(loss), C.byref(bout), fake, 1 << 30, None) == -13
+    assert lib.ts2d_backward(C.byref(cam), C.byref(geom), C.byref(flags), fake, fake, fake, 1 << 20, fake, C.byref(loss), C.byref(bout), fake, 1 << 30, None) == -13
     # small utilities
     assert lib.ts2d_fabric_publish(None, fake, 0, 16, None) == -7
     assert lib.ts2d_fabric_publish(fake, fake, 2, 16, None) == -14 and lib.ts2d_fabric_publish(fake, fake, 0, 0, None) == 0

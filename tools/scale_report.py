@@ -58,11 +58,7 @@ def work_stats(run, fwd_state, W, H):
                list_len_max=int(lens.max()), pairs_sum_n_contrib=int(ncon.sum()), n_contrib_mean=float(ncon.mean()), pairs_upper_256R=int(256 * int(run["num_rendered"])))
     if fwd_state is not None:
         R = out["R"]
-        bb = fwd_state[8]
-        al = lambda v: (v + 255) // 256 * 256
-        n4 = 4 * max(R, 1)
-        off1 = al(n4)
-        tkey1 = bb[off1:off1 + 4 * R].view(torch.int32).cpu().numpy().view(np.uint32)
+        tkey1 = harness.sorted_instance_keys(fwd_state, W, H)
         masks = tkey1 & 0xFF
         bits = np.unpackbits(masks.astype(np.uint8)[:, None], axis=1, bitorder="little")  # [R, 8]
         out["subtile_visits_mask_bits"] = int(bits.sum())

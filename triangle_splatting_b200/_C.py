@@ -41,6 +41,62 @@ def set_exact(flag: bool) -> bool:
     return old
 
 
+# One-enqueue forward (ts2d_forward): the binning state is sized for a capacity derived from the largest instance count seen so
+# far for the same problem shape, every kernel takes the true count R from device memory, and R is only read back -- behind an
+# event recorded right after the scan, while the rest of the frame is already queued -- to return it and to detect an overflow.
+# TS2D_SYNC_FORWARD=1 forces the two-call path (ts2d_forward_geometry blocks for R, like the reference's cudaMemcpy,
+# rasterizer.cu:190-193); it is also what the first frame of a shape and debug=True use.
+SYNC_FORWARD = os.environ.get("TS2D_SYNC_FORWARD", "0") == "1"
+_R_SEEN = {}  # (device index, P, W, H, primitive, shard) -> largest R seen
+
+
+def _capacity_for(key):
+    r = _R_SEEN.get(key)
+    if r is None or SYNC_FORWARD:
+        return None
+    return max(int(1.5 * r), r + (1 << 20))
+
+
+class FrameCounters:
+    """ts2d_counters handle: pinned host memory + events for the device-side counters of one forward pass."""
+
+    _free = []
+
+    def __init__(self):
+        lib = _lib.load()
+        if FrameCounters._free:
+            self.h = FrameCounters._free.pop()
+        else:
+            h = C.c_void_p()
+            _lib.check(lib.ts2d_counters_create(C.byref(h)), "ts2d_counters_create")
+            self.h = h
+
+    def num_rendered(self) -> int:
+        v = C.c_int64(0)
+        _lib.check(_lib.load().ts2d_counters_num_rendered(self.h, C.byref(v)), "ts2d_counters_num_rendered")
+        return int(v.value)
+
+    def backward_rows(self) -> int:
+        v = C.c_int64(0)
+        _lib.check(_lib.load().ts2d_counters_backward_rows(self.h, C.byref(v)), "ts2d_counters_backward_rows")
+        return int(v.value)
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h is not None and FrameCounters is not None:
+            FrameCounters._free.append(h)  # events and pinned memory are reused by a later frame
+
+
+class NumRendered(int):
+    """The `num_rendered` the reference returns (an int) that also carries the frame's counters handle from forward to backward:
+    the reference-shaped wrappers pass it through unchanged (ctx.num_rendered, __init__.py:93,123)."""
+
+    def __new__(cls, value, counters=None):
+        obj = super().__new__(cls, value)
+        obj.counters = counters
+        return obj
+
+
 class ModelInputs:
     """Host-side mirror of ts2d_model_inputs (include/ts2d.h)."""
 
@@ -229,15 +285,13 @@ def rasterize_triangles(image_width: int, image_height: int, tan_fovx: float, ta
                                            background_depth, background, vertex, shs, feature, opacity, P, use_shs, Cn, M, back_culling,
                                            rich_info, debug, shard, primitive, model)
         gbytes = lib.ts2d_geometry_state_bytes(P)
-        geometryBuffer = torch.empty((gbytes,), **u8)
-        num_rendered = C.c_int64(0)
-        _lib.check(lib.ts2d_forward_geometry(C.byref(cam), C.byref(geom), C.byref(flags), _ptr(radii), _ptr(geometryBuffer), gbytes,
-                                             C.byref(num_rendered), stream), "ts2d_forward_geometry")
-        R = int(num_rendered.value)
-        bbytes = lib.ts2d_binning_state_bytes(R, W, H)
         ibytes = lib.ts2d_image_state_bytes(W, H)
-        binningBuffer = torch.empty((bbytes,), **u8)
+        geometryBuffer = torch.empty((gbytes,), **u8)
         imageBuffer = torch.empty((ibytes,), **u8)
+        counters = FrameCounters()
+        shape_key = (dev.index, P, W, H, primitive, tuple(shard))
+        # (the peer-memory path keeps the blocking two-call forward: a repeated render would RED into the peers' replicas twice)
+        cap = None if (debug or fab is not None) else _capacity_for(shape_key)
         if fab is not None:
             if rich_info:
                 frame[offs[3]:].zero_()  # contrib_sum / contrib_max: the home slices receive REDs from every rank
@@ -252,8 +306,28 @@ def rasterize_triangles(image_width: int, image_height: int, tan_fovx: float, ta
             out = _lib.ForwardOut(None, _ptr(radii), None, None, None, None)
         else:
             out = _lib.ForwardOut(_ptr(out_feature), _ptr(radii), _ptr(depth), _ptr(normal), _ptr(contrib_sum), _ptr(contrib_max))
-        _lib.check(lib.ts2d_forward_render(C.byref(cam), C.byref(geom), C.byref(flags), R, _ptr(geometryBuffer), _ptr(binningBuffer), bbytes,
-                                           _ptr(imageBuffer), ibytes, C.byref(out), stream), "ts2d_forward_render")
+        R = None
+        if cap is not None:
+            # one enqueue, no synchronisation in front of the binning / composite kernels
+            bbytes = lib.ts2d_binning_state_bytes(cap, W, H)
+            binningBuffer = torch.empty((bbytes,), **u8)
+            _lib.check(lib.ts2d_forward(C.byref(cam), C.byref(geom), C.byref(flags), _ptr(radii), _ptr(geometryBuffer), gbytes,
+                                        _ptr(binningBuffer), bbytes, _ptr(imageBuffer), ibytes, C.byref(out), counters.h, stream), "ts2d_forward")
+            R = counters.num_rendered()  # waits for the scan only: the GPU is busy with the rest of the frame
+            if R > lib.ts2d_binning_capacity(bbytes):
+                cap = None  # the capacity guess was too small: the frame is invalid, render again below on the same geometry state
+        if cap is None:
+            if R is None:
+                num_rendered = C.c_int64(0)
+                _lib.check(lib.ts2d_forward_geometry(C.byref(cam), C.byref(geom), C.byref(flags), _ptr(radii), _ptr(geometryBuffer), gbytes,
+                                                     C.byref(num_rendered), stream), "ts2d_forward_geometry")
+                R = int(num_rendered.value)
+            bbytes = lib.ts2d_binning_state_bytes(R, W, H)
+            binningBuffer = torch.empty((bbytes,), **u8)
+            _lib.check(lib.ts2d_forward_render(C.byref(cam), C.byref(geom), C.byref(flags), R, _ptr(geometryBuffer), _ptr(binningBuffer), bbytes,
+                                               _ptr(imageBuffer), ibytes, C.byref(out), counters.h, stream), "ts2d_forward_render")
+        _R_SEEN[shape_key] = max(R, _R_SEEN.get(shape_key, 0))
+        R = NumRendered(R, counters)
         if fab is not None:
             fab_h.barrier(channel=0)     # every rank's pixel stores and REDs have landed
             if rich_info:                # publish this rank's home slice of contrib_sum / contrib_max to every replica
@@ -340,50 +414,38 @@ def rasterize_triangles_backward(tan_fovx: float, tan_fovy: float, viewmatrix: t
         cam, geom, flags, _keep = _structs(W, H, tan_fovx, tan_fovy, viewmatrix, projmatrix, campos, sh_degree, gamma, scale_modifier,
                                            background_depth, background, vertex, shs, feature, opacity, P, use_shs, Cn, M, False, rich_info,
                                            debug, shard, primitive, model)
-        sbytes = lib.ts2d_backward_scratch_bytes(P)
-        fab = _fabric_for(shard, gamma, dev)
-        if fab is not None:
-            scratch_f, scratch_mc, fab_h = fab.buffer("scratch", sbytes // 4)
-            scratch = scratch_f.view(torch.uint8)
+        # rows of the atomics-free gradient write-back: from the counters the forward pass left behind (no wait in practice: that
+        # forward finished long ago); a plain int (a caller that built the arguments itself) costs one blocking read
+        ctr = getattr(num_rendered, "counters", None)
+        if EXACT or not (0.6 <= float(gamma) <= 64.0):
+            rows = 0
+        elif ctr is not None:
+            rows = ctr.backward_rows()
         else:
-            scratch = torch.empty((sbytes,), device=dev, dtype=torch.uint8)
+            fcn = _lib.FrameCounters()
+            _lib.check(lib.ts2d_read_counters(_ptr(geometryBuffer), P, C.byref(fcn), stream), "ts2d_read_counters")
+            rows = int(fcn.backward_rows)
+        bbytes = binningBuffer.numel()
+        sbytes = lib.ts2d_backward_scratch_bytes(P, bbytes, rows)
+        scratch = torch.empty((sbytes,), device=dev, dtype=torch.uint8)
         loss = _lib.LossIn(_ptr(dL_dout_feature), _ptr(dL_dout_depth) if rich_info else None, _ptr(dL_dout_normal) if rich_info else None)
         out = _lib.BackwardOut(_ptr(dL_dvertex), _ptr(dL_dcenter2D), _ptr(dL_dshs), _ptr(dL_dfeature), _ptr(dL_dopacity),
                                C.cast(C.pointer(mgrads), C.c_void_p) if mgrads is not None else None)
         if shard[1] > 1:
-            # tile-sharded: composite over this rank's tiles, sum the 64 B/triangle accumulators over the ranks (NCCL on the
-            # current stream), then the per-triangle stage runs replicated on identical data -> identical gradients everywhere
+            # tile-sharded: composite over this rank's tiles -> this rank's partial per-triangle sums (the first 16 P floats of the
+            # scratch, themselves bit-reproducible), summed over the ranks, then the per-triangle stage runs replicated on
+            # identical data -> identical gradients everywhere
             from . import distributed
 
-            if fab is not None:
-                # NVLink peer memory: K8 REDs each triangle's sums into its home rank's replica of the scratch while it runs; the
-                # homes then publish their slices to every replica -- two small steps instead of a 64 B/triangle all-reduce
-                home_chunk = ((P + shard[1] - 1) // shard[1] + 31) // 32 * 32
-                scratch_f.zero_()
-                fab_h.barrier(channel=0)
-                fc = _lib.FabricC(world=shard[1], home_chunk=home_chunk)
-                for r, a in enumerate(fab_h.buffer_ptrs):
-                    fc.scratch[r] = int(a)
-                flags.fabric = C.cast(C.pointer(fc), C.c_void_p)
-            _lib.check(lib.ts2d_backward_composite(C.byref(cam), C.byref(geom), C.byref(flags), int(num_rendered), _ptr(geometryBuffer),
-                                                   _ptr(binningBuffer), _ptr(imageBuffer), C.byref(loss), _ptr(scratch), sbytes, stream),
-                       "ts2d_backward_composite")
-            if fab is not None:
-                fab_h.barrier(channel=0)
-                flags.fabric = None
-                first = shard[0] * home_chunk
-                if first < P:
-                    _lib.check(lib.ts2d_fabric_publish(_ptr(scratch_f), C.c_void_p(scratch_mc), 16 * first, 16 * min(home_chunk, P - first), stream),
-                               "ts2d_fabric_publish")
-                fab_h.barrier(channel=0)
-            else:
-                distributed.reduce_accumulators(scratch.view(torch.float32))
+            _lib.check(lib.ts2d_backward_composite(C.byref(cam), C.byref(geom), C.byref(flags), _ptr(geometryBuffer), _ptr(binningBuffer), bbytes,
+                                                   _ptr(imageBuffer), C.byref(loss), _ptr(scratch), sbytes, stream), "ts2d_backward_composite")
+            acc = scratch[:64 * P].view(torch.float32)
+            distributed.reduce_accumulators(acc)
             _lib.check(lib.ts2d_backward_geometry(C.byref(cam), C.byref(geom), C.byref(flags), _ptr(radii), _ptr(geometryBuffer),
-                                                  C.byref(out), _ptr(scratch), sbytes, stream), "ts2d_backward_geometry")
+                                                  C.byref(out), _ptr(acc), 64 * P, stream), "ts2d_backward_geometry")
         else:
-            _lib.check(lib.ts2d_backward(C.byref(cam), C.byref(geom), C.byref(flags), int(num_rendered), _ptr(radii), _ptr(geometryBuffer),
-                                         _ptr(binningBuffer), _ptr(imageBuffer), C.byref(loss), C.byref(out), _ptr(scratch), sbytes, stream),
-                       "ts2d_backward")
+            _lib.check(lib.ts2d_backward(C.byref(cam), C.byref(geom), C.byref(flags), _ptr(radii), _ptr(geometryBuffer), _ptr(binningBuffer),
+                                         bbytes, _ptr(imageBuffer), C.byref(loss), C.byref(out), _ptr(scratch), sbytes, stream), "ts2d_backward")
     if model is not None:
         return dL_dvertex, dL_dcenter2D, dL_df_dc, dL_df_rest, dL_dopacity
     return dL_dvertex, dL_dcenter2D, dL_dshs, dL_dfeature, dL_dopacity

@@ -50,8 +50,12 @@ MAX_RANKS = 8  # TS2D_MAX_RANKS
 class FabricC(C.Structure):
     """ts2d_fabric: multicast aliases of the image planes + peer tables of the reduced arrays (multi-GPU over NVLink peer memory)."""
     _fields_ = [("world", C.c_int32), ("home_chunk", C.c_int32), ("out_feature_mc", C.c_void_p), ("depth_mc", C.c_void_p),
-                ("normal_mc", C.c_void_p), ("contrib_sum", C.c_void_p * MAX_RANKS), ("contrib_max", C.c_void_p * MAX_RANKS),
-                ("scratch", C.c_void_p * MAX_RANKS)]
+                ("normal_mc", C.c_void_p), ("contrib_sum", C.c_void_p * MAX_RANKS), ("contrib_max", C.c_void_p * MAX_RANKS)]
+
+
+class FrameCounters(C.Structure):
+    """ts2d_frame_counters: device-side counters of a frame (R, rows of the atomics-free gradient write-back)."""
+    _fields_ = [("num_rendered", C.c_int64), ("backward_rows", C.c_int64)]
 
 
 class ForwardOut(C.Structure):
@@ -75,14 +79,22 @@ SYMBOLS = {
     "ts2d_geometry_state_bytes": (C.c_size_t, [C.c_int32]),
     "ts2d_binning_state_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "ts2d_image_state_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
-    "ts2d_backward_scratch_bytes": (C.c_size_t, [C.c_int32]),
+    "ts2d_binning_capacity": (C.c_int64, [C.c_size_t]),
+    "ts2d_backward_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_size_t, C.c_int64]),
+    "ts2d_counters_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "ts2d_counters_destroy": (None, [C.c_void_p]),
+    "ts2d_counters_num_rendered": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "ts2d_counters_backward_rows": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "ts2d_read_counters": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(FrameCounters), C.c_void_p]),
+    "ts2d_forward": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                               C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(ForwardOut), C.c_void_p, C.c_void_p]),
     "ts2d_forward_geometry": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_void_p, C.c_void_p, C.c_size_t,
                                         C.POINTER(C.c_int64), C.c_void_p]),
     "ts2d_forward_render": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_int64, C.c_void_p, C.c_void_p,
-                                      C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(ForwardOut), C.c_void_p]),
-    "ts2d_backward": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(ForwardOut), C.c_void_p, C.c_void_p]),
+    "ts2d_backward": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                 C.c_void_p, C.POINTER(LossIn), C.POINTER(BackwardOut), C.c_void_p, C.c_size_t, C.c_void_p]),
-    "ts2d_backward_composite": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_int64, C.c_void_p, C.c_void_p,
+    "ts2d_backward_composite": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_void_p, C.c_void_p, C.c_size_t,
                                           C.c_void_p, C.POINTER(LossIn), C.c_void_p, C.c_size_t, C.c_void_p]),
     "ts2d_backward_geometry": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_void_p, C.c_void_p,
                                          C.POINTER(BackwardOut), C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -97,14 +109,14 @@ SYMBOLS = {
                                            C.c_size_t, C.c_void_p, C.c_void_p]),
     "ts2d_downsample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "ts2d_downsample_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
-    "ts2d_export_binning": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+    "ts2d_export_binning": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "ts2d_export_image": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ts2d_profile_enable": (C.c_int, [C.c_int]),
     "ts2d_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
 
-ABI_VERSION = 4  # TS2D_ABI_VERSION (include/ts2d.h)
+ABI_VERSION = 5  # TS2D_ABI_VERSION (include/ts2d.h)
 PRIMITIVES = {"2D": 0, "3D": 1}  # TS2D_PRIMITIVE_* (include/ts2d.h)
 STAGES = ("preprocess", "order_scan", "binning", "render_fwd", "render_bwd", "preprocess_bwd")
 

@@ -39,6 +39,17 @@ struct StageTimer {
     }
 };
 
+}  // namespace
+
+// Host side of a frame's device counters: pinned memory the asynchronous copies land in, and the two events that say when.
+struct ts2d_counters {
+    ts2d_frame_counters *host = nullptr;  // cudaHostAlloc
+    cudaEvent_t ev_r = nullptr;           // num_rendered has landed (recorded right behind the scan: the rest of the frame is still queued)
+    cudaEvent_t ev_all = nullptr;         // backward_rows has landed (end of the forward pass)
+};
+
+namespace {
+
 struct Carver {
     char *p;
     size_t used;
@@ -58,36 +69,59 @@ size_t carve_geometry(void *blob, int32_t P, GeomState *gs)
     const size_t n = P > 0 ? (size_t)P : 1;
     Carver c(blob);
     GeomState g;
+    // header + look-back words first: one memset at the start of a frame clears them all (zero_bytes below)
     g.hdr = c.take<GeomHeader>(1);
+    g.sstatus_bytes = ts2d_scan_status_bytes((int64_t)n);
+    g.sstatus = (unsigned long long *)c.take<char>(g.sstatus_bytes);
+    g.status_bytes = ts2d_sort_status_bytes((int64_t)n);
+    g.status = (unsigned long long *)c.take<char>(g.status_bytes);
     g.rec0 = c.take<float4>(3 * n);
     g.rec1 = c.take<float4>(2 * n);
     g.dkey = c.take<uint32_t>(n);
     g.dkey2 = c.take<uint32_t>(n);
+    g.tmpk = c.take<uint32_t>(n);
     g.ids = c.take<uint32_t>(n);
     g.ids2 = c.take<uint32_t>(n);
     g.tiles = c.take<uint32_t>(n);
     g.rect = c.take<ushort4>(n);
     g.offs = c.take<uint32_t>(n);
+    g.estart = c.take<uint32_t>(n);
     g.clamp = c.take<uint8_t>(n);
-    g.cub_temp_bytes = ts2d_depth_sort_temp_bytes(P);
-    g.cub_temp = c.take<char>(g.cub_temp_bytes);
     if (gs) *gs = g;
     return ts2d_align_up(c.used, 256);
 }
+// bytes from the start of the geometry state that must be zero when a frame starts: header (counters, tickets, histograms)
+// and the look-back words of the depth sort and of the scan
+size_t geometry_zero_bytes(const GeomState &g) { return (size_t)((char *)g.status - (char *)g.hdr) + g.status_bytes; }
 
-size_t carve_binning(void *blob, int64_t R, BinState *bs)
+size_t carve_binning(void *blob, int64_t cap, BinState *bs)
 {
-    const size_t n = R > 0 ? (size_t)R : 1;
+    const size_t n = cap > 0 ? (size_t)cap : 1;
     Carver c(blob);
     BinState b;
+    b.cap = (int64_t)n;
+    b.status_bytes = ts2d_sort_status_bytes((int64_t)n);
+    b.status = (unsigned long long *)c.take<char>(b.status_bytes);
     b.tkey[0] = c.take<uint32_t>(n);
     b.tkey[1] = c.take<uint32_t>(n);
     b.tval[0] = c.take<uint32_t>(n);
     b.tval[1] = c.take<uint32_t>(n);
-    b.cub_temp_bytes = ts2d_tile_sort_temp_bytes(R);
-    b.cub_temp = c.take<char>(b.cub_temp_bytes);
     if (bs) *bs = b;
     return ts2d_align_up(c.used, 256);
+}
+// largest capacity whose binning state fits in `bytes` (the inverse of ts2d_binning_state_bytes: forward and backward both derive
+// the array layout from the size of the caller's blob, so the instance count itself never has to be known on the host)
+int64_t binning_capacity(size_t bytes)
+{
+    int64_t lo = 0, hi = (int64_t)(bytes / 16) + 1;
+    if (carve_binning(nullptr, 1, nullptr) > bytes) return 0;
+    lo = 1;
+    while (lo < hi) {
+        const int64_t mid = lo + (hi - lo + 1) / 2;
+        if (carve_binning(nullptr, mid, nullptr) <= bytes) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
 }
 
 size_t carve_image(void *blob, int32_t W, int32_t H, ImageState *is)
@@ -99,7 +133,29 @@ size_t carve_image(void *blob, int32_t W, int32_t H, ImageState *is)
     i.ranges = c.take<uint2>(gx * gy);
     i.n_contrib = c.take<uint32_t>(N);
     i.final_T = c.take<float>(N);
+    i.lastw = c.take<uint32_t>(8 * gx * gy);
     if (is) *is = i;
+    return ts2d_align_up(c.used, 256);
+}
+
+// backward scratch: accumulators, and (fast kernels) the row machinery of ts2d_bwd_reduce.cu
+size_t carve_scratch(void *blob, int32_t P, int64_t cap, int64_t rows, BwdScratch *out)
+{
+    const size_t n = P > 0 ? (size_t)P : 1;
+    Carver c(blob);
+    BwdScratch b = {};
+    b.gacc = c.take<float>(GACC_STRIDE * n);
+    b.cap = cap;
+    b.rows_cap = rows;
+    if (cap > 0) {
+        b.ei = c.take<uint32_t>((size_t)cap);
+        b.cnt = c.take<uint8_t>((size_t)cap);
+        b.sbase = c.take<uint32_t>((size_t)cap + 1);
+        b.sstatus_bytes = ts2d_scan_status_bytes(cap);
+        b.sstatus = (unsigned long long *)c.take<char>(b.sstatus_bytes);
+        b.rows = c.take<float4>(4 * (size_t)(rows > 0 ? rows : 1));
+    }
+    if (out) *out = b;
     return ts2d_align_up(c.used, 256);
 }
 
@@ -109,6 +165,7 @@ int validate(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f
     if (cam->width <= 0 || cam->height <= 0 || g->P < 0) return TS2D_E_SIZE;
     if ((int64_t)cam->width * cam->height > (int64_t)1 << 30) return TS2D_E_SIZE;
     if ((cam->width + TS2D_TILE - 1) / TS2D_TILE > 65535 || (cam->height + TS2D_TILE - 1) / TS2D_TILE > 65535) return TS2D_E_SIZE;
+    if ((int64_t)((cam->width + TS2D_TILE - 1) / TS2D_TILE) * ((cam->height + TS2D_TILE - 1) / TS2D_TILE) > ((int64_t)1 << 24)) return TS2D_E_SIZE;  // 24 tile bits in an instance key
     if (g->C < 1 || g->C > TS2D_MAX_CHANNELS) return TS2D_E_CHANNELS;
     if (g->gamma < 0.0f) return TS2D_E_GAMMA;
     if (f->shard_world < 1 || f->shard_rank < 0 || f->shard_rank >= f->shard_world) return TS2D_E_SHARD;
@@ -277,7 +334,7 @@ const char *ts2d_error_string(int code)
     case TS2D_E_SHARD: return "invalid shard_rank / shard_world";
     case TS2D_E_SIZE: return "image size or primitive count out of range";
     case TS2D_E_PRIMITIVE: return "flags.primitive must be TS2D_PRIMITIVE_2D or TS2D_PRIMITIVE_3D";
-    case TS2D_E_FABRIC: return "flags.fabric needs the fast kernels, the split backward, 2 <= world <= 8, home_chunk % 32 == 0 and every address the call writes";
+    case TS2D_E_FABRIC: return "flags.fabric needs the fast kernels, 2 <= world <= 8, home_chunk % 32 == 0 and every address the call writes";
     case TS2D_E_MODEL: return "model inputs / model gradients inconsistent (need use_shs, f_dc, f_rest for M > 1, opacity_logit, ratio > 0)";
     default: break;
     }
@@ -286,9 +343,141 @@ const char *ts2d_error_string(int code)
 }
 
 size_t ts2d_geometry_state_bytes(int32_t P) { return carve_geometry(nullptr, P, nullptr); }
-size_t ts2d_binning_state_bytes(int64_t R, int32_t, int32_t) { return carve_binning(nullptr, R, nullptr); }
+size_t ts2d_binning_state_bytes(int64_t capacity, int32_t, int32_t) { return carve_binning(nullptr, capacity, nullptr); }
+int64_t ts2d_binning_capacity(size_t binning_state_bytes) { return binning_capacity(binning_state_bytes); }
 size_t ts2d_image_state_bytes(int32_t W, int32_t H) { return carve_image(nullptr, W, H, nullptr); }
-size_t ts2d_backward_scratch_bytes(int32_t P) { return ts2d_align_up(sizeof(float) * GACC_STRIDE * (size_t)(P > 0 ? P : 1), 256); }
+size_t ts2d_backward_scratch_bytes(int32_t P, size_t binning_state_bytes, int64_t backward_rows)
+{
+    return carve_scratch(nullptr, P, binning_capacity(binning_state_bytes), backward_rows > 0 ? backward_rows : 1, nullptr);
+}
+
+}  // extern "C"
+
+namespace {
+
+// rows the scratch has room for: what is left after the fixed part
+BwdScratch scratch_view(void *scratch, size_t scratch_bytes, int32_t P, int64_t cap)
+{
+    BwdScratch sc;
+    const size_t fixed = carve_scratch(nullptr, P, cap, 1, nullptr);
+    int64_t rows = 1;
+    if (scratch_bytes > fixed) rows += (int64_t)((scratch_bytes - fixed) / 64);
+    if (scratch_bytes < fixed) rows = 0;
+    carve_scratch(scratch, P, cap, rows > 0 ? rows : 1, &sc);
+    sc.rows_cap = rows;
+    return sc;
+}
+
+int forward_geometry_impl(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int32_t *radii, GeomState gs,
+                          int64_t *num_rendered_host, cudaStream_t s)
+{
+    // one memset per frame: counters, tickets, digit histograms, look-back words of the depth sort and of the scan
+    TS2D_CUDA_TRY(cudaMemsetAsync(gs.hdr, 0, geometry_zero_bytes(gs), s));
+    if (flags->primitive == TS2D_PRIMITIVE_3D)
+        TS2D_STAGE(TS2D_STAGE_PREPROCESS, ts2d_launch_preprocess3d(cam, geom, flags, radii, gs, s));
+    else
+        TS2D_STAGE(TS2D_STAGE_PREPROCESS, ts2d_launch_preprocess(cam, geom, flags, radii, gs, s));
+    TS2D_STAGE(TS2D_STAGE_ORDER_SCAN, ts2d_launch_order_and_scan(geom->P, gs, num_rendered_host, s));
+    return 0;
+}
+
+int forward_render_impl(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int64_t num_rendered, GeomState gs, BinState bs,
+                        ImageState is, const ts2d_forward_out *out, ts2d_counters *ctr, cudaStream_t s)
+{
+    const int n_tiles = ((cam->width + TS2D_TILE - 1) / TS2D_TILE) * ((cam->height + TS2D_TILE - 1) / TS2D_TILE);
+    const int sb = ts2d_sorted_buf(n_tiles);
+    if (ctr) {  // R first: the host can size things / detect an overflow while the rest of the frame is still queued
+        TS2D_CUDA_TRY(cudaMemcpyAsync(&ctr->host->num_rendered, &gs.hdr->num_rendered, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        TS2D_CUDA_TRY(cudaEventRecord(ctr->ev_r, s));
+    }
+    // the render half of the header (row counter, tickets and histograms of the tile sort): cleared here so that a render can be
+    // repeated on the same geometry state (binning state too small the first time)
+    TS2D_CUDA_TRY(cudaMemsetAsync(&gs.hdr->render, 0, sizeof(gs.hdr->render), s));
+    TS2D_STAGE(TS2D_STAGE_BINNING, ts2d_launch_binning(cam, geom, flags, num_rendered, gs, bs, is, s));
+    if (flags->primitive == TS2D_PRIMITIVE_3D && ts2d_use_fast(geom, flags))
+        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render3d_fwd_fast(cam, geom, flags, gs, bs.tkey[sb], bs.tval[sb], is, out, s));
+    else if (flags->primitive == TS2D_PRIMITIVE_3D)
+        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render3d_fwd(cam, geom, flags, gs, bs.tval[sb], is, out, s));
+    else if (ts2d_use_fast(geom, flags))
+        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd_fast(cam, geom, flags, gs, bs.tkey[sb], bs.tval[sb], is, out, s));
+    else
+        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd(cam, geom, flags, gs, bs.tval[sb], is, out, s));
+    if (ctr) {
+        TS2D_CUDA_TRY(cudaMemcpyAsync(&ctr->host->backward_rows, &gs.hdr->render.bwd_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        TS2D_CUDA_TRY(cudaEventRecord(ctr->ev_all, s));
+    }
+    return 0;
+}
+
+// P == 0: no work is enqueued; the counters read zero
+int counters_clear(ts2d_counters *c, cudaStream_t s)
+{
+    if (!c) return 0;
+    c->host->num_rendered = c->host->backward_rows = 0;
+    TS2D_CUDA_TRY(cudaEventRecord(c->ev_r, s));
+    TS2D_CUDA_TRY(cudaEventRecord(c->ev_all, s));
+    return 0;
+}
+
+int validate_render(const ts2d_geometry *geom, const ts2d_flags *flags, const ts2d_forward_out *out)
+{
+    if (!out) return TS2D_E_NULL;
+    if (!flags->fabric) {
+        if (!out->out_feature) return TS2D_E_NULL;
+        if (flags->rich_info && (!out->depth || !out->normal || !out->contrib_sum || !out->contrib_max)) return TS2D_E_NULL;
+    }
+    if (const ts2d_fabric *m = flags->fabric) {
+        if (!ts2d_use_fast(geom, flags) || !fabric_ok(m) || !m->out_feature_mc) return TS2D_E_FABRIC;
+        if (flags->rich_info) {
+            if (!m->depth_mc || !m->normal_mc) return TS2D_E_FABRIC;
+            for (int r = 0; r < m->world; r++)
+                if (!m->contrib_sum[r] || !m->contrib_max[r]) return TS2D_E_FABRIC;
+        }
+    }
+    return 0;
+}
+
+// composite backward into sc.gacc: fast kernels -> rows -> fixed-order reduction; mirror kernels -> the reference's atomics
+int backward_composite_impl(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, GeomState gs, BinState bs, ImageState is,
+                            const ts2d_loss_in *loss, BwdScratch sc, cudaStream_t s)
+{
+    const int n_tiles = ((cam->width + TS2D_TILE - 1) / TS2D_TILE) * ((cam->height + TS2D_TILE - 1) / TS2D_TILE);
+    const int sb = ts2d_sorted_buf(n_tiles);
+    if (ts2d_use_fast(geom, flags)) {
+        if (sc.rows_cap <= 0) return TS2D_E_STATE_SIZE;
+        {
+            StageTimer t(TS2D_STAGE_RENDER_BWD, s);
+            int rc = ts2d_launch_bwd_rows_prepare(cam, flags, gs, bs, is, sc, s);
+            if (rc) return rc;
+            rc = flags->primitive == TS2D_PRIMITIVE_3D ? ts2d_launch_render3d_bwd_fast(cam, geom, flags, gs, bs.tkey[sb], bs.tval[sb], is, loss, sc, s)
+                                                       : ts2d_launch_render_bwd_fast(cam, geom, flags, gs, bs.tkey[sb], bs.tval[sb], is, loss, sc, s);
+            if (rc) return rc;
+            rc = ts2d_launch_bwd_rows_reduce(geom->P, gs, sc, s);
+            if (rc) return rc;
+        }
+        return dbg_sync(flags, s);
+    }
+    TS2D_CUDA_TRY(cudaMemsetAsync(sc.gacc, 0, sizeof(float) * GACC_STRIDE * (size_t)geom->P, s));
+    if (flags->primitive == TS2D_PRIMITIVE_3D)
+        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render3d_bwd(cam, geom, flags, gs, bs.tval[sb], is, loss, sc.gacc, s));
+    else
+        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd(cam, geom, flags, gs, bs.tval[sb], is, loss, sc.gacc, s));
+    return 0;
+}
+
+int backward_geometry_impl(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, const int32_t *radii, GeomState gs,
+                           const float *gacc, const ts2d_backward_out *out, cudaStream_t s)
+{
+    if (flags->primitive == TS2D_PRIMITIVE_3D)
+        TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess3d_bwd(cam, geom, flags, radii, gs, gacc, out, s));
+    else
+        TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess_bwd(cam, geom, flags, radii, gs, gacc, out, s));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
 
 int ts2d_forward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int32_t *radii, void *geometry_state,
                           size_t geometry_state_bytes, int64_t *num_rendered_host, void *stream)
@@ -301,57 +490,110 @@ int ts2d_forward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, con
     if (!radii || !geometry_state) return TS2D_E_NULL;
     GeomState gs;
     if (carve_geometry(geometry_state, geom->P, &gs) > geometry_state_bytes) return TS2D_E_STATE_SIZE;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (flags->primitive == TS2D_PRIMITIVE_3D)
-        TS2D_STAGE(TS2D_STAGE_PREPROCESS, ts2d_launch_preprocess3d(cam, geom, flags, radii, gs, s));
-    else
-        TS2D_STAGE(TS2D_STAGE_PREPROCESS, ts2d_launch_preprocess(cam, geom, flags, radii, gs, s));
-    TS2D_STAGE(TS2D_STAGE_ORDER_SCAN, ts2d_launch_order_and_scan(geom->P, gs, num_rendered_host, s));
-    return 0;
+    return forward_geometry_impl(cam, geom, flags, radii, gs, num_rendered_host, (cudaStream_t)stream);
 }
 
 int ts2d_forward_render(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int64_t num_rendered,
                         const void *geometry_state, void *binning_state, size_t binning_state_bytes, void *image_state,
-                        size_t image_state_bytes, const ts2d_forward_out *out, void *stream)
+                        size_t image_state_bytes, const ts2d_forward_out *out, ts2d_counters *counters, void *stream)
 {
     int rc = validate(cam, geom, flags);
     if (rc) return rc;
-    if (geom->P == 0) return 0;
-    if (!geometry_state || !binning_state || !image_state || !out) return TS2D_E_NULL;
-    if (!flags->fabric) {
-        if (!out->out_feature) return TS2D_E_NULL;
-        if (flags->rich_info && (!out->depth || !out->normal || !out->contrib_sum || !out->contrib_max)) return TS2D_E_NULL;
-    }
-    if (num_rendered < 0 || num_rendered >= ((int64_t)1 << 31)) return TS2D_E_SIZE;
-    if (const ts2d_fabric *m = flags->fabric) {
-        if (!ts2d_use_fast(geom, flags) || !fabric_ok(m) || !m->out_feature_mc) return TS2D_E_FABRIC;
-        if (flags->rich_info) {
-            if (!m->depth_mc || !m->normal_mc) return TS2D_E_FABRIC;
-            for (int r = 0; r < m->world; r++)
-                if (!m->contrib_sum[r] || !m->contrib_max[r]) return TS2D_E_FABRIC;
-        }
-    }
+    if (geom->P == 0) return counters_clear(counters, (cudaStream_t)stream);
+    if (!geometry_state || !binning_state || !image_state) return TS2D_E_NULL;
+    if ((rc = validate_render(geom, flags, out)) != 0) return rc;
+    if (num_rendered >= ((int64_t)1 << 31)) return TS2D_E_SIZE;
     GeomState gs;
     BinState bs;
     ImageState is;
     carve_geometry(const_cast<void *>(geometry_state), geom->P, &gs);
-    if (carve_binning(binning_state, num_rendered, &bs) > binning_state_bytes) return TS2D_E_STATE_SIZE;
+    const int64_t cap = binning_capacity(binning_state_bytes);
+    if (cap < 1 || (num_rendered > 0 && cap < num_rendered)) return TS2D_E_STATE_SIZE;
+    carve_binning(binning_state, cap, &bs);
+    if (carve_image(image_state, cam->width, cam->height, &is) > image_state_bytes) return TS2D_E_STATE_SIZE;
+    return forward_render_impl(cam, geom, flags, num_rendered, gs, bs, is, out, counters, (cudaStream_t)stream);
+}
+
+int ts2d_forward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int32_t *radii, void *geometry_state,
+                 size_t geometry_state_bytes, void *binning_state, size_t binning_state_bytes, void *image_state, size_t image_state_bytes,
+                 const ts2d_forward_out *out, ts2d_counters *counters, void *stream)
+{
+    int rc = validate(cam, geom, flags);
+    if (rc) return rc;
+    if (geom->P == 0) return counters_clear(counters, (cudaStream_t)stream);
+    if (!radii || !geometry_state || !binning_state || !image_state) return TS2D_E_NULL;
+    if ((rc = validate_render(geom, flags, out)) != 0) return rc;
+    GeomState gs;
+    BinState bs;
+    ImageState is;
+    if (carve_geometry(geometry_state, geom->P, &gs) > geometry_state_bytes) return TS2D_E_STATE_SIZE;
+    const int64_t cap = binning_capacity(binning_state_bytes);
+    if (cap < 1) return TS2D_E_STATE_SIZE;
+    carve_binning(binning_state, cap, &bs);
     if (carve_image(image_state, cam->width, cam->height, &is) > image_state_bytes) return TS2D_E_STATE_SIZE;
     cudaStream_t s = (cudaStream_t)stream;
-    TS2D_STAGE(TS2D_STAGE_BINNING, ts2d_launch_binning(cam, geom, flags, num_rendered, gs, bs, is, s));
-    if (flags->primitive == TS2D_PRIMITIVE_3D && ts2d_use_fast(geom, flags))
-        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render3d_fwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, out, s));
-    else if (flags->primitive == TS2D_PRIMITIVE_3D)
-        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render3d_fwd(cam, geom, flags, gs, bs.tval[1], is, out, s));
-    else if (ts2d_use_fast(geom, flags))
-        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, out, s));
-    else
-        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd(cam, geom, flags, gs, bs.tval[1], is, out, s));
+    if ((rc = forward_geometry_impl(cam, geom, flags, radii, gs, nullptr, s)) != 0) return rc;
+    return forward_render_impl(cam, geom, flags, -1, gs, bs, is, out, counters, s);
+}
+
+int ts2d_counters_create(ts2d_counters **out)
+{
+    if (!out) return TS2D_E_NULL;
+    ts2d_counters *c = new ts2d_counters();
+    cudaError_t e = cudaHostAlloc((void **)&c->host, sizeof(ts2d_frame_counters), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_r, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_all, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        ts2d_counters_destroy(c);
+        return (int)e;
+    }
+    c->host->num_rendered = c->host->backward_rows = 0;
+    *out = c;
     return 0;
 }
 
-int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int64_t num_rendered, const int32_t *radii,
-                  const void *geometry_state, const void *binning_state, const void *image_state, const ts2d_loss_in *loss,
+void ts2d_counters_destroy(ts2d_counters *c)
+{
+    if (!c) return;
+    if (c->ev_r) cudaEventDestroy(c->ev_r);
+    if (c->ev_all) cudaEventDestroy(c->ev_all);
+    if (c->host) cudaFreeHost(c->host);
+    delete c;
+}
+
+int ts2d_counters_num_rendered(ts2d_counters *c, int64_t *num_rendered)
+{
+    if (!c || !num_rendered) return TS2D_E_NULL;
+    TS2D_CUDA_TRY(cudaEventSynchronize(c->ev_r));
+    *num_rendered = c->host->num_rendered;
+    return 0;
+}
+
+int ts2d_counters_backward_rows(ts2d_counters *c, int64_t *backward_rows)
+{
+    if (!c || !backward_rows) return TS2D_E_NULL;
+    TS2D_CUDA_TRY(cudaEventSynchronize(c->ev_all));
+    *backward_rows = c->host->backward_rows;
+    return 0;
+}
+
+int ts2d_read_counters(const void *geometry_state, int32_t P, ts2d_frame_counters *out_host, void *stream)
+{
+    if (!out_host) return TS2D_E_NULL;
+    out_host->num_rendered = out_host->backward_rows = 0;
+    if (P <= 0) return 0;
+    if (!geometry_state) return TS2D_E_NULL;
+    GeomState gs;
+    carve_geometry(const_cast<void *>(geometry_state), P, &gs);
+    cudaStream_t s = (cudaStream_t)stream;
+    TS2D_CUDA_TRY(cudaMemcpyAsync(&out_host->num_rendered, &gs.hdr->num_rendered, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    TS2D_CUDA_TRY(cudaMemcpyAsync(&out_host->backward_rows, &gs.hdr->render.bwd_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    TS2D_CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, const int32_t *radii,
+                  const void *geometry_state, void *binning_state, size_t binning_state_bytes, const void *image_state, const ts2d_loss_in *loss,
                   const ts2d_backward_out *out, void *scratch, size_t scratch_bytes, void *stream)
 {
     int rc = validate(cam, geom, flags);
@@ -359,66 +601,46 @@ int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_
     if (geom->P == 0) return 0;
     if (!radii || !geometry_state || !binning_state || !image_state || !loss || !out || !scratch) return TS2D_E_NULL;
     if (!loss->dL_dout_feature) return TS2D_E_NULL;
-    if (flags->fabric && flags->fabric->scratch[0]) return TS2D_E_FABRIC;  // no place for the rendezvous between K8 and K9
     if ((rc = validate_backward_out(geom, out)) != 0) return rc;
     if (flags->rich_info && (!loss->dL_dout_depth || !loss->dL_dout_normal)) return TS2D_E_NULL;
-    if (scratch_bytes < ts2d_backward_scratch_bytes(geom->P)) return TS2D_E_STATE_SIZE;
     GeomState gs;
     BinState bs;
     ImageState is;
     carve_geometry(const_cast<void *>(geometry_state), geom->P, &gs);
-    carve_binning(const_cast<void *>(binning_state), num_rendered, &bs);
+    const int64_t cap = binning_capacity(binning_state_bytes);
+    if (cap < 1) return TS2D_E_STATE_SIZE;
+    carve_binning(binning_state, cap, &bs);
     carve_image(const_cast<void *>(image_state), cam->width, cam->height, &is);
+    if (scratch_bytes < carve_scratch(nullptr, geom->P, cap, 1, nullptr)) return TS2D_E_STATE_SIZE;
+    const BwdScratch sc = scratch_view(scratch, scratch_bytes, geom->P, cap);
     cudaStream_t s = (cudaStream_t)stream;
-    if (flags->primitive == TS2D_PRIMITIVE_3D && ts2d_use_fast(geom, flags))
-        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render3d_bwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, loss, (float *)scratch, s));
-    else if (flags->primitive == TS2D_PRIMITIVE_3D)
-        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render3d_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
-    else if (ts2d_use_fast(geom, flags))
-        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, loss, (float *)scratch, s));
-    else
-        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
-    if (flags->primitive == TS2D_PRIMITIVE_3D)
-        TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess3d_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
-    else
-        TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
-    return 0;
+    if ((rc = backward_composite_impl(cam, geom, flags, gs, bs, is, loss, sc, s)) != 0) return rc;
+    return backward_geometry_impl(cam, geom, flags, radii, gs, sc.gacc, out, s);
 }
 
-// The two halves of ts2d_backward, for tile-sharded multi-GPU: the per-triangle accumulators in `scratch` (16 floats per
-// triangle) are what the ranks all-reduce between the two calls -- 64 B/triangle instead of the 240+ B/triangle of the
+// The two halves of ts2d_backward, for tile-sharded multi-GPU: the per-triangle accumulators at the START of `scratch` (16 floats
+// per triangle, P triangles) are what the ranks sum between the two calls -- 64 B/triangle instead of the 240+ B/triangle of the
 // final gradients, and K9 then runs replicated on identical data.
-int ts2d_backward_composite(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int64_t num_rendered,
-                            const void *geometry_state, const void *binning_state, const void *image_state, const ts2d_loss_in *loss,
-                            void *scratch, size_t scratch_bytes, void *stream)
+int ts2d_backward_composite(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, const void *geometry_state,
+                            void *binning_state, size_t binning_state_bytes, const void *image_state, const ts2d_loss_in *loss, void *scratch,
+                            size_t scratch_bytes, void *stream)
 {
     int rc = validate(cam, geom, flags);
     if (rc) return rc;
     if (geom->P == 0) return 0;
     if (!geometry_state || !binning_state || !image_state || !loss || !scratch || !loss->dL_dout_feature) return TS2D_E_NULL;
     if (flags->rich_info && (!loss->dL_dout_depth || !loss->dL_dout_normal)) return TS2D_E_NULL;
-    if (scratch_bytes < ts2d_backward_scratch_bytes(geom->P)) return TS2D_E_STATE_SIZE;
-    if (flags->fabric && flags->fabric->scratch[0]) {
-        if (!ts2d_use_fast(geom, flags) || !fabric_ok(flags->fabric)) return TS2D_E_FABRIC;
-        for (int r = 0; r < flags->fabric->world; r++)
-            if (!flags->fabric->scratch[r]) return TS2D_E_FABRIC;
-    }
     GeomState gs;
     BinState bs;
     ImageState is;
     carve_geometry(const_cast<void *>(geometry_state), geom->P, &gs);
-    carve_binning(const_cast<void *>(binning_state), num_rendered, &bs);
+    const int64_t cap = binning_capacity(binning_state_bytes);
+    if (cap < 1) return TS2D_E_STATE_SIZE;
+    carve_binning(binning_state, cap, &bs);
     carve_image(const_cast<void *>(image_state), cam->width, cam->height, &is);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (flags->primitive == TS2D_PRIMITIVE_3D && ts2d_use_fast(geom, flags))
-        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render3d_bwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, loss, (float *)scratch, s));
-    else if (flags->primitive == TS2D_PRIMITIVE_3D)
-        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render3d_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
-    else if (ts2d_use_fast(geom, flags))
-        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd_fast(cam, geom, flags, gs, bs.tkey[1], bs.tval[1], is, loss, (float *)scratch, s));
-    else
-        TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd(cam, geom, flags, gs, bs.tval[1], is, loss, (float *)scratch, s));
-    return 0;
+    if (scratch_bytes < carve_scratch(nullptr, geom->P, cap, 1, nullptr)) return TS2D_E_STATE_SIZE;
+    const BwdScratch sc = scratch_view(scratch, scratch_bytes, geom->P, cap);
+    return backward_composite_impl(cam, geom, flags, gs, bs, is, loss, sc, (cudaStream_t)stream);
 }
 
 int ts2d_backward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, const int32_t *radii,
@@ -429,15 +651,10 @@ int ts2d_backward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, co
     if (geom->P == 0) return 0;
     if (!radii || !geometry_state || !out || !scratch) return TS2D_E_NULL;
     if ((rc = validate_backward_out(geom, out)) != 0) return rc;
-    if (scratch_bytes < ts2d_backward_scratch_bytes(geom->P)) return TS2D_E_STATE_SIZE;
+    if (scratch_bytes < sizeof(float) * GACC_STRIDE * (size_t)geom->P) return TS2D_E_STATE_SIZE;
     GeomState gs;
     carve_geometry(const_cast<void *>(geometry_state), geom->P, &gs);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (flags->primitive == TS2D_PRIMITIVE_3D)
-        TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess3d_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
-    else
-        TS2D_STAGE(TS2D_STAGE_PREPROCESS_BWD, ts2d_launch_preprocess_bwd(cam, geom, flags, radii, gs, (const float *)scratch, out, s));
-    return 0;
+    return backward_geometry_impl(cam, geom, flags, radii, gs, (const float *)scratch, out, (cudaStream_t)stream);
 }
 
 int ts2d_export_geometry(const void *geometry_state, int32_t P, float *v2d, float *area2, float *normal_view, float *v_depth, float *depth,
@@ -509,19 +726,22 @@ int ts2d_downsample_bwd(const float *dL_dout, float *dL_din, int32_t planes, int
     return (int)cudaGetLastError();
 }
 
-int ts2d_export_binning(const void *geometry_state, const void *binning_state, const void *image_state, int32_t P, int64_t R, int32_t W,
-                        int32_t H, uint64_t *keys_sorted, uint32_t *point_list, uint32_t *ranges, void *stream)
+int ts2d_export_binning(const void *geometry_state, const void *binning_state, size_t binning_state_bytes, const void *image_state, int32_t P,
+                        int64_t R, int32_t W, int32_t H, uint64_t *keys_sorted, uint32_t *point_list, uint32_t *ranges, void *stream)
 {
     if (!geometry_state || !binning_state || !image_state) return TS2D_E_NULL;
     GeomState gs;
     BinState bs;
     ImageState is;
     carve_geometry(const_cast<void *>(geometry_state), P, &gs);
-    carve_binning(const_cast<void *>(binning_state), R, &bs);
+    const int64_t cap = binning_capacity(binning_state_bytes);
+    if (cap < R) return TS2D_E_STATE_SIZE;
+    carve_binning(const_cast<void *>(binning_state), cap, &bs);
     carve_image(const_cast<void *>(image_state), W, H, &is);
     cudaStream_t s = (cudaStream_t)stream;
+    const int sb = ts2d_sorted_buf((int)(((W + TS2D_TILE - 1) / TS2D_TILE) * ((H + TS2D_TILE - 1) / TS2D_TILE)));
     if (R > 0 && (keys_sorted || point_list)) {
-        k_export_keys<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, bs.tkey[1], bs.tval[1], gs.dkey, keys_sorted, point_list);
+        k_export_keys<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, bs.tkey[sb], bs.tval[sb], gs.dkey, keys_sorted, point_list);
         TS2D_CUDA_TRY(cudaGetLastError());
     }
     if (ranges) {

@@ -13,18 +13,13 @@
 // bit-identical to the reference's point_list (ts2d_export_binning rebuilds the 64-bit keys).
 // The 8 key bits below the tile id carry each instance's sub-tile coverage mask through the sort.
 //
-// The radix passes and the scan are CUB device primitives from the CUDA toolkit (the reference uses
-// the same library for its sort/scan, rasterizer.cu:186,211); everything else is hand-written.
-#include <cub/cub.cuh>
-
+// Every kernel here is hand-written (ts2d_sort.cuh holds the radix passes and the scan) and takes the number of instances R
+// from DEVICE memory: nothing in this file needs R on the host, so a whole forward pass can be enqueued without a
+// synchronisation (the reference blocks on a cudaMemcpy of R, rasterizer.cu:190-193).
 #include "ts2d_prim3d.cuh"
+#include "ts2d_sort.cuh"
 
 namespace {
-
-struct GatherTiles {
-    const uint32_t *tiles;
-    __host__ __device__ __forceinline__ uint32_t operator()(uint32_t id) const { return tiles[id]; }
-};
 
 // Instance key = (tile id << 8) | sub-tile coverage mask.  The tile sort orders on the tile bits only and carries the mask
 // along for free; the fast composite kernels read it instead of re-deriving coverage from the raster record (once per
@@ -53,11 +48,13 @@ __device__ __forceinline__ uint32_t instance_key(uint32_t tile, int gx, uint32_t
 // 32 scan values held in the warp.  Same output as rasterizer.cu:63-74 in depth order, with coalesced stores and no
 // divergence on the rect size.  SHARDED: only the tiles this rank owns (tile % world == rank) count and are written; the
 // k-th owned tile is found row by row (each row holds every world-th tile starting at a closed-form first column).
+// `cap`: instances the output arrays hold; if the frame has more (R > cap: the caller sized the binning state too small)
+// the excess is dropped here -- the caller finds R > cap in the frame's counters and repeats the render.
 template <int MASKS, bool SHARDED>
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_emit_warp(int P, int gx, float gamma, EmitCam cam, int shard_rank, int shard_world, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
-            const ushort4 *__restrict__ rect, const uint32_t *__restrict__ offs, const float4 *__restrict__ rec0, uint32_t *__restrict__ tkey,
-            uint32_t *__restrict__ tval)
+            const ushort4 *__restrict__ rect, const uint32_t *__restrict__ offs, const float4 *__restrict__ rec0, uint32_t cap, uint32_t *__restrict__ tkey,
+            uint32_t *__restrict__ tval, uint32_t *__restrict__ estart)
 {
     const int lane = threadIdx.x & 31;
     const int r = (blockIdx.x * blockDim.x + threadIdx.x);
@@ -71,11 +68,12 @@ k_emit_warp(int P, int gx, float gamma, EmitCam cam, int shard_rank, int shard_w
         const ushort4 rc = rect[id];
         rc_lo = (uint32_t)rc.x | ((uint32_t)rc.y << 16);
         rc_hi = (uint32_t)rc.z | ((uint32_t)rc.w << 16);
+        if (n) estart[id] = end - n;
     } else {
         end = offs[P - 1];
     }
     const uint32_t start = end - n;
-    const uint32_t w_start = __shfl_sync(0xffffffffu, start, 0), w_end = __shfl_sync(0xffffffffu, end, 31);
+    const uint32_t w_start = __shfl_sync(0xffffffffu, start, 0), w_end = min(__shfl_sync(0xffffffffu, end, 31), cap);
     for (uint32_t base = w_start; base < w_end; base += 32) {
         const uint32_t i = base + lane;
         // t = number of lanes whose end <= i (ends are non-decreasing)
@@ -116,9 +114,10 @@ k_emit_warp(int P, int gx, float gamma, EmitCam cam, int shard_rank, int shard_w
     }
 }
 
-// rasterizer.cu:79-99 on 32-bit tile keys.
-__global__ void __launch_bounds__(TS2D_BLOCK) k_ranges(int64_t R, const uint32_t *__restrict__ tkey, uint2 *__restrict__ ranges)
+// rasterizer.cu:79-99 on 32-bit tile keys; R from the device.
+__global__ void __launch_bounds__(TS2D_BLOCK) k_ranges(const int64_t *__restrict__ n_dev, int64_t cap, const uint32_t *__restrict__ tkey, uint2 *__restrict__ ranges)
 {
+    const int64_t R = rs_count(n_dev, cap);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
     const uint32_t cur = tkey[i] >> TS2D_MASK_BITS;
@@ -134,80 +133,76 @@ __global__ void __launch_bounds__(TS2D_BLOCK) k_ranges(int64_t R, const uint32_t
     if (i == R - 1) ranges[cur].y = (uint32_t)R;
 }
 
-__global__ void k_set_header(GeomHeader *h, const uint32_t *offs, int P)
-{
-    h->num_rendered = (P > 0) ? (int64_t)offs[P - 1] : 0;
-}
+int hist_blocks(int64_t n) { return (int)((n + 4095) / 4096 < 592 ? ((n + 4095) / 4096 > 0 ? (n + 4095) / 4096 : 1) : 592); }
 
 }  // namespace
 
-size_t ts2d_depth_sort_temp_bytes(int32_t P)
-{
-    size_t sort_b = 0, scan_b = 0;
-    const int n = P > 0 ? P : 1;
-    uint32_t *np = nullptr;
-    cudaError_t e1 = cub::DeviceRadixSort::SortPairs(nullptr, sort_b, (const uint32_t *)np, np, (const uint32_t *)np, np, n, 0, 32);
-    cub::TransformInputIterator<uint32_t, GatherTiles, const uint32_t *> it(np, GatherTiles{np});
-    cudaError_t e2 = cub::DeviceScan::InclusiveSum(nullptr, scan_b, it, np, n);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
-        // No device (CPU-only box): CUB cannot size its temp storage.  Bound it: an alternate key+value buffer plus histograms.
-        cudaGetLastError();
-        return ts2d_align_up((size_t)n * 8 + (4u << 20), 256);
-    }
-    return ts2d_align_up(sort_b > scan_b ? sort_b : scan_b, 256);
-}
+size_t ts2d_sort_status_bytes(int64_t n_cap) { return ts2d_align_up(rs_status_bytes(n_cap), 256); }
+size_t ts2d_scan_status_bytes(int64_t n_cap) { return ts2d_align_up((size_t)sc_tiles(n_cap > 0 ? n_cap : 1) * sizeof(unsigned long long), 256); }
 
-size_t ts2d_tile_sort_temp_bytes(int64_t R)
-{
-    size_t sort_b = 0;
-    const int64_t n = R > 0 ? R : 1;
-    uint32_t *np = nullptr;
-    cudaError_t e1 = cub::DeviceRadixSort::SortPairs(nullptr, sort_b, (const uint32_t *)np, np, (const uint32_t *)np, np, n, 0, 32);
-    if (e1 != cudaSuccess) {
-        cudaGetLastError();
-        return ts2d_align_up((size_t)n * 8 + (4u << 20), 256);
-    }
-    return ts2d_align_up(sort_b, 256);
-}
-
-// K2/K3: depth order of the triangles, scan of tiles-touched in that order, R to the host.
+// K2/K3: depth order of the triangles (stable LSD radix sort of the 32-bit depth patterns, triangle id as the payload), scan of
+// tiles-touched in that order (-> offs, and R in the header).
 int ts2d_launch_order_and_scan(int32_t P, GeomState gs, int64_t *R_host, cudaStream_t s)
 {
-    size_t tb = gs.cub_temp_bytes;
-    TS2D_CUDA_TRY(cub::DeviceRadixSort::SortPairs(gs.cub_temp, tb, (const uint32_t *)gs.dkey, gs.dkey2, (const uint32_t *)gs.ids, gs.ids2, P, 0,
-                                                  32, s));
-    cub::TransformInputIterator<uint32_t, GatherTiles, const uint32_t *> it(gs.ids2, GatherTiles{gs.tiles});
-    tb = gs.cub_temp_bytes;
-    TS2D_CUDA_TRY(cub::DeviceScan::InclusiveSum(gs.cub_temp, tb, it, gs.offs, P, s));
-    k_set_header<<<1, 1, 0, s>>>(gs.hdr, gs.offs, P);
+    RadixHistArgs h = {};
+    h.keys = gs.dkey;
+    h.n_dev = nullptr;
+    h.n_cap = P;
+    h.ndigits = 4;
+    for (int d = 0; d < 4; d++) {
+        h.shift[d] = 8 * d;
+        h.mask[d] = 0xFFu;
+        h.hist[d] = gs.hdr->hist[d];
+    }
+    k_radix_hist<<<hist_blocks(P), RS_THREADS, 0, s>>>(h);
+    // dkey (kept: the export calls and the 64-bit key reconstruction read it) -> (tmpk, ids) -> (dkey2, ids2) -> (tmpk, ids) -> (dkey2, ids2)
+    const uint32_t *kin[4] = {gs.dkey, gs.tmpk, gs.dkey2, gs.tmpk}, *vin[4] = {nullptr, gs.ids, gs.ids2, gs.ids};
+    uint32_t *kout[4] = {gs.tmpk, gs.dkey2, gs.tmpk, gs.dkey2}, *vout[4] = {gs.ids, gs.ids2, gs.ids, gs.ids2};
+    for (int d = 0; d < 4; d++) {
+        RadixPassArgs a = {};
+        a.kin = kin[d];
+        a.kout = kout[d];
+        a.vin = vin[d];
+        a.vout = vout[d];
+        a.hist = gs.hdr->hist[d];
+        a.status = gs.status;
+        a.ticket = &gs.hdr->tickets[TS2D_TICKET_DEPTH0 + d];
+        a.n_dev = nullptr;
+        a.n_cap = P;
+        a.shift = 8 * d;
+        a.mask = 0xFFu;
+        a.pass_uid = (uint32_t)(d + 1);
+        k_radix_pass<<<(unsigned)rs_tiles(P), RS_THREADS, 0, s>>>(a);
+    }
+    k_scan_gather<<<(unsigned)sc_tiles(P), RS_THREADS, 0, s>>>(gs.ids2, gs.tiles, gs.offs, P, gs.sstatus, &gs.hdr->tickets[TS2D_TICKET_SCAN],
+                                                             &gs.hdr->num_rendered);
     TS2D_CUDA_TRY(cudaGetLastError());
-    int64_t R = 0;
-    TS2D_CUDA_TRY(cudaMemcpyAsync(&R, &gs.hdr->num_rendered, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    TS2D_CUDA_TRY(cudaStreamSynchronize(s));
-    *R_host = R;
+    if (R_host) {
+        int64_t R = 0;
+        TS2D_CUDA_TRY(cudaMemcpyAsync(&R, &gs.hdr->num_rendered, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        TS2D_CUDA_TRY(cudaStreamSynchronize(s));
+        *R_host = R;
+    }
     return 0;
 }
 
-static int bits_for(uint32_t n_tiles)
-{
-    int b = 1;
-    while (b < 32 && (1u << b) < n_tiles) b++;
-    return b;
-}
-
 // K4-K6.
-int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, int64_t R, GeomState gs, BinState bs, ImageState is,
+int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, int64_t R_host, GeomState gs, BinState bs, ImageState is,
                         cudaStream_t s)
 {
     const int gx = (cam->width + TS2D_TILE - 1) / TS2D_TILE, gy = (cam->height + TS2D_TILE - 1) / TS2D_TILE;
     const int n_tiles = gx * gy;
     const int P = g->P;
     TS2D_CUDA_TRY(cudaMemsetAsync(is.ranges, 0, sizeof(uint2) * (size_t)n_tiles, s));
-    if (R == 0) return 0;
+    if (R_host == 0) return 0;
+    const int64_t n_launch = R_host > 0 ? (R_host < bs.cap ? R_host : bs.cap) : bs.cap;  // what the grids are sized for
+    if (n_launch <= 0) return 0;
+    TS2D_CUDA_TRY(cudaMemsetAsync(bs.status, 0, ts2d_sort_status_bytes(n_launch), s));
     const int masks = !ts2d_use_fast(g, f) ? 0 : (f->primitive == TS2D_PRIMITIVE_3D ? 2 : 1);
     const int blocks = (P + TS2D_BLOCK - 1) / TS2D_BLOCK;
     const EmitCam ec = {cam->width, cam->height, cam->tan_fovx, cam->tan_fovy};
-#define TS2D_EMIT_ARGS P, gx, g->gamma, ec, f->shard_rank, f->shard_world, gs.ids2, gs.tiles, gs.rect, gs.offs, gs.rec0, bs.tkey[0], bs.tval[0]
+    const uint32_t cap32 = (uint32_t)(bs.cap < 0xFFFFFFFFll ? bs.cap : 0xFFFFFFFFll);
+#define TS2D_EMIT_ARGS P, gx, g->gamma, ec, f->shard_rank, f->shard_world, gs.ids2, gs.tiles, gs.rect, gs.offs, gs.rec0, cap32, bs.tkey[0], bs.tval[0], gs.estart
     if (f->shard_world > 1) {
         if (masks == 2) k_emit_warp<2, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
         else if (masks == 1) k_emit_warp<1, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
@@ -219,9 +214,37 @@ int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts
     }
 #undef TS2D_EMIT_ARGS
     TS2D_CUDA_TRY(cudaGetLastError());
-    size_t tb = bs.cub_temp_bytes;
-    TS2D_CUDA_TRY(cub::DeviceRadixSort::SortPairs(bs.cub_temp, tb, (const uint32_t *)bs.tkey[0], bs.tkey[1], (const uint32_t *)bs.tval[0],
-                                                  bs.tval[1], R, TS2D_MASK_BITS, TS2D_MASK_BITS + bits_for((uint32_t)n_tiles), s));
-    k_ranges<<<(unsigned)((R + TS2D_BLOCK - 1) / TS2D_BLOCK), TS2D_BLOCK, 0, s>>>(R, bs.tkey[1], is.ranges);
+    // stable sort on the tile bits: digits of 8 bits from bit TS2D_MASK_BITS up (the last one narrower)
+    const int tb = ts2d_tile_bits(n_tiles), np = ts2d_tile_sort_passes(n_tiles);
+    const int64_t *n_dev = &gs.hdr->num_rendered;
+    RadixHistArgs h = {};
+    h.keys = bs.tkey[0];
+    h.n_dev = n_dev;
+    h.n_cap = bs.cap;
+    h.ndigits = np;
+    for (int d = 0; d < np; d++) {
+        h.shift[d] = TS2D_MASK_BITS + 8 * d;
+        h.mask[d] = (d == np - 1) ? ((1u << (tb - 8 * d)) - 1u) : 0xFFu;
+        h.hist[d] = gs.hdr->render.hist[d];
+    }
+    k_radix_hist<<<hist_blocks(n_launch), RS_THREADS, 0, s>>>(h);
+    for (int d = 0; d < np; d++) {
+        RadixPassArgs a = {};
+        a.kin = bs.tkey[d & 1];
+        a.kout = bs.tkey[(d & 1) ^ 1];
+        a.vin = bs.tval[d & 1];
+        a.vout = bs.tval[(d & 1) ^ 1];
+        a.hist = gs.hdr->render.hist[d];
+        a.status = bs.status;
+        a.ticket = &gs.hdr->render.tickets[TS2D_TICKET_TILE0 + d];
+        a.n_dev = n_dev;
+        a.n_cap = bs.cap;
+        a.shift = h.shift[d];
+        a.mask = h.mask[d];
+        a.pass_uid = (uint32_t)(8 + d);
+        k_radix_pass<<<(unsigned)rs_tiles(n_launch), RS_THREADS, 0, s>>>(a);
+    }
+    const int sb = ts2d_sorted_buf(n_tiles);
+    k_ranges<<<(unsigned)((n_launch + TS2D_BLOCK - 1) / TS2D_BLOCK), TS2D_BLOCK, 0, s>>>(n_dev, bs.cap, bs.tkey[sb], is.ranges);
     return (int)cudaGetLastError();
 }

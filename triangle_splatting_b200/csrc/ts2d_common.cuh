@@ -6,19 +6,22 @@
 //     rec0   float4[3P]   48 B "raster record": {v1.x v1.y v2.x v2.y} {v3.x v3.y 1/area2 opacity} {r g b area2}
 //     rec1   float4[2P]   32 B rich record    : {n.x n.y n.z vd1} {vd2 vd3 0 0}        (rich_info only)
 //     dkey   u32[P]       fp32 bit pattern of view depth, 0xFFFFFFFF for culled triangles
-//     ids    u32[P]       iota (value input of the depth sort)
-//     dkey2  u32[P]       sorted depth keys;  ids2 u32[P]  triangle ids in depth-rank order
+//     dkey2  u32[P]       sorted depth keys;  ids2 u32[P]  triangle ids in depth-rank order  (tmpk / ids: ping-pong buffers of the sort)
 //     tiles  u32[P]       number of (owned) tiles in the triangle's rect
 //     rect   ushort4[P]   {min.x, min.y, max.x, max.y} in tiles
 //     offs   u32[P]       inclusive scan of tiles[] in depth-rank order
+//     estart u32[P]       first emission index of the triangle's instances (offs[rank] - tiles), by triangle id
 //     clamp  u8[P]        SH clamp mask (bit c set <=> channel c clamped at 0)
-//     hdr    GeomHeader   R (num_rendered)
-//   binning state (per instance, R entries)
-//     tkey[0]/tval[0] u32[R]  (tile id << 8 | sub-tile mask) / triangle id of each instance in emission (depth-rank) order
-//     tkey[1]/tval[1] u32[R]  the same after the stable tile sort; tval[1] is the per-tile list
+//     hdr    GeomHeader   R (num_rendered) and the other device-side counters of a frame
+//     status / sstatus    look-back words of the depth sort's passes / of the scan (ts2d_sort.cuh)
+//   binning state (per instance; sized for a CAPACITY >= R chosen by the caller: R itself may only be known on the device)
+//     tkey[0]/tval[0] u32[cap]  (tile id << 8 | sub-tile mask) / triangle id of each instance in emission (depth-rank) order
+//     tkey[1]/tval[1] u32[cap]  the same after the stable tile sort; tval[1] is the per-tile list
+//     status                    look-back words of the tile sort's passes
 //   image state
 //     ranges  uint2[tiles]  [start,end) of each tile in the sorted list
 //     n_contrib u32[H*W], final_T f32[H*W]
+//     lastw   u32[tiles*8]  per 8x4 sub-tile: max n_contrib of its pixels (where the backward starts; written by the fast K7)
 //
 // The raster record replaces the reference's nine SoA arrays (R2D/src/param_struct.h:44-57) so the
 // composite kernels stage one contiguous 48 B (+32 B) record per list entry instead of 9 indirect loads.
@@ -35,10 +38,18 @@
 #define TS2D_MASK_BITS 8  // low bits of an instance key: coverage of the tile's eight 8x4 sub-tiles (ts2d_fast.cuh)
 
 struct GeomHeader {
-    int64_t num_rendered;
+    int64_t num_rendered;  // R: written by the scan (ts2d_sort.cuh: k_scan_gather); may exceed the binning capacity (then the frame is invalid)
     uint32_t bg_bits;  // model inputs: fp32 bit pattern of max ||campos - v|| (norms are >= 0, so unsigned order == float order)
     uint32_t pad;
+    uint32_t tickets[8];      // block tickets of the depth sort's passes and of the scan
+    uint32_t hist[4][256];    // digit histograms of the depth sort's passes
+    struct Render {           // what a render (binning + composite) on this geometry state uses: cleared at its start, so it can be repeated
+        int64_t bwd_rows;     // number of (sub-tile, list entry) rows the fast composite backward will produce (counted by the fast K7)
+        uint32_t tickets[8];  // tile sort passes 0..2, backward row scan
+        uint32_t hist[3][256];  // digit histograms of the tile sort's passes
+    } render;
 };
+enum { TS2D_TICKET_DEPTH0 = 0, TS2D_TICKET_SCAN = 4, TS2D_TICKET_TILE0 = 0, TS2D_TICKET_BWD_SCAN = 4 };  // depth/scan index GeomHeader::tickets, tile/backward index Render::tickets
 
 // Device-side view of ts2d_model_inputs (include/ts2d.h); `on == 0` is the reference-shaped call.
 struct ModelIn {
@@ -58,27 +69,47 @@ struct ModelOut {
 struct GeomState {
     float4 *rec0;
     float4 *rec1;
-    uint32_t *dkey, *dkey2, *ids, *ids2;
+    uint32_t *dkey, *dkey2, *ids, *ids2, *tmpk;
     uint32_t *tiles;
     ushort4 *rect;
     uint32_t *offs;
+    uint32_t *estart;
     uint8_t *clamp;
     GeomHeader *hdr;
-    char *cub_temp;
-    size_t cub_temp_bytes;
+    unsigned long long *status;   // [rs_tiles(P)][256]
+    unsigned long long *sstatus;  // [sc_tiles(P)]
+    size_t status_bytes, sstatus_bytes;
 };
 
 struct BinState {
+    int64_t cap;  // instances the arrays hold
     uint32_t *tkey[2];
     uint32_t *tval[2];
-    char *cub_temp;
-    size_t cub_temp_bytes;
+    unsigned long long *status;  // [rs_tiles(cap)][256]
+    size_t status_bytes;
 };
 
 struct ImageState {
     uint2 *ranges;
     uint32_t *n_contrib;
     float *final_T;
+    uint32_t *lastw;
+};
+
+// Scratch of the backward pass (ts2d_backward_scratch_bytes): the per-triangle accumulators K9 reads, and -- fast kernels only --
+// the atomics-free write-back of the composite backward: every (sub-tile, list entry) pair the forward blended owns one 64 B
+// row; rows are laid out in EMISSION order (all rows of a triangle are consecutive), so the per-triangle sums are plain
+// sequential reductions in a fixed order (ts2d_bwd_reduce.cu).
+struct BwdScratch {
+    int64_t cap;          // instance capacity (== BinState.cap of the frame)
+    float *gacc;          // [16 P]
+    uint32_t *ei;         // [cap]   emission index of sorted list position
+    uint8_t *cnt;         // [cap]   rows of emission index e (popcount of its live sub-tile bits)
+    uint32_t *sbase;      // [cap + 1] exclusive scan of cnt
+    unsigned long long *sstatus;  // scan look-back words
+    size_t sstatus_bytes;
+    float4 *rows;         // [rows_cap][4]
+    int64_t rows_cap;
 };
 
 // ---- small vector helpers (own naming; semantics are plain component-wise fp32) ----
@@ -230,6 +261,16 @@ static inline ModelOut ts2d_model_out(const ts2d_backward_out *o)
     }
     return m;
 }
+// tile sort: the tile id sits above the 8 mask bits of an instance key and is sorted in 8-bit digits
+static inline int ts2d_tile_bits(int n_tiles)
+{
+    int b = 1;
+    while (b < 24 && (1 << b) < n_tiles) b++;
+    return b;
+}
+static inline int ts2d_tile_sort_passes(int n_tiles) { return (ts2d_tile_bits(n_tiles) + 7) / 8; }
+// which of the two (tkey, tval) buffers of the binning state holds the sorted list (the passes ping-pong, starting from buffer 0)
+static inline int ts2d_sorted_buf(int n_tiles) { return ts2d_tile_sort_passes(n_tiles) & 1; }
 // warps per CTA of the fast composite kernels (tuning knob for experiments: TS2D_CTA_WARPS = 1 | 2 | 4 | 8)
 static inline int ts2d_cta_warps()
 {
@@ -247,21 +288,28 @@ static inline const float *ts2d_bg_ptr(const ts2d_geometry *g, const GeomState &
     return (g->model && g->model->bg_depth_from_vertices) ? reinterpret_cast<const float *>(&gs.hdr->bg_bits) : nullptr;
 }
 
-size_t ts2d_depth_sort_temp_bytes(int32_t P);
-size_t ts2d_tile_sort_temp_bytes(int64_t R);
 
 // stage launchers (each returns 0 / cudaError_t)
 int ts2d_launch_preprocess(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, int32_t *radii, GeomState gs, cudaStream_t s);
+// K2/K3: depth order + scan.  R_host != NULL: R is copied to the host and the stream is synchronised (two-call forward);
+// NULL: nothing leaves the device (one-enqueue forward).
 int ts2d_launch_order_and_scan(int32_t P, GeomState gs, int64_t *R_host, cudaStream_t s);
-int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, int64_t R, GeomState gs, BinState bs, ImageState is,
+// K4-K6.  R_host >= 0: the instance count is known on the host (grids are sized for it); < 0: it only exists in gs.hdr
+int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, int64_t R_host, GeomState gs, BinState bs, ImageState is,
                         cudaStream_t s);
+size_t ts2d_sort_status_bytes(int64_t n_cap);
+size_t ts2d_scan_status_bytes(int64_t n_cap);
+// atomics-free gradient write-back (ts2d_bwd_reduce.cu)
+int ts2d_launch_bwd_rows_prepare(const ts2d_camera *cam, const ts2d_flags *f, GeomState gs, BinState bs, ImageState is, BwdScratch sc, cudaStream_t s);
+int ts2d_launch_bwd_rows_reduce(int32_t P, GeomState gs, BwdScratch sc, cudaStream_t s);
 int ts2d_launch_render_fwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,
                            ImageState is, const ts2d_forward_out *out, cudaStream_t s);
 // fast kernels: `keys` = sorted instance keys (tile << 8 | sub-tile mask), `list` = triangle ids, both in tile-list order
 int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
                                 const uint32_t *list, ImageState is, const ts2d_forward_out *out, cudaStream_t s);
+// (the fast backward kernels write per-(sub-tile, entry) rows into `sc`; ts2d_launch_bwd_rows_reduce() turns them into sc.gacc)
 int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
-                                const uint32_t *list, ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s);
+                                const uint32_t *list, ImageState is, const ts2d_loss_in *loss, BwdScratch sc, cudaStream_t s);
 // The fast kernels cover the gamma range the trainer schedules (1..50, VanillaTS_model.py:549-554) with margin;
 // outside it (for gamma < 0.6 the ecc <= 10 cut starts to matter; gamma -> 0 makes ecc^(2 gamma) degenerate) the exact mirror kernels are used.
 static inline bool ts2d_use_fast(const ts2d_geometry *g, const ts2d_flags *f) { return !f->exact && g->gamma >= 0.6f && g->gamma <= 64.0f; }
@@ -277,7 +325,7 @@ int ts2d_launch_preprocess3d_bwd(const ts2d_camera *cam, const ts2d_geometry *g,
 int ts2d_launch_render3d_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
                                   const uint32_t *list, ImageState is, const ts2d_forward_out *out, cudaStream_t s);
 int ts2d_launch_render3d_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
-                                  const uint32_t *list, ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s);
+                                  const uint32_t *list, ImageState is, const ts2d_loss_in *loss, BwdScratch sc, cudaStream_t s);
 int ts2d_launch_export_geometry3d(int P, GeomState gs, float *v_view, float *normal_view, float *depth, float *rgb, uint8_t *clamped,
                                   uint32_t *tiles_touched, uint32_t *rect_min, uint32_t *rect_max, cudaStream_t s);
 int ts2d_launch_render_bwd(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *list,

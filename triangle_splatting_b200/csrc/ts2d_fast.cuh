@@ -18,6 +18,8 @@
 // and a warp only gathers list entries whose bit is set.  Margins cover the rounding of both the affine form
 // and the reference's form, so culled pairs are exactly pairs the reference would have skipped.
 #pragma once
+#include <string.h>
+
 #include "ts2d_common.cuh"
 
 #define TS2D_LOG2E 1.4426950408889634f
@@ -87,17 +89,17 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st
 // multicast aliases and one multimem.st lands in every rank's replica.  Reductions: PeerSet holds every rank's mapping of a
 // symmetric array; triangle id is reduced on its home rank only (one copy => the same bits for every reader).
 struct PeerTab {
-    float *a[TS2D_MAX_RANKS];  // contrib_sum replicas (forward) / scratch replicas (backward), index = rank
-    float *b[TS2D_MAX_RANKS];  // contrib_max replicas (forward)
+    float *a[TS2D_MAX_RANKS];  // contrib_sum replicas, index = rank
+    float *b[TS2D_MAX_RANKS];  // contrib_max replicas
     int world;                 // <= 1: single copy, the kernels' plain pointer parameters are the arrays
     uint32_t chunk;            // triangles per home slice
 };
-// One table per translation unit, written stream-ordered in front of a fabric launch and cleared in front of the next plain launch.
-// (A kernel-parameter table would be copied to local memory by every thread for the dynamic index, and anything handed to the
-// out-of-line flush functions costs registers across the walk loop: the constant bank costs neither.)  The host side of a
-// translation unit is single-stream as far as fabric launches are concerned (the protocol around them is stream-ordered anyway).
+// One table per translation unit and per device, written stream-ordered in front of a launch whenever it differs from what that
+// device's copy of the symbol holds (fabric launch, or the first plain launch after one).  (A kernel-parameter table would be copied
+// to local memory by every thread for the dynamic index, and anything handed to the out-of-line flush functions costs registers
+// across the walk loop: the constant bank costs neither.)  Contract: launches that use different tables on ONE device must be
+// issued on one stream -- the symbol copy is ordered against kernels of that stream only.
 static __constant__ PeerTab c_peers;
-static bool g_peers_set = false;
 __device__ __forceinline__ float *home_select(float *const (&tab)[TS2D_MAX_RANKS], uint32_t id, float *local)
 {
     if (c_peers.world <= 1) return local;
@@ -107,20 +109,27 @@ __device__ __forceinline__ float *home_select(float *const (&tab)[TS2D_MAX_RANKS
     for (int k = 1; k < TS2D_MAX_RANKS; k++) p = (r == (uint32_t)k) ? tab[k] : p;
     return p;
 }
-static inline cudaError_t ts2d_set_peers(const ts2d_fabric *fb, bool forward, cudaStream_t s)
+static inline cudaError_t ts2d_set_peers(const ts2d_fabric *fb, bool /*forward*/, cudaStream_t s)
 {
-    if (!fb && !g_peers_set) return cudaSuccess;  // the table is zero-initialised: world == 0
+    constexpr int MAXDEV = 64;
+    static PeerTab g_uploaded[MAXDEV];  // zero-initialised == the zero-initialised symbol (world 0: single copy)
     PeerTab t = {};
     if (fb) {
         for (int r = 0; r < fb->world && r < TS2D_MAX_RANKS; r++) {
-            t.a[r] = forward ? fb->contrib_sum[r] : fb->scratch[r];
-            t.b[r] = forward ? fb->contrib_max[r] : nullptr;
+            t.a[r] = fb->contrib_sum[r];
+            t.b[r] = fb->contrib_max[r];
         }
         t.world = fb->world;
         t.chunk = (uint32_t)fb->home_chunk;
     }
-    g_peers_set = fb != nullptr;
-    return cudaMemcpyToSymbolAsync(c_peers, &t, sizeof(t), 0, cudaMemcpyHostToDevice, s);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const bool tracked = dev >= 0 && dev < MAXDEV;
+    if (tracked && memcmp(&g_uploaded[dev], &t, sizeof(t)) == 0) return cudaSuccess;
+    e = cudaMemcpyToSymbolAsync(c_peers, &t, sizeof(t), 0, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && tracked) g_uploaded[dev] = t;
+    return e;
 }
 __device__ __forceinline__ void st_out(float *p, float v, int mc)
 {

@@ -133,7 +133,6 @@ k_preprocess3d(int W, int H, int P, int D, int M, int C, bool use_shs, int gx, i
     tiles[idx] = out_tiles;
     rect[idx] = out_rect;
     dkey[idx] = out_key;
-    ids[idx] = (uint32_t)idx;
 }
 
 // ------------------------------------------------------------------------------------------------ K7 (3D)

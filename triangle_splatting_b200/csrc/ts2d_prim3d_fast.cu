@@ -66,13 +66,22 @@ __device__ __forceinline__ int gather_round(uint32_t sb, uint32_t &pend, uint32_
 }
 
 // Stage: lane i fetches the record of collected entry i (`base`: list index of tile-relative position 0).
+// BWD: the gather left (position | live sub-tile bits << 24) in the position word; the row this (sub-tile, entry) pair owns
+// (ts2d_bwd_reduce.cu) goes to slot_base + 4 * lane.
 template <bool BWD>
 __device__ __forceinline__ void stage_entry(uint32_t sb, int lane, int count, const uint32_t *__restrict__ list, uint32_t base,
-                                            const float4 *__restrict__ rec0, const float4 *__restrict__ rec1)
+                                            const float4 *__restrict__ rec0, const float4 *__restrict__ rec1, int warp = 0,
+                                            const uint32_t *__restrict__ ei_of = nullptr, const uint32_t *__restrict__ sbase = nullptr,
+                                            uint32_t slot_base = 0)
 {
     if (lane < count) {
         const uint32_t ea = sb + lane * F3_EB;
-        const uint32_t pos = lds32(ea + 76);
+        uint32_t pos = lds32(ea + 76);
+        if (BWD) {
+            const uint32_t bits = pos >> 24;
+            pos &= 0xFFFFFFu;
+            sts32(slot_base + 4 * lane, __ldg(sbase + __ldg(ei_of + base + pos)) + __popc(bits & ((1u << warp) - 1u)));
+        }
         const uint32_t id = list[base + pos];
         const float4 *r = rec0 + 3 * (size_t)id;
         const float4 *q = rec1 + 2 * (size_t)id;
@@ -118,7 +127,8 @@ k_render3d_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world
                     const uint2 *__restrict__ ranges, const uint32_t *keys, const uint32_t *__restrict__ list,
                     const float4 *__restrict__ rec0, const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr, const float *__restrict__ background,
                     float *__restrict__ final_T, uint32_t *__restrict__ n_contrib, float *__restrict__ out_feature, float *__restrict__ out_depth,
-                    float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max, int mc)
+                    float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max, int mc,
+                    uint32_t *__restrict__ lastw, unsigned long long *__restrict__ bwd_rows)
 {
     if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     using L = Fwd3Layout<RICH>;
@@ -142,6 +152,7 @@ k_render3d_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accd = 0.f, accn0 = 0.f, accn1 = 0.f, accn2 = 0.f;
     uint32_t last = range.y - range.x;  // n_contrib if the pixel never saturates
     bool done = !inside;
+    uint32_t rows = 0;  // (sub-tile, entry) pairs the backward pass will visit: one 64 B row each (ts2d_bwd_reduce.cu)
 
     auto flush_panel = [&](int visited) {
         __syncwarp();
@@ -246,7 +257,15 @@ k_render3d_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world
             }
         }
         if constexpr (RICH) flush_panel(visited);
+        rows += (uint32_t)visited;  // no coverage-bit clearing in 3D (see flush_panel): every visited entry gets a row in the backward pass
         __syncwarp();  // the next gather overwrites positions / entries / panel rows
+    }
+    {   // where the backward walk of this sub-tile starts, and how many rows it will write
+        const uint32_t wl = __reduce_max_sync(0xffffffffu, inside ? last : 0u);
+        if (lane == 0) {
+            lastw[8 * (size_t)tile + warp] = wl;
+            if (rows) atomicAdd(bwd_rows, (unsigned long long)rows);
+        }
     }
 
     if (inside) {
@@ -278,10 +297,11 @@ constexpr int B3_WROW = B3_NS * 32 + 1;
 //   F     per pixel {gp0 gp1 gp2 gd} {gn0 gn1 gn2 -}; pixel p at p * 32 + (p >> 3) * 16 (the four quarters of phase 2 read
 //         four different rows with one LDS.128: the 16 B skew per quarter puts them on disjoint banks)
 //   W     panel [B3_ROWS][B3_WROW]: [scalar * 32 + pixel]
-//   INFO  per panel row {v1 v2.x}{v2.yz v3.xy}{v3.z n}{K 1/nn id -}   (64 B used, 80 B stride: conflict-free LDS.128 across rows)
+//   INFO  per panel row {v1 v2.x}{v2.yz v3.xy}{v3.z n}{K 1/nn id row}   (64 B used, 80 B stride: conflict-free LDS.128 across rows)
 constexpr int B3_INFO = 80;
 struct Bwd3Layout {
-    static constexpr int F = B3_CAP * F3_EB;
+    static constexpr int SLOT = B3_CAP * F3_EB;      // u32[B3_CAP]: row index of (this sub-tile, staged entry j)
+    static constexpr int F = B3_CAP * F3_EB + B3_CAP * 4;
     static constexpr int W = F + 32 * 32 + 64;
     static constexpr int INFO = W + ((B3_ROWS * B3_WROW * 4 + 15) / 16) * 16;
     static constexpr int BYTES = INFO + B3_ROWS * B3_INFO;
@@ -292,7 +312,7 @@ __device__ __forceinline__ uint32_t f_row(int p) { return (uint32_t)(p * 32 + (p
 // combined with two xor-shuffles, every lane maps the moments to the 16 accumulator components and issues one 16 B RED.
 // Accumulator line (GACC_STRIDE floats): [0..2] dL/dv1_view [3..5] dL/dv2_view [6..8] dL/dv3_view [9..11] dL/dn [12..14] dL/drgb [15] dL/dop
 template <bool GEO>
-static __device__ __noinline__ void bwd3_flush_panel(uint32_t wb, uint32_t ib, uint32_t fb, float *__restrict__ gacc, int filled, int lane)
+static __device__ __noinline__ void bwd3_flush_panel(uint32_t wb, uint32_t ib, uint32_t fb, float4 *__restrict__ rows, uint32_t rows_cap, int filled, int lane)
 {
     const int k = lane & 7, quarter = lane >> 3;
     __syncwarp();
@@ -301,7 +321,7 @@ static __device__ __noinline__ void bwd3_flush_panel(uint32_t wb, uint32_t ib, u
     Tri3 t;
     t.v1 = t.v2 = t.v3 = t.n = mk3(0.f, 0.f, 0.f);
     float inv_nn = 0.f, invK = 0.f;
-    uint32_t id = 0;
+    uint32_t slot = 0;
     f3 e2 = mk3(0.f, 0.f, 0.f), e3 = e2, f2 = e2, f3v = e2;
     if (k < filled) {
         const uint32_t ia = ib + B3_INFO * k;
@@ -309,7 +329,7 @@ static __device__ __noinline__ void bwd3_flush_panel(uint32_t wb, uint32_t ib, u
         const float4 kq = lds128(ia + 48);
         inv_nn = kq.y;
         invK = fabsf(kq.x) > 1.0e-30f ? 1.0f / kq.x : 0.0f;
-        id = __float_as_uint(kq.z);
+        slot = __float_as_uint(kq.w);
         e2 = t.v2 - t.v1;
         e3 = t.v3 - t.v1;
         f2 = cross3(e2, t.n) * inv_nn;
@@ -358,23 +378,23 @@ static __device__ __noinline__ void bwd3_flush_panel(uint32_t wb, uint32_t ib, u
     if (GEO) { XQ(s_n0); XQ(s_n1); XQ(s_n2); }
 #undef XQ
     if (k < filled) {
-        float *g = home_select(c_peers.a, id, gacc) + (size_t)id * GACC_STRIDE;  // the triangle's home replica (local when single-GPU)
-        const bool mc = c_peers.world > 1;
         const float cA2 = -U1a2, cB2 = U1a1 + U1a2;                                       // G2 = cA2 f2 + cB2 f3
         const float cA3 = -(U1 - U1a2 + U2a2), cB3 = U1 - U1a1 - U1a2 - U2 + U2a1 + U2a2; // G3
         const float cA1 = U2a2, cB1 = -(U2a1 + U2a2);                                      // G1 (+ E0 n)
+        float4 q;  // the lane's quarter of the accumulator line; one 16-byte store into the pair's own row, no atomics
         if (quarter == 0) {
             const f3 G1 = cA1 * f2 + cB1 * f3v + E0 * t.n;
-            red_add4_out(g, G1.x, G1.y, G1.z, fmaf(cA2, f2.x, cB2 * f3v.x), mc);
+            q = make_float4(G1.x, G1.y, G1.z, fmaf(cA2, f2.x, cB2 * f3v.x));
         } else if (quarter == 1) {
-            red_add4_out(g + 4, fmaf(cA2, f2.y, cB2 * f3v.y), fmaf(cA2, f2.z, cB2 * f3v.z), fmaf(cA3, f2.x, cB3 * f3v.x), fmaf(cA3, f2.y, cB3 * f3v.y), mc);
+            q = make_float4(fmaf(cA2, f2.y, cB2 * f3v.y), fmaf(cA2, f2.z, cB2 * f3v.z), fmaf(cA3, f2.x, cB3 * f3v.x), fmaf(cA3, f2.y, cB3 * f3v.y));
         } else if (quarter == 2) {
             const float cn = -inv_nn * (U1a1 + U2a2);
             const f3 GN = mk3(s_n0, s_n1, s_n2) + cn * t.n - (Ea2 * e2 + Ea3 * e3);
-            red_add4_out(g + 8, fmaf(cA3, f2.z, cB3 * f3v.z), GN.x, GN.y, GN.z, mc);
+            q = make_float4(fmaf(cA3, f2.z, cB3 * f3v.z), GN.x, GN.y, GN.z);
         } else {
-            red_add4_out(g + 12, s_c0, s_c1, s_c2, s_op, mc);
+            q = make_float4(s_c0, s_c1, s_c2, s_op);
         }
+        if (slot < rows_cap) rows[4 * (size_t)slot + quarter] = q;
     }
     __syncwarp();
 }
@@ -385,7 +405,8 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
                     const uint2 *__restrict__ ranges, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ list,
                     const float4 *__restrict__ rec0, const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr, const float *__restrict__ background,
                     const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dout_feature,
-                    const float *__restrict__ dL_dout_depth, const float *__restrict__ dL_dout_normal, float *__restrict__ gacc)
+                    const float *__restrict__ dL_dout_depth, const float *__restrict__ dL_dout_normal, const uint32_t *__restrict__ ei_of,
+                    const uint32_t *__restrict__ sbase, float4 *__restrict__ rows, uint32_t rows_cap)
 {
     if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     using L = Bwd3Layout;
@@ -432,8 +453,8 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
 
     int prow = 0;  // next free panel row (rows persist across rounds)
     auto flush_panel = [&](int filled) {
-        if (geo) bwd3_flush_panel<true>(sb + L::W, sb + L::INFO, sb + L::F, gacc, filled, lane);
-        else bwd3_flush_panel<false>(sb + L::W, sb + L::INFO, sb + L::F, gacc, filled, lane);
+        if (geo) bwd3_flush_panel<true>(sb + L::W, sb + L::INFO, sb + L::F, rows, rows_cap, filled, lane);
+        else bwd3_flush_panel<false>(sb + L::W, sb + L::INFO, sb + L::F, rows, rows_cap, filled, lane);
     };
 
     // Back to front: `rem` list positions [0, rem) (tile-relative) are still to be scanned; a chunk is the 32 positions below
@@ -444,7 +465,7 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
     auto next_chunk = [&](uint32_t &p, uint32_t &ppos) {
         if (rem == 0u) return false;
         p = __ballot_sync(0xffffffffu, (kreg >> warp) & 1u);
-        ppos = rem - 1u - lane;  // garbage on lanes >= rem, whose ballot bit is 0
+        ppos = (rem - 1u - lane) | (kreg << 24);  // position | live sub-tile bits; garbage on lanes >= rem, whose ballot bit is 0
         rem -= min(rem, 32u);
         kreg = (lane < rem) ? __ldg(keys + range.x + rem - 1 - lane) : 0u;
         return true;
@@ -453,7 +474,7 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
         const int count = gather_round<B3_CAP, 76>(sb, pend, pend_pos, lane, lt_mask, next_chunk);
         if (count == 0) break;
         __syncwarp();
-        stage_entry<true>(sb, lane, count, list, range.x, rec0, rec1);
+        stage_entry<true>(sb, lane, count, list, range.x, rec0, rec1, warp, ei_of, sbase, sb + L::SLOT);
         __syncwarp();
         // ---- walk
         uint32_t ea = sb;
@@ -506,7 +527,7 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
                     }
                 }
             }
-            if (!__any_sync(0xffffffffu, visited)) continue;
+            (void)visited;  // every staged entry owns a row and is flushed (zeros when no pixel of the sub-tile visited the pair)
             const uint32_t row = sb + L::W + (prow * B3_WROW + lane) * 4;
             sts32f(row, w_c);
             sts32f(row + 128, w_op);
@@ -518,7 +539,7 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
                 sts128(ia, e0);
                 sts128(ia + 16, e1);
                 sts128(ia + 32, e2);
-                sts128(ia + 48, e4);
+                sts128(ia + 48, make_float4(e4.x, e4.y, e4.z, __uint_as_float(lds32(sb + L::SLOT + 4 * j))));
             }
             if (++prow == B3_ROWS) {
                 flush_panel(B3_ROWS);
@@ -549,6 +570,7 @@ int ts2d_launch_render3d_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g
     float *o_feature = mc ? fb->out_feature_mc : out->out_feature, *o_depth = mc ? fb->depth_mc : out->depth, *o_normal = mc ? fb->normal_mc : out->normal;
     float *o_csum = mc ? nullptr : out->contrib_sum, *o_cmax = mc ? nullptr : out->contrib_max;
     TS2D_CUDA_TRY(ts2d_set_peers(fb, true, s));
+    unsigned long long *rows_ctr = reinterpret_cast<unsigned long long *>(&gs.hdr->render.bwd_rows);
 #define TS2D_F3_LAUNCH_CW(R, G, CW, ...)                                                                                               \
     do {                                                                                                                               \
         const size_t smem = CW * (size_t)Fwd3Layout<R>::BYTES;                                                                         \
@@ -566,11 +588,11 @@ int ts2d_launch_render3d_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g
             TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_sum, 0, sizeof(float) * (size_t)g->P, s));
             TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
         }
-        if (g1) TS2D_F3_LAUNCH(true, true, o_depth, o_normal, o_csum, o_cmax, mc);
-        else TS2D_F3_LAUNCH(true, false, o_depth, o_normal, o_csum, o_cmax, mc);
+        if (g1) TS2D_F3_LAUNCH(true, true, o_depth, o_normal, o_csum, o_cmax, mc, is.lastw, rows_ctr);
+        else TS2D_F3_LAUNCH(true, false, o_depth, o_normal, o_csum, o_cmax, mc, is.lastw, rows_ctr);
     } else {
-        if (g1) TS2D_F3_LAUNCH(false, true, nullptr, nullptr, o_csum, o_cmax, mc);
-        else TS2D_F3_LAUNCH(false, false, nullptr, nullptr, o_csum, o_cmax, mc);
+        if (g1) TS2D_F3_LAUNCH(false, true, nullptr, nullptr, o_csum, o_cmax, mc, is.lastw, rows_ctr);
+        else TS2D_F3_LAUNCH(false, false, nullptr, nullptr, o_csum, o_cmax, mc, is.lastw, rows_ctr);
     }
 #undef TS2D_F3_LAUNCH
 #undef TS2D_F3_LAUNCH_CW
@@ -579,17 +601,15 @@ int ts2d_launch_render3d_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g
 }
 
 int ts2d_launch_render3d_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
-                                  const uint32_t *list, ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s)
+                                  const uint32_t *list, ImageState is, const ts2d_loss_in *loss, BwdScratch sc, cudaStream_t s)
 {
     const int W = cam->width, H = cam->height;
     const int gx = (W + TS2D_TILE - 1) / TS2D_TILE, gy = (H + TS2D_TILE - 1) / TS2D_TILE;
     const int n_tiles = gx * gy;
     const int owned = (n_tiles - f->shard_rank + f->shard_world - 1) / f->shard_world;
-    const ts2d_fabric *fb = (f->fabric && f->fabric->scratch[0]) ? f->fabric : nullptr;  // see ts2d_launch_render_bwd_fast
-    TS2D_CUDA_TRY(ts2d_set_peers(fb, false, s));
-    if (!fb) TS2D_CUDA_TRY(cudaMemsetAsync(gacc, 0, sizeof(float) * GACC_STRIDE * (size_t)g->P, s));
     if (owned <= 0) return 0;
     const bool g1 = g->gamma == 1.0f;
+    const uint32_t rows_cap = (uint32_t)(sc.rows_cap < 0xFFFFFFFFll ? sc.rows_cap : 0xFFFFFFFFll);
 #define TS2D_B3_ARGS                                                                                                                     \
     W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, cam->tan_fovx, cam->tan_fovy, is.ranges, keys, list, gs.rec0,       \
         gs.rec1, g->background_depth, ts2d_bg_ptr(g, gs), g->background, is.final_T, is.n_contrib, loss->dL_dout_feature
@@ -598,7 +618,7 @@ int ts2d_launch_render3d_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g
         const size_t smem = CW * (size_t)Bwd3Layout::BYTES;                                                                            \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_bwd_fast<R, G, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_bwd_fast<R, G, CW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));       \
-        k_render3d_bwd_fast<R, G, CW><<<owned * (8 / CW), 32 * CW, smem, s>>>(TS2D_B3_ARGS, __VA_ARGS__, gacc);                     \
+        k_render3d_bwd_fast<R, G, CW><<<owned * (8 / CW), 32 * CW, smem, s>>>(TS2D_B3_ARGS, __VA_ARGS__, sc.ei, sc.sbase, sc.rows, rows_cap); \
     } while (0)
 #define TS2D_B3_LAUNCH(R, G, ...)                                                                                                      \
     do {                                                                                                                               \

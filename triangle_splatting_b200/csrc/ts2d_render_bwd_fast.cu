@@ -16,7 +16,9 @@
 //                              each pair in an 8-row shared-memory panel W[row][pixel];
 //   phase 2 (lane = triangle): every 8 rows, each lane owns (row, quarter of the 32 pixels) and accumulates the
 //                              16 sums with plain FFMAs from W and the per-pixel table F -- no per-pair shuffles,
-//                              no selects -- then two xor-combines and one 16-byte RED per lane (out of line).
+//                              no selects -- then two xor-combines and one 16-byte STORE per lane (out of line) into the
+//                              64 B row this (sub-tile, list entry) pair owns: no atomics anywhere, the per-triangle sums are
+//                              finished by a sequential reduction in a fixed order (ts2d_bwd_reduce.cu) -- bit-reproducible.
 // This replaces a 16-value warp butterfly per pair-iteration (16 SHFL + 16 FADD + 30 SEL) by 3 STS + ~30
 // amortised instructions, and moves all Jacobian arithmetic out of the per-pixel loop.
 #include "ts2d_fast.cuh"
@@ -31,13 +33,14 @@ constexpr int BW_WROW = 97;     // 3 scalars x 32 pixels + 1 pad word: conflict-
 //   POS   non-RICH only: u32[32] list positions (RICH keeps them in the entry's spare word)
 //   F     per pixel {gp0 gp1 gp2 gd} {gn0 gn1 gn2 -}
 //   W     panel [8 rows][97]: [scalar * 32 + pixel]
-//   INFO  per panel row {v1 v2} {v3 1/area2 op} {id}: what phase 2 needs to know about the triangle (48 B stride)
+//   INFO  per panel row {v1 v2} {v3 1/area2 op} {id, row index}: what phase 2 needs to know about the triangle (48 B stride)
 template <bool RICH>
 struct BwdLayout {
     static constexpr int EB = RICH ? 80 : 48;
-    static constexpr int POS = RICH ? 72 : 32 * 48;
+    static constexpr int POS = RICH ? 72 : 32 * 48;        // tile-relative list position of entry j: POS + j * POS_STRIDE
+    static constexpr int SLOT = RICH ? 76 : 32 * 48 + 128; // row index of (this sub-tile, entry j): SLOT + j * POS_STRIDE
     static constexpr int POS_STRIDE = RICH ? 80 : 4;
-    static constexpr int F = RICH ? 32 * 80 : 32 * 48 + 128;
+    static constexpr int F = RICH ? 32 * 80 : 32 * 48 + 256;
     static constexpr int W = F + 32 * 32 + 64;  // F rows are skewed by 16 B per group of 8 pixels, see f_row()
     static constexpr int INFO = W + ((BW_ROWS * BW_WROW * 4 + 15) / 16) * 16;
     static constexpr int BYTES = INFO + BW_ROWS * 48;
@@ -54,7 +57,7 @@ __device__ __forceinline__ uint32_t f_row(int p) { return (uint32_t)(p * 32 + (p
 // colour-only case does not even issue the geometry terms as predicated-off instructions).
 template <bool GEO>
 static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, uint32_t fb, const float4 *__restrict__ rec1,
-                                                    float *__restrict__ gacc, float ox, float oy,
+                                                    float4 *__restrict__ rows, uint32_t rows_cap, float ox, float oy,
                                                     float sub_x0, float sub_y0, int filled, int lane)
 {
     constexpr bool geo = GEO;
@@ -112,8 +115,7 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
 #undef XQ
     if (k < filled) {
         const float4 e1 = lds128(ib + 48 * k), e2 = lds128(ib + 48 * k + 16);
-        float *g = home_select(c_peers.a, id, gacc) + (size_t)id * GACC_STRIDE;  // the triangle's home replica (local when single-GPU)
-        const bool mc = c_peers.world > 1;
+        const uint32_t slot = lds32(ib + 48 * k + 36);  // the row of this (sub-tile, entry) pair
         const float inv = e2.z;
         const float p1x = e1.x - ox, p1y = e1.y - oy, p2x = e1.z - ox, p2y = e1.w - oy, p3x = e2.x - ox, p3y = e2.y - oy;
         float S1 = u10, M1x = u1x, M1y = u1y, S2 = u20, M2x = u2x, M2y = u2y;
@@ -132,10 +134,12 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
         }
         // moments about v1: q = p - v1 = d - (v1 - o)
         const float Q1x = fmaf(-p1x, S1, M1x), Q1y = fmaf(-p1y, S1, M1y), Q2x = fmaf(-p1x, S2, M2x), Q2y = fmaf(-p1y, S2, M2y);
-        if (quarter == 0) red_add4_out(g, S1, Q1x, Q1y, S2, mc);
-        else if (quarter == 1) red_add4_out(g + 4, Q2x, Q2y, s_op, s_n0, mc);
-        else if (quarter == 2) red_add4_out(g + 8, s_c0, s_c1, s_c2, s_n1, mc);
-        else if (geo) red_add4_out(g + 12, s_n2, gv0, gv1, gv2, mc);
+        float4 q;  // the lane's quarter of the 16-float accumulator layout (GACC_STRIDE, ts2d_common.cuh)
+        if (quarter == 0) q = make_float4(S1, Q1x, Q1y, S2);
+        else if (quarter == 1) q = make_float4(Q2x, Q2y, s_op, s_n0);
+        else if (quarter == 2) q = make_float4(s_c0, s_c1, s_c2, s_n1);
+        else q = make_float4(s_n2, gv0, gv1, gv2);  // zeros without geometry gradients
+        if (slot < rows_cap) rows[4 * (size_t)slot + quarter] = q;
     }
     __syncwarp();
 }
@@ -146,7 +150,8 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                   const uint32_t *__restrict__ keys, const uint32_t *__restrict__ list, const float4 *__restrict__ rec0,
                   const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr, const float *__restrict__ background, const float *__restrict__ final_T,
                   const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dout_feature, const float *__restrict__ dL_dout_depth,
-                  const float *__restrict__ dL_dout_normal, float *__restrict__ gacc)
+                  const float *__restrict__ dL_dout_normal, const uint32_t *__restrict__ ei_of, const uint32_t *__restrict__ sbase,
+                  float4 *__restrict__ rows, uint32_t rows_cap)
 {
     if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     using L = BwdLayout<RICH>;
@@ -202,8 +207,8 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
     int prow = 0;  // next free panel row (rows persist across rounds: phase 2 only needs the triangle id)
     const float sub_x0 = (float)((warp & 1) * 8), sub_y0 = (float)((warp >> 1) * 4);
     auto flush_panel = [&](int filled) {
-        if (geo) bwd_flush_panel<true>(sb + L::W, sb + L::INFO, sb + L::F, rec1, gacc, ox, oy, sub_x0, sub_y0, filled, lane);
-        else bwd_flush_panel<false>(sb + L::W, sb + L::INFO, sb + L::F, rec1, gacc, ox, oy, sub_x0, sub_y0, filled, lane);
+        if (geo) bwd_flush_panel<true>(sb + L::W, sb + L::INFO, sb + L::F, rec1, rows, rows_cap, ox, oy, sub_x0, sub_y0, filled, lane);
+        else bwd_flush_panel<false>(sb + L::W, sb + L::INFO, sb + L::F, rec1, rows, rows_cap, ox, oy, sub_x0, sub_y0, filled, lane);
     };
 
     // Back to front: `rem` list positions [range.x, range.x + rem) are still to be scanned; a chunk is the 32 positions
@@ -218,7 +223,8 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
             const uint32_t b = __ballot_sync(0xffffffffu, cov);
             const int n = __popc(b);
             if (count + n > 32) break;  // this chunk opens the next round (kreg still holds it)
-            if (cov) sts32(sb + L::POS + (count + __popc(b & lt_mask)) * L::POS_STRIDE, rem - 1 - lane);  // tile-relative position
+            // tile-relative position | live sub-tile bits << 24 (ts2d_bwd_reduce.cu: k_bwd_rows_mark left only the live ones in the key)
+            if (cov) sts32(sb + L::POS + (count + __popc(b & lt_mask)) * L::POS_STRIDE, (rem - 1 - lane) | (kreg << 24));
             count += n;
             rem -= min(rem, 32u);
             kreg = (lane < rem) ? __ldg(keys + range.x + rem - 1 - lane) : 0u;
@@ -228,7 +234,11 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
         // ---- stage
         if (lane < count) {
             const uint32_t ea = sb + lane * L::EB;
-            const uint32_t id = list[range.x + lds32(sb + L::POS + lane * L::POS_STRIDE)];
+            const uint32_t packed = lds32(sb + L::POS + lane * L::POS_STRIDE);
+            const uint32_t prel = packed & 0xFFFFFFu, bits = packed >> 24;
+            const uint32_t id = list[range.x + prel];
+            // row of (this sub-tile, this entry): rows of an instance are numbered by sub-tile among its live bits
+            const uint32_t slot = __ldg(sbase + __ldg(ei_of + range.x + prel)) + __popc(bits & ((1u << warp) - 1u));
             const float4 *r = rec0 + 3 * (size_t)id;
             const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
             sts128(ea, r0);
@@ -238,9 +248,11 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                 const float4 *q = rec1 + 2 * (size_t)id;
                 const float4 q0 = __ldg(q), q1 = __ldg(q + 1);
                 sts128(ea + 48, q0);
-                sts32f(ea + 64, q1.x);  // +72 holds the list position
+                sts32f(ea + 64, q1.x);  // +72 holds the list position, +76 the row index
                 sts32f(ea + 68, q1.y);
             }
+            sts32(sb + L::POS + lane * L::POS_STRIDE, prel);
+            sts32(sb + L::SLOT + lane * L::POS_STRIDE, slot);
         }
         __syncwarp();
         // ---- walk
@@ -295,7 +307,8 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                     w_D = __uint_as_float((__float_as_uint(D) & ~3u) | sel);
                 }
             }
-            if (!__any_sync(0xffffffffu, w_c != 0.0f)) continue;
+            // every staged entry owns a row (its live bit is set), so every staged entry is flushed -- also when no pixel of the
+            // sub-tile turns out to contribute (non-rich forward: conservative coverage bits): the row is then written as zeros
             const uint32_t row = sb + L::W + (prow * BW_WROW + lane) * 4;
             sts32f(row, w_c);
             sts32f(row + 128, w_op);
@@ -305,6 +318,7 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                 sts128(ia, e1);
                 sts128(ia + 16, e2);
                 sts32(ia + 32, lds32(ea + 44));
+                sts32(ia + 36, lds32(sb + L::SLOT + j * L::POS_STRIDE));
             }
             if (++prow == BW_ROWS) {
                 flush_panel(BW_ROWS);
@@ -319,19 +333,15 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
 }  // namespace
 
 int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
-                                const uint32_t *list, ImageState is, const ts2d_loss_in *loss, float *gacc, cudaStream_t s)
+                                const uint32_t *list, ImageState is, const ts2d_loss_in *loss, BwdScratch sc, cudaStream_t s)
 {
     const int W = cam->width, H = cam->height;
     const int gx = (W + TS2D_TILE - 1) / TS2D_TILE, gy = (H + TS2D_TILE - 1) / TS2D_TILE;
     const int n_tiles = gx * gy;
     const int owned = (n_tiles - f->shard_rank + f->shard_world - 1) / f->shard_world;
-    // multi-GPU over peer memory (ts2d_fabric): the REDs of triangle i go to its home rank's replica of the scratch;
-    // the caller has zeroed every replica and synchronised the ranks
-    const ts2d_fabric *fb = (f->fabric && f->fabric->scratch[0]) ? f->fabric : nullptr;
-    TS2D_CUDA_TRY(ts2d_set_peers(fb, false, s));
-    if (!fb) TS2D_CUDA_TRY(cudaMemsetAsync(gacc, 0, sizeof(float) * GACC_STRIDE * (size_t)g->P, s));
     if (owned <= 0) return 0;
     const bool g1 = g->gamma == 1.0f;
+    const uint32_t rows_cap = (uint32_t)(sc.rows_cap < 0xFFFFFFFFll ? sc.rows_cap : 0xFFFFFFFFll);
 #define TS2D_BWD_ARGS                                                                                                                 \
     W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, keys, list, gs.rec0, gs.rec1, g->background_depth, ts2d_bg_ptr(g, gs),   \
         g->background, is.final_T, is.n_contrib, loss->dL_dout_feature
@@ -340,7 +350,7 @@ int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
         const size_t smem = CW * (size_t)BwdLayout<R>::BYTES;                                                                           \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_bwd_fast<R, G, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_bwd_fast<R, G, CW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));          \
-        k_render_bwd_fast<R, G, CW><<<owned * (8 / CW), 32 * CW, smem, s>>>(TS2D_BWD_ARGS, __VA_ARGS__, gacc);                       \
+        k_render_bwd_fast<R, G, CW><<<owned * (8 / CW), 32 * CW, smem, s>>>(TS2D_BWD_ARGS, __VA_ARGS__, sc.ei, sc.sbase, sc.rows, rows_cap); \
     } while (0)
 #define TS2D_BWD_LAUNCH(R, G, ...)                                                                                                      \
     do {                                                                                                                                \

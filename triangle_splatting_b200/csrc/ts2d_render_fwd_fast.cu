@@ -89,7 +89,8 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                   const uint32_t *keys, const uint32_t *__restrict__ list, const float4 *__restrict__ rec0,
                   const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr, const float *__restrict__ background, float *__restrict__ final_T,
                   uint32_t *__restrict__ n_contrib, float *__restrict__ out_feature, float *__restrict__ out_depth,
-                  float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max, int mc)
+                  float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max, int mc,
+                  uint32_t *__restrict__ lastw, unsigned long long *__restrict__ bwd_rows)
 {
     if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     using L = FwdLayout<RICH>;
@@ -117,12 +118,14 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
     float acc2 = 0.f, accd = 0.f, accn2 = 0.f;
     uint32_t last = range.y - range.x;  // n_contrib if the pixel never saturates
     bool done = !inside;
+    uint32_t rows = 0;  // (sub-tile, entry) pairs the backward pass will visit: one 64 B row each (ts2d_bwd_reduce.cu)
 
     // contrib_sum / contrib_max (forward.cu:323-324), RICH: every visited entry j leaves its 32 per-pixel contrib values in panel
     // row j (zeros where the pixel skipped it); after the walk lane j reduces row j with plain FADD / FMNMX and issues the
     // triangle's RED pair -- one flush per round of up to 32 entries, nothing but a single STS inside the walk.
     auto flush_panel = [&](int visited) {
         __syncwarp();
+        bool kept = false;
         if (lane < visited) {
             const uint32_t row = sb + L::PANEL + lane * (FW_PROW * 4);
             float s = 0.0f, m = 0.0f;
@@ -133,6 +136,7 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                 m = fmaxf(m, v);
             }
             if (m > 0.0f) {
+                kept = true;
                 const uint32_t id = lds32(sb + lane * L::EB + 44);
                 red_add_out(home_select(c_peers.a, id, contrib_sum) + id, s, mc);
                 red_max_out((unsigned int *)home_select(c_peers.b, id, contrib_max) + id, __float_as_uint(m), mc);  // contrib >= 0: bit order == value order
@@ -143,6 +147,7 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                 atomicAnd(keys_rw + lds32(sb + L::POS + lane * L::POS_STRIDE), ~(1u << warp));
             }
         }
+        rows += __popc(__ballot_sync(0xffffffffu, kept));
     };
 
     uint32_t cur = range.x;  // next list position to scan
@@ -241,7 +246,15 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
             }
         }
         if constexpr (RICH) flush_panel(visited);
+        else rows += (uint32_t)visited;  // no per-entry blend information without the panel: every visited entry gets a row
         __syncwarp();  // the next gather overwrites positions / entries / panel rows
+    }
+    {   // where the backward walk of this sub-tile starts, and how many rows it will write
+        const uint32_t wl = __reduce_max_sync(0xffffffffu, inside ? last : 0u);
+        if (lane == 0) {
+            lastw[8 * (size_t)tile + warp] = wl;
+            if (rows) atomicAdd(bwd_rows, (unsigned long long)rows);
+        }
     }
 
     if (inside) {
@@ -283,6 +296,7 @@ int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
     float *o_feature = mc ? fb->out_feature_mc : out->out_feature, *o_depth = mc ? fb->depth_mc : out->depth, *o_normal = mc ? fb->normal_mc : out->normal;
     float *o_csum = mc ? nullptr : out->contrib_sum, *o_cmax = mc ? nullptr : out->contrib_max;
     TS2D_CUDA_TRY(ts2d_set_peers(fb, true, s));
+    unsigned long long *rows_ctr = reinterpret_cast<unsigned long long *>(&gs.hdr->render.bwd_rows);
 #define TS2D_FWD_LAUNCH_CW(R, G, CW, ...)                                                                                              \
     do {                                                                                                                               \
         const size_t smem = CW * (size_t)FwdLayout<R>::BYTES;                                                                          \
@@ -302,11 +316,11 @@ int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
             TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_sum, 0, sizeof(float) * (size_t)g->P, s));
             TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
         }
-        if (g1) TS2D_FWD_LAUNCH(true, true, o_depth, o_normal, o_csum, o_cmax, mc);
-        else TS2D_FWD_LAUNCH(true, false, o_depth, o_normal, o_csum, o_cmax, mc);
+        if (g1) TS2D_FWD_LAUNCH(true, true, o_depth, o_normal, o_csum, o_cmax, mc, is.lastw, rows_ctr);
+        else TS2D_FWD_LAUNCH(true, false, o_depth, o_normal, o_csum, o_cmax, mc, is.lastw, rows_ctr);
     } else {
-        if (g1) TS2D_FWD_LAUNCH(false, true, nullptr, nullptr, o_csum, o_cmax, mc);
-        else TS2D_FWD_LAUNCH(false, false, nullptr, nullptr, o_csum, o_cmax, mc);
+        if (g1) TS2D_FWD_LAUNCH(false, true, nullptr, nullptr, o_csum, o_cmax, mc, is.lastw, rows_ctr);
+        else TS2D_FWD_LAUNCH(false, false, nullptr, nullptr, o_csum, o_cmax, mc, is.lastw, rows_ctr);
     }
 #undef TS2D_FWD_LAUNCH
 #undef TS2D_FWD_LAUNCH_CW

@@ -1,0 +1,278 @@
+// ts2d_sort.cuh -- hand-written device-wide primitives of the binning chain (sm_100a): a stable LSD radix sort (8-bit digits,
+// one kernel per pass, chained look-back between tiles) and a chained inclusive scan.  They replace cub::DeviceRadixSort /
+// cub::DeviceScan (which the reference calls at R2D/src/rasterizer.cu:186,211): the problem sizes, the payloads and the element
+// count are specific to this pipeline --
+//   * the element count may live on the DEVICE (`n_dev`): the host enqueues the whole frame without knowing the number of
+//     instances R, grids are sized for the capacity of the caller's buffers and blocks past the end retire immediately;
+//   * pass 0 of the tile sort reads only the bits that are sorted on and carries the sub-tile coverage mask in the low key bits.
+//
+// One pass = one kernel: a block takes a ticket (tile index = ticket, so a block only ever waits for tiles whose blocks are already
+// running), ranks its 3072 keys by digit (warp-level match, keys of a warp are consecutive in memory so the ranking is stable),
+// publishes its 256 digit counts, looks back over the preceding tiles' published counts (partial | inclusive, one 64-bit word per
+// (tile, digit) tagged with the pass id so that one memset per frame serves every pass), and scatters through shared memory so
+// that every run of equal digits is written with consecutive addresses.
+#pragma once
+#include "ts2d_common.cuh"
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 12;                     // keys per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 3072 keys per block
+constexpr int RS_BINS = 256;
+
+static inline int64_t rs_tiles(int64_t n) { return (n + RS_TILE - 1) / RS_TILE; }
+static inline size_t rs_status_bytes(int64_t n_cap) { return (size_t)(rs_tiles(n_cap > 0 ? n_cap : 1)) * RS_BINS * sizeof(unsigned long long); }
+
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// element count of a launch: the device-side count clamped to the capacity the buffers were sized for, or the host's number
+__device__ __forceinline__ int64_t rs_count(const int64_t *n_dev, int64_t n_cap)
+{
+    if (!n_dev) return n_cap;
+    const int64_t n = *n_dev;
+    return n < n_cap ? n : n_cap;
+}
+
+// exclusive scan of one value per thread over a 256-thread block; `total` (optional) receives the sum.  s_w: 8 words of scratch.
+__device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t *s_w, uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    uint32_t base = 0, sum = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) {
+        const uint32_t c = s_w[w];
+        if (w < warp) base += c;
+        sum += c;
+    }
+    if (total) *total = sum;
+    __syncthreads();  // s_w may be reused by the caller
+    return base + x - v;
+}
+
+// ---- digit histograms of up to four 8-bit digits, one sweep over the keys ---------------------------------------------------
+struct RadixHistArgs {
+    const uint32_t *keys;
+    const int64_t *n_dev;
+    int64_t n_cap;
+    int ndigits;
+    int shift[4];
+    uint32_t mask[4];
+    uint32_t *hist[4];  // [256] each, zeroed by the caller (stream-ordered)
+};
+
+static __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(RadixHistArgs a)
+{
+    __shared__ uint32_t s_h[4][RS_BINS];
+    const int64_t n = rs_count(a.n_dev, a.n_cap);
+    for (int d = 0; d < a.ndigits; d++) s_h[d][threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t k = a.keys[i];
+        for (int d = 0; d < a.ndigits; d++) atomicAdd(&s_h[d][(k >> a.shift[d]) & a.mask[d]], 1u);
+    }
+    __syncthreads();
+    for (int d = 0; d < a.ndigits; d++) {
+        const uint32_t c = s_h[d][threadIdx.x];
+        if (c) atomicAdd(a.hist[d] + threadIdx.x, c);
+    }
+}
+
+// ---- one radix pass ------------------------------------------------------------------------------------------------------
+struct RadixPassArgs {
+    const uint32_t *kin;
+    uint32_t *kout;
+    const uint32_t *vin;   // NULL: the value of element i is i (first pass over an iota payload)
+    uint32_t *vout;
+    const uint32_t *hist;  // [256] digit counts of this pass (k_radix_hist)
+    unsigned long long *status;  // [tiles][256], zero or stale (other pass ids) on entry
+    uint32_t *ticket;      // zero on entry
+    const int64_t *n_dev;
+    int64_t n_cap;
+    int shift;
+    uint32_t mask;
+    uint32_t pass_uid;     // unique (non-zero) per pass between two memsets of `status`
+};
+
+static __global__ void __launch_bounds__(RS_THREADS) k_radix_pass(RadixPassArgs a)
+{
+    __shared__ uint32_t s_cnt[RS_WARPS][RS_BINS];  // per-warp digit counters, then per-warp exclusive offsets
+    __shared__ uint32_t s_texcl[RS_BINS];          // first position of digit d in the tile's sorted order
+    __shared__ uint32_t s_gbase[RS_BINS];          // global position of tile-sorted element t with digit d: s_gbase[d] + t
+    __shared__ uint32_t s_key[RS_TILE], s_val[RS_TILE];
+    __shared__ uint32_t s_w[RS_WARPS];
+    __shared__ uint32_t s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n = rs_count(a.n_dev, a.n_cap);
+    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) s_cnt[w][tid] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t base = (int64_t)tile * RS_TILE;
+    if (base >= n) return;  // past the end (grids are sized for the capacity): nobody waits for this tile
+    const int count = (int)((n - base) < (int64_t)RS_TILE ? (n - base) : (int64_t)RS_TILE);
+
+    // global exclusive digit offsets of this pass
+    const uint32_t gexcl = block_excl_scan256(a.hist[tid], s_w, nullptr);
+
+    // load (warp w: 32 * RS_ITEMS consecutive keys; item i of lane l = element w * 384 + i * 32 + l) and rank
+    uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const int e = warp * (32 * RS_ITEMS) + i * 32 + lane;
+        const bool valid = e < count;
+        key[i] = valid ? a.kin[base + e] : 0u;
+        val[i] = valid ? (a.vin ? a.vin[base + e] : (uint32_t)(base + e)) : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const int e = warp * (32 * RS_ITEMS) + i * 32 + lane;
+        const bool valid = e < count;
+        const uint32_t d = (key[i] >> a.shift) & a.mask;
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : (0x10000u | (uint32_t)lane));  // past-the-end lanes match only themselves
+        const uint32_t lower = peers & lt_mask;
+        uint32_t prev = 0;
+        if (valid) prev = s_cnt[warp][d];
+        __syncwarp();
+        if (valid && lower == 0u) s_cnt[warp][d] = prev + __popc(peers);
+        __syncwarp();
+        rank[i] = prev + __popc(lower);
+    }
+    __syncthreads();
+
+    // digit `tid`: counts of the 8 warps -> exclusive offsets per warp, tile total
+    uint32_t tcount = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) {
+        const uint32_t c = s_cnt[w][tid];
+        s_cnt[w][tid] = tcount;
+        tcount += c;
+    }
+    const uint32_t texcl = block_excl_scan256(tcount, s_w, nullptr);
+    s_texcl[tid] = texcl;
+
+    // chained look-back over the preceding tiles' counts of digit `tid`
+    {
+        const unsigned long long tagP = ((unsigned long long)((a.pass_uid << 2) | 1u)) << 32, tagI = ((unsigned long long)((a.pass_uid << 2) | 2u)) << 32;
+        unsigned long long *mine = a.status + (size_t)tile * RS_BINS + tid;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            st_relaxed_u64(mine, tagI | tcount);
+        } else {
+            st_relaxed_u64(mine, tagP | tcount);
+            int64_t j = (int64_t)tile - 1;
+            while (true) {
+                const unsigned long long w = ld_relaxed_u64(a.status + (size_t)j * RS_BINS + tid);
+                const unsigned long long tg = w & 0xFFFFFFFF00000000ull;
+                if (tg == tagI) {
+                    excl += (uint32_t)w;
+                    break;
+                }
+                if (tg == tagP) {
+                    excl += (uint32_t)w;
+                    j--;  // tile 0 always publishes an inclusive word, so j never runs below 0
+                    continue;
+                }
+                __nanosleep(20);  // not published yet (zero, or a word of an earlier pass)
+            }
+            st_relaxed_u64(mine, tagI | (unsigned long long)(excl + tcount));
+        }
+        s_gbase[tid] = gexcl + excl - texcl;
+    }
+    __syncthreads();
+
+    // tile-local sorted order in shared memory
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const int e = warp * (32 * RS_ITEMS) + i * 32 + lane;
+        if (e < count) {
+            const uint32_t d = (key[i] >> a.shift) & a.mask;
+            const uint32_t pos = s_texcl[d] + s_cnt[warp][d] + rank[i];
+            s_key[pos] = key[i];
+            s_val[pos] = val[i];
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < count; t += RS_THREADS) {
+        const uint32_t k = s_key[t];
+        const uint32_t dst = s_gbase[(k >> a.shift) & a.mask] + (uint32_t)t;
+        a.kout[dst] = k;
+        a.vout[dst] = s_val[t];
+    }
+}
+
+// ---- chained inclusive scan of f(i) = tiles[order[i]] (tiles-touched in depth-rank order, rasterizer.cu:186) ----------------------
+// One status word per tile (same partial | inclusive protocol); the block of the last tile stores the total.
+constexpr int SC_ITEMS = 8;
+constexpr int SC_TILE = RS_THREADS * SC_ITEMS;  // 2048
+static inline int64_t sc_tiles(int64_t n) { return (n + SC_TILE - 1) / SC_TILE; }
+
+static __global__ void __launch_bounds__(RS_THREADS)
+k_scan_gather(const uint32_t *__restrict__ order, const uint32_t *__restrict__ src, uint32_t *__restrict__ out, int n, unsigned long long *status,
+              uint32_t *ticket, int64_t *total_out)
+{
+    __shared__ uint32_t s_w[RS_WARPS];
+    __shared__ uint32_t s_tile, s_excl;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int base = (int)tile * SC_TILE;
+    if (base >= n) return;
+    uint32_t v[SC_ITEMS], sum = 0;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; i++) {  // thread t owns SC_ITEMS consecutive elements
+        const int e = base + tid * SC_ITEMS + i;
+        v[i] = e < n ? src[order[e]] : 0u;
+        sum += v[i];
+    }
+    uint32_t total;
+    uint32_t excl = block_excl_scan256(sum, s_w, &total);
+    if (tid == 0) {
+        const unsigned long long tagP = 1ull << 32, tagI = 2ull << 32;
+        uint32_t look = 0;
+        if (tile == 0) {
+            st_relaxed_u64(status, tagI | total);
+        } else {
+            st_relaxed_u64(status + tile, tagP | total);
+            int64_t j = (int64_t)tile - 1;
+            while (true) {
+                const unsigned long long w = ld_relaxed_u64(status + j);
+                const unsigned long long tg = w & 0xFFFFFFFF00000000ull;
+                if (tg == tagI) { look += (uint32_t)w; break; }
+                if (tg == tagP) { look += (uint32_t)w; j--; continue; }
+                __nanosleep(20);
+            }
+            st_relaxed_u64(status + tile, tagI | (unsigned long long)(look + total));
+        }
+        s_excl = look;
+        if (base + SC_TILE >= n) *total_out = (int64_t)look + (int64_t)total;  // last tile: R (the sum fits 32 bits, see validate())
+    }
+    __syncthreads();
+    excl += s_excl;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; i++) {
+        const int e = base + tid * SC_ITEMS + i;
+        excl += v[i];
+        if (e < n) out[e] = excl;
+    }
+}
