@@ -283,6 +283,14 @@ def run_oracle(sc: Scene, kind: str = "f32", backward: bool = True, primitive: s
     return out
 
 
+def normal_err(ours: dict, ref: dict) -> float:
+    """`normal` is a SIGNED sum of contrib * n over the blended triangles: where the components cancel, |a - b| / |b| says nothing.
+    The natural scale of a pixel is the sum of the magnitudes of its terms, sum contrib = 1 - final_T (|n| = 1): returns
+    max |a - b| / (1 - T + 1e-3).  (Reference vs truth: ~2e-6 in this metric; the fast kernels' alpha carries a few 1e-6.)"""
+    w = 1.0 - np.asarray(ref["final_T"], np.float64) + 1e-3
+    return float((np.abs(np.asarray(ours["normal"], np.float64) - np.asarray(ref["normal"], np.float64)) / w[None]).max())
+
+
 def run_truth(sc: Scene, base: dict, primitive: str = "2D", backward: bool = True) -> dict:
     """fp64 values, the reference's fp32 decisions (oracle kind "f64d"): the exact-arithmetic result of the computation whose
     per-triangle fp32 state, tile lists and per-pixel stopping points are those of `base` (a run_reference / run_ours / golden
@@ -316,6 +324,32 @@ def err_quantiles(a, b, qs=(0.5, 0.99, 0.9999, 1.0), rel_floor: float = 1e-3):
     eps = rel_floor * float(np.sqrt(np.mean(b * b))) + 1e-30
     e = np.abs(a - b) / np.maximum(np.abs(b), eps)
     return [float(x) for x in np.quantile(e, qs)]
+
+
+# ------------------------------------------------------------------------------------ gradient bars
+# north_star asks for 1e-5 on gradients.  Measured against the exact-arithmetic result of the reference's own computation
+# (run_truth: fp64 values, the reference's decisions), the REFERENCE sits at 1e-4 .. 5e-3 (99th .. 99.99th percentile of
+# |g - truth| / max(|truth|, 1e-3 RMS), C2 / C3, profiles/scale_report_r02.txt) and at O(1) in the maximum -- its reverse walk
+# divides T by (1 - alpha) down to 1e-2 and by (ecc + 1e-8) -- while two runs of it differ by 1e-6 .. 3e-5 (the order of its fp32
+# atomics).  No fp32 implementation can be held to 1e-5 of the reference entry by entry unless it repeats the reference's rounding
+# errors operation by operation (flags.exact does, for the forward pass).  The bars are therefore:
+#   accuracy   at the 99th and 99.99th percentile and in the maximum, ours is at most GRAD_K times as far from the truth as the
+#              reference is (+ a 1e-6 floor);
+#   proximity  99 % of the entries differ from the reference by no more than GRAD_K times the reference's own 99th-percentile error;
+#   determinism two runs of ours are bit-identical (tests/test_gpu_scale.py) -- the reference's are not.
+GRAD_K = 1.5
+GRAD_QS = (0.99, 0.9999, 1.0)
+
+
+def assert_gradients_as_accurate_as_reference(ours: dict, ref: dict, truth: dict, what: str, k: float = GRAD_K, keys=None):
+    for key in keys or GRAD_KEYS:
+        if key not in ref or key not in ours or key not in truth:
+            continue
+        eo, er = err_quantiles(ours[key], truth[key], GRAD_QS), err_quantiles(ref[key], truth[key], GRAD_QS)
+        for q, a, b in zip(GRAD_QS, eo, er):
+            assert a <= k * b + 1e-6, f"{what}: {key}: q{q}: ours-vs-truth {a:.2e} > {k} x reference-vs-truth {b:.2e}"
+        near = err_quantiles(ours[key], ref[key], (0.99,))[0]
+        assert near <= k * er[0] + 1e-6, f"{what}: {key}: 99 % of |ours - reference| within {near:.2e}, reference's own p99 error {er[0]:.2e}"
 
 
 # ------------------------------------------------------------------------------------ comparing

@@ -18,7 +18,9 @@ from harness import mismatch_count, rel_err
 
 pytestmark = pytest.mark.gpu
 
-GRAD_MAX, GRAD_FRAC = 1e-1, 0.03  # as tests/test_gpu_parity.py
+# gradients of two of OUR paths over identical fp32 inputs (same kernels, deterministic sums): equal up to the rounding of the few
+# operations that differ between them (fused vs torch sigmoid / rescale backward)
+GRAD_MAX, GRAD_FRAC = 1e-3, 1e-3
 
 
 def _params(sc, dev, seed=11):

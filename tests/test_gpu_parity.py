@@ -23,18 +23,12 @@ MODES = ("exact", "fast")
 # What "parity" can mean per output, measured on a B200 (tests/gpu_report.py -> profiles/parity_report_r01_*.txt):
 #  * exact mode (flags.exact=1): every forward output has the reference's bits.
 #  * pixels, depth: <= 1e-5 in both modes.
-#  * `normal` is a SIGNED sum (components of unit normals cancel), final_T a product of hundreds of factors and
-#    contrib_sum/contrib_max per-triangle statistics: the reference's own fp32 values are 1e-4..1e-2 away from the fp64
-#    truth in this metric; the fast path (different but equally accurate fp32 roundings) gets the bars below.
-#  * gradients: the reference sums them with fp32 atomics in a non-deterministic order through an ill-conditioned reverse
-#    walk (T /= 1-alpha, /(ecc+eps)).  Two runs of the reference differ by up to 2e-3 (dL_dvertex) / 2e-2 (dL_dcenter2D)
-#    in this metric, and it sits 1e-2..6e-2 from the fp64 truth.  "1e-5" is therefore not attainable by anything --
-#    including the reference itself; the bar is "as close to the reference as the reference is to itself" (max <= GRAD_MAX,
-#    almost all entries within 1e-4) plus test_gradient_accuracy_vs_truth (no further from fp64 than the reference is).
-FAST_TOL = {"normal": 2e-2, "final_T": 1e-4, "contrib_sum": 1e-4, "contrib_max": 1e-4}
-GRAD_MAX = 1e-1
-GRAD_FRAC = 0.03  # share of entries allowed beyond 1e-4
-GRAD_TOL = GRAD_MAX
+#  * fast mode: `normal` is judged on its natural scale (harness.normal_err, 1e-5); final_T (a product of hundreds of factors)
+#    and the per-triangle contrib statistics (sums of thousands of terms) get 5e-5 (measured <= 1.7e-5, profiles/scale_report_r02.txt).
+#  * gradients: harness.assert_gradients_as_accurate_as_reference -- no fixed tolerance, the reference's own error is the yardstick.
+FAST_TOL = {"final_T": 5e-5, "contrib_sum": 5e-5, "contrib_max": 5e-5}
+NORMAL_TOL = 1e-5
+NORMAL_TOL3D = 1e-4  # the 3D primitive's normals are NOT unit vectors (R3D/src/forward.cu:94): scale |n| instead of 1
 
 
 def _set_mode(mode):
@@ -50,7 +44,7 @@ def _golden(name):
     return dict(np.load(p))
 
 
-def _check_against(ours, ref, sc, what, mode):
+def _check_against(ours, ref, sc, what, mode, primitive="2D"):
     rich = sc.rich_info
     for k in INT_KEYS:
         if k in ref and k in ours:
@@ -67,15 +61,16 @@ def _check_against(ours, ref, sc, what, mode):
             if mode == "exact" and k not in ("contrib_sum",):  # contrib_sum is an atomic sum in the reference too
                 assert mismatch_count(np.asarray(ours[k]).view(np.uint32), np.asarray(ref[k]).view(np.uint32)) == 0, f"{what}: {k} bits differ"
                 continue
+            if k == "normal" and mode != "exact":
+                e = harness.normal_err(ours, ref)
+                assert e <= NORMAL_TOL, f"{what}: normal err {e:.3e} of the pixel's blended weight > {NORMAL_TOL}"
+                continue
             tol = TOL if mode == "exact" else FAST_TOL.get(k, TOL)
             e = rel_err(ours[k], ref[k])
             assert e <= tol, f"{what}: {k} rel err {e:.3e} > {tol}"
-    for k in GRAD_KEYS:
-        if k in ref and k in ours:
-            e = rel_err(ours[k], ref[k])
-            assert e <= GRAD_MAX, f"{what}: {k} rel err {e:.3e} > {GRAD_MAX}"
-            f = harness.frac_above(ours[k], ref[k], 1e-4, 1e-3)
-            assert f <= GRAD_FRAC, f"{what}: {k}: {f:.2e} of entries differ by more than 1e-4"
+    if any(k in ref and k in ours for k in GRAD_KEYS):
+        truth = harness.run_truth(sc, ref, primitive)
+        harness.assert_gradients_as_accurate_as_reference(ours, ref, truth, what)
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -136,7 +131,9 @@ def test_exact_mode_forward_is_bit_identical_to_reference(cuda_device):
 
 
 def test_gradient_accuracy_vs_truth(cuda_device):
-    """Our gradients are at least as close to the fp64 truth (CPU oracle) as the reference's own are (golden)."""
+    """Our gradients are at least as close to the PURE fp64 evaluation (CPU oracle kind f64: its own decisions, unlike run_truth)
+    as the reference's own are (golden) -- on the scenes where fp64 happens to take the same decisions as fp32."""
+    compared = 0
     for name in harness.GOLDEN_SCENES:
         sc = harness.golden_scene(name)
         gold = _golden(name)
@@ -150,7 +147,9 @@ def test_gradient_accuracy_vs_truth(cuda_device):
                 if k in gold:
                     e_ref, e_ours = rel_err(gold[k], truth[k]), rel_err(ours[k], truth[k])
                     assert e_ours <= 2.0 * e_ref + 1e-4, f"{name}/{mode}: {k}: ours-vs-truth {e_ours:.2e}, reference-vs-truth {e_ref:.2e}"
+                    compared += 1
     _set_mode("fast")
+    assert compared >= 8, f"only {compared} (scene, mode, tensor) triples were comparable: the test compared next to nothing"
 
 
 def test_config_c1_forward_matches_reference_or_oracle(cuda_device):
@@ -242,8 +241,8 @@ def test_autograd_function_end_to_end(cuda_device):
         direct = harness.run_ours(harness.golden_scene(name), cuda_device)
         assert np.array_equal(out[0].detach().cpu().numpy(), direct["out_feature"])
         for t, k in ((vertex, "dL_dvertex"), (shs, "dL_dshs"), (opacity, "dL_dopacity"), (center2D, "dL_dcenter2D")):
-            # two runs of the same kernels differ by the order of the fp32 gradient atomics
-            assert rel_err(t.grad.cpu().numpy(), direct[k]) <= GRAD_TOL, k
+            # no atomics anywhere in the gradient path: a second run through another entry point reproduces every bit
+            assert np.array_equal(t.grad.cpu().numpy().reshape(direct[k].shape), direct[k]), k
 
 
 def test_properties_full_size(cuda_device):
@@ -301,7 +300,7 @@ def test_3d_vs_golden(name, mode, cuda_device):
         chk = sc.vertex.double().sum().item() + sc.opacity.double().sum().item()
         assert abs(chk - float(gold["input_checksum"])) < 1e-9 * max(1.0, abs(chk)), "scene regeneration differs from the golden run"
         ours = harness.run_ours(sc, cuda_device, primitive="3D")
-        _check_against(ours, gold, sc, f"golden3d[{name}/{mode}]", mode)
+        _check_against(ours, gold, sc, f"golden3d[{name}/{mode}]", mode, "3D")
     finally:
         _set_mode("fast")
 
@@ -317,7 +316,7 @@ def test_3d_vs_live_reference(name, mode, cuda_device):
         sc = harness.golden_scene(name, "3D")
         theirs = harness.run_reference(sc, cuda_device, ref=ref, primitive="3D")
         ours = harness.run_ours(sc, cuda_device, primitive="3D")
-        _check_against(ours, theirs, sc, f"live3d[{name}/{mode}]", mode)
+        _check_against(ours, theirs, sc, f"live3d[{name}/{mode}]", mode, "3D")
     finally:
         _set_mode("fast")
 
@@ -342,7 +341,8 @@ def test_3d_fast_equals_exact_at_scale(cuda_device):
                 assert mismatch_count(a[k], b[k]) == 0, f"{kw}: {k} differs between the mirror and the fast kernels"
         for k in ("out_feature", "depth"):
             assert rel_err(b[k], a[k]) <= TOL, f"{kw}: {k} rel err {rel_err(b[k], a[k]):.3e}"
-        for k in ("normal", "final_T", "contrib_sum", "contrib_max"):
+        assert harness.normal_err(b, a) <= NORMAL_TOL3D, f"{kw}: normal err {harness.normal_err(b, a):.3e}"
+        for k in ("final_T", "contrib_sum", "contrib_max"):
             assert rel_err(b[k], a[k]) <= FAST_TOL[k], f"{kw}: {k} rel err {rel_err(b[k], a[k]):.3e}"
         # Gradients: the mirror kernels repeat the reference's per-pair Jacobians (cross products of cancelling differences,
         # ~1e-5 relative noise per pair, R3D/src/backward.cu:401-428), the fast kernels sum well-conditioned moments; measured on a
@@ -435,7 +435,7 @@ def test_3d_autograd_shim_and_noncontiguous_inputs(cuda_device):
     direct = harness.run_ours(harness.golden_scene("sh3_rich", "3D"), cuda_device, primitive="3D")
     assert np.array_equal(out[0].detach().cpu().numpy(), direct["out_feature"])
     for t, k in ((vertex, "dL_dvertex"), (shs, "dL_dshs"), (opacity, "dL_dopacity"), (center2D, "dL_dcenter2D")):
-        assert rel_err(t.grad.cpu().numpy(), direct[k]) <= GRAD_TOL, k
+        assert np.array_equal(t.grad.cpu().numpy().reshape(direct[k].shape), direct[k]), k
 
 
 def test_3d_empty_culled_and_ragged(cuda_device):

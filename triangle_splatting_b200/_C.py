@@ -48,13 +48,14 @@ def set_exact(flag: bool) -> bool:
 # rasterizer.cu:190-193); it is also what the first frame of a shape and debug=True use.
 SYNC_FORWARD = os.environ.get("TS2D_SYNC_FORWARD", "0") == "1"
 _R_SEEN = {}  # (device index, P, W, H, primitive, shard) -> largest R seen
+CAPACITY_MARGIN = 1 << 20  # instances added on top of the largest R seen (16 B each: memory is not what limits this path)
 
 
 def _capacity_for(key):
     r = _R_SEEN.get(key)
     if r is None or SYNC_FORWARD:
         return None
-    return max(int(1.5 * r), r + (1 << 20))
+    return max(int(1.5 * r), r + CAPACITY_MARGIN)
 
 
 class FrameCounters:

@@ -355,16 +355,13 @@ size_t ts2d_backward_scratch_bytes(int32_t P, size_t binning_state_bytes, int64_
 
 namespace {
 
-// rows the scratch has room for: what is left after the fixed part
+// rows the scratch has room for: everything behind the start of the row array
 BwdScratch scratch_view(void *scratch, size_t scratch_bytes, int32_t P, int64_t cap)
 {
     BwdScratch sc;
-    const size_t fixed = carve_scratch(nullptr, P, cap, 1, nullptr);
-    int64_t rows = 1;
-    if (scratch_bytes > fixed) rows += (int64_t)((scratch_bytes - fixed) / 64);
-    if (scratch_bytes < fixed) rows = 0;
-    carve_scratch(scratch, P, cap, rows > 0 ? rows : 1, &sc);
-    sc.rows_cap = rows;
+    carve_scratch(scratch, P, cap, 1, &sc);
+    const size_t rows_off = (size_t)((char *)sc.rows - (char *)scratch);
+    sc.rows_cap = (cap > 0 && scratch_bytes > rows_off) ? (int64_t)((scratch_bytes - rows_off) / 64) : 0;
     return sc;
 }
 

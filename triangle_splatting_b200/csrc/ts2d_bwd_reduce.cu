@@ -14,8 +14,8 @@
 //                      the triangle's rect) -> ei[pos], popcount -> cnt[ei]
 //   k_scan_u8          exclusive scan of cnt over emission indices -> sbase (row of emission index e starts at sbase[e])
 //   composite backward row of (pos, sub-tile w) = sbase[ei[pos]] + popc(live bits below w): one 16-byte store per quarter-lane
-//   k_bwd_rows_reduce  one thread per depth rank: sums rows [sbase[start], sbase[end]) of its triangle into the 64 B accumulator
-//                      line K9 reads (zeros for triangles without rows: no memset of the accumulators either)
+//   k_bwd_rows_reduce  64 depth ranks per block: streams their (contiguous) rows through shared memory, 4 lanes per triangle sum its
+//                      rows in row order into the 64 B accumulator line K9 reads (zeros for triangles without rows: no memset either)
 #include "ts2d_sort.cuh"
 
 namespace {
@@ -95,14 +95,7 @@ k_scan_u8(const uint8_t *__restrict__ src, uint32_t *__restrict__ out, const int
             st_relaxed_u64(status, tagI | total);
         } else {
             st_relaxed_u64(status + tile, tagP | total);
-            int64_t j = (int64_t)tile - 1;
-            while (true) {
-                const unsigned long long w = ld_relaxed_u64(status + j);
-                const unsigned long long tg = w & 0xFFFFFFFF00000000ull;
-                if (tg == tagI) { look += (uint32_t)w; break; }
-                if (tg == tagP) { look += (uint32_t)w; j--; continue; }
-                __nanosleep(20);
-            }
+            look = lookback_sum(status, (int64_t)tile - 1, 1, tagP, tagI);
             st_relaxed_u64(status + tile, tagI | (unsigned long long)(look + total));
         }
         s_excl = look;
@@ -117,37 +110,67 @@ k_scan_u8(const uint8_t *__restrict__ src, uint32_t *__restrict__ out, const int
     }
 }
 
-// one thread per depth rank; rows of adjacent ranks are adjacent in memory
-__global__ void __launch_bounds__(TS2D_BLOCK)
+// Row reduction.  A block owns RR_RANKS consecutive depth ranks; their rows are ONE contiguous span of the row array (rows are laid
+// out in emission order and the instance ranges of consecutive ranks are consecutive).  The block streams the span through shared
+// memory in chunks with fully coalesced 16-byte loads; 4 lanes per rank (one per float4 column of a row) then add the rows of their
+// rank that sit in the chunk, in row order: every accumulator sees its addends in one fixed order, whatever the launch looks like.
+constexpr int RR_RANKS = 64;    // ranks per block = quads per block (256 threads)
+constexpr int RR_CHUNK = 256;   // rows staged per step (16 KB)
+
+__device__ __forceinline__ float4 ldg_stream128(const float4 *p)
+{
+    float4 v;  // read once: do not let the rows displace the raster records from L1 / L2
+    asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(4 * RR_RANKS)
 k_bwd_rows_reduce(int P, const int64_t *__restrict__ n_dev, int64_t cap, int64_t rows_cap, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
                   const uint32_t *__restrict__ offs, const uint32_t *__restrict__ sbase, const float4 *__restrict__ rows, float4 *__restrict__ gacc)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= P) return;
+    __shared__ float4 s_rows[RR_CHUNK * 4];
+    __shared__ uint32_t s_b[RR_RANKS + 1];  // first row of each rank of the block; [RR_RANKS] = end of the span
+    __shared__ uint32_t s_id[RR_RANKS];
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.x * RR_RANKS;
     const int64_t R = rs_count(n_dev, cap);
-    const uint32_t id = order[r];
-    const uint32_t n = tiles[id];
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-    if (n) {
-        int64_t end = offs[r], start = end - n;
-        end = end < R ? end : R;
-        start = start < R ? start : R;
-        int64_t b0 = sbase[start], b1 = sbase[end];
-        b1 = b1 < rows_cap ? b1 : rows_cap;
-        for (int64_t s = b0; s < b1; s++) {
-            const float4 *q = rows + 4 * s;
-            const float4 x0 = __ldg(q), x1 = __ldg(q + 1), x2 = __ldg(q + 2), x3 = __ldg(q + 3);
-            a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
-            a1.x += x1.x; a1.y += x1.y; a1.z += x1.z; a1.w += x1.w;
-            a2.x += x2.x; a2.y += x2.y; a2.z += x2.z; a2.w += x2.w;
-            a3.x += x3.x; a3.y += x3.y; a3.z += x3.z; a3.w += x3.w;
-        }
+    if (tid <= RR_RANKS) {
+        // instance ranges of consecutive ranks are consecutive: rank r starts at offs[r - 1] (inclusive scan) and ends at offs[r]
+        const int r = r0 + tid;
+        int64_t e = 0;
+        if (r > 0) e = offs[(r - 1 < P ? r - 1 : P - 1)];
+        e = e < R ? e : R;
+        int64_t b = R > 0 ? sbase[e] : 0;  // no instances: the scan wrote nothing
+        s_b[tid] = (uint32_t)(b < rows_cap ? b : rows_cap);
+        if (tid < RR_RANKS) s_id[tid] = r < P ? order[r] : 0xFFFFFFFFu;
     }
-    float4 *g = gacc + 4 * (size_t)id;
-    g[0] = a0;
-    g[1] = a1;
-    g[2] = a2;
-    g[3] = a3;
+    __syncthreads();
+    const int q = tid >> 2, c = tid & 3;
+    const uint32_t lo = s_b[q], hi = s_b[q + 1];
+    const uint32_t span0 = s_b[0], span1 = s_b[RR_RANKS];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t c0 = span0; c0 < span1; c0 += RR_CHUNK) {
+        const uint32_t n4 = 4u * min((uint32_t)RR_CHUNK, span1 - c0);
+        const float4 *src = rows + 4 * (size_t)c0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t i = (uint32_t)tid + 256u * k;
+            if (i < n4) s_rows[i] = ldg_stream128(src + i);
+        }
+        __syncthreads();
+        const uint32_t a = max(lo, c0), b = min(hi, c0 + (uint32_t)RR_CHUNK);
+        for (uint32_t s = a; s < b; s++) {
+            const float4 x = s_rows[4 * (s - c0) + c];
+            acc.x += x.x;
+            acc.y += x.y;
+            acc.z += x.z;
+            acc.w += x.w;
+        }
+        __syncthreads();
+    }
+    const uint32_t id = s_id[q];
+    if (id != 0xFFFFFFFFu) gacc[4 * (size_t)id + c] = acc;  // zeros for triangles without rows: the accumulators need no memset
+    (void)tiles;
 }
 
 }  // namespace
@@ -170,7 +193,7 @@ int ts2d_launch_bwd_rows_prepare(const ts2d_camera *cam, const ts2d_flags *f, Ge
 int ts2d_launch_bwd_rows_reduce(int32_t P, GeomState gs, BwdScratch sc, cudaStream_t s)
 {
     if (P <= 0) return 0;
-    k_bwd_rows_reduce<<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(P, &gs.hdr->num_rendered, sc.cap, sc.rows_cap, gs.ids2, gs.tiles, gs.offs,
+    k_bwd_rows_reduce<<<(P + RR_RANKS - 1) / RR_RANKS, 4 * RR_RANKS, 0, s>>>(P, &gs.hdr->num_rendered, sc.cap, sc.rows_cap, gs.ids2, gs.tiles, gs.offs,
                                                                             sc.sbase, sc.rows, reinterpret_cast<float4 *>(sc.gacc));
     return (int)cudaGetLastError();
 }

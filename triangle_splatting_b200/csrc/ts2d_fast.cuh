@@ -85,6 +85,12 @@ __device__ __forceinline__ void sts128(uint32_t a, float4 v)
 __device__ __forceinline__ void sts32f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
+// streaming (evict-first) 16-byte store
+__device__ __forceinline__ void st_stream128(float4 *p, float4 v)
+{
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // Multi-GPU over NVLink peer memory (include/ts2d.h: ts2d_fabric).  Pixels: `mc` != 0 means the output plane pointers are NVSwitch
 // multicast aliases and one multimem.st lands in every rank's replica.  Reductions: PeerSet holds every rank's mapping of a
 // symmetric array; triangle id is reduced on its home rank only (one copy => the same bits for every reader).

@@ -394,7 +394,7 @@ static __device__ __noinline__ void bwd3_flush_panel(uint32_t wb, uint32_t ib, u
         } else {
             q = make_float4(s_c0, s_c1, s_c2, s_op);
         }
-        if (slot < rows_cap) rows[4 * (size_t)slot + quarter] = q;
+        if (slot < rows_cap) st_stream128(rows + 4 * (size_t)slot + quarter, q);  // written once, read once by the row reduction: keep it out of the way of the raster records in L2
     }
     __syncwarp();
 }

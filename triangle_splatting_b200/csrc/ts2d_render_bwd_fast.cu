@@ -139,7 +139,7 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
         else if (quarter == 1) q = make_float4(Q2x, Q2y, s_op, s_n0);
         else if (quarter == 2) q = make_float4(s_c0, s_c1, s_c2, s_n1);
         else q = make_float4(s_n2, gv0, gv1, gv2);  // zeros without geometry gradients
-        if (slot < rows_cap) rows[4 * (size_t)slot + quarter] = q;
+        if (slot < rows_cap) st_stream128(rows + 4 * (size_t)slot + quarter, q);  // written once, read once by the row reduction: keep it out of the way of the raster records in L2
     }
     __syncwarp();
 }

@@ -42,6 +42,41 @@ __device__ __forceinline__ int64_t rs_count(const int64_t *n_dev, int64_t n_cap)
     return n < n_cap ? n : n_cap;
 }
 
+// Chained look-back over the status words of the preceding tiles (stride `stride` words apart, the first at `first`): sum of their
+// counts back to the nearest tile that has published an INCLUSIVE prefix.  When a whole wave of blocks starts at once every block has
+// to walk back over the partial counts of the blocks in front of it, so the walk issues its loads eight at a time (independent
+// loads: one L2 round trip per eight tiles instead of one per tile); words that turn out to lie beyond the stopping point were
+// read for nothing, words that are not published yet are simply read again.
+__device__ __forceinline__ uint32_t lookback_sum(const unsigned long long *status, int64_t j, size_t stride, unsigned long long tagP,
+                                                 unsigned long long tagI)
+{
+    constexpr int LB = 8;
+    uint32_t excl = 0;
+    while (true) {
+        unsigned long long w[LB];
+#pragma unroll
+        for (int b = 0; b < LB; b++) w[b] = (j - b >= 0) ? ld_relaxed_u64(status + (size_t)(j - b) * stride) : tagI;  // below tile 0: stop, add 0
+        int used = LB;
+        bool done = false;
+#pragma unroll
+        for (int b = 0; b < LB; b++) {
+            if (done || used != LB) continue;
+            const unsigned long long tg = w[b] & 0xFFFFFFFF00000000ull;
+            if (tg == tagI) {
+                excl += (uint32_t)w[b];
+                done = true;
+            } else if (tg == tagP) {
+                excl += (uint32_t)w[b];
+            } else {
+                used = b;  // not published yet (zero, or a word of an earlier pass): resume from here
+            }
+        }
+        if (done) return excl;
+        j -= used;
+        if (used != LB) __nanosleep(20);
+    }
+}
+
 // exclusive scan of one value per thread over a 256-thread block; `total` (optional) receives the sum.  s_w: 8 words of scratch.
 __device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t *s_w, uint32_t *total)
 {
@@ -84,9 +119,18 @@ static __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(RadixHistArgs 
     for (int d = 0; d < a.ndigits; d++) s_h[d][threadIdx.x] = 0;
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t k = a.keys[i];
-        for (int d = 0; d < a.ndigits; d++) atomicAdd(&s_h[d][(k >> a.shift[d]) & a.mask[d]], 1u);
+    const uint32_t lane_lt = (1u << (threadIdx.x & 31)) - 1u;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {  // warp-uniform trip count
+        const int64_t i = i0 + threadIdx.x;
+        const bool valid = i < n;
+        const uint32_t k = valid ? a.keys[i] : 0u;
+        for (int d = 0; d < a.ndigits; d++) {
+            // neighbouring keys share their upper digits (consecutive instances of a triangle sit in neighbouring tiles): one shared-memory
+            // atomic per distinct digit of the warp instead of one per key
+            const uint32_t bin = (k >> a.shift[d]) & a.mask[d];
+            const uint32_t peers = __match_any_sync(0xffffffffu, valid ? bin : (0x10000u | (threadIdx.x & 31)));
+            if (valid && (peers & lane_lt) == 0u) atomicAdd(&s_h[d][bin], (uint32_t)__popc(peers));
+        }
     }
     __syncthreads();
     for (int d = 0; d < a.ndigits; d++) {
@@ -179,21 +223,7 @@ static __global__ void __launch_bounds__(RS_THREADS) k_radix_pass(RadixPassArgs 
             st_relaxed_u64(mine, tagI | tcount);
         } else {
             st_relaxed_u64(mine, tagP | tcount);
-            int64_t j = (int64_t)tile - 1;
-            while (true) {
-                const unsigned long long w = ld_relaxed_u64(a.status + (size_t)j * RS_BINS + tid);
-                const unsigned long long tg = w & 0xFFFFFFFF00000000ull;
-                if (tg == tagI) {
-                    excl += (uint32_t)w;
-                    break;
-                }
-                if (tg == tagP) {
-                    excl += (uint32_t)w;
-                    j--;  // tile 0 always publishes an inclusive word, so j never runs below 0
-                    continue;
-                }
-                __nanosleep(20);  // not published yet (zero, or a word of an earlier pass)
-            }
+            excl = lookback_sum(a.status + tid, (int64_t)tile - 1, RS_BINS, tagP, tagI);
             st_relaxed_u64(mine, tagI | (unsigned long long)(excl + tcount));
         }
         s_gbase[tid] = gexcl + excl - texcl;
@@ -254,14 +284,7 @@ k_scan_gather(const uint32_t *__restrict__ order, const uint32_t *__restrict__ s
             st_relaxed_u64(status, tagI | total);
         } else {
             st_relaxed_u64(status + tile, tagP | total);
-            int64_t j = (int64_t)tile - 1;
-            while (true) {
-                const unsigned long long w = ld_relaxed_u64(status + j);
-                const unsigned long long tg = w & 0xFFFFFFFF00000000ull;
-                if (tg == tagI) { look += (uint32_t)w; break; }
-                if (tg == tagP) { look += (uint32_t)w; j--; continue; }
-                __nanosleep(20);
-            }
+            look = lookback_sum(status, (int64_t)tile - 1, 1, tagP, tagI);
             st_relaxed_u64(status + tile, tagI | (unsigned long long)(look + total));
         }
         s_excl = look;
