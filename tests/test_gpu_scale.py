@@ -7,8 +7,8 @@ configuration the bench quotes is compared here, not only the 2 000-triangle gol
   integers   radii, tile rects, tiles_touched, the sorted (key, value) list, ranges, num_rendered, n_contrib, clamp masks: bit-exact
   pixels     out_feature, depth <= 1e-5 (max |a-b| / max(|b|, 1e-3 RMS)); normal <= 1e-5 of the pixel's blended weight; final_T and the
              contrib statistics <= 5e-5
-  gradients  harness.assert_gradients_as_accurate_as_reference (ours no further from the truth than 1.5 x the reference, at the
-             99th / 99.99th percentile and in the maximum; 99 % of |ours - reference| below 1.5 x the reference's own p99 error) and,
+  gradients  harness.assert_gradients_as_accurate_as_reference (ours no further from the truth than 1.5 x the reference at the
+             99th / 99.99th percentile, 4 x in the maximum; 99 % of |ours - reference| below 1.5 x the reference's own p99 error) and,
              where the reference is run twice, ours-vs-reference within GRAD_SPREAD_K x its run-to-run spread at the same percentiles
              or within the reference's own error, whichever is larger
   determinism two runs of ours: every output and every gradient bit-identical (the reference's gradients are not)

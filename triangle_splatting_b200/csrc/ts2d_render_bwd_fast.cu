@@ -117,17 +117,20 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
         const float4 e1 = lds128(ib + 48 * k), e2 = lds128(ib + 48 * k + 16);
         const uint32_t slot = lds32(ib + 48 * k + 36);  // the row of this (sub-tile, entry) pair
         const float inv = e2.z;
-        const float p1x = e1.x - ox, p1y = e1.y - oy, p2x = e1.z - ox, p2y = e1.w - oy, p3x = e2.x - ox, p3y = e2.y - oy;
+        const float p1x = e1.x - ox, p1y = e1.y - oy;
         float S1 = u10, M1x = u1x, M1y = u1y, S2 = u20, M2x = u2x, M2y = u2y;
         float gv0 = 0.f, gv1 = 0.f, gv2 = 0.f;
         if (geo) {
-            // affine barycentrics about the tile origin: a_i(d) = a_io + A_i dx + B_i dy
-            const float a1o = (p2x * p3y - p2y * p3x) * inv, A1 = (e1.w - e2.y) * inv, B1 = (e2.x - e1.z) * inv;
-            const float a2o = (p3x * p1y - p3y * p1x) * inv, A2 = (e2.y - e1.y) * inv, B2 = (e1.x - e2.x) * inv;
-            const float a3o = 1.0f - a1o - a2o, A3 = -A1 - A2, B3 = -B1 - B2;
-            gv0 = fmaf(B1, m2, fmaf(A1, m1, a1o * m0));   // sum gd contrib a_1
-            gv1 = fmaf(B2, m2, fmaf(A2, m1, a2o * m0));
-            gv2 = fmaf(B3, m2, fmaf(A3, m1, a3o * m0));
+            // sum gd contrib a_i with the barycentrics expanded about v1, where a = (1, 0, 0): a_i(p) = a_i(v1) + grad a_i . (p - v1).
+            // (Expanding about the tile origin instead needs a_i(origin), a cross product of vertex offsets of up to a tile plus the
+            // dilated triangle: for a triangle of a few pixels that constant alone carries 1e-5 of rounding.)
+            const float A1 = (e1.w - e2.y) * inv, B1 = (e2.x - e1.z) * inv;  // grad a_1
+            const float A2 = (e2.y - e1.y) * inv, B2 = (e1.x - e2.x) * inv;  // grad a_2
+            const float mqx = fmaf(-p1x, m0, m1), mqy = fmaf(-p1y, m0, m2);  // first moments of gd contrib about v1
+            const float t1 = fmaf(B1, mqy, A1 * mqx), t2 = fmaf(B2, mqy, A2 * mqx);
+            gv0 = m0 + t1;
+            gv1 = t2;
+            gv2 = -t1 - t2;  // a_3 = 1 - a_1 - a_2
             const float d13 = vd1 - vd3, d23 = vd2 - vd3;   // depth term of ga_k = (vd_k - vd_3) gd contrib
             S1 = fmaf(d13, m0, S1); M1x = fmaf(d13, m1, M1x); M1y = fmaf(d13, m2, M1y);
             S2 = fmaf(d23, m0, S2); M2x = fmaf(d23, m1, M2x); M2y = fmaf(d23, m2, M2y);
