@@ -86,6 +86,7 @@ size_t carve_geometry(void *blob, int32_t P, GeomState *gs)
     g.rect = c.take<ushort4>(n);
     g.offs = c.take<uint32_t>(n);
     g.estart = c.take<uint32_t>(n);
+    g.csum64 = c.take<unsigned long long>(n);
     g.clamp = c.take<uint8_t>(n);
     if (gs) *gs = g;
     return ts2d_align_up(c.used, 256);

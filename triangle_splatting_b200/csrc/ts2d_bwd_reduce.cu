@@ -73,13 +73,11 @@ k_scan_u8(const uint8_t *__restrict__ src, uint32_t *__restrict__ out, const int
     if (base >= n) return;
     uint32_t v[SC_ITEMS], sum = 0;
     const int64_t e0 = base + (int64_t)tid * SC_ITEMS;
-    if (e0 + SC_ITEMS <= n) {  // 8 consecutive bytes, 8-byte aligned (cnt is 256-byte aligned, SC_ITEMS == 8)
-        const uint2 w = *reinterpret_cast<const uint2 *>(src + e0);
+    if (e0 + SC_ITEMS <= n) {  // 16 consecutive bytes, 16-byte aligned (cnt is 256-byte aligned, SC_ITEMS == 16)
+        const uint4 w = *reinterpret_cast<const uint4 *>(src + e0);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            v[i] = (w.x >> (8 * i)) & 0xFFu;
-            v[4 + i] = (w.y >> (8 * i)) & 0xFFu;
-        }
+        for (int i = 0; i < 16; i++) v[i] = (ww[i >> 2] >> (8 * (i & 3))) & 0xFFu;
     } else {
 #pragma unroll
         for (int i = 0; i < SC_ITEMS; i++) v[i] = (e0 + i < n) ? src[e0 + i] : 0u;
@@ -173,7 +171,22 @@ k_bwd_rows_reduce(int P, const int64_t *__restrict__ n_dev, int64_t cap, int64_t
     (void)tiles;
 }
 
+__global__ void __launch_bounds__(TS2D_BLOCK) k_contrib_finish(int P, const unsigned long long *__restrict__ csum64, float *__restrict__ contrib_sum)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) contrib_sum[i] = (float)csum64[i] * (1.0f / 4294967296.0f);
+}
+
 }  // namespace
+
+// contrib_sum (forward.cu:323) is summed over (sub-tile, entry) pairs as 2^-32 fixed-point integers by the fast forward kernels:
+// the result does not depend on the order of the atomics.  This turns the sums into the fp32 output.
+int ts2d_launch_contrib_finish(int32_t P, const unsigned long long *csum64, float *contrib_sum, cudaStream_t s)
+{
+    if (P <= 0) return 0;
+    k_contrib_finish<<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(P, csum64, contrib_sum);
+    return (int)cudaGetLastError();
+}
 
 int ts2d_launch_bwd_rows_prepare(const ts2d_camera *cam, const ts2d_flags *f, GeomState gs, BinState bs, ImageState is, BwdScratch sc, cudaStream_t s)
 {

@@ -74,6 +74,7 @@ struct GeomState {
     ushort4 *rect;
     uint32_t *offs;
     uint32_t *estart;
+    unsigned long long *csum64;  // contrib_sum in 2^-32 fixed point (fast forward kernels)
     uint8_t *clamp;
     GeomHeader *hdr;
     unsigned long long *status;   // [rs_tiles(P)][256]
@@ -297,6 +298,7 @@ int ts2d_launch_order_and_scan(int32_t P, GeomState gs, int64_t *R_host, cudaStr
 // K4-K6.  R_host >= 0: the instance count is known on the host (grids are sized for it); < 0: it only exists in gs.hdr
 int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, int64_t R_host, GeomState gs, BinState bs, ImageState is,
                         cudaStream_t s);
+int ts2d_launch_contrib_finish(int32_t P, const unsigned long long *csum64, float *contrib_sum, cudaStream_t s);
 size_t ts2d_sort_status_bytes(int64_t n_cap);
 size_t ts2d_scan_status_bytes(int64_t n_cap);
 // atomics-free gradient write-back (ts2d_bwd_reduce.cu)

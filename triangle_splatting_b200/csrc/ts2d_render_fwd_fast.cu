@@ -90,7 +90,7 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                   const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr, const float *__restrict__ background, float *__restrict__ final_T,
                   uint32_t *__restrict__ n_contrib, float *__restrict__ out_feature, float *__restrict__ out_depth,
                   float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max, int mc,
-                  uint32_t *__restrict__ lastw, unsigned long long *__restrict__ bwd_rows)
+                  uint32_t *__restrict__ lastw, unsigned long long *__restrict__ bwd_rows, unsigned long long *__restrict__ csum64)
 {
     if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     using L = FwdLayout<RICH>;
@@ -138,7 +138,8 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
             if (m > 0.0f) {
                 kept = true;
                 const uint32_t id = lds32(sb + lane * L::EB + 44);
-                red_add_out(home_select(c_peers.a, id, contrib_sum) + id, s, mc);
+                if (csum64) atomicAdd(csum64 + id, __float2ull_rn(s * 4294967296.0f));  // 2^-32 fixed point: integer sums do not depend on the order of the additions
+                else red_add_out(home_select(c_peers.a, id, contrib_sum) + id, s, mc);
                 red_max_out((unsigned int *)home_select(c_peers.b, id, contrib_max) + id, __float_as_uint(m), mc);  // contrib >= 0: bit order == value order
             } else {
                 // No pixel of this sub-tile blended the entry (footprint between pixel centres, or every pixel under it already
@@ -297,6 +298,9 @@ int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
     float *o_csum = mc ? nullptr : out->contrib_sum, *o_cmax = mc ? nullptr : out->contrib_max;
     TS2D_CUDA_TRY(ts2d_set_peers(fb, true, s));
     unsigned long long *rows_ctr = reinterpret_cast<unsigned long long *>(&gs.hdr->render.bwd_rows);
+    // contrib_sum is accumulated in 2^-32 fixed point (bit-reproducible) and converted once at the end; over the peer-memory fabric it
+    // stays a float RED into the triangle's home replica
+    unsigned long long *csum64 = (f->rich_info && !mc) ? gs.csum64 : nullptr;
 #define TS2D_FWD_LAUNCH_CW(R, G, CW, ...)                                                                                              \
     do {                                                                                                                               \
         const size_t smem = CW * (size_t)FwdLayout<R>::BYTES;                                                                          \
@@ -313,14 +317,14 @@ int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
     } while (0)
     if (f->rich_info) {
         if (!mc) {
-            TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_sum, 0, sizeof(float) * (size_t)g->P, s));
+            TS2D_CUDA_TRY(cudaMemsetAsync(gs.csum64, 0, sizeof(unsigned long long) * (size_t)g->P, s));
             TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
         }
-        if (g1) TS2D_FWD_LAUNCH(true, true, o_depth, o_normal, o_csum, o_cmax, mc, is.lastw, rows_ctr);
-        else TS2D_FWD_LAUNCH(true, false, o_depth, o_normal, o_csum, o_cmax, mc, is.lastw, rows_ctr);
+        if (g1) TS2D_FWD_LAUNCH(true, true, o_depth, o_normal, o_csum, o_cmax, mc, is.lastw, rows_ctr, csum64);
+        else TS2D_FWD_LAUNCH(true, false, o_depth, o_normal, o_csum, o_cmax, mc, is.lastw, rows_ctr, csum64);
     } else {
-        if (g1) TS2D_FWD_LAUNCH(false, true, nullptr, nullptr, o_csum, o_cmax, mc, is.lastw, rows_ctr);
-        else TS2D_FWD_LAUNCH(false, false, nullptr, nullptr, o_csum, o_cmax, mc, is.lastw, rows_ctr);
+        if (g1) TS2D_FWD_LAUNCH(false, true, nullptr, nullptr, o_csum, o_cmax, mc, is.lastw, rows_ctr, csum64);
+        else TS2D_FWD_LAUNCH(false, false, nullptr, nullptr, o_csum, o_cmax, mc, is.lastw, rows_ctr, csum64);
     }
 #undef TS2D_FWD_LAUNCH
 #undef TS2D_FWD_LAUNCH_CW

@@ -119,18 +119,10 @@ static __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(RadixHistArgs 
     for (int d = 0; d < a.ndigits; d++) s_h[d][threadIdx.x] = 0;
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const uint32_t lane_lt = (1u << (threadIdx.x & 31)) - 1u;
-    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {  // warp-uniform trip count
-        const int64_t i = i0 + threadIdx.x;
-        const bool valid = i < n;
-        const uint32_t k = valid ? a.keys[i] : 0u;
-        for (int d = 0; d < a.ndigits; d++) {
-            // neighbouring keys share their upper digits (consecutive instances of a triangle sit in neighbouring tiles): one shared-memory
-            // atomic per distinct digit of the warp instead of one per key
-            const uint32_t bin = (k >> a.shift[d]) & a.mask[d];
-            const uint32_t peers = __match_any_sync(0xffffffffu, valid ? bin : (0x10000u | (threadIdx.x & 31)));
-            if (valid && (peers & lane_lt) == 0u) atomicAdd(&s_h[d][bin], (uint32_t)__popc(peers));
-        }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t k = a.keys[i];
+        // (warp-aggregating equal digits with match.any before the atomic was measured: 2.5x slower than the plain shared atomics)
+        for (int d = 0; d < a.ndigits; d++) atomicAdd(&s_h[d][(k >> a.shift[d]) & a.mask[d]], 1u);
     }
     __syncthreads();
     for (int d = 0; d < a.ndigits; d++) {
@@ -252,8 +244,8 @@ static __global__ void __launch_bounds__(RS_THREADS) k_radix_pass(RadixPassArgs 
 
 // ---- chained inclusive scan of f(i) = tiles[order[i]] (tiles-touched in depth-rank order, rasterizer.cu:186) ----------------------
 // One status word per tile (same partial | inclusive protocol); the block of the last tile stores the total.
-constexpr int SC_ITEMS = 8;
-constexpr int SC_TILE = RS_THREADS * SC_ITEMS;  // 2048
+constexpr int SC_ITEMS = 16;
+constexpr int SC_TILE = RS_THREADS * SC_ITEMS;  // 4096 (fewer, larger tiles: the chain of look-backs is what bounds a scan of a few MB)
 static inline int64_t sc_tiles(int64_t n) { return (n + SC_TILE - 1) / SC_TILE; }
 
 static __global__ void __launch_bounds__(RS_THREADS)
