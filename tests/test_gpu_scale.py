@@ -33,7 +33,7 @@ CASES = {
     "C2_2D_geometry_grads": ("C2", "2D", dict(geometry_grads=True), True),
     "C3_2D": ("C3", "2D", dict(), True),
     "C4_3D": ("C4", "3D", dict(), True),  # gamma 7, straight-through binarised opacity, 1600x1600 (render_up_scale 2)
-    "C5_3D": ("C5", "3D", dict(), False),  # 5 M triangles, geometry gradients (MatrixCity mesh recipe)
+    "C5_3D": ("C5", "3D", dict(), True),  # 5 M triangles, geometry gradients (MatrixCity mesh recipe)
 }
 
 

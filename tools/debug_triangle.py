@@ -22,6 +22,7 @@ s = sc.to(dev)
 _C.set_exact(False)
 fwd = _C.rasterize_triangles(*harness._fwd_args(s))
 st = harness.decode_state(s, fwd, dev)
+st["radii"] = fwd[2].cpu().numpy()
 W, H = sc.cam["image_width"], sc.cam["image_height"]
 keys = harness.sorted_instance_keys(fwd, W, H)  # after the forward pass: emit mask minus the bits K7 cleared
 gx = (W + 15) // 16

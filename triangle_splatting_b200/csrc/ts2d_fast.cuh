@@ -213,6 +213,8 @@ struct GammaK {
     float band;      // relative half-width of the alpha decision band
     float terr_c0;   // rel. error bound of a fast alpha = terr_c0 + terr_c1 * |power|
     float terr_c1;
+    float terr_c1_base;  // the part of terr_c1 that does not come from the barycentrics (pow / exp implementations)
+    float loc_k, loc_c;  // local-frame evaluation: |ecc - ecc_reference| <= 1.25 u (loc_k kappa + loc_c), see make_local()
     bool is_one;     // gamma == 1: ecc^(2 gamma) = ecc*ecc
 };
 
@@ -232,7 +234,14 @@ __device__ __forceinline__ GammaK make_gamma(float gamma)
     const float lg = g.is_one ? 0.0f : 2.0e-7f * gamma;  // log2f (1 ulp of |log2 ecc| <= 3.4) * 2 gamma * ln 2 + exp2f (2 ulp)
     g.terr_c0 = 1.8e-6f * gamma + 4.0e-7f;
     g.terr_c1 = 3.6e-6f * gamma + 2.4e-7f + lg;
+    g.terr_c1_base = 2.4e-7f + lg;
     g.band = 1.5f * (g.terr_c0 + g.terr_c1 * 5.6f) + 2.0e-6f;
+    {   // contributing region of a pair: ecc <= Ec = min(10, (2 ln 255)^(1 / (2 gamma))) (opacity <= 1)
+        const float Ec = fminf(10.0f, g.is_one ? 3.3288f : exp2f(3.4701f * g.inv_two_gamma));  // log2(2 ln 255) = 3.4701
+        const float amin = fabsf(1.0f - Ec) * (1.0f / 3.0f), amax = 1.0f + 2.0f * amin, Sa = 1.0f + 4.0f * amin;
+        g.loc_k = 6.0f * Sa * Sa + 60.0f * Sa;
+        g.loc_c = 3.0f * (6.0f * amax + 2.0f) + Ec + 5.0f * Ec + 8.0f;
+    }
     return g;
 }
 
@@ -326,3 +335,74 @@ __device__ __forceinline__ bool eval_fast(const float4 e1, const float4 e2, floa
     // ecc >= 9.9 implies alpha <= exp(-0.5 * 9.9^1.2) << 1/255, i.e. d < -band: skipped by both.
     return d >= 0.0f;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Local-frame evaluation (what the fast 2D kernels run per pair).  With v1 as the origin, q = pixel - v1, e2 = v2 - v1,
+// e3 = v3 - v1 the barycentrics are LINEAR in q:
+//     a2 = cross(q, e3) / area2 ... precisely  a2 = (e3.y q.x - e3.x q.y) / area2,   a3 = (e2.x q.y - e2.y q.x) / area2,   a1 = 1 - a2 - a3,
+// so E_i = 1 - 3 a_i (ecc = max_i E_i, E_1 + E_2 + E_3 = 0) costs one packed subtract and two packed FMAs per pixel:
+//     {E2, E3} = q.x {cx2, cx3} + (q.y {cy2, cy3} + 1),   cx2 = -3 e3.y / area2, cy2 = 3 e3.x / area2, cx3 = 3 e2.y / area2, cy3 = -3 e2.x / area2
+// (the coefficients are formed once per staged entry).  The reference forms the same numbers from pixel-relative cross
+// products (forward.cu:299-305); both roundings are a few ulp of |pv|^2 / |area2| away from the exact value.  The decision bands
+// and the transmittance error bound use a rigorous per-entry bound on |ecc_here - ecc_reference| for every pair that can
+// contribute (ecc <= Ec, the largest eccentricity at which alpha can still reach 1/255):
+//     there all |a_i| <= amax = 1 + 2 |amin|, amin = (1 - Ec) / 3, sum |a_i| <= Sa = 1 + 4 |amin|, hence |pv_k|, |q| <= Sa Lmax
+//     (Lmax = longest edge) and every product of two offsets times 1 / |area2| is <= Sa^2 kappa, kappa = Lmax^2 / |area2|;
+//     reference:  |d ecc| <= u (6 Sa^2 kappa + 3 (6 amax + 2) + Ec)        (one rounded product + FMA + IEEE divide per a_i, a3 = 1 - a1 - a2, fma)
+//     here:       |d ecc| <= u (60 Sa kappa + 5 Ec + 8)                    (coefficients carry 4 u, q carries u, two FMAs per E_i, E1 = -(E2 + E3))
+// with u = 2^-24.  A pair outside that region is further from every threshold than either error.
+struct LocalTri {
+    float4 q0;       // {v1.x, v1.y, cx2, cx3}
+    float4 q1;       // {cy2, cy3, opacity, half-width of the alpha decision band}
+    float c0e, c1e;  // relative error bound of a fast alpha of this entry: c0e + c1e |power|
+};
+
+__device__ __forceinline__ LocalTri make_local(const float4 r0, const float4 r1, const GammaK gk)
+{
+    LocalTri t;
+    const float e2x = r0.z - r0.x, e2y = r0.w - r0.y, e3x = r1.x - r0.x, e3y = r1.y - r0.y;
+    const float k = -3.0f * r1.z;  // -3 / area2
+    t.q0 = make_float4(r0.x, r0.y, e3y * k, -e2y * k);
+    const float e23x = e3x - e2x, e23y = e3y - e2y;
+    const float l2 = fmaxf(fmaxf(fmaf(e2x, e2x, e2y * e2y), fmaf(e3x, e3x, e3y * e3y)), fmaf(e23x, e23x, e23y * e23y));
+    const float kappa = l2 * fabsf(r1.z) * 1.0001f;
+    const float u = 5.9604645e-8f;
+    float de = 1.25f * u * fmaf(gk.loc_k, kappa, gk.loc_c);  // |ecc_here - ecc_reference| wherever the pair can contribute
+    if (r1.w > 1.0f) de *= 16.0f * r1.w;  // opacity above 1 (not produced by the model's sigmoid): the contributing region is wider than Ec
+    t.c0e = fmaf(gk.gamma, de, 4.0e-7f);
+    t.c1e = fmaf(2.0f * gk.gamma, de, gk.terr_c1_base);
+    t.q1 = make_float4(-e3x * k, e2x * k, r1.w, fmaf(1.5f, fmaf(t.c1e, 5.6f, t.c0e), 2.0e-6f));
+    return t;
+}
+
+// Fast per-pair evaluation in the local frame.  P = {px, py}.  `f.e1..e3` are the three 1 - 3 a_i, `f.qx, f.qy` the pixel relative
+// to v1 (the rich outputs interpolate the vertex depths with them).  Same contract as eval_fast().
+struct LocalPair {
+    float qx, qy, e1, e2, e3, ecc, power, G, og, alpha;
+};
+__device__ __forceinline__ bool eval_local(const float4 q0, const float4 q1, const v2 P, const GammaK gk, LocalPair &f, bool &uncertain)
+{
+    const v2 q = sub2(P, mk2v(q0.x, q0.y));
+    v2 E = fma2(bc(q.b), mk2v(q1.x, q1.y), bc(1.0f));
+    E = fma2(bc(q.a), mk2v(q0.z, q0.w), E);
+    f.qx = q.a;
+    f.qy = q.b;
+    f.e2 = E.a;
+    f.e3 = E.b;
+    f.e1 = -(E.a + E.b);
+    f.ecc = fmaxf(fmaxf(f.e1, f.e2), f.e3);
+    float pw;
+    if (gk.is_one)
+        pw = f.ecc * f.ecc;
+    else
+        pw = exp2f(gk.two_gamma * log2f(fmaxf(f.ecc, 1.0e-30f)));  // full-precision log2f/exp2f: the error is multiplied by 2 gamma |power|
+    f.power = -0.5f * pw;
+    f.G = ex2_approx(f.power * TS2D_LOG2E);
+    f.og = q1.z * f.G;
+    f.alpha = fminf(0.99f, f.og);
+    const float d = fmaf(f.alpha, 255.0f, -1.0f);  // alpha * 255 - 1
+    uncertain = (fabsf(d) <= q1.w) || (f.ecc < 1.0e-4f);
+    return d >= 0.0f;  // (the reference's ecc > 10 cut: see eval_fast)
+}
+// first arg-min of (a1, a2, a3) in that order (backward.cu:449-461) == first arg-max of (E1, E2, E3)
+__device__ __forceinline__ uint32_t argmin_sel(float e1, float e2, float e3) { return (e1 >= e2 && e1 >= e3) ? 1u : ((e2 >= e1 && e2 >= e3) ? 2u : 3u); }

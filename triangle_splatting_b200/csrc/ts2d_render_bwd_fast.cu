@@ -29,18 +29,18 @@ constexpr int BW_ROWS = 8;      // triangles per phase-2 panel
 constexpr int BW_WROW = 97;     // 3 scalars x 32 pixels + 1 pad word: conflict-free for both phases
 
 // Per-warp shared-memory block (byte offsets from the warp's base address):
-//   ENT   entry j at j * EB: {v1.x v1.y v2.x v2.y} {v3.x v3.y 1/area2 op} {r g b id} [RICH: {n.x n.y n.z vd1} {vd2 vd3 pos -}]
+//   ENT   entry j at j * EB: {v1.x v1.y cx2 cx3} {cy2 cy3 op band} {r g b id} [RICH: {n.x n.y n.z vd1} {Dx Dy pos row}]   (LocalTri, ts2d_fast.cuh)
 //   POS   non-RICH only: u32[32] list positions (RICH keeps them in the entry's spare word)
 //   F     per pixel {gp0 gp1 gp2 gd} {gn0 gn1 gn2 -}
 //   W     panel [8 rows][97]: [scalar * 32 + pixel]
-//   INFO  per panel row {v1 v2} {v3 1/area2 op} {id, row index}: what phase 2 needs to know about the triangle (48 B stride)
+//   INFO  per panel row {v1.x v1.y cx2 cx3} {cy2 cy3 id row}: what phase 2 needs to know about the triangle (48 B stride: conflict-free)
 template <bool RICH>
 struct BwdLayout {
     static constexpr int EB = RICH ? 80 : 48;
     static constexpr int POS = RICH ? 72 : 32 * 48;        // tile-relative list position of entry j: POS + j * POS_STRIDE
     static constexpr int SLOT = RICH ? 76 : 32 * 48 + 128; // row index of (this sub-tile, entry j): SLOT + j * POS_STRIDE
     static constexpr int POS_STRIDE = RICH ? 80 : 4;
-    static constexpr int F = RICH ? 32 * 80 : 32 * 48 + 256;
+    static constexpr int F = RICH ? 32 * 80 : 32 * 48 + 256;  // (the backward needs no per-entry error bound: it repeats decisions, it does not track T's error)
     static constexpr int W = F + 32 * 32 + 64;  // F rows are skewed by 16 B per group of 8 pixels, see f_row()
     static constexpr int INFO = W + ((BW_ROWS * BW_WROW * 4 + 15) / 16) * 16;
     static constexpr int BYTES = INFO + BW_ROWS * 48;
@@ -71,7 +71,7 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
     uint32_t id = 0;
     float vd1 = 0.f, vd2 = 0.f, vd3 = 0.f;
     if (k < filled) {
-        id = lds32(ib + 48 * k + 32);
+        id = lds32(ib + 48 * k + 24);
         if (geo) {  // vertex depths: re-read from L1/L2, in flight during the panel sums
             vd1 = __ldg(&rec1[2 * (size_t)id].w);
             const float2 q = __ldg(reinterpret_cast<const float2 *>(rec1 + 2 * (size_t)id + 1));
@@ -114,9 +114,8 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
     if (geo) { XQ(s_n0); XQ(s_n1); XQ(s_n2); XQ(m0); XQ(m1); XQ(m2); }
 #undef XQ
     if (k < filled) {
-        const float4 e1 = lds128(ib + 48 * k), e2 = lds128(ib + 48 * k + 16);
-        const uint32_t slot = lds32(ib + 48 * k + 36);  // the row of this (sub-tile, entry) pair
-        const float inv = e2.z;
+        const float4 e1 = lds128(ib + 48 * k), e2 = lds128(ib + 48 * k + 16);  // {v1.x v1.y cx2 cx3} {cy2 cy3 id row}
+        const uint32_t slot = __float_as_uint(e2.w);  // the row of this (sub-tile, entry) pair
         const float p1x = e1.x - ox, p1y = e1.y - oy;
         float S1 = u10, M1x = u1x, M1y = u1y, S2 = u20, M2x = u2x, M2y = u2y;
         float gv0 = 0.f, gv1 = 0.f, gv2 = 0.f;
@@ -124,13 +123,12 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
             // sum gd contrib a_i with the barycentrics expanded about v1, where a = (1, 0, 0): a_i(p) = a_i(v1) + grad a_i . (p - v1).
             // (Expanding about the tile origin instead needs a_i(origin), a cross product of vertex offsets of up to a tile plus the
             // dilated triangle: for a triangle of a few pixels that constant alone carries 1e-5 of rounding.)
-            const float A1 = (e1.w - e2.y) * inv, B1 = (e2.x - e1.z) * inv;  // grad a_1
-            const float A2 = (e2.y - e1.y) * inv, B2 = (e1.x - e2.x) * inv;  // grad a_2
+            // grad a_2 = -(cx2, cy2) / 3, grad a_3 = -(cx3, cy3) / 3, grad a_1 = -(grad a_2 + grad a_3)
             const float mqx = fmaf(-p1x, m0, m1), mqy = fmaf(-p1y, m0, m2);  // first moments of gd contrib about v1
-            const float t1 = fmaf(B1, mqy, A1 * mqx), t2 = fmaf(B2, mqy, A2 * mqx);
-            gv0 = m0 + t1;
+            const float t2 = fmaf(e2.x, mqy, e1.z * mqx) * (-1.0f / 3.0f), t3 = fmaf(e2.y, mqy, e1.w * mqx) * (-1.0f / 3.0f);
             gv1 = t2;
-            gv2 = -t1 - t2;  // a_3 = 1 - a_1 - a_2
+            gv2 = t3;
+            gv0 = m0 - t2 - t3;  // a_1 = 1 - a_2 - a_3
             const float d13 = vd1 - vd3, d23 = vd2 - vd3;   // depth term of ga_k = (vd_k - vd_3) gd contrib
             S1 = fmaf(d13, m0, S1); M1x = fmaf(d13, m1, M1x); M1y = fmaf(d13, m2, M1y);
             S2 = fmaf(d23, m0, S2); M2x = fmaf(d23, m1, M2x); M2y = fmaf(d23, m2, M2y);
@@ -169,6 +167,7 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
     const int px = tile_x * TS2D_TILE + lx, py = tile_y * TS2D_TILE + ly;
     const bool inside = px < W_ && py < H;
     const float pxf = (float)px, pyf = (float)py;
+    const v2 Pxy = mk2v(pxf, pyf);
     const float ox = (float)(tile_x * TS2D_TILE), oy = (float)(tile_y * TS2D_TILE);
     const size_t pix = (size_t)W_ * py + px;
     const size_t HW = (size_t)H * W_;
@@ -244,15 +243,18 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
             const uint32_t slot = __ldg(sbase + __ldg(ei_of + range.x + prel)) + __popc(bits & ((1u << warp) - 1u));
             const float4 *r = rec0 + 3 * (size_t)id;
             const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
-            sts128(ea, r0);
-            sts128(ea + 16, r1);
+            const LocalTri lt = make_local(r0, r1, gk);
+            sts128(ea, lt.q0);
+            sts128(ea + 16, lt.q1);
             sts128(ea + 32, make_float4(r2.x, r2.y, r2.z, __uint_as_float(id)));
             if (RICH) {
                 const float4 *q = rec1 + 2 * (size_t)id;
                 const float4 q0 = __ldg(q), q1 = __ldg(q + 1);
                 sts128(ea + 48, q0);
-                sts32f(ea + 64, q1.x);  // +72 holds the list position, +76 the row index
-                sts32f(ea + 68, q1.y);
+                // depth = vd1 + q.x Dx + q.y Dy (see k_render_fwd_fast); +72 holds the list position, +76 the row index
+                const float d21 = (q1.x - q0.w) * (-1.0f / 3.0f), d31 = (q1.y - q0.w) * (-1.0f / 3.0f);
+                sts32f(ea + 64, fmaf(lt.q0.z, d21, lt.q0.w * d31));
+                sts32f(ea + 68, fmaf(lt.q1.x, d21, lt.q1.y * d31));
             }
             sts32(sb + L::POS + lane * L::POS_STRIDE, prel);
             sts32(sb + L::SLOT + lane * L::POS_STRIDE, slot);
@@ -265,17 +267,19 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
             const uint32_t pos = lds32(sb + L::POS + j * L::POS_STRIDE);
             float w_c = 0.0f, w_op = 0.0f, w_D = 0.0f;
             if (pos < last) {
-                FastPair f;
+                LocalPair f;
                 bool unc;
-                bool hit = eval_fast(e1, e2, pxf, pyf, gk, f, unc);
+                bool hit = eval_local(e1, e2, Pxy, gk, f, unc);
                 // one more reference decision lives in the backward pass: op*G < 0.99 (clamp not active)
-                unc = unc || (fabsf(f.og - 0.99f) <= 0.99f * gk.band);
-                if (unc) {
-                    const float area2 = __ldg(&rec0[3 * (size_t)lds32(ea + 44) + 2].w);
+                unc = unc || (fabsf(f.og - 0.99f) <= 0.99f * e2.w);
+                if (unc) {  // the reference's own arithmetic on the vertices of the raster record (rare path)
+                    const uint32_t id = lds32(ea + 44);
+                    const float4 r0 = __ldg(rec0 + 3 * (size_t)id), r1 = __ldg(rec0 + 3 * (size_t)id + 1);
+                    const float area2 = __ldg(&rec0[3 * (size_t)id + 2].w);
                     PairEval e;
-                    hit = eval_exact(e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, area2, e2.w, gk.two_gamma, pxf, pyf, e);
-                    f.a1 = e.a1; f.a2 = e.a2; f.a3 = e.a3; f.ecc = e.ecc;
-                    if (hit) { f.power = e.power; f.G = e.G; f.og = __fmul_rn(e2.w, e.G); f.alpha = e.alpha; }
+                    hit = eval_exact(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, area2, r1.w, gk.two_gamma, pxf, pyf, e);
+                    f.e1 = fmaf(e.a1, -3.0f, 1.0f); f.e2 = fmaf(e.a2, -3.0f, 1.0f); f.e3 = fmaf(e.a3, -3.0f, 1.0f); f.ecc = e.ecc;  // order-preserving: the arg-min stays the reference's
+                    if (hit) { f.power = e.power; f.G = e.G; f.og = __fmul_rn(r1.w, e.G); f.alpha = e.alpha; }
                 }
                 if (hit) {
                     const float4 col = lds128(ea + 32);
@@ -297,7 +301,7 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                         accn0 = fmaf(f.alpha, q0.x, om * accn0);
                         accn1 = fmaf(f.alpha, q0.y, om * accn1);
                         accn2 = fmaf(f.alpha, q0.z, om * accn2);
-                        const float depth = fmaf(q1.y, f.a3, fmaf(q0.w, f.a1, q1.x * f.a2));
+                        const float depth = fmaf(f.qy, q1.y, fmaf(f.qx, q1.x, q0.w));
                         dL_dcontrib = fmaf(gd, depth - accd, dL_dcontrib);
                         accd = fmaf(f.alpha, depth, om * accd);
                     }
@@ -306,7 +310,7 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                     const float dL_dpower = (f.og < 0.99f) ? dL_dalpha * f.alpha : 0.0f;
                     const float D = -3.0f * dL_dpower * gk.two_gamma * f.power * rcp_approx(f.ecc + TS2D_EPS);
                     // sub-gradient of min: first arg-min in the order a1, a2, a3 (backward.cu:449-461)
-                    const uint32_t sel = (f.a1 <= f.a2 && f.a1 <= f.a3) ? 1u : ((f.a2 <= f.a1 && f.a2 <= f.a3) ? 2u : 3u);
+                    const uint32_t sel = argmin_sel(f.e1, f.e2, f.e3);
                     w_D = __uint_as_float((__float_as_uint(D) & ~3u) | sel);
                 }
             }
@@ -319,9 +323,7 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
             {   // row info for phase 2; every lane stores the same words (cheaper than electing one: no lane id, no predicate)
                 const uint32_t ia = sb + L::INFO + prow * 48;
                 sts128(ia, e1);
-                sts128(ia + 16, e2);
-                sts32(ia + 32, lds32(ea + 44));
-                sts32(ia + 36, lds32(sb + L::SLOT + j * L::POS_STRIDE));
+                sts128(ia + 16, make_float4(e2.x, e2.y, __uint_as_float(lds32(ea + 44)), __uint_as_float(lds32(sb + L::SLOT + j * L::POS_STRIDE))));
             }
             if (++prow == BW_ROWS) {
                 flush_panel(BW_ROWS);

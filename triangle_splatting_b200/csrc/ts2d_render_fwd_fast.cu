@@ -12,10 +12,10 @@
 //            instance) and compacts their list positions until up to 32 are collected;
 //   stage    lane i loads the raster record of collected entry i (3(+2) LDG.128) into the warp's private
 //            shared-memory buffer -- only records that the sub-tile really needs are read;
-//   walk     a plain counted loop over the staged entries: reference-shaped barycentrics with one reciprocal
-//            multiply, min3, 1 MUFU.EX2 per pixel; decisions inside the rounding band are re-taken with
-//            eval_exact(); the T <= 1e-4 cut is re-taken with an exact transmittance re-walk done cooperatively
-//            by the warp (exact_T_upto) when T lands inside its running error bound.
+//   walk     a plain counted loop over the staged entries: barycentrics in the triangle's own frame (eval_local, ts2d_fast.cuh:
+//            one packed subtract + two packed FMAs for the three 1 - 3 a_i), max3, 1 MUFU.EX2 per pixel; decisions inside the
+//            rounding band are re-taken with eval_exact(); the T <= 1e-4 cut is re-taken with an exact transmittance re-walk
+//            done cooperatively by the warp (exact_T_upto) when T lands inside its running error bound.
 //   contrib_sum / contrib_max: each visited entry leaves its 32 per-pixel contrib values in one row of a 32-row panel
 //            (a single STS in the walk); after the walk the lanes switch roles (lane = entry), reduce their row with
 //            plain FADD / FMNMX and issue one RED pair per triangle that was blended anywhere in the sub-tile.
@@ -26,16 +26,17 @@ namespace {
 constexpr int FW_PROW = 33;    // panel row stride in words: conflict-free for both access patterns
 
 // Per-warp shared-memory block (byte offsets from the warp's base address):
-//   entry j at j * EB:  {v1.x v1.y v2.x v2.y} {v3.x v3.y 1/area2 op} {r g b id} [RICH: {n.x n.y n.z vd1} {vd2 vd3 pos -}]
+//   entry j at j * EB:  {v1.x v1.y cx2 cx3} {cy2 cy3 op band} {r g b id} {c0e c1e Dx Dy} [RICH: {n.x n.y n.z vd1} {pos - - -}]
+//            (LocalTri of ts2d_fast.cuh; depth of the pixel = vd1 + q.x Dx + q.y Dy, q = pixel - v1)
 //   non-RICH: list positions in a separate u32[32] after the entries;
 //   RICH: contrib panel [32 entries][33] floats after that (row j = the 32 pixels' contrib of staged entry j).
 template <bool RICH>
 struct FwdLayout {
-    static constexpr int EB = RICH ? 80 : 48;
-    static constexpr int POS = RICH ? 72 : 32 * 48;      // position of entry j: POS + j * POS_STRIDE
-    static constexpr int POS_STRIDE = RICH ? 80 : 4;
-    static constexpr int PANEL = RICH ? 32 * 80 : 0;
-    static constexpr int BYTES = RICH ? 32 * 80 + 32 * FW_PROW * 4 : 32 * 48 + 128;
+    static constexpr int EB = RICH ? 96 : 64;
+    static constexpr int POS = RICH ? 80 : 32 * 64;      // position of entry j: POS + j * POS_STRIDE
+    static constexpr int POS_STRIDE = RICH ? 96 : 4;
+    static constexpr int PANEL = RICH ? 32 * 96 : 0;
+    static constexpr int BYTES = RICH ? 32 * 96 + 32 * FW_PROW * 4 : 32 * 64 + 128;
 };
 
 // Exact transmittance of pixel (px, py) after visiting list positions [start, upto] (inclusive), computed with the
@@ -61,19 +62,16 @@ __device__ __noinline__ float exact_T_upto(const uint32_t *__restrict__ list, co
     return T;
 }
 
-// The reference's own decision and alpha for one pair.
-__device__ __forceinline__ bool exact_pair(const float4 e1, const float4 e2, const float4 *__restrict__ rec0, uint32_t id, float two_gamma,
-                                           float px, float py, float &alpha, float &power, float &a1, float &a2, float &a3)
+// The reference's own decision and alpha for one pair (vertices re-read from the raster record: rare path).
+// -> {alpha, power}; alpha < 0: the reference skips the pair.  Out of line: results come back in registers, the libdevice
+// powf / expf / IEEE-divide code stays out of the walk loop's register budget.
+__device__ __noinline__ float2 exact_pair(const float4 *__restrict__ rec0, uint32_t id, float two_gamma, float px, float py)
 {
+    const float4 r0 = __ldg(rec0 + 3 * (size_t)id), r1 = __ldg(rec0 + 3 * (size_t)id + 1);
     const float area2 = __ldg(&rec0[3 * (size_t)id + 2].w);
     PairEval e;
-    const bool hit = eval_exact(e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, area2, e2.w, two_gamma, px, py, e);
-    alpha = e.alpha;
-    power = e.power;
-    a1 = e.a1;
-    a2 = e.a2;
-    a3 = e.a3;
-    return hit;
+    const bool hit = eval_exact(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, area2, r1.w, two_gamma, px, py, e);
+    return make_float2(hit ? e.alpha : -1.0f, hit ? e.power : 0.0f);
 }
 
 #ifndef TS2D_FWD_MINB
@@ -106,6 +104,7 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
     const bool inside = px < W && py < H;
     float pxf = (float)px, pyf = (float)py;
     asm volatile("" : "+f"(pxf), "+f"(pyf));  // opaque: keep them in registers (ptxas re-materialised two I2FP per walk iteration)
+    const v2 Pxy = mk2v(pxf, pyf);
     GammaK gk = make_gamma(GAMMA1 ? 1.0f : gamma);  // gamma == 1: every constant of the error model folds to an immediate
     gk.is_one = GAMMA1;
     const uint32_t sb = smem_base(s_raw + lwarp * L::BYTES);  // this warp's block
@@ -175,16 +174,21 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
             const uint32_t id = list[lds32(sb + L::POS + lane * L::POS_STRIDE)];
             const float4 *r = rec0 + 3 * (size_t)id;
             const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
-            sts128(ea, r0);
-            sts128(ea + 16, r1);
+            const LocalTri lt = make_local(r0, r1, gk);
+            sts128(ea, lt.q0);
+            sts128(ea + 16, lt.q1);
             sts128(ea + 32, make_float4(r2.x, r2.y, r2.z, __uint_as_float(id)));
+            float Dx = 0.0f, Dy = 0.0f;
             if constexpr (RICH) {
                 const float4 *q = rec1 + 2 * (size_t)id;
                 const float4 q0 = __ldg(q), q1 = __ldg(q + 1);
-                sts128(ea + 48, q0);
-                sts32f(ea + 64, q1.x);  // +72 holds the list position
-                sts32f(ea + 68, q1.y);
+                sts128(ea + 64, q0);  // +80 holds the list position
+                // depth = sum a_i vd_i = vd1 + a2 (vd2 - vd1) + a3 (vd3 - vd1), a2 = -(q . c2) / 3, a3 = -(q . c3) / 3
+                const float d21 = (q1.x - q0.w) * (-1.0f / 3.0f), d31 = (q1.y - q0.w) * (-1.0f / 3.0f);
+                Dx = fmaf(lt.q0.z, d21, lt.q0.w * d31);
+                Dy = fmaf(lt.q1.x, d21, lt.q1.y * d31);
             }
+            sts128(ea + 48, make_float4(lt.c0e, lt.c1e, Dx, Dy));
         }
         __syncwarp();
         // ---- walk
@@ -195,25 +199,29 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
             float contrib = 0.0f;  // > 0 <=> this lane blended the triangle
             bool evt = false;      // this lane's transmittance reached the 1e-4 cut or its error band: handled out of line below
             if (!done) {
-                FastPair f;
+                LocalPair f;
                 bool unc;
-                bool hit = eval_fast(e1, e2, pxf, pyf, gk, f, unc);
-                if (unc) hit = exact_pair(e1, e2, rec0, lds32(ea + 44), gk.two_gamma, pxf, pyf, f.alpha, f.power, f.a1, f.a2, f.a3);
+                bool hit = eval_local(e1, e2, Pxy, gk, f, unc);
+                if (unc) {
+                    const float2 ex = exact_pair(rec0, lds32(ea + 44), gk.two_gamma, pxf, pyf);
+                    hit = ex.x >= 0.0f;
+                    f.alpha = ex.x;
+                    f.power = ex.y;
+                }
                 if (hit) {
                     contrib = f.alpha * T;
-                    const float4 col = lds128(ea + 32);
+                    const float4 col = lds128(ea + 32), ce = lds128(ea + 48);
                     acc01 = fma2(bc(contrib), mk2v(col.x, col.y), acc01);
                     acc2 = fmaf(contrib, col.z, acc2);
                     if constexpr (RICH) {
-                        const float4 q0 = lds128(ea + 48);
-                        const float2 q1 = lds64(ea + 64);
+                        const float4 q0 = lds128(ea + 64);
                         accn01 = fma2(bc(contrib), mk2v(q0.x, q0.y), accn01);
                         accn2 = fmaf(contrib, q0.z, accn2);
-                        accd = fmaf(contrib, fmaf(f.a3, q1.y, fmaf(q0.w, f.a1, q1.x * f.a2)), accd);
+                        accd = fmaf(contrib, fmaf(f.qy, ce.w, fmaf(f.qx, ce.z, q0.w)), accd);
                     }
                     const float om = 1.0f - f.alpha;
                     // |T_new - T_ref_new| <= |T - T_ref| * om + T * |d alpha| + rounding of the two product chains
-                    Terr = fmaf(Terr, om, contrib * (unc ? 0.0f : fmaf(gk.terr_c1, fabsf(f.power), gk.terr_c0)));
+                    Terr = fmaf(Terr, om, contrib * (unc ? 0.0f : fmaf(ce.y, fabsf(f.power), ce.x)));
                     T *= om;
                     Terr = fmaf(T, 1.3e-7f, Terr);
                     evt = (T - 0.0001f) <= Terr;  // saturated (T <= 1e-4) or within the error band of the cut
@@ -329,5 +337,7 @@ int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
 #undef TS2D_FWD_LAUNCH
 #undef TS2D_FWD_LAUNCH_CW
 #undef TS2D_FWD_ARGS
-    return (int)cudaGetLastError();
+    TS2D_CUDA_TRY(cudaGetLastError());
+    if (csum64) return ts2d_launch_contrib_finish(g->P, csum64, out->contrib_sum, s);
+    return 0;
 }
