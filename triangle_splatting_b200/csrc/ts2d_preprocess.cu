@@ -274,14 +274,17 @@ k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool ri
         const f2 e12 = s2 - s1, e23 = s3 - s2, e31 = s1 - s3, w = s3 - s1;
         const float S1 = A0.x, S2 = A0.w;
         const f2 Q1 = mk2(A0.y, A0.z), Q2 = mk2(A1.x, A1.y);
-        const float Tt = (S1 + cross2(e23, Q1) * inv) + cross2(e31, Q2) * inv;  // sum ga1 a1 + sum ga2 a2
-        g1 = perp2(e23 * Tt - w * S2 + Q2) * inv;
-        g2 = perp2(e31 * Tt + w * S1 - Q1) * inv;
-        g3 = perp2((e12 * Tt - e12 * S1) + (Q1 - Q2)) * inv;
-        // g1 + g2 + g3 in closed form: the Tt and Q terms cancel identically (e12 + e23 + e31 = 0), what is left is the response to a
-        // rigid translation, perp(e23 S1 + e31 S2) / area2.  Summing the three rounded vectors instead leaves eps |e| |Tt| / |area2| of
-        // noise in dL_dcenter2D (measured at C3: one entry 0.7 off, where the closed form and the reference agree to 1e-3).
-        gc2d = perp2(e23 * S1 + e31 * S2) * inv;
+        // D = sum ga1 (a1 - 1) + sum ga2 a2: how far the weighted pixels sit from v1 in barycentric terms.  Keeping it apart from S1
+        // matters: with T = S1 + D the terms e31 T + w S1 of the vertex-2 gradient cancel down to e31 D, and for a triangle whose
+        // contributing pixels lie near v1 (|D| << |S1|) the rounded cancellation used to cost vertex 2 (and 3) most of their digits
+        // (measured at C3: single entries 0.7 off where the reference is exact to 1e-6).
+        const float D = (cross2(e23, Q1) + cross2(e31, Q2)) * inv;
+        const f2 gc = perp2(e23 * S1 + e31 * S2) * inv;  // response to a rigid translation = g1 + g2 + g3 (the Q and D terms cancel identically)
+        g1 = gc + perp2(e23 * D + Q2) * inv;
+        g2 = perp2(e31 * D - Q1) * inv;
+        g3 = perp2(e12 * D + (Q1 - Q2)) * inv;
+        (void)w;
+        gc2d = gc;  // dL_dcenter2D (backward.cu:191) in closed form rather than as the sum of the three rounded vectors
     }
     const float g_op = A1.z;
     const f3 g_rgb = mk3(A2.x, A2.y, A2.z);
