@@ -17,7 +17,10 @@ A "step" is one forward + backward of the rasterizer through the reference-shape
 --impl reference times the UNMODIFIED reference CUDA extension (oracle/_ref, built from /root/reference by
 oracle/build_ref.py) on the same scene through its own pybind entry points; if that module cannot be loaded
 it falls back to the CPU oracle port on a bounded sample and says so.
-N > 1: image-space tile sharding of ONE render (tile % N == rank) + NCCL all-reduce; strong scaling.
+N > 1: image-space tile sharding of ONE render (tile % N == rank); pixels and contrib statistics travel through NVLink peer memory
+inside the forward kernel when the fabric is available (else one NCCL all-reduce), the per-triangle gradient accumulators are summed
+with one all-reduce; strong scaling.  `--check` (default on for N > 1) compares the sharded frame and gradients with the single-GPU
+result on every rank, outside the timed region.
 """
 from __future__ import annotations
 
@@ -87,7 +90,7 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def algorithmic_bytes(P, V, R, N, T, K, M, rich):
+def algorithmic_bytes(P, V, R, N, T, K, M, rich, rows=0):
     """bytes each stage must touch once (no temp / zero-fill / sort-pass amplification)."""
     rho = 1 if rich else 0
     rec = 44 + 24 * rho
@@ -98,6 +101,10 @@ def algorithmic_bytes(P, V, R, N, T, K, M, rich):
         "render_fwd": (4 + rec) * R + (20 + 16 * rho) * N + 8 * rho * V,
         "render_bwd": (4 + rec) * R + (20 + 16 * rho) * N + (40 + 24 * rho) * V,
         "preprocess_bwd": (40 + 24 * rho) * V + (36 + 12 * K + 3) * V + 4 * P + (36 + 8 + 4 + 12 + 12 * M) * P,
+        # not in SURVEY 8(d) (the reference has no counterpart): bookkeeping of the atomics-free gradient write-back, counted as what
+        # it must touch once -- a key, a list entry and an index per instance / one 64 B row per (sub-tile, entry) pair in and out
+        "bwd_prepare": 8 * R + 9 * R,
+        "bwd_reduce": 64 * rows + 64 * P,
     }
 
 
@@ -436,6 +443,66 @@ def cpu_oracle_baseline(sc, tile_step=None, budget_s=20.0, primitive="2D"):
             "seconds_measured": t_geom + t_fwd_all + t_bwd}
 
 
+def sharded_vs_single_check(step, sc, dev, primitive, world):
+    """Outside the timed region, on EVERY rank: the tile-sharded frame and gradients of `step` against the same step with sharding
+    switched off (the whole frame on this GPU).  Returns the worst figures over the ranks and whether all ranks hold identical bits."""
+    from triangle_splatting_b200 import distributed as tsd
+
+    def run(st):
+        out = st()
+        res = {"image": out[0], "depth": out[2], "normal": out[3], "contrib_sum": out[4], "contrib_max": out[5], "radii": out[1].float(),
+               "dL_dvertex": st.vertex.grad, "dL_dshs": st.shs.grad, "dL_dopacity": st.opacity.grad}
+        return {k: v.detach().clone() for k, v in res.items()}
+
+    sharded = run(step)
+    tsd.disable_tile_sharding()
+    single = run(OursStep(sc, dev, primitive))
+    tsd.enable_tile_sharding()
+    rel = {}
+    for k, b in single.items():
+        a = sharded[k]
+        eps = 1e-3 * b.double().pow(2).mean().sqrt() + 1e-30
+        rel[k] = float(((a.double() - b.double()).abs() / torch.maximum(b.double().abs(), eps)).max().item())
+    keys = sorted(rel)
+    worst = torch.tensor([rel[k] for k in keys], device=dev, dtype=torch.float64)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    sums = torch.stack([sharded[k].double().sum() for k in keys])  # a checksum per tensor: equal on all ranks <=> (practically) identical bits
+    lo, hi = sums.clone(), sums.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return {"ranks": world, "metric": "max |sharded - single| / max(|single|, 1e-3 RMS), worst rank", "rel_err": {k: float(v) for k, v in zip(keys, worst.tolist())},
+            "radii_equal": rel["radii"] == 0.0 and float(worst[keys.index("radii")]) == 0.0, "all_ranks_identical": bool(torch.equal(lo, hi))}
+
+
+def work_statistics(fwd_state, sc, dev, world, stage_ms):
+    """SURVEY 8(d) work figures of this rank's shard from the forward pass's own state: list lengths, sum of n_contrib (the pairs the
+    reference's loops visit), the 256 R upper bound, the (sub-tile, entry) rows of the backward, and ns per pair of K7 / K8."""
+    from triangle_splatting_b200 import _lib
+
+    lib = _lib.load()
+    W, H = sc.cam["image_width"], sc.cam["image_height"]
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    R, gb, bb, ib = int(fwd_state[0]), fwd_state[7], fwd_state[8], fwd_state[9]
+    p = lambda x: ctypes.c_void_p(x.data_ptr())
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    ranges = torch.zeros((gx * gy, 2), device=dev, dtype=torch.int32)
+    ncon = torch.zeros((H, W), device=dev, dtype=torch.int32)
+    _lib.check(lib.ts2d_export_binning(p(gb), p(bb), bb.numel(), p(ib), sc.P, R, W, H, None, None, p(ranges), stream), "export_binning")
+    _lib.check(lib.ts2d_export_image(p(ib), W, H, p(ncon), None, stream), "export_image")
+    ctr = getattr(fwd_state[0], "counters", None)
+    rows = int(ctr.backward_rows()) if ctr is not None else 0
+    lens = (ranges[:, 1] - ranges[:, 0]).long()
+    lens = lens[lens > 0] if world > 1 else lens  # sharded: only the tiles this rank owns have lists
+    pairs = int(ncon.long().sum().item())
+    out = {"num_rendered": R, "tiles_with_lists": int(lens.numel()), "list_len_mean": round(float(lens.float().mean().item()), 2) if lens.numel() else 0.0,
+           "list_len_max": int(lens.max().item()) if lens.numel() else 0, "pairs_sum_n_contrib": pairs,
+           "n_contrib_mean": round(pairs / max(1, (W * H) // world), 2), "pairs_upper_256R": 256 * R, "backward_rows": rows}
+    if pairs:
+        out["ns_per_pair_render_fwd"] = round(stage_ms["render_fwd"] * 1e6 / pairs, 5)
+        out["ns_per_pair_render_bwd"] = round(stage_ms["render_bwd"] * 1e6 / pairs, 5)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------- main
 def sample_clocks(step, dev, index, timed_ms, steps, sampler_result):
     """nvidia-smi needs ~100 ms per sample; if the timed region was shorter than that, sample the same load in a ~1 s
@@ -461,18 +528,22 @@ def timed_region(step, steps, warmup, dev, world):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
         step()
-    e1.record()
+        ev[i + 1].record()  # per-step marks inside the same timed region (no synchronisation): median / p10 / p90 for free
     torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1)
+    ms = ev[0].elapsed_time(ev[steps])
+    per = torch.tensor([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)], device=dev)
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(per, op=dist.ReduceOp.MAX)
         dist.barrier()
         ms = float(t.item())
+    q = torch.quantile(per.float(), torch.tensor([0.1, 0.5, 0.9], device=dev)).tolist()
+    timed_region.per_step = {"p10_ms": round(q[0], 4), "median_ms": round(q[1], 4), "p90_ms": round(q[2], 4)}
     return ms
 
 
@@ -518,6 +589,7 @@ def main():
     ap.add_argument("--primitive", default="2D", choices=["2D", "3D"],
                     help="2D: diff_triangle_rasterization_2D (the north-star path); 3D: diff_triangle_rasterization_3D (the *_mesh configs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="N > 1: skip the sharded-vs-single-GPU comparison (outside the timed region)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-model-step", action="store_true", help="skip the model-level step (fused parameter-space front-end)")
     a = ap.parse_args()
@@ -535,7 +607,7 @@ def main():
                        f"(M={sc.shs.shape[1]}), rich_info={sc.rich_info}, gamma={sc.gamma}, fwd+bwd",
            "primitive": a.primitive, "P": sc.P, "width": sc.cam["image_width"], "height": sc.cam["image_height"], "sh_degree": sc.sh_degree,
            "l2_policy": "inputs larger than L2 (SH 288 MB + 120 MB raster records + instance lists >> 126 MB L2); no explicit flush",
-           "parallelism": "single GPU" if a.gpus == 1 else f"image-space tile sharding x{a.gpus} (tile % N == rank) + NCCL all-reduce"}
+           "parallelism": "single GPU"}  # N > 1: filled in below once the exchange mechanism that actually ran is known
 
     if not torch.cuda.is_available():
         if a.impl == "reference" and rank == 0:
@@ -627,6 +699,16 @@ def main():
     step = OursStep(sc, dev, a.primitive)
     out = step()  # first call: also gives V, R for the byte model
     torch.cuda.synchronize(dev)
+    if world > 1:
+        from triangle_splatting_b200 import distributed as tsd
+
+        used_fabric = tsd.fabric(dev) is not None
+        cfg["parallelism"] = (f"image-space tile sharding x{world} (tile % N == rank), strong scaling; forward exchange: "
+                              + ("NVLink peer memory inside K7 (multimem.st of the owned pixels into every replica, contrib statistics RED-ed into "
+                                 "the triangle's home replica, multimem publish of the home slices; symmetric-memory signal-pad barriers)"
+                                 if used_fabric else "NCCL all-reduce(sum) of the zero-filled frame planes + contrib_sum, all-reduce(max) of contrib_max")
+                              + "; backward exchange: NCCL all-reduce(sum) of the 64 B/triangle accumulators between K8 + row reduction and K9")
+        cfg["exchange"] = {"forward": "fabric" if used_fabric else "nccl", "backward": "nccl"}
     radii = out[1]
     V = int((radii > 0).sum().item())
     N = sc.cam["image_width"] * sc.cam["image_height"]
@@ -640,8 +722,9 @@ def main():
     smp.start()
     ms = timed_region(step, a.steps, a.warmup, dev, world)
     clocks = sample_clocks(step, dev, local_rank, ms, a.steps, smp.stop())
-    st_ms = (ctypes.c_float * 6)()
-    st_n = (ctypes.c_int32 * 6)()
+    per_step = dict(getattr(timed_region, "per_step", {}))
+    st_ms = (ctypes.c_float * len(_lib.STAGES))()
+    st_n = (ctypes.c_int32 * len(_lib.STAGES))()
     lib.ts2d_profile_read(st_ms, st_n)
     lib.ts2d_profile_enable(0)
     n_calls = a.steps + a.warmup
@@ -653,14 +736,17 @@ def main():
     s, c = step.sc, step.sc.cam
     fa = (c["image_width"], c["image_height"], c["tanfovx"], c["tanfovy"], c["viewmatrix"], c["projmatrix"], c["campos"], s.sh_degree,
           s.gamma, 1.0, s.background_depth, s.background, s.vertex, s.shs, torch.Tensor([]), s.opacity, s.back_culling, s.rich_info, False)
-    R_local = int(tsC.rasterize_triangles(*fa, shard=(rank, world) if world > 1 else (0, 1), primitive=a.primitive)[0])
+    fwd_state = tsC.rasterize_triangles(*fa, shard=(rank, world) if world > 1 else (0, 1), primitive=a.primitive)
+    R_local = int(fwd_state[0])
     R_total = R_local * world if R_local is not None else None  # interleaved tiles: shards are balanced to <1%
+    work = work_statistics(fwd_state, sc, dev, world, stage_ms) if rank == 0 else None
+    del fwd_state
 
     line = None
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         K = (sc.sh_degree + 1) ** 2
-        ab = algorithmic_bytes(sc.P, V, R_local, N // world, T // world, K, sc.shs.shape[1], sc.rich_info)
+        ab = algorithmic_bytes(sc.P, V, R_local, N // world, T // world, K, sc.shs.shape[1], sc.rich_info, rows=work.get("backward_rows", 0))
         dom = max(stage_ms, key=lambda k: stage_ms[k])
         stages = {k: {"ms": round(stage_ms[k], 4), "alg_bytes": ab[k], "gbs": round(ab[k] / (stage_ms[k] * 1e-3) / 1e9, 1) if stage_ms[k] > 0 else None,
                       "share": round(stage_ms[k] / max(1e-9, sum(stage_ms.values())), 3)} for k in stage_ms}
@@ -673,18 +759,21 @@ def main():
                 issue_pct = tj.get("issue_active_pct", {}).get(dom)
         except (OSError, KeyError, ValueError):
             pass
-        roof = {"bound": "hbm", "traffic_source": traffic_src, "kernel": {"render_fwd": "k_render_fwd", "render_bwd": "k_render_bwd", "preprocess": "k_preprocess",
-                                            "preprocess_bwd": "k_preprocess_bwd", "binning": "k_emit + cub radix + k_ranges",
-                                            "order_scan": "cub radix + scan"}[dom],
+        roof = {"bound": "hbm", "traffic_source": traffic_src, "kernel": {"render_fwd": "k_render_fwd_fast", "render_bwd": "k_render_bwd_fast", "preprocess": "k_preprocess",
+                                            "preprocess_bwd": "k_preprocess_bwd", "binning": "k_emit_warp + k_radix_hist + k_radix_pass + k_ranges",
+                                            "order_scan": "k_radix_hist + k_radix_pass + k_scan_gather", "bwd_prepare": "k_bwd_rows_mark + k_scan_u8",
+                                            "bwd_reduce": "k_bwd_rows_reduce"}[dom],
                 "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5), "traffic": traffic, "peak_source": peak_src,
                 "issue_active_pct": issue_pct,
                 "note": "per-pixel composite is FP32/MUFU-issue bound, not HBM bound (SURVEY.md section 8d): issue_active_pct (ncu, same capture as "
                         "`traffic`) is the fraction of its real ceiling; per-stage figures in `stages`",
                 "whole_frame_gbs": round(sum(ab.values()) / (ms / a.steps * 1e-3) / 1e9, 1)}
-        own_per_step = 7  # k_preprocess, k_set_header, k_emit, k_ranges, k_render_fwd, k_render_bwd, k_preprocess_bwd
-        line = dict(base, impl="ours", value=fps, ms_per_step=ms / a.steps, config=cfg, clocks=clocks, roofline=roof, stages=stages,
-                    gpu_launches=own_per_step * a.steps,
-                    library_launches_note="plus ~14 CUB radix-sort/scan kernels and 4 memsets per step (toolkit library, not counted)",
+        tile_bits = max(1, (T - 1).bit_length())
+        # K1, depth histogram, 4 depth passes, scan | emit, tile histogram, tile passes, ranges, K7, contrib finish | row marking, row scan,
+        # K8, row reduction, K9 -- every one of them a kernel of libts2d (no library kernels on the path; memsets not counted)
+        own_per_step = 7 + (4 + (tile_bits + 7) // 8 + (1 if sc.rich_info else 0)) + 5
+        line = dict(base, impl="ours", value=fps, ms_per_step=ms / a.steps, per_step=per_step, config=cfg, clocks=clocks, roofline=roof, stages=stages,
+                    gpu_launches=own_per_step * a.steps, work=work,
                     scene={"P": sc.P, "visible": V, "num_rendered_rank0": R_local, "num_rendered_est": R_total, "tiles": T, "pixels": N})
 
     # e2e (all ranks participate: the step contains collectives when sharded)
@@ -722,6 +811,11 @@ def main():
 
     if rank == 0 and world == 1 and not a.no_model_step:
         line["image_loss"] = image_loss_ms(sc, dev, fused=True)
+
+    if world > 1 and not a.no_check:
+        chk = sharded_vs_single_check(step, sc, dev, a.primitive, world)
+        if rank == 0:
+            line["check"] = chk
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:

@@ -338,9 +338,11 @@ enum {
     TS2D_STAGE_ORDER_SCAN = 1,     /* K2/K3 depth sort of P keys + scan */
     TS2D_STAGE_BINNING = 2,        /* K4-K6 emit, tile radix sort, ranges */
     TS2D_STAGE_RENDER_FWD = 3,     /* K7 */
-    TS2D_STAGE_RENDER_BWD = 4,     /* K8: row marking + scan, composite backward, per-triangle row reduction */
+    TS2D_STAGE_RENDER_BWD = 4,     /* K8: composite backward */
     TS2D_STAGE_PREPROCESS_BWD = 5, /* K9 */
-    TS2D_NUM_STAGES = 6
+    TS2D_STAGE_BWD_PREPARE = 6,    /* row marking + scan in front of K8 (atomics-free write-back) */
+    TS2D_STAGE_BWD_REDUCE = 7,     /* per-triangle row reduction behind K8 */
+    TS2D_NUM_STAGES = 8
 };
 int ts2d_profile_enable(int enable);
 int ts2d_profile_read(float *ms_out /*[TS2D_NUM_STAGES]*/, int32_t *launches_out /*[TS2D_NUM_STAGES]*/);

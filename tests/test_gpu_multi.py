@@ -3,7 +3,8 @@
 One process per GPU over NCCL: every rank composites only the tiles it owns (tile % world == rank), the frame is
 assembled with an all-reduce, the per-triangle gradient accumulators are all-reduced between the composite and the
 per-triangle backward.  Every rank must end up with the single-GPU result: forward outputs to fp32 rounding of the
-all-reduce (exact for disjoint tiles: x + 0), gradients up to the summation order of the atomics."""
+all-reduce (exact for disjoint tiles: x + 0), gradients up to the re-association of the per-triangle sums (per rank, then over ranks).
+Worlds 4 and 8 run when the box has that many GPUs (`gpurun --gpus 8`)."""
 import os
 import socket
 
@@ -51,7 +52,12 @@ def _worker(rank, world, port, ret):
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        sc = harness.golden_scene("sh3_rich")
+        from triangle_splatting_b200.scenes import make_scene
+
+        # small golden scene for world 2 (70 tiles); 60 k triangles on 640x480 (1 200 tiles, ~280 k instances) for the wider worlds, where
+        # the home-chunk routing of the contrib statistics and the ownership pattern tile % world see every rank
+        sc = harness.golden_scene("sh3_rich") if world == 2 else make_scene("multi", 60_000, 640, 480, sh_degree=1, rich_info=True,
+                                                                            geometry_grads=True, seed=17)
         single = _run(sc, dev)  # sharding off: the single-GPU answer, computed on this very GPU
         res = {}
         for mode in ("0", "auto"):  # NCCL collectives / NVLink peer memory (multicast pixel stores + home-rank reductions)
@@ -67,7 +73,7 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_tile_sharded_render_matches_single_gpu(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -88,8 +94,16 @@ def test_tile_sharded_render_matches_single_gpu(world):
                     assert np.array_equal(single[k], sharded[k]), f"{what}: {k} (disjoint tiles: stores / sums with zeros)"
                 assert rel_err(sharded["contrib_sum"], single["contrib_sum"]) <= 1e-5, what
                 for k in ("dL_dvertex", "dL_dshs", "dL_dopacity", "dL_dcenter2D"):
-                    assert rel_err(sharded[k], single[k]) <= 1e-1 and harness.frac_above(sharded[k], single[k], 1e-4, 1e-3) <= 0.03, f"{what}: {k}"
-            # all ranks hold the same frame and the same gradients, bit for bit (replicated optimizers must not drift apart)
-            a, b = ret[0][1][mode][frame], ret[1][1][mode][frame]
-            for k in a:
-                assert np.array_equal(a[k], b[k]), f"mode {mode} frame {frame}: ranks disagree on {k}"
+                    # the per-triangle sums are the same numbers added in another order (per rank first, then over the ranks): fp32
+                    # re-association only -- 99.9 % of the entries within 1e-5, every entry within 5e-2 of max(|g|, 1e-3 RMS)
+                    q = harness.err_quantiles(sharded[k], single[k], (0.999, 1.0))
+                    assert q[0] <= 1e-5 and q[1] <= 5e-2, f"{what}: {k}: {q}"
+            # all ranks hold the same frame and the same gradients, bit for bit (replicated optimizers must not drift apart) ...
+            for r in range(1, world):
+                a, b = ret[0][1][mode][frame], ret[r][1][mode][frame]
+                for k in a:
+                    assert np.array_equal(a[k], b[k]), f"mode {mode} frame {frame}: ranks 0 and {r} disagree on {k}"
+        # ... and two consecutive frames of the same scene are bit-identical too (no atomics in the gradient path, fixed-order exchange)
+        for k in ret[0][1][mode][0]:
+            if k != "contrib_sum" or mode == "0":  # over the fabric contrib_sum is a float RED into the home replica
+                assert np.array_equal(ret[0][1][mode][0][k], ret[0][1][mode][1][k]), f"mode {mode}: {k} differs between two frames"

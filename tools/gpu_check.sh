@@ -15,8 +15,7 @@ except Exception as ex: print("bench FAILED", ex)
 PY
   rm -f gpurun_out/scale_report.txt gpurun_out/scale_report.json
   timeout 400 python tools/scale_report.py --truth C3 > gpurun_out/check_scale.log 2>&1; grep -E "^==|work|dL_d|integer" gpurun_out/check_scale.log | cut -c1-330
-  timeout 300 python tools/debug_triangle.py C3 641034 295324 > gpurun_out/check_triangle.log 2>&1; cat gpurun_out/check_triangle.log | cut -c1-300
+  timeout 300 python tools/debug_outlier.py C3 > gpurun_out/check_outlier.log 2>&1; grep -E "^dL|tri " gpurun_out/check_outlier.log | head -16 | cut -c1-200
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-model-step > gpurun_out/ncu_launch.log 2>&1
   python tools/ncu_launches.py gpurun_out/launches.csv
-  timeout 500 ncu --set full --clock-control none --import-source on -k regex:"k_render_bwd_fast|k_radix_pass|k_bwd_rows_mark|k_scan_u8|k_render_fwd_fast" --launch-skip 12 -c 14 -o gpurun_out/prof_r02 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-model-step > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log | cut -c1-200; ls -la gpurun_out/prof_r02.ncu-rep
 fi

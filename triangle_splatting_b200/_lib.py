@@ -118,7 +118,7 @@ SYMBOLS = {
 
 ABI_VERSION = 5  # TS2D_ABI_VERSION (include/ts2d.h)
 PRIMITIVES = {"2D": 0, "3D": 1}  # TS2D_PRIMITIVE_* (include/ts2d.h)
-STAGES = ("preprocess", "order_scan", "binning", "render_fwd", "render_bwd", "preprocess_bwd")
+STAGES = ("preprocess", "order_scan", "binning", "render_fwd", "render_bwd", "preprocess_bwd", "bwd_prepare", "bwd_reduce")
 
 
 def lib_path() -> Path:

@@ -443,16 +443,12 @@ int backward_composite_impl(const ts2d_camera *cam, const ts2d_geometry *geom, c
     const int sb = ts2d_sorted_buf(n_tiles);
     if (ts2d_use_fast(geom, flags)) {
         if (sc.rows_cap <= 0) return TS2D_E_STATE_SIZE;
-        {
-            StageTimer t(TS2D_STAGE_RENDER_BWD, s);
-            int rc = ts2d_launch_bwd_rows_prepare(cam, flags, gs, bs, is, sc, s);
-            if (rc) return rc;
-            rc = flags->primitive == TS2D_PRIMITIVE_3D ? ts2d_launch_render3d_bwd_fast(cam, geom, flags, gs, bs.tkey[sb], bs.tval[sb], is, loss, sc, s)
-                                                       : ts2d_launch_render_bwd_fast(cam, geom, flags, gs, bs.tkey[sb], bs.tval[sb], is, loss, sc, s);
-            if (rc) return rc;
-            rc = ts2d_launch_bwd_rows_reduce(geom->P, gs, sc, s);
-            if (rc) return rc;
-        }
+        TS2D_STAGE(TS2D_STAGE_BWD_PREPARE, ts2d_launch_bwd_rows_prepare(cam, flags, gs, bs, is, sc, s));
+        if (flags->primitive == TS2D_PRIMITIVE_3D)
+            TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render3d_bwd_fast(cam, geom, flags, gs, bs.tkey[sb], bs.tval[sb], is, loss, sc, s));
+        else
+            TS2D_STAGE(TS2D_STAGE_RENDER_BWD, ts2d_launch_render_bwd_fast(cam, geom, flags, gs, bs.tkey[sb], bs.tval[sb], is, loss, sc, s));
+        TS2D_STAGE(TS2D_STAGE_BWD_REDUCE, ts2d_launch_bwd_rows_reduce(geom->P, gs, sc, s));
         return dbg_sync(flags, s);
     }
     TS2D_CUDA_TRY(cudaMemsetAsync(sc.gacc, 0, sizeof(float) * GACC_STRIDE * (size_t)geom->P, s));

@@ -138,7 +138,7 @@ int hist_blocks(int64_t n) { return (int)((n + 4095) / 4096 < 592 ? ((n + 4095) 
 }  // namespace
 
 size_t ts2d_sort_status_bytes(int64_t n_cap) { return ts2d_align_up(rs_status_bytes(n_cap), 256); }
-size_t ts2d_scan_status_bytes(int64_t n_cap) { return ts2d_align_up((size_t)sc_tiles(n_cap > 0 ? n_cap : 1) * sizeof(unsigned long long), 256); }
+size_t ts2d_scan_status_bytes(int64_t n_cap) { return ts2d_align_up((size_t)sc_tiles(n_cap > 0 ? n_cap : 1) * sizeof(unsigned long long), 256); }  // block sums of ts2d_scan (u32; sized generously)
 
 // K2/K3: depth order of the triangles (stable LSD radix sort of the 32-bit depth patterns, triangle id as the payload), scan of
 // tiles-touched in that order (-> offs, and R in the header).
@@ -174,9 +174,8 @@ int ts2d_launch_order_and_scan(int32_t P, GeomState gs, int64_t *R_host, cudaStr
         a.pass_uid = (uint32_t)(d + 1);
         k_radix_pass<<<(unsigned)rs_tiles(P), RS_THREADS, 0, s>>>(a);
     }
-    k_scan_gather<<<(unsigned)sc_tiles(P), RS_THREADS, 0, s>>>(gs.ids2, gs.tiles, gs.offs, P, gs.sstatus, &gs.hdr->tickets[TS2D_TICKET_SCAN],
-                                                             &gs.hdr->num_rendered);
-    TS2D_CUDA_TRY(cudaGetLastError());
+    TS2D_CUDA_TRY((ts2d_scan<LoadGatherU32, true>(LoadGatherU32{gs.ids2, gs.tiles}, nullptr, P, reinterpret_cast<uint32_t *>(gs.sstatus), gs.offs,
+                                                   &gs.hdr->num_rendered, false, s)));
     if (R_host) {
         int64_t R = 0;
         TS2D_CUDA_TRY(cudaMemcpyAsync(&R, &gs.hdr->num_rendered, sizeof(int64_t), cudaMemcpyDeviceToHost, s));

@@ -12,7 +12,7 @@
 //                      below the sub-tile's own last contributor `lastw`), written back into the instance key (the backward
 //                      kernel reads them there); emission index ei of the instance (from estart[id] and the tile's place in
 //                      the triangle's rect) -> ei[pos], popcount -> cnt[ei]
-//   k_scan_u8          exclusive scan of cnt over emission indices -> sbase (row of emission index e starts at sbase[e])
+//   ts2d_scan          exclusive scan of cnt over emission indices -> sbase (row of emission index e starts at sbase[e])
 //   composite backward row of (pos, sub-tile w) = sbase[ei[pos]] + popc(live bits below w): one 16-byte store per quarter-lane
 //   k_bwd_rows_reduce  64 depth ranks per block: streams their (contiguous) rows through shared memory, 4 lanes per triangle sum its
 //                      rows in row order into the 64 B accumulator line K9 reads (zeros for triangles without rows: no memset either)
@@ -20,91 +20,66 @@
 
 namespace {
 
+// MK positions per thread, every dependent-load stage issued for all of them before the next one: the kernel is a chain of
+// gathers (key -> tile -> ranges / lastw, list -> rect / estart) and latency-bound at one position per thread (ncu: 34 of 41 stall
+// cycles per issue on the long scoreboard).
+constexpr int MK = 4;
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_bwd_rows_mark(const int64_t *__restrict__ n_dev, int64_t cap, int gx, int shard_rank, int shard_world, uint32_t *tkey, const uint32_t *__restrict__ list,
                 const uint2 *__restrict__ ranges, const uint32_t *__restrict__ lastw, const ushort4 *__restrict__ rect,
                 const uint32_t *__restrict__ estart, uint32_t *__restrict__ ei_out, uint8_t *__restrict__ cnt)
 {
     const int64_t R = rs_count(n_dev, cap);
-    const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= R) return;
-    const uint32_t key = tkey[pos];
-    const uint32_t tile = key >> TS2D_MASK_BITS;
-    const uint32_t rel = (uint32_t)pos - ranges[tile].x;
-    const uint4 l0 = __ldg(reinterpret_cast<const uint4 *>(lastw + 8 * (size_t)tile)), l1 = __ldg(reinterpret_cast<const uint4 *>(lastw + 8 * (size_t)tile) + 1);
-    uint32_t live = key & 0xFFu;
-    live &= (rel < l0.x ? 1u : 0u) | (rel < l0.y ? 2u : 0u) | (rel < l0.z ? 4u : 0u) | (rel < l0.w ? 8u : 0u) | (rel < l1.x ? 16u : 0u) |
-            (rel < l1.y ? 32u : 0u) | (rel < l1.z ? 64u : 0u) | (rel < l1.w ? 128u : 0u);
-    if (live != (key & 0xFFu)) tkey[pos] = (key & ~0xFFu) | live;
-    const uint32_t id = list[pos];
-    const ushort4 rc = rect[id];
-    const uint32_t ty = tile / (uint32_t)gx, tx = tile - ty * (uint32_t)gx;
-    uint32_t k;
-    if (shard_world == 1) {
-        k = (ty - rc.y) * (uint32_t)(rc.z - rc.x) + (tx - rc.x);
-    } else {  // k-th OWNED tile of the rect, row-major (the order k_emit_warp<.., true> deals them in)
-        const uint32_t world = (uint32_t)shard_world, rank = (uint32_t)shard_rank;
-        k = 0;
-        for (uint32_t y = rc.y; y < ty; y++) {
-            const uint32_t x0 = rc.x + (rank + world - (y * (uint32_t)gx + rc.x) % world) % world;
-            k += x0 < rc.z ? (rc.z - x0 + world - 1) / world : 0u;
+    const int64_t p0 = (int64_t)blockIdx.x * (blockDim.x * MK) + threadIdx.x;
+    uint32_t key[MK], id[MK];
+    bool ok[MK];
+#pragma unroll
+    for (int u = 0; u < MK; u++) {
+        const int64_t pos = p0 + (int64_t)u * blockDim.x;
+        ok[u] = pos < R;
+        key[u] = ok[u] ? tkey[pos] : 0u;
+        id[u] = ok[u] ? list[pos] : 0u;
+    }
+    uint32_t first[MK], est[MK];
+    uint4 l0[MK], l1[MK];
+    ushort4 rc[MK];
+#pragma unroll
+    for (int u = 0; u < MK; u++) {
+        const uint32_t tile = key[u] >> TS2D_MASK_BITS;
+        first[u] = ok[u] ? ranges[tile].x : 0u;
+        l0[u] = ok[u] ? __ldg(reinterpret_cast<const uint4 *>(lastw + 8 * (size_t)tile)) : make_uint4(0, 0, 0, 0);
+        l1[u] = ok[u] ? __ldg(reinterpret_cast<const uint4 *>(lastw + 8 * (size_t)tile) + 1) : make_uint4(0, 0, 0, 0);
+        rc[u] = ok[u] ? rect[id[u]] : make_ushort4(0, 0, 1, 1);
+        est[u] = ok[u] ? estart[id[u]] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < MK; u++) {
+        if (!ok[u]) continue;
+        const int64_t pos = p0 + (int64_t)u * blockDim.x;
+        const uint32_t tile = key[u] >> TS2D_MASK_BITS;
+        const uint32_t rel = (uint32_t)pos - first[u];
+        uint32_t live = key[u] & 0xFFu;
+        live &= (rel < l0[u].x ? 1u : 0u) | (rel < l0[u].y ? 2u : 0u) | (rel < l0[u].z ? 4u : 0u) | (rel < l0[u].w ? 8u : 0u) | (rel < l1[u].x ? 16u : 0u) |
+                (rel < l1[u].y ? 32u : 0u) | (rel < l1[u].z ? 64u : 0u) | (rel < l1[u].w ? 128u : 0u);
+        if (live != (key[u] & 0xFFu)) tkey[pos] = (key[u] & ~0xFFu) | live;
+        const uint32_t ty = tile / (uint32_t)gx, tx = tile - ty * (uint32_t)gx;
+        const ushort4 r = rc[u];
+        uint32_t k;
+        if (shard_world == 1) {
+            k = (ty - r.y) * (uint32_t)(r.z - r.x) + (tx - r.x);
+        } else {  // k-th OWNED tile of the rect, row-major (the order k_emit_warp<.., true> deals them in)
+            const uint32_t world = (uint32_t)shard_world, rank = (uint32_t)shard_rank;
+            k = 0;
+            for (uint32_t y = r.y; y < ty; y++) {
+                const uint32_t x0 = r.x + (rank + world - (y * (uint32_t)gx + r.x) % world) % world;
+                k += x0 < r.z ? (r.z - x0 + world - 1) / world : 0u;
+            }
+            const uint32_t x0 = r.x + (rank + world - (ty * (uint32_t)gx + r.x) % world) % world;
+            k += (tx - x0) / world;
         }
-        const uint32_t x0 = rc.x + (rank + world - (ty * (uint32_t)gx + rc.x) % world) % world;
-        k += (tx - x0) / world;
-    }
-    const uint32_t e = estart[id] + k;
-    ei_out[pos] = e;
-    if (e < cap) cnt[e] = (uint8_t)__popc(live);
-}
-
-// exclusive scan of n (device-side) bytes -> out[0..n], out[n] = total; same chained look-back as k_scan_gather
-__global__ void __launch_bounds__(RS_THREADS)
-k_scan_u8(const uint8_t *__restrict__ src, uint32_t *__restrict__ out, const int64_t *__restrict__ n_dev, int64_t cap, unsigned long long *status,
-          uint32_t *ticket)
-{
-    __shared__ uint32_t s_w[RS_WARPS];
-    __shared__ uint32_t s_tile, s_excl;
-    const int64_t n = rs_count(n_dev, cap);
-    const int tid = threadIdx.x;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const int64_t base = (int64_t)tile * SC_TILE;
-    if (base >= n) return;
-    uint32_t v[SC_ITEMS], sum = 0;
-    const int64_t e0 = base + (int64_t)tid * SC_ITEMS;
-    if (e0 + SC_ITEMS <= n) {  // 16 consecutive bytes, 16-byte aligned (cnt is 256-byte aligned, SC_ITEMS == 16)
-        const uint4 w = *reinterpret_cast<const uint4 *>(src + e0);
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = (ww[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-    } else {
-#pragma unroll
-        for (int i = 0; i < SC_ITEMS; i++) v[i] = (e0 + i < n) ? src[e0 + i] : 0u;
-    }
-#pragma unroll
-    for (int i = 0; i < SC_ITEMS; i++) sum += v[i];
-    uint32_t total;
-    uint32_t excl = block_excl_scan256(sum, s_w, &total);
-    if (tid == 0) {
-        const unsigned long long tagP = 1ull << 32, tagI = 2ull << 32;
-        uint32_t look = 0;
-        if (tile == 0) {
-            st_relaxed_u64(status, tagI | total);
-        } else {
-            st_relaxed_u64(status + tile, tagP | total);
-            look = lookback_sum(status, (int64_t)tile - 1, 1, tagP, tagI);
-            st_relaxed_u64(status + tile, tagI | (unsigned long long)(look + total));
-        }
-        s_excl = look;
-        if (base + SC_TILE >= n) out[n] = look + total;
-    }
-    __syncthreads();
-    excl += s_excl;
-#pragma unroll
-    for (int i = 0; i < SC_ITEMS; i++) {
-        if (e0 + i < n) out[e0 + i] = excl;
-        excl += v[i];
+        const uint32_t e = est[u] + k;
+        ei_out[pos] = e;
+        if (e < cap) cnt[e] = (uint8_t)__popc(live);
     }
 }
 
@@ -194,13 +169,12 @@ int ts2d_launch_bwd_rows_prepare(const ts2d_camera *cam, const ts2d_flags *f, Ge
     const int sbuf = ts2d_sorted_buf(gx * gy);
     const int64_t *n_dev = &gs.hdr->num_rendered;
     if (bs.cap <= 0) return 0;
-    TS2D_CUDA_TRY(cudaMemsetAsync(sc.sstatus, 0, sc.sstatus_bytes, s));
-    TS2D_CUDA_TRY(cudaMemsetAsync(&gs.hdr->render.tickets[TS2D_TICKET_BWD_SCAN], 0, sizeof(uint32_t), s));
-    k_bwd_rows_mark<<<(unsigned)((bs.cap + TS2D_BLOCK - 1) / TS2D_BLOCK), TS2D_BLOCK, 0, s>>>(n_dev, bs.cap, gx, f->shard_rank, f->shard_world, bs.tkey[sbuf],
+    k_bwd_rows_mark<<<(unsigned)((bs.cap + TS2D_BLOCK * MK - 1) / (TS2D_BLOCK * MK)), TS2D_BLOCK, 0, s>>>(n_dev, bs.cap, gx, f->shard_rank, f->shard_world, bs.tkey[sbuf],
                                                                                              bs.tval[sbuf], is.ranges, is.lastw, gs.rect, gs.estart,
                                                                                              sc.ei, sc.cnt);
-    k_scan_u8<<<(unsigned)sc_tiles(bs.cap), RS_THREADS, 0, s>>>(sc.cnt, sc.sbase, n_dev, bs.cap, sc.sstatus, &gs.hdr->render.tickets[TS2D_TICKET_BWD_SCAN]);
-    return (int)cudaGetLastError();
+    TS2D_CUDA_TRY(cudaGetLastError());
+    // sbase = exclusive scan of cnt over emission indices, sbase[R] = number of rows
+    return (int)ts2d_scan<LoadU8, false>(LoadU8{sc.cnt}, n_dev, bs.cap, reinterpret_cast<uint32_t *>(sc.sstatus), sc.sbase, nullptr, true, s);
 }
 
 int ts2d_launch_bwd_rows_reduce(int32_t P, GeomState gs, BwdScratch sc, cudaStream_t s)
