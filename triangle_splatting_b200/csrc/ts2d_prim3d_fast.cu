@@ -290,7 +290,7 @@ k_render3d_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world
 // ------------------------------------------------------------------------------------------------ K8 (3D, fast)
 constexpr int B3_CAP = 16;      // entries staged per round
 constexpr int B3_ROWS = 8;      // triangles per phase-2 panel
-constexpr int B3_NS = 6;        // parked scalars per pair: contrib, dL/dop term, u1, u2 (D routed to the arg-min barycentric), a1, a2
+constexpr int B3_NS = 5;        // parked scalars per pair: contrib, dL/dop term, D | arg-min, a1, a2
 constexpr int B3_WROW = B3_NS * 32 + 1;
 
 // Per-warp shared-memory block:
@@ -340,16 +340,18 @@ static __device__ __noinline__ void bwd3_flush_panel(uint32_t wb, uint32_t ib, u
         const uint32_t frow = fb + f_row(quarter * 8);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const float c = lds32f(row + 4 * i), w1 = lds32f(row + 4 * (32 + i));
-            // D routed by the walk: (u1, u2) = (D, 0), (0, D), (-D, -D) for the arg-min a1, a2, a3  [da3 = -da1 - da2]  (not packed
-            // into D's mantissa LSBs: that perturbed every term by a biased 3.6e-7, see ts2d_render_bwd_fast.cu)
-            const float u1 = lds32f(row + 4 * (64 + i)), u2 = lds32f(row + 4 * (96 + i));
-            const float a1 = lds32f(row + 4 * (128 + i)), a2 = lds32f(row + 4 * (160 + i));
+            const float c = lds32f(row + 4 * i), w1 = lds32f(row + 4 * (32 + i)), Dp = lds32f(row + 4 * (64 + i));
+            const float a1 = lds32f(row + 4 * (96 + i)), a2 = lds32f(row + 4 * (128 + i));
             const float4 f0 = lds128(frow + 32 * i);
             s_c0 = fmaf(c, f0.x, s_c0);
             s_c1 = fmaf(c, f0.y, s_c1);
             s_c2 = fmaf(c, f0.z, s_c2);
             s_op += w1;
+            // arg-min barycentric (1, 2, 3) in the two LSBs of D: (u1, u2) = (D, 0), (0, D), (-D, -D)  [da3 = -da1 - da2]
+            const uint32_t db = __float_as_uint(Dp);
+            const bool to1 = (db & 1u) != 0u, to2 = (db & 2u) != 0u;
+            const float Ds = (to1 && to2) ? -Dp : Dp;
+            const float u1 = to1 ? Ds : 0.0f, u2 = to2 ? Ds : 0.0f;
             const float a3 = 1.0f - a1 - a2;
             U1 += u1;
             U1a1 = fmaf(u1, a1, U1a1);
@@ -480,7 +482,7 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
         for (int j = 0; j < count; j++, ea += F3_EB) {
             const float4 e0 = lds128(ea), e1 = lds128(ea + 16), e2 = lds128(ea + 32), e4 = lds128(ea + 64);
             const uint32_t pos = __float_as_uint(e4.w);
-            float w_c = 0.0f, w_op = 0.0f, w_u1 = 0.0f, w_u2 = 0.0f, w_a1 = 0.0f, w_a2 = 0.0f;
+            float w_c = 0.0f, w_op = 0.0f, w_D = 0.0f, w_a1 = 0.0f, w_a2 = 0.0f;
             bool visited = false;  // NOT "contrib != 0": the backward's cut is on G, so a pair with op == 0 still feeds dL/dop
             if (pos < last) {
                 const Tri3 t = unpack3(e0, e1, e2);
@@ -519,9 +521,8 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
                         const float dL_dpower = (og < 0.99f) ? dL_dalpha * e.alpha : 0.0f;
                         const float D = -3.0f * dL_dpower * gk.two_gamma * e.power * rcp_approx(e.ecc + TS2D_EPS);
                         // sub-gradient of min: first arg-min in the order a1, a2, a3 (R3D/src/backward.cu:389-399)
-                        const bool m1 = e.a1 <= e.a2 && e.a1 <= e.a3, m2 = !m1 && e.a2 <= e.a1 && e.a2 <= e.a3;
-                        w_u1 = m1 ? D : (m2 ? 0.0f : -D);
-                        w_u2 = m2 ? D : (m1 ? 0.0f : -D);
+                        const uint32_t sel = (e.a1 <= e.a2 && e.a1 <= e.a3) ? 1u : ((e.a2 <= e.a1 && e.a2 <= e.a3) ? 2u : 3u);
+                        w_D = __uint_as_float((__float_as_uint(D) & ~3u) | sel);
                         w_a1 = e.a1;
                         w_a2 = e.a2;
                     }
@@ -531,10 +532,9 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
             const uint32_t row = sb + L::W + (prow * B3_WROW + lane) * 4;
             sts32f(row, w_c);
             sts32f(row + 128, w_op);
-            sts32f(row + 256, w_u1);
-            sts32f(row + 384, w_u2);
-            sts32f(row + 512, w_a1);
-            sts32f(row + 640, w_a2);
+            sts32f(row + 256, w_D);
+            sts32f(row + 384, w_a1);
+            sts32f(row + 512, w_a2);
             {   // row info for phase 2; every lane stores the same words
                 const uint32_t ia = sb + L::INFO + prow * B3_INFO;
                 sts128(ia, e0);

@@ -8,8 +8,8 @@
 //
 // What is different from the reference is how the per-pair contributions are summed over pixels.  The reference
 // issues 10-16 global atomics per contributing (pixel, triangle) pair.  Here every one of the 16 per-triangle
-// outputs is written as  sum_p w(p) * f(p)  where w is one of only FOUR per-pair scalars that depend on the
-// sequential walk (contrib = alpha T, dL/dalpha * G, and D = dL/d ecc routed to the arg-min barycentric: u1, u2) and
+// outputs is written as  sum_p w(p) * f(p)  where w is one of only THREE per-pair scalars that depend on the
+// sequential walk (contrib = alpha T, dL/dalpha * G, and D = dL/d ecc routed to the arg-min barycentric) and
 // f is a per-pixel constant (upstream gradients, pixel offsets) -- the barycentrics being affine in the pixel,
 // their Jacobians reduce to first moments (see ts2d_preprocess.cu: the moments -> vertex-gradient map).
 //   phase 1 (lane = pixel):    walk the staged entries, run the T / colour recurrences, park the three scalars of
@@ -26,13 +26,13 @@
 namespace {
 
 constexpr int BW_ROWS = 8;      // triangles per phase-2 panel
-constexpr int BW_WROW = 129;    // 4 scalars x 32 pixels + 1 pad word: conflict-free for both phases
+constexpr int BW_WROW = 97;     // 3 scalars x 32 pixels + 1 pad word: conflict-free for both phases
 
 // Per-warp shared-memory block (byte offsets from the warp's base address):
 //   ENT   entry j at j * EB: {v1.x v1.y v2.x v2.y} {v3.x v3.y 1/area2 op} {r g b id} [RICH: {n.x n.y n.z vd1} {vd2 vd3 pos -}]
 //   POS   non-RICH only: u32[32] list positions (RICH keeps them in the entry's spare word)
 //   F     per pixel {gp0 gp1 gp2 gd} {gn0 gn1 gn2 -}
-//   W     panel [8 rows][129]: [scalar * 32 + pixel]
+//   W     panel [8 rows][97]: [scalar * 32 + pixel]
 //   INFO  per panel row {v1 v2} {v3 1/area2 op} {id, row index}: what phase 2 needs to know about the triangle (48 B stride)
 template <bool RICH>
 struct BwdLayout {
@@ -84,16 +84,16 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
         for (int i = 0; i < 8; i++) {
             // pixel p = quarter * 8 + i (lane index of phase 1) inside the sub-tile: x = p & 7 = i, y = p >> 3 = quarter
             const float dxp = (float)i;  // x offset inside the sub-tile (an immediate); sub_x0 is added once after the loop
-            const float c = lds32f(row + 4 * i), w1 = lds32f(row + 4 * (32 + i));
-            // D already routed to ga_1 / ga_2 by the walk: (u1, u2) = (D, 0), (0, D) or (-D, -D) for the arg-min a1, a2, a3.  (An earlier
-            // version parked D with the arg-min in its two mantissa LSBs: a BIASED 3.6e-7 relative perturbation of every term -- six
-            // times fp32 rounding -- which showed as 20 .. 70 % errors on the few dL_dcenter2D entries whose terms cancel to 1e-4 of
-            // their size; the reference's per-term rounding is unbiased.)
-            const v2 u = mk2v(lds32f(row + 4 * (64 + i)), lds32f(row + 4 * (96 + i)));
+            const float c = lds32f(row + 4 * i), w1 = lds32f(row + 4 * (32 + i)), Dp = lds32f(row + 4 * (64 + i));
             const float4 f0 = lds128(frow + 32 * i);
             s_c01 = fma2(bc(c), mk2v(f0.x, f0.y), s_c01);
             s_c2 = fmaf(c, f0.z, s_c2);
             s_op += w1;
+            // arg-min barycentric (1, 2, 3) packed in the two LSBs: D goes to a1 (bit 0) and / or a2 (bit 1), negated when to a3 (both)
+            const uint32_t db = __float_as_uint(Dp);
+            const bool to1 = (db & 1u) != 0u, to2 = (db & 2u) != 0u;
+            const float Ds = (to1 && to2) ? -Dp : Dp;
+            const v2 u = mk2v(to1 ? Ds : 0.0f, to2 ? Ds : 0.0f);
             if (geo) {
                 const float4 f1 = lds128(frow + 32 * i + 16);
                 const float cg = c * f0.w;                       // contrib * gd
@@ -263,7 +263,7 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
         for (int j = 0; j < count; j++, ea += L::EB) {
             const float4 e1 = lds128(ea), e2 = lds128(ea + 16);
             const uint32_t pos = lds32(sb + L::POS + j * L::POS_STRIDE);
-            float w_c = 0.0f, w_op = 0.0f, w_u1 = 0.0f, w_u2 = 0.0f;
+            float w_c = 0.0f, w_op = 0.0f, w_D = 0.0f;
             if (pos < last) {
                 FastPair f;
                 bool unc;
@@ -278,6 +278,20 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                     if (hit) { f.power = e.power; f.G = e.G; f.og = __fmul_rn(e2.w, e.G); f.alpha = e.alpha; }
                 }
                 if (hit) {
+                    {   // The arg-min of (a1, a2, a3) is one more reference decision: dL/d min(a) goes to ONE barycentric, and near a
+                        // corner of a thin triangle the choice changes the vertex gradient by its own size.  The fast a1, a2 are
+                        // c * rn(1 / area2) where the reference divides (same c, bit for bit): |a_fast - a_ref| <= 1.5 * 2^-23 |a| for
+                        // a1 and a2, their sum plus two roundings at 1 for a3 = 1 - a1 - a2.  Within that band of a tie: exact values.
+                        const float lo12 = fminf(f.a1, f.a2), hi12 = fmaxf(f.a1, f.a2);
+                        const float second = fmaxf(lo12, fminf(hi12, f.a3));
+                        const float tie = fmaf(fabsf(f.a1) + fabsf(f.a2) + fabsf(f.a3), 0x1p-22f, 0x1p-22f);
+                        if (second - fminf(lo12, f.a3) <= tie) {
+                            const float area2 = __ldg(&rec0[3 * (size_t)lds32(ea + 44) + 2].w);
+                            PairEval e;
+                            (void)eval_exact(e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, area2, e2.w, gk.two_gamma, pxf, pyf, e);
+                            f.a1 = e.a1; f.a2 = e.a2; f.a3 = e.a3;
+                        }
+                    }
                     const float4 col = lds128(ea + 32);
                     const float om = 1.0f - f.alpha;
                     T = T * rcp_approx(om);
@@ -306,10 +320,8 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                     const float dL_dpower = (f.og < 0.99f) ? dL_dalpha * f.alpha : 0.0f;
                     const float D = -3.0f * dL_dpower * gk.two_gamma * f.power * rcp_approx(f.ecc + TS2D_EPS);
                     // sub-gradient of min: first arg-min in the order a1, a2, a3 (backward.cu:449-461)
-                    const bool m1 = f.a1 <= f.a2 && f.a1 <= f.a3, m2 = !m1 && f.a2 <= f.a1 && f.a2 <= f.a3;
-                    // ga_k = dL/da_k - dL/da_3: the arg-min a3 feeds both with the opposite sign
-                    w_u1 = m1 ? D : (m2 ? 0.0f : -D);
-                    w_u2 = m2 ? D : (m1 ? 0.0f : -D);
+                    const uint32_t sel = (f.a1 <= f.a2 && f.a1 <= f.a3) ? 1u : ((f.a2 <= f.a1 && f.a2 <= f.a3) ? 2u : 3u);
+                    w_D = __uint_as_float((__float_as_uint(D) & ~3u) | sel);
                 }
             }
             // every staged entry owns a row (its live bit is set), so every staged entry is flushed -- also when no pixel of the
@@ -317,8 +329,7 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
             const uint32_t row = sb + L::W + (prow * BW_WROW + lane) * 4;
             sts32f(row, w_c);
             sts32f(row + 128, w_op);
-            sts32f(row + 256, w_u1);
-            sts32f(row + 384, w_u2);
+            sts32f(row + 256, w_D);
             {   // row info for phase 2; every lane stores the same words (cheaper than electing one: no lane id, no predicate)
                 const uint32_t ia = sb + L::INFO + prow * 48;
                 sts128(ia, e1);

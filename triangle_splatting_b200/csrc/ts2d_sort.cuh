@@ -249,13 +249,36 @@ constexpr int SC_ITEMS = 16;
 constexpr int SC_TILE = RS_THREADS * SC_ITEMS;  // 4096 elements per block
 static inline int64_t sc_tiles(int64_t n) { return (n + SC_TILE - 1) / SC_TILE; }
 
+// A Load gives f(i) for the strided block-sum pass and block16() -- 16 consecutive elements starting at a multiple of 16, all below n --
+// for the thread-blocked apply pass (vector loads: one 16-byte load for bytes, four for the gathered indices).
 struct LoadGatherU32 {  // f(i) = src[order[i]]: tiles-touched in depth-rank order (rasterizer.cu:186)
     const uint32_t *order, *src;
     __device__ __forceinline__ uint32_t operator()(int64_t i) const { return src[order[i]]; }
+    __device__ __forceinline__ void block16(int64_t base, uint32_t (&v)[16]) const
+    {
+        const uint4 *o = reinterpret_cast<const uint4 *>(order + base);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint4 w = __ldg(o + q);
+            v[4 * q + 0] = src[w.x];
+            v[4 * q + 1] = src[w.y];
+            v[4 * q + 2] = src[w.z];
+            v[4 * q + 3] = src[w.w];
+        }
+    }
 };
 struct LoadU8 {
     const uint8_t *src;
     __device__ __forceinline__ uint32_t operator()(int64_t i) const { return src[i]; }
+    __device__ __forceinline__ void block16(int64_t base, uint32_t (&v)[16]) const
+    {
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(src + base));
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) v[4 * q + b] = (ws[q] >> (8 * b)) & 0xffu;
+    }
 };
 
 template <class Load>
@@ -312,18 +335,38 @@ k_scan_apply(Load f, const int64_t *n_dev, int64_t n_cap, const uint32_t *__rest
     const int64_t n = rs_count(n_dev, n_cap);
     const int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;  // thread t owns SC_ITEMS consecutive elements
     if ((int64_t)blockIdx.x * SC_TILE >= n) return;
+    static_assert(SC_ITEMS == 16, "block16");
     uint32_t v[SC_ITEMS], sum = 0;
+    const bool full = base + SC_ITEMS <= n;
+    if (full) {
+        f.block16(base, v);
+    } else {
 #pragma unroll
-    for (int i = 0; i < SC_ITEMS; i++) {
-        v[i] = (base + i < n) ? f(base + i) : 0u;
-        sum += v[i];
+        for (int i = 0; i < SC_ITEMS; i++) v[i] = (base + i < n) ? f(base + i) : 0u;
     }
-    uint32_t run = block_excl_scan256(sum, s_w, nullptr) + sums[blockIdx.x];
 #pragma unroll
-    for (int i = 0; i < SC_ITEMS; i++) {
-        if (INCLUSIVE) run += v[i];
-        if (base + i < n) out[base + i] = run;
-        if (!INCLUSIVE) run += v[i];
+    for (int i = 0; i < SC_ITEMS; i++) sum += v[i];
+    uint32_t run = block_excl_scan256(sum, s_w, nullptr) + sums[blockIdx.x];
+    if (full) {
+        uint4 *o = reinterpret_cast<uint4 *>(out + base);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t r[4];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                if (INCLUSIVE) run += v[4 * q + b];
+                r[b] = run;
+                if (!INCLUSIVE) run += v[4 * q + b];
+            }
+            o[q] = make_uint4(r[0], r[1], r[2], r[3]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < SC_ITEMS; i++) {
+            if (INCLUSIVE) run += v[i];
+            if (base + i < n) out[base + i] = run;
+            if (!INCLUSIVE) run += v[i];
+        }
     }
 }
 
