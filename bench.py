@@ -703,12 +703,13 @@ def main():
         from triangle_splatting_b200 import distributed as tsd
 
         used_fabric = tsd.fabric(dev) is not None
-        cfg["parallelism"] = (f"image-space tile sharding x{world} (tile % N == rank), strong scaling; forward exchange: "
-                              + ("NVLink peer memory inside K7 (multimem.st of the owned pixels into every replica, contrib statistics RED-ed into "
-                                 "the triangle's home replica, multimem publish of the home slices; symmetric-memory signal-pad barriers)"
-                                 if used_fabric else "NCCL all-reduce(sum) of the zero-filled frame planes + contrib_sum, all-reduce(max) of contrib_max")
-                              + "; backward exchange: NCCL all-reduce(sum) of the 64 B/triangle accumulators between K8 + row reduction and K9")
-        cfg["exchange"] = {"forward": "fabric" if used_fabric else "nccl", "backward": "nccl"}
+        cfg["parallelism"] = (f"image-space tile sharding x{world} (tile % N == rank), strong scaling; exchange: "
+                              + ("NVLink peer memory, kernels behind the composite kernels on the same stream: multimem.st of the owned tiles' 64-byte "
+                                 "rows into every replica; contrib statistics and the 64 B/triangle gradient accumulators combined per home slice "
+                                 "inside the switch (multimem.ld_reduce) and written back to every replica; two signal-pad rendezvous per pass"
+                                 if used_fabric else "NCCL all-reduce(sum) of the zero-filled frame planes + contrib_sum, all-reduce(max) of contrib_max; "
+                                 "NCCL all-reduce(sum) of the 64 B/triangle accumulators between K8 + row reduction and K9"))
+        cfg["exchange"] = {"forward": "fabric" if used_fabric else "nccl", "backward": "fabric" if used_fabric else "nccl"}
     radii = out[1]
     V = int((radii > 0).sum().item())
     N = sc.cam["image_width"] * sc.cam["image_height"]

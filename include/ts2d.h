@@ -58,7 +58,7 @@
 extern "C" {
 #endif
 
-#define TS2D_ABI_VERSION 5
+#define TS2D_ABI_VERSION 6
 #define TS2D_TILE 16          /* R2D/src/config.h:4-5  BLOCK_X = BLOCK_Y = 16 */
 #define TS2D_MAX_CHANNELS 3   /* R2D/src/config.h:3 */
 
@@ -77,7 +77,7 @@ enum {
     TS2D_E_SIZE = -11,         /* image or primitive count out of range */
     TS2D_E_PRIMITIVE = -12,    /* flags.primitive is neither TS2D_PRIMITIVE_2D nor TS2D_PRIMITIVE_3D */
     TS2D_E_MODEL = -13,        /* geometry.model / backward_out.model inconsistent (missing pointer, use_shs == 0, M == 0) */
-    TS2D_E_FABRIC = -14        /* flags.fabric with the mirror kernels / ts2d_backward(), bad world / home_chunk, or a required address missing */
+    TS2D_E_FABRIC = -14        /* ts2d_exchange_*: bad rank / world / operation, or a misaligned base, first or count */
 };
 
 /* R2D/src/param_struct.h:127-137 (CameraInfo).  Matrices are the 16 floats of the (contiguous)
@@ -160,28 +160,22 @@ typedef struct ts2d_flags {
                                   R3D/src/forward.cu:61-306, R3D/src/backward.cu:144-454).  Same entry points, same
                                   state blobs, same outputs; dL_dcenter2D is then the view-space xy of the summed
                                   vertex gradients (R3D/src/backward.cu:211-213). */
-    const struct ts2d_fabric *fabric;  /* NULL unless the ranks exchange through NVLink peer memory, see below */
 } ts2d_flags;
 
-/* Multi-GPU over NVLink peer memory (no counterpart in the reference).  The ranks of a tile-sharded render hold SYMMETRIC buffers
- * (same layout on every rank; cuMem + cuMulticast, e.g. torch symmetric memory) and the fast composite kernels exchange through them
- * while they run, instead of a collective afterwards:
- *   pixels        every rank stores the pixels of its own tiles into ALL replicas with multimem.st on the NVSwitch multicast alias
- *                 (*_mc) -- disjoint tiles, plain stores, bit-identical frames everywhere;
- *   reductions    contrib_sum / contrib_max of triangle i are reduced on ONE rank, its home  min(i / home_chunk, world - 1),
- *                 with red.global over that rank's peer mapping (peer tables below, index = rank): a single copy receives every
- *                 rank's partial values, so all ranks later read the same bits;
- *   publish       ts2d_fabric_publish(): the home rank copies its finished slice to every replica (multimem.st).
- * The caller owns the protocol: zero the reduced arrays on every replica, rendezvous, run the kernel, rendezvous, publish, rendezvous.
- * ts2d_forward_out then only carries `radii`.  Only the fast kernels (flags.exact == 0, gamma in their range) take this path.
- * The backward exchange is a sum of each rank's per-triangle accumulators in rank order (ts2d_backward_composite), see distributed.py. */
+/* Multi-GPU exchange over NVLink peer memory (no counterpart in the reference: it has no distributed code).  The composite kernels
+ * know nothing about other GPUs: a rank renders the tiles it owns (shard_rank / shard_world above) into ITS replica of a SYMMETRIC
+ * buffer (same layout on every rank, mapped by every peer and behind one NVSwitch multicast alias; cuMem + cuMulticast, e.g. torch
+ * symmetric memory), and two exchange kernels, launched behind them on the same stream, complete the frame and the sums everywhere:
+ *   ts2d_exchange_tiles      the 64-byte rows of the owned tiles of `n_planes` planar [H][W] images: replica -> every replica
+ *                            (multimem.st.v4; disjoint tiles, so all ranks end up with the same frame, bit for bit);
+ *   ts2d_exchange_allreduce  this rank's slice [first, first + count) of an array: combined over all replicas inside the switch
+ *                            (multimem.ld_reduce) and written back to all of them (multimem.st).  One rank computes each element and
+ *                            the switch combines in a fixed order: same bits on every rank and in every frame.
+ * The caller owns the protocol: rendezvous of the ranks after the local results are complete and before anybody publishes (which
+ * also says that nobody still reads the previous frame), exchange kernels, rendezvous.  Two rendezvous per pass. */
 #define TS2D_MAX_RANKS 8
-typedef struct ts2d_fabric {
-    int32_t world;                 /* ranks sharing the render, <= TS2D_MAX_RANKS */
-    int32_t home_chunk;            /* triangles per home slice (a multiple of 32) */
-    float *out_feature_mc, *depth_mc, *normal_mc;              /* multicast aliases of the image planes */
-    float *contrib_sum[TS2D_MAX_RANKS], *contrib_max[TS2D_MAX_RANKS];  /* peer addresses of every rank's replica */
-} ts2d_fabric;
+#define TS2D_EXCHANGE_ADD_F32 0   /* fp32 sum; first, count multiples of 4, 16-byte aligned base */
+#define TS2D_EXCHANGE_MAX_U32 1   /* u32 maximum (contrib_max: non-negative floats, bit order == value order) */
 
 #define TS2D_PRIMITIVE_2D 0
 #define TS2D_PRIMITIVE_3D 1
@@ -277,10 +271,12 @@ int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_
 /* ts2d_backward split in two for tile-sharded multi-GPU (no counterpart in the reference): each rank runs the composite
  * backward over its own tiles; the first 16 * P floats of `scratch` then hold its per-triangle partial sums (the reference's
  * dL_dv*_2D / dL_dnormal_view / dL_dv_depth / dL_drgb / dL_dopacity temporaries, rasterizer.cu:289-300, in this library's layout),
- * the caller sum-reduces those across ranks, then every rank runs the per-triangle stage on the sums. */
+ * the caller sum-reduces those across ranks, then every rank runs the per-triangle stage on the sums.  `accumulators` != NULL puts
+ * the 16 * P floats there instead (e.g. into a symmetric buffer for ts2d_exchange_allreduce); ts2d_backward_geometry reads them
+ * from wherever its `scratch` argument points. */
 int ts2d_backward_composite(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags,
                             const void *geometry_state, void *binning_state, size_t binning_state_bytes, const void *image_state,
-                            const ts2d_loss_in *loss, void *scratch, size_t scratch_bytes, void *stream);
+                            const ts2d_loss_in *loss, void *scratch, size_t scratch_bytes, float *accumulators, void *stream);
 int ts2d_backward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, const int32_t *radii,
                            const void *geometry_state, const ts2d_backward_out *out, const void *scratch, size_t scratch_bytes,
                            void *stream);
@@ -293,9 +289,11 @@ int ts2d_backward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, co
 int ts2d_downsample(const float *in, float *out, int32_t planes, int32_t out_width, int32_t out_height, int32_t s, void *stream);
 int ts2d_downsample_bwd(const float *dL_dout, float *dL_din, int32_t planes, int32_t out_width, int32_t out_height, int32_t s, void *stream);
 
-/* Copy local[first .. first + count) to the same range of every replica through the multicast alias (multimem.st); `first` and
- * `count` in floats, both multiples of 4, both pointers 16-byte aligned.  See ts2d_fabric. */
-int ts2d_fabric_publish(const float *local, float *multicast, int64_t first, int64_t count, void *stream);
+/* Multi-GPU exchange, see above.  `local` / `multicast`: this rank's replica and the multicast alias of the same symmetric buffer
+ * ([n_planes][height][width] floats for the tiles; element index `first` of the 4-byte array for the all-reduce). */
+int ts2d_exchange_tiles(const float *local, float *multicast, int32_t n_planes, int32_t width, int32_t height, int32_t rank, int32_t world,
+                        void *stream);
+int ts2d_exchange_allreduce(void *multicast, int64_t first, int64_t count, int32_t op, void *stream);
 
 /* Fused image loss on the rendered frame (first step):
  *     loss = w_l1 * mean|image - gt| + w_ssim * (1 - mean SSIM(image, gt))

@@ -25,7 +25,7 @@ def test_library_loads_and_exports_everything():
     lib = _lib.load()
     for name in _declared():
         assert hasattr(lib, name), name
-    assert lib.ts2d_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.ts2d_abi_version() == _lib.ABI_VERSION == 6
     assert b"vertex must have dimensions" in lib.ts2d_error_string(-1)
     assert lib.ts2d_error_string(0) == b"ok"
 
@@ -38,7 +38,7 @@ def test_ctypes_structs_match_the_header_layout():
 
     names = {"ts2d_camera": _lib.Camera, "ts2d_geometry": _lib.Geometry, "ts2d_flags": _lib.Flags, "ts2d_forward_out": _lib.ForwardOut,
              "ts2d_loss_in": _lib.LossIn, "ts2d_backward_out": _lib.BackwardOut, "ts2d_model_inputs": _lib.ModelInputs,
-             "ts2d_model_grads": _lib.ModelGrads, "ts2d_fabric": _lib.FabricC, "ts2d_frame_counters": _lib.FrameCounters}
+             "ts2d_model_grads": _lib.ModelGrads, "ts2d_frame_counters": _lib.FrameCounters}
     body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in names)
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "t.c")
@@ -88,7 +88,7 @@ def _dummy_call_structs(P=4, **geom_over):
              shs=fake, feature=None, opacity=fake, model=None)
     g.update(geom_over)
     geom = _lib.Geometry(**g)
-    flags = _lib.Flags(0, 1, 0, 0, 1, 0, 0, None)
+    flags = _lib.Flags(0, 1, 0, 0, 1, 0, 0)
     return cam, geom, flags, fake
 
 
@@ -118,17 +118,15 @@ def test_argument_errors_are_reported_before_any_device_work():
                                                      model=C.cast(C.pointer(mi), C.c_void_p))
         assert lib.ts2d_forward_geometry(C.byref(cam), C.byref(geom), C.byref(flags), fake, fake, 1 << 30, C.byref(R), None) == -13
     assert b"model inputs" in lib.ts2d_error_string(-13)
-    # peer-memory fabric: needs the fast kernels, 2 <= world <= 8, home_chunk % 32 == 0, the aliases the call writes
-    out = _lib.ForwardOut(None, fake, None, None, None, None)
-    for fab, exact in ((_lib.FabricC(world=2, home_chunk=32, out_feature_mc=0x2000), 1), (_lib.FabricC(world=1, home_chunk=32, out_feature_mc=0x2000), 0),
-                       (_lib.FabricC(world=2, home_chunk=33, out_feature_mc=0x2000), 0), (_lib.FabricC(world=2, home_chunk=32), 0),
-                       (_lib.FabricC(world=2, home_chunk=32, out_feature_mc=0x2000), 0)):  # last: rich_info without depth / normal aliases
-        cam, geom, flags, fake = _dummy_call_structs()
-        flags.exact, flags.fabric = exact, C.cast(C.pointer(fab), C.c_void_p)
-        assert lib.ts2d_forward_render(C.byref(cam), C.byref(geom), C.byref(flags), 10, fake, fake, 1 << 30, fake, 1 << 30, C.byref(out), None, None) == -14
-        assert lib.ts2d_forward(C.byref(cam), C.byref(geom), C.byref(flags), fake, fake, 1 << 30, fake, 1 << 30, fake, 1 << 30, C.byref(out), None, None) == -14
+    # exchange kernels: 2 <= world <= 8, 0 <= rank < world, known operation, aligned base / first / count -- checked before any launch
+    for args in ((fake, fake, 7, 64, 64, 0, 1), (fake, fake, 7, 64, 64, 2, 2), (fake, fake, 7, 64, 64, 0, 9), (fake, C.c_void_p(0x1004), 7, 64, 64, 0, 2)):
+        assert lib.ts2d_exchange_tiles(*args, None) == -14, args
+    assert lib.ts2d_exchange_tiles(None, fake, 7, 64, 64, 0, 2, None) == -7
+    for args in ((fake, 2, 8, 0), (fake, 0, 6, 0), (fake, 0, 8, 5), (C.c_void_p(0x1004), 0, 8, 0), (fake, -4, 8, 1)):
+        assert lib.ts2d_exchange_allreduce(*args, None) == -14, args
+    assert lib.ts2d_exchange_allreduce(fake, 0, 0, 0, None) == 0  # empty slice: nothing to do
     loss = _lib.LossIn(fake, fake, fake)
-    assert b"fabric" in lib.ts2d_error_string(-14)
+    assert b"ts2d_exchange" in lib.ts2d_error_string(-14)
     # state blobs too small for what they must hold
     cam, geom, flags, fake = _dummy_call_structs()
     out = _lib.ForwardOut(fake, fake, fake, fake, fake, fake)
@@ -142,8 +140,6 @@ def test_argument_errors_are_reported_before_any_device_work():
     cam, geom, flags, fake = _dummy_call_structs()
     assert lib.ts2d_backward(C.byref(cam), C.byref(geom), C.byref(flags), fake, fake, fake, 1 << 20, fake, C.byref(loss), C.byref(bout), fake, 1 << 30, None) == -13
     # small utilities
-    assert lib.ts2d_fabric_publish(None, fake, 0, 16, None) == -7
-    assert lib.ts2d_fabric_publish(fake, fake, 2, 16, None) == -14 and lib.ts2d_fabric_publish(fake, fake, 0, 0, None) == 0
     assert lib.ts2d_downsample(None, fake, 1, 8, 8, 2, None) == -7 and lib.ts2d_downsample(fake, fake, 0, 8, 8, 2, None) == -11
     assert lib.ts2d_downsample_bwd(fake, fake, 1, 8, 8, 0, None) == -11
     # P == 0 short-circuits (extension_interface.cu:130)

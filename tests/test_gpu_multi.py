@@ -1,9 +1,10 @@
 """Multi-GPU parity (needs >= 2 GPUs; `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`).
 
-One process per GPU over NCCL: every rank composites only the tiles it owns (tile % world == rank), the frame is
-assembled with an all-reduce, the per-triangle gradient accumulators are all-reduced between the composite and the
-per-triangle backward.  Every rank must end up with the single-GPU result: forward outputs to fp32 rounding of the
-all-reduce (exact for disjoint tiles: x + 0), gradients up to the re-association of the per-triangle sums (per rank, then over ranks).
+One process per GPU: every rank composites only the tiles it owns (tile % world == rank); the frame is assembled and the
+per-triangle gradient accumulators are summed between the composite and the per-triangle backward -- by NCCL all-reduces
+(TS2D_FABRIC=0) or by the exchange kernels over NVLink peer memory (include/ts2d.h: ts2d_exchange_tiles / ts2d_exchange_allreduce).
+Every rank must end up with the single-GPU result: pixels bit for bit (disjoint tiles: copies, or x + 0), gradients up to the
+re-association of the per-triangle sums (per rank, then over ranks).
 Worlds 4 and 8 run when the box has that many GPUs (`gpurun --gpus 8`)."""
 import os
 import socket
@@ -60,7 +61,7 @@ def _worker(rank, world, port, ret):
                                                                             geometry_grads=True, seed=17)
         single = _run(sc, dev)  # sharding off: the single-GPU answer, computed on this very GPU
         res = {}
-        for mode in ("0", "auto"):  # NCCL collectives / NVLink peer memory (multicast pixel stores + home-rank reductions)
+        for mode in ("0", "auto"):  # NCCL collectives / NVLink peer memory (multicast tile rows + in-switch reductions of the home slices)
             os.environ["TS2D_FABRIC"] = mode
             tsd.enable_tile_sharding()
             sharded = _run(sc, dev)
@@ -95,9 +96,10 @@ def test_tile_sharded_render_matches_single_gpu(world):
                 assert rel_err(sharded["contrib_sum"], single["contrib_sum"]) <= 1e-5, what
                 for k in ("dL_dvertex", "dL_dshs", "dL_dopacity", "dL_dcenter2D"):
                     # the per-triangle sums are the same numbers added in another order (per rank first, then over the ranks): fp32
-                    # re-association only -- 99.9 % of the entries within 1e-5, every entry within 5e-2 of max(|g|, 1e-3 RMS)
-                    q = harness.err_quantiles(sharded[k], single[k], (0.999, 1.0))
-                    assert q[0] <= 1e-5 and q[1] <= 5e-2, f"{what}: {k}: {q}"
+                    # re-association only -- 99 % of the entries within 1e-5, 99.9 % within 1e-4, every entry within 5e-2 of
+                    # max(|g|, 1e-3 RMS)  (measured on the 2 000-triangle scene, world 2: 2.0e-5 at 99.9 %, 2.0e-4 in the maximum)
+                    q = harness.err_quantiles(sharded[k], single[k], (0.99, 0.999, 1.0))
+                    assert q[0] <= 1e-5 and q[1] <= 1e-4 and q[2] <= 5e-2, f"{what}: {k}: {q}"
             # all ranks hold the same frame and the same gradients, bit for bit (replicated optimizers must not drift apart) ...
             for r in range(1, world):
                 a, b = ret[0][1][mode][frame], ret[r][1][mode][frame]
@@ -105,5 +107,4 @@ def test_tile_sharded_render_matches_single_gpu(world):
                     assert np.array_equal(a[k], b[k]), f"mode {mode} frame {frame}: ranks 0 and {r} disagree on {k}"
         # ... and two consecutive frames of the same scene are bit-identical too (no atomics in the gradient path, fixed-order exchange)
         for k in ret[0][1][mode][0]:
-            if k != "contrib_sum" or mode == "0":  # over the fabric contrib_sum is a float RED into the home replica
-                assert np.array_equal(ret[0][1][mode][0][k], ret[0][1][mode][1][k]), f"mode {mode}: {k} differs between two frames"
+            assert np.array_equal(ret[0][1][mode][0][k], ret[0][1][mode][1][k]), f"mode {mode}: {k} differs between two frames"

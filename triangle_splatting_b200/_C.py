@@ -135,14 +135,20 @@ class ModelInputs:
 STAT_FIELDS = ("gradient_accum", "gradient_denom", "contrib_sum", "contrib_max", "contrib_denom", "max_radii2D")
 
 
-def _fabric_for(shard, gamma, dev):
-    """NVLink peer-memory fabric for a tile-sharded call, or None (then NCCL collectives above this module do the exchange).
-    Only the fast kernels write through multicast addresses (same condition as ts2d_use_fast in ts2d_common.cuh)."""
-    if shard[1] <= 1 or EXACT or not (0.6 <= float(gamma) <= 64.0):
+def _fabric_for(shard, dev):
+    """NVLink peer-memory fabric for a tile-sharded call, or None (then NCCL collectives above this module do the exchange)."""
+    if shard[1] <= 1:
         return None
     from . import distributed
 
     return distributed.fabric(dev)
+
+
+def _home_slice(n4: int, rank: int, world: int):
+    """This rank's slice (first, count) of an array of n4 (a multiple of 4) four-byte elements, both multiples of 4."""
+    chunk = ((n4 + world - 1) // world + 3) // 4 * 4
+    first = min(rank * chunk, n4)
+    return first, min(chunk, n4 - first)
 
 
 def _ptr(t: torch.Tensor | None):
@@ -243,18 +249,23 @@ def rasterize_triangles(image_width: int, image_height: int, tan_fovx: float, ta
     sharded = shard[1] > 1
     alloc = torch.zeros if (P == 0 or sharded) else torch.empty  # every owned pixel is written by the composite kernel
     radii = torch.zeros((P,), device=dev, dtype=torch.int32) if P == 0 else torch.empty((P,), device=dev, dtype=torch.int32)
-    fab = _fabric_for(shard, gamma, dev) if (sharded and P > 0) else None
+    fab = _fabric_for(shard, dev) if (sharded and P > 0) else None
     if fab is not None:
-        # NVLink peer memory (include/ts2d.h: ts2d_fabric): one symmetric buffer [image | depth | normal | contrib_sum | contrib_max]
-        # per rank.  K7 stores its tiles' pixels into every replica through the multicast alias and REDs contrib_sum / contrib_max
-        # into each triangle's home replica, which is then published to all: the frame is complete without a collective.
+        # NVLink peer memory (include/ts2d.h: "Multi-GPU exchange"): the outputs live in this rank's replica of ONE symmetric buffer
+        # [image | depth | normal | pad | contrib_sum | contrib_max]; the composite kernel fills the owned tiles and this rank's partial
+        # contrib statistics, the exchange kernels behind it complete every replica -- no collective, no zero-filled planes
         n_img, n_pix = Cn * H * W, H * W
         pad4 = lambda n: (n + 3) // 4 * 4
-        sizes = [pad4(n_img), pad4(n_pix), pad4(3 * n_pix), pad4(P), pad4(P)] if rich_info else [pad4(n_img)]
-        offs = [sum(sizes[:i]) for i in range(len(sizes) + 1)]
-        frame, mc_base, fab_h = fab.buffer("frame", offs[-1])
-        home_chunk = ((P + shard[1] - 1) // shard[1] + 31) // 32 * 32
-        out_feature = depth = normal = contrib_sum = contrib_max = None  # carved from a private copy of the replica after the render
+        n_planes = Cn + 4 if rich_info else Cn
+        o_sum = pad4(n_planes * n_pix)
+        o_max = o_sum + (pad4(P) if rich_info else 0)
+        frame, mc_base, fab_h = fab.buffer("frame", o_max + (pad4(P) if rich_info else 0))
+        out_feature = frame[:n_img].view(Cn, H, W)
+        if rich_info:
+            depth, normal = frame[n_img:n_img + n_pix].view(H, W), frame[n_img + n_pix:n_img + 4 * n_pix].view(3, H, W)
+            contrib_sum, contrib_max = frame[o_sum:o_sum + P], frame[o_max:o_max + P]
+        else:
+            depth = normal = contrib_sum = contrib_max = torch.empty((0,), **f32)
     elif sharded and rich_info and P > 0:
         # one buffer [image | depth | normal | contrib_sum]: the ranks' partial frames are summed with ONE in-place all-reduce
         n_img, n_pix = Cn * H * W, H * W
@@ -291,22 +302,8 @@ def rasterize_triangles(image_width: int, image_height: int, tan_fovx: float, ta
         imageBuffer = torch.empty((ibytes,), **u8)
         counters = FrameCounters()
         shape_key = (dev.index, P, W, H, primitive, tuple(shard))
-        # (the peer-memory path keeps the blocking two-call forward: a repeated render would RED into the peers' replicas twice)
-        cap = None if (debug or fab is not None) else _capacity_for(shape_key)
-        if fab is not None:
-            if rich_info:
-                frame[offs[3]:].zero_()  # contrib_sum / contrib_max: the home slices receive REDs from every rank
-            fab_h.barrier(channel=0)     # every replica zeroed, and nobody still reads the previous frame
-            peers = [int(a) for a in fab_h.buffer_ptrs]
-            fc = _lib.FabricC(world=shard[1], home_chunk=home_chunk, out_feature_mc=mc_base)
-            if rich_info:
-                fc.depth_mc, fc.normal_mc = mc_base + 4 * offs[1], mc_base + 4 * offs[2]
-                for r in range(shard[1]):
-                    fc.contrib_sum[r], fc.contrib_max[r] = peers[r] + 4 * offs[3], peers[r] + 4 * offs[4]
-            flags.fabric = C.cast(C.pointer(fc), C.c_void_p)
-            out = _lib.ForwardOut(None, _ptr(radii), None, None, None, None)
-        else:
-            out = _lib.ForwardOut(_ptr(out_feature), _ptr(radii), _ptr(depth), _ptr(normal), _ptr(contrib_sum), _ptr(contrib_max))
+        cap = None if debug else _capacity_for(shape_key)
+        out = _lib.ForwardOut(_ptr(out_feature), _ptr(radii), _ptr(depth), _ptr(normal), _ptr(contrib_sum), _ptr(contrib_max))
         R = None
         if cap is not None:
             # one enqueue, no synchronisation in front of the binning / composite kernels
@@ -330,21 +327,19 @@ def rasterize_triangles(image_width: int, image_height: int, tan_fovx: float, ta
         _R_SEEN[shape_key] = max(R, _R_SEEN.get(shape_key, 0))
         R = NumRendered(R, counters)
         if fab is not None:
-            fab_h.barrier(channel=0)     # every rank's pixel stores and REDs have landed
-            if rich_info:                # publish this rank's home slice of contrib_sum / contrib_max to every replica
-                first = shard[0] * home_chunk
-                count = pad4(min(home_chunk, P - first)) if first < P else 0
-                for o in (offs[3], offs[4]):
-                    _lib.check(lib.ts2d_fabric_publish(C.c_void_p(frame.data_ptr() + 4 * o), C.c_void_p(mc_base + 4 * o), first, count, stream),
-                               "ts2d_fabric_publish")
-                fab_h.barrier(channel=0)
+            fab_h.barrier(channel=0)     # every rank's tiles and partial statistics are complete, and nobody still reads the previous frame
+            _lib.check(lib.ts2d_exchange_tiles(C.c_void_p(frame.data_ptr()), C.c_void_p(mc_base), n_planes, W, H, shard[0], shard[1], stream),
+                       "ts2d_exchange_tiles")
+            if rich_info:
+                first, count = _home_slice(pad4(P), shard[0], shard[1])
+                _lib.check(lib.ts2d_exchange_allreduce(C.c_void_p(mc_base), o_sum + first, count, _lib.EXCHANGE_ADD_F32, stream), "ts2d_exchange_allreduce")
+                _lib.check(lib.ts2d_exchange_allreduce(C.c_void_p(mc_base), o_max + first, count, _lib.EXCHANGE_MAX_U32, stream), "ts2d_exchange_allreduce")
+            fab_h.barrier(channel=0)     # every rank has published
             mine = frame.clone()         # the symmetric buffer is reused by the next frame
             out_feature = mine[:n_img].view(Cn, H, W)
             if rich_info:
-                depth, normal = mine[offs[1]:offs[1] + n_pix].view(H, W), mine[offs[2]:offs[2] + 3 * n_pix].view(3, H, W)
-                contrib_sum, contrib_max = mine[offs[3]:offs[3] + P], mine[offs[4]:offs[4] + P]
-            else:
-                depth = normal = contrib_sum = contrib_max = torch.empty((0,), **f32)
+                depth, normal = mine[n_img:n_img + n_pix].view(H, W), mine[n_img + n_pix:n_img + 4 * n_pix].view(3, H, W)
+                contrib_sum, contrib_max = mine[o_sum:o_sum + P], mine[o_max:o_max + P]
             out_feature._ts2d_assembled = True  # tells the autograd wrapper that no collective is needed
     return R, out_feature, radii, depth, normal, contrib_sum, contrib_max, geometryBuffer, binningBuffer, imageBuffer
 
@@ -438,10 +433,23 @@ def rasterize_triangles_backward(tan_fovx: float, tan_fovy: float, viewmatrix: t
             # identical data -> identical gradients everywhere
             from . import distributed
 
+            fab = _fabric_for(shard, dev)
+            if fab is not None:
+                # over peer memory: the partial sums go straight into this rank's replica of a symmetric array; every rank combines
+                # its slice of the triangles inside the switch and writes it back to all replicas (include/ts2d.h: ts2d_exchange_allreduce)
+                acc, acc_mc, acc_h = fab.buffer("accumulators", 16 * P)
+            else:
+                acc, acc_mc, acc_h = scratch[:64 * P].view(torch.float32), None, None
             _lib.check(lib.ts2d_backward_composite(C.byref(cam), C.byref(geom), C.byref(flags), _ptr(geometryBuffer), _ptr(binningBuffer), bbytes,
-                                                   _ptr(imageBuffer), C.byref(loss), _ptr(scratch), sbytes, stream), "ts2d_backward_composite")
-            acc = scratch[:64 * P].view(torch.float32)
-            distributed.reduce_accumulators(acc)
+                                                   _ptr(imageBuffer), C.byref(loss), _ptr(scratch), sbytes, _ptr(acc) if fab is not None else None,
+                                                   stream), "ts2d_backward_composite")
+            if fab is not None:
+                acc_h.barrier(channel=0)
+                first, count = _home_slice(16 * P, shard[0], shard[1])
+                _lib.check(lib.ts2d_exchange_allreduce(C.c_void_p(acc_mc), first, count, _lib.EXCHANGE_ADD_F32, stream), "ts2d_exchange_allreduce")
+                acc_h.barrier(channel=0)
+            else:
+                distributed.reduce_accumulators(acc)
             _lib.check(lib.ts2d_backward_geometry(C.byref(cam), C.byref(geom), C.byref(flags), _ptr(radii), _ptr(geometryBuffer),
                                                   C.byref(out), _ptr(acc), 64 * P, stream), "ts2d_backward_geometry")
         else:

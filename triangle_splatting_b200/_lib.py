@@ -41,16 +41,13 @@ class ModelGrads(C.Structure):
 
 class Flags(C.Structure):
     _fields_ = [("back_culling", C.c_int32), ("rich_info", C.c_int32), ("debug", C.c_int32), ("shard_rank", C.c_int32),
-                ("shard_world", C.c_int32), ("exact", C.c_int32), ("primitive", C.c_int32), ("fabric", C.c_void_p)]  # POINTER(FabricC) or NULL
+                ("shard_world", C.c_int32), ("exact", C.c_int32), ("primitive", C.c_int32)]
 
 
 MAX_RANKS = 8  # TS2D_MAX_RANKS
 
 
-class FabricC(C.Structure):
-    """ts2d_fabric: multicast aliases of the image planes + peer tables of the reduced arrays (multi-GPU over NVLink peer memory)."""
-    _fields_ = [("world", C.c_int32), ("home_chunk", C.c_int32), ("out_feature_mc", C.c_void_p), ("depth_mc", C.c_void_p),
-                ("normal_mc", C.c_void_p), ("contrib_sum", C.c_void_p * MAX_RANKS), ("contrib_max", C.c_void_p * MAX_RANKS)]
+EXCHANGE_ADD_F32, EXCHANGE_MAX_U32 = 0, 1  # TS2D_EXCHANGE_*
 
 
 class FrameCounters(C.Structure):
@@ -95,13 +92,14 @@ SYMBOLS = {
     "ts2d_backward": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                 C.c_void_p, C.POINTER(LossIn), C.POINTER(BackwardOut), C.c_void_p, C.c_size_t, C.c_void_p]),
     "ts2d_backward_composite": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_void_p, C.c_void_p, C.c_size_t,
-                                          C.c_void_p, C.POINTER(LossIn), C.c_void_p, C.c_size_t, C.c_void_p]),
+                                          C.c_void_p, C.POINTER(LossIn), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "ts2d_backward_geometry": (C.c_int, [C.POINTER(Camera), C.POINTER(Geometry), C.POINTER(Flags), C.c_void_p, C.c_void_p,
                                          C.POINTER(BackwardOut), C.c_void_p, C.c_size_t, C.c_void_p]),
     "ts2d_export_geometry": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 10 + [C.c_void_p]),
     "ts2d_export_geometry3d": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 8 + [C.c_void_p]),
     "ts2d_export_model": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "ts2d_fabric_publish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "ts2d_exchange_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "ts2d_exchange_allreduce": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
     "ts2d_image_loss_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "ts2d_image_loss_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -116,7 +114,7 @@ SYMBOLS = {
     "ts2d_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
 
-ABI_VERSION = 5  # TS2D_ABI_VERSION (include/ts2d.h)
+ABI_VERSION = 6  # TS2D_ABI_VERSION (include/ts2d.h)
 PRIMITIVES = {"2D": 0, "3D": 1}  # TS2D_PRIMITIVE_* (include/ts2d.h)
 STAGES = ("preprocess", "order_scan", "binning", "render_fwd", "render_bwd", "preprocess_bwd", "bwd_prepare", "bwd_reduce")
 

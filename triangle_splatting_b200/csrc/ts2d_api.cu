@@ -190,7 +190,6 @@ int validate(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f
     return 0;
 }
 
-bool fabric_ok(const ts2d_fabric *m) { return m->world >= 2 && m->world <= TS2D_MAX_RANKS && m->home_chunk > 0 && m->home_chunk % 32 == 0; }
 
 int validate_backward_out(const ts2d_geometry *g, const ts2d_backward_out *out)
 {
@@ -304,15 +303,6 @@ __global__ void k_downsample_bwd(const float *__restrict__ g_out, float *__restr
     g_in[((size_t)blockIdx.z * Hi + yi) * Wi + xi] = w != 0.0f ? w * g_out[((size_t)blockIdx.z * H + y) * W + x] : 0.0f;
 }
 
-// ts2d_fabric_publish: local slice -> every replica (one multimem.st.v4 per 16 bytes)
-__global__ void k_fabric_publish(const float4 *__restrict__ local, float4 *mc, int64_t n4)
-{
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const float4 v = local[i];
-        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-    }
-}
-
 }  // namespace
 
 extern "C" {
@@ -335,7 +325,7 @@ const char *ts2d_error_string(int code)
     case TS2D_E_SHARD: return "invalid shard_rank / shard_world";
     case TS2D_E_SIZE: return "image size or primitive count out of range";
     case TS2D_E_PRIMITIVE: return "flags.primitive must be TS2D_PRIMITIVE_2D or TS2D_PRIMITIVE_3D";
-    case TS2D_E_FABRIC: return "flags.fabric needs the fast kernels, 2 <= world <= 8, home_chunk % 32 == 0 and every address the call writes";
+    case TS2D_E_FABRIC: return "ts2d_exchange_*: 2 <= world <= 8, 0 <= rank < world, a known operation, 16-byte aligned base, first and count multiples of 4 for fp32 sums";
     case TS2D_E_MODEL: return "model inputs / model gradients inconsistent (need use_shs, f_dc, f_rest for M > 1, opacity_logit, ratio > 0)";
     default: break;
     }
@@ -420,18 +410,8 @@ int counters_clear(ts2d_counters *c, cudaStream_t s)
 int validate_render(const ts2d_geometry *geom, const ts2d_flags *flags, const ts2d_forward_out *out)
 {
     if (!out) return TS2D_E_NULL;
-    if (!flags->fabric) {
-        if (!out->out_feature) return TS2D_E_NULL;
-        if (flags->rich_info && (!out->depth || !out->normal || !out->contrib_sum || !out->contrib_max)) return TS2D_E_NULL;
-    }
-    if (const ts2d_fabric *m = flags->fabric) {
-        if (!ts2d_use_fast(geom, flags) || !fabric_ok(m) || !m->out_feature_mc) return TS2D_E_FABRIC;
-        if (flags->rich_info) {
-            if (!m->depth_mc || !m->normal_mc) return TS2D_E_FABRIC;
-            for (int r = 0; r < m->world; r++)
-                if (!m->contrib_sum[r] || !m->contrib_max[r]) return TS2D_E_FABRIC;
-        }
-    }
+    if (!out->out_feature) return TS2D_E_NULL;
+    if (flags->rich_info && (!out->depth || !out->normal || !out->contrib_sum || !out->contrib_max)) return TS2D_E_NULL;
     return 0;
 }
 
@@ -617,7 +597,7 @@ int ts2d_backward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_
 // final gradients, and K9 then runs replicated on identical data.
 int ts2d_backward_composite(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, const void *geometry_state,
                             void *binning_state, size_t binning_state_bytes, const void *image_state, const ts2d_loss_in *loss, void *scratch,
-                            size_t scratch_bytes, void *stream)
+                            size_t scratch_bytes, float *accumulators, void *stream)
 {
     int rc = validate(cam, geom, flags);
     if (rc) return rc;
@@ -633,7 +613,8 @@ int ts2d_backward_composite(const ts2d_camera *cam, const ts2d_geometry *geom, c
     carve_binning(binning_state, cap, &bs);
     carve_image(const_cast<void *>(image_state), cam->width, cam->height, &is);
     if (scratch_bytes < carve_scratch(nullptr, geom->P, cap, 1, nullptr)) return TS2D_E_STATE_SIZE;
-    const BwdScratch sc = scratch_view(scratch, scratch_bytes, geom->P, cap);
+    BwdScratch sc = scratch_view(scratch, scratch_bytes, geom->P, cap);
+    if (accumulators) sc.gacc = accumulators;
     return backward_composite_impl(cam, geom, flags, gs, bs, is, loss, sc, (cudaStream_t)stream);
 }
 
@@ -689,17 +670,6 @@ int ts2d_export_model(const void *geometry_state, int32_t P, int32_t primitive, 
     }
     if (background_depth) TS2D_CUDA_TRY(cudaMemcpyAsync(background_depth, &gs.hdr->bg_bits, sizeof(float), cudaMemcpyDeviceToDevice, s));
     return 0;
-}
-
-int ts2d_fabric_publish(const float *local, float *multicast, int64_t first, int64_t count, void *stream)
-{
-    if (count <= 0) return 0;
-    if (!local || !multicast) return TS2D_E_NULL;
-    if (first < 0 || (first & 3) || (count & 3) || ((uintptr_t)local & 15) || ((uintptr_t)multicast & 15)) return TS2D_E_FABRIC;
-    const int64_t n4 = count / 4;
-    const int blocks = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
-    k_fabric_publish<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(local + first), reinterpret_cast<float4 *>(multicast + first), n4);
-    return (int)cudaGetLastError();
 }
 
 int ts2d_downsample(const float *in, float *out, int32_t planes, int32_t out_width, int32_t out_height, int32_t sc, void *stream)

@@ -91,74 +91,6 @@ __device__ __forceinline__ void st_stream128(float4 *p, float4 v)
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// Multi-GPU over NVLink peer memory (include/ts2d.h: ts2d_fabric).  Pixels: `mc` != 0 means the output plane pointers are NVSwitch
-// multicast aliases and one multimem.st lands in every rank's replica.  Reductions: PeerSet holds every rank's mapping of a
-// symmetric array; triangle id is reduced on its home rank only (one copy => the same bits for every reader).
-struct PeerTab {
-    float *a[TS2D_MAX_RANKS];  // contrib_sum replicas, index = rank
-    float *b[TS2D_MAX_RANKS];  // contrib_max replicas
-    int world;                 // <= 1: single copy, the kernels' plain pointer parameters are the arrays
-    uint32_t chunk;            // triangles per home slice
-};
-// One table per translation unit and per device, written stream-ordered in front of a launch whenever it differs from what that
-// device's copy of the symbol holds (fabric launch, or the first plain launch after one).  (A kernel-parameter table would be copied
-// to local memory by every thread for the dynamic index, and anything handed to the out-of-line flush functions costs registers
-// across the walk loop: the constant bank costs neither.)  Contract: launches that use different tables on ONE device must be
-// issued on one stream -- the symbol copy is ordered against kernels of that stream only.
-static __constant__ PeerTab c_peers;
-__device__ __forceinline__ float *home_select(float *const (&tab)[TS2D_MAX_RANKS], uint32_t id, float *local)
-{
-    if (c_peers.world <= 1) return local;
-    const uint32_t r = min(id / c_peers.chunk, (uint32_t)c_peers.world - 1u);
-    float *p = tab[0];
-#pragma unroll
-    for (int k = 1; k < TS2D_MAX_RANKS; k++) p = (r == (uint32_t)k) ? tab[k] : p;
-    return p;
-}
-static inline cudaError_t ts2d_set_peers(const ts2d_fabric *fb, bool /*forward*/, cudaStream_t s)
-{
-    constexpr int MAXDEV = 64;
-    static PeerTab g_uploaded[MAXDEV];  // zero-initialised == the zero-initialised symbol (world 0: single copy)
-    PeerTab t = {};
-    if (fb) {
-        for (int r = 0; r < fb->world && r < TS2D_MAX_RANKS; r++) {
-            t.a[r] = fb->contrib_sum[r];
-            t.b[r] = fb->contrib_max[r];
-        }
-        t.world = fb->world;
-        t.chunk = (uint32_t)fb->home_chunk;
-    }
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    const bool tracked = dev >= 0 && dev < MAXDEV;
-    if (tracked && memcmp(&g_uploaded[dev], &t, sizeof(t)) == 0) return cudaSuccess;
-    e = cudaMemcpyToSymbolAsync(c_peers, &t, sizeof(t), 0, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess && tracked) g_uploaded[dev] = t;
-    return e;
-}
-__device__ __forceinline__ void st_out(float *p, float v, int mc)
-{
-    if (mc) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-    else *p = v;
-}
-// REDs into a home replica: system scope when the target may be a peer GPU's memory (the operation is performed at the owner's L2)
-__device__ __forceinline__ void red_add4_out(float *addr, float a, float b, float c, float d, bool sys)
-{
-    if (sys) asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-    else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ void red_add_out(float *p, float v, bool sys)
-{
-    if (sys) asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-    else atomicAdd(p, v);
-}
-__device__ __forceinline__ void red_max_out(unsigned int *p, unsigned int v, bool sys)
-{
-    if (sys) asm volatile("red.relaxed.sys.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-    else atomicMax(p, v);
-}
-
 // Packed fp32: sm_100 executes add/mul/fma.rn.f32x2 as ONE FADD2 / FMUL2 / FFMA2 issue slot for two independent IEEE fp32
 // operations; an operand may be a register pair, one register broadcast to both halves (bc()), or an immediate -- ptxas folds
 // the pack / broadcast into the operand form, no MOVs.  Used where two sums share their multiplier (the issue-bound kernels).
@@ -208,6 +140,8 @@ __device__ __forceinline__ v2 sub2(v2 x, v2 y)
 }
 
 // gamma-dependent constants (kernel-uniform)
+#define TS2D_ARGMIN_TIE 2.7e-6f  // 2^-22 * (1 + sum |a_i|), sum |a_i| <= 10: see the arg-min note in ts2d_render_bwd_fast.cu
+
 struct GammaK {
     float gamma, two_gamma, inv_two_gamma;
     float band;      // relative half-width of the alpha decision band

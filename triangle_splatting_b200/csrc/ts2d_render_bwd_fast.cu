@@ -270,6 +270,14 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                 bool hit = eval_fast(e1, e2, pxf, pyf, gk, f, unc);
                 // one more reference decision lives in the backward pass: op*G < 0.99 (clamp not active)
                 unc = unc || (fabsf(f.og - 0.99f) <= 0.99f * gk.band);
+                {   // ... and so does the arg-min of (a1, a2, a3): dL/d min(a) goes to ONE barycentric, and near a corner of a thin
+                    // triangle the choice changes the vertex gradient by its own size.  The fast a1, a2 are c * rn(1 / area2) where
+                    // the reference divides (same c, bit for bit): |a_fast - a_ref| <= 1.5 * 2^-23 |a| for a1 and a2, their sum plus
+                    // two roundings at 1 for a3 = 1 - a1 - a2; with every |a_i| <= 5.4 where a pair can contribute (ecc <= 7.4 at
+                    // gamma = 0.6) the two smallest can swap only when they are within TS2D_ARGMIN_TIE of each other.
+                    const float lo12 = fminf(f.a1, f.a2), hi12 = fmaxf(f.a1, f.a2);
+                    unc = unc || (fmaxf(lo12, fminf(hi12, f.a3)) - fminf(lo12, f.a3) <= TS2D_ARGMIN_TIE);
+                }
                 if (unc) {
                     const float area2 = __ldg(&rec0[3 * (size_t)lds32(ea + 44) + 2].w);
                     PairEval e;
@@ -278,20 +286,6 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                     if (hit) { f.power = e.power; f.G = e.G; f.og = __fmul_rn(e2.w, e.G); f.alpha = e.alpha; }
                 }
                 if (hit) {
-                    {   // The arg-min of (a1, a2, a3) is one more reference decision: dL/d min(a) goes to ONE barycentric, and near a
-                        // corner of a thin triangle the choice changes the vertex gradient by its own size.  The fast a1, a2 are
-                        // c * rn(1 / area2) where the reference divides (same c, bit for bit): |a_fast - a_ref| <= 1.5 * 2^-23 |a| for
-                        // a1 and a2, their sum plus two roundings at 1 for a3 = 1 - a1 - a2.  Within that band of a tie: exact values.
-                        const float lo12 = fminf(f.a1, f.a2), hi12 = fmaxf(f.a1, f.a2);
-                        const float second = fmaxf(lo12, fminf(hi12, f.a3));
-                        const float tie = fmaf(fabsf(f.a1) + fabsf(f.a2) + fabsf(f.a3), 0x1p-22f, 0x1p-22f);
-                        if (second - fminf(lo12, f.a3) <= tie) {
-                            const float area2 = __ldg(&rec0[3 * (size_t)lds32(ea + 44) + 2].w);
-                            PairEval e;
-                            (void)eval_exact(e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, area2, e2.w, gk.two_gamma, pxf, pyf, e);
-                            f.a1 = e.a1; f.a2 = e.a2; f.a3 = e.a3;
-                        }
-                    }
                     const float4 col = lds128(ea + 32);
                     const float om = 1.0f - f.alpha;
                     T = T * rcp_approx(om);

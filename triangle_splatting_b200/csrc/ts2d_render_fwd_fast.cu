@@ -89,7 +89,7 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                   const uint32_t *keys, const uint32_t *__restrict__ list, const float4 *__restrict__ rec0,
                   const float4 *__restrict__ rec1, float bg_depth, const float *__restrict__ bg_ptr, const float *__restrict__ background, float *__restrict__ final_T,
                   uint32_t *__restrict__ n_contrib, float *__restrict__ out_feature, float *__restrict__ out_depth,
-                  float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max, int mc,
+                  float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max,
                   uint32_t *__restrict__ lastw, unsigned long long *__restrict__ bwd_rows, unsigned long long *__restrict__ csum64)
 {
     if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
@@ -138,9 +138,8 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
             if (m > 0.0f) {
                 kept = true;
                 const uint32_t id = lds32(sb + lane * L::EB + 44);
-                if (csum64) atomicAdd(csum64 + id, __float2ull_rn(s * 4294967296.0f));  // 2^-32 fixed point: integer sums do not depend on the order of the additions
-                else red_add_out(home_select(c_peers.a, id, contrib_sum) + id, s, mc);
-                red_max_out((unsigned int *)home_select(c_peers.b, id, contrib_max) + id, __float_as_uint(m), mc);  // contrib >= 0: bit order == value order
+                atomicAdd(csum64 + id, __float2ull_rn(s * 4294967296.0f));  // 2^-32 fixed point: integer sums do not depend on the order of the additions
+                atomicMax((unsigned int *)contrib_max + id, __float_as_uint(m));  // contrib >= 0: bit order == value order
             } else {
                 // No pixel of this sub-tile blended the entry (footprint between pixel centres, or every pixel under it already
                 // saturated): clear the sub-tile's coverage bit in the instance key, so the backward pass -- whose per-pair decisions
@@ -264,14 +263,14 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
         const size_t HW = (size_t)H * W;
         final_T[pix] = T;
         n_contrib[pix] = last;
-        st_out(out_feature + pix, fmaf(T, bg0, acc01.a), mc);
-        if (C > 1) st_out(out_feature + HW + pix, fmaf(T, bg1, acc01.b), mc);
-        if (C > 2) st_out(out_feature + 2 * HW + pix, fmaf(T, bg2, acc2), mc);
+        out_feature[pix] = fmaf(T, bg0, acc01.a);
+        if (C > 1) out_feature[HW + pix] = fmaf(T, bg1, acc01.b);
+        if (C > 2) out_feature[2 * HW + pix] = fmaf(T, bg2, acc2);
         if constexpr (RICH) {
-            st_out(out_depth + pix, fmaf(T, bg_depth, accd), mc);
-            st_out(out_normal + pix, accn01.a, mc);
-            st_out(out_normal + HW + pix, accn01.b, mc);
-            st_out(out_normal + 2 * HW + pix, accn2, mc);
+            out_depth[pix] = fmaf(T, bg_depth, accd);
+            out_normal[pix] = accn01.a;
+            out_normal[HW + pix] = accn01.b;
+            out_normal[2 * HW + pix] = accn2;
         }
     }
 }
@@ -290,17 +289,10 @@ int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
 #define TS2D_FWD_ARGS                                                                                                                       \
     W, H, g->C, gx, f->shard_rank, f->shard_world, n_tiles, g->gamma, is.ranges, keys, list, gs.rec0, gs.rec1, g->background_depth, ts2d_bg_ptr(g, gs),         \
         g->background, is.final_T, is.n_contrib, o_feature
-    // multi-GPU over peer memory (ts2d_fabric): pixels go through the multicast aliases of the image planes (every rank's replica at
-    // once), contrib_sum / contrib_max REDs to the triangle's home replica; the caller zeroed those and synchronised the ranks
-    const ts2d_fabric *fb = f->fabric;
-    const int mc = fb != nullptr;
-    float *o_feature = mc ? fb->out_feature_mc : out->out_feature, *o_depth = mc ? fb->depth_mc : out->depth, *o_normal = mc ? fb->normal_mc : out->normal;
-    float *o_csum = mc ? nullptr : out->contrib_sum, *o_cmax = mc ? nullptr : out->contrib_max;
-    TS2D_CUDA_TRY(ts2d_set_peers(fb, true, s));
+    float *o_feature = out->out_feature, *o_depth = out->depth, *o_normal = out->normal, *o_csum = out->contrib_sum, *o_cmax = out->contrib_max;
     unsigned long long *rows_ctr = reinterpret_cast<unsigned long long *>(&gs.hdr->render.bwd_rows);
-    // contrib_sum is accumulated in 2^-32 fixed point (bit-reproducible) and converted once at the end; over the peer-memory fabric it
-    // stays a float RED into the triangle's home replica
-    unsigned long long *csum64 = (f->rich_info && !mc) ? gs.csum64 : nullptr;
+    // contrib_sum is accumulated in 2^-32 fixed point (bit-reproducible) and converted once at the end
+    unsigned long long *csum64 = f->rich_info ? gs.csum64 : nullptr;
 #define TS2D_FWD_LAUNCH_CW(R, G, CW, ...)                                                                                              \
     do {                                                                                                                               \
         const size_t smem = CW * (size_t)FwdLayout<R>::BYTES;                                                                          \
@@ -316,15 +308,13 @@ int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
         }                                                                                                                              \
     } while (0)
     if (f->rich_info) {
-        if (!mc) {
-            TS2D_CUDA_TRY(cudaMemsetAsync(gs.csum64, 0, sizeof(unsigned long long) * (size_t)g->P, s));
-            TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
-        }
-        if (g1) TS2D_FWD_LAUNCH(true, true, o_depth, o_normal, o_csum, o_cmax, mc, is.lastw, rows_ctr, csum64);
-        else TS2D_FWD_LAUNCH(true, false, o_depth, o_normal, o_csum, o_cmax, mc, is.lastw, rows_ctr, csum64);
+        TS2D_CUDA_TRY(cudaMemsetAsync(gs.csum64, 0, sizeof(unsigned long long) * (size_t)g->P, s));
+        TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
+        if (g1) TS2D_FWD_LAUNCH(true, true, o_depth, o_normal, o_csum, o_cmax, is.lastw, rows_ctr, csum64);
+        else TS2D_FWD_LAUNCH(true, false, o_depth, o_normal, o_csum, o_cmax, is.lastw, rows_ctr, csum64);
     } else {
-        if (g1) TS2D_FWD_LAUNCH(false, true, nullptr, nullptr, o_csum, o_cmax, mc, is.lastw, rows_ctr, csum64);
-        else TS2D_FWD_LAUNCH(false, false, nullptr, nullptr, o_csum, o_cmax, mc, is.lastw, rows_ctr, csum64);
+        if (g1) TS2D_FWD_LAUNCH(false, true, nullptr, nullptr, o_csum, o_cmax, is.lastw, rows_ctr, csum64);
+        else TS2D_FWD_LAUNCH(false, false, nullptr, nullptr, o_csum, o_cmax, is.lastw, rows_ctr, csum64);
     }
 #undef TS2D_FWD_LAUNCH
 #undef TS2D_FWD_LAUNCH_CW

@@ -4,15 +4,19 @@ which has no distributed code at all -- SURVEY.md section 2a / 8e).
 One process per GPU (torchrun), parameters replicated.  Tile ``t`` is owned by rank ``t % world``
 (interleaved for load balance against non-uniform triangle density).  Per frame:
 
-  forward   every rank runs the per-triangle preprocess (cheap, keeps ``radii`` identical everywhere),
-            emits/sorts/composites only its own tiles into a zero-filled full-size image;
-            one all-reduce(sum) of the packed image planes rebuilds the frame; contrib_sum is
-            all-reduced with sum, contrib_max with max.
-  backward  every rank walks its own tiles, producing partial per-triangle gradients; the five
-            gradient tensors are packed into one bucket and all-reduced(sum) over NCCL/NVLink.
+  forward   every rank runs the per-triangle preprocess and the depth sort (cheap, keeps ``radii`` identical everywhere),
+            emits / sorts / composites only its own tiles;
+  backward  every rank walks its own tiles, producing partial per-triangle accumulators (64 B per triangle, themselves
+            bit-reproducible); their sum over the ranks feeds the replicated per-triangle backward.
 
-All collectives are issued on the current CUDA stream through torch.distributed (backend "nccl" on
-GPUs, "gloo" in the CPU tests of the host logic).
+Two exchange paths, same results on every rank either way:
+  fabric    (default when torch symmetric memory gives a multicast mapping) the outputs live in a symmetric buffer; exchange kernels
+            launched behind the composite kernels (include/ts2d.h: ts2d_exchange_tiles, ts2d_exchange_allreduce) copy the owned
+            tiles' rows into every replica with multimem.st and combine home slices of the contrib statistics / accumulators inside
+            the NVSwitch (multimem.ld_reduce); two signal-pad rendezvous per pass, no collective library call;
+  NCCL      (TS2D_FABRIC=0, or no multicast) all-reduce(sum) of the zero-filled frame planes + contrib_sum, all-reduce(max) of
+            contrib_max, all-reduce(sum) of the accumulators, on the current CUDA stream through torch.distributed
+            (backend "nccl" on GPUs, "gloo" in the CPU tests of the host logic).
 """
 from __future__ import annotations
 
@@ -25,13 +29,9 @@ _STATE = {"enabled": False, "group": None, "rank": 0, "world": 1, "fabric": None
 
 
 class Fabric:
-    """Symmetric buffers over NVLink peer memory with NVSwitch multicast aliases (torch symmetric memory: cuMem + cuMulticast).
-
-    The fast composite kernels exchange through them while they run (include/ts2d.h: ts2d_fabric): the pixels of a rank's tiles are
-    stored into every replica with multimem.st, per-triangle sums are reduced on the triangle's home rank over its peer mapping and
-    the home then publishes its slice to every replica -- so a tile-sharded frame is assembled and its gradient sums are completed
-    without a collective, bit-identically on every rank; what is left between ranks are signal-pad barriers.
-    Buffers are persistent (allocation + rendezvous is a collective): one per role, grown on demand."""
+    """Symmetric buffers over NVLink peer memory with NVSwitch multicast aliases (torch symmetric memory: cuMem + cuMulticast), the
+    storage the exchange kernels of include/ts2d.h work on.  Buffers are persistent (allocation + rendezvous is a collective): one per
+    role, grown on demand."""
 
     def __init__(self, group, device):
         import torch.distributed._symmetric_memory as symm
