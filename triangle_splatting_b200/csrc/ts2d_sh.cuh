@@ -198,73 +198,76 @@ __device__ __forceinline__ f3 sh_colour(int deg, const float *sh, f3 pos, f3 cam
     return mk3(fmaxf(rgb.x, 0.0f), fmaxf(rgb.y, 0.0f), fmaxf(rgb.z, 0.0f));
 }
 
+// Back-propagation through u = v / |v|: the Jacobian is the projector onto the plane normal to u, scaled by 1 / |v|.
 __device__ __forceinline__ f3 grad_norm3(f3 v, f3 dv)
 {
-    const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
-    const float n = sqrtf(sum2);
-    const float inv = 1.0f / (n * n * n);
-    return mk3(((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * inv,
-               (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * inv,
-               (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * inv);
+    const float inv_n = 1.0f / len3(v);
+    const f3 u = v * inv_n;
+    return (dv - dot3(u, dv) * u) * inv_n;
 }
 
 __device__ __forceinline__ void st3(float *p, f3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
 
-// SH backward: writes dL/dsh for the active coefficients, zero for the inactive ones, returns dL/dcentre.
+// SH backward (the adjoint of sh_colour; backward.cu:9-119 computes the same two results): dL/dsh_k = b_k(dir) g for the active
+// coefficients (zero for the inactive ones), and dL/dcentre through the view direction,  d rgb / d dir = sum_k sh_k (grad b_k)^T,
+// so  dL/ddir = sum_k <g, sh_k> grad b_k.  One pass over the coefficients: the scalar c_k = <g, sh_k> is taken before out_k is
+// written, so `out` may alias `sh` (the tiled kernel back-propagates in place in shared memory).  b_k are the homogeneous
+// polynomials of sh_colour, their gradients written out by hand:
+//   k  b_k / constant                grad b_k / constant
+//   1  y                             (0, 1, 0)                         9   y (3xx - yy)        (6xy, 3(xx - yy), 0)
+//   2  z                             (0, 0, 1)                         10  xyz                 (yz, xz, xy)
+//   3  x                             (1, 0, 0)                         11  y (4zz - xx - yy)   (-2xy, 4zz - xx - 3yy, 8yz)
+//   4  xy                            (y, x, 0)                         12  z (2zz - 3xx - 3yy) (-6xz, -6yz, 3(2zz - xx - yy))
+//   5  yz                            (0, z, y)                         13  x (4zz - xx - yy)   (4zz - 3xx - yy, -2xy, 8xz)
+//   6  2zz - xx - yy                 (-2x, -2y, 4z)                    14  z (xx - yy)         (2xz, -2yz, xx - yy)
+//   7  xz                            (z, 0, x)                         15  x (xx - 3yy)        (3(xx - yy), -6xy, 0)
+//   8  xx - yy                       (2x, -2y, 0)
 __device__ __forceinline__ f3 sh_colour_bwd(int deg, int M, const float *sh, f3 pos, f3 cam, uint8_t mask, f3 g, float *out)
 {
-    const f3 dir_orig = pos - cam;
-    const f3 dir = dir_orig / len3(dir_orig);
-    g.x *= (mask & 1) ? 0.0f : 1.0f;
-    g.y *= (mask & 2) ? 0.0f : 1.0f;
-    g.z *= (mask & 4) ? 0.0f : 1.0f;
-    f3 dx = mk3(0, 0, 0), dy = mk3(0, 0, 0), dz = mk3(0, 0, 0);
-    const float x = dir.x, y = dir.y, z = dir.z;
-    // `out` may alias `sh` (the tiled kernel back-propagates in place in shared memory): within every band the
-    // coefficients are read before the band's gradients are written.
+    const f3 view = pos - cam;
+    const f3 u = view / len3(view);
+    if (mask & 1) g.x = 0.0f;  // clamped channels pass no gradient
+    if (mask & 2) g.y = 0.0f;
+    if (mask & 4) g.z = 0.0f;
+    f3 gd = mk3(0, 0, 0);
+    auto term = [&](int k, float konst, float b, float bx, float by, float bz) {
+        const float c = konst * dot3(g, ld3(sh + 3 * k));
+        st3(out + 3 * k, (konst * b) * g);
+        gd.x = fmaf(c, bx, gd.x);
+        gd.y = fmaf(c, by, gd.y);
+        gd.z = fmaf(c, bz, gd.z);
+    };
+    const float x = u.x, y = u.y, z = u.z;
     st3(out, kC0 * g);
-    int written = 1;
+    int active = 1;
     if (deg > 0) {
-        dx = -kC1 * ld3(sh + 9);
-        dy = -kC1 * ld3(sh + 3);
-        dz = kC1 * ld3(sh + 6);
-        st3(out + 3, (-kC1 * y) * g);
-        st3(out + 6, (kC1 * z) * g);
-        st3(out + 9, (-kC1 * x) * g);
-        written = 4;
-        if (deg > 1) {
-            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-            const f3 s4 = ld3(sh + 12), s5 = ld3(sh + 15), s6 = ld3(sh + 18), s7 = ld3(sh + 21), s8 = ld3(sh + 24);
-            st3(out + 12, (kC2[0] * xy) * g);
-            st3(out + 15, (kC2[1] * yz) * g);
-            st3(out + 18, (kC2[2] * (2.f * zz - xx - yy)) * g);
-            st3(out + 21, (kC2[3] * xz) * g);
-            st3(out + 24, (kC2[4] * (xx - yy)) * g);
-            dx = dx + (kC2[0] * y * s4 + kC2[2] * 2.f * -x * s6 + kC2[3] * z * s7 + kC2[4] * 2.f * x * s8);
-            dy = dy + (kC2[0] * x * s4 + kC2[1] * z * s5 + kC2[2] * 2.f * -y * s6 + kC2[4] * 2.f * -y * s8);
-            dz = dz + (kC2[1] * y * s5 + kC2[2] * 2.f * 2.f * z * s6 + kC2[3] * x * s7);
-            written = 9;
-            if (deg > 2) {
-                const f3 s9 = ld3(sh + 27), s10 = ld3(sh + 30), s11 = ld3(sh + 33), s12 = ld3(sh + 36), s13 = ld3(sh + 39), s14 = ld3(sh + 42),
-                         s15 = ld3(sh + 45);
-                st3(out + 27, (kC3[0] * y * (3.f * xx - yy)) * g);
-                st3(out + 30, (kC3[1] * xy * z) * g);
-                st3(out + 33, (kC3[2] * y * (4.f * zz - xx - yy)) * g);
-                st3(out + 36, (kC3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * g);
-                st3(out + 39, (kC3[4] * x * (4.f * zz - xx - yy)) * g);
-                st3(out + 42, (kC3[5] * z * (xx - yy)) * g);
-                st3(out + 45, (kC3[6] * x * (xx - 3.f * yy)) * g);
-                dx = dx + (kC3[0] * s9 * 3.f * 2.f * xy + kC3[1] * s10 * yz + kC3[2] * s11 * -2.f * xy + kC3[3] * s12 * -3.f * 2.f * xz +
-                           kC3[4] * s13 * (-3.f * xx + 4.f * zz - yy) + kC3[5] * s14 * 2.f * xz + kC3[6] * s15 * 3.f * (xx - yy));
-                dy = dy + (kC3[0] * s9 * 3.f * (xx - yy) + kC3[1] * s10 * xz + kC3[2] * s11 * (-3.f * yy + 4.f * zz - xx) +
-                           kC3[3] * s12 * -3.f * 2.f * yz + kC3[4] * s13 * -2.f * xy + kC3[5] * s14 * -2.f * yz + kC3[6] * s15 * -3.f * 2.f * xy);
-                dz = dz + (kC3[1] * s10 * xy + kC3[2] * s11 * 4.f * 2.f * yz + kC3[3] * s12 * 3.f * (2.f * zz - xx - yy) +
-                           kC3[4] * s13 * 4.f * 2.f * xz + kC3[5] * s14 * (xx - yy));
-                written = 16;
-            }
+        term(1, -kC1, y, 0.0f, 1.0f, 0.0f);
+        term(2, kC1, z, 0.0f, 0.0f, 1.0f);
+        term(3, -kC1, x, 1.0f, 0.0f, 0.0f);
+        active = 4;
+    }
+    if (deg > 1) {
+        const float xx = x * x, yy = y * y, zz = z * z;
+        const float d = xx - yy, p = 2.0f * zz - xx - yy;
+        term(4, kC2[0], x * y, y, x, 0.0f);
+        term(5, kC2[1], y * z, 0.0f, z, y);
+        term(6, kC2[2], p, -2.0f * x, -2.0f * y, 4.0f * z);
+        term(7, kC2[3], x * z, z, 0.0f, x);
+        term(8, kC2[4], d, 2.0f * x, -2.0f * y, 0.0f);
+        active = 9;
+        if (deg > 2) {
+            const float xy = x * y, yz = y * z, xz = x * z;
+            const float r = 4.0f * zz - xx - yy;  // shared by k = 11 and k = 13
+            term(9, kC3[0], y * (3.0f * xx - yy), 6.0f * xy, 3.0f * d, 0.0f);
+            term(10, kC3[1], xy * z, yz, xz, xy);
+            term(11, kC3[2], y * r, -2.0f * xy, r - 2.0f * yy, 8.0f * yz);
+            term(12, kC3[3], z * (p - 2.0f * (xx + yy)), -6.0f * xz, -6.0f * yz, 3.0f * p);
+            term(13, kC3[4], x * r, r - 2.0f * xx, -2.0f * xy, 8.0f * xz);
+            term(14, kC3[5], z * d, 2.0f * xz, -2.0f * yz, d);
+            term(15, kC3[6], x * (xx - 3.0f * yy), 3.0f * d, -6.0f * xy, 0.0f);
+            active = 16;
         }
     }
-    for (int k = 3 * written; k < 3 * M; k++) out[k] = 0.0f;
-    const f3 gdir = mk3(dot3(g, dx), dot3(g, dy), dot3(g, dz));
-    return grad_norm3(dir_orig, gdir);
+    for (int k = 3 * active; k < 3 * M; k++) out[k] = 0.0f;
+    return grad_norm3(view, gd);
 }
