@@ -54,7 +54,7 @@ template <int MASKS, bool SHARDED>
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_emit_warp(int P, int gx, float gamma, EmitCam cam, int shard_rank, int shard_world, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
             const ushort4 *__restrict__ rect, const uint32_t *__restrict__ offs, const float4 *__restrict__ rec0, uint32_t cap, uint32_t *__restrict__ tkey,
-            uint32_t *__restrict__ tval, uint32_t *__restrict__ estart)
+            uint32_t *__restrict__ tval, uint32_t *__restrict__ estart, uint2 *__restrict__ ranges)
 {
     const int lane = threadIdx.x & 31;
     const int r = (blockIdx.x * blockDim.x + threadIdx.x);
@@ -110,27 +110,49 @@ k_emit_warp(int P, int gx, float gamma, EmitCam cam, int shard_rank, int shard_w
             }
             tkey[i] = instance_key<MASKS>(tile, gx, t_id, rec0, gk, cam);
             tval[i] = t_id;
+            atomicAdd(&ranges[tile].y, 1u);  // instances per tile (the array is zero on entry): k_tile_tables turns the counts into ranges
         }
     }
 }
 
-// rasterizer.cu:79-99 on 32-bit tile keys; R from the device.
-__global__ void __launch_bounds__(TS2D_BLOCK) k_ranges(const int64_t *__restrict__ n_dev, int64_t cap, const uint32_t *__restrict__ tkey, uint2 *__restrict__ ranges)
+// Tile ranges and the digit histograms of the tile sort from the per-tile instance counts the emission left in ranges[].y -- one
+// block, before the sort runs (the ranges depend on the counts only): replaces identifyTileRanges (rasterizer.cu:79-99, a pass over
+// the R sorted keys) and a histogram pass over the R unsorted keys.  Tiles without instances keep {0, 0} like the reference's
+// zero-initialised array.  hist[d][b] = instances whose d-th 8-bit digit of the tile id is b (all 256 bins are written).
+__global__ void __launch_bounds__(1024) k_tile_tables(int n_tiles, int np, uint2 *__restrict__ ranges, uint32_t *__restrict__ hist0, uint32_t *__restrict__ hist1,
+                                                     uint32_t *__restrict__ hist2)
 {
-    const int64_t R = rs_count(n_dev, cap);
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R) return;
-    const uint32_t cur = tkey[i] >> TS2D_MASK_BITS;
-    if (i == 0)
-        ranges[cur].x = 0;
-    else {
-        const uint32_t prev = tkey[i - 1] >> TS2D_MASK_BITS;
-        if (cur != prev) {
-            ranges[prev].y = (uint32_t)i;
-            ranges[cur].x = (uint32_t)i;
+    __shared__ uint32_t s_part[1024];
+    __shared__ uint32_t s_h[3][RS_BINS];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 3 * RS_BINS; i += 1024) (&s_h[0][0])[i] = 0;
+    const int per = (n_tiles + 1023) / 1024;
+    const int t0 = tid * per, t1 = min(n_tiles, t0 + per);
+    uint32_t sum = 0;
+    for (int t = t0; t < t1; t++) sum += ranges[t].y;
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan of the 1024 partial sums
+        const uint32_t v = tid >= o ? s_part[tid - o] : 0u;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[tid] - sum;
+    for (int t = t0; t < t1; t++) {
+        const uint32_t c = ranges[t].y;
+        if (c) {
+            ranges[t] = make_uint2(run, run + c);
+            for (int d = 0; d < np; d++) atomicAdd(&s_h[d][((uint32_t)t >> (8 * d)) & 0xFFu], c);
+            run += c;
         }
     }
-    if (i == R - 1) ranges[cur].y = (uint32_t)R;
+    __syncthreads();
+    if (tid < RS_BINS) {
+        hist0[tid] = s_h[0][tid];
+        if (np > 1) hist1[tid] = s_h[1][tid];
+        if (np > 2) hist2[tid] = s_h[2][tid];
+    }
 }
 
 int hist_blocks(int64_t n) { return (int)((n + 4095) / 4096 < 592 ? ((n + 4095) / 4096 > 0 ? (n + 4095) / 4096 : 1) : 592); }
@@ -201,7 +223,7 @@ int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts
     const int blocks = (P + TS2D_BLOCK - 1) / TS2D_BLOCK;
     const EmitCam ec = {cam->width, cam->height, cam->tan_fovx, cam->tan_fovy};
     const uint32_t cap32 = (uint32_t)(bs.cap < 0xFFFFFFFFll ? bs.cap : 0xFFFFFFFFll);
-#define TS2D_EMIT_ARGS P, gx, g->gamma, ec, f->shard_rank, f->shard_world, gs.ids2, gs.tiles, gs.rect, gs.offs, gs.rec0, cap32, bs.tkey[0], bs.tval[0], gs.estart
+#define TS2D_EMIT_ARGS P, gx, g->gamma, ec, f->shard_rank, f->shard_world, gs.ids2, gs.tiles, gs.rect, gs.offs, gs.rec0, cap32, bs.tkey[0], bs.tval[0], gs.estart, is.ranges
     if (f->shard_world > 1) {
         if (masks == 2) k_emit_warp<2, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
         else if (masks == 1) k_emit_warp<1, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
@@ -216,17 +238,8 @@ int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts
     // stable sort on the tile bits: digits of 8 bits from bit TS2D_MASK_BITS up (the last one narrower)
     const int tb = ts2d_tile_bits(n_tiles), np = ts2d_tile_sort_passes(n_tiles);
     const int64_t *n_dev = &gs.hdr->num_rendered;
-    RadixHistArgs h = {};
-    h.keys = bs.tkey[0];
-    h.n_dev = n_dev;
-    h.n_cap = bs.cap;
-    h.ndigits = np;
-    for (int d = 0; d < np; d++) {
-        h.shift[d] = TS2D_MASK_BITS + 8 * d;
-        h.mask[d] = (d == np - 1) ? ((1u << (tb - 8 * d)) - 1u) : 0xFFu;
-        h.hist[d] = gs.hdr->render.hist[d];
-    }
-    k_radix_hist<<<hist_blocks(n_launch), RS_THREADS, 0, s>>>(h);
+    static_assert(TS2D_MASK_BITS == 8, "the digits of the tile sort are the bytes of the tile id");
+    k_tile_tables<<<1, 1024, 0, s>>>(n_tiles, np, is.ranges, gs.hdr->render.hist[0], gs.hdr->render.hist[1], gs.hdr->render.hist[2]);
     for (int d = 0; d < np; d++) {
         RadixPassArgs a = {};
         a.kin = bs.tkey[d & 1];
@@ -238,12 +251,10 @@ int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts
         a.ticket = &gs.hdr->render.tickets[TS2D_TICKET_TILE0 + d];
         a.n_dev = n_dev;
         a.n_cap = bs.cap;
-        a.shift = h.shift[d];
-        a.mask = h.mask[d];
+        a.shift = TS2D_MASK_BITS + 8 * d;
+        a.mask = (d == np - 1) ? ((1u << (tb - 8 * d)) - 1u) : 0xFFu;
         a.pass_uid = (uint32_t)(8 + d);
         k_radix_pass<<<(unsigned)rs_tiles(n_launch), RS_THREADS, 0, s>>>(a);
     }
-    const int sb = ts2d_sorted_buf(n_tiles);
-    k_ranges<<<(unsigned)((n_launch + TS2D_BLOCK - 1) / TS2D_BLOCK), TS2D_BLOCK, 0, s>>>(n_dev, bs.cap, bs.tkey[sb], is.ranges);
     return (int)cudaGetLastError();
 }
