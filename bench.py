@@ -761,8 +761,8 @@ def main():
         except (OSError, KeyError, ValueError):
             pass
         roof = {"bound": "hbm", "traffic_source": traffic_src, "kernel": {"render_fwd": "k_render_fwd_fast", "render_bwd": "k_render_bwd_fast", "preprocess": "k_preprocess",
-                                            "preprocess_bwd": "k_preprocess_bwd", "binning": "k_emit_warp + k_radix_hist + k_radix_pass + k_ranges",
-                                            "order_scan": "k_radix_hist + k_radix_pass + k_scan_gather", "bwd_prepare": "k_bwd_rows_mark + k_scan_u8",
+                                            "preprocess_bwd": "k_preprocess_bwd", "binning": "k_emit_warp + k_tile_tables + k_radix_pass",
+                                            "order_scan": "k_radix_hist + k_radix_pass + k_scan_sums / _block_sums / _apply", "bwd_prepare": "k_bwd_rows_mark + k_scan_sums / _block_sums / _apply",
                                             "bwd_reduce": "k_bwd_rows_reduce"}[dom],
                 "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5), "traffic": traffic, "peak_source": peak_src,
                 "issue_active_pct": issue_pct,
@@ -770,9 +770,10 @@ def main():
                         "`traffic`) is the fraction of its real ceiling; per-stage figures in `stages`",
                 "whole_frame_gbs": round(sum(ab.values()) / (ms / a.steps * 1e-3) / 1e9, 1)}
         tile_bits = max(1, (T - 1).bit_length())
-        # K1, depth histogram, 4 depth passes, scan | emit, tile histogram, tile passes, ranges, K7, contrib finish | row marking, row scan,
-        # K8, row reduction, K9 -- every one of them a kernel of libts2d (no library kernels on the path; memsets not counted)
-        own_per_step = 7 + (4 + (tile_bits + 7) // 8 + (1 if sc.rich_info else 0)) + 5
+        # K1, depth histogram, 4 depth passes, 3 scan kernels | emit, tile tables (ranges + digit histograms), tile passes, K7, contrib
+        # finish | row marking, 3 scan kernels, K8, row reduction, K9 -- every one of them a kernel of libts2d (no library kernels on
+        # the path; memsets not counted)
+        own_per_step = 9 + (3 + (tile_bits + 7) // 8 + (1 if sc.rich_info else 0)) + 7
         line = dict(base, impl="ours", value=fps, ms_per_step=ms / a.steps, per_step=per_step, config=cfg, clocks=clocks, roofline=roof, stages=stages,
                     gpu_launches=own_per_step * a.steps, work=work,
                     scene={"P": sc.P, "visible": V, "num_rendered_rank0": R_local, "num_rendered_est": R_total, "tiles": T, "pixels": N})

@@ -20,10 +20,10 @@
 
 namespace {
 
-// MK positions per thread, every dependent-load stage issued for all of them before the next one: the kernel is a chain of
-// gathers (key -> tile -> ranges / lastw, list -> rect / estart) and latency-bound at one position per thread (ncu: 34 of 41 stall
-// cycles per issue on the long scoreboard).
-constexpr int MK = 4;
+// MK positions per thread.  The kernel is a chain of gathers (key -> tile -> ranges / lastw, list -> rect / estart) whose limit is the
+// L2 transaction rate (ncu: l1tex 77 %, lts 59 % of peak), not latency: 4 positions per thread cost 92 registers and two thirds of
+// the occupancy for nothing (129 us against 118 us with one position and 31 registers).
+constexpr int MK = 1;
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_bwd_rows_mark(const int64_t *__restrict__ n_dev, int64_t cap, int gx, int shard_rank, int shard_world, uint32_t *tkey, const uint32_t *__restrict__ list,
                 const uint2 *__restrict__ ranges, const uint32_t *__restrict__ lastw, const ushort4 *__restrict__ rect,
