@@ -385,6 +385,58 @@ def image_loss_ms(sc, dev, fused: bool, steps=10, w_ssim=0.2):
                     f", fwd + bwd on a 3x{h}x{w} frame"}
 
 
+def reference_geometry_loss(depth, normal, tan_fovx, tan_fovy, scale_factor=0.5, q=0.9):
+    """The trainer's geometry term as the reference computes it (trainer_utils.py:159-185 ScharrFilter, :212-255 DepthNormalLoss; the
+    shipped MatrixCity config: scale_factor 0.5), torch ops."""
+    import torch.nn.functional as F
+
+    kx = torch.tensor([[-3, 0, 3], [-10, 0, 10], [-3, 0, 3]], dtype=torch.float32, device=depth.device).view(1, 1, 3, 3) / 32
+    ky = torch.tensor([[-3, -10, -3], [0, 0, 0], [3, 10, 3]], dtype=torch.float32, device=depth.device).view(1, 1, 3, 3) / 32
+    W0, H0 = depth.shape[-1], depth.shape[-2]
+    d = depth.unsqueeze(0).unsqueeze(0)
+    if scale_factor is not None and scale_factor != 1:
+        d = F.interpolate(d, scale_factor=scale_factor, mode="bilinear", align_corners=False)
+    grad = torch.cat((F.conv2d(d, kx, padding=1), F.conv2d(d, ky, padding=1)), dim=1).squeeze(0)
+    Dx, Dy = torch.unbind(grad / d.squeeze(0), 0)
+    W, H = d.shape[-1], d.shape[-2]
+    x, y = torch.meshgrid(torch.arange(W, dtype=torch.float32, device=depth.device), torch.arange(H, dtype=torch.float32, device=depth.device), indexing="xy")
+    nrm = torch.stack([W * Dx / (2 * tan_fovx), H * Dy / (2 * tan_fovy), -(1 + (x - W / 2 + 0.5) * Dx + (y - H / 2 + 0.5) * Dy)], dim=0)
+    gnorm = grad.norm(dim=0, keepdim=True)
+    if W0 != W or H0 != H:
+        nrm = F.interpolate(nrm.unsqueeze(0), size=(H0, W0), mode="bilinear", align_corners=False).squeeze(0)
+        gnorm = F.interpolate(gnorm.unsqueeze(0), size=(H0, W0), mode="bilinear", align_corners=False).squeeze(0)
+    nrm = nrm / nrm.norm(dim=0, keepdim=True)
+    mask = (gnorm < torch.quantile(gnorm, q)).float().squeeze(0)
+    normal = F.normalize(normal, p=2, dim=0, eps=1e-8)
+    return ((1 - (normal * nrm).sum(dim=0)) * mask).mean()
+
+
+def geometry_loss_ms(sc, dev, fused: bool, steps=10):
+    """fwd + bwd of the depth-normal consistency loss on a frame of the workload's size (median of per-step CUDA-event times)."""
+    g = torch.Generator().manual_seed(99)
+    h, w = sc.cam["image_height"], sc.cam["image_width"]
+    yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    depth = (4.0 + 0.002 * xx + 0.003 * yy + 0.5 * torch.sin(xx / 70.0) * torch.cos(yy / 50.0) + 0.01 * torch.rand(h, w, generator=g)).to(dev).requires_grad_(True)
+    normal = (torch.randn(3, h, w, generator=g) * 0.3 + torch.tensor([0.1, -0.2, -1.0]).view(3, 1, 1)).to(dev).requires_grad_(True)
+    tfx, tfy = float(sc.cam["tanfovx"]), float(sc.cam["tanfovy"])
+    if fused:
+        from triangle_splatting_b200 import depth_normal_loss
+
+        fn = lambda: depth_normal_loss(depth, normal, tfx, tfy, 0.5)
+    else:
+        fn = lambda: reference_geometry_loss(depth, normal, tfx, tfy, 0.5)
+
+    def step():
+        depth.grad = normal.grad = None
+        fn().backward()
+
+    med, mean = median_step_ms(step, steps, 3, dev, 1)
+    return {"ms": med, "mean_ms": mean, "steps": steps, "scale_factor": 0.5,
+            "what": ("fused depth-normal loss kernels of libts2d (ts2d_depth_normal_loss_forward / _backward: radix select instead of a sort)" if fused else
+                     "the reference's torch composition (DepthNormalLoss: interpolate, Scharr convolutions, torch.quantile, normalise, masked mean)") +
+                    f", fwd + bwd on a {h}x{w} depth + normal frame"}
+
+
 MODEL_STEP_WHAT = ("raw parameters (_vertex, _f_dc, _f_rest, _opacity logits) -> opacity activation, SH concat, background depth -> "
                    "rasterizer fwd + bwd -> gradients w.r.t. the raw parameters + _training_statistic; CUDA events, parameters resident")
 
@@ -664,8 +716,14 @@ def main():
                 img_loss = image_loss_ms(sc, dev, fused=False)
             except Exception as ex:  # noqa: BLE001
                 img_loss = {"ms": None, "what": f"failed: {ex}"}
+        geo_loss = None
+        if not a.no_model_step:
+            try:
+                geo_loss = geometry_loss_ms(sc, dev, fused=False)
+            except Exception as ex:  # noqa: BLE001
+                geo_loss = {"ms": None, "what": f"failed: {ex}"}
         line = dict(base, impl="reference", n_gpus=1, value=fps, ms_per_step=ms / a.steps, config=cfg, clocks=clocks, model_step=model_step,
-                    image_loss=img_loss,
+                    image_loss=img_loss, geometry_loss=geo_loss,
                     e2e={"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                     cpu_baseline={"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference",
                                   "sample": "full workload on the reference's own CUDA build (oracle/_ref, sm_100): the reference has no CPU "
@@ -813,6 +871,7 @@ def main():
 
     if rank == 0 and world == 1 and not a.no_model_step:
         line["image_loss"] = image_loss_ms(sc, dev, fused=True)
+        line["geometry_loss"] = geometry_loss_ms(sc, dev, fused=True)
 
     if world > 1 and not a.no_check:
         chk = sharded_vs_single_check(step, sc, dev, a.primitive, world)

@@ -58,7 +58,7 @@
 extern "C" {
 #endif
 
-#define TS2D_ABI_VERSION 6
+#define TS2D_ABI_VERSION 7
 #define TS2D_TILE 16          /* R2D/src/config.h:4-5  BLOCK_X = BLOCK_Y = 16 */
 #define TS2D_MAX_CHANNELS 3   /* R2D/src/config.h:3 */
 
@@ -288,6 +288,20 @@ int ts2d_backward_geometry(const ts2d_camera *cam, const ts2d_geometry *geom, co
  * [planes][H][W].  ts2d_downsample_bwd is its adjoint (writes every element of dL_din). */
 int ts2d_downsample(const float *in, float *out, int32_t planes, int32_t out_width, int32_t out_height, int32_t s, void *stream);
 int ts2d_downsample_bwd(const float *dL_dout, float *dL_din, int32_t planes, int32_t out_width, int32_t out_height, int32_t s, void *stream);
+
+/* Fused depth-normal consistency loss, the geometry term of the trainer (DepthNormalLoss, src/diff_recon/trainers/trainer_utils.py:203-257,
+ * used at VanillaTS_trainer.py:84,111): mean((1 - <normalize(normal), normal_from_depth(depth)>) * mask), mask = pixels whose depth-gradient
+ * norm (Scharr, :159-185) lies below its `quantile` over the frame (torch.quantile semantics, linear interpolation; 0.9 in the reference).
+ * depth [H][W], normal [3][H][W].  half_resolution = 1 evaluates the depth surface on the bilinearly halved depth map and up-samples the
+ * result (the reference's scale_factor = 0.5, what its shipped config uses); 0 = scale_factor None / 1.  forward() writes the loss to the
+ * device scalar *loss and leaves what backward() needs in `scratch`; backward() writes dL/ddepth and / or dL/dnormal (either may be NULL:
+ * depth_grad / normal_grad = False), scaled by the device scalar *grad_loss (NULL = 1).  No host synchronisation, no float atomics in the
+ * gradients (bit-reproducible). */
+size_t ts2d_depth_normal_loss_scratch_bytes(int32_t width, int32_t height, int32_t half_resolution);
+int ts2d_depth_normal_loss_forward(const float *depth, const float *normal, int32_t width, int32_t height, float tan_fovx, float tan_fovy,
+                                   int32_t half_resolution, float quantile, float *loss, void *scratch, size_t scratch_bytes, void *stream);
+int ts2d_depth_normal_loss_backward(int32_t width, int32_t height, float tan_fovx, float tan_fovy, int32_t half_resolution, const float *grad_loss,
+                                    void *scratch, size_t scratch_bytes, float *dL_ddepth, float *dL_dnormal, void *stream);
 
 /* Multi-GPU exchange, see above.  `local` / `multicast`: this rank's replica and the multicast alias of the same symmetric buffer
  * ([n_planes][height][width] floats for the tiles; element index `first` of the 4-byte array for the all-reduce). */

@@ -74,3 +74,105 @@ def image_loss_backward(image: np.ndarray, gt: np.ndarray, w_l1: float, w_ssim: 
     k = gaussian_kernel_2d()
     n = x.size
     return -w_ssim / n * (smooth(d1, k) + 2 * x * smooth(d2, k) + y * smooth(d3, k)) + w_l1 / n * np.sign(x - y)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Depth-normal consistency loss (the trainer's geometry term): trainer_utils.py:159-185 (ScharrFilter), :203-257 (DepthNormalLoss).
+# Restated with explicit resampling matrices so that the backward is the transpose of the very same operators; the backward is
+# written the way the CUDA kernels compute it (tests/test_loss_oracle.py checks both directions against torch autograd running the
+# reference's own class, and against the committed fixtures tests/golden/depth_normal_*.npz generated from it).
+
+SCHARR_X = np.array([[-3, 0, 3], [-10, 0, 10], [-3, 0, 3]], dtype=np.float64) / 32  # :162
+SCHARR_Y = np.array([[-3, -10, -3], [0, 0, 0], [3, 10, 3]], dtype=np.float64) / 32  # :163
+
+
+def correlate3(x: np.ndarray, k: np.ndarray, transpose: bool = False) -> np.ndarray:
+    """F.conv2d(x, k, padding=1) of one plane (:178-179), or its adjoint."""
+    h, w = x.shape
+    xp = np.zeros((h + 2, w + 2), dtype=x.dtype)
+    xp[1:1 + h, 1:1 + w] = x
+    out = np.zeros_like(x)
+    for i in range(3):
+        for j in range(3):
+            out += (k[2 - i, 2 - j] if transpose else k[i, j]) * xp[i:i + h, j:j + w]
+    return out
+
+
+def down_matrix(n_in: int) -> np.ndarray:
+    """F.interpolate(scale_factor=0.5, mode="bilinear", align_corners=False) along one axis (:217): floor(n/2) outputs, output d
+    samples the source at 2 (d + 0.5) - 0.5 = 2d + 0.5, i.e. the mean of elements 2d and 2d + 1."""
+    n_out = n_in // 2
+    m = np.zeros((n_out, n_in))
+    for d in range(n_out):
+        m[d, 2 * d] = m[d, 2 * d + 1] = 0.5
+    return m
+
+
+def up_matrix(n_in: int, n_out: int) -> np.ndarray:
+    """F.interpolate(size=n_out, mode="bilinear", align_corners=False) along one axis (:233, :241): source index
+    max(scale (d + 0.5) - 0.5, 0) with scale = n_in / n_out, neighbours clamped at the border."""
+    m = np.zeros((n_out, n_in))
+    scale = n_in / n_out
+    for d in range(n_out):
+        src = max(scale * (d + 0.5) - 0.5, 0.0)
+        i0 = min(int(np.floor(src)), n_in - 1)
+        i1 = min(i0 + 1, n_in - 1)
+        w1 = src - i0
+        m[d, i0] += 1.0 - w1
+        m[d, i1] += w1
+    return m
+
+
+def torch_quantile(v: np.ndarray, q: float, rank_dtype=np.float32) -> float:
+    """torch.quantile(v, q) with the default linear interpolation (:242): ranks = q (n - 1) computed IN THE INPUT'S DTYPE (fp32 for
+    the reference's tensors -- at two million pixels that rounds the rank to a multiple of 1/8), lerp between the two order statistics."""
+    s = np.sort(np.asarray(v).ravel())
+    rank = rank_dtype(rank_dtype(q) * rank_dtype(s.size - 1))
+    lo = int(np.floor(rank))
+    hi = min(int(np.ceil(rank)), s.size - 1)
+    w = float(rank - rank_dtype(lo))
+    return float(s[lo] + w * (s[hi] - s[lo]))
+
+
+def depth_normal_loss(depth: np.ndarray, normal: np.ndarray, tan_fovx: float, tan_fovy: float, scale_factor=None, quantile: float = 0.9,
+                      rank_dtype=np.float32, with_grad: bool = False):
+    """-> loss, or (loss, dL/ddepth, dL/dnormal) in fp64.  depth (H, W), normal (3, H, W)."""
+    d0 = np.asarray(depth, dtype=np.float64)
+    nr = np.asarray(normal, dtype=np.float64)
+    H0, W0 = d0.shape
+    resample = scale_factor is not None and scale_factor != 1
+    if resample and scale_factor != 0.5:
+        raise ValueError("only scale_factor None, 1 or 0.5 (what the shipped configs use) is restated")
+    Dy_, Dx_ = (down_matrix(H0), down_matrix(W0)) if resample else (np.eye(H0), np.eye(W0))
+    d = Dy_ @ d0 @ Dx_.T                                                     # :217
+    H, W = d.shape
+    Uy, Ux = (up_matrix(H, H0), up_matrix(W, W0)) if resample else (np.eye(H0), np.eye(W0))
+    gx, gy = correlate3(d, SCHARR_X), correlate3(d, SCHARR_Y)                # :219
+    Dx, Dy = gx / d, gy / d                                                  # :220
+    x, y = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64), indexing="xy")
+    cx, cy = x - W / 2 + 0.5, y - H / 2 + 0.5
+    n_h = np.stack([W * Dx / (2 * tan_fovx), H * Dy / (2 * tan_fovy), -(1 + cx * Dx + cy * Dy)])   # :226-229
+    n_f = np.stack([Uy @ p @ Ux.T for p in n_h])                             # :232-233
+    len_f = np.sqrt((n_f * n_f).sum(0))
+    dn = n_f / len_f                                                         # :234
+    gn_f = Uy @ np.sqrt(gx * gx + gy * gy) @ Ux.T                            # :238-241
+    thr = torch_quantile(gn_f, quantile, rank_dtype)                         # :242
+    mask = (gn_f < thr).astype(np.float64)                                   # :243
+    len_n = np.maximum(np.sqrt((nr * nr).sum(0)), 1e-8)
+    nrm = nr / len_n                                                         # :254 (F.normalize, eps = 1e-8)
+    N = H0 * W0
+    loss = float(((1.0 - (nrm * dn).sum(0)) * mask).sum() / N)               # :255
+    if not with_grad:
+        return loss
+    g_dn = -mask * nrm / N
+    g_nrm = -mask * dn / N
+    g_normal = (g_nrm - nrm * (nrm * g_nrm).sum(0)) / len_n                  # through x / max(|x|, eps) (|x| > eps)
+    g_nf = (g_dn - dn * (dn * g_dn).sum(0)) / len_f
+    g_nh = np.stack([Uy.T @ p @ Ux for p in g_nf])
+    g_Dx = g_nh[0] * W / (2 * tan_fovx) - g_nh[2] * cx
+    g_Dy = g_nh[1] * H / (2 * tan_fovy) - g_nh[2] * cy
+    g_gx, g_gy = g_Dx / d, g_Dy / d
+    g_dd = -(g_Dx * gx + g_Dy * gy) / (d * d)
+    g_dh = correlate3(g_gx, SCHARR_X, transpose=True) + correlate3(g_gy, SCHARR_Y, transpose=True) + g_dd
+    g_depth = Dy_.T @ g_dh @ Dx_
+    return loss, g_depth, g_normal

@@ -25,7 +25,7 @@ def test_library_loads_and_exports_everything():
     lib = _lib.load()
     for name in _declared():
         assert hasattr(lib, name), name
-    assert lib.ts2d_abi_version() == _lib.ABI_VERSION == 6
+    assert lib.ts2d_abi_version() == _lib.ABI_VERSION == 7
     assert b"vertex must have dimensions" in lib.ts2d_error_string(-1)
     assert lib.ts2d_error_string(0) == b"ok"
 

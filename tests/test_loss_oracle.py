@@ -80,3 +80,82 @@ def test_backward_matches_autograd(images, w_ssim):
     mine = lo.image_loss_backward(img.numpy(), gt.numpy(), 1 - w_ssim, w_ssim)
     scale = np.abs(x.grad.numpy()).max()
     assert np.abs(mine - x.grad.numpy()).max() <= 2e-6 * scale  # fp32-built window of the reference vs the fp64 one here
+
+
+# ---- depth-normal consistency loss (the geometry term) ---------------------------------------------------------------------------
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+DN_CASES = ["half_38x50", "half_odd_37x53", "full_21x25", "half_96x128"]
+
+
+def _load_dn(name):
+    z = np.load(os.path.join(GOLDEN, f"depth_normal_{name}.npz"))
+    sf = float(z["scale_factor"])
+    return z, (None if sf < 0 else sf)
+
+
+def _rel(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / max(float(np.abs(b).max()), 1e-30))
+
+
+@pytest.mark.parametrize("name", DN_CASES)
+def test_depth_normal_oracle_vs_reference_fixtures(name):
+    """oracle/loss.py: depth_normal_loss against the outputs of the reference's own DepthNormalLoss (tests/golden/make_loss_golden.py,
+    fp32 on the CPU): loss to 1e-6, both gradients to 2e-5 of their largest entry (the fixtures are fp32, the oracle fp64)."""
+    z, sf = _load_dn(name)
+    loss, g_depth, g_normal = lo.depth_normal_loss(z["depth"], z["normal"], float(z["tan_fovx"]), float(z["tan_fovy"]), sf, with_grad=True)
+    assert abs(loss - float(z["loss"])) <= 1e-6 * abs(float(z["loss"]))
+    assert _rel(g_depth, z["g_depth"]) <= 2e-5
+    assert _rel(g_normal, z["g_normal"]) <= 2e-5
+
+
+def test_depth_normal_oracle_vs_live_reference_class():
+    """Same comparison against the class itself when the reference tree is present (it is in the build container, not on the GPU box)."""
+    sys.path.insert(0, GOLDEN)
+    import make_loss_golden as mk
+
+    if not os.path.exists(mk.REF):
+        pytest.skip("/root/reference not present")
+    ref = mk.load_reference_module()
+    for h, w, sf in ((30, 44, 0.5), (33, 41, 0.5), (26, 26, None), (24, 40, 1)):
+        depth, normal = mk.scene(h, w, seed=7 * h + w)
+        d, n = depth.clone().requires_grad_(True), normal.clone().requires_grad_(True)
+        loss = ref.DepthNormalLoss(scale_factor=sf)(d, n, 0.6, 0.45)
+        loss.backward()
+        o = lo.depth_normal_loss(depth.numpy(), normal.numpy(), 0.6, 0.45, sf, with_grad=True)
+        assert abs(o[0] - float(loss)) <= 1e-6 * abs(float(loss)), (h, w, sf)
+        assert _rel(o[1], d.grad.numpy()) <= 2e-5 and _rel(o[2], n.grad.numpy()) <= 2e-5, (h, w, sf)
+        # depth_grad / normal_grad = False detach the respective input (:250-253): the other gradient is unchanged
+        d2, n2 = depth.clone().requires_grad_(True), normal.clone().requires_grad_(True)
+        ref.DepthNormalLoss(scale_factor=sf, depth_grad=False)(d2, n2, 0.6, 0.45).backward()
+        assert d2.grad is None and torch.equal(n2.grad, n.grad)
+
+
+def test_depth_normal_oracle_gradient_is_the_derivative():
+    """Central differences in fp64 on the oracle itself (mask held: perturbations far below the distance of any pixel to the threshold)."""
+    z, sf = _load_dn("half_odd_37x53")
+    depth, normal = z["depth"].astype(np.float64), z["normal"].astype(np.float64)
+    args = (float(z["tan_fovx"]), float(z["tan_fovy"]), sf)
+    _, g_depth, g_normal = lo.depth_normal_loss(depth, normal, *args, rank_dtype=np.float64, with_grad=True)
+    rng = np.random.default_rng(0)
+    for _ in range(12):
+        y, x = rng.integers(0, depth.shape[0]), rng.integers(0, depth.shape[1])
+        e = 1e-6
+        dp, dm = depth.copy(), depth.copy()
+        dp[y, x] += e
+        dm[y, x] -= e
+        fd = (lo.depth_normal_loss(dp, normal, *args, rank_dtype=np.float64) - lo.depth_normal_loss(dm, normal, *args, rank_dtype=np.float64)) / (2 * e)
+        assert abs(fd - g_depth[y, x]) <= 1e-6 * max(abs(g_depth).max(), 1e-12) + 1e-4 * abs(g_depth[y, x]), (y, x, fd, g_depth[y, x])
+        c = rng.integers(0, 3)
+        np_, nm = normal.copy(), normal.copy()
+        np_[c, y, x] += e
+        nm[c, y, x] -= e
+        fd = (lo.depth_normal_loss(depth, np_, *args, rank_dtype=np.float64) - lo.depth_normal_loss(depth, nm, *args, rank_dtype=np.float64)) / (2 * e)
+        assert abs(fd - g_normal[c, y, x]) <= 1e-6 * max(abs(g_normal).max(), 1e-12) + 1e-4 * abs(g_normal[c, y, x])
+
+
+def test_torch_quantile_restatement():
+    g = torch.Generator().manual_seed(5)
+    for n in (7, 100, 4097):
+        v = torch.rand(n, generator=g)
+        for q in (0.0, 0.3, 0.9, 1.0):
+            assert abs(lo.torch_quantile(v.numpy(), q) - float(torch.quantile(v, q))) <= 1e-7

@@ -163,6 +163,6 @@ class TriangleRasterizer3D(TriangleRasterizer):
 from .frontend import TriangleModelRasterizer, TrainingStatistics, bilinear_downsample, gamma_rescale_ratio  # noqa: E402
 
 __all__ += ["TriangleModelRasterizer", "TrainingStatistics", "bilinear_downsample", "gamma_rescale_ratio"]
-from .loss import ImageLoss, image_loss  # noqa: E402
+from .loss import DepthNormalLoss, ImageLoss, depth_normal_loss, image_loss  # noqa: E402
 
-__all__ += ["ImageLoss", "image_loss"]
+__all__ += ["ImageLoss", "image_loss", "DepthNormalLoss", "depth_normal_loss"]

@@ -105,6 +105,11 @@ SYMBOLS = {
                                           C.c_void_p, C.c_size_t, C.c_void_p]),
     "ts2d_image_loss_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                            C.c_size_t, C.c_void_p, C.c_void_p]),
+    "ts2d_depth_normal_loss_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "ts2d_depth_normal_loss_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_void_p,
+                                                 C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ts2d_depth_normal_loss_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p]),
     "ts2d_downsample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "ts2d_downsample_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "ts2d_export_binning": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
@@ -114,7 +119,7 @@ SYMBOLS = {
     "ts2d_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
 
-ABI_VERSION = 6  # TS2D_ABI_VERSION (include/ts2d.h)
+ABI_VERSION = 7  # TS2D_ABI_VERSION (include/ts2d.h)
 PRIMITIVES = {"2D": 0, "3D": 1}  # TS2D_PRIMITIVE_* (include/ts2d.h)
 STAGES = ("preprocess", "order_scan", "binning", "render_fwd", "render_bwd", "preprocess_bwd", "bwd_prepare", "bwd_reduce")
 

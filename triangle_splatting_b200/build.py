@@ -17,7 +17,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libts2d.so"
-SOURCES = ["ts2d_api.cu", "ts2d_preprocess.cu", "ts2d_binning.cu", "ts2d_render_fwd.cu", "ts2d_render_bwd.cu", "ts2d_render_fwd_fast.cu", "ts2d_render_bwd_fast.cu", "ts2d_bwd_reduce.cu", "ts2d_exchange.cu", "ts2d_prim3d.cu", "ts2d_prim3d_fast.cu", "ts2d_loss.cu"]
+SOURCES = ["ts2d_api.cu", "ts2d_preprocess.cu", "ts2d_binning.cu", "ts2d_render_fwd.cu", "ts2d_render_bwd.cu", "ts2d_render_fwd_fast.cu", "ts2d_render_bwd_fast.cu", "ts2d_bwd_reduce.cu", "ts2d_exchange.cu", "ts2d_prim3d.cu", "ts2d_prim3d_fast.cu", "ts2d_loss.cu", "ts2d_geometry_loss.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # NOTE: no --use_fast_math: bit-exact tile binning needs IEEE div/sqrt and the default FMA contraction.
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + ARCH
