@@ -85,7 +85,7 @@ size_t carve_geometry(void *blob, int32_t P, GeomState *gs)
     g.tiles = c.take<uint32_t>(n);
     g.rect = c.take<ushort4>(n);
     g.offs = c.take<uint32_t>(n);
-    g.estart = c.take<uint32_t>(n);
+    g.binrec = c.take<uint4>(n);
     g.csum64 = c.take<unsigned long long>(n);
     g.clamp = c.take<uint8_t>(n);
     if (gs) *gs = g;

@@ -54,7 +54,7 @@ template <int MASKS, bool SHARDED>
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_emit_warp(int P, int gx, float gamma, EmitCam cam, int shard_rank, int shard_world, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
             const ushort4 *__restrict__ rect, const uint32_t *__restrict__ offs, const float4 *__restrict__ rec0, uint32_t cap, uint32_t *__restrict__ tkey,
-            uint32_t *__restrict__ tval, uint32_t *__restrict__ estart, uint2 *__restrict__ ranges)
+            uint32_t *__restrict__ tval, uint4 *__restrict__ binrec, uint2 *__restrict__ ranges)
 {
     const int lane = threadIdx.x & 31;
     const int r = (blockIdx.x * blockDim.x + threadIdx.x);
@@ -68,7 +68,7 @@ k_emit_warp(int P, int gx, float gamma, EmitCam cam, int shard_rank, int shard_w
         const ushort4 rc = rect[id];
         rc_lo = (uint32_t)rc.x | ((uint32_t)rc.y << 16);
         rc_hi = (uint32_t)rc.z | ((uint32_t)rc.w << 16);
-        if (n) estart[id] = end - n;
+        if (n) binrec[id] = make_uint4(rc_lo, rc_hi, end - n, n);  // one record per triangle for the backward's row marking
     } else {
         end = offs[P - 1];
     }
@@ -223,7 +223,7 @@ int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts
     const int blocks = (P + TS2D_BLOCK - 1) / TS2D_BLOCK;
     const EmitCam ec = {cam->width, cam->height, cam->tan_fovx, cam->tan_fovy};
     const uint32_t cap32 = (uint32_t)(bs.cap < 0xFFFFFFFFll ? bs.cap : 0xFFFFFFFFll);
-#define TS2D_EMIT_ARGS P, gx, g->gamma, ec, f->shard_rank, f->shard_world, gs.ids2, gs.tiles, gs.rect, gs.offs, gs.rec0, cap32, bs.tkey[0], bs.tval[0], gs.estart, is.ranges
+#define TS2D_EMIT_ARGS P, gx, g->gamma, ec, f->shard_rank, f->shard_world, gs.ids2, gs.tiles, gs.rect, gs.offs, gs.rec0, cap32, bs.tkey[0], bs.tval[0], gs.binrec, is.ranges
     if (f->shard_world > 1) {
         if (masks == 2) k_emit_warp<2, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
         else if (masks == 1) k_emit_warp<1, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);

@@ -10,7 +10,7 @@
 //
 //   k_bwd_rows_mark    per sorted list position: live sub-tile bits (coverage bit still set after the forward pass AND position
 //                      below the sub-tile's own last contributor `lastw`), written back into the instance key (the backward
-//                      kernel reads them there); emission index ei of the instance (from estart[id] and the tile's place in
+//                      kernel reads them there); emission index ei of the instance (from binrec[id] and the tile's place in
 //                      the triangle's rect) -> ei[pos], popcount -> cnt[ei]
 //   ts2d_scan          exclusive scan of cnt over emission indices -> sbase (row of emission index e starts at sbase[e])
 //   composite backward row of (pos, sub-tile w) = sbase[ei[pos]] + popc(live bits below w): one 16-byte store per quarter-lane
@@ -20,14 +20,14 @@
 
 namespace {
 
-// MK positions per thread.  The kernel is a chain of gathers (key -> tile -> ranges / lastw, list -> rect / estart) whose limit is the
+// MK positions per thread.  The kernel is a chain of gathers (key -> tile -> ranges / lastw, list -> the triangle's 16-byte bin record) whose limit is the
 // L2 transaction rate (ncu: l1tex 77 %, lts 59 % of peak), not latency: 4 positions per thread cost 92 registers and two thirds of
 // the occupancy for nothing (129 us against 118 us with one position and 31 registers).
 constexpr int MK = 1;
 __global__ void __launch_bounds__(TS2D_BLOCK)
 k_bwd_rows_mark(const int64_t *__restrict__ n_dev, int64_t cap, int gx, int shard_rank, int shard_world, uint32_t *tkey, const uint32_t *__restrict__ list,
-                const uint2 *__restrict__ ranges, const uint32_t *__restrict__ lastw, const ushort4 *__restrict__ rect,
-                const uint32_t *__restrict__ estart, uint32_t *__restrict__ ei_out, uint8_t *__restrict__ cnt)
+                const uint2 *__restrict__ ranges, const uint32_t *__restrict__ lastw, const uint4 *__restrict__ binrec,
+                uint32_t *__restrict__ ei_out, uint8_t *__restrict__ cnt)
 {
     const int64_t R = rs_count(n_dev, cap);
     const int64_t p0 = (int64_t)blockIdx.x * (blockDim.x * MK) + threadIdx.x;
@@ -42,15 +42,15 @@ k_bwd_rows_mark(const int64_t *__restrict__ n_dev, int64_t cap, int gx, int shar
     }
     uint32_t first[MK], est[MK];
     uint4 l0[MK], l1[MK];
-    ushort4 rc[MK];
+    uint4 br[MK];
 #pragma unroll
     for (int u = 0; u < MK; u++) {
         const uint32_t tile = key[u] >> TS2D_MASK_BITS;
         first[u] = ok[u] ? ranges[tile].x : 0u;
         l0[u] = ok[u] ? __ldg(reinterpret_cast<const uint4 *>(lastw + 8 * (size_t)tile)) : make_uint4(0, 0, 0, 0);
         l1[u] = ok[u] ? __ldg(reinterpret_cast<const uint4 *>(lastw + 8 * (size_t)tile) + 1) : make_uint4(0, 0, 0, 0);
-        rc[u] = ok[u] ? rect[id[u]] : make_ushort4(0, 0, 1, 1);
-        est[u] = ok[u] ? estart[id[u]] : 0u;
+        br[u] = ok[u] ? __ldg(binrec + id[u]) : make_uint4(0u, 0x00010001u, 0u, 0u);
+        est[u] = br[u].z;
     }
 #pragma unroll
     for (int u = 0; u < MK; u++) {
@@ -63,7 +63,8 @@ k_bwd_rows_mark(const int64_t *__restrict__ n_dev, int64_t cap, int gx, int shar
                 (rel < l1[u].y ? 32u : 0u) | (rel < l1[u].z ? 64u : 0u) | (rel < l1[u].w ? 128u : 0u);
         if (live != (key[u] & 0xFFu)) tkey[pos] = (key[u] & ~0xFFu) | live;
         const uint32_t ty = tile / (uint32_t)gx, tx = tile - ty * (uint32_t)gx;
-        const ushort4 r = rc[u];
+        const ushort4 r = make_ushort4((unsigned short)(br[u].x & 0xffffu), (unsigned short)(br[u].x >> 16), (unsigned short)(br[u].y & 0xffffu),
+                                       (unsigned short)(br[u].y >> 16));
         uint32_t k;
         if (shard_world == 1) {
             k = (ty - r.y) * (uint32_t)(r.z - r.x) + (tx - r.x);
@@ -170,7 +171,7 @@ int ts2d_launch_bwd_rows_prepare(const ts2d_camera *cam, const ts2d_flags *f, Ge
     const int64_t *n_dev = &gs.hdr->num_rendered;
     if (bs.cap <= 0) return 0;
     k_bwd_rows_mark<<<(unsigned)((bs.cap + TS2D_BLOCK * MK - 1) / (TS2D_BLOCK * MK)), TS2D_BLOCK, 0, s>>>(n_dev, bs.cap, gx, f->shard_rank, f->shard_world, bs.tkey[sbuf],
-                                                                                             bs.tval[sbuf], is.ranges, is.lastw, gs.rect, gs.estart,
+                                                                                             bs.tval[sbuf], is.ranges, is.lastw, gs.binrec,
                                                                                              sc.ei, sc.cnt);
     TS2D_CUDA_TRY(cudaGetLastError());
     // sbase = exclusive scan of cnt over emission indices, sbase[R] = number of rows

@@ -10,7 +10,8 @@
 //     tiles  u32[P]       number of (owned) tiles in the triangle's rect
 //     rect   ushort4[P]   {min.x, min.y, max.x, max.y} in tiles
 //     offs   u32[P]       inclusive scan of tiles[] in depth-rank order
-//     estart u32[P]       first emission index of the triangle's instances (offs[rank] - tiles), by triangle id
+//     binrec uint4[P]     {rect.x | rect.y << 16, rect.z | rect.w << 16, first emission index (offs[rank] - tiles), tiles}, by triangle
+//                         id: what the backward's row marking needs about the triangle of an instance, in ONE 16-byte gather
 //     clamp  u8[P]        SH clamp mask (bit c set <=> channel c clamped at 0)
 //     hdr    GeomHeader   R (num_rendered) and the other device-side counters of a frame
 //     status / sstatus    look-back words of the depth sort's passes / of the scan (ts2d_sort.cuh)
@@ -73,7 +74,7 @@ struct GeomState {
     uint32_t *tiles;
     ushort4 *rect;
     uint32_t *offs;
-    uint32_t *estart;
+    uint4 *binrec;
     unsigned long long *csum64;  // contrib_sum in 2^-32 fixed point (fast forward kernels)
     uint8_t *clamp;
     GeomHeader *hdr;

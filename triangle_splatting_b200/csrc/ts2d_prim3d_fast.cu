@@ -481,6 +481,7 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
         for (int j = 0; j < count; j++, ea += F3_EB) {
             const float4 e0 = lds128(ea), e1 = lds128(ea + 16), e2 = lds128(ea + 32), e4 = lds128(ea + 64);
             const uint32_t pos = __float_as_uint(e4.w);
+            const uint32_t info_slot = lds32(sb + L::SLOT + 4 * j);  // for the panel's INFO row: requested early, used after the pair evaluation
             float w_c = 0.0f, w_op = 0.0f, w_D = 0.0f, w_a1 = 0.0f, w_a2 = 0.0f;
             bool visited = false;  // NOT "contrib != 0": the backward's cut is on G, so a pair with op == 0 still feeds dL/dop
             if (pos < last) {
@@ -539,7 +540,7 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
                 sts128(ia, e0);
                 sts128(ia + 16, e1);
                 sts128(ia + 32, e2);
-                sts128(ia + 48, make_float4(e4.x, e4.y, e4.z, __uint_as_float(lds32(sb + L::SLOT + 4 * j))));
+                sts128(ia + 48, make_float4(e4.x, e4.y, e4.z, __uint_as_float(info_slot)));
             }
             if (++prow == B3_ROWS) {
                 flush_panel(B3_ROWS);

@@ -263,6 +263,9 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
         for (int j = 0; j < count; j++, ea += L::EB) {
             const float4 e1 = lds128(ea), e2 = lds128(ea + 16);
             const uint32_t pos = lds32(sb + L::POS + j * L::POS_STRIDE);
+            // id and row index of the entry, for the panel's INFO row: requested here so that their latency hides behind the pair
+            // evaluation (the shared-memory helpers are volatile asm: the compiler keeps them where they are written)
+            const uint32_t info_id = lds32(ea + 44), info_slot = lds32(sb + L::SLOT + j * L::POS_STRIDE);
             float w_c = 0.0f, w_op = 0.0f, w_D = 0.0f;
             if (pos < last) {
                 FastPair f;
@@ -328,8 +331,8 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                 const uint32_t ia = sb + L::INFO + prow * 48;
                 sts128(ia, e1);
                 sts128(ia + 16, e2);
-                sts32(ia + 32, lds32(ea + 44));
-                sts32(ia + 36, lds32(sb + L::SLOT + j * L::POS_STRIDE));
+                sts32(ia + 32, info_id);
+                sts32(ia + 36, info_slot);
             }
             if (++prow == BW_ROWS) {
                 flush_panel(BW_ROWS);
