@@ -282,7 +282,7 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                     unc = unc || (fmaxf(lo12, fminf(hi12, f.a3)) - fminf(lo12, f.a3) <= TS2D_ARGMIN_TIE);
                 }
                 if (unc) {
-                    const float area2 = __ldg(&rec0[3 * (size_t)lds32(ea + 44) + 2].w);
+                    const float area2 = __ldg(&rec0[3 * (size_t)info_id + 2].w);
                     PairEval e;
                     hit = eval_exact(e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, area2, e2.w, gk.two_gamma, pxf, pyf, e);
                     f.a1 = e.a1; f.a2 = e.a2; f.a3 = e.a3; f.ecc = e.ecc;

@@ -187,10 +187,13 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
         }
         __syncwarp();
         // ---- walk
+        // software-pipelined by one entry: the vertex words of entry j + 1 are requested before the panel store of entry j (a shared
+        // load cannot be moved above a store that may alias it, so at the top of the iteration it would sit behind that store with
+        // its whole latency in front of the pair evaluation; one entry past the staged ones is read and never used)
         uint32_t ea = sb, prow = sb + L::PANEL;
         int visited = count;
+        float4 e1 = lds128(ea), e2 = lds128(ea + 16);
         for (int j = 0; j < count; j++, ea += L::EB, prow += FW_PROW * 4) {
-            const float4 e1 = lds128(ea), e2 = lds128(ea + 16);
             float contrib = 0.0f;  // > 0 <=> this lane blended the triangle
             bool evt = false;      // this lane's transmittance reached the 1e-4 cut or its error band: handled out of line below
             if (!done) {
@@ -199,26 +202,35 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                 bool hit = eval_fast(e1, e2, pxf, pyf, gk, f, unc);
                 if (unc) hit = exact_pair(e1, e2, rec0, lds32(ea + 44), gk.two_gamma, pxf, pyf, f.alpha, f.power, f.a1, f.a2, f.a3);
                 if (hit) {
-                    contrib = f.alpha * T;
+                    // the entry's colour / normal / depth words are requested first and consumed last: the shared-memory helpers are
+                    // volatile asm, so the compiler leaves the loads where they are written and the transmittance update runs under them
                     const float4 col = lds128(ea + 32);
-                    acc01 = fma2(bc(contrib), mk2v(col.x, col.y), acc01);
-                    acc2 = fmaf(contrib, col.z, acc2);
+                    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float2 q1 = make_float2(0.f, 0.f);
                     if constexpr (RICH) {
-                        const float4 q0 = lds128(ea + 48);
-                        const float2 q1 = lds64(ea + 64);
-                        accn01 = fma2(bc(contrib), mk2v(q0.x, q0.y), accn01);
-                        accn2 = fmaf(contrib, q0.z, accn2);
-                        accd = fmaf(contrib, fmaf(f.a3, q1.y, fmaf(q0.w, f.a1, q1.x * f.a2)), accd);
+                        q0 = lds128(ea + 48);
+                        q1 = lds64(ea + 64);
                     }
+                    contrib = f.alpha * T;
                     const float om = 1.0f - f.alpha;
                     // |T_new - T_ref_new| <= |T - T_ref| * om + T * |d alpha| + rounding of the two product chains
                     Terr = fmaf(Terr, om, contrib * (unc ? 0.0f : fmaf(gk.terr_c1, fabsf(f.power), gk.terr_c0)));
                     T *= om;
                     Terr = fmaf(T, 1.3e-7f, Terr);
                     evt = (T - 0.0001f) <= Terr;  // saturated (T <= 1e-4) or within the error band of the cut
+                    acc01 = fma2(bc(contrib), mk2v(col.x, col.y), acc01);
+                    acc2 = fmaf(contrib, col.z, acc2);
+                    if constexpr (RICH) {
+                        accn01 = fma2(bc(contrib), mk2v(q0.x, q0.y), accn01);
+                        accn2 = fmaf(contrib, q0.z, accn2);
+                        accd = fmaf(contrib, fmaf(f.a3, q1.y, fmaf(q0.w, f.a1, q1.x * f.a2)), accd);
+                    }
                 }
             }
+            const float4 n1 = lds128(ea + L::EB), n2 = lds128(ea + L::EB + 16);
             if constexpr (RICH) sts32f(prow + lane * 4, contrib);
+            e1 = n1;
+            e2 = n2;
             if (__any_sync(0xffffffffu, evt)) {  // at most a few times per pixel: everything about saturation lives here
                 const uint32_t pos = lds32(sb + L::POS + j * L::POS_STRIDE);
                 const float dT = T - 0.0001f;
