@@ -90,20 +90,23 @@ def test_one_enqueue_forward_equals_two_call_forward(cuda_device):
     from triangle_splatting_b200.scenes import make_config
 
     sc = make_config("C2", P=60_000, width=640, height=480)
-    old, old_margin = _C.SYNC_FORWARD, _C.CAPACITY_MARGIN
+    old = _C.configure(sync_forward=True, sync_backward=True)
     try:
-        _C.SYNC_FORWARD = True
-        _C._R_SEEN.clear()
+        _C.forget_shapes()
         two_call = harness.run_ours(sc, cuda_device)
-        _C.SYNC_FORWARD = False
-        assert _C._R_SEEN, "the two-call forward must have recorded R"
-        one = harness.run_ours(sc, cuda_device)  # capacity from the recorded R: the one-enqueue path
-        _C.CAPACITY_MARGIN = 0
-        for key in list(_C._R_SEEN):
-            _C._R_SEEN[key] = 1  # capacity guess far too small -> overflow -> repeated render
+        _C.configure(sync_forward=False, sync_backward=False)
+        r_seen, rows_seen = _C.shapes_seen()
+        assert r_seen > 0, "the two-call forward must have recorded R"
+        assert rows_seen > 0, "the backward must have recorded its row count"
+        one = harness.run_ours(sc, cuda_device)  # capacities from the recorded R / rows: the one-enqueue paths (forward and backward)
+        _C.configure(capacity_margin=0, rows_margin=0)
+        # capacity guesses far too small -> the frame overflows the binning state -> repeated render; the backward's row array drops
+        # rows -> composite repeated with the exact size
+        _C.poison_shapes(1, 1)
         repaired = harness.run_ours(sc, cuda_device)
+        assert _C.shapes_seen() == (r_seen, rows_seen), "the repairs must have recorded the true counts"
     finally:
-        _C.SYNC_FORWARD, _C.CAPACITY_MARGIN = old, old_margin
+        _C.configure(*old)
     for k, v in two_call.items():
         assert np.array_equal(one[k], v), f"one-enqueue forward: {k} differs"
         assert np.array_equal(repaired[k], v), f"repeated render after an overflow: {k} differs"

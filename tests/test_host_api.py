@@ -40,7 +40,38 @@ def test_derive_matches_reference_rules():
     assert _C._derive(v, torch.zeros(5, 4, 3), torch.zeros(0, 3)) == (5, True, 3, 4)
 
 
-def test_cpu_tensors_fail_loudly():
+@pytest.fixture(params=["native", "ctypes"])
+def host_layer(request, monkeypatch):
+    """Both host layers over the C ABI: the compiled pybind11 module (csrc/ts2d_pybind.cpp) and the ctypes code of _C.py."""
+    if request.param == "native":
+        assert _C.native() is not None, "the compiled host layer must be built (python -m triangle_splatting_b200.build)"
+    else:
+        monkeypatch.setattr(_C, "_NATIVE", False)
+    return request.param
+
+
+def test_compiled_host_layer_mirrors_the_reference_pybind_module():
+    """R2D/ext.cpp:4-9: a pybind11 module with rasterize_triangles / rasterize_triangles_backward, here on top of the C ABI."""
+    from triangle_splatting_b200 import _lib
+
+    nat = _C.native()
+    assert nat is not None and nat.__name__.endswith("_C_native")
+    assert nat.abi_version() == _lib.ABI_VERSION
+    for n in ("rasterize_triangles", "rasterize_triangles_backward", "FrameCounters", "configure", "forget_shapes"):
+        assert hasattr(nat, n)
+    doc = nat.rasterize_triangles.__doc__
+    # the reference's positional order (extension_interface.cu:19-40)
+    order = ["image_width", "image_height", "tan_fovx", "tan_fovy", "viewmatrix", "projmatrix", "campos", "sh_degree", "gamma", "scale_modifier",
+             "background_depth", "background", "vertex", "shs", "feature", "opacity", "back_culling", "rich_info", "debug"]
+    pos = [doc.index(n + ":") for n in order]
+    assert pos == sorted(pos)
+    old = _C.configure()
+    assert _C.configure(sync_forward=True)[0] == old[0] and nat.configure()[0] is True
+    _C.configure(*old)
+    assert tuple(nat.configure()) == tuple(old)
+
+
+def test_cpu_tensors_fail_loudly(host_layer):
     """There is no CPU fallback: CPU inputs must raise, not silently compute."""
     sc = make_scene("x", 4, 32, 32)
     args = harness._fwd_args(sc)
@@ -48,7 +79,7 @@ def test_cpu_tensors_fail_loudly():
         _C.rasterize_triangles(*args)
 
 
-def test_argument_errors_precede_device_work():
+def test_argument_errors_precede_device_work(host_layer):
     sc = make_scene("x", 4, 32, 32)
     args = list(harness._fwd_args(sc))
     args[12] = sc.vertex.reshape(4, 9)

@@ -44,3 +44,8 @@ t2 = time.perf_counter()
 torch.cuda.synchronize()
 print(f"forward + backward, 200 triangles, 64x64: {1e6 * (t1 - t0) / n:.0f} us per step with a synchronise per step, "
       f"{1e6 * (t2 - t1) / n:.0f} us of host time per step when the queue is left to run")
+from triangle_splatting_b200 import _C  # noqa: E402
+
+nat = _C.native()
+print(f"host layer: {'compiled _C_native' if nat is not None else 'ctypes'}; counter handles created: "
+      f"{nat.counters_created() if nat is not None else _C.FrameCounters.created} over {20 + 2 * n} steps")

@@ -49,6 +49,87 @@ def set_exact(flag: bool) -> bool:
 SYNC_FORWARD = os.environ.get("TS2D_SYNC_FORWARD", "0") == "1"
 _R_SEEN = {}  # (device index, P, W, H, primitive, shard) -> largest R seen
 CAPACITY_MARGIN = 1 << 20  # instances added on top of the largest R seen (16 B each: memory is not what limits this path)
+# Backward, same idea: the row array of the atomics-free gradient write-back is sized from the largest row count seen for the
+# shape, the whole backward pass is enqueued, and only then the frame's true row count is read (it landed with the end of the
+# forward pass, so the wait never stalls the queue); the kernels never store past the capacity, a frame that needed more rows is
+# composited again with the exact size.  TS2D_SYNC_BACKWARD=1 waits for the count first.
+SYNC_BACKWARD = os.environ.get("TS2D_SYNC_BACKWARD", "0") == "1"
+_ROWS_SEEN = {}  # (device index, P, W, H, primitive, shard) -> largest backward row count seen
+ROWS_MARGIN = 1 << 16  # rows (64 B each) on top of 1.25 x the largest count seen
+
+# Host layer of the reference-shaped single-GPU call: the compiled pybind11 module _C_native (csrc/ts2d_pybind.cpp -- what the
+# reference's ext.cpp / extension_interface.cu are to its library) when it is built, else the ctypes code below; both sit on the same
+# C ABI and the same libts2d.so.  TS2D_HOST=ctypes forces the Python layer, TS2D_HOST=native makes a missing module an error.
+# The tile-sharded and the parameter-space calls always take the ctypes layer.
+HOST = os.environ.get("TS2D_HOST", "auto")
+_NATIVE = None
+
+
+def native():
+    """The compiled host layer, or None."""
+    global _NATIVE
+    if _NATIVE is None:
+        _NATIVE = False
+        if HOST != "ctypes":
+            try:
+                from . import build as _build
+
+                _lib.load()
+                if os.environ.get("TS2D_NO_AUTOBUILD", "0") != "1" and _build.native_needs_build():
+                    _build.build_native()
+                from . import _C_native
+
+                if _C_native.abi_version() != _lib.ABI_VERSION:
+                    raise RuntimeError(f"_C_native was built against ABI {_C_native.abi_version()}, this package binds {_lib.ABI_VERSION}")
+                _C_native.configure(SYNC_FORWARD, SYNC_BACKWARD, CAPACITY_MARGIN, ROWS_MARGIN)
+                _NATIVE = _C_native
+            except Exception as ex:  # noqa: BLE001  -- the ctypes layer does the same job (same library, same kernels)
+                if HOST == "native":
+                    raise
+                import warnings
+
+                warnings.warn(f"triangle_splatting_b200: compiled host layer _C_native unavailable ({ex}); using the ctypes layer")
+    return _NATIVE or None
+
+
+def configure(sync_forward=None, sync_backward=None, capacity_margin=None, rows_margin=None):
+    """Knobs of the one-enqueue paths, for both host layers; returns the previous (sync_forward, sync_backward, capacity_margin, rows_margin)."""
+    global SYNC_FORWARD, SYNC_BACKWARD, CAPACITY_MARGIN, ROWS_MARGIN
+    old = (SYNC_FORWARD, SYNC_BACKWARD, CAPACITY_MARGIN, ROWS_MARGIN)
+    SYNC_FORWARD = SYNC_FORWARD if sync_forward is None else bool(sync_forward)
+    SYNC_BACKWARD = SYNC_BACKWARD if sync_backward is None else bool(sync_backward)
+    CAPACITY_MARGIN = CAPACITY_MARGIN if capacity_margin is None else int(capacity_margin)
+    ROWS_MARGIN = ROWS_MARGIN if rows_margin is None else int(rows_margin)
+    if native() is not None:
+        native().configure(SYNC_FORWARD, SYNC_BACKWARD, CAPACITY_MARGIN, ROWS_MARGIN)
+    return old
+
+
+def forget_shapes():
+    """Drop the instance / row counts remembered per problem shape (the next frame of every shape takes the synchronous path)."""
+    _R_SEEN.clear()
+    _ROWS_SEEN.clear()
+    if native() is not None:
+        native().forget_shapes()
+
+
+def poison_shapes(r: int = 1, rows: int = 1):
+    """Tests: pretend every shape seen so far had `r` instances and `rows` backward rows (forces the overflow repairs)."""
+    for k in _R_SEEN:
+        _R_SEEN[k] = r
+    for k in _ROWS_SEEN:
+        _ROWS_SEEN[k] = rows
+    if native() is not None:
+        native().poison_shapes(r, rows)
+
+
+def shapes_seen():
+    """-> (largest R remembered, largest backward row count remembered) over both host layers."""
+    r, rows = max(_R_SEEN.values(), default=0), max(_ROWS_SEEN.values(), default=0)
+    if native() is not None:
+        _, nr, _, nrows = native().shapes_seen()
+        r, rows = max(r, nr), max(rows, nrows)
+    return r, rows
 
 
 def _capacity_for(key):
@@ -62,6 +143,7 @@ class FrameCounters:
     """ts2d_counters handle: pinned host memory + events for the device-side counters of one forward pass."""
 
     _free = []
+    created = 0  # handles made so far (a steady-state training loop reuses the ones it gave back)
 
     def __init__(self):
         lib = _lib.load()
@@ -70,6 +152,7 @@ class FrameCounters:
         else:
             h = C.c_void_p()
             _lib.check(lib.ts2d_counters_create(C.byref(h)), "ts2d_counters_create")
+            FrameCounters.created += 1
             self.h = h
 
     def num_rendered(self) -> int:
@@ -216,6 +299,12 @@ def rasterize_triangles(image_width: int, image_height: int, tan_fovx: float, ta
     """-> (num_rendered:int, out_feature, radii, depth, normal, contrib_sum, contrib_max, geometryBuffer, binningBuffer, imageBuffer)
 
     Mirrors rasterizeTrianglesForward (extension_interface.cu:19-152)."""
+    nat = native() if (model is None and shard[1] <= 1) else None
+    if nat is not None:
+        out = nat.rasterize_triangles(image_width, image_height, tan_fovx, tan_fovy, viewmatrix, projmatrix, campos, sh_degree, gamma, scale_modifier,
+                                      background_depth, background, vertex, shs, feature, opacity, back_culling, rich_info, debug,
+                                      _lib.PRIMITIVES[primitive], EXACT)
+        return (NumRendered(out[0], out[10]),) + out[1:10]
     lib = _lib.load()
     if model is not None:  # parameter-space inputs: shs / opacity come from the model's raw tensors
         shs = feature = opacity = torch.empty(0)
@@ -360,6 +449,14 @@ def rasterize_triangles_backward(tan_fovx: float, tan_fovy: float, viewmatrix: t
     With `model` (parameter-space inputs) the tuple is (dL_d_vertex, dL_dcenter2D, dL_d_f_dc (P,1,3), dL_d_f_rest (P,M-1,3),
     dL_d_opacity_logit (P,1)); `stats` (dict of the six (P,) tensors of VanillaTS_model.py:196-201, any subset) is updated in
     place for the visible triangles, `fwd_contrib` = (contrib_sum, contrib_max) of the forward pass."""
+    nat = native() if (model is None and shard[1] <= 1 and stats is None) else None
+    if nat is not None:
+        ctr = getattr(num_rendered, "counters", None)
+        if ctr is None or isinstance(ctr, nat.FrameCounters):
+            return nat.rasterize_triangles_backward(tan_fovx, tan_fovy, viewmatrix, projmatrix, campos, sh_degree, gamma, scale_modifier, background_depth,
+                                                    background, vertex, shs, feature, opacity, int(num_rendered), radii, geometryBuffer, binningBuffer,
+                                                    imageBuffer, dL_dout_feature, dL_dout_depth, dL_dout_normal, rich_info, debug, ctr,
+                                                    _lib.PRIMITIVES[primitive], EXACT)
     lib = _lib.load()
     if model is not None:
         shs = feature = opacity = torch.empty(0, device=vertex.device)
@@ -413,48 +510,62 @@ def rasterize_triangles_backward(tan_fovx: float, tan_fovy: float, viewmatrix: t
         # rows of the atomics-free gradient write-back: from the counters the forward pass left behind (no wait in practice: that
         # forward finished long ago); a plain int (a caller that built the arguments itself) costs one blocking read
         ctr = getattr(num_rendered, "counters", None)
+        rows_key = (dev.index, P, W, H, primitive, tuple(shard))
+        rows = None  # the frame's row count, once known
         if EXACT or not (0.6 <= float(gamma) <= 64.0):
-            rows = 0
+            rows = rows_cap = 0
+        elif ctr is not None and not SYNC_BACKWARD and not debug and rows_key in _ROWS_SEEN:
+            rows_cap = _ROWS_SEEN[rows_key] + _ROWS_SEEN[rows_key] // 4 + ROWS_MARGIN  # checked against the true count below
         elif ctr is not None:
-            rows = ctr.backward_rows()
+            rows = rows_cap = ctr.backward_rows()
         else:
             fcn = _lib.FrameCounters()
             _lib.check(lib.ts2d_read_counters(_ptr(geometryBuffer), P, C.byref(fcn), stream), "ts2d_read_counters")
-            rows = int(fcn.backward_rows)
+            rows = rows_cap = int(fcn.backward_rows)
         bbytes = binningBuffer.numel()
-        sbytes = lib.ts2d_backward_scratch_bytes(P, bbytes, rows)
-        scratch = torch.empty((sbytes,), device=dev, dtype=torch.uint8)
         loss = _lib.LossIn(_ptr(dL_dout_feature), _ptr(dL_dout_depth) if rich_info else None, _ptr(dL_dout_normal) if rich_info else None)
         out = _lib.BackwardOut(_ptr(dL_dvertex), _ptr(dL_dcenter2D), _ptr(dL_dshs), _ptr(dL_dfeature), _ptr(dL_dopacity),
                                C.cast(C.pointer(mgrads), C.c_void_p) if mgrads is not None else None)
-        if shard[1] > 1:
-            # tile-sharded: composite over this rank's tiles -> this rank's partial per-triangle sums (the first 16 P floats of the
-            # scratch, themselves bit-reproducible), summed over the ranks, then the per-triangle stage runs replicated on
-            # identical data -> identical gradients everywhere
-            from . import distributed
-
-            fab = _fabric_for(shard, dev)
-            if fab is not None:
-                # over peer memory: the partial sums go straight into this rank's replica of a symmetric array; every rank combines
-                # its slice of the triangles inside the switch and writes it back to all replicas (include/ts2d.h: ts2d_exchange_allreduce)
-                acc, acc_mc, acc_h = fab.buffer("accumulators", 16 * P)
-            else:
-                acc, acc_mc, acc_h = scratch[:64 * P].view(torch.float32), None, None
+        # tile-sharded over peer memory: the partial sums go straight into this rank's replica of a symmetric array
+        fab = _fabric_for(shard, dev) if shard[1] > 1 else None
+        acc_mc = acc_h = None
+        if fab is not None:
+            acc, acc_mc, acc_h = fab.buffer("accumulators", 16 * P)
+        while True:
+            sbytes = lib.ts2d_backward_scratch_bytes(P, bbytes, rows_cap)
+            scratch = torch.empty((sbytes,), device=dev, dtype=torch.uint8)
+            if rows is not None and shard[1] == 1:  # row count known up front: the whole pass in one call
+                _lib.check(lib.ts2d_backward(C.byref(cam), C.byref(geom), C.byref(flags), _ptr(radii), _ptr(geometryBuffer), _ptr(binningBuffer),
+                                             bbytes, _ptr(imageBuffer), C.byref(loss), C.byref(out), _ptr(scratch), sbytes, stream), "ts2d_backward")
+                break
+            # composite (K8 + row reduction) -> per-triangle sums: the first 16 P floats of the scratch, or the symmetric array
+            if fab is None:
+                acc = scratch[:64 * P].view(torch.float32)
             _lib.check(lib.ts2d_backward_composite(C.byref(cam), C.byref(geom), C.byref(flags), _ptr(geometryBuffer), _ptr(binningBuffer), bbytes,
                                                    _ptr(imageBuffer), C.byref(loss), _ptr(scratch), sbytes, _ptr(acc) if fab is not None else None,
                                                    stream), "ts2d_backward_composite")
-            if fab is not None:
-                acc_h.barrier(channel=0)
-                first, count = _home_slice(16 * P, shard[0], shard[1])
-                _lib.check(lib.ts2d_exchange_allreduce(C.c_void_p(acc_mc), first, count, _lib.EXCHANGE_ADD_F32, stream), "ts2d_exchange_allreduce")
-                acc_h.barrier(channel=0)
-            else:
-                distributed.reduce_accumulators(acc)
+            if rows is None:
+                rows = ctr.backward_rows()  # landed with the end of the forward pass: the composite above is already queued behind it
+                if rows > rows_cap:
+                    rows_cap = rows  # the guess was too small (rows beyond it were dropped): composite again, exact size
+                    continue
+            if shard[1] > 1:
+                # sum the ranks' partial sums, then the per-triangle stage runs replicated on identical data -> identical gradients
+                if fab is not None:
+                    # every rank combines its slice of the triangles inside the switch and writes it back to all replicas
+                    acc_h.barrier(channel=0)
+                    first, count = _home_slice(16 * P, shard[0], shard[1])
+                    _lib.check(lib.ts2d_exchange_allreduce(C.c_void_p(acc_mc), first, count, _lib.EXCHANGE_ADD_F32, stream), "ts2d_exchange_allreduce")
+                    acc_h.barrier(channel=0)
+                else:
+                    from . import distributed
+
+                    distributed.reduce_accumulators(acc)
             _lib.check(lib.ts2d_backward_geometry(C.byref(cam), C.byref(geom), C.byref(flags), _ptr(radii), _ptr(geometryBuffer),
                                                   C.byref(out), _ptr(acc), 64 * P, stream), "ts2d_backward_geometry")
-        else:
-            _lib.check(lib.ts2d_backward(C.byref(cam), C.byref(geom), C.byref(flags), _ptr(radii), _ptr(geometryBuffer), _ptr(binningBuffer),
-                                         bbytes, _ptr(imageBuffer), C.byref(loss), C.byref(out), _ptr(scratch), sbytes, stream), "ts2d_backward")
+            break
+        if rows_cap > 0:
+            _ROWS_SEEN[rows_key] = max(rows, _ROWS_SEEN.get(rows_key, 0))
     if model is not None:
         return dL_dvertex, dL_dcenter2D, dL_df_dc, dL_df_rest, dL_dopacity
     return dL_dvertex, dL_dcenter2D, dL_dshs, dL_dfeature, dL_dopacity

@@ -71,6 +71,51 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+# ---------------------------------------------------------------------------------------------- pybind11 layer (_C_native)
+NATIVE_SRC = CSRC / "ts2d_pybind.cpp"
+NATIVE_NAME = "_C_native"
+
+
+def native_path() -> Path:
+    import sysconfig
+
+    return PKG / f"{NATIVE_NAME}{sysconfig.get_config_var('EXT_SUFFIX')}"
+
+
+def native_needs_build() -> bool:
+    t = native_path()
+    if not t.exists():
+        return True
+    deps = [NATIVE_SRC, PKG.parent / "include" / "ts2d.h"]
+    return t.stat().st_mtime < max(p.stat().st_mtime for p in deps)
+
+
+def build_native(force: bool = False, verbose: bool = False) -> Path:
+    """g++ build of csrc/ts2d_pybind.cpp against torch's headers into triangle_splatting_b200/_C_native*.so (git-ignored, in-tree so
+    that it travels to the GPU box); links libts2d.so through an $ORIGIN-relative rpath.  No CUDA code in it: nvcc is not involved."""
+    target = native_path()
+    if not force and not native_needs_build():
+        return target
+    build(force=False)
+    import sysconfig
+
+    from torch.utils import cpp_extension as ce
+
+    inc = [f"-I{p}" for p in ce.include_paths("cuda")] + [f"-I{sysconfig.get_paths()['include']}", f"-I{PKG.parent / 'include'}"]
+    cmd = ["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-DTORCH_API_INCLUDE_EXTENSION_H", f"-DTORCH_EXTENSION_NAME={NATIVE_NAME}",
+           "-D_GLIBCXX_USE_CXX11_ABI=1", str(NATIVE_SRC), "-o", str(target)] + inc
+    for d in ce.library_paths("cuda"):
+        cmd += [f"-L{d}", f"-Wl,-rpath,{d}"]
+    cmd += [f"-L{LIBDIR}", "-Wl,-rpath,$ORIGIN/lib", "-lts2d", "-lc10", "-ltorch", "-ltorch_cpu", "-ltorch_python", "-lc10_cuda"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose:
+        print(r.stdout, r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for {NATIVE_SRC.name}:\n{r.stdout}\n{r.stderr}")
+    return target
+
+
 if __name__ == "__main__":
     p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(p)
+    print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))
