@@ -26,14 +26,17 @@
 namespace {
 
 constexpr int BW_ROWS = 8;      // triangles per phase-2 panel
-constexpr int BW_WROW = 97;     // 3 scalars x 32 pixels + 1 pad word: conflict-free for both phases
+constexpr int BW_WROW = 99;     // 3 scalars x 32 pixels + the two arg-min ballots + 1 pad word (any odd stride is conflict-free for both phases)
+constexpr int BW_BAL = 96 * 4;  // byte offset of the row's ballot words {to a1, to a2}
 
 // Per-warp shared-memory block (byte offsets from the warp's base address):
 //   ENT   entry j at j * EB: {v1.x v1.y v2.x v2.y} {v3.x v3.y 1/area2 op} {r g b id} [RICH: {n.x n.y n.z vd1} {vd2 vd3 pos -}]
 //   POS   non-RICH only: u32[32] list positions (RICH keeps them in the entry's spare word)
 //   F     per pixel {gp0 gp1 gp2 gd} {gn0 gn1 gn2 -}
-//   W     panel [8 rows][97]: [scalar * 32 + pixel]
-//   INFO  per panel row {v1 v2} {v3 1/area2 op} {id, row index}: what phase 2 needs to know about the triangle (48 B stride)
+//   W     panel [8 rows][99]: [scalar * 32 + pixel], then the two ballots that route D (bit p of word 96: pixel p's D goes to a1, word 97: to a2)
+//   INFO  per panel row {v1 v2} {v3 1/area2 op} {id, row index} (48 B stride): what phase 2 needs to know about the triangle -- written only
+//         for rows that outlive their gather round (the staged entries are overwritten by the next one); rows of the current round are
+//         read from the staged entries themselves
 template <bool RICH>
 struct BwdLayout {
     static constexpr int EB = RICH ? 80 : 48;
@@ -55,14 +58,20 @@ __device__ __forceinline__ uint32_t f_row(int p) { return (uint32_t)(p * 32 + (p
 // wb / ib / fb: shared-space addresses of the warp's W panel, row ids and F table.
 // GEO: some pixel of the sub-tile has a non-zero normal / depth upstream gradient (a template parameter, so that the common
 // colour-only case does not even issue the geometry terms as predicated-off instructions).
-template <bool GEO>
-static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, uint32_t fb, const float4 *__restrict__ rec1,
+// jbase: index (among the entries staged in the current round, at `eb`) of the entry panel row 0 belongs to; rows with jbase + k < 0
+// were carried over from an earlier round and have their copy in INFO.
+template <bool RICH, bool GEO>
+static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, uint32_t fb, uint32_t eb, int jbase, const float4 *__restrict__ rec1,
                                                     float4 *__restrict__ rows, uint32_t rows_cap, float ox, float oy,
                                                     float sub_x0, float sub_y0, int filled, int lane)
 {
+    using L = BwdLayout<RICH>;
     constexpr bool geo = GEO;
     const int k = lane & 7, quarter = lane >> 3;
     __syncwarp();
+    // where this row's triangle record lives: the staged entry (current round) or its INFO copy (carried rows)
+    const int ent = jbase + k;
+    const uint32_t src = ent >= 0 ? eb + (uint32_t)ent * L::EB : ib + 48 * k;
     // sums that share their multiplier ride in pairs on the packed pipe: {c0, c1}, {n0, n1}, {u1, u2} and their x-moments;
     // the y-moments need no loop term at all: the lane's 8 pixels share one row, M_y = dy * S
     v2 s_c01 = bc(0.f), s_n01 = bc(0.f), U0 = bc(0.f), Ux = bc(0.f);
@@ -71,7 +80,7 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
     uint32_t id = 0;
     float vd1 = 0.f, vd2 = 0.f, vd3 = 0.f;
     if (k < filled) {
-        id = lds32(ib + 48 * k + 32);
+        id = lds32(src + (ent >= 0 ? 44 : 32));
         if (geo) {  // vertex depths: re-read from L1/L2, in flight during the panel sums
             vd1 = __ldg(&rec1[2 * (size_t)id].w);
             const float2 q = __ldg(reinterpret_cast<const float2 *>(rec1 + 2 * (size_t)id + 1));
@@ -80,6 +89,9 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
         }
         const uint32_t row = wb + (k * BW_WROW + quarter * 8) * 4;
         const uint32_t frow = fb + f_row(quarter * 8);
+        // arg-min routing of D: bit i of bq1 / bq2 says that pixel quarter * 8 + i sends its D to a1 / a2 (both: the arg-min was a3 and
+        // phase 1 stored -D)
+        const uint32_t bq1 = lds32(wb + k * (BW_WROW * 4) + BW_BAL) >> (quarter * 8), bq2 = lds32(wb + k * (BW_WROW * 4) + BW_BAL + 4) >> (quarter * 8);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             // pixel p = quarter * 8 + i (lane index of phase 1) inside the sub-tile: x = p & 7 = i, y = p >> 3 = quarter
@@ -89,11 +101,7 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
             s_c01 = fma2(bc(c), mk2v(f0.x, f0.y), s_c01);
             s_c2 = fmaf(c, f0.z, s_c2);
             s_op += w1;
-            // arg-min barycentric (1, 2, 3) packed in the two LSBs: D goes to a1 (bit 0) and / or a2 (bit 1), negated when to a3 (both)
-            const uint32_t db = __float_as_uint(Dp);
-            const bool to1 = (db & 1u) != 0u, to2 = (db & 2u) != 0u;
-            const float Ds = (to1 && to2) ? -Dp : Dp;
-            const v2 u = mk2v(to1 ? Ds : 0.0f, to2 ? Ds : 0.0f);
+            const v2 u = mk2v(((bq1 >> i) & 1u) ? Dp : 0.0f, ((bq2 >> i) & 1u) ? Dp : 0.0f);
             if (geo) {
                 const float4 f1 = lds128(frow + 32 * i + 16);
                 const float cg = c * f0.w;                       // contrib * gd
@@ -114,8 +122,9 @@ static __device__ __noinline__ void bwd_flush_panel(uint32_t wb, uint32_t ib, ui
     if (geo) { XQ(s_n0); XQ(s_n1); XQ(s_n2); XQ(m0); XQ(m1); XQ(m2); }
 #undef XQ
     if (k < filled) {
-        const float4 e1 = lds128(ib + 48 * k), e2 = lds128(ib + 48 * k + 16);
-        const uint32_t slot = lds32(ib + 48 * k + 36);  // the row of this (sub-tile, entry) pair
+        const float4 e1 = lds128(src), e2 = lds128(src + 16);
+        // the row of this (sub-tile, entry) pair
+        const uint32_t slot = lds32(ent >= 0 ? (RICH ? src + 76 : eb + L::SLOT + 4 * (uint32_t)ent) : src + 36);
         const float inv = e2.z;
         const float p1x = e1.x - ox, p1y = e1.y - oy;
         float S1 = u10, M1x = u1x, M1y = u1y, S2 = u20, M2x = u2x, M2y = u2y;
@@ -176,6 +185,8 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
     gk.is_one = GAMMA1;
     const uint32_t sb = smem_base(smem_raw + lwarp * L::BYTES);  // this warp's block
     const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t lane4 = 4u * lane;
+    asm volatile("" : "+r"(lane4));  // opaque: keep the lane's panel offset in a register (ptxas re-read SR_TID in every walk iteration)
 
     const uint2 range = ranges[tile];
     float T = inside ? final_T[pix] : 0.0f;
@@ -207,11 +218,13 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
     const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last);
     __syncwarp();
 
-    int prow = 0;  // next free panel row (rows persist across rounds: phase 2 only needs the triangle id)
+    int prow = 0;   // next free panel row (rows persist across rounds)
+    uint32_t urow = sb + L::W;  // ... and its shared-space address
+    int jbase = 0;  // staged-entry index of panel row 0 (negative: the first -jbase rows were carried over from earlier rounds)
     const float sub_x0 = (float)((warp & 1) * 8), sub_y0 = (float)((warp >> 1) * 4);
     auto flush_panel = [&](int filled) {
-        if (geo) bwd_flush_panel<true>(sb + L::W, sb + L::INFO, sb + L::F, rec1, rows, rows_cap, ox, oy, sub_x0, sub_y0, filled, lane);
-        else bwd_flush_panel<false>(sb + L::W, sb + L::INFO, sb + L::F, rec1, rows, rows_cap, ox, oy, sub_x0, sub_y0, filled, lane);
+        if (geo) bwd_flush_panel<RICH, RICH>(sb + L::W, sb + L::INFO, sb + L::F, sb, jbase, rec1, rows, rows_cap, ox, oy, sub_x0, sub_y0, filled, lane);
+        else bwd_flush_panel<RICH, false>(sb + L::W, sb + L::INFO, sb + L::F, sb, jbase, rec1, rows, rows_cap, ox, oy, sub_x0, sub_y0, filled, lane);
     };
 
     // Back to front: `rem` list positions [range.x, range.x + rem) are still to be scanned; a chunk is the 32 positions
@@ -263,14 +276,16 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
         for (int j = 0; j < count; j++, ea += L::EB) {
             const float4 e1 = lds128(ea), e2 = lds128(ea + 16);
             const uint32_t pos = lds32(sb + L::POS + j * L::POS_STRIDE);
-            // id and row index of the entry, for the panel's INFO row: requested here so that their latency hides behind the pair
-            // evaluation (the shared-memory helpers are volatile asm: the compiler keeps them where they are written)
-            const uint32_t info_id = lds32(ea + 44), info_slot = lds32(sb + L::SLOT + j * L::POS_STRIDE);
             float w_c = 0.0f, w_op = 0.0f, w_D = 0.0f;
-            if (pos < last) {
+            bool not1 = false, not2 = false;  // D does not go to a1 / a2
+            {
+                // evaluated by every lane, also those whose own last contributor lies in front of this entry (they are masked out
+                // of the result): a branch around the evaluation would put the entry loads behind the position load and compare
                 FastPair f;
                 bool unc;
                 bool hit = eval_fast(e1, e2, pxf, pyf, gk, f, unc);
+                const bool live = pos < last;
+                hit = hit && live;
                 // one more reference decision lives in the backward pass: op*G < 0.99 (clamp not active)
                 unc = unc || (fabsf(f.og - 0.99f) <= 0.99f * gk.band);
                 {   // ... and so does the arg-min of (a1, a2, a3): dL/d min(a) goes to ONE barycentric, and near a corner of a thin
@@ -281,8 +296,8 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                     const float lo12 = fminf(f.a1, f.a2), hi12 = fmaxf(f.a1, f.a2);
                     unc = unc || (fmaxf(lo12, fminf(hi12, f.a3)) - fminf(lo12, f.a3) <= TS2D_ARGMIN_TIE);
                 }
-                if (unc) {
-                    const float area2 = __ldg(&rec0[3 * (size_t)info_id + 2].w);
+                if (unc && live) {
+                    const float area2 = __ldg(&rec0[3 * (size_t)lds32(ea + 44) + 2].w);
                     PairEval e;
                     hit = eval_exact(e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, area2, e2.w, gk.two_gamma, pxf, pyf, e);
                     f.a1 = e.a1; f.a2 = e.a2; f.a3 = e.a3; f.ecc = e.ecc;
@@ -316,28 +331,43 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                     w_op = dL_dalpha * f.G;  // unconditional (backward.cu:490)
                     const float dL_dpower = (f.og < 0.99f) ? dL_dalpha * f.alpha : 0.0f;
                     const float D = -3.0f * dL_dpower * gk.two_gamma * f.power * rcp_approx(f.ecc + TS2D_EPS);
-                    // sub-gradient of min: first arg-min in the order a1, a2, a3 (backward.cu:449-461)
-                    const uint32_t sel = (f.a1 <= f.a2 && f.a1 <= f.a3) ? 1u : ((f.a2 <= f.a1 && f.a2 <= f.a3) ? 2u : 3u);
-                    w_D = __uint_as_float((__float_as_uint(D) & ~3u) | sel);
+                    // sub-gradient of min: first arg-min in the order a1, a2, a3 (backward.cu:449-461).  a3 = 1 - a1 - a2, so D to a3 is -D
+                    // to both a1 and a2: the panel gets the signed value, the choice travels as two warp ballots
+                    not2 = f.a1 <= f.a2 && f.a1 <= f.a3;           // arg-min a1
+                    not1 = !not2 && f.a2 <= f.a1 && f.a2 <= f.a3;  // arg-min a2
+                    w_D = (not1 || not2) ? D : -D;
                 }
             }
             // every staged entry owns a row (its live bit is set), so every staged entry is flushed -- also when no pixel of the
             // sub-tile turns out to contribute (non-rich forward: conservative coverage bits): the row is then written as zeros
-            const uint32_t row = sb + L::W + (prow * BW_WROW + lane) * 4;
-            sts32f(row, w_c);
-            sts32f(row + 128, w_op);
-            sts32f(row + 256, w_D);
-            {   // row info for phase 2; every lane stores the same words (cheaper than electing one: no lane id, no predicate)
-                const uint32_t ia = sb + L::INFO + prow * 48;
-                sts128(ia, e1);
-                sts128(ia + 16, e2);
-                sts32(ia + 32, info_id);
-                sts32(ia + 36, info_slot);
-            }
+            const uint32_t to1 = __ballot_sync(0xffffffffu, !not1), to2 = __ballot_sync(0xffffffffu, !not2);
+            sts32f(urow + lane4, w_c);
+            sts32f(urow + lane4 + 128, w_op);
+            sts32f(urow + lane4 + 256, w_D);
+            sts32(urow + BW_BAL, to1);  // every lane stores the same words (cheaper than electing one: no predicate)
+            sts32(urow + BW_BAL + 4, to2);
+            urow += BW_WROW * 4;
             if (++prow == BW_ROWS) {
                 flush_panel(BW_ROWS);
                 prow = 0;
+                urow = sb + L::W;
+                jbase = j + 1;
             }
+        }
+        // rows that stay in the panel: the staged entries they point to are overwritten by the next gather, keep a copy of what
+        // phase 2 needs (at most 7 rows per round instead of a copy per visited entry)
+        {
+            const int ent = jbase + lane;
+            if (lane < prow && ent >= 0) {
+                const uint32_t src = sb + (uint32_t)ent * L::EB, dst = sb + L::INFO + 48 * lane;
+                const float4 c1 = lds128(src), c2 = lds128(src + 16);
+                const uint32_t cid = lds32(src + 44), cslot = lds32(sb + L::SLOT + ent * L::POS_STRIDE);
+                sts128(dst, c1);
+                sts128(dst + 16, c2);
+                sts32(dst + 32, cid);
+                sts32(dst + 36, cslot);
+            }
+            jbase = -prow;
         }
         __syncwarp();  // the next gather overwrites positions / entries
     }
