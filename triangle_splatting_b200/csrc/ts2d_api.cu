@@ -369,28 +369,50 @@ int forward_geometry_impl(const ts2d_camera *cam, const ts2d_geometry *geom, con
     return 0;
 }
 
+// One-enqueue forward: everything the render half of the frame needs zeroed (tile ranges, look-back words of the tile sort, the
+// fixed-point contrib_sum and contrib_max of the fast kernels) is cleared HERE, in front of K1, so that the kernels of the frame
+// follow each other without a memset or copy node in between (ts2d_grid_chain: each kernel's launch overlaps its predecessor's tail).
+// The render half of the geometry header is part of the frame's first memset (forward_geometry_impl).
+int forward_clear_impl(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, GeomState gs, BinState bs, ImageState is,
+                       const ts2d_forward_out *out, cudaStream_t s)
+{
+    const int n_tiles = ((cam->width + TS2D_TILE - 1) / TS2D_TILE) * ((cam->height + TS2D_TILE - 1) / TS2D_TILE);
+    TS2D_CUDA_TRY(cudaMemsetAsync(is.ranges, 0, sizeof(uint2) * (size_t)n_tiles, s));
+    TS2D_CUDA_TRY(cudaMemsetAsync(bs.status, 0, ts2d_sort_status_bytes(bs.cap), s));
+    if (flags->rich_info && ts2d_use_fast(geom, flags)) {
+        TS2D_CUDA_TRY(cudaMemsetAsync(gs.csum64, 0, sizeof(unsigned long long) * (size_t)geom->P, s));
+        TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)geom->P, s));
+    }
+    return 0;
+}
+
+// pre_cleared: called behind forward_clear_impl + forward_geometry_impl in the same enqueue (ts2d_forward)
 int forward_render_impl(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int64_t num_rendered, GeomState gs, BinState bs,
-                        ImageState is, const ts2d_forward_out *out, ts2d_counters *ctr, cudaStream_t s)
+                        ImageState is, const ts2d_forward_out *out, ts2d_counters *ctr, bool pre_cleared, cudaStream_t s)
 {
     const int n_tiles = ((cam->width + TS2D_TILE - 1) / TS2D_TILE) * ((cam->height + TS2D_TILE - 1) / TS2D_TILE);
     const int sb = ts2d_sorted_buf(n_tiles);
-    if (ctr) {  // R first: the host can size things / detect an overflow while the rest of the frame is still queued
+    if (ctr && !pre_cleared) {  // R first: the host can size things / detect an overflow while the rest of the frame is still queued
         TS2D_CUDA_TRY(cudaMemcpyAsync(&ctr->host->num_rendered, &gs.hdr->num_rendered, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         TS2D_CUDA_TRY(cudaEventRecord(ctr->ev_r, s));
     }
     // the render half of the header (row counter, tickets and histograms of the tile sort): cleared here so that a render can be
     // repeated on the same geometry state (binning state too small the first time)
-    TS2D_CUDA_TRY(cudaMemsetAsync(&gs.hdr->render, 0, sizeof(gs.hdr->render), s));
-    TS2D_STAGE(TS2D_STAGE_BINNING, ts2d_launch_binning(cam, geom, flags, num_rendered, gs, bs, is, s));
+    if (!pre_cleared) TS2D_CUDA_TRY(cudaMemsetAsync(&gs.hdr->render, 0, sizeof(gs.hdr->render), s));
+    TS2D_STAGE(TS2D_STAGE_BINNING, ts2d_launch_binning(cam, geom, flags, num_rendered, gs, bs, is, pre_cleared, s));
     if (flags->primitive == TS2D_PRIMITIVE_3D && ts2d_use_fast(geom, flags))
-        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render3d_fwd_fast(cam, geom, flags, gs, bs.tkey[sb], bs.tval[sb], is, out, s));
+        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render3d_fwd_fast(cam, geom, flags, gs, bs.tkey[sb], bs.tval[sb], is, out, pre_cleared, s));
     else if (flags->primitive == TS2D_PRIMITIVE_3D)
         TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render3d_fwd(cam, geom, flags, gs, bs.tval[sb], is, out, s));
     else if (ts2d_use_fast(geom, flags))
-        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd_fast(cam, geom, flags, gs, bs.tkey[sb], bs.tval[sb], is, out, s));
+        TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd_fast(cam, geom, flags, gs, bs.tkey[sb], bs.tval[sb], is, out, pre_cleared, s));
     else
         TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd(cam, geom, flags, gs, bs.tval[sb], is, out, s));
     if (ctr) {
+        if (pre_cleared) {  // one-enqueue forward: R leaves the device with the row count, behind the last kernel of the frame
+            TS2D_CUDA_TRY(cudaMemcpyAsync(&ctr->host->num_rendered, &gs.hdr->num_rendered, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            TS2D_CUDA_TRY(cudaEventRecord(ctr->ev_r, s));
+        }
         TS2D_CUDA_TRY(cudaMemcpyAsync(&ctr->host->backward_rows, &gs.hdr->render.bwd_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         TS2D_CUDA_TRY(cudaEventRecord(ctr->ev_all, s));
     }
@@ -485,7 +507,7 @@ int ts2d_forward_render(const ts2d_camera *cam, const ts2d_geometry *geom, const
     if (cap < 1 || (num_rendered > 0 && cap < num_rendered)) return TS2D_E_STATE_SIZE;
     carve_binning(binning_state, cap, &bs);
     if (carve_image(image_state, cam->width, cam->height, &is) > image_state_bytes) return TS2D_E_STATE_SIZE;
-    return forward_render_impl(cam, geom, flags, num_rendered, gs, bs, is, out, counters, (cudaStream_t)stream);
+    return forward_render_impl(cam, geom, flags, num_rendered, gs, bs, is, out, counters, false, (cudaStream_t)stream);
 }
 
 int ts2d_forward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, int32_t *radii, void *geometry_state,
@@ -506,8 +528,9 @@ int ts2d_forward(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_f
     carve_binning(binning_state, cap, &bs);
     if (carve_image(image_state, cam->width, cam->height, &is) > image_state_bytes) return TS2D_E_STATE_SIZE;
     cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = forward_clear_impl(cam, geom, flags, gs, bs, is, out, s)) != 0) return rc;
     if ((rc = forward_geometry_impl(cam, geom, flags, radii, gs, nullptr, s)) != 0) return rc;
-    return forward_render_impl(cam, geom, flags, -1, gs, bs, is, out, counters, s);
+    return forward_render_impl(cam, geom, flags, -1, gs, bs, is, out, counters, true, s);
 }
 
 int ts2d_counters_create(ts2d_counters **out)

@@ -56,6 +56,7 @@ k_emit_warp(int P, int gx, float gamma, EmitCam cam, int shard_rank, int shard_w
             const ushort4 *__restrict__ rect, const uint32_t *__restrict__ offs, const float4 *__restrict__ rec0, uint32_t cap, uint32_t *__restrict__ tkey,
             uint32_t *__restrict__ tval, uint4 *__restrict__ binrec, uint2 *__restrict__ ranges)
 {
+    ts2d_grid_chain();
     const int lane = threadIdx.x & 31;
     const int r = (blockIdx.x * blockDim.x + threadIdx.x);
     const GammaK gk = make_gamma(gamma);
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(1024) k_tile_tables(int n_tiles, int np, uint2
 {
     __shared__ uint32_t s_part[1024];
     __shared__ uint32_t s_h[3][RS_BINS];
+    ts2d_grid_chain();
     const int tid = threadIdx.x;
     for (int i = tid; i < 3 * RS_BINS; i += 1024) (&s_h[0][0])[i] = 0;
     const int per = (n_tiles + 1023) / 1024;
@@ -176,7 +178,7 @@ int ts2d_launch_order_and_scan(int32_t P, GeomState gs, int64_t *R_host, cudaStr
         h.mask[d] = 0xFFu;
         h.hist[d] = gs.hdr->hist[d];
     }
-    k_radix_hist<<<hist_blocks(P), RS_THREADS, 0, s>>>(h);
+    TS2D_CUDA_TRY(ts2d_launch(k_radix_hist, hist_blocks(P), RS_THREADS, 0, s, h));
     // dkey (kept: the export calls and the 64-bit key reconstruction read it) -> (tmpk, ids) -> (dkey2, ids2) -> (tmpk, ids) -> (dkey2, ids2)
     const uint32_t *kin[4] = {gs.dkey, gs.tmpk, gs.dkey2, gs.tmpk}, *vin[4] = {nullptr, gs.ids, gs.ids2, gs.ids};
     uint32_t *kout[4] = {gs.tmpk, gs.dkey2, gs.tmpk, gs.dkey2}, *vout[4] = {gs.ids, gs.ids2, gs.ids, gs.ids2};
@@ -194,7 +196,7 @@ int ts2d_launch_order_and_scan(int32_t P, GeomState gs, int64_t *R_host, cudaStr
         a.shift = 8 * d;
         a.mask = 0xFFu;
         a.pass_uid = (uint32_t)(d + 1);
-        k_radix_pass<<<(unsigned)rs_tiles(P), RS_THREADS, 0, s>>>(a);
+        TS2D_CUDA_TRY(ts2d_launch(k_radix_pass, (unsigned)rs_tiles(P), RS_THREADS, 0, s, a));
     }
     TS2D_CUDA_TRY((ts2d_scan<LoadGatherU32, true>(LoadGatherU32{gs.ids2, gs.tiles}, nullptr, P, reinterpret_cast<uint32_t *>(gs.sstatus), gs.offs,
                                                    &gs.hdr->num_rendered, false, s)));
@@ -209,29 +211,29 @@ int ts2d_launch_order_and_scan(int32_t P, GeomState gs, int64_t *R_host, cudaStr
 
 // K4-K6.
 int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, int64_t R_host, GeomState gs, BinState bs, ImageState is,
-                        cudaStream_t s)
+                        bool pre_cleared, cudaStream_t s)
 {
     const int gx = (cam->width + TS2D_TILE - 1) / TS2D_TILE, gy = (cam->height + TS2D_TILE - 1) / TS2D_TILE;
     const int n_tiles = gx * gy;
     const int P = g->P;
-    TS2D_CUDA_TRY(cudaMemsetAsync(is.ranges, 0, sizeof(uint2) * (size_t)n_tiles, s));
+    if (!pre_cleared) TS2D_CUDA_TRY(cudaMemsetAsync(is.ranges, 0, sizeof(uint2) * (size_t)n_tiles, s));
     if (R_host == 0) return 0;
     const int64_t n_launch = R_host > 0 ? (R_host < bs.cap ? R_host : bs.cap) : bs.cap;  // what the grids are sized for
     if (n_launch <= 0) return 0;
-    TS2D_CUDA_TRY(cudaMemsetAsync(bs.status, 0, ts2d_sort_status_bytes(n_launch), s));
+    if (!pre_cleared) TS2D_CUDA_TRY(cudaMemsetAsync(bs.status, 0, ts2d_sort_status_bytes(n_launch), s));
     const int masks = !ts2d_use_fast(g, f) ? 0 : (f->primitive == TS2D_PRIMITIVE_3D ? 2 : 1);
     const int blocks = (P + TS2D_BLOCK - 1) / TS2D_BLOCK;
     const EmitCam ec = {cam->width, cam->height, cam->tan_fovx, cam->tan_fovy};
     const uint32_t cap32 = (uint32_t)(bs.cap < 0xFFFFFFFFll ? bs.cap : 0xFFFFFFFFll);
 #define TS2D_EMIT_ARGS P, gx, g->gamma, ec, f->shard_rank, f->shard_world, gs.ids2, gs.tiles, gs.rect, gs.offs, gs.rec0, cap32, bs.tkey[0], bs.tval[0], gs.binrec, is.ranges
     if (f->shard_world > 1) {
-        if (masks == 2) k_emit_warp<2, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
-        else if (masks == 1) k_emit_warp<1, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
-        else k_emit_warp<0, true><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
+        if (masks == 2) TS2D_CUDA_TRY(ts2d_launch(k_emit_warp<2, true>, blocks, TS2D_BLOCK, 0, s, TS2D_EMIT_ARGS));
+        else if (masks == 1) TS2D_CUDA_TRY(ts2d_launch(k_emit_warp<1, true>, blocks, TS2D_BLOCK, 0, s, TS2D_EMIT_ARGS));
+        else TS2D_CUDA_TRY(ts2d_launch(k_emit_warp<0, true>, blocks, TS2D_BLOCK, 0, s, TS2D_EMIT_ARGS));
     } else {
-        if (masks == 2) k_emit_warp<2, false><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
-        else if (masks == 1) k_emit_warp<1, false><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
-        else k_emit_warp<0, false><<<blocks, TS2D_BLOCK, 0, s>>>(TS2D_EMIT_ARGS);
+        if (masks == 2) TS2D_CUDA_TRY(ts2d_launch(k_emit_warp<2, false>, blocks, TS2D_BLOCK, 0, s, TS2D_EMIT_ARGS));
+        else if (masks == 1) TS2D_CUDA_TRY(ts2d_launch(k_emit_warp<1, false>, blocks, TS2D_BLOCK, 0, s, TS2D_EMIT_ARGS));
+        else TS2D_CUDA_TRY(ts2d_launch(k_emit_warp<0, false>, blocks, TS2D_BLOCK, 0, s, TS2D_EMIT_ARGS));
     }
 #undef TS2D_EMIT_ARGS
     TS2D_CUDA_TRY(cudaGetLastError());
@@ -239,7 +241,7 @@ int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts
     const int tb = ts2d_tile_bits(n_tiles), np = ts2d_tile_sort_passes(n_tiles);
     const int64_t *n_dev = &gs.hdr->num_rendered;
     static_assert(TS2D_MASK_BITS == 8, "the digits of the tile sort are the bytes of the tile id");
-    k_tile_tables<<<1, 1024, 0, s>>>(n_tiles, np, is.ranges, gs.hdr->render.hist[0], gs.hdr->render.hist[1], gs.hdr->render.hist[2]);
+    TS2D_CUDA_TRY(ts2d_launch(k_tile_tables, 1, 1024, 0, s, n_tiles, np, is.ranges, gs.hdr->render.hist[0], gs.hdr->render.hist[1], gs.hdr->render.hist[2]));
     for (int d = 0; d < np; d++) {
         RadixPassArgs a = {};
         a.kin = bs.tkey[d & 1];
@@ -254,7 +256,7 @@ int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts
         a.shift = TS2D_MASK_BITS + 8 * d;
         a.mask = (d == np - 1) ? ((1u << (tb - 8 * d)) - 1u) : 0xFFu;
         a.pass_uid = (uint32_t)(8 + d);
-        k_radix_pass<<<(unsigned)rs_tiles(n_launch), RS_THREADS, 0, s>>>(a);
+        TS2D_CUDA_TRY(ts2d_launch(k_radix_pass, (unsigned)rs_tiles(n_launch), RS_THREADS, 0, s, a));
     }
     return (int)cudaGetLastError();
 }

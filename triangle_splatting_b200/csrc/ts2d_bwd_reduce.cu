@@ -29,6 +29,7 @@ k_bwd_rows_mark(const int64_t *__restrict__ n_dev, int64_t cap, int gx, int shar
                 const uint2 *__restrict__ ranges, const uint32_t *__restrict__ lastw, const uint4 *__restrict__ binrec,
                 uint32_t *__restrict__ ei_out, uint8_t *__restrict__ cnt)
 {
+    ts2d_grid_chain();
     const int64_t R = rs_count(n_dev, cap);
     const int64_t p0 = (int64_t)blockIdx.x * (blockDim.x * MK) + threadIdx.x;
     uint32_t key[MK], id[MK];
@@ -105,6 +106,7 @@ k_bwd_rows_reduce(int P, const int64_t *__restrict__ n_dev, int64_t cap, int64_t
     __shared__ float4 s_rows[RR_CHUNK * 4];
     __shared__ uint32_t s_b[RR_RANKS + 1];  // first row of each rank of the block; [RR_RANKS] = end of the span
     __shared__ uint32_t s_id[RR_RANKS];
+    ts2d_grid_chain();
     const int tid = threadIdx.x;
     const int r0 = blockIdx.x * RR_RANKS;
     const int64_t R = rs_count(n_dev, cap);
@@ -149,6 +151,7 @@ k_bwd_rows_reduce(int P, const int64_t *__restrict__ n_dev, int64_t cap, int64_t
 
 __global__ void __launch_bounds__(TS2D_BLOCK) k_contrib_finish(int P, const unsigned long long *__restrict__ csum64, float *__restrict__ contrib_sum)
 {
+    ts2d_grid_chain();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P) contrib_sum[i] = (float)csum64[i] * (1.0f / 4294967296.0f);
 }
@@ -160,8 +163,7 @@ __global__ void __launch_bounds__(TS2D_BLOCK) k_contrib_finish(int P, const unsi
 int ts2d_launch_contrib_finish(int32_t P, const unsigned long long *csum64, float *contrib_sum, cudaStream_t s)
 {
     if (P <= 0) return 0;
-    k_contrib_finish<<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(P, csum64, contrib_sum);
-    return (int)cudaGetLastError();
+    return (int)ts2d_launch(k_contrib_finish, (P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s, P, csum64, contrib_sum);
 }
 
 int ts2d_launch_bwd_rows_prepare(const ts2d_camera *cam, const ts2d_flags *f, GeomState gs, BinState bs, ImageState is, BwdScratch sc, cudaStream_t s)
@@ -170,10 +172,8 @@ int ts2d_launch_bwd_rows_prepare(const ts2d_camera *cam, const ts2d_flags *f, Ge
     const int sbuf = ts2d_sorted_buf(gx * gy);
     const int64_t *n_dev = &gs.hdr->num_rendered;
     if (bs.cap <= 0) return 0;
-    k_bwd_rows_mark<<<(unsigned)((bs.cap + TS2D_BLOCK * MK - 1) / (TS2D_BLOCK * MK)), TS2D_BLOCK, 0, s>>>(n_dev, bs.cap, gx, f->shard_rank, f->shard_world, bs.tkey[sbuf],
-                                                                                             bs.tval[sbuf], is.ranges, is.lastw, gs.binrec,
-                                                                                             sc.ei, sc.cnt);
-    TS2D_CUDA_TRY(cudaGetLastError());
+    TS2D_CUDA_TRY(ts2d_launch(k_bwd_rows_mark, (unsigned)((bs.cap + TS2D_BLOCK * MK - 1) / (TS2D_BLOCK * MK)), TS2D_BLOCK, 0, s, n_dev, bs.cap, gx, f->shard_rank,
+                              f->shard_world, bs.tkey[sbuf], bs.tval[sbuf], is.ranges, is.lastw, gs.binrec, sc.ei, sc.cnt));
     // sbase = exclusive scan of cnt over emission indices, sbase[R] = number of rows
     return (int)ts2d_scan<LoadU8, false>(LoadU8{sc.cnt}, n_dev, bs.cap, reinterpret_cast<uint32_t *>(sc.sstatus), sc.sbase, nullptr, true, s);
 }
@@ -181,7 +181,6 @@ int ts2d_launch_bwd_rows_prepare(const ts2d_camera *cam, const ts2d_flags *f, Ge
 int ts2d_launch_bwd_rows_reduce(int32_t P, GeomState gs, BwdScratch sc, cudaStream_t s)
 {
     if (P <= 0) return 0;
-    k_bwd_rows_reduce<<<(P + RR_RANKS - 1) / RR_RANKS, 4 * RR_RANKS, 0, s>>>(P, &gs.hdr->num_rendered, sc.cap, sc.rows_cap, gs.ids2, gs.tiles, gs.offs,
-                                                                            sc.sbase, sc.rows, reinterpret_cast<float4 *>(sc.gacc));
-    return (int)cudaGetLastError();
+    return (int)ts2d_launch(k_bwd_rows_reduce, (P + RR_RANKS - 1) / RR_RANKS, 4 * RR_RANKS, 0, s, P, &gs.hdr->num_rendered, sc.cap, sc.rows_cap, gs.ids2,
+                            gs.tiles, gs.offs, sc.sbase, sc.rows, reinterpret_cast<float4 *>(sc.gacc));
 }

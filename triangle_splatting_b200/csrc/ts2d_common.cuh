@@ -228,6 +228,46 @@ __device__ __forceinline__ float warp_sum(float v)
         if (_e != cudaSuccess) return (int)_e; \
     } while (0)
 
+// ---- programmatic dependent launch between the kernels of a frame ------------------------------------------------------------
+// A frame is a chain of ~22 kernels, most of them short (radix passes, scans, tables): at the small configurations the drain /
+// launch / ramp-up gap between two of them is a visible share of the frame.  Every kernel of the chain starts with
+// ts2d_grid_chain(): it lets the NEXT kernel of the stream be scheduled as soon as all of this kernel's blocks have started
+// (griddepcontrol.launch_dependents) and then waits until the PREVIOUS kernel has completed and its writes are visible
+// (griddepcontrol.wait) -- before touching global memory, so the data dependences (and the anti-dependences: buffers are
+// reused along the chain) are exactly those of plain stream order; only block scheduling and the kernel prologue overlap the
+// predecessor's tail.  Completion is transitive (a kernel cannot complete before its own wait returned), so kernel N + 2 sees
+// everything kernel N wrote.  Launched without the attribute (TS2D_PDL=0, or behind a memset / copy) both instructions are no-ops.
+__device__ __forceinline__ void ts2d_grid_chain()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+static inline bool ts2d_pdl()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("TS2D_PDL");
+        v = e ? (atoi(e) != 0) : 1;
+    }
+    return v != 0;
+}
+// launch of a chain kernel: <<<grid, block, smem, s>>> plus the programmatic-stream-serialization attribute
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ts2d_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = ts2d_pdl() ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Host-side helpers shared by the .cu translation units
 static inline size_t ts2d_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline ModelIn ts2d_model_in(const ts2d_geometry *g, const GeomHeader *hdr)
@@ -296,9 +336,11 @@ int ts2d_launch_preprocess(const ts2d_camera *cam, const ts2d_geometry *g, const
 // K2/K3: depth order + scan.  R_host != NULL: R is copied to the host and the stream is synchronised (two-call forward);
 // NULL: nothing leaves the device (one-enqueue forward).
 int ts2d_launch_order_and_scan(int32_t P, GeomState gs, int64_t *R_host, cudaStream_t s);
-// K4-K6.  R_host >= 0: the instance count is known on the host (grids are sized for it); < 0: it only exists in gs.hdr
+// K4-K6.  R_host >= 0: the instance count is known on the host (grids are sized for it); < 0: it only exists in gs.hdr.
+// pre_cleared: the caller zeroed the tile ranges and the look-back words of the tile sort at the start of the frame
+// (ts2d_forward_clear), so that no memset node sits between the kernels of the frame (ts2d_grid_chain)
 int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, int64_t R_host, GeomState gs, BinState bs, ImageState is,
-                        cudaStream_t s);
+                        bool pre_cleared, cudaStream_t s);
 int ts2d_launch_contrib_finish(int32_t P, const unsigned long long *csum64, float *contrib_sum, cudaStream_t s);
 size_t ts2d_sort_status_bytes(int64_t n_cap);
 size_t ts2d_scan_status_bytes(int64_t n_cap);
@@ -309,7 +351,7 @@ int ts2d_launch_render_fwd(const ts2d_camera *cam, const ts2d_geometry *g, const
                            ImageState is, const ts2d_forward_out *out, cudaStream_t s);
 // fast kernels: `keys` = sorted instance keys (tile << 8 | sub-tile mask), `list` = triangle ids, both in tile-list order
 int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
-                                const uint32_t *list, ImageState is, const ts2d_forward_out *out, cudaStream_t s);
+                                const uint32_t *list, ImageState is, const ts2d_forward_out *out, bool pre_cleared, cudaStream_t s);
 // (the fast backward kernels write per-(sub-tile, entry) rows into `sc`; ts2d_launch_bwd_rows_reduce() turns them into sc.gacc)
 int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
                                 const uint32_t *list, ImageState is, const ts2d_loss_in *loss, BwdScratch sc, cudaStream_t s);
@@ -326,7 +368,7 @@ int ts2d_launch_preprocess3d_bwd(const ts2d_camera *cam, const ts2d_geometry *g,
                                  const float *gacc, const ts2d_backward_out *out, cudaStream_t s);
 // fast kernels of the 3D primitive (ts2d_prim3d_fast.cu); same roles as ts2d_launch_render_{fwd,bwd}_fast
 int ts2d_launch_render3d_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
-                                  const uint32_t *list, ImageState is, const ts2d_forward_out *out, cudaStream_t s);
+                                  const uint32_t *list, ImageState is, const ts2d_forward_out *out, bool pre_cleared, cudaStream_t s);
 int ts2d_launch_render3d_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
                                   const uint32_t *list, ImageState is, const ts2d_loss_in *loss, BwdScratch sc, cudaStream_t s);
 int ts2d_launch_export_geometry3d(int P, GeomState gs, float *v_view, float *normal_view, float *depth, float *rgb, uint8_t *clamped,

@@ -45,6 +45,7 @@ k_preprocess(int W, int H, int P, int D, int M, int C, bool rich, bool use_shs, 
              uint8_t *__restrict__ clamp, ModelIn mi)
 {
     extern __shared__ __align__(16) float s_rows[];
+    ts2d_grid_chain();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const float *sh_row = shs + (size_t)idx * M * 3;
     if (MODEL) {
@@ -180,13 +181,13 @@ int ts2d_launch_preprocess(const ts2d_camera *cam, const ts2d_geometry *g, const
         if (mi.bg_bits) TS2D_CUDA_TRY(cudaMemsetAsync(mi.bg_bits, 0, sizeof(uint32_t), s));
         const size_t smem = (size_t)(TS2D_BLOCK / 32) * 32 * ts2d_split_row_stride(g->M) * sizeof(float);
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_preprocess<true, true><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K1_ARGS);
+        TS2D_CUDA_TRY(ts2d_launch(k_preprocess<true, true>, (P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s, TS2D_K1_ARGS));
     } else if (g->use_shs && ts2d_rows_tileable(g->M, g->shs, g->shs) && 2 * K >= g->M) {
         const size_t smem = (size_t)(TS2D_BLOCK / 32) * 32 * ((3 * g->M) / 4 + 1) * 16;
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_preprocess<true, false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K1_ARGS);
+        TS2D_CUDA_TRY(ts2d_launch(k_preprocess<true, false>, (P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s, TS2D_K1_ARGS));
     } else {
-        k_preprocess<false, false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(TS2D_K1_ARGS);
+        TS2D_CUDA_TRY(ts2d_launch(k_preprocess<false, false>, (P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s, TS2D_K1_ARGS));
     }
 #undef TS2D_K1_ARGS
     return (int)cudaGetLastError();
@@ -226,6 +227,7 @@ k_preprocess_bwd(int W, int H, int P, int D, int M, int C, bool use_shs, bool ri
                  float *__restrict__ dL_dfeature, float *__restrict__ dL_dopacity, ModelIn mi, ModelOut mo)
 {
     extern __shared__ __align__(16) float s_rows[];
+    ts2d_grid_chain();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row0 = idx - lane;                       // first triangle of this warp
@@ -396,14 +398,14 @@ int ts2d_launch_preprocess_bwd(const ts2d_camera *cam, const ts2d_geometry *g, c
         const size_t smem = (size_t)(TS2D_BLOCK / 32) * 32 * ts2d_split_row_stride(g->M) * sizeof(float);
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess_bwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess_bwd<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        k_preprocess_bwd<true, true><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K9_ARGS);
+        TS2D_CUDA_TRY(ts2d_launch(k_preprocess_bwd<true, true>, (P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s, TS2D_K9_ARGS));
     } else if (tiled) {
         const size_t smem = (size_t)(TS2D_BLOCK / 32) * 32 * ((3 * g->M) / 4 + 1) * 16;
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess_bwd<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_preprocess_bwd<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        k_preprocess_bwd<true, false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s>>>(TS2D_K9_ARGS);
+        TS2D_CUDA_TRY(ts2d_launch(k_preprocess_bwd<true, false>, (P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, smem, s, TS2D_K9_ARGS));
     } else {
-        k_preprocess_bwd<false, false><<<(P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s>>>(TS2D_K9_ARGS);
+        TS2D_CUDA_TRY(ts2d_launch(k_preprocess_bwd<false, false>, (P + TS2D_BLOCK - 1) / TS2D_BLOCK, TS2D_BLOCK, 0, s, TS2D_K9_ARGS));
     }
 #undef TS2D_K9_ARGS
     return (int)cudaGetLastError();

@@ -130,6 +130,7 @@ k_render3d_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world
                     float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max,
                     uint32_t *__restrict__ lastw, unsigned long long *__restrict__ bwd_rows, unsigned long long *__restrict__ csum64)
 {
+    ts2d_grid_chain();
     if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     using L = Fwd3Layout<RICH>;
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -408,6 +409,7 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
                     const float *__restrict__ dL_dout_depth, const float *__restrict__ dL_dout_normal, const uint32_t *__restrict__ ei_of,
                     const uint32_t *__restrict__ sbase, float4 *__restrict__ rows, uint32_t rows_cap)
 {
+    ts2d_grid_chain();
     if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     using L = Bwd3Layout;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -555,7 +557,7 @@ k_render3d_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_worl
 }  // namespace
 
 int ts2d_launch_render3d_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
-                                  const uint32_t *list, ImageState is, const ts2d_forward_out *out, cudaStream_t s)
+                                  const uint32_t *list, ImageState is, const ts2d_forward_out *out, bool pre_cleared, cudaStream_t s)
 {
     const int W = cam->width, H = cam->height;
     const int gx = (W + TS2D_TILE - 1) / TS2D_TILE, gy = (H + TS2D_TILE - 1) / TS2D_TILE;
@@ -575,7 +577,7 @@ int ts2d_launch_render3d_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g
         const size_t smem = CW * (size_t)Fwd3Layout<R>::BYTES;                                                                         \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_fwd_fast<R, G, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_fwd_fast<R, G, CW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));       \
-        k_render3d_fwd_fast<R, G, CW><<<owned * (8 / CW), 32 * CW, smem, s>>>(TS2D_F3_ARGS, __VA_ARGS__);                              \
+        TS2D_CUDA_TRY(ts2d_launch(k_render3d_fwd_fast<R, G, CW>, owned * (8 / CW), 32 * CW, smem, s, TS2D_F3_ARGS, __VA_ARGS__));        \
     } while (0)
 #define TS2D_F3_LAUNCH(R, G, ...)                                                                                                      \
     do {                                                                                                                               \
@@ -583,8 +585,10 @@ int ts2d_launch_render3d_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g
         else TS2D_F3_LAUNCH_CW(R, G, 1, __VA_ARGS__);                                                                                  \
     } while (0)
     if (f->rich_info) {
-        TS2D_CUDA_TRY(cudaMemsetAsync(gs.csum64, 0, sizeof(unsigned long long) * (size_t)g->P, s));
-        TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
+        if (!pre_cleared) {
+            TS2D_CUDA_TRY(cudaMemsetAsync(gs.csum64, 0, sizeof(unsigned long long) * (size_t)g->P, s));
+            TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
+        }
         if (g1) TS2D_F3_LAUNCH(true, true, o_depth, o_normal, o_csum, o_cmax, is.lastw, rows_ctr, csum64);
         else TS2D_F3_LAUNCH(true, false, o_depth, o_normal, o_csum, o_cmax, is.lastw, rows_ctr, csum64);
     } else {
@@ -617,7 +621,7 @@ int ts2d_launch_render3d_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g
         const size_t smem = CW * (size_t)Bwd3Layout::BYTES;                                                                            \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_bwd_fast<R, G, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render3d_bwd_fast<R, G, CW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));       \
-        k_render3d_bwd_fast<R, G, CW><<<owned * (8 / CW), 32 * CW, smem, s>>>(TS2D_B3_ARGS, __VA_ARGS__, sc.ei, sc.sbase, sc.rows, rows_cap); \
+        TS2D_CUDA_TRY(ts2d_launch(k_render3d_bwd_fast<R, G, CW>, owned * (8 / CW), 32 * CW, smem, s, TS2D_B3_ARGS, __VA_ARGS__, sc.ei, sc.sbase, sc.rows, rows_cap)); \
     } while (0)
 #define TS2D_B3_LAUNCH(R, G, ...)                                                                                                      \
     do {                                                                                                                               \

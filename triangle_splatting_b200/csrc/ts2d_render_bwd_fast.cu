@@ -165,6 +165,7 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                   const float *__restrict__ dL_dout_normal, const uint32_t *__restrict__ ei_of, const uint32_t *__restrict__ sbase,
                   float4 *__restrict__ rows, uint32_t rows_cap)
 {
+    ts2d_grid_chain();
     if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     using L = BwdLayout<RICH>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -394,7 +395,7 @@ int ts2d_launch_render_bwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
         const size_t smem = CW * (size_t)BwdLayout<R>::BYTES;                                                                           \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_bwd_fast<R, G, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_bwd_fast<R, G, CW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));          \
-        k_render_bwd_fast<R, G, CW><<<owned * (8 / CW), 32 * CW, smem, s>>>(TS2D_BWD_ARGS, __VA_ARGS__, sc.ei, sc.sbase, sc.rows, rows_cap); \
+        TS2D_CUDA_TRY(ts2d_launch(k_render_bwd_fast<R, G, CW>, owned * (8 / CW), 32 * CW, smem, s, TS2D_BWD_ARGS, __VA_ARGS__, sc.ei, sc.sbase, sc.rows, rows_cap)); \
     } while (0)
 #define TS2D_BWD_LAUNCH(R, G, ...)                                                                                                      \
     do {                                                                                                                                \

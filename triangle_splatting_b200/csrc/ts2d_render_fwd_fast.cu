@@ -92,6 +92,7 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                   float *__restrict__ out_normal, float *__restrict__ contrib_sum, float *__restrict__ contrib_max,
                   uint32_t *__restrict__ lastw, unsigned long long *__restrict__ bwd_rows, unsigned long long *__restrict__ csum64)
 {
+    ts2d_grid_chain();
     if (bg_ptr) bg_depth = __ldg(bg_ptr);  // model inputs: background depth computed on the device by K1
     using L = FwdLayout<RICH>;
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -290,7 +291,7 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
 }  // namespace
 
 int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, const ts2d_flags *f, GeomState gs, const uint32_t *keys,
-                                const uint32_t *list, ImageState is, const ts2d_forward_out *out, cudaStream_t s)
+                                const uint32_t *list, ImageState is, const ts2d_forward_out *out, bool pre_cleared, cudaStream_t s)
 {
     const int W = cam->width, H = cam->height;
     const int gx = (W + TS2D_TILE - 1) / TS2D_TILE, gy = (H + TS2D_TILE - 1) / TS2D_TILE;
@@ -310,7 +311,7 @@ int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
         const size_t smem = CW * (size_t)FwdLayout<R>::BYTES;                                                                          \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_fwd_fast<R, G, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
         TS2D_CUDA_TRY(cudaFuncSetAttribute(k_render_fwd_fast<R, G, CW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));         \
-        k_render_fwd_fast<R, G, CW><<<owned * (8 / CW), 32 * CW, smem, s>>>(TS2D_FWD_ARGS, __VA_ARGS__);                               \
+        TS2D_CUDA_TRY(ts2d_launch(k_render_fwd_fast<R, G, CW>, owned * (8 / CW), 32 * CW, smem, s, TS2D_FWD_ARGS, __VA_ARGS__));         \
     } while (0)
 #define TS2D_FWD_LAUNCH(R, G, ...)                                                                                                     \
     do {                                                                                                                               \
@@ -320,8 +321,10 @@ int ts2d_launch_render_fwd_fast(const ts2d_camera *cam, const ts2d_geometry *g, 
         }                                                                                                                              \
     } while (0)
     if (f->rich_info) {
-        TS2D_CUDA_TRY(cudaMemsetAsync(gs.csum64, 0, sizeof(unsigned long long) * (size_t)g->P, s));
-        TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
+        if (!pre_cleared) {  // (the one-enqueue forward clears both at the start of the frame: no memset node between the chain's kernels)
+            TS2D_CUDA_TRY(cudaMemsetAsync(gs.csum64, 0, sizeof(unsigned long long) * (size_t)g->P, s));
+            TS2D_CUDA_TRY(cudaMemsetAsync(out->contrib_max, 0, sizeof(float) * (size_t)g->P, s));
+        }
         if (g1) TS2D_FWD_LAUNCH(true, true, o_depth, o_normal, o_csum, o_cmax, is.lastw, rows_ctr, csum64);
         else TS2D_FWD_LAUNCH(true, false, o_depth, o_normal, o_csum, o_cmax, is.lastw, rows_ctr, csum64);
     } else {

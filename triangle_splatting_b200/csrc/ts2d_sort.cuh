@@ -115,6 +115,7 @@ struct RadixHistArgs {
 static __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(RadixHistArgs a)
 {
     __shared__ uint32_t s_h[4][RS_BINS];
+    ts2d_grid_chain();
     const int64_t n = rs_count(a.n_dev, a.n_cap);
     for (int d = 0; d < a.ndigits; d++) s_h[d][threadIdx.x] = 0;
     __syncthreads();
@@ -156,6 +157,7 @@ static __global__ void __launch_bounds__(RS_THREADS, 4) k_radix_pass(RadixPassAr
     __shared__ uint32_t s_w[RS_WARPS];
     __shared__ uint32_t s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    ts2d_grid_chain();
     const int64_t n = rs_count(a.n_dev, a.n_cap);
     if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
 #pragma unroll
@@ -285,6 +287,7 @@ template <class Load>
 static __global__ void __launch_bounds__(RS_THREADS) k_scan_sums(Load f, const int64_t *n_dev, int64_t n_cap, uint32_t *__restrict__ sums)
 {
     __shared__ uint32_t s_w[RS_WARPS];
+    ts2d_grid_chain();
     const int64_t n = rs_count(n_dev, n_cap);
     const int64_t base = (int64_t)blockIdx.x * SC_TILE;
     uint32_t sum = 0;
@@ -302,6 +305,7 @@ static __global__ void __launch_bounds__(RS_THREADS) k_scan_sums(Load f, const i
 static __global__ void __launch_bounds__(1024) k_scan_block_sums(uint32_t *sums, int nb, int64_t *total64, uint32_t *total32, const int64_t *n_dev, int64_t n_cap)
 {
     __shared__ uint32_t s_part[1024];
+    ts2d_grid_chain();
     const int tid = threadIdx.x;
     const int per = (nb + 1023) / 1024;
     const int b0 = tid * per, b1 = min(nb, b0 + per);
@@ -332,6 +336,7 @@ static __global__ void __launch_bounds__(RS_THREADS)
 k_scan_apply(Load f, const int64_t *n_dev, int64_t n_cap, const uint32_t *__restrict__ sums, uint32_t *__restrict__ out)
 {
     __shared__ uint32_t s_w[RS_WARPS];
+    ts2d_grid_chain();
     const int64_t n = rs_count(n_dev, n_cap);
     const int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;  // thread t owns SC_ITEMS consecutive elements
     if ((int64_t)blockIdx.x * SC_TILE >= n) return;
@@ -375,8 +380,8 @@ template <class Load, bool INCLUSIVE>
 static inline cudaError_t ts2d_scan(Load f, const int64_t *n_dev, int64_t n_cap, uint32_t *sums, uint32_t *out, int64_t *total64, bool total_at_end, cudaStream_t s)
 {
     const int nb = (int)sc_tiles(n_cap > 0 ? n_cap : 1);
-    k_scan_sums<Load><<<nb, RS_THREADS, 0, s>>>(f, n_dev, n_cap, sums);
-    k_scan_block_sums<<<1, 1024, 0, s>>>(sums, nb, total64, total_at_end ? out : nullptr, n_dev, n_cap);
-    k_scan_apply<Load, INCLUSIVE><<<nb, RS_THREADS, 0, s>>>(f, n_dev, n_cap, sums, out);
-    return cudaGetLastError();
+    cudaError_t e = ts2d_launch(k_scan_sums<Load>, nb, RS_THREADS, 0, s, f, n_dev, n_cap, sums);
+    if (e == cudaSuccess) e = ts2d_launch(k_scan_block_sums, 1, 1024, 0, s, sums, nb, total64, total_at_end ? out : (uint32_t *)nullptr, n_dev, n_cap);
+    if (e == cudaSuccess) e = ts2d_launch(k_scan_apply<Load, INCLUSIVE>, nb, RS_THREADS, 0, s, f, n_dev, n_cap, (const uint32_t *)sums, out);
+    return e;
 }
