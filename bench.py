@@ -126,15 +126,24 @@ def scene_for(config: str):
 _COPY_STREAMS = {}
 
 
-def prefetch_gt(host, dev):
+def step_start_mark(dev):
+    """Event on the current stream at the start of a step: everything the previous step queued lies in front of it."""
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
+    return ev
+
+
+def prefetch_gt(host, dev, after):
     """H2D copy of this step's ground-truth image on a side stream (inside the timed region, both arms): the image is not
-    needed before the loss, so the PCIe transfer overlaps the forward pass.  Returns a callable that makes the current
-    stream wait for the copy and hands back the device tensor."""
+    needed before the loss, so the PCIe transfer overlaps the forward pass.  Called AFTER the forward pass has been queued (the
+    device idles until the step's first kernel arrives, so nothing is put in front of that); `after` = step_start_mark() keeps the
+    copy ordered behind the previous step only, not behind this step's forward.  Returns a callable that makes the current stream
+    wait for the copy and hands back the device tensor."""
     cs = _COPY_STREAMS.get(dev)
     if cs is None:
         cs = _COPY_STREAMS[dev] = torch.cuda.Stream(device=dev)
     cur = torch.cuda.current_stream(dev)
-    cs.wait_stream(cur)  # ordered after the previous step's consumers of the buffer the allocator may hand back
+    cs.wait_event(after)  # ordered after the previous step's consumers of the buffer the allocator may hand back
     with torch.cuda.stream(cs):
         gt = host["gt"].to(dev, non_blocking=True)
     done = torch.cuda.Event()
@@ -180,12 +189,12 @@ class OursStep:
     def e2e_step(self, host):
         """camera + GT image from pinned host memory -> forward -> L1 loss -> backward -> loss to host."""
         self.vertex.grad = self.shs.grad = self.opacity.grad = None
+        mark = step_start_mark(self.dev)
         cam = {k: host[k].to(self.dev, non_blocking=True) for k in ("viewmatrix", "projmatrix", "campos", "background")}
-        gt = prefetch_gt(host, self.dev)
         kw = self.sc.settings_kwargs()
         kw.update(cam)
         out = self.forward(self.rast_cls(raster_settings=self.settings_cls(**kw)))
-        gt = gt()
+        gt = prefetch_gt(host, self.dev, mark)()
         loss = (out[0] - gt).abs().mean()
         loss.backward()
         return float(loss.item())
@@ -260,12 +269,12 @@ class ReferenceStep:
 
     def e2e_step(self, host):
         self.vertex.grad = self.shs.grad = self.opacity.grad = None
+        mark = step_start_mark(self.dev)
         cam = {k: host[k].to(self.dev, non_blocking=True) for k in ("viewmatrix", "projmatrix", "campos", "background")}
-        gt = prefetch_gt(host, self.dev)
         kw = self.sc.settings_kwargs()
         kw.update(cam)
         out = self.forward(kw)
-        gt = gt()
+        gt = prefetch_gt(host, self.dev, mark)()  # same order as our arm
         loss = (out[0] - gt).abs().mean()
         loss.backward()
         return float(loss.item())
@@ -776,19 +785,24 @@ def main():
     # R of the whole frame (each rank only knows its shard's R)
     from triangle_splatting_b200 import _C as tsC  # noqa: N811
     R_local = None
-    lib.ts2d_profile_enable(1)
     smp = ClockSampler(local_rank)
     smp.start()
     ms = timed_region(step, a.steps, a.warmup, dev, world)
     clocks = sample_clocks(step, dev, local_rank, ms, a.steps, smp.stop())
     per_step = dict(getattr(timed_region, "per_step", {}))
+    fps = a.steps / (ms / 1e3)
+    # per-stage times: a second pass of the same steps with the library's stage events switched on, OUTSIDE the timed region -- the
+    # events (two per stage) are stream operations of their own and sit between kernels that otherwise follow each other by
+    # programmatic dependent launch, so the stage table is an explanation of the frame time, not a part of it
+    lib.ts2d_profile_enable(1)
+    for _ in range(a.steps):
+        step()
+    torch.cuda.synchronize(dev)
     st_ms = (ctypes.c_float * len(_lib.STAGES))()
     st_n = (ctypes.c_int32 * len(_lib.STAGES))()
     lib.ts2d_profile_read(st_ms, st_n)
     lib.ts2d_profile_enable(0)
-    n_calls = a.steps + a.warmup
     stage_ms = {s: st_ms[i] / max(1, st_n[i]) for i, s in enumerate(_lib.STAGES)}
-    fps = a.steps / (ms / 1e3)
 
     # R (num_rendered) of this rank's shard: one forward through the raw _C API.  Every rank makes the call: a tile-sharded
     # forward is collective (barriers of the peer-memory fabric, or the NCCL assembly in the autograd wrapper)

@@ -371,7 +371,8 @@ int forward_geometry_impl(const ts2d_camera *cam, const ts2d_geometry *geom, con
 
 // One-enqueue forward: everything the render half of the frame needs zeroed (tile ranges, look-back words of the tile sort, the
 // fixed-point contrib_sum and contrib_max of the fast kernels) is cleared HERE, in front of K1, so that the kernels of the frame
-// follow each other without a memset or copy node in between (ts2d_grid_chain: each kernel's launch overlaps its predecessor's tail).
+// follow each other without a memset node in between (ts2d_grid_chain: each kernel's launch overlaps its predecessor's tail); the one
+// copy node left is R going to the host right behind the scan (the host layer must not wait for the end of the pass to see it).
 // The render half of the geometry header is part of the frame's first memset (forward_geometry_impl).
 int forward_clear_impl(const ts2d_camera *cam, const ts2d_geometry *geom, const ts2d_flags *flags, GeomState gs, BinState bs, ImageState is,
                        const ts2d_forward_out *out, cudaStream_t s)
@@ -392,7 +393,7 @@ int forward_render_impl(const ts2d_camera *cam, const ts2d_geometry *geom, const
 {
     const int n_tiles = ((cam->width + TS2D_TILE - 1) / TS2D_TILE) * ((cam->height + TS2D_TILE - 1) / TS2D_TILE);
     const int sb = ts2d_sorted_buf(n_tiles);
-    if (ctr && !pre_cleared) {  // R first: the host can size things / detect an overflow while the rest of the frame is still queued
+    if (ctr) {  // R first: the host layer waits for it (to return it and to detect an overflow) while the rest of the frame is still queued
         TS2D_CUDA_TRY(cudaMemcpyAsync(&ctr->host->num_rendered, &gs.hdr->num_rendered, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         TS2D_CUDA_TRY(cudaEventRecord(ctr->ev_r, s));
     }
@@ -409,10 +410,6 @@ int forward_render_impl(const ts2d_camera *cam, const ts2d_geometry *geom, const
     else
         TS2D_STAGE(TS2D_STAGE_RENDER_FWD, ts2d_launch_render_fwd(cam, geom, flags, gs, bs.tval[sb], is, out, s));
     if (ctr) {
-        if (pre_cleared) {  // one-enqueue forward: R leaves the device with the row count, behind the last kernel of the frame
-            TS2D_CUDA_TRY(cudaMemcpyAsync(&ctr->host->num_rendered, &gs.hdr->num_rendered, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-            TS2D_CUDA_TRY(cudaEventRecord(ctr->ev_r, s));
-        }
         TS2D_CUDA_TRY(cudaMemcpyAsync(&ctr->host->backward_rows, &gs.hdr->render.bwd_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         TS2D_CUDA_TRY(cudaEventRecord(ctr->ev_all, s));
     }
