@@ -1,5 +1,6 @@
 # One gpurun call: the GPU suite with programmatic dependent launch on (the default) -- and once more with TS2D_PDL=0 if anything fails --,
-# then the A/B of the bench stage-free frame time with the launch attribute on / off at C3 and C4-3D, the reference arm, and the ncu
+# then the A/B of the frame time with the launch attribute on the short-kernel chains (default) / off (TS2D_PDL=0) / on every launch
+# (TS2D_PDL=2) at C3 and C4-3D, the other configurations, the reference arm, and the ncu
 # launch list + one full capture of the two composite kernels at HEAD.
 # Usage: gpurun --timeout 900 -- 'bash tools/gpu_pdl.sh'
 E=gpurun_out/pdl
@@ -20,10 +21,12 @@ PY
 }
 timeout 300 python bench.py --steps 20 --warmup 5 > $E/bench_ours_n1.json 2> $E/bench_ours_n1.err
 TS2D_PDL=0 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-model-step --no-check > $E/bench_ours_n1_pdl0.json 2> $E/bench_ours_n1_pdl0.err
-show bench_ours_n1 bench_ours_n1_pdl0
+TS2D_PDL=2 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-model-step --no-check > $E/bench_ours_n1_pdl2.json 2> $E/bench_ours_n1_pdl2.err
+show bench_ours_n1 bench_ours_n1_pdl0 bench_ours_n1_pdl2
 timeout 200 python bench.py --config C4 --primitive 3D --steps 40 --warmup 10 --no-cpu-baseline --no-model-step --no-check > $E/bench_ours_C4_3D.json 2> $E/bench_ours_C4_3D.err
 TS2D_PDL=0 timeout 200 python bench.py --config C4 --primitive 3D --steps 40 --warmup 10 --no-cpu-baseline --no-model-step --no-check > $E/bench_ours_C4_3D_pdl0.json 2> $E/bench_ours_C4_3D_pdl0.err
-show bench_ours_C4_3D bench_ours_C4_3D_pdl0
+TS2D_PDL=2 timeout 200 python bench.py --config C4 --primitive 3D --steps 40 --warmup 10 --no-cpu-baseline --no-model-step --no-check > $E/bench_ours_C4_3D_pdl2.json 2> $E/bench_ours_C4_3D_pdl2.err
+show bench_ours_C4_3D bench_ours_C4_3D_pdl0 bench_ours_C4_3D_pdl2
 if [ -z "$SKIP_REF" ]; then
 timeout 300 python bench.py --impl reference --steps 20 --warmup 5 > $E/bench_reference_n1.json 2> $E/bench_reference_n1.err
 show bench_reference_n1

@@ -196,7 +196,7 @@ int ts2d_launch_order_and_scan(int32_t P, GeomState gs, int64_t *R_host, cudaStr
         a.shift = 8 * d;
         a.mask = 0xFFu;
         a.pass_uid = (uint32_t)(d + 1);
-        TS2D_CUDA_TRY(ts2d_launch(k_radix_pass, (unsigned)rs_tiles(P), RS_THREADS, 0, s, a));
+        TS2D_CUDA_TRY(ts2d_launch_chained(k_radix_pass, (unsigned)rs_tiles(P), RS_THREADS, 0, s, a));
     }
     TS2D_CUDA_TRY((ts2d_scan<LoadGatherU32, true>(LoadGatherU32{gs.ids2, gs.tiles}, nullptr, P, reinterpret_cast<uint32_t *>(gs.sstatus), gs.offs,
                                                    &gs.hdr->num_rendered, false, s)));
@@ -241,7 +241,7 @@ int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts
     const int tb = ts2d_tile_bits(n_tiles), np = ts2d_tile_sort_passes(n_tiles);
     const int64_t *n_dev = &gs.hdr->num_rendered;
     static_assert(TS2D_MASK_BITS == 8, "the digits of the tile sort are the bytes of the tile id");
-    TS2D_CUDA_TRY(ts2d_launch(k_tile_tables, 1, 1024, 0, s, n_tiles, np, is.ranges, gs.hdr->render.hist[0], gs.hdr->render.hist[1], gs.hdr->render.hist[2]));
+    TS2D_CUDA_TRY(ts2d_launch_chained(k_tile_tables, 1, 1024, 0, s, n_tiles, np, is.ranges, gs.hdr->render.hist[0], gs.hdr->render.hist[1], gs.hdr->render.hist[2]));
     for (int d = 0; d < np; d++) {
         RadixPassArgs a = {};
         a.kin = bs.tkey[d & 1];
@@ -256,7 +256,7 @@ int ts2d_launch_binning(const ts2d_camera *cam, const ts2d_geometry *g, const ts
         a.shift = TS2D_MASK_BITS + 8 * d;
         a.mask = (d == np - 1) ? ((1u << (tb - 8 * d)) - 1u) : 0xFFu;
         a.pass_uid = (uint32_t)(8 + d);
-        TS2D_CUDA_TRY(ts2d_launch(k_radix_pass, (unsigned)rs_tiles(n_launch), RS_THREADS, 0, s, a));
+        TS2D_CUDA_TRY(ts2d_launch_chained(k_radix_pass, (unsigned)rs_tiles(n_launch), RS_THREADS, 0, s, a));
     }
     return (int)cudaGetLastError();
 }

@@ -228,32 +228,37 @@ __device__ __forceinline__ float warp_sum(float v)
         if (_e != cudaSuccess) return (int)_e; \
     } while (0)
 
-// ---- programmatic dependent launch between the kernels of a frame ------------------------------------------------------------
+// ---- programmatic dependent launch inside the short-kernel chains of a frame -------------------------------------------------
 // A frame is a chain of ~22 kernels, most of them short (radix passes, scans, tables): at the small configurations the drain /
-// launch / ramp-up gap between two of them is a visible share of the frame.  Every kernel of the chain starts with
+// launch / ramp-up gap between two of them is a visible share of the frame.  Every kernel of the frame starts with
 // ts2d_grid_chain(): it lets the NEXT kernel of the stream be scheduled as soon as all of this kernel's blocks have started
 // (griddepcontrol.launch_dependents) and then waits until the PREVIOUS kernel has completed and its writes are visible
 // (griddepcontrol.wait) -- before touching global memory, so the data dependences (and the anti-dependences: buffers are
 // reused along the chain) are exactly those of plain stream order; only block scheduling and the kernel prologue overlap the
 // predecessor's tail.  Completion is transitive (a kernel cannot complete before its own wait returned), so kernel N + 2 sees
-// everything kernel N wrote.  Launched without the attribute (TS2D_PDL=0, or behind a memset / copy) both instructions are no-ops.
+// everything kernel N wrote.  Both instructions are no-ops for a kernel launched without the attribute.
+// WHICH launches carry the attribute was measured (B200; profiles/r02/README.md): inside the sort / scan / table chains it takes
+// 3.5 % off the C4 frame (0.599 -> 0.578 ms) and 14 us off the C3 frame; on the edges into and out of the long kernels (K1, K7, K8,
+// row reduction, K9) it gave nothing at C4 and cost 45 us at C3 -- so only the short kernels are launched with it
+// (ts2d_launch_chained), the long ones and whatever follows them plainly (ts2d_launch).  TS2D_PDL=0 turns it off everywhere, TS2D_PDL=2
+// puts it on every launch of the frame.
 __device__ __forceinline__ void ts2d_grid_chain()
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
-static inline bool ts2d_pdl()
+static inline int ts2d_pdl()  // 0 = off, 1 = the short-kernel chains (default), 2 = every kernel of the frame (the measured-and-rejected variant)
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("TS2D_PDL");
-        v = e ? (atoi(e) != 0) : 1;
+        v = e ? atoi(e) : 1;
+        if (v < 0 || v > 2) v = 1;
     }
-    return v != 0;
+    return v;
 }
-// launch of a chain kernel: <<<grid, block, smem, s>>> plus the programmatic-stream-serialization attribute
 template <typename... KArgs, typename... Args>
-static inline cudaError_t ts2d_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
+static inline cudaError_t ts2d_launch_impl(bool chained, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -264,8 +269,20 @@ static inline cudaError_t ts2d_launch(void (*kernel)(KArgs...), dim3 grid, dim3 
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = ts2d_pdl() ? 1u : 0u;
+    cfg.numAttrs = ((chained && ts2d_pdl() >= 1) || ts2d_pdl() >= 2) ? 1u : 0u;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// plain launch: <<<grid, block, smem, s>>>
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ts2d_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
+{
+    return ts2d_launch_impl(false, kernel, grid, block, smem, s, static_cast<Args &&>(args)...);
+}
+// launch of a short kernel behind another kernel of the frame: may be scheduled while its predecessor drains
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ts2d_launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
+{
+    return ts2d_launch_impl(true, kernel, grid, block, smem, s, static_cast<Args &&>(args)...);
 }
 
 // Host-side helpers shared by the .cu translation units

@@ -228,7 +228,7 @@ __device__ __forceinline__ uint32_t subtile_mask(const float4 r0, const float4 r
 // Returns whether the pair contributes according to the fast value; `uncertain` says the reference's decision
 // cannot be inferred from it (then the caller uses eval_exact).
 struct FastPair {
-    float a1, a2, a3, ecc, power, G, og, alpha;
+    float a1, a2, a3, ecc, pw, power, G, og, alpha;  // pw = ecc^(2 gamma), power = -pw / 2
     float pv1x, pv1y, pv2x, pv2y, pv3x, pv3y;
 };
 
@@ -250,8 +250,11 @@ __device__ __forceinline__ bool eval_fast(const float4 e1, const float4 e2, floa
         pw = f.ecc * f.ecc;
     else
         pw = exp2f(gk.two_gamma * log2f(fmaxf(f.ecc, 1.0e-30f)));  // full-precision log2f/exp2f: the error is multiplied by 2 gamma |power|
-    f.power = -0.5f * pw;
-    f.G = ex2_approx(f.power * TS2D_LOG2E);
+    f.pw = pw;
+    f.power = -0.5f * pw;  // (dead code where the caller works from pw)
+    // exp(power) = 2^(pw * (-log2(e) / 2)): the same bits as 2^(power * log2(e)) -- the factor 1/2 is a power of two, it commutes with
+    // the rounding of the product -- in one multiply instead of two
+    f.G = ex2_approx(pw * (-0.5f * TS2D_LOG2E));
     f.og = e2.w * f.G;
     f.alpha = fminf(0.99f, f.og);
     const float d = fmaf(f.alpha, 255.0f, -1.0f);  // alpha * 255 - 1

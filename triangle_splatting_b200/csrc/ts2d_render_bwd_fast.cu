@@ -302,7 +302,7 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                     PairEval e;
                     hit = eval_exact(e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, area2, e2.w, gk.two_gamma, pxf, pyf, e);
                     f.a1 = e.a1; f.a2 = e.a2; f.a3 = e.a3; f.ecc = e.ecc;
-                    if (hit) { f.power = e.power; f.G = e.G; f.og = __fmul_rn(e2.w, e.G); f.alpha = e.alpha; }
+                    if (hit) { f.power = e.power; f.pw = -2.0f * e.power; f.G = e.G; f.og = __fmul_rn(e2.w, e.G); f.alpha = e.alpha; }
                 }
                 if (hit) {
                     const float4 col = lds128(ea + 32);
@@ -331,7 +331,10 @@ k_render_bwd_fast(int W_, int H, int C, int gx, int shard_rank, int shard_world,
                     const float dL_dalpha = dL_dcontrib * T;
                     w_op = dL_dalpha * f.G;  // unconditional (backward.cu:490)
                     const float dL_dpower = (f.og < 0.99f) ? dL_dalpha * f.alpha : 0.0f;
-                    const float D = -3.0f * dL_dpower * gk.two_gamma * f.power * rcp_approx(f.ecc + TS2D_EPS);
+                    // -3 dL_dpower * 2 gamma * power / (ecc + eps).  gamma == 1: -3 * 2 * (-pw / 2) = 3 pw with the factors of two exact, so
+                    // (3 dL_dpower) pw carries the same roundings as the general expression in two multiplies instead of four
+                    const float rec = rcp_approx(f.ecc + TS2D_EPS);
+                    const float D = gk.is_one ? ((3.0f * dL_dpower) * f.pw) * rec : -3.0f * dL_dpower * gk.two_gamma * f.power * rec;
                     // sub-gradient of min: first arg-min in the order a1, a2, a3 (backward.cu:449-461).  a3 = 1 - a1 - a2, so D to a3 is -D
                     // to both a1 and a2: the panel gets the signed value, the choice travels as two warp ballots
                     not2 = f.a1 <= f.a2 && f.a1 <= f.a3;           // arg-min a1

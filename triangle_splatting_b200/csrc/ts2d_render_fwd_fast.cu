@@ -191,7 +191,7 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
         // software-pipelined by one entry: the vertex words of entry j + 1 are requested before the panel store of entry j (a shared
         // load cannot be moved above a store that may alias it, so at the top of the iteration it would sit behind that store with
         // its whole latency in front of the pair evaluation; one entry past the staged ones is read and never used)
-        uint32_t ea = sb, prow = sb + L::PANEL;
+        uint32_t ea = sb, prow = sb + L::PANEL + lane * 4;  // this lane's word of the entry's panel row
         int visited = count;
         float4 e1 = lds128(ea), e2 = lds128(ea + 16);
         for (int j = 0; j < count; j++, ea += L::EB, prow += FW_PROW * 4) {
@@ -215,7 +215,8 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                     contrib = f.alpha * T;
                     const float om = 1.0f - f.alpha;
                     // |T_new - T_ref_new| <= |T - T_ref| * om + T * |d alpha| + rounding of the two product chains
-                    Terr = fmaf(Terr, om, contrib * (unc ? 0.0f : fmaf(gk.terr_c1, fabsf(f.power), gk.terr_c0)));
+                    // (terr_c1 |power| written as (terr_c1 / 2) pw: the same product, so the same rounded sum, without forming power)
+                    Terr = fmaf(Terr, om, contrib * (unc ? 0.0f : fmaf(0.5f * gk.terr_c1, f.pw, gk.terr_c0)));
                     T *= om;
                     Terr = fmaf(T, 1.3e-7f, Terr);
                     evt = (T - 0.0001f) <= Terr;  // saturated (T <= 1e-4) or within the error band of the cut
@@ -229,7 +230,7 @@ k_render_fwd_fast(int W, int H, int C, int gx, int shard_rank, int shard_world, 
                 }
             }
             const float4 n1 = lds128(ea + L::EB), n2 = lds128(ea + L::EB + 16);
-            if constexpr (RICH) sts32f(prow + lane * 4, contrib);
+            if constexpr (RICH) sts32f(prow, contrib);
             e1 = n1;
             e2 = n2;
             if (__any_sync(0xffffffffu, evt)) {  // at most a few times per pixel: everything about saturation lives here

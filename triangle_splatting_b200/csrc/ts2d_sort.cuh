@@ -380,8 +380,8 @@ template <class Load, bool INCLUSIVE>
 static inline cudaError_t ts2d_scan(Load f, const int64_t *n_dev, int64_t n_cap, uint32_t *sums, uint32_t *out, int64_t *total64, bool total_at_end, cudaStream_t s)
 {
     const int nb = (int)sc_tiles(n_cap > 0 ? n_cap : 1);
-    cudaError_t e = ts2d_launch(k_scan_sums<Load>, nb, RS_THREADS, 0, s, f, n_dev, n_cap, sums);
-    if (e == cudaSuccess) e = ts2d_launch(k_scan_block_sums, 1, 1024, 0, s, sums, nb, total64, total_at_end ? out : (uint32_t *)nullptr, n_dev, n_cap);
-    if (e == cudaSuccess) e = ts2d_launch(k_scan_apply<Load, INCLUSIVE>, nb, RS_THREADS, 0, s, f, n_dev, n_cap, (const uint32_t *)sums, out);
+    cudaError_t e = ts2d_launch_chained(k_scan_sums<Load>, nb, RS_THREADS, 0, s, f, n_dev, n_cap, sums);
+    if (e == cudaSuccess) e = ts2d_launch_chained(k_scan_block_sums, 1, 1024, 0, s, sums, nb, total64, total_at_end ? out : (uint32_t *)nullptr, n_dev, n_cap);
+    if (e == cudaSuccess) e = ts2d_launch_chained(k_scan_apply<Load, INCLUSIVE>, nb, RS_THREADS, 0, s, f, n_dev, n_cap, (const uint32_t *)sums, out);
     return e;
 }
