@@ -65,6 +65,10 @@ def fabric(device) -> Optional["Fabric"]:
     mode = os.environ.get("TS2D_FABRIC", "auto")
     if mode == "0":
         return None
+    from . import _lib
+
+    if _STATE["world"] > _lib.MAX_RANKS:  # the exchange kernels address at most TS2D_MAX_RANKS replicas: larger groups take the NCCL path
+        return None
     f = _STATE["fabric"]
     if f is None:
         try:
